@@ -1,0 +1,216 @@
+/* g19.h -- C ABI of lib2019global_b200 (the B200 radiance-loop engine).
+ *
+ * This is the drop-in boundary for the ONE hot path of preon7/2019global:
+ * RayTracer::run and everything it calls (reference include/raytracer.h:23-87).
+ * The reference has no FFI of its own; its seam is the public surface of the
+ * header-only classes RayTracer / Octree / Entity / Material / Camera / Image.
+ * Every entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain C, no C++ types, no exceptions across the boundary.
+ * Every function returns an int status (G19_OK == 0) unless stated otherwise.
+ * Caller owns all input buffers; the library copies what it keeps.
+ * One g19_ctx serves one render at a time; g19_cancel / g19_progress are the
+ * only calls that may be made concurrently with a running g19_render*.
+ * There is NO CPU fallback: without a CUDA device g19_create fails loudly.
+ */
+#ifndef G19_H
+#define G19_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G19_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+    G19_OK = 0,
+    G19_ERR_INVALID = 1,   /* bad argument                                   */
+    G19_ERR_NO_DEVICE = 2, /* no usable CUDA device (there is no CPU path)   */
+    G19_ERR_CUDA = 3,      /* CUDA runtime error, see g19_last_error         */
+    G19_ERR_NO_SCENE = 4,  /* render before g19_upload_scene                 */
+    G19_ERR_CANCELLED = 5, /* g19_cancel observed; output is partial         */
+    G19_ERR_LIMIT = 6,     /* scene exceeds a documented device-side limit   */
+    G19_ERR_REJECTED = 7   /* entity rejected by the root-overlap test       */
+};
+
+/* ---- entities (reference include/entities.h) ---------------------------- */
+/* One value per concrete reference class. A composite is ONE entity id.     */
+enum g19_entity_kind {
+    G19_IMP_SPHERE = 0,    /* ImpSphere(pos, radius, color)      entities.h:43-133  */
+    G19_IMP_TRIANGLE = 1,  /* ImpTriangle(p1,p2,p3)              entities.h:136-306 */
+    G19_EXP_RECTANGLE = 2, /* ExpRectangle(p1,p2,p3)             entities.h:308-377 */
+    G19_EXP_BOX = 3,       /* ExpBox(min,max)                    entities.h:379-454 */
+    G19_EXP_SPHERE = 4,    /* ExpSphere(pos, radius, color)      entities.h:457-575 */
+    G19_EXP_QUAD = 5,      /* ExpQuad(pos,width,length,alpha,c)  entities.h:579-647 */
+    G19_EXP_CUBE = 6,      /* ExpCube(pos,w,l,h,color)           entities.h:650-818 */
+    G19_EXP_CONE = 7       /* ExpCone(pos,dir,height,radius,c)   entities.h:821-967 */
+};
+
+/* Bounce model used by G19_MODE_PATH only (the reference has no bounces;
+ * reference Material, material.h:12-107, only feeds G19_MODE_REF shading). */
+enum g19_bsdf {
+    G19_BSDF_DIFFUSE = 0,
+    G19_BSDF_MIRROR = 1,
+    G19_BSDF_GLASS = 2,
+    G19_BSDF_EMITTER = 3
+};
+
+/* Constructor arguments of one reference entity, in the reference's own types
+ * (double points, float scalars -- the float/double split is part of the
+ * bit-exact contract).
+ *   kind            p[0..2]   p[3..5]   p[6..8]   f[0]    f[1]    f[2]
+ *   IMP_SPHERE      pos                           radius
+ *   IMP_TRIANGLE    p1        p2        p3
+ *   EXP_RECTANGLE   p1        p2        p3
+ *   EXP_BOX         min       max
+ *   EXP_SPHERE      pos                           radius
+ *   EXP_QUAD        pos                           width   length  alpha
+ *   EXP_CUBE        pos                           width   length  height
+ *   EXP_CONE        pos       dir                 height  radius
+ * color is Material(color) (material.h:13-16). For the kinds whose reference
+ * constructor takes no colour (triangle, rectangle, box) it is what a caller
+ * assigns to the public Entity::material field afterwards; the reference
+ * default is (1,0,0) (entities.h:21). */
+typedef struct g19_entity_desc {
+    int32_t kind;        /* enum g19_entity_kind */
+    int32_t bsdf;        /* enum g19_bsdf (PATH mode) */
+    double p[9];
+    float f[4];
+    double color[3];
+    float emission[3];   /* radiance of a G19_BSDF_EMITTER (PATH mode) */
+    float ior;           /* index of refraction of G19_BSDF_GLASS (PATH mode) */
+} g19_entity_desc;
+
+/* ---- scene = Octree + the entities pushed into it (octree.h:12-68) ------ */
+typedef struct g19_scene g19_scene;
+
+/* Octree(min,max)                                            octree.h:14    */
+int g19_scene_create(const double min[3], const double max[3], g19_scene** out);
+void g19_scene_destroy(g19_scene* scene);
+/* new <Entity>(...) followed by Octree::push_back            octree.h:20-30.
+ * *out_index (nullable) receives the entity id = construction order. An
+ * entity whose bounding box misses the root is still numbered but silently
+ * absent from the tree, exactly like the reference; the call then returns
+ * G19_ERR_REJECTED (informational). */
+int g19_scene_add_entity(g19_scene* scene, const g19_entity_desc* desc, int32_t* out_index);
+int g19_scene_entity_count(const g19_scene* scene);
+int g19_scene_get_entity(const g19_scene* scene, int32_t index, g19_entity_desc* out);
+/* Entity::boundingBox() as the reference computes it (incl. its quirks).    */
+int g19_scene_entity_bbox(const g19_scene* scene, int32_t index, double out_min_max[6]);
+/* The triangles a composite owns (public `triangles` members), 9 doubles
+ * each. Returns the count; writes at most max_tris. IMP_SPHERE returns 0.   */
+int g19_scene_entity_triangles(const g19_scene* scene, int32_t index, double* out, int max_tris);
+
+/* Procedural scenes of BASELINE.json `configs`.    */
+enum g19_builtin_scene {
+    G19_SCENE_DEFAULT = 0,     /* main.cpp:24-57 literal (config 1)             */
+    G19_SCENE_CORNELL = 1,     /* diffuse Cornell box + 2 spheres + area light  */
+    G19_SCENE_CORNELL_GLASS = 2, /* same, one mirror + one glass sphere         */
+    G19_SCENE_HEIGHTFIELD = 3  /* n x n heightfield, 2 n^2 ... triangles        */
+};
+typedef struct g19_camera {
+    double pos[3];     /* Camera::pos      camera.h:12 */
+    double look_at[3]; /* Camera ctor arg  camera.h:8  */
+    double focal;      /* Camera::focalDist camera.h:16 */
+} g19_camera;
+/* Builds a named scene; `n` is the heightfield grid size (ignored otherwise).
+ * w,h select the camera pitch that centres the frame (SURVEY hard part 4).
+ * out_camera / out_light (nullable) receive the matching camera and light.  */
+int g19_scene_builtin(int which, int n, int w, int h, g19_scene** out,
+                      g19_camera* out_camera, double out_light[3]);
+
+/* ---- engine -------------------------------------------------------------- */
+typedef struct g19_ctx g19_ctx;
+
+enum g19_mode {
+    G19_MODE_REF = 0, /* bug-for-bug reference: 1 primary ray per pixel through
+                         the pixel corner, reference octree candidate semantics,
+                         LAST intersecting candidate wins, Blinn-Phong + checker,
+                         truncating RGB888 store (raytracer.h:23-87).          */
+    G19_MODE_PATH = 1 /* path tracing: spp, pixel jitter, bounces, area light,
+                         mirror/glass, nearest hit -- NOT in the reference;
+                         defined by this repo's oracle (oracle/path_oracle.c). */
+};
+
+typedef struct g19_params {
+    int32_t width, height; /* RayTracer::run(w,h)  raytracer.h:23 */
+    int32_t mode;          /* enum g19_mode */
+    int32_t spp;           /* PATH: samples per pixel (REF: ignored, 1) */
+    int32_t max_depth;     /* PATH: max ray segments per camera path    */
+    uint32_t seed;         /* PATH: RNG key; counter = (pixel, sample, bounce) */
+    /* Image-tile sharding: 32x32 tiles, tile t belongs to rank
+     * t % world. rank=0, world=1 renders everything. Pixels of other ranks
+     * are left untouched in the output buffers.                             */
+    int32_t rank, world;
+    int32_t spp_per_pass;  /* PATH: samples per wavefront pass (0 = auto)   */
+    int32_t profile;       /* 1: time every kernel class with CUDA events   */
+} g19_params;
+
+typedef struct g19_stats {
+    uint64_t samples;         /* camera paths started                         */
+    uint64_t extend_segments; /* rays through traverse+intersect              */
+    uint64_t shadow_segments; /* any-hit rays                                 */
+    uint64_t kernel_launches; /* kernels of this library launched by the call */
+    double render_ms;         /* device time of the whole call (CUDA events)  */
+    /* per kernel class, only when params.profile: [raygen+extend, shade,
+     * shadow, accumulate, ref_visibility, ref_shade, other]                 */
+    double class_ms[8];
+    uint64_t class_launches[8];
+    uint64_t node_tests, prim_tests; /* REF mode, only when profile           */
+} g19_stats;
+
+enum { G19_K_EXTEND = 0, G19_K_SHADE = 1, G19_K_SHADOW = 2, G19_K_ACCUM = 3,
+       G19_K_REF_VIS = 4, G19_K_REF_SHADE = 5, G19_K_OTHER = 6 };
+
+/* RayTracer(camera, light) + device selection. devices==NULL,n==0 -> the
+ * current CUDA device. Fails with G19_ERR_NO_DEVICE when CUDA is unusable.  */
+int g19_create(const int* devices, int n_devices, g19_ctx** out);
+void g19_destroy(g19_ctx* ctx);
+const char* g19_last_error(const g19_ctx* ctx); /* ctx may be NULL: create errors */
+
+/* RayTracer::setScene(const Octree*)                       raytracer.h:21.
+ * Builds the reference octree (octree.h:75-129) and the engine's own linear
+ * octree on the host, flattens both and copies them to HBM.                 */
+int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene);
+
+/* RayTracer::run(w,h)                                      raytracer.h:23-87.
+ * Blocking; HOST pointers, each nullable:
+ *   rgb888_out   w*h*3 bytes, row-major, row 0 = top (Image / QImage RGB888,
+ *                image.h:9-16)
+ *   hit_id_out   w*h int32: REF mode primary-hit entity id, -1 = miss
+ *   radiance_out w*h*3 float: linear radiance (REF: the shaded colour)       */
+int g19_render(g19_ctx* ctx, const g19_camera* camera, const double light[3],
+               const g19_params* params, uint8_t* rgb888_out, int32_t* hit_id_out,
+               float* radiance_out);
+/* Same with DEVICE pointers (HBM-resident outputs) on `stream` (a
+ * cudaStream_t, NULL = legacy default). Asynchronous w.r.t. the host unless
+ * params->profile; stats (nullable) are complete after the stream is synced. */
+int g19_render_device(g19_ctx* ctx, const g19_camera* camera, const double light[3],
+                      const g19_params* params, uint8_t* d_rgb888, int32_t* d_hit_id,
+                      float* d_radiance, void* stream);
+int g19_get_stats(g19_ctx* ctx, g19_stats* out);
+
+/* RayTracer::stop()/running()                              raytracer.h:89-91 */
+int g19_cancel(g19_ctx* ctx);
+/* Fraction of the current render already enqueued+finished, 0..1.            */
+int g19_progress(g19_ctx* ctx, double* out_fraction);
+
+/* Unit-level probes (used by the parity tests; they run the SAME device
+ * functions as the render kernels, one thread per ray).
+ * Entity::intersect(ray, point, normal)                    entities.h:26    */
+int g19_probe_intersect(g19_ctx* ctx, int32_t entity, int n, const double* origins,
+                        const double* dirs, int32_t* out_hit, double* out_points,
+                        double* out_normals);
+/* Octree::intersect(ray) candidate list                    octree.h:46-68.
+ * Writes up to max_out entity ids for ONE ray, returns the count in *out_n. */
+int g19_probe_candidates(g19_ctx* ctx, const double origin[3], const double dir[3],
+                         int32_t* out_ids, int max_out, int* out_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G19_H */
