@@ -1,0 +1,553 @@
+// engine.cu -- g19_ctx: device state, scene flattening/upload, render drivers.
+//
+// Implements the engine half of include/g19.h. The reference's RayTracer
+// (include/raytracer.h:15-101) owns a Camera, a light and a non-owning Octree*
+// and renders with run(w,h); here the ctx owns the flattened scene in HBM and
+// g19_render* is run(). There is no CPU path: every entry point that computes
+// launches CUDA kernels, and g19_create fails when no device is usable.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "g19.h"
+#include "kernels.h"
+#include "path.h"
+#include "scene.h"
+
+using namespace g19;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+} // namespace
+
+struct g19_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr; // used by the host-pointer entry points
+    std::string err;
+    std::atomic<int> cancel{0};
+    std::atomic<int> progress_milli{0};
+    int sm_count = 148;
+    bool has_scene = false;
+
+    // REF view
+    DevBuf ref_nodes, ref_ents, ref_entities, ref_tris;
+    RefSceneD ref{};
+    int ref_depth = 0;
+    // PATH view
+    PathSceneBuffers path;
+
+    // per-render work buffers (local-pixel indexed)
+    DevBuf ids_l, points_l, normals_l, rgb_l, colour_l, counters;
+    // frame buffers for the host-pointer entry point
+    DevBuf rgb_f, ids_f, rad_f;
+    PathWork work;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t cls0 = nullptr, cls1 = nullptr;
+    g19_stats stats{};
+    bool stats_pending = false;
+};
+
+namespace {
+
+#define G19_CUDA(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            return G19_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+template <typename T> cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+    size_t bytes = v.size() * sizeof(T);
+    cudaError_t e = b.ensure(bytes ? bytes : sizeof(T));
+    if (e != cudaSuccess || !bytes) return e;
+    return cudaMemcpyAsync(b.p, v.data(), bytes, cudaMemcpyHostToDevice, s);
+}
+
+void copy3(double* dst, V3 v) {
+    dst[0] = v.x;
+    dst[1] = v.y;
+    dst[2] = v.z;
+}
+
+// ---- flatten the reference octree ---------------
+int flatten_ref(g19_ctx* ctx, const g19_scene& s) {
+    std::vector<RefNodeD> nodes(s.nodes.size());
+    std::vector<int32_t> lists;
+    for (size_t i = 0; i < s.nodes.size(); ++i) {
+        const HostNode& h = s.nodes[i];
+        RefNodeD& d = nodes[i];
+        copy3(d.mn, h.mn);
+        copy3(d.mx, h.mx);
+        d.first_child = h.first_child;
+        d.ent_count = int32_t(h.ents.size());
+        d.ent_offset = 0;
+        d.pad = 0;
+        if (h.first_child < 0) { // only leaf lists are ever returned (octree.h:133-135)
+            d.ent_offset = int32_t(lists.size());
+            lists.insert(lists.end(), h.ents.begin(), h.ents.end());
+        }
+    }
+    std::vector<RefEntityD> ents(s.ents.size());
+    std::vector<RefTriD> tris;
+    size_t ntri = 0;
+    for (auto& e : s.ents) ntri += e.tris.size();
+    tris.reserve(ntri);
+    for (size_t i = 0; i < s.ents.size(); ++i) {
+        const HostEntity& h = s.ents[i];
+        RefEntityD& d = ents[i];
+        std::memset(&d, 0, sizeof d);
+        d.kind = h.kind;
+        d.combine = h.combine;
+        d.tri_offset = int32_t(tris.size());
+        d.tri_count = int32_t(h.tris.size());
+        d.first_tested = h.first_tested;
+        d.radius = h.radius;
+        std::memcpy(d.f, h.desc.f, sizeof d.f);
+        copy3(d.pos, h.pos);
+        d.color[0] = h.desc.color[0];
+        d.color[1] = h.desc.color[1];
+        d.color[2] = h.desc.color[2];
+        copy3(d.aux0, h.aux0);
+        copy3(d.aux1, h.aux1);
+        for (const HostTri& t : h.tris) {
+            RefTriD r;
+            std::memset(&r, 0, sizeof r);
+            copy3(r.p1, t.p1);
+            copy3(r.p2, t.p2);
+            copy3(r.p3, t.p3);
+            copy3(r.pos, t.pos);
+            copy3(r.normal, t.normal);
+            r.e1[0] = float(t.edge1.x); r.e1[1] = float(t.edge1.y); r.e1[2] = float(t.edge1.z);
+            r.e2[0] = float(t.edge2.x); r.e2[1] = float(t.edge2.y); r.e2[2] = float(t.edge2.z);
+            tris.push_back(r);
+        }
+    }
+    ctx->ref_depth = max_depth(s);
+    if (ctx->ref_depth >= 39) {
+        ctx->err = "reference octree deeper than the device traversal stack (39 levels)";
+        return G19_ERR_LIMIT;
+    }
+    G19_CUDA(ctx, upload(ctx->ref_nodes, nodes, ctx->stream));
+    G19_CUDA(ctx, upload(ctx->ref_ents, lists, ctx->stream));
+    G19_CUDA(ctx, upload(ctx->ref_entities, ents, ctx->stream));
+    G19_CUDA(ctx, upload(ctx->ref_tris, tris, ctx->stream));
+    G19_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host vectors die at scope exit
+    ctx->ref.nodes = ctx->ref_nodes.as<RefNodeD>();
+    ctx->ref.ents = ctx->ref_ents.as<int32_t>();
+    ctx->ref.entities = ctx->ref_entities.as<RefEntityD>();
+    ctx->ref.tris = ctx->ref_tris.as<RefTriD>();
+    ctx->ref.n_nodes = int32_t(nodes.size());
+    ctx->ref.n_entities = int32_t(ents.size());
+    return G19_OK;
+}
+
+// Camera basis, raytracer.h:26-30 and camera.h:8-10, in the reference's order.
+V3 add(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+V3 mul(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+double dotv(V3 a, V3 b) {
+    double tx = a.x * b.x, ty = a.y * b.y, tz = a.z * b.z;
+    return tx + ty + tz;
+}
+V3 crossv(V3 a, V3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+V3 unitv(V3 v) { return mul(v, 1.0 / std::sqrt(dotv(v, v))); }
+
+RefCamera make_camera(const g19_camera& c, const double light[3], int w) {
+    V3 pos = {c.pos[0], c.pos[1], c.pos[2]};
+    V3 look = {c.look_at[0], c.look_at[1], c.look_at[2]};
+    V3 up = {0, 0, 1.0};
+    V3 forward = unitv(sub(look, pos));
+    V3 left = unitv(crossv(up, forward));
+    V3 fwd = {c.focal * forward.x, c.focal * forward.y, c.focal * forward.z}; // scalar * vec
+    V3 t = add(pos, fwd);
+    t = add(t, mul(mul(mul(left, double(w)), 0.5), 0.0002));
+    t = add(t, mul(mul(mul(up, double(w)), 0.5), 0.0002)); // the WIDTH, also vertically (raytracer.h:30)
+    V3 top_left = sub(t, pos);
+    RefCamera r;
+    copy3(r.pos, pos);
+    copy3(r.up, up);
+    copy3(r.left, left);
+    copy3(r.top_left, top_left);
+    r.light[0] = light ? light[0] : 0;
+    r.light[1] = light ? light[1] : 0;
+    r.light[2] = light ? light[2] : 0;
+    return r;
+}
+
+int check_params(g19_ctx* ctx, const g19_camera* cam, const g19_params* p) {
+    if (!ctx) return G19_ERR_INVALID;
+    if (!cam || !p || p->width < 0 || p->height < 0 || p->world < 1 || p->rank < 0 || p->rank >= p->world ||
+        (p->mode != G19_MODE_REF && p->mode != G19_MODE_PATH)) {
+        ctx->err = "invalid camera/params";
+        return G19_ERR_INVALID;
+    }
+    if ((long long)p->width * p->height > (1ll << 30)) {
+        ctx->err = "image larger than 2^30 pixels";
+        return G19_ERR_LIMIT;
+    }
+    if (!ctx->has_scene) {
+        ctx->err = "g19_render before g19_upload_scene";
+        return G19_ERR_NO_SCENE;
+    }
+    return G19_OK;
+}
+
+struct ClassTimer { // CUDA-event timing of one kernel class (params.profile)
+    g19_ctx* ctx;
+    cudaStream_t s;
+    bool on;
+    void begin() {
+        if (on) cudaEventRecord(ctx->cls0, s);
+    }
+    void end(int cls, int launches) {
+        ctx->stats.class_launches[cls] += launches;
+        ctx->stats.kernel_launches += launches;
+        if (!on) return;
+        cudaEventRecord(ctx->cls1, s);
+        cudaEventSynchronize(ctx->cls1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->cls0, ctx->cls1);
+        ctx->stats.class_ms[cls] += ms;
+    }
+};
+
+int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p, const TileMap& map,
+               uint8_t* d_rgb, int32_t* d_ids, float* d_rad, cudaStream_t s) {
+    RefCamera rc = make_camera(*cam, light, p->width);
+    size_t n = size_t(map.n_local_pix);
+    G19_CUDA(ctx, ctx->ids_l.ensure(n * sizeof(int32_t)));
+    G19_CUDA(ctx, ctx->points_l.ensure(n * 3 * sizeof(double)));
+    G19_CUDA(ctx, ctx->normals_l.ensure(n * 3 * sizeof(double)));
+    G19_CUDA(ctx, ctx->rgb_l.ensure(n * 3));
+    G19_CUDA(ctx, ctx->colour_l.ensure(n * 3 * sizeof(float)));
+    G19_CUDA(ctx, ctx->counters.ensure(2 * sizeof(unsigned long long)));
+    unsigned long long* counters = nullptr;
+    if (p->profile) {
+        counters = ctx->counters.as<unsigned long long>();
+        G19_CUDA(ctx, cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s));
+    }
+    ClassTimer t{ctx, s, p->profile != 0};
+    t.begin();
+    launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                          ctx->normals_l.as<double>(), counters, s);
+    t.end(G19_K_REF_VIS, 1);
+    t.begin();
+    launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                     ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s);
+    t.end(G19_K_REF_SHADE, 1);
+    t.begin();
+    launch_untile(map, d_rgb ? ctx->rgb_l.as<uint8_t>() : nullptr, d_ids ? ctx->ids_l.as<int32_t>() : nullptr,
+                  d_rad ? ctx->colour_l.as<float>() : nullptr, d_rgb, d_ids, d_rad, s);
+    t.end(G19_K_OTHER, 1);
+    G19_CUDA(ctx, cudaGetLastError());
+    ctx->stats.samples = 0;
+    if (p->profile) {
+        unsigned long long h[2] = {0, 0};
+        G19_CUDA(ctx, cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, s));
+        G19_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->stats.node_tests = h[0];
+        ctx->stats.prim_tests = h[1];
+    }
+    // in-frame pixels owned by this rank
+    uint64_t owned = 0;
+    for (int lt = 0; lt < map.n_local_tiles; ++lt) {
+        int tile = lt * map.world + map.rank;
+        int ty = tile / map.tiles_x, tx = tile % map.tiles_x;
+        int wx = std::min(kTile, map.w - tx * kTile), wy = std::min(kTile, map.h - ty * kTile);
+        owned += uint64_t(wx) * uint64_t(wy);
+    }
+    ctx->stats.samples = owned;
+    ctx->stats.extend_segments = owned;
+    return G19_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int g19_create(const int* devices, int n_devices, g19_ctx** out) {
+    if (!out) return G19_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                         "); lib2019global_b200 has no CPU path";
+        return G19_ERR_NO_DEVICE;
+    }
+    int dev = 0;
+    if (devices && n_devices > 0) dev = devices[0];
+    else cudaGetDevice(&dev);
+    if (dev < 0 || dev >= count) {
+        g_create_error = "device index out of range";
+        return G19_ERR_INVALID;
+    }
+    if (n_devices > 1) {
+        g_create_error = "one g19_ctx drives one device; run one process (rank) per GPU and shard tiles with "
+                         "g19_params.rank/world";
+        return G19_ERR_INVALID;
+    }
+    e = cudaSetDevice(dev);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return G19_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return G19_ERR_NO_DEVICE;
+    }
+    if (prop.major != 10) {
+        g_create_error = "lib2019global_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                         std::to_string(prop.minor);
+        return G19_ERR_NO_DEVICE;
+    }
+    g19_ctx* ctx = new (std::nothrow) g19_ctx();
+    if (!ctx) return G19_ERR_INVALID;
+    ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->cls0) != cudaSuccess || cudaEventCreate(&ctx->cls1) != cudaSuccess) {
+        g_create_error = "stream/event creation failed";
+        delete ctx;
+        return G19_ERR_CUDA;
+    }
+    *out = ctx;
+    return G19_OK;
+}
+
+void g19_destroy(g19_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&ctx->ref_nodes, &ctx->ref_ents, &ctx->ref_entities, &ctx->ref_tris, &ctx->ids_l, &ctx->points_l,
+                      &ctx->normals_l, &ctx->rgb_l, &ctx->colour_l, &ctx->counters, &ctx->rgb_f, &ctx->ids_f,
+                      &ctx->rad_f})
+        b->release();
+    path_release(ctx->path, ctx->work);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->cls0) cudaEventDestroy(ctx->cls0);
+    if (ctx->cls1) cudaEventDestroy(ctx->cls1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* g19_last_error(const g19_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene) {
+    if (!ctx || !scene) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->has_scene = false;
+    int rc = flatten_ref(ctx, *scene);
+    if (rc != G19_OK) return rc;
+    std::string perr;
+    rc = path_upload(ctx->path, *scene, ctx->stream, perr);
+    if (rc != G19_OK) {
+        ctx->err = perr;
+        return rc;
+    }
+    ctx->has_scene = true;
+    return G19_OK;
+}
+
+int g19_render_device(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p,
+                      uint8_t* d_rgb, int32_t* d_ids, float* d_rad, void* stream) {
+    int rc = check_params(ctx, cam, p);
+    if (rc != G19_OK) return rc;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ctx->cancel.store(0);
+    ctx->progress_milli.store(0);
+    ctx->stats = g19_stats{};
+    TileMap map = make_tile_map(p->width, p->height, p->rank, p->world);
+    G19_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    if (p->mode == G19_MODE_REF) {
+        rc = render_ref(ctx, cam, light, p, map, d_rgb, d_ids, d_rad, s);
+    } else {
+        RefCamera rc64 = make_camera(*cam, light, p->width);
+        PathRenderArgs a;
+        a.cam = rc64;
+        a.params = *p;
+        a.map = map;
+        a.d_rgb = d_rgb;
+        a.d_rad = d_rad;
+        a.d_ids = d_ids;
+        a.stream = s;
+        a.sm_count = ctx->sm_count;
+        a.cancel = &ctx->cancel;
+        a.progress_milli = &ctx->progress_milli;
+        a.cls0 = ctx->cls0;
+        a.cls1 = ctx->cls1;
+        std::string perr;
+        rc = path_render(ctx->path, ctx->work, a, ctx->stats, perr);
+        if (rc != G19_OK) ctx->err = perr;
+    }
+    if (rc != G19_OK && rc != G19_ERR_CANCELLED) return rc;
+    G19_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    ctx->stats_pending = true;
+    ctx->progress_milli.store(1000);
+    return rc;
+}
+
+int g19_render(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p, uint8_t* rgb,
+               int32_t* ids, float* rad) {
+    int rc = check_params(ctx, cam, p);
+    if (rc != G19_OK) return rc;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t npx = size_t(p->width) * size_t(p->height);
+    if (npx == 0) return G19_OK;
+    cudaStream_t s = ctx->stream;
+    if (rgb) G19_CUDA(ctx, ctx->rgb_f.ensure(npx * 3));
+    if (ids) G19_CUDA(ctx, ctx->ids_f.ensure(npx * sizeof(int32_t)));
+    if (rad) G19_CUDA(ctx, ctx->rad_f.ensure(npx * 3 * sizeof(float)));
+    // pixels owned by other ranks stay as the caller left them: seed the device
+    // copies from the caller's buffers when sharded, else clear (Image::clear, image.h:24)
+    if (p->world > 1) {
+        if (rgb) G19_CUDA(ctx, cudaMemcpyAsync(ctx->rgb_f.p, rgb, npx * 3, cudaMemcpyHostToDevice, s));
+        if (ids) G19_CUDA(ctx, cudaMemcpyAsync(ctx->ids_f.p, ids, npx * 4, cudaMemcpyHostToDevice, s));
+        if (rad) G19_CUDA(ctx, cudaMemcpyAsync(ctx->rad_f.p, rad, npx * 12, cudaMemcpyHostToDevice, s));
+    }
+    rc = g19_render_device(ctx, cam, light, p, rgb ? ctx->rgb_f.as<uint8_t>() : nullptr,
+                           ids ? ctx->ids_f.as<int32_t>() : nullptr, rad ? ctx->rad_f.as<float>() : nullptr, s);
+    if (rc != G19_OK && rc != G19_ERR_CANCELLED) return rc;
+    if (rgb) G19_CUDA(ctx, cudaMemcpyAsync(rgb, ctx->rgb_f.p, npx * 3, cudaMemcpyDeviceToHost, s));
+    if (ids) G19_CUDA(ctx, cudaMemcpyAsync(ids, ctx->ids_f.p, npx * 4, cudaMemcpyDeviceToHost, s));
+    if (rad) G19_CUDA(ctx, cudaMemcpyAsync(rad, ctx->rad_f.p, npx * 12, cudaMemcpyDeviceToHost, s));
+    G19_CUDA(ctx, cudaStreamSynchronize(s));
+    return rc;
+}
+
+int g19_get_stats(g19_ctx* ctx, g19_stats* out) {
+    if (!ctx || !out) return G19_ERR_INVALID;
+    if (ctx->stats_pending) {
+        G19_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        G19_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats.render_ms = ms;
+        std::string perr;
+        int rc = path_finish_stats(ctx->work, ctx->stats, perr);
+        if (rc != G19_OK) {
+            ctx->err = perr;
+            return rc;
+        }
+        ctx->stats_pending = false;
+    }
+    *out = ctx->stats;
+    return G19_OK;
+}
+
+int g19_cancel(g19_ctx* ctx) {
+    if (!ctx) return G19_ERR_INVALID;
+    ctx->cancel.store(1);
+    return G19_OK;
+}
+
+int g19_progress(g19_ctx* ctx, double* out) {
+    if (!ctx || !out) return G19_ERR_INVALID;
+    *out = ctx->progress_milli.load() / 1000.0;
+    return G19_OK;
+}
+
+int g19_probe_intersect(g19_ctx* ctx, int32_t entity, int n, const double* origins, const double* dirs, int32_t* hit,
+                        double* points, double* normals) {
+    if (!ctx || !origins || !dirs || !hit || !points || !normals || n < 0) return G19_ERR_INVALID;
+    if (!ctx->has_scene) return G19_ERR_NO_SCENE;
+    if (entity < 0 || entity >= ctx->ref.n_entities) return G19_ERR_INVALID;
+    if (n == 0) return G19_OK;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf o, d, h, p, nn;
+    size_t v = size_t(n) * 3 * sizeof(double);
+    cudaStream_t s = ctx->stream;
+    int rc = G19_OK;
+    auto fail = [&](cudaError_t e, const char* what) {
+        ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+        rc = G19_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = o.ensure(v)) != cudaSuccess || (e = d.ensure(v)) != cudaSuccess ||
+        (e = h.ensure(size_t(n) * 4)) != cudaSuccess || (e = p.ensure(v)) != cudaSuccess ||
+        (e = nn.ensure(v)) != cudaSuccess) {
+        fail(e, "probe alloc");
+    } else {
+        cudaMemcpyAsync(o.p, origins, v, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d.p, dirs, v, cudaMemcpyHostToDevice, s);
+        launch_probe_intersect(ctx->ref, entity, n, o.as<double>(), d.as<double>(), h.as<int32_t>(), p.as<double>(),
+                               nn.as<double>(), s);
+        cudaMemcpyAsync(hit, h.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(points, p.p, v, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(normals, nn.p, v, cudaMemcpyDeviceToHost, s);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) fail(e, "probe_intersect");
+    }
+    for (DevBuf* b : {&o, &d, &h, &p, &nn}) b->release();
+    return rc;
+}
+
+int g19_probe_candidates(g19_ctx* ctx, const double origin[3], const double dir[3], int32_t* out_ids, int max_out,
+                         int* out_n) {
+    if (!ctx || !origin || !dir || !out_n || max_out < 0) return G19_ERR_INVALID;
+    if (!ctx->has_scene) return G19_ERR_NO_SCENE;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf od, ids, cnt;
+    cudaStream_t s = ctx->stream;
+    double h[6] = {origin[0], origin[1], origin[2], dir[0], dir[1], dir[2]};
+    int rc = G19_OK;
+    cudaError_t e;
+    if ((e = od.ensure(sizeof h)) != cudaSuccess || (e = ids.ensure(size_t(max_out ? max_out : 1) * 4)) != cudaSuccess ||
+        (e = cnt.ensure(4)) != cudaSuccess) {
+        ctx->err = std::string("probe alloc: ") + cudaGetErrorString(e);
+        rc = G19_ERR_CUDA;
+    } else {
+        cudaMemcpyAsync(od.p, h, sizeof h, cudaMemcpyHostToDevice, s);
+        launch_probe_candidates(ctx->ref, od.as<double>(), ids.as<int32_t>(), max_out, cnt.as<int32_t>(), s);
+        int32_t n = 0;
+        cudaMemcpyAsync(&n, cnt.p, 4, cudaMemcpyDeviceToHost, s);
+        e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess && out_ids && max_out > 0) {
+            int m = n < max_out ? n : max_out;
+            e = cudaMemcpy(out_ids, ids.p, size_t(m) * 4, cudaMemcpyDeviceToHost);
+        }
+        if (e != cudaSuccess) {
+            ctx->err = std::string("probe_candidates: ") + cudaGetErrorString(e);
+            rc = G19_ERR_CUDA;
+        }
+        *out_n = n;
+    }
+    for (DevBuf* b : {&od, &ids, &cnt}) b->release();
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,481 @@
+// path.cu -- host side of G19_MODE_PATH: primitive extraction, the engine's own
+// linear octree ("FIXED" semantics of SURVEY.md section 7, hard part 1: true
+// bounds, every primitive reachable, nearest hit), and the wavefront driver.
+//
+// Reference counterpart: the octree build of include/octree.h:75-129 -- which
+// loses entities on split and boxes spheres around the origin -- is NOT
+// reproduced here; it lives, bug for bug, in scene.cpp for REF mode. This tree
+// is what the path tracer traverses:
+//   * node boxes are implicit: the root box is Octree::min/max, a node at
+//     level l with integer coordinates (ix,iy,iz) spans
+//     root_lo + (i, i+1) * root_size * 2^-l per axis (same float expression on
+//     host and device, so the boxes tile space without cracks)
+//   * records are 8 bytes; the 8 children of a node are contiguous = one 64 B
+//     line; nodes are laid out breadth first so the top levels are a prefix
+//     that the kernels stage into shared memory
+#include "path.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace g19 {
+
+cudaError_t DeviceArray::ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    // pad so that 16-byte bulk copies may run past the logical end
+    cudaError_t e = cudaMalloc(&p, need + 256);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+}
+void DeviceArray::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+};
+
+struct BuildPrim {
+    PrimHot hot;
+    PrimCold cold;
+    Box box;
+};
+
+float clamp01(double v) { return float(v < 0 ? 0 : (v > 1 ? 1 : v)); }
+
+void add_triangle(std::vector<BuildPrim>& out, const HostTri& t, int material, int entity) {
+    BuildPrim p;
+    std::memset(&p, 0, sizeof p);
+    float v0[3] = {float(t.p1.x), float(t.p1.y), float(t.p1.z)};
+    float v1[3] = {float(t.p2.x), float(t.p2.y), float(t.p2.z)};
+    float v2[3] = {float(t.p3.x), float(t.p3.y), float(t.p3.z)};
+    float e1[3], e2[3];
+    for (int k = 0; k < 3; ++k) {
+        e1[k] = v1[k] - v0[k];
+        e2[k] = v2[k] - v0[k];
+    }
+    float* q = p.hot.q;
+    q[0] = v0[0]; q[1] = v0[1]; q[2] = v0[2]; q[3] = e1[0];
+    q[4] = e1[1]; q[5] = e1[2]; q[6] = e2[0]; q[7] = e2[1];
+    q[8] = e2[2]; q[9] = 0; q[10] = 0; q[11] = 1.0f; // kind = triangle
+    // geometric normal from the double-precision vertices
+    double ax = t.p2.x - t.p1.x, ay = t.p2.y - t.p1.y, az = t.p2.z - t.p1.z;
+    double bx = t.p3.x - t.p1.x, by = t.p3.y - t.p1.y, bz = t.p3.z - t.p1.z;
+    double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+    if (len > 0) { nx /= len; ny /= len; nz /= len; }
+    p.cold.n[0] = float(nx); p.cold.n[1] = float(ny); p.cold.n[2] = float(nz);
+    p.cold.material = material;
+    p.cold.entity = entity;
+    for (int k = 0; k < 3; ++k) {
+        p.box.lo[k] = std::min(v0[k], std::min(v1[k], v2[k]));
+        p.box.hi[k] = std::max(v0[k], std::max(v1[k], v2[k]));
+    }
+    out.push_back(p);
+}
+
+void add_sphere(std::vector<BuildPrim>& out, const HostEntity& e, int material, int entity) {
+    BuildPrim p;
+    std::memset(&p, 0, sizeof p);
+    float c[3] = {float(e.pos.x), float(e.pos.y), float(e.pos.z)};
+    float* q = p.hot.q;
+    q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; q[3] = e.radius;
+    q[11] = 0.0f; // kind = sphere
+    p.cold.material = material;
+    p.cold.entity = entity;
+    for (int k = 0; k < 3; ++k) {
+        p.box.lo[k] = c[k] - e.radius;
+        p.box.hi[k] = c[k] + e.radius;
+    }
+    out.push_back(p);
+}
+
+struct Pending {
+    uint32_t node;
+    int level;
+    uint32_t ix, iy, iz;
+    std::vector<uint32_t> prims;
+};
+
+bool overlaps(const Box& a, const float lo[3], const float hi[3]) {
+    for (int k = 0; k < 3; ++k)
+        if (a.hi[k] < lo[k] || a.lo[k] > hi[k]) return false;
+    return true;
+}
+
+} // namespace
+
+// Cell bounds: the ONE expression shared with the device (path_kernels.cu cell_lo/cell_hi).
+static inline float cell_edge(float root_lo, float root_size, int level, uint32_t i) {
+    return root_lo + float(i) * std::ldexp(root_size, -level);
+}
+
+int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream, std::string& err) {
+    std::vector<BuildPrim> prims;
+    std::vector<MaterialD> materials;
+    std::vector<LightD> lights;
+    for (bool& h : b.has_bsdf) h = false;
+    for (size_t ei = 0; ei < scene.ents.size(); ++ei) {
+        const HostEntity& e = scene.ents[ei];
+        if (!e.in_tree) continue; // rejected by Octree::push_back: not part of the scene
+        MaterialD m;
+        m.albedo[0] = clamp01(e.desc.color[0]);
+        m.albedo[1] = clamp01(e.desc.color[1]);
+        m.albedo[2] = clamp01(e.desc.color[2]);
+        m.bsdf = e.desc.bsdf;
+        if (m.bsdf < 0 || m.bsdf > 3) m.bsdf = G19_BSDF_DIFFUSE;
+        m.emission[0] = e.desc.emission[0];
+        m.emission[1] = e.desc.emission[1];
+        m.emission[2] = e.desc.emission[2];
+        m.ior = e.desc.ior > 0 ? e.desc.ior : 1.5f;
+        // one material per entity, deduplicated against the previous one (meshes)
+        int mi;
+        if (!materials.empty() && std::memcmp(&materials.back(), &m, sizeof m) == 0) mi = int(materials.size()) - 1;
+        else { materials.push_back(m); mi = int(materials.size()) - 1; }
+        b.has_bsdf[m.bsdf] = true;
+        // material index and class ride in the spare words of the hot record
+        auto tag = [&](BuildPrim& p) {
+            int32_t mat_bits = mi, bsdf_bits = m.bsdf;
+            std::memcpy(&p.hot.q[9], &mat_bits, 4);
+            std::memcpy(&p.hot.q[10], &bsdf_bits, 4);
+        };
+        if (e.combine == COMBINE_SPHERE) {
+            add_sphere(prims, e, mi, int(ei));
+            tag(prims.back());
+        } else {
+            for (size_t t = size_t(e.first_tested); t < e.tris.size(); ++t) {
+                add_triangle(prims, e.tris[t], mi, int(ei));
+                tag(prims.back());
+                if (m.bsdf == G19_BSDF_EMITTER) {
+                    const BuildPrim& p = prims.back();
+                    LightD l;
+                    std::memset(&l, 0, sizeof l);
+                    const float* q = p.hot.q;
+                    l.v0[0] = q[0]; l.v0[1] = q[1]; l.v0[2] = q[2];
+                    l.e1[0] = q[3]; l.e1[1] = q[4]; l.e1[2] = q[5];
+                    l.e2[0] = q[6]; l.e2[1] = q[7]; l.e2[2] = q[8];
+                    float cx = l.e1[1] * l.e2[2] - l.e1[2] * l.e2[1];
+                    float cy = l.e1[2] * l.e2[0] - l.e1[0] * l.e2[2];
+                    float cz = l.e1[0] * l.e2[1] - l.e1[1] * l.e2[0];
+                    l.area = 0.5f * std::sqrt(cx * cx + cy * cy + cz * cz);
+                    l.prim = int32_t(prims.size()) - 1;
+                    l.n[0] = p.cold.n[0]; l.n[1] = p.cold.n[1]; l.n[2] = p.cold.n[2];
+                    l.emission[0] = m.emission[0]; l.emission[1] = m.emission[1]; l.emission[2] = m.emission[2];
+                    if (l.area > 0) lights.push_back(l);
+                }
+            }
+        }
+    }
+    for (LightD& l : lights) l.pdf_pick = 1.0f / float(lights.size());
+    if (prims.size() >= 0x7fffffffu) {
+        err = "too many primitives";
+        return G19_ERR_LIMIT;
+    }
+
+    // ---- linear octree, breadth first ------------------------------------------
+    const int kLeafMax = 8;
+    float root_lo[3] = {float(scene.rmin.x), float(scene.rmin.y), float(scene.rmin.z)};
+    float root_hi[3] = {float(scene.rmax.x), float(scene.rmax.y), float(scene.rmax.z)};
+    for (int k = 0; k < 3; ++k) { // the root box must enclose every primitive
+        for (const BuildPrim& p : prims) {
+            root_lo[k] = std::min(root_lo[k], p.box.lo[k]);
+            root_hi[k] = std::max(root_hi[k], p.box.hi[k]);
+        }
+    }
+    float root_size[3] = {root_hi[0] - root_lo[0], root_hi[1] - root_lo[1], root_hi[2] - root_lo[2]};
+    for (int k = 0; k < 3; ++k) { // nudge up so that lo + 1 * size >= hi after rounding
+        while (root_lo[k] + root_size[k] < root_hi[k]) root_size[k] = std::nextafter(root_size[k], INFINITY);
+        if (!(root_size[k] > 0)) root_size[k] = 1.0f;
+    }
+    std::vector<PathNodeD> nodes(1);
+    std::vector<uint32_t> index;
+    std::vector<Pending> frontier(1), next;
+    frontier[0].node = 0;
+    frontier[0].level = 0;
+    frontier[0].ix = frontier[0].iy = frontier[0].iz = 0;
+    frontier[0].prims.resize(prims.size());
+    for (size_t i = 0; i < prims.size(); ++i) frontier[0].prims[i] = uint32_t(i);
+    int tree_depth = 0;
+    while (!frontier.empty()) {
+        next.clear();
+        for (Pending& n : frontier) {
+            bool leaf = int(n.prims.size()) <= kLeafMax || n.level >= kMaxTreeDepth;
+            std::vector<uint32_t> child[8];
+            if (!leaf) {
+                size_t refs = 0;
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t cx = 2 * n.ix + (c & 1), cy = 2 * n.iy + ((c >> 1) & 1), cz = 2 * n.iz + ((c >> 2) & 1);
+                    float lo[3] = {cell_edge(root_lo[0], root_size[0], n.level + 1, cx),
+                                   cell_edge(root_lo[1], root_size[1], n.level + 1, cy),
+                                   cell_edge(root_lo[2], root_size[2], n.level + 1, cz)};
+                    float hi[3] = {cell_edge(root_lo[0], root_size[0], n.level + 1, cx + 1),
+                                   cell_edge(root_lo[1], root_size[1], n.level + 1, cy + 1),
+                                   cell_edge(root_lo[2], root_size[2], n.level + 1, cz + 1)};
+                    for (uint32_t pi : n.prims)
+                        if (overlaps(prims[pi].box, lo, hi)) child[c].push_back(pi);
+                    refs += child[c].size();
+                }
+                // splitting must pay: stop when the children mostly duplicate the parent
+                if (refs >= 3 * n.prims.size()) leaf = true;
+            }
+            if (leaf) {
+                nodes[n.node].first = uint32_t(index.size());
+                nodes[n.node].count = uint32_t(n.prims.size()) | kLeafBit;
+                index.insert(index.end(), n.prims.begin(), n.prims.end());
+                continue;
+            }
+            uint32_t base = uint32_t(nodes.size());
+            nodes[n.node].first = base;
+            nodes[n.node].count = 0;
+            nodes.resize(nodes.size() + 8);
+            tree_depth = std::max(tree_depth, n.level + 1);
+            for (int c = 0; c < 8; ++c) {
+                Pending ch;
+                ch.node = base + c;
+                ch.level = n.level + 1;
+                ch.ix = 2 * n.ix + (c & 1);
+                ch.iy = 2 * n.iy + ((c >> 1) & 1);
+                ch.iz = 2 * n.iz + ((c >> 2) & 1);
+                ch.prims = std::move(child[c]);
+                next.push_back(std::move(ch));
+            }
+        }
+        frontier.swap(next);
+    }
+
+    std::vector<PrimHot> hot(prims.size());
+    std::vector<PrimCold> cold(prims.size());
+    for (size_t i = 0; i < prims.size(); ++i) {
+        hot[i] = prims[i].hot;
+        cold[i] = prims[i].cold;
+    }
+    auto up = [&](DeviceArray& d, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = d.ensure(bytes ? bytes : 16);
+        if (e != cudaSuccess || !bytes) return e;
+        return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, stream);
+    };
+    cudaError_t e;
+    if ((e = up(b.nodes, nodes.data(), nodes.size() * sizeof(PathNodeD))) != cudaSuccess ||
+        (e = up(b.prim_index, index.data(), index.size() * sizeof(uint32_t))) != cudaSuccess ||
+        (e = up(b.hot, hot.data(), hot.size() * sizeof(PrimHot))) != cudaSuccess ||
+        (e = up(b.cold, cold.data(), cold.size() * sizeof(PrimCold))) != cudaSuccess ||
+        (e = up(b.materials, materials.data(), materials.size() * sizeof(MaterialD))) != cudaSuccess ||
+        (e = up(b.lights, lights.data(), lights.size() * sizeof(LightD))) != cudaSuccess ||
+        (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
+        err = std::string("path_upload: ") + cudaGetErrorString(e);
+        return G19_ERR_CUDA;
+    }
+    PathSceneD& v = b.view;
+    v.nodes = static_cast<const PathNodeD*>(b.nodes.p);
+    v.prim_index = static_cast<const uint32_t*>(b.prim_index.p);
+    v.hot = static_cast<const PrimHot*>(b.hot.p);
+    v.cold = static_cast<const PrimCold*>(b.cold.p);
+    v.materials = static_cast<const MaterialD*>(b.materials.p);
+    v.lights = static_cast<const LightD*>(b.lights.p);
+    v.n_nodes = int32_t(nodes.size());
+    v.n_index = int32_t(index.size());
+    v.n_prims = int32_t(prims.size());
+    v.n_lights = int32_t(lights.size());
+    v.tree_depth = tree_depth;
+    for (int k = 0; k < 3; ++k) {
+        v.root_lo[k] = root_lo[k];
+        v.root_size[k] = root_size[k];
+    }
+    return G19_OK;
+}
+
+void path_release(PathSceneBuffers& b, PathWork& w) {
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &w.ro, &w.rd, &w.tp,
+                           &w.hit, &w.L, &w.queues, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
+        d->release();
+    if (w.events) {
+        for (int i = 0; i < w.n_events; ++i) cudaEventDestroy(w.events[i]);
+        delete[] w.events;
+        w.events = nullptr;
+        w.n_events = 0;
+    }
+}
+
+namespace {
+
+struct ClassClock { // non-blocking CUDA-event bracket around each launch group
+    PathWork& w;
+    cudaStream_t s;
+    bool on;
+    void begin() {
+        if (!on || w.used_events + 2 > w.n_events) return;
+        cudaEventRecord(w.events[w.used_events], s);
+    }
+    void end(int cls) {
+        if (!on || w.used_events + 2 > w.n_events) return;
+        cudaEventRecord(w.events[w.used_events + 1], s);
+        w.event_class[w.used_events / 2] = cls;
+        w.used_events += 2;
+    }
+};
+
+} // namespace
+
+int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err) {
+    const g19_params& p = a.params;
+    if (p.spp < 1 || p.max_depth < 1 || p.max_depth > kMaxPathDepth) {
+        err = "PATH mode needs spp >= 1 and 1 <= max_depth <= 64";
+        return G19_ERR_INVALID;
+    }
+    cudaStream_t s = a.stream;
+    const size_t npix = size_t(a.map.n_local_pix);
+    if (npix == 0) return G19_OK;
+    // pass size: enough slots to fill the machine, small enough to stay cache friendly
+    int spp_pass = p.spp_per_pass;
+    if (spp_pass <= 0) {
+        const size_t target = size_t(1) << 22;
+        spp_pass = int(std::max<size_t>(1, target / npix));
+    }
+    spp_pass = std::min(spp_pass, p.spp);
+    const size_t P = npix * size_t(spp_pass);
+    if (P > 0xfffffff0ull) {
+        err = "pass too large";
+        return G19_ERR_LIMIT;
+    }
+#define PATH_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            err = std::string(#call) + ": " + cudaGetErrorString(e__);         \
+            return G19_ERR_CUDA;                                               \
+        }                                                                      \
+    } while (0)
+    if (P > w.capacity) {
+        PATH_CUDA(w.ro.ensure(P * sizeof(float4)));
+        PATH_CUDA(w.rd.ensure(P * sizeof(float2)));
+        PATH_CUDA(w.tp.ensure(P * sizeof(float4)));
+        PATH_CUDA(w.hit.ensure(P * sizeof(uint2)));
+        PATH_CUDA(w.L.ensure(P * 3 * sizeof(float)));
+        PATH_CUDA(w.queues.ensure(P * 5 * sizeof(uint32_t)));
+        w.capacity = P;
+        PATH_CUDA(cudaMemsetAsync(w.L.p, 0, P * 3 * sizeof(float), s));
+    }
+    const size_t plane = w.capacity;
+    PATH_CUDA(w.counts.ensure((kMaxPathDepth + 1) * 4 * sizeof(uint32_t)));
+    PATH_CUDA(w.totals.ensure(8 * sizeof(unsigned long long)));
+    PATH_CUDA(w.accum.ensure(npix * 3 * sizeof(float)));
+    PATH_CUDA(w.rad_l.ensure(npix * 3 * sizeof(float)));
+    PATH_CUDA(w.rgb_l.ensure(npix * 3));
+    PATH_CUDA(cudaMemsetAsync(w.counts.p, 0, (kMaxPathDepth + 1) * 4 * sizeof(uint32_t), s));
+    PATH_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(unsigned long long), s));
+    PATH_CUDA(cudaMemsetAsync(w.accum.p, 0, npix * 3 * sizeof(float), s));
+    if (p.profile && !w.events) {
+        w.n_events = 8192;
+        w.events = new cudaEvent_t[w.n_events];
+        for (int i = 0; i < w.n_events; ++i) PATH_CUDA(cudaEventCreate(&w.events[i]));
+    }
+    w.used_events = 0;
+
+    PassArgs pa;
+    pa.scene = b.view;
+    for (int k = 0; k < 3; ++k) {
+        pa.cam.pos[k] = float(a.cam.pos[k]);
+        pa.cam.top_left[k] = float(a.cam.top_left[k]);
+        pa.cam.left[k] = float(a.cam.left[k]);
+        pa.cam.up[k] = float(a.cam.up[k]);
+    }
+    pa.map = a.map;
+    pa.seed = p.seed;
+    pa.max_depth = p.max_depth;
+    pa.ro = static_cast<float4*>(w.ro.p);
+    pa.rd = static_cast<float2*>(w.rd.p);
+    pa.tp = static_cast<float4*>(w.tp.p);
+    pa.hit = static_cast<uint2*>(w.hit.p);
+    pa.L = static_cast<float*>(w.L.p);
+    pa.plane = plane;
+    for (int k = 0; k < 5; ++k) pa.q[k] = static_cast<uint32_t*>(w.queues.p) + size_t(k) * plane;
+    pa.counts = static_cast<uint32_t*>(w.counts.p);
+    pa.totals = static_cast<unsigned long long*>(w.totals.p);
+    pa.accum = static_cast<float*>(w.accum.p);
+
+    const int grid_extend = a.sm_count * extend_blocks_per_sm();
+    const int grid_shade = a.sm_count * shade_blocks_per_sm();
+    ClassClock clk{w, s, p.profile != 0};
+    int rc = G19_OK;
+    for (int base = 0; base < p.spp; base += spp_pass) {
+        if (a.cancel && a.cancel->load()) { // RayTracer::stop(): honoured between passes
+            rc = G19_ERR_CANCELLED;
+            break;
+        }
+        pa.sample_base = base;
+        pa.spp_pass = std::min(spp_pass, p.spp - base);
+        pa.n_slots = uint32_t(npix * size_t(pa.spp_pass));
+        for (int bounce = 0; bounce < p.max_depth; ++bounce) {
+            clk.begin();
+            launch_extend(pa, bounce, grid_extend, s);
+            clk.end(G19_K_EXTEND);
+            stats.class_launches[G19_K_EXTEND] += 1;
+            clk.begin();
+            int n = 0;
+            for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
+                if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
+                launch_shade(pa, bounce, kind, grid_shade, s);
+                ++n;
+            }
+            clk.end(G19_K_SHADE);
+            stats.class_launches[G19_K_SHADE] += n;
+        }
+        clk.begin();
+        launch_accumulate(pa, grid_shade, s);
+        clk.end(G19_K_ACCUM);
+        stats.class_launches[G19_K_ACCUM] += 1;
+        stats.samples += uint64_t(pa.spp_pass); // scaled by owned pixels below
+        if (a.progress_milli) a.progress_milli->store(int(1000.0 * double(base + pa.spp_pass) / double(p.spp)));
+    }
+    const int done_spp = int(stats.samples);
+    clk.begin();
+    launch_resolve(a.map, pa.accum, done_spp > 0 ? done_spp : 1, static_cast<float*>(w.rad_l.p),
+                   static_cast<uint8_t*>(w.rgb_l.p), s);
+    launch_untile(a.map, a.d_rgb ? static_cast<uint8_t*>(w.rgb_l.p) : nullptr, nullptr,
+                  a.d_rad ? static_cast<float*>(w.rad_l.p) : nullptr, a.d_rgb, nullptr, a.d_rad, s);
+    clk.end(G19_K_OTHER);
+    stats.class_launches[G19_K_OTHER] += 2;
+    PATH_CUDA(cudaGetLastError());
+    for (int k = 0; k < 8; ++k) stats.kernel_launches += stats.class_launches[k];
+    // owned in-frame pixels
+    uint64_t owned = 0;
+    for (int lt = 0; lt < a.map.n_local_tiles; ++lt) {
+        int tile = lt * a.map.world + a.map.rank;
+        int ty = tile / a.map.tiles_x, tx = tile % a.map.tiles_x;
+        owned += uint64_t(std::min(kTile, a.map.w - tx * kTile)) * uint64_t(std::min(kTile, a.map.h - ty * kTile));
+    }
+    stats.samples = owned * uint64_t(done_spp);
+    w.totals_pending = true;
+    w.totals_stream = s;
+    return rc;
+#undef PATH_CUDA
+}
+
+int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
+    if (!w.totals_pending) return G19_OK;
+    unsigned long long h[8];
+    cudaError_t e = cudaMemcpy(h, w.totals.p, sizeof h, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        err = std::string("path_finish_stats: ") + cudaGetErrorString(e);
+        return G19_ERR_CUDA;
+    }
+    stats.extend_segments = h[0] + stats.samples; // bounce 0 has no queue: one segment per camera path
+    stats.shadow_segments = h[1];
+    for (int i = 0; i + 1 < w.used_events; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, w.events[i], w.events[i + 1]) == cudaSuccess) stats.class_ms[w.event_class[i / 2]] += ms;
+    }
+    w.totals_pending = false;
+    return G19_OK;
+}
+
+} // namespace g19

@@ -1,0 +1,131 @@
+// path.h -- G19_MODE_PATH: host-side driver of the wavefront path tracer.
+//
+// Nothing here has a counterpart in the reference (it casts one primary ray
+// per pixel and shades directly, raytracer.h:32-86). The transport model is
+// defined by this repo and pinned by oracle/path_oracle.c (FP64, brute force):
+//   * camera: the reference's pinhole (raytracer.h:26-30) with a uniform
+//     jitter in [0,1)^2 added to the integer pixel corner
+//   * geometry: the primitives each entity would test in REF mode, intersected
+//     properly (nearest hit, t > 0, Moller-Trumbore / analytic sphere)
+//   * BSDFs: lambert (albedo = clamp(Material::color,0,1)), mirror, dielectric
+//   * light: triangle emitters, next-event estimation at diffuse hits, emission
+//     counted on camera rays and after specular bounces only
+//   * max_depth = maximum number of ray segments along the camera path
+//   * RNG: Philox4x32-10, counter (pixel, sample, bounce, stream), key (seed, K)
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "g19.h"
+#include "kernels.h"
+#include "scene.h"
+
+namespace g19 {
+
+constexpr int kMaxPathDepth = 64;    // segments per path
+constexpr int kMaxTreeDepth = 14;    // linear-octree levels below the root
+constexpr int kNumQueues = 4;        // extend, diffuse, mirror, glass
+enum { Q_EXTEND = 0, Q_DIFFUSE = 1, Q_MIRROR = 2, Q_GLASS = 3 };
+
+struct PathSceneD {
+    const PathNodeD* nodes;
+    const uint32_t* prim_index;
+    const PrimHot* hot;
+    const PrimCold* cold;
+    const MaterialD* materials;
+    const LightD* lights;
+    int32_t n_nodes, n_index, n_prims, n_lights, tree_depth;
+    float root_lo[3], root_size[3];
+};
+
+struct PathCamera { // float copies of the reference basis (RefCamera)
+    float pos[3], top_left[3], left[3], up[3];
+};
+
+struct DeviceArray {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need);
+    void release();
+};
+
+struct PathSceneBuffers {
+    DeviceArray nodes, prim_index, hot, cold, materials, lights;
+    PathSceneD view{};
+    bool has_bsdf[4] = {false, false, false, false};
+};
+
+// SoA wavefront state for one pass of P path slots (slot = sample_in_pass * n_local_pix + local_pixel).
+struct PathWork {
+    size_t capacity = 0;       // slots
+    DeviceArray ro;            // float4[P]: origin.xyz, dir.x
+    DeviceArray rd;            // float2[P]: dir.y, dir.z
+    DeviceArray tp;            // float4[P]: throughput.rgb, flags (bit0: last bounce specular)
+    DeviceArray hit;           // uint2[P] : t (float bits), primitive (0xffffffff = miss)
+    DeviceArray L;             // float[3][P]: radiance gathered by the path so far
+    DeviceArray queues;        // uint32[5][P]: extend A, extend B, diffuse, mirror, glass
+    DeviceArray counts;        // uint32[kMaxPathDepth+1][4] queue lengths per bounce
+    DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
+    DeviceArray accum;         // float[3][n_local_pix]
+    DeviceArray rad_l, rgb_l;  // resolved local-pixel outputs
+    // event pool for params.profile
+    cudaEvent_t* events = nullptr;
+    int n_events = 0, used_events = 0;
+    int event_class[4096];
+    bool totals_pending = false;
+    cudaStream_t totals_stream = nullptr;
+};
+
+struct PathRenderArgs {
+    RefCamera cam;
+    g19_params params;
+    TileMap map;
+    uint8_t* d_rgb;
+    float* d_rad;
+    int32_t* d_ids;
+    cudaStream_t stream;
+    int sm_count;
+    std::atomic<int>* cancel;
+    std::atomic<int>* progress_milli;
+    cudaEvent_t cls0, cls1;
+};
+
+int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream, std::string& err);
+int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err);
+int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err);
+void path_release(PathSceneBuffers& b, PathWork& w);
+
+// ---- path_kernels.cu -------------------------------------------------------
+struct PassArgs {
+    PathSceneD scene;
+    PathCamera cam;
+    TileMap map;
+    uint32_t seed;
+    int32_t spp_pass;      // samples in this pass
+    int32_t sample_base;   // first sample index of this pass
+    int32_t max_depth;
+    uint32_t n_slots;      // spp_pass * n_local_pix
+    float4* ro;
+    float2* rd;
+    float4* tp;
+    uint2* hit;
+    float* L;              // 3 planes of capacity `plane`
+    size_t plane;          // slots per plane (capacity)
+    uint32_t* q[5];
+    uint32_t* counts;      // [kMaxPathDepth+1][4]
+    unsigned long long* totals;
+    float* accum;          // 3 planes of n_local_pix
+};
+
+void launch_extend(const PassArgs& a, int bounce, int grid, cudaStream_t s);
+void launch_shade(const PassArgs& a, int bounce, int kind, int grid, cudaStream_t s);
+void launch_accumulate(const PassArgs& a, int grid, cudaStream_t s);
+void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s);
+int extend_blocks_per_sm();
+int shade_blocks_per_sm();
+
+} // namespace g19

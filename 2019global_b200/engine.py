@@ -1,0 +1,276 @@
+"""Python front end of lib2019global_b200.so (ctypes over include/g19.h).
+
+Class and method names follow the reference's host interface so that tests read
+like a port of its main.cpp (reference main.cpp:24-59):
+
+    scene = Octree((-20,)*3, (20,)*3)            # include/octree.h:14
+    scene.push_back(ImpSphere((3,4,4), 2, (1,0,0)))   # octree.h:20
+    rt = RayTracer(Camera((-10,0,0), (1,0,0), 0.1), light=(-10,10,10))
+    rt.setScene(scene)                            # raytracer.h:21
+    rt.start(); image = rt.run(500, 500)          # raytracer.h:23,91
+
+The compute path is the CUDA library; there is no fallback. Importing this
+module without the built .so raises, and creating a RayTracer without a B200
+raises G19Error(ERR_NO_DEVICE).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib2019global_b200.so")
+
+# every symbol include/g19.h declares
+EXPORTS = [
+    "g19_scene_create", "g19_scene_destroy", "g19_scene_add_entity", "g19_scene_entity_count",
+    "g19_scene_get_entity", "g19_scene_entity_bbox", "g19_scene_entity_triangles", "g19_scene_builtin",
+    "g19_create", "g19_destroy", "g19_last_error", "g19_upload_scene", "g19_render", "g19_render_device",
+    "g19_get_stats", "g19_cancel", "g19_progress", "g19_probe_intersect", "g19_probe_candidates",
+]
+
+
+class G19Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("g19 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("lib2019global_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                              " -- there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.g19_last_error.restype = C.c_char_p
+        L.g19_last_error.argtypes = [C.c_void_p]
+        L.g19_scene_destroy.restype = None
+        L.g19_scene_destroy.argtypes = [C.c_void_p]
+        L.g19_destroy.restype = None
+        L.g19_destroy.argtypes = [C.c_void_p]
+        L.g19_scene_add_entity.argtypes = [C.c_void_p, C.POINTER(abi.EntityDesc), C.POINTER(C.c_int32)]
+        L.g19_scene_get_entity.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.EntityDesc)]
+        L.g19_scene_entity_count.argtypes = [C.c_void_p]
+        L.g19_scene_entity_bbox.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.g19_scene_entity_triangles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int]
+        L.g19_upload_scene.argtypes = [C.c_void_p, C.c_void_p]
+        L.g19_render.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_void_p, C.POINTER(abi.Params), C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
+        L.g19_render_device.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_void_p, C.POINTER(abi.Params),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g19_get_stats.argtypes = [C.c_void_p, C.POINTER(abi.Stats)]
+        L.g19_cancel.argtypes = [C.c_void_p]
+        L.g19_progress.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.g19_probe_intersect.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+        L.g19_probe_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+# ---- entities: constructor arguments exactly as the reference's classes take them ----
+def ImpSphere(pos, radius, color, **kw):
+    return abi.EntityDesc.make(abi.IMP_SPHERE, pos, [radius], color, **kw)
+
+
+def ImpTriangle(p1, p2, p3, color=(1.0, 0.0, 0.0), **kw):
+    return abi.EntityDesc.make(abi.IMP_TRIANGLE, list(p1) + list(p2) + list(p3), [], color, **kw)
+
+
+def ExpRectangle(p1, p2, p3, color=(1.0, 0.0, 0.0), **kw):
+    return abi.EntityDesc.make(abi.EXP_RECTANGLE, list(p1) + list(p2) + list(p3), [], color, **kw)
+
+
+def ExpBox(mn, mx, color=(1.0, 0.0, 0.0), **kw):
+    return abi.EntityDesc.make(abi.EXP_BOX, list(mn) + list(mx), [], color, **kw)
+
+
+def ExpSphere(pos, radius, color, **kw):
+    return abi.EntityDesc.make(abi.EXP_SPHERE, pos, [radius], color, **kw)
+
+
+def ExpQuad(pos, width, length, alpha, color, **kw):
+    return abi.EntityDesc.make(abi.EXP_QUAD, pos, [width, length, alpha], color, **kw)
+
+
+def ExpCube(pos, width, length, height, color, **kw):
+    return abi.EntityDesc.make(abi.EXP_CUBE, pos, [width, length, height], color, **kw)
+
+
+def ExpCone(pos, direction, height, radius, color, **kw):
+    return abi.EntityDesc.make(abi.EXP_CONE, list(pos) + list(direction), [height, radius], color, **kw)
+
+
+def Camera(pos, look_at=(0.0, 0.0, 0.0), focal=0.04):
+    """camera.h:7-10 (the one-argument form looks at the origin with focal 0.04)."""
+    return abi.Camera.make(pos, look_at, focal)
+
+
+class Octree:
+    """Octree(min, max) + push_back (include/octree.h:12-30). Host-side only: no GPU needed."""
+
+    def __init__(self, mn, mx, _handle=None):
+        self._L = lib()
+        if _handle is not None:
+            self.h = _handle
+        else:
+            h = C.c_void_p()
+            rc = self._L.g19_scene_create(abi.d3(mn), abi.d3(mx), C.byref(h))
+            if rc != abi.OK:
+                raise G19Error(rc, "g19_scene_create")
+            self.h = h
+        self.min, self.max = tuple(mn), tuple(mx)
+
+    @classmethod
+    def builtin(cls, which, n=0, w=500, h=500):
+        """One of BASELINE.json's procedural configs -> (scene, camera, light)."""
+        L = lib()
+        hd = C.c_void_p()
+        cam = abi.Camera()
+        light = (C.c_double * 3)()
+        rc = L.g19_scene_builtin(which, n, w, h, C.byref(hd), C.byref(cam), light)
+        if rc != abi.OK:
+            raise G19Error(rc, "g19_scene_builtin")
+        return cls((-20,) * 3, (20,) * 3, _handle=hd), cam, tuple(light[:])
+
+    def __del__(self):
+        try:
+            self._L.g19_scene_destroy(self.h)
+        except Exception:
+            pass
+
+    def push_back(self, desc):
+        """Returns (entity_id, accepted). A rejected entity is numbered but not in the tree (octree.h:22-24)."""
+        idx = C.c_int32(-1)
+        rc = self._L.g19_scene_add_entity(self.h, C.byref(desc), C.byref(idx))
+        if rc not in (abi.OK, abi.ERR_REJECTED):
+            raise G19Error(rc, "g19_scene_add_entity")
+        return idx.value, rc == abi.OK
+
+    def __len__(self):
+        return self._L.g19_scene_entity_count(self.h)
+
+    def entity(self, i):
+        d = abi.EntityDesc()
+        rc = self._L.g19_scene_get_entity(self.h, i, C.byref(d))
+        if rc != abi.OK:
+            raise G19Error(rc, "g19_scene_get_entity")
+        return d
+
+    def entities(self):
+        return [self.entity(i) for i in range(len(self))]
+
+    def bbox(self, i):
+        out = np.zeros(6)
+        self._L.g19_scene_entity_bbox(self.h, i, _ptr(out))
+        return out
+
+    def triangles(self, i, max_tris=256):
+        out = np.zeros((max_tris, 9))
+        n = self._L.g19_scene_entity_triangles(self.h, i, _ptr(out), max_tris)
+        return out[:min(n, max_tris)].copy()
+
+
+class RayTracer:
+    """RayTracer(camera, light) with setScene/run/start/stop/running (include/raytracer.h:15-101)."""
+
+    def __init__(self, camera, light, device=None):
+        self._L = lib()
+        self.camera, self.light = camera, tuple(light)
+        h = C.c_void_p()
+        if device is None:
+            rc = self._L.g19_create(None, 0, C.byref(h))
+        else:
+            dev = (C.c_int * 1)(device)
+            rc = self._L.g19_create(dev, 1, C.byref(h))
+        if rc != abi.OK:
+            raise G19Error(rc, self._L.g19_last_error(None).decode())
+        self.h = h
+        self._running = False
+        self._scene = None
+
+    def __del__(self):
+        try:
+            self._L.g19_destroy(self.h)
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=()):
+        if rc != abi.OK and rc not in allow:
+            raise G19Error(rc, self._L.g19_last_error(self.h).decode())
+        return rc
+
+    def setScene(self, scene):
+        self._scene = scene  # the reference keeps a non-owning pointer; keep the Python object alive
+        self._check(self._L.g19_upload_scene(self.h, scene.h))
+
+    def running(self):
+        return self._running
+
+    def start(self):
+        self._running = True
+
+    def stop(self):
+        self._running = False
+        self._L.g19_cancel(self.h)
+
+    def params(self, w, h, mode=abi.MODE_REF, spp=1, max_depth=1, seed=0, rank=0, world=1, spp_per_pass=0, profile=0):
+        return abi.Params(w, h, mode, spp, max_depth, seed, rank, world, spp_per_pass, profile)
+
+    def run(self, w, h, mode=abi.MODE_REF, want=("rgb",), out=None, **kw):
+        """Blocking render into host arrays (the reference's run(w,h)). Returns a dict of numpy arrays."""
+        if not self._running:  # raytracer.h:32: nothing renders before start()
+            return {"rgb": np.zeros((h, w, 3), np.uint8)}
+        p = self.params(w, h, mode, **kw)
+        out = out or {}
+        rgb = out.get("rgb", np.zeros((h, w, 3), np.uint8)) if "rgb" in want else None
+        ids = out.get("ids", np.full((h, w), -1, np.int32)) if "ids" in want else None
+        rad = out.get("radiance", np.zeros((h, w, 3), np.float32)) if "radiance" in want else None
+        self._check(self._L.g19_render(self.h, C.byref(self.camera), abi.d3(self.light), C.byref(p), _ptr(rgb),
+                                       _ptr(ids), _ptr(rad)), allow=(abi.ERR_CANCELLED,))
+        return {"rgb": rgb, "ids": ids, "radiance": rad}
+
+    def run_device(self, p, d_rgb=0, d_ids=0, d_rad=0, stream=0):
+        """Asynchronous render into device pointers (ints, e.g. torch.Tensor.data_ptr())."""
+        return self._check(self._L.g19_render_device(self.h, C.byref(self.camera), abi.d3(self.light), C.byref(p),
+                                                     C.c_void_p(d_rgb), C.c_void_p(d_ids), C.c_void_p(d_rad),
+                                                     C.c_void_p(stream)), allow=(abi.ERR_CANCELLED,))
+
+    def stats(self):
+        s = abi.Stats()
+        self._check(self._L.g19_get_stats(self.h, C.byref(s)))
+        return s
+
+    def progress(self):
+        v = C.c_double(0)
+        self._L.g19_progress(self.h, C.byref(v))
+        return v.value
+
+    # unit-level probes (tests)
+    def probe_intersect(self, entity, origins, dirs):
+        o = np.ascontiguousarray(origins, dtype=np.float64)
+        d = np.ascontiguousarray(dirs, dtype=np.float64)
+        n = o.shape[0]
+        hit = np.zeros(n, np.int32)
+        pts = np.zeros((n, 3))
+        nrm = np.zeros((n, 3))
+        self._check(self._L.g19_probe_intersect(self.h, entity, n, _ptr(o), _ptr(d), _ptr(hit), _ptr(pts), _ptr(nrm)))
+        return hit, pts, nrm
+
+    def probe_candidates(self, o, d, max_out=1 << 16):
+        out = np.zeros(max_out, np.int32)
+        n = C.c_int(0)
+        self._check(self._L.g19_probe_candidates(self.h, abi.d3(o), abi.d3(d), _ptr(out), max_out, C.byref(n)))
+        return out[:min(n.value, max_out)].copy()

@@ -118,3 +118,14 @@ class CheckerScene:
         self.lib.fn("trace")(self.h, C.byref(cam), abi.d3(light), w, h, y0, y1, _ptr(ids), _ptr(pts), _ptr(nrm),
                              _ptr(rgb), threads)
         return {"ids": ids, "points": pts, "normals": nrm, "rgb": rgb}
+
+
+def path_render(scene, cam, w, h, spp, max_depth, seed=0, window=None, threads=8):
+    """FP64 brute-force path oracle (oracle/path_oracle.c) -> (radiance (h,w,3) float32, [extend, shadow])."""
+    assert scene.lib.which == "oracle"
+    x0, y0, x1, y1 = window if window else (0, 0, w, h)
+    rad = np.zeros((h, w, 3), np.float32)
+    segs = (C.c_uint64 * 2)()
+    fn = scene.lib.lib.g19o_path_render
+    fn(scene.h, C.byref(cam), w, h, spp, max_depth, C.c_uint32(seed), x0, y0, x1, y1, _ptr(rad), segs, threads)
+    return rad, (int(segs[0]), int(segs[1]))

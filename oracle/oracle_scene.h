@@ -32,6 +32,7 @@ typedef struct {
     int ntri;
     o_tri* tris;   /* composite triangles / own triangle(s) / box face pairs */
     d3 p3, p4;     /* ExpRectangle extras for getTextureCoord */
+    int in_tree;   /* 0: rejected by Octree::push_back's root test (octree.h:22-24) */
     g19_entity_desc desc;
 } o_entity;
 

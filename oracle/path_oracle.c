@@ -1,2 +1,333 @@
-/* placeholder, replaced below */
-int g19o_path_placeholder(void) { return 0; }
+/* path_oracle.c -- FP64, brute-force CPU definition of G19_MODE_PATH.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle_scene.h).
+ *
+ * PARITY UNPINNED BY THE REFERENCE: the reference casts one primary ray per
+ * pixel and shades it directly (reference include/raytracer.h:32-86,
+ * include/material.h:48-62); it has no spp loop, no jitter, no RNG, no bounce
+ * sampling, no area light, no mirror/glass.
+ * This file is therefore the DEFINITION the CUDA wavefront tracer
+ * (2019global_b200/csrc/path_kernels.cu) is checked against, not a restatement:
+ *   - camera: the reference pinhole (raytracer.h:26-30,41) + uniform jitter
+ *   - geometry: the primitives each entity tests in REF mode (spheres analytic,
+ *     everything else its triangle list), float-rounded vertices, nearest hit
+ *     with t > 0, found by testing EVERY primitive (no octree: this also checks
+ *     the GPU's tree)
+ *   - lambert / mirror / dielectric, triangle emitters, next-event estimation,
+ *     emission on camera rays and after specular bounces only
+ *   - Philox4x32-10 keyed on (pixel, sample, bounce, stream); the integer
+ *     stream is bit-identical to the device's, discrete choices that depend on
+ *     a float product are made in float like the device
+ * What IS pinned: the camera basis comes from the same expression as
+ * ref_restate.c (byte-equal to the compiled reference), and a max_depth=1 image
+ * of a scene without emitters is black wherever REF mode reports a miss.
+ */
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "oracle_scene.h"
+
+#define RAY_EPS 1.0e-3
+#define PI_D 3.14159265358979323846
+
+typedef struct { double x, y, z; } v3;
+static v3 V(double x, double y, double z) { v3 r = {x, y, z}; return r; }
+static v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 vmul(v3 a, double s) { return V(a.x * s, a.y * s, a.z * s); }
+static v3 vmulv(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static double vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static v3 vnorm(v3 a) { return vmul(a, 1.0 / sqrt(vdot(a, a))); }
+
+typedef struct {
+    int is_tri;
+    v3 v0, e1, e2, n; /* triangle */
+    v3 c; double r;   /* sphere */
+    int bsdf;
+    v3 albedo, emission;
+    double ior;
+    int entity;
+} p_prim;
+
+typedef struct { v3 v0, e1, e2, n, emission; double area; } p_light;
+
+typedef struct {
+    int n_prims, n_lights;
+    p_prim* prims;
+    p_light* lights;
+} p_scene;
+
+static double clamp01(double v) { return v < 0 ? 0 : (v > 1 ? 1 : v); }
+static v3 fround(d3 p) { return V((double)(float)p.x, (double)(float)p.y, (double)(float)p.z); }
+
+static p_scene* build_prims(const o_scene* s) {
+    p_scene* ps = calloc(1, sizeof *ps);
+    int cap = 0;
+    for (int i = 0; i < s->n_ent; ++i) cap += s->ent[i].ntri + 1;
+    ps->prims = calloc((size_t)cap + 1, sizeof(p_prim));
+    ps->lights = calloc((size_t)cap + 1, sizeof(p_light));
+    for (int i = 0; i < s->n_ent; ++i) {
+        const o_entity* e = &s->ent[i];
+        if (!e->in_tree) continue;
+        p_prim base;
+        memset(&base, 0, sizeof base);
+        base.bsdf = (e->desc.bsdf < 0 || e->desc.bsdf > 3) ? 0 : e->desc.bsdf;
+        base.albedo = V(clamp01(e->desc.color[0]), clamp01(e->desc.color[1]), clamp01(e->desc.color[2]));
+        base.emission = V(e->desc.emission[0], e->desc.emission[1], e->desc.emission[2]);
+        base.ior = e->desc.ior > 0 ? e->desc.ior : 1.5;
+        base.entity = i;
+        if (e->kind == G19_IMP_SPHERE) {
+            p_prim p = base;
+            p.is_tri = 0;
+            p.c = fround(e->pos);
+            p.r = (double)e->radius;
+            ps->prims[ps->n_prims++] = p;
+            continue;
+        }
+        int from = (e->kind == G19_EXP_SPHERE) ? 1 : 0; /* the triangles REF mode tests */
+        for (int t = from; t < e->ntri; ++t) {
+            p_prim p = base;
+            p.is_tri = 1;
+            v3 a = fround(e->tris[t].p1), b = fround(e->tris[t].p2), c = fround(e->tris[t].p3);
+            p.v0 = a;
+            p.e1 = V((double)(float)(b.x - a.x), (double)(float)(b.y - a.y), (double)(float)(b.z - a.z));
+            p.e2 = V((double)(float)(c.x - a.x), (double)(float)(c.y - a.y), (double)(float)(c.z - a.z));
+            d3 q1 = e->tris[t].p1, q2 = e->tris[t].p2, q3 = e->tris[t].p3;
+            v3 n = vcross(V(q2.x - q1.x, q2.y - q1.y, q2.z - q1.z), V(q3.x - q1.x, q3.y - q1.y, q3.z - q1.z));
+            double len = sqrt(vdot(n, n));
+            if (len > 0) n = vmul(n, 1.0 / len);
+            p.n = fround((d3){n.x, n.y, n.z});
+            ps->prims[ps->n_prims++] = p;
+            if (p.bsdf == G19_BSDF_EMITTER) {
+                p_light l;
+                l.v0 = p.v0; l.e1 = p.e1; l.e2 = p.e2; l.n = p.n; l.emission = p.emission;
+                v3 cr = vcross(p.e1, p.e2);
+                l.area = (double)(0.5f * sqrtf((float)vdot(cr, cr)));
+                if (l.area > 0) ps->lights[ps->n_lights++] = l;
+            }
+        }
+    }
+    return ps;
+}
+
+static void free_prims(p_scene* ps) { free(ps->prims); free(ps->lights); free(ps); }
+
+/* Philox4x32-10, key = (seed, "2019") */
+static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t out[4]) {
+    uint32_t k1 = 0x32303139u;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static float u01f(uint32_t v) { return (float)(v >> 8) * (1.0f / 16777216.0f); }
+
+static double hit_prim(const p_prim* p, v3 o, v3 d, double tmin, double tmax) {
+    if (p->is_tri) {
+        v3 pv = vcross(d, p->e2);
+        double det = vdot(p->e1, pv);
+        if (fabs(det) < 1.0e-20) return -1;
+        double inv = 1.0 / det;
+        v3 tv = vsub(o, p->v0);
+        double u = vdot(tv, pv) * inv;
+        if (u < 0 || u > 1) return -1;
+        v3 qv = vcross(tv, p->e1);
+        double v = vdot(d, qv) * inv;
+        if (v < 0 || u + v > 1) return -1;
+        double t = vdot(p->e2, qv) * inv;
+        return (t > tmin && t < tmax) ? t : -1;
+    }
+    v3 oc = vsub(o, p->c);
+    double b = vdot(oc, d);
+    v3 l = vsub(oc, vmul(d, b));
+    double disc = p->r * p->r - vdot(l, l);
+    if (disc < 0) return -1;
+    double sq = sqrt(disc), t0 = -b - sq, t1 = -b + sq;
+    if (t0 > tmin && t0 < tmax) return t0;
+    if (t1 > tmin && t1 < tmax) return t1;
+    return -1;
+}
+
+static int closest(const p_scene* s, v3 o, v3 d, double* t_out) {
+    double best = DBL_MAX;
+    int bi = -1;
+    for (int i = 0; i < s->n_prims; ++i) {
+        double t = hit_prim(&s->prims[i], o, d, 0.0, best);
+        if (t >= 0) { best = t; bi = i; }
+    }
+    *t_out = best;
+    return bi;
+}
+static int occluded(const p_scene* s, v3 o, v3 d, double tmax) {
+    for (int i = 0; i < s->n_prims; ++i)
+        if (hit_prim(&s->prims[i], o, d, 0.0, tmax) >= 0) return 1;
+    return 0;
+}
+
+static void onb(v3 n, v3* t, v3* b) {
+    double s = copysign(1.0, n.z), a = -1.0 / (s + n.z), bb = n.x * n.y * a;
+    *t = V(1.0 + s * n.x * n.x * a, s * bb, -s * n.x);
+    *b = V(bb, s + n.y * n.y * a, -n.y);
+}
+
+typedef struct {
+    const p_scene* s;
+    v3 cpos, up, left, top_left;
+    int w, h, spp, max_depth, x0, y0, x1, y1, t, nthreads;
+    uint32_t seed;
+    float* radiance;
+    uint64_t extend, shadow;
+} job;
+
+static v3 trace_path(job* j, int x, int y, uint32_t sample) {
+    const p_scene* s = j->s;
+    uint32_t pixel = (uint32_t)y * (uint32_t)j->w + (uint32_t)x, r[4];
+    philox(pixel, sample, 0, 0, j->seed, r);
+    double fx = ((double)x + (double)u01f(r[0])) * 0.0002, fy = ((double)y + (double)u01f(r[1])) * 0.0002;
+    v3 o = j->cpos;
+    v3 d = vnorm(vsub(vsub(j->top_left, vmul(j->left, fx)), vmul(j->up, fy)));
+    v3 T = V(1, 1, 1), L = V(0, 0, 0);
+    int specular = 1;
+    for (int b = 0; b < j->max_depth; ++b) {
+        double t;
+        j->extend++;
+        int pi = closest(s, o, d, &t);
+        if (pi < 0) break;
+        const p_prim* pr = &s->prims[pi];
+        if (pr->bsdf == G19_BSDF_EMITTER) {
+            if (b == 0 || specular) L = vadd(L, vmulv(T, pr->emission));
+            break;
+        }
+        v3 p = vadd(o, vmul(d, t));
+        v3 ng = pr->is_tri ? pr->n : vmul(vsub(p, pr->c), 1.0 / pr->r);
+        int entering = vdot(ng, d) < 0;
+        v3 nf = entering ? ng : vmul(ng, -1);
+        philox(pixel, sample, (uint32_t)b, 1, j->seed, r);
+        v3 no, nd;
+        if (pr->bsdf == G19_BSDF_DIFFUSE) {
+            if (s->n_lights > 0) {
+                float pick = u01f(r[0]) * (float)s->n_lights; /* float product, like the device */
+                int li = (int)pick;
+                if (li > s->n_lights - 1) li = s->n_lights - 1;
+                double u1 = (double)(pick - (float)li), u2 = (double)u01f(r[1]);
+                const p_light* lt = &s->lights[li];
+                double su = sqrt(u1), b1 = su * (1.0 - u2), b2 = su * u2;
+                v3 yl = vadd(vadd(lt->v0, vmul(lt->e1, b1)), vmul(lt->e2, b2));
+                v3 wv = vsub(yl, p);
+                double dist2 = vdot(wv, wv), dist = sqrt(dist2);
+                wv = vmul(wv, 1.0 / dist);
+                double cs = vdot(nf, wv), cl = fabs(vdot(lt->n, wv));
+                if (cs > 0 && cl > 0 && dist > 2.0 * RAY_EPS) {
+                    j->shadow++;
+                    if (!occluded(s, vadd(p, vmul(nf, RAY_EPS)), wv, dist - 2.0 * RAY_EPS)) {
+                        double g = cs * cl * lt->area / (dist2 * (1.0 / (double)s->n_lights)) * (1.0 / PI_D);
+                        L = vadd(L, vmul(vmulv(vmulv(T, pr->albedo), lt->emission), g));
+                    }
+                }
+            }
+            double u3 = (double)u01f(r[2]), u4 = (double)u01f(r[3]);
+            double rr = sqrt(u3), phi = 2.0 * PI_D * u4;
+            v3 tx, ty;
+            onb(nf, &tx, &ty);
+            nd = vnorm(vadd(vadd(vmul(tx, rr * cos(phi)), vmul(ty, rr * sin(phi))), vmul(nf, sqrt(fmax(0.0, 1.0 - u3)))));
+            no = vadd(p, vmul(nf, RAY_EPS));
+            T = vmulv(T, pr->albedo);
+            specular = 0;
+        } else if (pr->bsdf == G19_BSDF_MIRROR) {
+            nd = vnorm(vsub(d, vmul(nf, 2.0 * vdot(d, nf))));
+            no = vadd(p, vmul(nf, RAY_EPS));
+            T = vmulv(T, pr->albedo);
+            specular = 1;
+        } else {
+            double etai = entering ? 1.0 : pr->ior, etat = entering ? pr->ior : 1.0, eta = etai / etat;
+            double cosi = fmin(1.0, -vdot(d, nf));
+            double sin2t = eta * eta * fmax(0.0, 1.0 - cosi * cosi), F = 1.0, cost = 0.0;
+            if (sin2t < 1.0) {
+                cost = sqrt(1.0 - sin2t);
+                double rs = (etai * cosi - etat * cost) / (etai * cosi + etat * cost);
+                double rp = (etai * cost - etat * cosi) / (etai * cost + etat * cosi);
+                F = 0.5 * (rs * rs + rp * rp);
+            }
+            if ((double)u01f(r[0]) < F) {
+                nd = vnorm(vadd(d, vmul(nf, 2.0 * cosi)));
+                no = vadd(p, vmul(nf, RAY_EPS));
+            } else {
+                nd = vnorm(vadd(vmul(d, eta), vmul(nf, eta * cosi - cost)));
+                no = vsub(p, vmul(nf, RAY_EPS));
+            }
+            T = vmulv(T, pr->albedo);
+            specular = 1;
+        }
+        if (!(T.x > 0 || T.y > 0 || T.z > 0)) break;
+        o = no;
+        d = nd;
+    }
+    return L;
+}
+
+static void* rows(void* arg) {
+    job* j = arg;
+    for (int y = j->y0 + j->t; y < j->y1; y += j->nthreads) {
+        for (int x = j->x0; x < j->x1; ++x) {
+            v3 sum = V(0, 0, 0);
+            for (int sidx = 0; sidx < j->spp; ++sidx) sum = vadd(sum, trace_path(j, x, y, (uint32_t)sidx));
+            size_t i = ((size_t)y * (size_t)j->w + (size_t)x) * 3;
+            j->radiance[i] = (float)(sum.x / j->spp);
+            j->radiance[i + 1] = (float)(sum.y / j->spp);
+            j->radiance[i + 2] = (float)(sum.z / j->spp);
+        }
+    }
+    return NULL;
+}
+
+/* Renders the window [x0,x1) x [y0,y1) of a w x h frame; pixels outside are left
+ * untouched. segs[0] = extend segments, segs[1] = shadow segments. */
+int g19o_path_render(void* scene, const g19_camera* cam, int w, int h, int spp, int max_depth, uint32_t seed, int x0,
+                     int y0, int x1, int y1, float* radiance, uint64_t* segs, int nthreads) {
+    const o_scene* os = scene;
+    p_scene* ps = build_prims(os);
+    /* camera basis: same expressions as ref_restate.c g19o_trace (raytracer.h:26-30) */
+    v3 cpos = V(cam->pos[0], cam->pos[1], cam->pos[2]);
+    v3 up = V(0, 0, 1.0);
+    v3 fwd = vsub(V(cam->look_at[0], cam->look_at[1], cam->look_at[2]), cpos);
+    {
+        double tx = fwd.x * fwd.x, ty = fwd.y * fwd.y, tz = fwd.z * fwd.z;
+        fwd = vmul(fwd, 1.0 / sqrt(tx + ty + tz));
+    }
+    v3 left = V(up.y * fwd.z - fwd.y * up.z, up.z * fwd.x - fwd.z * up.x, up.x * fwd.y - fwd.x * up.y);
+    {
+        double tx = left.x * left.x, ty = left.y * left.y, tz = left.z * left.z;
+        left = vmul(left, 1.0 / sqrt(tx + ty + tz));
+    }
+    v3 t = vadd(cpos, V(cam->focal * fwd.x, cam->focal * fwd.y, cam->focal * fwd.z));
+    t = vadd(t, vmul(vmul(vmul(left, (double)w), 0.5), 0.0002));
+    t = vadd(t, vmul(vmul(vmul(up, (double)w), 0.5), 0.0002));
+    v3 top_left = vsub(t, cpos);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    static job jobs[256];
+    pthread_t th[256];
+    for (int k = 0; k < nthreads; ++k) {
+        job j = {ps, cpos, up, left, top_left, w, h, spp, max_depth, x0, y0, x1, y1, k, nthreads, seed, radiance, 0, 0};
+        jobs[k] = j;
+    }
+    if (nthreads == 1) rows(&jobs[0]);
+    else {
+        for (int k = 0; k < nthreads; ++k) pthread_create(&th[k], NULL, rows, &jobs[k]);
+        for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+    }
+    if (segs) {
+        segs[0] = segs[1] = 0;
+        for (int k = 0; k < nthreads; ++k) { segs[0] += jobs[k].extend; segs[1] += jobs[k].shadow; }
+    }
+    free_prims(ps);
+    return 0;
+}

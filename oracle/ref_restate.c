@@ -621,8 +621,9 @@ int g19o_scene_add(void* h, const g19_entity_desc* d) {
     }
     if (entity_build(&s->ent[s->n_ent], d) != 0) return -1;
     int id = s->n_ent++;
-    const o_entity* e = &s->ent[id];
-    if (bbox_overlap(s->root->bmin, s->root->bmax, e->bbmin, e->bbmax)) node_push(s, s->root, id); /* octree.h:20-30 */
+    o_entity* e = &s->ent[id];
+    e->in_tree = bbox_overlap(s->root->bmin, s->root->bmax, e->bbmin, e->bbmax);
+    if (e->in_tree) node_push(s, s->root, id); /* octree.h:20-30 */
     return id;
 }
 

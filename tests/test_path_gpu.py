@@ -1,0 +1,142 @@
+"""G19_MODE_PATH (wavefront path tracer) on the GPU against the FP64 brute-force oracle.
+
+The reference has no bounce transport, so the oracle here is this
+repo's own definition (oracle/path_oracle.c). Tolerances:
+  (i)  same seed: relRMSE = sqrt(mean((gpu-cpu)^2)) / mean(cpu) <= 1e-2 on linear radiance --
+       FP32 vs FP64 paths only part ways at discontinuities;
+  (ii) different seeds: relRMSE(gpu, cpu') <= 1.5 x relRMSE(cpu, cpu').
+Everything integer is exact: segment counts may differ only by the handful of paths that
+diverge at a discontinuity (<= 0.1 %), and the GPU result is bit-identical across runs,
+pass sizes and tile sharding.
+"""
+import numpy as np
+import pytest
+
+from oracle import binding
+from util import mirror, rel_rmse
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(g19, abi, sc, cam, light, w, h, **kw):
+    rt = g19.RayTracer(cam, light)
+    rt.setScene(sc)
+    rt.start()
+    out = rt.run(w, h, mode=abi.MODE_PATH, want=("rgb", "radiance"), **kw)
+    return rt, out, rt.stats()
+
+
+@pytest.mark.parametrize("which,depth,spp", [("CORNELL", 5, 16), ("CORNELL_GLASS", 12, 16)])
+def test_same_seed_matches_oracle(g19, abi, oracle, which, depth, spp):
+    w, h = 96, 54
+    sc, cam, light = g19.Octree.builtin(getattr(abi, "SCENE_" + which), w=w, h=h)
+    rt, got, st = _gpu(g19, abi, sc, cam, light, w, h, spp=spp, max_depth=depth, seed=7)
+    exp, segs = binding.path_render(mirror(oracle, sc), cam, w, h, spp, depth, seed=7)
+    assert exp.mean() > 0.05
+    err = rel_rmse(got["radiance"], exp)
+    print("%s: same-seed relRMSE %.3e, segments gpu %d/%d cpu %d/%d" % (which, err, st.extend_segments,
+                                                                         st.shadow_segments, segs[0], segs[1]))
+    assert err <= 1e-2
+    assert st.samples == w * h * spp
+    assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
+    assert abs(int(st.shadow_segments) - segs[1]) <= 1e-3 * segs[1] + 2
+    # RGB888 is the truncated clamp of the radiance (Image::setPixel)
+    q = (255.0 * np.clip(got["radiance"], 0, 1)).astype(np.int32)
+    assert np.abs(q - got["rgb"].astype(np.int32)).max() <= 1
+
+
+def test_independent_seeds_statistical(g19, abi, oracle):
+    w, h, spp, depth = 64, 36, 64, 5
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h)
+    rt, got, st = _gpu(g19, abi, sc, cam, light, w, h, spp=spp, max_depth=depth, seed=1)
+    chk = mirror(oracle, sc)
+    a, _ = binding.path_render(chk, cam, w, h, spp, depth, seed=2)
+    b, _ = binding.path_render(chk, cam, w, h, spp, depth, seed=3)
+    base = rel_rmse(a, b)
+    err = rel_rmse(got["radiance"], b)
+    print("independent seeds: gpu-vs-cpu %.3f, cpu-vs-cpu %.3f" % (err, base))
+    assert err <= 1.5 * base
+
+
+def test_heightfield_matches_oracle(g19, abi, oracle):
+    w, h, spp, depth = 64, 36, 4, 4
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_HEIGHTFIELD, n=24, w=w, h=h)
+    rt, got, st = _gpu(g19, abi, sc, cam, light, w, h, spp=spp, max_depth=depth, seed=3)
+    exp, segs = binding.path_render(mirror(oracle, sc), cam, w, h, spp, depth, seed=3)
+    assert exp.mean() > 0.01
+    err = rel_rmse(got["radiance"], exp)
+    print("heightfield: same-seed relRMSE %.3e segments %d vs %d" % (err, st.extend_segments, segs[0]))
+    assert err <= 1e-2
+    assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
+
+
+def test_large_octree_agrees_with_small_leaves(g19, abi, oracle):
+    """A deeper linear octree (n=96: 18 432 triangles) still finds the nearest hit: depth-1 image vs oracle."""
+    w, h = 128, 72
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_HEIGHTFIELD, n=96, w=w, h=h)
+    rt, got, st = _gpu(g19, abi, sc, cam, light, w, h, spp=2, max_depth=2, seed=11)
+    exp, segs = binding.path_render(mirror(oracle, sc), cam, w, h, 2, 2, seed=11)
+    assert rel_rmse(got["radiance"], exp) <= 1e-2
+    assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
+
+
+def test_deterministic_and_pass_invariant(g19, abi):
+    w, h = 100, 70  # ragged tiles
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL_GLASS, w=w, h=h)
+    rt, a, sa = _gpu(g19, abi, sc, cam, light, w, h, spp=12, max_depth=8, seed=5)
+    b = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=12, max_depth=8, seed=5)
+    assert a["radiance"].tobytes() == b["radiance"].tobytes()
+    for spp_pass in (1, 5, 12):
+        c = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=12, max_depth=8, seed=5, spp_per_pass=spp_pass)
+        assert a["radiance"].tobytes() == c["radiance"].tobytes(), spp_pass
+    d = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=12, max_depth=8, seed=6)
+    assert a["radiance"].tobytes() != d["radiance"].tobytes()
+
+
+def test_tile_sharding_bit_identical(g19, abi):
+    w, h = 130, 75
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h)
+    rt, one, st1 = _gpu(g19, abi, sc, cam, light, w, h, spp=8, max_depth=5, seed=9)
+    out = {"radiance": np.zeros((h, w, 3), np.float32), "rgb": np.zeros((h, w, 3), np.uint8)}
+    total = 0
+    for rank in range(4):
+        rt.run(w, h, mode=abi.MODE_PATH, want=("rgb", "radiance"), out=out, spp=8, max_depth=5, seed=9, rank=rank,
+               world=4)
+        total += rt.stats().samples
+    assert total == st1.samples == w * h * 8
+    assert out["radiance"].tobytes() == one["radiance"].tobytes()
+    assert np.array_equal(out["rgb"], one["rgb"])
+
+
+def test_edge_cases(g19, abi):
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL, w=64, h=64)
+    rt = g19.RayTracer(cam, light)
+    rt.setScene(sc)
+    rt.start()
+    # depth 1: only directly visible emitters contribute
+    d1 = rt.run(64, 64, mode=abi.MODE_PATH, want=("radiance",), spp=4, max_depth=1)["radiance"]
+    assert ((d1 == 0) | (d1 == 17.0)).all() or np.isclose(d1[d1 > 0].max(), 17.0)
+    with pytest.raises(g19.G19Error):
+        rt.run(64, 64, mode=abi.MODE_PATH, spp=0, max_depth=5)
+    with pytest.raises(g19.G19Error):
+        rt.run(64, 64, mode=abi.MODE_PATH, spp=1, max_depth=0)
+    # empty scene: black
+    empty = g19.Octree((-1,) * 3, (1,) * 3)
+    rt.setScene(empty)
+    z = rt.run(40, 24, mode=abi.MODE_PATH, want=("radiance",), spp=2, max_depth=3)["radiance"]
+    assert (z == 0).all()
+
+
+def test_cancel_between_passes(g19, abi):
+    import threading
+    w, h = 256, 256
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h)
+    rt = g19.RayTracer(cam, light)
+    rt.setScene(sc)
+    rt.start()
+    t = threading.Timer(0.05, rt.stop)  # the GUI thread calling stop() (viewer.h:29-34)
+    t.start()
+    rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=4096, max_depth=5, spp_per_pass=1)
+    t.join()
+    assert rt.stats().samples < w * h * 4096
+    assert 0.0 <= rt.progress() <= 1.0
