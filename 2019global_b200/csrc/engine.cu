@@ -243,7 +243,8 @@ struct ClassTimer { // CUDA-event timing of one kernel class (params.profile)
 };
 
 int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p, const TileMap& map,
-               uint8_t* d_rgb, int32_t* d_ids, float* d_rad, cudaStream_t s) {
+               uint8_t* d_rgb, int32_t* d_ids, float* d_rad, uint8_t* t_rgb, int32_t* t_ids, float* t_rad,
+               cudaStream_t s) {
     RefCamera rc = make_camera(*cam, light, p->width);
     size_t n = size_t(map.n_local_pix);
     G19_CUDA(ctx, ctx->ids_l.ensure(n * sizeof(int32_t)));
@@ -271,6 +272,9 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
                   d_rad ? ctx->colour_l.as<float>() : nullptr, d_rgb, d_ids, d_rad, s);
     t.end(G19_K_OTHER, 1);
     G19_CUDA(ctx, cudaGetLastError());
+    if (t_rgb) G19_CUDA(ctx, cudaMemcpyAsync(t_rgb, ctx->rgb_l.p, n * 3, cudaMemcpyDeviceToDevice, s));
+    if (t_ids) G19_CUDA(ctx, cudaMemcpyAsync(t_ids, ctx->ids_l.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (t_rad) G19_CUDA(ctx, cudaMemcpyAsync(t_rad, ctx->colour_l.p, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ctx->stats.samples = 0;
     if (p->profile) {
         unsigned long long h[2] = {0, 0};
@@ -384,8 +388,9 @@ int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene) {
     return G19_OK;
 }
 
-int g19_render_device(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p,
-                      uint8_t* d_rgb, int32_t* d_ids, float* d_rad, void* stream) {
+static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p,
+                      uint8_t* d_rgb, int32_t* d_ids, float* d_rad, uint8_t* t_rgb, int32_t* t_ids, float* t_rad,
+                      void* stream) {
     int rc = check_params(ctx, cam, p);
     if (rc != G19_OK) return rc;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -396,7 +401,7 @@ int g19_render_device(g19_ctx* ctx, const g19_camera* cam, const double light[3]
     TileMap map = make_tile_map(p->width, p->height, p->rank, p->world);
     G19_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     if (p->mode == G19_MODE_REF) {
-        rc = render_ref(ctx, cam, light, p, map, d_rgb, d_ids, d_rad, s);
+        rc = render_ref(ctx, cam, light, p, map, d_rgb, d_ids, d_rad, t_rgb, t_ids, t_rad, s);
     } else {
         RefCamera rc64 = make_camera(*cam, light, p->width);
         PathRenderArgs a;
@@ -406,6 +411,8 @@ int g19_render_device(g19_ctx* ctx, const g19_camera* cam, const double light[3]
         a.d_rgb = d_rgb;
         a.d_rad = d_rad;
         a.d_ids = d_ids;
+        a.t_rgb = t_rgb;
+        a.t_rad = t_rad;
         a.stream = s;
         a.sm_count = ctx->sm_count;
         a.cancel = &ctx->cancel;
@@ -421,6 +428,31 @@ int g19_render_device(g19_ctx* ctx, const g19_camera* cam, const double light[3]
     ctx->stats_pending = true;
     ctx->progress_milli.store(1000);
     return rc;
+}
+
+int g19_render_device(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p,
+                      uint8_t* d_rgb, int32_t* d_ids, float* d_rad, void* stream) {
+    return render_any(ctx, cam, light, p, d_rgb, d_ids, d_rad, nullptr, nullptr, nullptr, stream);
+}
+
+int64_t g19_tile_pixels(int w, int h, int rank, int world) {
+    if (w < 0 || h < 0 || world < 1 || rank < 0 || rank >= world) return -1;
+    return make_tile_map(w, h, rank, world).n_local_pix;
+}
+
+int g19_render_tiles_device(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p,
+                            uint8_t* t_rgb, int32_t* t_ids, float* t_rad, void* stream) {
+    return render_any(ctx, cam, light, p, nullptr, nullptr, nullptr, t_rgb, t_ids, t_rad, stream);
+}
+
+int g19_untile_device(g19_ctx* ctx, int w, int h, int rank, int world, const uint8_t* t_rgb, const int32_t* t_ids,
+                      const float* t_rad, uint8_t* d_rgb, int32_t* d_ids, float* d_rad, void* stream) {
+    if (!ctx || w < 0 || h < 0 || world < 1 || rank < 0 || rank >= world) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    launch_untile(make_tile_map(w, h, rank, world), t_rgb, t_ids, t_rad, d_rgb, d_ids, d_rad,
+                  static_cast<cudaStream_t>(stream));
+    G19_CUDA(ctx, cudaGetLastError());
+    return G19_OK;
 }
 
 int g19_render(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p, uint8_t* rgb,

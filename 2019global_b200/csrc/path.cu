@@ -444,6 +444,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
                   a.d_rad ? static_cast<float*>(w.rad_l.p) : nullptr, a.d_rgb, nullptr, a.d_rad, s);
     clk.end(G19_K_OTHER);
     stats.class_launches[G19_K_OTHER] += 2;
+    if (a.t_rad) PATH_CUDA(cudaMemcpyAsync(a.t_rad, w.rad_l.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (a.t_rgb) PATH_CUDA(cudaMemcpyAsync(a.t_rgb, w.rgb_l.p, npix * 3, cudaMemcpyDeviceToDevice, s));
     PATH_CUDA(cudaGetLastError());
     for (int k = 0; k < 8; ++k) stats.kernel_launches += stats.class_launches[k];
     // owned in-frame pixels
@@ -470,6 +472,9 @@ int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
     }
     stats.extend_segments = h[0] + stats.samples; // bounce 0 has no queue: one segment per camera path
     stats.shadow_segments = h[1];
+    stats.shade_calls = h[2];
+    stats.shade_calls_first = h[3];
+    stats.lit_samples = h[4];
     for (int i = 0; i + 1 < w.used_events; i += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, w.events[i], w.events[i + 1]) == cudaSuccess) stats.class_ms[w.event_class[i / 2]] += ms;

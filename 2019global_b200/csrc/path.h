@@ -84,9 +84,11 @@ struct PathRenderArgs {
     RefCamera cam;
     g19_params params;
     TileMap map;
-    uint8_t* d_rgb;
+    uint8_t* d_rgb;   // full-frame outputs (nullable)
     float* d_rad;
     int32_t* d_ids;
+    uint8_t* t_rgb;   // compact local-pixel outputs (nullable)
+    float* t_rad;
     cudaStream_t stream;
     int sm_count;
     std::atomic<int>* cancel;

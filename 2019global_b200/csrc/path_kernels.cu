@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 2) shade_kernel(const PassArgs a, co
     uint32_t* const queues[1] = {a.q[(bounce + 1) & 1]};
     uint32_t* const counters[1] = {a.counts + (bounce + 1) * 4 + Q_EXTEND};
     const bool more = bounce + 1 < a.max_depth;
-    unsigned shadow_rays = 0;
+    unsigned shadow_rays = 0, lit = 0;
     const uint32_t stride = gridDim.x * kThreads;
     for (uint32_t base = blockIdx.x * kThreads; base < n; base += stride) {
         const uint32_t q = base + threadIdx.x;
@@ -491,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 2) shade_kernel(const PassArgs a, co
                         ++shadow_rays;
                         bool blocked = traverse<true>(S, stack, p + nf * kRayEps, w, 0.0f, dist - 2.0f * kRayEps, tt, pp);
                         if (!blocked) {
+                            ++lit;
                             float gterm = cs * cl * lt.area / (dist2 * lt.pdf_pick) * (1.0f / kPi);
                             add_radiance(a, slot, f3(T.x * albedo.x * lt.emission[0] * gterm,
                                                      T.y * albedo.y * lt.emission[1] * gterm,
@@ -546,8 +547,14 @@ __global__ void __launch_bounds__(kThreads, 2) shade_kernel(const PassArgs a, co
         block_append<1>(app_sm, kind, slot, queues, counters);
     }
     if (KIND == Q_DIFFUSE) {
-        for (int off = 16; off > 0; off >>= 1) shadow_rays += __shfl_xor_sync(0xffffffffu, shadow_rays, off);
-        if ((threadIdx.x & 31) == 0 && shadow_rays) atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
+        for (int off = 16; off > 0; off >>= 1) {
+            shadow_rays += __shfl_xor_sync(0xffffffffu, shadow_rays, off);
+            lit += __shfl_xor_sync(0xffffffffu, lit, off);
+        }
+        if ((threadIdx.x & 31) == 0 && shadow_rays) {
+            atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
+            atomicAdd(a.totals + 4, (unsigned long long)lit);
+        }
     }
 }
 
@@ -574,6 +581,10 @@ __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) 
             uint32_t v = a.counts[i];
             if (v) {
                 if ((i & 3) == Q_EXTEND) atomicAdd(a.totals + 0, (unsigned long long)v);
+                else {
+                    atomicAdd(a.totals + 2, (unsigned long long)v);
+                    if (i < 4) atomicAdd(a.totals + 3, (unsigned long long)v);
+                }
                 a.counts[i] = 0;
             }
         }

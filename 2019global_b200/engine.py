@@ -274,3 +274,28 @@ class RayTracer:
         n = C.c_int(0)
         self._check(self._L.g19_probe_candidates(self.h, abi.d3(o), abi.d3(d), _ptr(out), max_out, C.byref(n)))
         return out[:min(n.value, max_out)].copy()
+
+
+def tile_pixels(w, h, rank, world):
+    """Entries in a rank's compact local-pixel arrays (g19_tile_pixels)."""
+    L = lib()
+    L.g19_tile_pixels.restype = C.c_int64
+    return int(L.g19_tile_pixels(w, h, rank, world))
+
+
+def _render_tiles(self, p, t_rgb=0, t_ids=0, t_rad=0, stream=0):
+    """Render this rank's tiles into compact device arrays (the payload sent to rank 0)."""
+    return self._check(self._L.g19_render_tiles_device(self.h, C.byref(self.camera), abi.d3(self.light), C.byref(p),
+                                                       C.c_void_p(t_rgb), C.c_void_p(t_ids), C.c_void_p(t_rad),
+                                                       C.c_void_p(stream)), allow=(abi.ERR_CANCELLED,))
+
+
+def _untile(self, w, h, rank, world, t_rgb=0, t_ids=0, t_rad=0, d_rgb=0, d_ids=0, d_rad=0, stream=0):
+    """Scatter rank `rank`'s compact arrays into the full frame (device pointers)."""
+    return self._check(self._L.g19_untile_device(self.h, w, h, rank, world, C.c_void_p(t_rgb), C.c_void_p(t_ids),
+                                                 C.c_void_p(t_rad), C.c_void_p(d_rgb), C.c_void_p(d_ids),
+                                                 C.c_void_p(d_rad), C.c_void_p(stream)))
+
+
+RayTracer.render_tiles = _render_tiles
+RayTracer.untile = _untile

@@ -161,6 +161,9 @@ typedef struct g19_stats {
     double class_ms[8];
     uint64_t class_launches[8];
     uint64_t node_tests, prim_tests; /* REF mode, only when profile           */
+    uint64_t shade_calls;     /* PATH: surface interactions shaded            */
+    uint64_t shade_calls_first; /* ... of which on the camera segment         */
+    uint64_t lit_samples;     /* PATH: unoccluded next-event samples          */
 } g19_stats;
 
 enum { G19_K_EXTEND = 0, G19_K_SHADE = 1, G19_K_SHADOW = 2, G19_K_ACCUM = 3,
@@ -193,6 +196,26 @@ int g19_render_device(g19_ctx* ctx, const g19_camera* camera, const double light
                       const g19_params* params, uint8_t* d_rgb888, int32_t* d_hit_id,
                       float* d_radiance, void* stream);
 int g19_get_stats(g19_ctx* ctx, g19_stats* out);
+
+/* Multi-GPU: one process and one g19_ctx per GPU, image
+ * tiles interleaved by params->rank/world. A rank's pixels form a compact
+ * "local pixel" array: local tile j is global tile j*world+rank (row-major
+ * tile order), 1024 pixels per tile, row-major inside the tile, out-of-frame
+ * positions of edge tiles included as padding.
+ *   g19_tile_pixels          entries in that array for (w,h,rank,world)
+ *   g19_render_tiles_device  like g19_render_device, but fills the compact
+ *                            arrays (rgb: 3 B, ids: int32, rad: 3 floats per
+ *                            entry) -- the payload a rank sends to rank 0
+ *   g19_untile_device        scatters one rank's compact arrays into the
+ *                            full row-major frame (what rank 0 runs on each
+ *                            received payload; other pixels untouched)      */
+int64_t g19_tile_pixels(int width, int height, int rank, int world);
+int g19_render_tiles_device(g19_ctx* ctx, const g19_camera* camera, const double light[3],
+                            const g19_params* params, uint8_t* d_tile_rgb, int32_t* d_tile_ids,
+                            float* d_tile_rad, void* stream);
+int g19_untile_device(g19_ctx* ctx, int width, int height, int rank, int world,
+                      const uint8_t* d_tile_rgb, const int32_t* d_tile_ids, const float* d_tile_rad,
+                      uint8_t* d_rgb888, int32_t* d_hit_id, float* d_radiance, void* stream);
 
 /* RayTracer::stop()/running()                              raytracer.h:89-91 */
 int g19_cancel(g19_ctx* ctx);

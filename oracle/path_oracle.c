@@ -185,6 +185,7 @@ typedef struct {
     uint32_t seed;
     float* radiance;
     uint64_t extend, shadow;
+    char pad[128]; /* keep each thread's counters on their own cache lines */
 } job;
 
 static v3 trace_path(job* j, int x, int y, uint32_t sample) {
@@ -274,7 +275,9 @@ static v3 trace_path(job* j, int x, int y, uint32_t sample) {
 }
 
 static void* rows(void* arg) {
-    job* j = arg;
+    job* shared = arg;
+    job local = *shared; /* thread-private copy: the segment counters are hot */
+    job* j = &local;
     for (int y = j->y0 + j->t; y < j->y1; y += j->nthreads) {
         for (int x = j->x0; x < j->x1; ++x) {
             v3 sum = V(0, 0, 0);
@@ -285,6 +288,8 @@ static void* rows(void* arg) {
             j->radiance[i + 2] = (float)(sum.z / j->spp);
         }
     }
+    shared->extend = local.extend;
+    shared->shadow = local.shadow;
     return NULL;
 }
 

@@ -1,0 +1,103 @@
+"""Host side of the product (scene.cpp, builtin_scenes.cpp, C-ABI surface). No GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from util import mirror, zoo
+
+
+def test_library_exports_every_declared_symbol(g19):
+    L = g19.lib()
+    header = open(os.path.join(os.path.dirname(g19.LIB_PATH), "..", "include", "g19.h")).read()
+    declared = sorted(set(re.findall(r"\b(g19_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), "include/g19.h declares %s but the library does not export it" % name
+    assert set(g19.EXPORTS) <= set(declared)
+
+
+def test_abi_struct_sizes(g19, abi):
+    # mirrors of include/g19.h: g19_entity_desc, g19_camera, g19_params
+    assert ctypes.sizeof(abi.EntityDesc) == 8 + 72 + 16 + 24 + 12 + 4
+    assert ctypes.sizeof(abi.Camera) == 56
+    assert ctypes.sizeof(abi.Params) == 40
+
+
+def test_entity_geometry_matches_oracle_bits(g19, oracle):
+    z = zoo(g19)
+    chk = mirror(oracle, z)
+    for i in range(len(z)):
+        assert z.bbox(i).tobytes() == chk.bbox(i).tobytes(), i
+        assert z.triangles(i).tobytes() == chk.triangles(i).tobytes(), i
+    # a few randomised constructor arguments per composite kind
+    rng = np.random.default_rng(3)
+    sc = g19.Octree((-50,) * 3, (50,) * 3)
+    for _ in range(10):
+        p = rng.uniform(-3, 3, 3)
+        sc.push_back(g19.ExpQuad(p, *rng.uniform(0.5, 4, 2), rng.uniform(0.1, 3.0), (1, 0, 0)))
+        sc.push_back(g19.ExpCube(p, *rng.uniform(0.5, 4, 3), (1, 0, 0)))
+        sc.push_back(g19.ExpCone(p, rng.uniform(-1, 1, 3), *rng.uniform(0.5, 4, 2), (1, 0, 0)))
+        sc.push_back(g19.ExpSphere(p, rng.uniform(0.5, 3), (1, 0, 0)))
+        sc.push_back(g19.ImpTriangle(*rng.uniform(-4, 4, (3, 3))))
+    chk = mirror(oracle, sc)
+    for i in range(len(sc)):
+        assert sc.bbox(i).tobytes() == chk.bbox(i).tobytes(), i
+        assert sc.triangles(i).tobytes() == chk.triangles(i).tobytes(), i
+
+
+def test_default_scene_is_main_cpp_literal(g19, abi):
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_DEFAULT)
+    kinds = [d.kind for d in sc.entities()]
+    assert kinds == [abi.EXP_QUAD, abi.IMP_SPHERE, abi.IMP_SPHERE]  # main.cpp:46-48 push order
+    assert tuple(cam.pos) == (-10, 0, 0) and tuple(cam.look_at) == (1, 0, 0) and cam.focal == 0.1
+    assert light == (-10, 10, 10)
+    # SURVEY hard part 5: the sphere's bbox is centred on the ORIGIN
+    assert sc.bbox(1).tolist() == [-2, -2, -2, 2, 2, 2]
+
+
+def test_builtin_scene_shapes(g19, abi):
+    sc, cam, _ = g19.Octree.builtin(abi.SCENE_CORNELL, w=1920, h=1080)
+    assert len(sc) == 14
+    bs = [d.bsdf for d in sc.entities()]
+    assert bs.count(abi.BSDF_EMITTER) == 2 and bs[-2:] == [abi.BSDF_DIFFUSE] * 2
+    gl, _, _ = g19.Octree.builtin(abi.SCENE_CORNELL_GLASS, w=64, h=64)
+    assert [d.bsdf for d in gl.entities()][-2:] == [abi.BSDF_MIRROR, abi.BSDF_GLASS]
+    # pitch that re-centres the 16:9 frame: focal*sin(theta) = (w-h)/2 * 0.0002
+    f = np.array(cam.look_at) - np.array(cam.pos)
+    assert np.isclose(-f[2] * cam.focal, (1920 - 1080) / 2 * 0.0002)
+    hf, _, _ = g19.Octree.builtin(abi.SCENE_HEIGHTFIELD, n=16, w=64, h=64)
+    assert len(hf) == 2 * 16 * 16 + 2
+    with pytest.raises(g19.G19Error):
+        g19.Octree.builtin(abi.SCENE_HEIGHTFIELD, n=0)
+
+
+def test_rejected_entity_is_numbered_but_absent(g19, abi):
+    sc = g19.Octree((-1,) * 3, (1,) * 3)
+    i0, ok0 = sc.push_back(g19.ImpTriangle((5, 5, 5), (6, 5, 5), (5, 6, 5)))
+    i1, ok1 = sc.push_back(g19.ImpSphere((9, 9, 9), 0.5, (1, 1, 1)))  # bbox is origin-centred: accepted!
+    assert (i0, ok0) == (0, False) and (i1, ok1) == (1, True)
+    assert len(sc) == 2
+
+
+def test_tile_map_matches_c_abi(g19):
+    tiles = __import__("importlib").import_module("2019global_b200.tiles")
+    for (w, h) in ((1920, 1080), (333, 217), (32, 32), (1, 1), (3840, 2160)):
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(w * h, np.int32)
+            for r in range(world):
+                g = tiles.local_pixels(w, h, r, world)
+                assert g.shape[0] == g19.engine.tile_pixels(w, h, r, world)
+                seen[g[g >= 0]] += 1
+            assert (seen == 1).all()  # every pixel owned exactly once
+
+
+def test_no_gpu_fails_loudly(g19):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(g19.G19Error) as e:
+        g19.RayTracer(g19.Camera((-10, 0, 0)), (0, 0, 0))
+    assert e.value.code == g19.abi.ERR_NO_DEVICE and "no CPU path" in str(e.value)
