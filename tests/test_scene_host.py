@@ -12,7 +12,7 @@ from util import mirror, zoo
 def test_library_exports_every_declared_symbol(g19):
     L = g19.lib()
     header = open(os.path.join(os.path.dirname(g19.LIB_PATH), "..", "include", "g19.h")).read()
-    declared = sorted(set(re.findall(r"\b(g19_[a-z_0-9]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"^(?:int|void|int64_t|const char\*)\s+(g19_[a-z_0-9]+)\s*\(", header, re.M)))
     assert len(declared) >= 20
     for name in declared:
         assert hasattr(L, name), "include/g19.h declares %s but the library does not export it" % name
