@@ -5,7 +5,8 @@
 Per translation unit:
   scene.cpp, builtin_scenes.cpp   host C++, -ffp-contract=off (bit-exact geometry)
   ref_kernels.cu                  -fmad=false (bit-exact reference arithmetic)
-  path_kernels.cu, path.cu, engine.cu
+  path_kernels.cu                 --use_fast_math (FP32 tracer: MUFU rcp/rsqrt/sin/cos)
+  path.cu, engine.cu
 All with -gencode arch=compute_100a,code=sm_100a -lineinfo. nvcc cross-compiles
 without a GPU; the resulting .so travels to the GPU box with the snapshot.
 """
@@ -26,7 +27,7 @@ UNITS = [
     ("scene.cpp", []),
     ("builtin_scenes.cpp", []),
     ("ref_kernels.cu", ["-fmad=false", "-Xptxas", "-v"]),
-    ("path_kernels.cu", ["-Xptxas", "-v"]),
+    ("path_kernels.cu", ["--use_fast_math", "-Xptxas", "-v"]),
     ("path.cu", []),
     ("engine.cu", []),
 ]

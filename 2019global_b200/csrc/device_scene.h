@@ -45,11 +45,14 @@ struct alignas(64) RefEntityD {
 static_assert(sizeof(RefEntityD) == 192, "RefEntityD layout");
 
 // ---- PATH view --------------------------------------------------------------
-// Hot intersection record, 48 B = 3 x float4:
-//   triangle: q0 = (v0.xyz, e1.x) q1 = (e1.y, e1.z, e2.x, e2.y) q2 = (e2.z, _, _, kind=1)
-//   sphere  : q0 = (c.xyz, r)     q1 = unused                  q2 = (_, _, _, kind=0)
+// Hot intersection record, 64 B = 4 x float4 (one line per two primitives):
+//   triangle: rows 0..2 = the affine map world -> (b1, b2, h): barycentric coordinates of the
+//             foot point and the height above the plane in units of the normal, so that a ray
+//             o + t d hits at t = -h(o)/h'(d) with (u,v) = (b1,b2)(o) + t (b1,b2)'(d)
+//   sphere  : row 0 = (centre.xyz, radius)
+//   row 3   = (material index bits, bsdf bits, kind: 1 triangle / 0 sphere, 0)
 struct alignas(16) PrimHot {
-    float q[12];
+    float q[16];
 };
 // Cold shading record, 32 B: geometric normal (triangles), material, entity id.
 struct alignas(16) PrimCold {

@@ -63,10 +63,24 @@ void add_triangle(std::vector<BuildPrim>& out, const HostTri& t, int material, i
         e1[k] = v1[k] - v0[k];
         e2[k] = v2[k] - v0[k];
     }
-    float* q = p.hot.q;
-    q[0] = v0[0]; q[1] = v0[1]; q[2] = v0[2]; q[3] = e1[0];
-    q[4] = e1[1]; q[5] = e1[2]; q[6] = e2[0]; q[7] = e2[1];
-    q[8] = e2[2]; q[9] = 0; q[10] = 0; q[11] = 1.0f; // kind = triangle
+    // world -> (b1, b2, h): rows of [e1 e2 n]^-1 with n = e1 x e2, translation -M v0
+    {
+        double a[3] = {e1[0], e1[1], e1[2]}, b[3] = {e2[0], e2[1], e2[2]};
+        double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        float* q = p.hot.q;
+        if (nn > 0) {
+            double r0[3] = {(b[1] * n[2] - b[2] * n[1]) / nn, (b[2] * n[0] - b[0] * n[2]) / nn, (b[0] * n[1] - b[1] * n[0]) / nn};
+            double r1[3] = {(n[1] * a[2] - n[2] * a[1]) / nn, (n[2] * a[0] - n[0] * a[2]) / nn, (n[0] * a[1] - n[1] * a[0]) / nn};
+            double r2[3] = {n[0] / nn, n[1] / nn, n[2] / nn};
+            const double* rows[3] = {r0, r1, r2};
+            for (int r = 0; r < 3; ++r) {
+                for (int k = 0; k < 3; ++k) q[4 * r + k] = float(rows[r][k]);
+                q[4 * r + 3] = float(-(rows[r][0] * v0[0] + rows[r][1] * v0[1] + rows[r][2] * v0[2]));
+            }
+        } // else: all-zero rows -> t = 0/0 = NaN -> never hit
+        q[14] = 1.0f; // kind = triangle
+    }
     // geometric normal from the double-precision vertices
     double ax = t.p2.x - t.p1.x, ay = t.p2.y - t.p1.y, az = t.p2.z - t.p1.z;
     double bx = t.p3.x - t.p1.x, by = t.p3.y - t.p1.y, bz = t.p3.z - t.p1.z;
@@ -89,7 +103,7 @@ void add_sphere(std::vector<BuildPrim>& out, const HostEntity& e, int material, 
     float c[3] = {float(e.pos.x), float(e.pos.y), float(e.pos.z)};
     float* q = p.hot.q;
     q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; q[3] = e.radius;
-    q[11] = 0.0f; // kind = sphere
+    q[14] = 0.0f; // kind = sphere
     p.cold.material = material;
     p.cold.entity = entity;
     for (int k = 0; k < 3; ++k) {
@@ -145,8 +159,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         // material index and class ride in the spare words of the hot record
         auto tag = [&](BuildPrim& p) {
             int32_t mat_bits = mi, bsdf_bits = m.bsdf;
-            std::memcpy(&p.hot.q[9], &mat_bits, 4);
-            std::memcpy(&p.hot.q[10], &bsdf_bits, 4);
+            std::memcpy(&p.hot.q[12], &mat_bits, 4);
+            std::memcpy(&p.hot.q[13], &bsdf_bits, 4);
         };
         if (e.combine == COMBINE_SPHERE) {
             add_sphere(prims, e, mi, int(ei));
@@ -159,10 +173,15 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
                     const BuildPrim& p = prims.back();
                     LightD l;
                     std::memset(&l, 0, sizeof l);
-                    const float* q = p.hot.q;
-                    l.v0[0] = q[0]; l.v0[1] = q[1]; l.v0[2] = q[2];
-                    l.e1[0] = q[3]; l.e1[1] = q[4]; l.e1[2] = q[5];
-                    l.e2[0] = q[6]; l.e2[1] = q[7]; l.e2[2] = q[8];
+                    const HostTri& ht = e.tris[t];
+                    const float fv0[3] = {float(ht.p1.x), float(ht.p1.y), float(ht.p1.z)};
+                    const float fv1[3] = {float(ht.p2.x), float(ht.p2.y), float(ht.p2.z)};
+                    const float fv2[3] = {float(ht.p3.x), float(ht.p3.y), float(ht.p3.z)};
+                    for (int k = 0; k < 3; ++k) {
+                        l.v0[k] = fv0[k];
+                        l.e1[k] = fv1[k] - fv0[k];
+                        l.e2[k] = fv2[k] - fv0[k];
+                    }
                     float cx = l.e1[1] * l.e2[2] - l.e1[2] * l.e2[1];
                     float cy = l.e1[2] * l.e2[0] - l.e1[0] * l.e2[2];
                     float cz = l.e1[0] * l.e2[1] - l.e1[1] * l.e2[0];
@@ -402,8 +421,11 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa.totals = static_cast<unsigned long long*>(w.totals.p);
     pa.accum = static_cast<float*>(w.accum.p);
 
-    const int grid_extend = a.sm_count * extend_blocks_per_sm();
-    const int grid_shade = a.sm_count * shade_blocks_per_sm();
+    // stage the breadth-first prefix of the tree and the first primitives (<= ~24 KB)
+    pa.stage_nodes = std::min(b.view.n_nodes, 1024);
+    pa.stage_index = std::min(b.view.n_index, 1024);
+    pa.stage_prims = std::min(b.view.n_prims, 192);
+    pa.stack_levels = b.view.tree_depth + 1;
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
     for (int base = 0; base < p.spp; base += spp_pass) {
@@ -416,21 +438,21 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         pa.n_slots = uint32_t(npix * size_t(pa.spp_pass));
         for (int bounce = 0; bounce < p.max_depth; ++bounce) {
             clk.begin();
-            launch_extend(pa, bounce, grid_extend, s);
+            launch_extend(pa, bounce, a.sm_count, s);
             clk.end(G19_K_EXTEND);
             stats.class_launches[G19_K_EXTEND] += 1;
             clk.begin();
             int n = 0;
             for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
                 if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
-                launch_shade(pa, bounce, kind, grid_shade, s);
+                launch_shade(pa, bounce, kind, a.sm_count, s);
                 ++n;
             }
             clk.end(G19_K_SHADE);
             stats.class_launches[G19_K_SHADE] += n;
         }
         clk.begin();
-        launch_accumulate(pa, grid_shade, s);
+        launch_accumulate(pa, s);
         clk.end(G19_K_ACCUM);
         stats.class_launches[G19_K_ACCUM] += 1;
         stats.samples += uint64_t(pa.spp_pass); // scaled by owned pixels below

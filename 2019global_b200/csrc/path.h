@@ -121,13 +121,13 @@ struct PassArgs {
     uint32_t* counts;      // [kMaxPathDepth+1][4]
     unsigned long long* totals;
     float* accum;          // 3 planes of n_local_pix
+    // shared-memory staging (see path_kernels.cu stage_scene)
+    int32_t stage_nodes, stage_index, stage_prims, stack_levels;
 };
 
-void launch_extend(const PassArgs& a, int bounce, int grid, cudaStream_t s);
-void launch_shade(const PassArgs& a, int bounce, int kind, int grid, cudaStream_t s);
-void launch_accumulate(const PassArgs& a, int grid, cudaStream_t s);
+void launch_extend(const PassArgs& a, int bounce, int sm_count, cudaStream_t s);
+void launch_shade(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s);
+void launch_accumulate(const PassArgs& a, cudaStream_t s);
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s);
-int extend_blocks_per_sm();
-int shade_blocks_per_sm();
 
 } // namespace g19

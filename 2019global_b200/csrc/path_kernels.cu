@@ -35,9 +35,6 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStageNodes = 1024;  // 8 KB
-constexpr int kStageIndex = 1024;  // 4 KB
-constexpr int kStagePrims = 256;   // 12 KB
 constexpr float kRayEps = 1.0e-3f; // origin offset along the normal (scene units)
 constexpr float kPi = 3.14159265358979323846f;
 
@@ -71,49 +68,63 @@ __device__ __forceinline__ float3 cross(float3 a, float3 b) {
 __device__ __forceinline__ float3 normalize(float3 v) { return v * (1.0f / sqrtf(dot(v, v))); }
 
 // ---- shared-memory scene prefix ----------------------------------------------
-struct SceneSmem {
-    alignas(16) PathNodeD nodes[kStageNodes];
-    alignas(16) uint32_t index[kStageIndex];
-    alignas(16) float4 hot[kStagePrims * 3];
-    alignas(8) unsigned long long bar;
-};
+// Dynamic shared memory, sized on the host to what the scene needs (PassArgs::stage_*):
+//   [nodes: stage_nodes x 8 B][leaf index: stage_index x 4 B][hot prims: stage_prims x 64 B]
+//   [traversal stack: stack_levels x kThreads x 4 B][mbarrier: 8 B]
+// A Cornell box stages whole (a few hundred bytes) and leaves the SM free for more CTAs.
+extern __shared__ __align__(16) unsigned char g19_dyn_smem[];
 
-struct SceneAccess {
+template <bool ALL> struct SceneAccess {
     const PathSceneD* g;
-    const SceneSmem* s;
+    const uint2* nodes_s;
+    const uint32_t* index_s;
+    const float4* hot_s;
+    uint32_t* stack;
     int n_nodes_s, n_index_s, n_prims_s;
     __device__ __forceinline__ uint2 node(uint32_t i) const {
-        if (i < (uint32_t)n_nodes_s) return make_uint2(s->nodes[i].first, s->nodes[i].count);
+        if (ALL || i < (uint32_t)n_nodes_s) return nodes_s[i];
         return __ldg(reinterpret_cast<const uint2*>(g->nodes) + i);
     }
     __device__ __forceinline__ uint32_t prim_index(uint32_t i) const {
-        return (i < (uint32_t)n_index_s) ? s->index[i] : __ldg(g->prim_index + i);
+        if (ALL || i < (uint32_t)n_index_s) return index_s[i];
+        return __ldg(g->prim_index + i);
     }
-    __device__ __forceinline__ void prim(uint32_t i, float4& a, float4& b, float4& c) const {
-        if (i < (uint32_t)n_prims_s) {
-            a = s->hot[3 * i]; b = s->hot[3 * i + 1]; c = s->hot[3 * i + 2];
+    __device__ __forceinline__ void prim(uint32_t i, float4& a, float4& b, float4& c, float4& k) const {
+        if (ALL || i < (uint32_t)n_prims_s) {
+            a = hot_s[4 * i]; b = hot_s[4 * i + 1]; c = hot_s[4 * i + 2]; k = hot_s[4 * i + 3];
         } else {
-            const float4* p = reinterpret_cast<const float4*>(g->hot) + 3 * (size_t)i;
-            a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2);
+            const float4* p = reinterpret_cast<const float4*>(g->hot) + 4 * (size_t)i;
+            a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); k = __ldg(p + 3);
         }
+    }
+    __device__ __forceinline__ float4 prim_tag(uint32_t i) const { // row 3: material, bsdf, kind
+        if (ALL || i < (uint32_t)n_prims_s) return hot_s[4 * i + 3];
+        return __ldg(reinterpret_cast<const float4*>(g->hot) + 4 * (size_t)i + 3);
     }
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Stage the scene prefix with TMA bulk copies completing on one mbarrier.
-__device__ __forceinline__ SceneAccess stage_scene(const PathSceneD& g, SceneSmem& sm) {
-    SceneAccess acc;
-    acc.g = &g;
-    acc.s = &sm;
-    acc.n_nodes_s = min(g.n_nodes, kStageNodes);
-    acc.n_index_s = min(g.n_index, kStageIndex);
-    acc.n_prims_s = min(g.n_prims, kStagePrims);
+// Stage the scene prefix with TMA bulk copies (cp.async.bulk) completing on one mbarrier.
+template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(const PassArgs& a) {
+    const PathSceneD& g = a.scene;
+    SceneAccess<ALL> acc;
+    acc.g = &a.scene;
+    acc.n_nodes_s = a.stage_nodes;
+    acc.n_index_s = a.stage_index;
+    acc.n_prims_s = a.stage_prims;
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
-    uint32_t nb = (uint32_t(acc.n_nodes_s) * 8u + 15u) & ~15u;
-    uint32_t ib = (uint32_t(acc.n_index_s) * 4u + 15u) & ~15u;
-    uint32_t pb = uint32_t(acc.n_prims_s) * 48u;
-    uint32_t bar = smem_addr(&sm.bar);
+    const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
+    const uint32_t ib = (uint32_t(a.stage_index) * 4u + 15u) & ~15u;
+    const uint32_t pb = uint32_t(a.stage_prims) * 64u;
+    unsigned char* base = g19_dyn_smem;
+    acc.nodes_s = reinterpret_cast<const uint2*>(base);
+    acc.index_s = reinterpret_cast<const uint32_t*>(base + nb);
+    acc.hot_s = reinterpret_cast<const float4*>(base + nb + ib);
+    acc.stack = reinterpret_cast<uint32_t*>(base + nb + ib + pb) + threadIdx.x;
+    unsigned long long* barp =
+        reinterpret_cast<unsigned long long*>(base + nb + ib + pb + uint32_t(a.stack_levels) * kThreads * 4u);
+    const uint32_t bar = smem_addr(barp);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -123,17 +134,17 @@ __device__ __forceinline__ SceneAccess stage_scene(const PathSceneD& g, SceneSme
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + ib + pb) : "memory");
         if (nb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_addr(sm.nodes)),
+                             smem_addr(base)),
                          "l"(g.nodes), "r"(nb), "r"(bar)
                          : "memory");
         if (ib)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_addr(sm.index)),
+                             smem_addr(base + nb)),
                          "l"(g.prim_index), "r"(ib), "r"(bar)
                          : "memory");
         if (pb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_addr(sm.hot)),
+                             smem_addr(base + nb + ib)),
                          "l"(g.hot), "r"(pb), "r"(bar)
                          : "memory");
     }
@@ -149,24 +160,23 @@ __device__ __forceinline__ SceneAccess stage_scene(const PathSceneD& g, SceneSme
 }
 
 // ---- primitive intersection ---------------------------------------------------
-// Returns t (>= tmin, < tmax) or -1.
-__device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float3 o, float3 d, float tmin, float tmax) {
-    if (c.w != 0.0f) { // triangle: Moller-Trumbore
-        float3 v0 = f3(a.x, a.y, a.z), e1 = f3(a.w, b.x, b.y), e2 = f3(b.z, b.w, c.x);
-        float3 pv = cross(d, e2);
-        float det = dot(e1, pv);
-        if (fabsf(det) < 1.0e-20f) return -1.0f;
-        float inv = 1.0f / det;
-        float3 tv = o - v0;
-        float u = dot(tv, pv) * inv;
-        if (u < 0.0f || u > 1.0f) return -1.0f;
-        float3 qv = cross(tv, e1);
-        float v = dot(d, qv) * inv;
-        if (v < 0.0f || u + v > 1.0f) return -1.0f;
-        float t = dot(e2, qv) * inv;
-        return (t > tmin && t < tmax) ? t : -1.0f;
+// Returns t in (tmin, tmax) or -1. Triangles: the ray is mapped into the triangle's own
+// (b1, b2, h) frame by the precomputed affine rows -- 6 dot products, one fast division,
+// no branches. Spheres: unit direction, discriminant from the perpendicular offset.
+__device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 k, float3 o, float3 d, float tmin,
+                                          float tmax) {
+    if (k.z != 0.0f) {
+        float oz = fmaf(c.x, o.x, fmaf(c.y, o.y, fmaf(c.z, o.z, c.w)));
+        float dz = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
+        float t = __fdividef(-oz, dz);
+        float ox = fmaf(a.x, o.x, fmaf(a.y, o.y, fmaf(a.z, o.z, a.w)));
+        float dx = fmaf(a.x, d.x, fmaf(a.y, d.y, a.z * d.z));
+        float oy = fmaf(b.x, o.x, fmaf(b.y, o.y, fmaf(b.z, o.z, b.w)));
+        float dy = fmaf(b.x, d.x, fmaf(b.y, d.y, b.z * d.z));
+        float u = fmaf(t, dx, ox), v = fmaf(t, dy, oy);
+        bool ok = (t > tmin) & (t < tmax) & (u >= 0.0f) & (v >= 0.0f) & (u + v <= 1.0f);
+        return ok ? t : -1.0f;
     }
-    // sphere (unit direction); discriminant from the perpendicular offset for stability
     float3 oc = o - f3(a.x, a.y, a.z);
     float bq = dot(oc, d);
     float3 l = oc - d * bq;
@@ -190,10 +200,11 @@ __device__ __forceinline__ float cell_edge(float root_lo, float size_at_level, u
 // bounds everything behind it. Per level the kernel keeps the child base index
 // on a short stack in shared memory (one column per thread, conflict free), a
 // 4-bit child counter packed in a register, and the integer cell coordinates.
-template <bool ANY>
-__device__ bool traverse(const SceneAccess& S, uint32_t* stack, float3 o, float3 d, float tmin, float tmax,
-                         float& t_hit, uint32_t& prim_hit) {
+template <bool ANY, bool ALL>
+__device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tmin, float tmax, float& t_hit,
+                         uint32_t& prim_hit) {
     const PathSceneD& g = *S.g;
+    uint32_t* const stack = S.stack;
     float3 dd = d;
     if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
     if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
@@ -206,9 +217,9 @@ __device__ bool traverse(const SceneAccess& S, uint32_t* stack, float3 o, float3
     auto leaf = [&](uint32_t first, uint32_t n) -> bool {
         for (uint32_t k = 0; k < n; ++k) {
             uint32_t pi = S.prim_index(first + k);
-            float4 qa, qb, qc;
-            S.prim(pi, qa, qb, qc);
-            float t = hit_prim(qa, qb, qc, o, d, tmin, best);
+            float4 qa, qb, qc, qk;
+            S.prim(pi, qa, qb, qc, qk);
+            float t = hit_prim(qa, qb, qc, qk, o, d, tmin, best);
             if (t >= 0.0f) {
                 best = t;
                 best_prim = pi;
@@ -343,13 +354,10 @@ __device__ __forceinline__ void add_radiance(const PassArgs& a, uint32_t slot, f
 }
 
 // ---- extend ------------------------------------------------------------------------
-template <bool FIRST>
-__global__ void __launch_bounds__(kThreads, 2) extend_kernel(const PassArgs a, const int bounce) {
-    __shared__ SceneSmem scene_sm;
-    __shared__ uint32_t stack_sm[(kMaxTreeDepth + 1) * kThreads];
+template <bool FIRST, bool ALL>
+__global__ void __launch_bounds__(kThreads, 4) extend_kernel(const PassArgs a, const int bounce) {
     __shared__ AppendSmem<3> app_sm;
-    const SceneAccess S = stage_scene(a.scene, scene_sm);
-    uint32_t* stack = stack_sm + threadIdx.x;
+    const SceneAccess<ALL> S = stage_scene<ALL>(a);
 
     const uint32_t n = FIRST ? a.n_slots : a.counts[bounce * 4 + Q_EXTEND];
     const uint32_t* __restrict__ qin = a.q[bounce & 1];
@@ -379,17 +387,16 @@ __global__ void __launch_bounds__(kThreads, 2) extend_kernel(const PassArgs a, c
             if (live) {
                 float t = FLT_MAX;
                 uint32_t prim = 0xffffffffu;
-                bool hit = traverse<false>(S, stack, o, d, 0.0f, FLT_MAX, t, prim);
+                bool hit = traverse<false, ALL>(S, o, d, 0.0f, FLT_MAX, t, prim);
                 a.hit[slot] = make_uint2(__float_as_uint(t), prim);
                 if (hit) {
-                    float4 qa, qb, qc;
-                    S.prim(prim, qa, qb, qc);
-                    int bsdf = __float_as_int(qc.z); // material class rides in the hot record
+                    const float4 tag = S.prim_tag(prim); // material class rides in the hot record
+                    int bsdf = __float_as_int(tag.y);
                     if (bsdf == G19_BSDF_EMITTER) {
                         // emission counts on camera rays and after specular bounces only (NEE covers the rest)
                         float4 T = FIRST ? make_float4(1.f, 1.f, 1.f, 0.f) : a.tp[slot];
                         if (FIRST || (__float_as_uint(T.w) & 1u)) {
-                            const MaterialD& m = a.scene.materials[__float_as_int(qc.y)];
+                            const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
                             add_radiance(a, slot, f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]));
                         }
                     } else {
@@ -411,14 +418,11 @@ __device__ __forceinline__ void onb(float3 n, float3& t, float3& b) { // Duff et
     b = f3(bb, s + n.y * n.y * a, -n.y);
 }
 
-template <int KIND, bool FIRST>
-__global__ void __launch_bounds__(kThreads, 2) shade_kernel(const PassArgs a, const int bounce) {
-    __shared__ SceneSmem scene_sm;
-    __shared__ uint32_t stack_sm[(KIND == Q_DIFFUSE ? (kMaxTreeDepth + 1) * kThreads : 1)];
+template <int KIND, bool FIRST, bool ALL>
+__global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_kernel(const PassArgs a, const int bounce) {
     __shared__ AppendSmem<1> app_sm;
-    SceneAccess S;
-    if (KIND == Q_DIFFUSE) S = stage_scene(a.scene, scene_sm); // shadow rays traverse
-    uint32_t* stack = stack_sm + (KIND == Q_DIFFUSE ? threadIdx.x : 0);
+    SceneAccess<ALL> S;
+    if (KIND == Q_DIFFUSE) S = stage_scene<ALL>(a); // shadow rays traverse
 
     const uint32_t n = a.counts[bounce * 4 + KIND];
     const uint32_t* __restrict__ qin = a.q[1 + KIND];
@@ -456,9 +460,9 @@ __global__ void __launch_bounds__(kThreads, 2) shade_kernel(const PassArgs a, co
             const MaterialD mat = a.scene.materials[cold.material];
             float3 ng;
             {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 3 * (size_t)prim);
-                const float4 q2 = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 3 * (size_t)prim + 2);
-                if (q2.w != 0.0f) ng = f3(cold.n[0], cold.n[1], cold.n[2]);
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 4 * (size_t)prim);
+                const float4 q3 = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 4 * (size_t)prim + 3);
+                if (q3.z != 0.0f) ng = f3(cold.n[0], cold.n[1], cold.n[2]);
                 else ng = (p - f3(q0.x, q0.y, q0.z)) * (1.0f / q0.w);
             }
             const bool entering = dot(ng, d) < 0.0f;
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 2) shade_kernel(const PassArgs a, co
                         float tt;
                         uint32_t pp;
                         ++shadow_rays;
-                        bool blocked = traverse<true>(S, stack, p + nf * kRayEps, w, 0.0f, dist - 2.0f * kRayEps, tt, pp);
+                        bool blocked = traverse<true, ALL>(S, p + nf * kRayEps, w, 0.0f, dist - 2.0f * kRayEps, tt, pp);
                         if (!blocked) {
                             ++lit;
                             float gterm = cs * cl * lt.area / (dist2 * lt.pdf_pick) * (1.0f / kPi);
@@ -561,19 +565,41 @@ __global__ void __launch_bounds__(kThreads, 2) shade_kernel(const PassArgs a, co
 // ---- accumulate / resolve ---------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) {
     const uint32_t npix = (uint32_t)a.map.n_local_pix;
-    const uint32_t stride = gridDim.x * kThreads;
-    for (uint32_t lp = blockIdx.x * kThreads + threadIdx.x; lp < npix; lp += stride) {
+    const uint32_t lp = blockIdx.x * kThreads + threadIdx.x;
+    if (lp < npix) {
+        float acc0 = a.accum[lp], acc1 = a.accum[(size_t)npix + lp], acc2 = a.accum[2 * (size_t)npix + lp];
+        float* L0 = a.L + lp;
+        float* L1 = a.L + a.plane + lp;
+        float* L2 = a.L + 2 * a.plane + lp;
+        // strictly in sample order (independent of the pass split); loads batched four samples deep
+        int s = 0;
+        for (; s + 4 <= a.spp_pass; s += 4) {
+            float v0[4], v1[4], v2[4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float acc = a.accum[(size_t)c * npix + lp];
-            float* L = a.L + (size_t)c * a.plane;
-            for (int s = 0; s < a.spp_pass; ++s) { // strictly in sample order: independent of the pass split
-                size_t i = (size_t)s * npix + lp;
-                acc += L[i];
-                L[i] = 0.0f;
+            for (int k = 0; k < 4; ++k) {
+                size_t i = (size_t)(s + k) * npix;
+                v0[k] = L0[i]; v1[k] = L1[i]; v2[k] = L2[i];
             }
-            a.accum[(size_t)c * npix + lp] = acc;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                size_t i = (size_t)(s + k) * npix;
+                acc0 += v0[k]; acc1 += v1[k]; acc2 += v2[k];
+                if (v0[k] != 0.0f) L0[i] = 0.0f;
+                if (v1[k] != 0.0f) L1[i] = 0.0f;
+                if (v2[k] != 0.0f) L2[i] = 0.0f;
+            }
         }
+        for (; s < a.spp_pass; ++s) {
+            size_t i = (size_t)s * npix;
+            float v0 = L0[i], v1 = L1[i], v2 = L2[i];
+            acc0 += v0; acc1 += v1; acc2 += v2;
+            if (v0 != 0.0f) L0[i] = 0.0f;
+            if (v1 != 0.0f) L1[i] = 0.0f;
+            if (v2 != 0.0f) L2[i] = 0.0f;
+        }
+        a.accum[lp] = acc0;
+        a.accum[(size_t)npix + lp] = acc1;
+        a.accum[2 * (size_t)npix + lp] = acc2;
     }
     // fold this pass's queue lengths into the running totals and clear them
     if (blockIdx.x == 0) {
@@ -607,33 +633,73 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(TileMap map, const fl
 
 } // namespace
 
-int extend_blocks_per_sm() { return 2; }
-int shade_blocks_per_sm() { return 2; }
-
-void launch_extend(const PassArgs& a, int bounce, int grid, cudaStream_t s) {
-    if (bounce == 0) extend_kernel<true><<<grid, kThreads, 0, s>>>(a, bounce);
-    else extend_kernel<false><<<grid, kThreads, 0, s>>>(a, bounce);
+// Persistent grids: SM count x the CTAs the occupancy calculator says are resident.
+template <typename K> static int resident_grid(K kernel, size_t smem, int sm_count) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * sm_count;
 }
 
-void launch_shade(const PassArgs& a, int bounce, int kind, int grid, cudaStream_t s) {
-    const bool first = bounce == 0;
-    switch (kind) {
-    case Q_DIFFUSE:
-        if (first) shade_kernel<Q_DIFFUSE, true><<<grid, kThreads, 0, s>>>(a, bounce);
-        else shade_kernel<Q_DIFFUSE, false><<<grid, kThreads, 0, s>>>(a, bounce);
-        break;
-    case Q_MIRROR:
-        if (first) shade_kernel<Q_MIRROR, true><<<grid, kThreads, 0, s>>>(a, bounce);
-        else shade_kernel<Q_MIRROR, false><<<grid, kThreads, 0, s>>>(a, bounce);
-        break;
-    default:
-        if (first) shade_kernel<Q_GLASS, true><<<grid, kThreads, 0, s>>>(a, bounce);
-        else shade_kernel<Q_GLASS, false><<<grid, kThreads, 0, s>>>(a, bounce);
-        break;
+size_t path_smem_bytes(const PassArgs& a, bool with_scene) {
+    if (!with_scene) return 0;
+    size_t nb = (size_t(a.stage_nodes) * 8 + 15) & ~size_t(15);
+    size_t ib = (size_t(a.stage_index) * 4 + 15) & ~size_t(15);
+    return nb + ib + size_t(a.stage_prims) * 64 + size_t(a.stack_levels) * kThreads * 4 + 16;
+}
+
+static bool all_staged(const PassArgs& a) {
+    return a.stage_nodes >= a.scene.n_nodes && a.stage_index >= a.scene.n_index && a.stage_prims >= a.scene.n_prims;
+}
+
+template <typename K> static void launch_persistent(K kernel, const PassArgs& a, int bounce, size_t smem, int sm_count,
+                                                    cudaStream_t s) {
+    static int grid = 0;          // one instance per kernel instantiation
+    static size_t grid_smem = ~size_t(0);
+    if (grid_smem != smem) {
+        grid = resident_grid(kernel, smem, sm_count);
+        grid_smem = smem;
+    }
+    kernel<<<grid, kThreads, smem, s>>>(a, bounce);
+}
+
+void launch_extend(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
+    const size_t smem = path_smem_bytes(a, true);
+    const bool all = all_staged(a);
+    if (bounce == 0) {
+        if (all) launch_persistent(extend_kernel<true, true>, a, bounce, smem, sm_count, s);
+        else launch_persistent(extend_kernel<true, false>, a, bounce, smem, sm_count, s);
+    } else {
+        if (all) launch_persistent(extend_kernel<false, true>, a, bounce, smem, sm_count, s);
+        else launch_persistent(extend_kernel<false, false>, a, bounce, smem, sm_count, s);
     }
 }
 
-void launch_accumulate(const PassArgs& a, int grid, cudaStream_t s) { accumulate_kernel<<<grid, kThreads, 0, s>>>(a); }
+template <int KIND> static void launch_shade_k(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
+    const size_t smem = path_smem_bytes(a, KIND == Q_DIFFUSE);
+    const bool all = all_staged(a), first = bounce == 0;
+    if (first) {
+        if (all) launch_persistent(shade_kernel<KIND, true, true>, a, bounce, smem, sm_count, s);
+        else launch_persistent(shade_kernel<KIND, true, false>, a, bounce, smem, sm_count, s);
+    } else {
+        if (all) launch_persistent(shade_kernel<KIND, false, true>, a, bounce, smem, sm_count, s);
+        else launch_persistent(shade_kernel<KIND, false, false>, a, bounce, smem, sm_count, s);
+    }
+}
+
+void launch_shade(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s) {
+    switch (kind) {
+    case Q_DIFFUSE: launch_shade_k<Q_DIFFUSE>(a, bounce, sm_count, s); break;
+    case Q_MIRROR: launch_shade_k<Q_MIRROR>(a, bounce, sm_count, s); break;
+    default: launch_shade_k<Q_GLASS>(a, bounce, sm_count, s); break;
+    }
+}
+
+void launch_accumulate(const PassArgs& a, cudaStream_t s) {
+    int blocks = (a.map.n_local_pix + kThreads - 1) / kThreads;
+    if (blocks < 1) blocks = 1;
+    accumulate_kernel<<<blocks, kThreads, 0, s>>>(a);
+}
 
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s) {
     if (map.n_local_pix == 0) return;

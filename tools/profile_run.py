@@ -1,0 +1,28 @@
+"""Short single-GPU run of the bench workload for ncu (one frame, fewer spp): exits 0 on success."""
+import argparse
+import importlib
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ap = argparse.ArgumentParser()
+ap.add_argument("--spp", type=int, default=8)
+ap.add_argument("--depth", type=int, default=5)
+ap.add_argument("--scene", default="CORNELL")
+ap.add_argument("--n", type=int, default=0)
+ap.add_argument("--w", type=int, default=1920)
+ap.add_argument("--h", type=int, default=1080)
+ap.add_argument("--mode", default="PATH")
+ap.add_argument("--frames", type=int, default=1)
+a = ap.parse_args()
+g19 = importlib.import_module("2019global_b200")
+abi = g19.abi
+sc, cam, light = g19.Octree.builtin(getattr(abi, "SCENE_" + a.scene), n=a.n, w=a.w, h=a.h)
+rt = g19.RayTracer(cam, light, device=0)
+rt.setScene(sc)
+rt.start()
+for _ in range(a.frames):
+    out = rt.run(a.w, a.h, mode=getattr(abi, "MODE_" + a.mode), want=("rgb",), spp=a.spp, max_depth=a.depth, seed=0)
+st = rt.stats()
+print("ok: %.2f ms, %d samples, %d extend, %d shadow segments, %d launches" % (
+    st.render_ms, st.samples, st.extend_segments, st.shadow_segments, st.kernel_launches))
