@@ -548,6 +548,62 @@ int g19_probe_intersect(g19_ctx* ctx, int32_t entity, int n, const double* origi
     return rc;
 }
 
+int g19_probe_texcoord(g19_ctx* ctx, int32_t entity, int n, const double* points, int32_t* out_uv) {
+    if (!ctx || !points || !out_uv || n < 0) return G19_ERR_INVALID;
+    if (!ctx->has_scene) return G19_ERR_NO_SCENE;
+    if (entity < 0 || entity >= ctx->ref.n_entities) return G19_ERR_INVALID;
+    if (n == 0) return G19_OK;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf p, uv;
+    cudaStream_t s = ctx->stream;
+    cudaError_t e;
+    int rc = G19_OK;
+    if ((e = p.ensure(size_t(n) * 24)) != cudaSuccess || (e = uv.ensure(size_t(n) * 8)) != cudaSuccess) {
+        ctx->err = std::string("probe alloc: ") + cudaGetErrorString(e);
+        rc = G19_ERR_CUDA;
+    } else {
+        cudaMemcpyAsync(p.p, points, size_t(n) * 24, cudaMemcpyHostToDevice, s);
+        launch_probe_texcoord(ctx->ref, entity, n, p.as<double>(), uv.as<int32_t>(), s);
+        cudaMemcpyAsync(out_uv, uv.p, size_t(n) * 8, cudaMemcpyDeviceToHost, s);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) {
+            ctx->err = std::string("probe_texcoord: ") + cudaGetErrorString(e);
+            rc = G19_ERR_CUDA;
+        }
+    }
+    p.release();
+    uv.release();
+    return rc;
+}
+
+int g19_probe_shade(g19_ctx* ctx, int32_t entity, int textured, const double ray_dir[3], const double light[3],
+                    const double point[3], const double normal[3], int u, int v, double out_rgb[3]) {
+    if (!ctx || !ray_dir || !light || !point || !normal || !out_rgb) return G19_ERR_INVALID;
+    if (!ctx->has_scene) return G19_ERR_NO_SCENE;
+    if (entity < 0 || entity >= ctx->ref.n_entities) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf in, out;
+    cudaStream_t s = ctx->stream;
+    double h[15] = {ray_dir[0], ray_dir[1], ray_dir[2], light[0], light[1], light[2], point[0], point[1],
+                    point[2],   normal[0],  normal[1],  normal[2], 0,       0,        0};
+    cudaError_t e;
+    int rc = G19_OK;
+    if ((e = in.ensure(sizeof h)) != cudaSuccess || (e = out.ensure(24)) != cudaSuccess) {
+        ctx->err = std::string("probe alloc: ") + cudaGetErrorString(e);
+        rc = G19_ERR_CUDA;
+    } else {
+        cudaMemcpyAsync(in.p, h, sizeof h, cudaMemcpyHostToDevice, s);
+        launch_probe_shade(ctx->ref, entity, textured, in.as<double>(), u, v, out.as<double>(), s);
+        cudaMemcpyAsync(out_rgb, out.p, 24, cudaMemcpyDeviceToHost, s);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) {
+            ctx->err = std::string("probe_shade: ") + cudaGetErrorString(e);
+            rc = G19_ERR_CUDA;
+        }
+    }
+    in.release();
+    out.release();
+    return rc;
+}
+
 int g19_probe_candidates(g19_ctx* ctx, const double origin[3], const double dir[3], int32_t* out_ids, int max_out,
                          int* out_n) {
     if (!ctx || !origin || !dir || !out_n || max_out < 0) return G19_ERR_INVALID;

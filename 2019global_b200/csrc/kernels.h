@@ -67,6 +67,12 @@ void launch_probe_intersect(const RefSceneD& scene, int32_t entity, int n, const
 void launch_probe_candidates(const RefSceneD& scene, const double* origin_dir6, int32_t* out_ids, int max_out,
                              int32_t* out_n, cudaStream_t stream);
 
+// Entity::getTextureCoord on n points; Material::blinn_phong(_texture) on one point.
+void launch_probe_texcoord(const RefSceneD& scene, int32_t entity, int n, const double* points, int32_t* uv,
+                           cudaStream_t stream);
+void launch_probe_shade(const RefSceneD& scene, int32_t entity, int textured, const double* in15, int u, int v,
+                        double* out_rgb, cudaStream_t stream);
+
 // ---- shared (ref_kernels.cu) ----------------------------------------------
 // Scatter compact local-pixel buffers into full-frame row-major buffers.
 void launch_untile(const TileMap& map, const uint8_t* rgb_local, const int32_t* ids_local, const float* rad_local,

@@ -652,13 +652,18 @@ static bool all_staged(const PassArgs& a) {
     return a.stage_nodes >= a.scene.n_nodes && a.stage_index >= a.scene.n_index && a.stage_prims >= a.scene.n_prims;
 }
 
+// The grid of a persistent kernel = SM count x resident CTAs, cached per (kernel, smem size).
 template <typename K> static void launch_persistent(K kernel, const PassArgs& a, int bounce, size_t smem, int sm_count,
                                                     cudaStream_t s) {
-    static int grid = 0;          // one instance per kernel instantiation
-    static size_t grid_smem = ~size_t(0);
-    if (grid_smem != smem) {
+    struct Entry { const void* fn; size_t smem; int grid; };
+    static Entry cache[64];
+    static int n_cache = 0;
+    int grid = 0;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].fn == (const void*)kernel && cache[i].smem == smem) grid = cache[i].grid;
+    if (!grid) {
         grid = resident_grid(kernel, smem, sm_count);
-        grid_smem = smem;
+        if (n_cache < 64) cache[n_cache++] = Entry{(const void*)kernel, smem, grid};
     }
     kernel<<<grid, kThreads, smem, s>>>(a, bounce);
 }

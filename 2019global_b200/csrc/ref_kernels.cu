@@ -533,6 +533,37 @@ __global__ void probe_candidates_kernel(RefSceneD s, const double* __restrict__ 
     *out_n = n;
 }
 
+__global__ void probe_texcoord_kernel(RefSceneD s, int entity, int n, const double* __restrict__ points,
+                                      int32_t* __restrict__ uv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int u, v;
+    texture_coord(s, s.entities + entity, ld3(points + 3 * i), u, v);
+    uv[2 * i] = u;
+    uv[2 * i + 1] = v;
+}
+
+// in15 = ray dir (normalised here, as the Ray ctor does), light, point, normal, unused
+__global__ void probe_shade_kernel(RefSceneD s, int entity, int textured, const double* __restrict__ in, int u, int v,
+                                   double* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    D3 dir = unit(ld3(in)), light = ld3(in + 3), ip = ld3(in + 6), nn = ld3(in + 9);
+    D3 color = ld3(s.entities[entity].color);
+    D3 c;
+    if (textured) {
+        c = blinn_phong_texture(color, dir, light, ip, nn, u, v);
+    } else { // Material::blinn_phong, material.h:31-46 (unused by RayTracer::run, raytracer.h:79)
+        D3 la = color * 0.1;
+        D3 ldir = unit(light - ip);
+        D3 ld = (std_max(0.0, dot3(nn, ldir)) * (color * 0.5)) * 0.7;
+        D3 bis = unit(unit(-dir) + unit(light - ip));
+        D3 ls = (pow(std_max(0.0, dot3(nn, bis)), 5.0) * mk(1, 1, 1)) * 1.0;
+        D3 o = la + ld + ls;
+        c = mk(std_min(o.x, 1.0), std_min(o.y, 1.0), std_min(o.z, 1.0));
+    }
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+
 // ---- untile ----------------------------------------------------------------------
 __global__ void untile_kernel(TileMap map, const uint8_t* __restrict__ rgb_l, const int32_t* __restrict__ ids_l,
                               const float* __restrict__ rad_l, uint8_t* __restrict__ rgb_f,
@@ -583,6 +614,17 @@ void launch_probe_intersect(const RefSceneD& scene, int32_t entity, int n, const
 void launch_probe_candidates(const RefSceneD& scene, const double* origin_dir6, int32_t* out_ids, int max_out,
                              int32_t* out_n, cudaStream_t stream) {
     probe_candidates_kernel<<<1, 32, 0, stream>>>(scene, origin_dir6, out_ids, max_out, out_n);
+}
+
+void launch_probe_texcoord(const RefSceneD& scene, int32_t entity, int n, const double* points, int32_t* uv,
+                           cudaStream_t stream) {
+    if (n <= 0) return;
+    probe_texcoord_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(scene, entity, n, points, uv);
+}
+
+void launch_probe_shade(const RefSceneD& scene, int32_t entity, int textured, const double* in15, int u, int v,
+                        double* out_rgb, cudaStream_t stream) {
+    probe_shade_kernel<<<1, 32, 0, stream>>>(scene, entity, textured, in15, u, v, out_rgb);
 }
 
 void launch_untile(const TileMap& map, const uint8_t* rgb_local, const int32_t* ids_local, const float* rad_local,

@@ -386,6 +386,26 @@ int g19_scene_entity_triangles(const g19_scene* s, int32_t i, double* out, int m
     return n;
 }
 
+int g19_entity_bbox(const g19_entity_desc* d, double o[6]) {
+    HostEntity e;
+    if (!d || !o || !build_entity(*d, e)) return G19_ERR_INVALID;
+    o[0] = e.bbmin.x; o[1] = e.bbmin.y; o[2] = e.bbmin.z;
+    o[3] = e.bbmax.x; o[4] = e.bbmax.y; o[5] = e.bbmax.z;
+    return G19_OK;
+}
+
+int g19_entity_triangles(const g19_entity_desc* d, double* out, int max_tris) {
+    HostEntity e;
+    if (!d || !build_entity(*d, e)) return 0;
+    int n = int(e.tris.size());
+    for (int k = 0; k < n && k < max_tris && out; ++k) {
+        const HostTri& t = e.tris[k];
+        double v[9] = {t.p1.x, t.p1.y, t.p1.z, t.p2.x, t.p2.y, t.p2.z, t.p3.x, t.p3.y, t.p3.z};
+        std::memcpy(out + 9 * k, v, sizeof v);
+    }
+    return n;
+}
+
 int g19_scene_builtin(int which, int n, int w, int h, g19_scene** out, g19_camera* cam, double light[3]) {
     return make_builtin(which, n, w, h, out, cam, light);
 }

@@ -105,6 +105,11 @@ int g19_scene_entity_bbox(const g19_scene* scene, int32_t index, double out_min_
  * each. Returns the count; writes at most max_tris. IMP_SPHERE returns 0.   */
 int g19_scene_entity_triangles(const g19_scene* scene, int32_t index, double* out, int max_tris);
 
+/* Stateless forms of the two calls above, for one entity outside any scene
+ * (what an Entity subclass needs to fill its public members at construction). */
+int g19_entity_bbox(const g19_entity_desc* desc, double out_min_max[6]);
+int g19_entity_triangles(const g19_entity_desc* desc, double* out, int max_tris);
+
 /* Procedural scenes of BASELINE.json `configs`.    */
 enum g19_builtin_scene {
     G19_SCENE_DEFAULT = 0,     /* main.cpp:24-57 literal (config 1)             */
@@ -232,6 +237,15 @@ int g19_probe_intersect(g19_ctx* ctx, int32_t entity, int n, const double* origi
  * Writes up to max_out entity ids for ONE ray, returns the count in *out_n. */
 int g19_probe_candidates(g19_ctx* ctx, const double origin[3], const double dir[3],
                          int32_t* out_ids, int max_out, int* out_n);
+
+/* Entity::getTextureCoord(point)                           entities.h:32    */
+int g19_probe_texcoord(g19_ctx* ctx, int32_t entity, int n, const double* points, int32_t* out_uv);
+/* Material::blinn_phong_texture / blinn_phong              material.h:31-62.
+ * One call per point: ray direction, light, hit point, normal, (u,v);
+ * textured=0 selects the untextured variant. out_rgb: 3 doubles in [0,1].   */
+int g19_probe_shade(g19_ctx* ctx, int32_t entity, int textured, const double ray_dir[3],
+                    const double light[3], const double point[3], const double normal[3], int u, int v,
+                    double out_rgb[3]);
 
 #ifdef __cplusplus
 }
