@@ -48,7 +48,26 @@ struct BuildPrim {
     PrimHot hot;
     PrimCold cold;
     Box box;
+    float v[3][3]; // triangle corners (float), for the parallelogram merge
+    bool tri;
 };
+
+// world -> (b1, b2, h) rows for the frame (v0; e1, e2): rows of [e1 e2 n]^-1, n = e1 x e2, translation -M v0
+void affine_rows(float* q, const float v0[3], const float e1[3], const float e2[3]) {
+    double a[3] = {e1[0], e1[1], e1[2]}, b[3] = {e2[0], e2[1], e2[2]};
+    double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    for (int k = 0; k < 12; ++k) q[k] = 0.0f; // degenerate: t = 0/0 = NaN -> never hit
+    if (!(nn > 0)) return;
+    double r0[3] = {(b[1] * n[2] - b[2] * n[1]) / nn, (b[2] * n[0] - b[0] * n[2]) / nn, (b[0] * n[1] - b[1] * n[0]) / nn};
+    double r1[3] = {(n[1] * a[2] - n[2] * a[1]) / nn, (n[2] * a[0] - n[0] * a[2]) / nn, (n[0] * a[1] - n[1] * a[0]) / nn};
+    double r2[3] = {n[0] / nn, n[1] / nn, n[2] / nn};
+    const double* rows[3] = {r0, r1, r2};
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) q[4 * r + k] = float(rows[r][k]);
+        q[4 * r + 3] = float(-(rows[r][0] * v0[0] + rows[r][1] * v0[1] + rows[r][2] * v0[2]));
+    }
+}
 
 float clamp01(double v) { return float(v < 0 ? 0 : (v > 1 ? 1 : v)); }
 
@@ -63,24 +82,10 @@ void add_triangle(std::vector<BuildPrim>& out, const HostTri& t, int material, i
         e1[k] = v1[k] - v0[k];
         e2[k] = v2[k] - v0[k];
     }
-    // world -> (b1, b2, h): rows of [e1 e2 n]^-1 with n = e1 x e2, translation -M v0
-    {
-        double a[3] = {e1[0], e1[1], e1[2]}, b[3] = {e2[0], e2[1], e2[2]};
-        double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
-        double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-        float* q = p.hot.q;
-        if (nn > 0) {
-            double r0[3] = {(b[1] * n[2] - b[2] * n[1]) / nn, (b[2] * n[0] - b[0] * n[2]) / nn, (b[0] * n[1] - b[1] * n[0]) / nn};
-            double r1[3] = {(n[1] * a[2] - n[2] * a[1]) / nn, (n[2] * a[0] - n[0] * a[2]) / nn, (n[0] * a[1] - n[1] * a[0]) / nn};
-            double r2[3] = {n[0] / nn, n[1] / nn, n[2] / nn};
-            const double* rows[3] = {r0, r1, r2};
-            for (int r = 0; r < 3; ++r) {
-                for (int k = 0; k < 3; ++k) q[4 * r + k] = float(rows[r][k]);
-                q[4 * r + 3] = float(-(rows[r][0] * v0[0] + rows[r][1] * v0[1] + rows[r][2] * v0[2]));
-            }
-        } // else: all-zero rows -> t = 0/0 = NaN -> never hit
-        q[14] = 1.0f; // kind = triangle
-    }
+    affine_rows(p.hot.q, v0, e1, e2);
+    p.hot.q[14] = 1.0f; // kind = triangle
+    p.tri = true;
+    for (int k = 0; k < 3; ++k) { p.v[0][k] = v0[k]; p.v[1][k] = v1[k]; p.v[2][k] = v2[k]; }
     // geometric normal from the double-precision vertices
     double ax = t.p2.x - t.p1.x, ay = t.p2.y - t.p1.y, az = t.p2.z - t.p1.z;
     double bx = t.p3.x - t.p1.x, by = t.p3.y - t.p1.y, bz = t.p3.z - t.p1.z;
@@ -104,6 +109,7 @@ void add_sphere(std::vector<BuildPrim>& out, const HostEntity& e, int material, 
     float* q = p.hot.q;
     q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; q[3] = e.radius;
     q[14] = 0.0f; // kind = sphere
+    p.tri = false;
     p.cold.material = material;
     p.cold.entity = entity;
     for (int k = 0; k < 3; ++k) {
@@ -195,6 +201,58 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         }
     }
     for (LightD& l : lights) l.pdf_pick = 1.0f / float(lights.size());
+
+    // ---- merge coplanar triangle pairs into parallelograms --------------------------------
+    // Two consecutive triangles with the same material that share an edge s1-s2 and whose
+    // other corners u, v satisfy s1 + s2 = u + v tile the parallelogram (s1; u-s1, v-s1): one
+    // primitive test (b1, b2 in [0,1]) instead of two. Walls, floors and light panels built
+    // as triangle pairs (the Cornell configs) halve their test count; a curved mesh keeps
+    // its triangles. The oracle still tests the triangles: the union is the same point set.
+    {
+        std::vector<BuildPrim> merged;
+        merged.reserve(prims.size());
+        for (size_t i = 0; i < prims.size(); ++i) {
+            bool done = false;
+            if (i + 1 < prims.size() && prims[i].tri && prims[i + 1].tri &&
+                prims[i].cold.material == prims[i + 1].cold.material) {
+                const BuildPrim &A = prims[i], &B = prims[i + 1];
+                int sa[2], sb[2], ns = 0;
+                for (int x = 0; x < 3; ++x)
+                    for (int y = 0; y < 3; ++y)
+                        if (ns < 2 && A.v[x][0] == B.v[y][0] && A.v[x][1] == B.v[y][1] && A.v[x][2] == B.v[y][2]) {
+                            sa[ns] = x; sb[ns] = y; ++ns;
+                        }
+                if (ns == 2 && sa[0] != sa[1] && sb[0] != sb[1]) {
+                    const float* s1 = A.v[sa[0]];
+                    const float* s2 = A.v[sa[1]];
+                    const float* u = A.v[3 - sa[0] - sa[1]];
+                    const float* v = B.v[3 - sb[0] - sb[1]];
+                    double scale = 0, gap = 0;
+                    for (int k = 0; k < 3; ++k) {
+                        gap = std::max(gap, std::fabs(double(s1[k]) + s2[k] - u[k] - v[k]));
+                        scale = std::max(scale, std::fabs(double(s2[k]) - s1[k]));
+                    }
+                    if (gap <= 1e-6 * scale && scale > 0) {
+                        BuildPrim q = A;
+                        float e1[3], e2[3];
+                        for (int k = 0; k < 3; ++k) { e1[k] = u[k] - s1[k]; e2[k] = v[k] - s1[k]; }
+                        affine_rows(q.hot.q, s1, e1, e2);
+                        q.hot.q[14] = 2.0f; // kind = parallelogram
+                        for (int k = 0; k < 3; ++k) {
+                            q.box.lo[k] = std::min(A.box.lo[k], B.box.lo[k]);
+                            q.box.hi[k] = std::max(A.box.hi[k], B.box.hi[k]);
+                        }
+                        q.tri = false;
+                        merged.push_back(q);
+                        ++i;
+                        done = true;
+                    }
+                }
+            }
+            if (!done) merged.push_back(prims[i]);
+        }
+        prims.swap(merged);
+    }
     if (prims.size() >= 0x7fffffffu) {
         err = "too many primitives";
         return G19_ERR_LIMIT;
@@ -277,6 +335,14 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         hot[i] = prims[i].hot;
         cold[i] = prims[i].cold;
     }
+    // Leaf-ordered copy of the hot records: a leaf's primitives are contiguous, so the
+    // traversal streams them without an index indirection; the primitive id rides in q[15].
+    std::vector<PrimHot> hot_leaf(index.size());
+    for (size_t k = 0; k < index.size(); ++k) {
+        hot_leaf[k] = prims[index[k]].hot;
+        uint32_t id = index[k];
+        std::memcpy(&hot_leaf[k].q[15], &id, 4);
+    }
     auto up = [&](DeviceArray& d, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = d.ensure(bytes ? bytes : 16);
         if (e != cudaSuccess || !bytes) return e;
@@ -284,7 +350,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     };
     cudaError_t e;
     if ((e = up(b.nodes, nodes.data(), nodes.size() * sizeof(PathNodeD))) != cudaSuccess ||
-        (e = up(b.prim_index, index.data(), index.size() * sizeof(uint32_t))) != cudaSuccess ||
+        (e = up(b.prim_index, hot_leaf.data(), hot_leaf.size() * sizeof(PrimHot))) != cudaSuccess ||
         (e = up(b.hot, hot.data(), hot.size() * sizeof(PrimHot))) != cudaSuccess ||
         (e = up(b.cold, cold.data(), cold.size() * sizeof(PrimCold))) != cudaSuccess ||
         (e = up(b.materials, materials.data(), materials.size() * sizeof(MaterialD))) != cudaSuccess ||
@@ -295,7 +361,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     }
     PathSceneD& v = b.view;
     v.nodes = static_cast<const PathNodeD*>(b.nodes.p);
-    v.prim_index = static_cast<const uint32_t*>(b.prim_index.p);
+    v.hot_leaf = static_cast<const PrimHot*>(b.prim_index.p);
     v.hot = static_cast<const PrimHot*>(b.hot.p);
     v.cold = static_cast<const PrimCold*>(b.cold.p);
     v.materials = static_cast<const MaterialD*>(b.materials.p);
@@ -379,7 +445,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         PATH_CUDA(w.tp.ensure(P * sizeof(float4)));
         PATH_CUDA(w.hit.ensure(P * sizeof(uint2)));
         PATH_CUDA(w.L.ensure(P * 3 * sizeof(float)));
-        PATH_CUDA(w.queues.ensure(P * 5 * sizeof(uint32_t)));
+        PATH_CUDA(w.queues.ensure((P + kQueueSlack) * 5 * sizeof(uint32_t)));
         w.capacity = P;
         PATH_CUDA(cudaMemsetAsync(w.L.p, 0, P * 3 * sizeof(float), s));
     }
@@ -416,15 +482,15 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa.hit = static_cast<uint2*>(w.hit.p);
     pa.L = static_cast<float*>(w.L.p);
     pa.plane = plane;
-    for (int k = 0; k < 5; ++k) pa.q[k] = static_cast<uint32_t*>(w.queues.p) + size_t(k) * plane;
+    pa.queue_cap = plane + kQueueSlack;
+    for (int k = 0; k < 5; ++k) pa.q[k] = static_cast<uint32_t*>(w.queues.p) + size_t(k) * pa.queue_cap;
     pa.counts = static_cast<uint32_t*>(w.counts.p);
     pa.totals = static_cast<unsigned long long*>(w.totals.p);
     pa.accum = static_cast<float*>(w.accum.p);
 
     // stage the breadth-first prefix of the tree and the first primitives (<= ~24 KB)
     pa.stage_nodes = std::min(b.view.n_nodes, 1024);
-    pa.stage_index = std::min(b.view.n_index, 1024);
-    pa.stage_prims = std::min(b.view.n_prims, 192);
+    pa.stage_prims = std::min(b.view.n_index, 192); // leaf-ordered hot records
     pa.stack_levels = b.view.tree_depth + 1;
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;

@@ -29,12 +29,16 @@ namespace g19 {
 constexpr int kMaxPathDepth = 64;    // segments per path
 constexpr int kMaxTreeDepth = 14;    // linear-octree levels below the root
 constexpr int kNumQueues = 4;        // extend, diffuse, mirror, glass
+// Queue entries are reserved in warp-private chunks; a launch can leave at most one partly used
+// chunk per warp and queue behind (padded with an invalid marker): 2 Mi entries of slack cover
+// 148 SMs x 64 warps x 64 entries x 3 producer kernels.
+constexpr size_t kQueueSlack = size_t(2) << 20;
 enum { Q_EXTEND = 0, Q_DIFFUSE = 1, Q_MIRROR = 2, Q_GLASS = 3 };
 
 struct PathSceneD {
     const PathNodeD* nodes;
-    const uint32_t* prim_index;
-    const PrimHot* hot;
+    const PrimHot* hot_leaf; // hot records in leaf order (n_index of them), id in q[15]
+    const PrimHot* hot;      // hot records by primitive id (shading: sphere centres)
     const PrimCold* cold;
     const MaterialD* materials;
     const LightD* lights;
@@ -67,7 +71,7 @@ struct PathWork {
     DeviceArray tp;            // float4[P]: throughput.rgb, flags (bit0: last bounce specular)
     DeviceArray hit;           // uint2[P] : t (float bits), primitive (0xffffffff = miss)
     DeviceArray L;             // float[3][P]: radiance gathered by the path so far
-    DeviceArray queues;        // uint32[5][P]: extend A, extend B, diffuse, mirror, glass
+    DeviceArray queues;        // uint32[5][P + slack]: extend A, extend B, diffuse, mirror, glass
     DeviceArray counts;        // uint32[kMaxPathDepth+1][4] queue lengths per bounce
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
     DeviceArray accum;         // float[3][n_local_pix]
@@ -118,11 +122,12 @@ struct PassArgs {
     float* L;              // 3 planes of capacity `plane`
     size_t plane;          // slots per plane (capacity)
     uint32_t* q[5];
+    size_t queue_cap;      // entries per queue (P + chunk slack)
     uint32_t* counts;      // [kMaxPathDepth+1][4]
     unsigned long long* totals;
     float* accum;          // 3 planes of n_local_pix
     // shared-memory staging (see path_kernels.cu stage_scene)
-    int32_t stage_nodes, stage_index, stage_prims, stack_levels;
+    int32_t stage_nodes, stage_prims, stack_levels;
 };
 
 void launch_extend(const PassArgs& a, int bounce, int sm_count, cudaStream_t s);

@@ -5,8 +5,8 @@
 //   extend<FIRST>   ray generation (bounce 0: regenerated from the pixel index,
 //                   no ray record is read) + linear-octree traversal + primitive
 //                   intersection; writes the 8-byte hit record; sorts the slot
-//                   into a per-material queue by warp-ballot compaction with one
-//                   atomic per CTA per queue; emitters are terminated in place
+//                   into a per-material queue by warp-ballot compaction;
+//                   emitters are terminated in place
 //   shade<KIND>     one launch per material queue (diffuse / mirror / glass):
 //                   next-event estimation with an inline any-hit traversal,
 //                   BSDF sampling, writes the 40-byte ray record of the next
@@ -22,10 +22,20 @@
 // (global pixel, sample, bounce, stream): results do not depend on queue
 // order, pass size or how tiles are split across GPUs.
 //
-// Scene access: the breadth-first prefix of the node array, of the leaf index
-// list and of the primitive records is staged into shared memory at kernel
-// start with cp.async.bulk (TMA bulk copy, one mbarrier); anything beyond the
-// staged prefix is read through L2 with read-only loads.
+// What the ncu captures of round 1 drove (profiles/):
+//   * the kernels are issue-bound, not HBM-bound -> triangle test by a precomputed affine map
+//     (6 dot products, one MUFU division, no branches), coplanar triangle pairs merged into
+//     parallelograms by the builder, leaf primitives stored contiguously (no index hop),
+//     two primitives per leaf-loop iteration (independent FMA chains)
+//   * barrier stalls from block-level compaction -> queue space is reserved in warp-private
+//     64-entry chunks: one atomic per 64 outputs, no __syncthreads, unused tail padded with
+//     an invalid marker that consumers skip
+//   * long-scoreboard stalls on the queue -> ray dependent loads -> two-deep software pipeline
+//     (slot index two iterations ahead, ray record one iteration ahead)
+//
+// Scene access: the breadth-first prefix of the node array and of the leaf-ordered primitive
+// records is staged into shared memory at kernel start with cp.async.bulk (TMA bulk copy, one
+// mbarrier); anything beyond the staged prefix is read through L2 with read-only loads.
 #include "path.h"
 
 #include <cfloat>
@@ -34,8 +44,10 @@ namespace g19 {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr float kRayEps = 1.0e-3f; // origin offset along the normal (scene units)
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kInvalid = 0xffffffffu; // padding entry of a queue / "no primitive"
+constexpr uint32_t kChunk = 64;            // queue entries reserved per atomic (>= 32)
+constexpr float kRayEps = 1.0e-3f;         // origin offset along the normal (scene units)
 constexpr float kPi = 3.14159265358979323846f;
 
 // ---- Philox4x32-10 (Salmon et al. 2011); identical integer stream in oracle/path_oracle.c
@@ -62,44 +74,33 @@ __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x *
 __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ float3 cross(float3 a, float3 b) {
-    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
-}
-__device__ __forceinline__ float3 normalize(float3 v) { return v * (1.0f / sqrtf(dot(v, v))); }
+__device__ __forceinline__ float3 normalize(float3 v) { return v * rsqrtf(dot(v, v)); }
 
 // ---- shared-memory scene prefix ----------------------------------------------
 // Dynamic shared memory, sized on the host to what the scene needs (PassArgs::stage_*):
-//   [nodes: stage_nodes x 8 B][leaf index: stage_index x 4 B][hot prims: stage_prims x 64 B]
+//   [nodes: stage_nodes x 8 B][leaf-ordered hot prims: stage_prims x 64 B]
 //   [traversal stack: stack_levels x kThreads x 4 B][mbarrier: 8 B]
-// A Cornell box stages whole (a few hundred bytes) and leaves the SM free for more CTAs.
+// A Cornell box stages whole (about 0.5 KB) and leaves the SM free for more CTAs.
 extern __shared__ __align__(16) unsigned char g19_dyn_smem[];
 
 template <bool ALL> struct SceneAccess {
     const PathSceneD* g;
     const uint2* nodes_s;
-    const uint32_t* index_s;
     const float4* hot_s;
     uint32_t* stack;
-    int n_nodes_s, n_index_s, n_prims_s;
+    int n_nodes_s, n_prims_s;
     __device__ __forceinline__ uint2 node(uint32_t i) const {
         if (ALL || i < (uint32_t)n_nodes_s) return nodes_s[i];
         return __ldg(reinterpret_cast<const uint2*>(g->nodes) + i);
     }
-    __device__ __forceinline__ uint32_t prim_index(uint32_t i) const {
-        if (ALL || i < (uint32_t)n_index_s) return index_s[i];
-        return __ldg(g->prim_index + i);
-    }
-    __device__ __forceinline__ void prim(uint32_t i, float4& a, float4& b, float4& c, float4& k) const {
-        if (ALL || i < (uint32_t)n_prims_s) {
-            a = hot_s[4 * i]; b = hot_s[4 * i + 1]; c = hot_s[4 * i + 2]; k = hot_s[4 * i + 3];
+    // k-th record of the leaf-ordered array; row 3 = (material, bsdf, kind, primitive id)
+    __device__ __forceinline__ void prim(uint32_t k, float4& a, float4& b, float4& c, float4& t) const {
+        if (ALL || k < (uint32_t)n_prims_s) {
+            a = hot_s[4 * k]; b = hot_s[4 * k + 1]; c = hot_s[4 * k + 2]; t = hot_s[4 * k + 3];
         } else {
-            const float4* p = reinterpret_cast<const float4*>(g->hot) + 4 * (size_t)i;
-            a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); k = __ldg(p + 3);
+            const float4* p = reinterpret_cast<const float4*>(g->hot_leaf) + 4 * (size_t)k;
+            a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); t = __ldg(p + 3);
         }
-    }
-    __device__ __forceinline__ float4 prim_tag(uint32_t i) const { // row 3: material, bsdf, kind
-        if (ALL || i < (uint32_t)n_prims_s) return hot_s[4 * i + 3];
-        return __ldg(reinterpret_cast<const float4*>(g->hot) + 4 * (size_t)i + 3);
     }
 };
 
@@ -111,19 +112,15 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     SceneAccess<ALL> acc;
     acc.g = &a.scene;
     acc.n_nodes_s = a.stage_nodes;
-    acc.n_index_s = a.stage_index;
     acc.n_prims_s = a.stage_prims;
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
-    const uint32_t ib = (uint32_t(a.stage_index) * 4u + 15u) & ~15u;
     const uint32_t pb = uint32_t(a.stage_prims) * 64u;
     unsigned char* base = g19_dyn_smem;
     acc.nodes_s = reinterpret_cast<const uint2*>(base);
-    acc.index_s = reinterpret_cast<const uint32_t*>(base + nb);
-    acc.hot_s = reinterpret_cast<const float4*>(base + nb + ib);
-    acc.stack = reinterpret_cast<uint32_t*>(base + nb + ib + pb) + threadIdx.x;
-    unsigned long long* barp =
-        reinterpret_cast<unsigned long long*>(base + nb + ib + pb + uint32_t(a.stack_levels) * kThreads * 4u);
+    acc.hot_s = reinterpret_cast<const float4*>(base + nb);
+    acc.stack = reinterpret_cast<uint32_t*>(base + nb + pb) + threadIdx.x;
+    unsigned long long* barp = reinterpret_cast<unsigned long long*>(base + nb + pb + uint32_t(a.stack_levels) * kThreads * 4u);
     const uint32_t bar = smem_addr(barp);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -131,25 +128,19 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + ib + pb) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + pb) : "memory");
         if (nb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(base)),
                          "l"(g.nodes), "r"(nb), "r"(bar)
                          : "memory");
-        if (ib)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_addr(base + nb)),
-                         "l"(g.prim_index), "r"(ib), "r"(bar)
-                         : "memory");
         if (pb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_addr(base + nb + ib)),
-                         "l"(g.hot), "r"(pb), "r"(bar)
+                             smem_addr(base + nb)),
+                         "l"(g.hot_leaf), "r"(pb), "r"(bar)
                          : "memory");
     }
-    // everyone waits for phase 0 of the barrier
-    uint32_t done = 0;
+    uint32_t done = 0; // everyone waits for phase 0 of the barrier
     while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
@@ -160,12 +151,13 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
 }
 
 // ---- primitive intersection ---------------------------------------------------
-// Returns t in (tmin, tmax) or -1. Triangles: the ray is mapped into the triangle's own
-// (b1, b2, h) frame by the precomputed affine rows -- 6 dot products, one fast division,
-// no branches. Spheres: unit direction, discriminant from the perpendicular offset.
-__device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 k, float3 o, float3 d, float tmin,
+// Returns t in (tmin, tmax) or -1. Triangles / parallelograms: the ray is mapped into the
+// primitive's own (b1, b2, h) frame by the precomputed affine rows -- 6 dot products, one
+// fast division, no branches. Spheres: unit direction, discriminant from the perpendicular
+// offset. tag.z = kind: 0 sphere, 1 triangle (b1+b2 <= 1), 2 parallelogram (b1, b2 <= 1).
+__device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 tag, float3 o, float3 d, float tmin,
                                           float tmax) {
-    if (k.z != 0.0f) {
+    if (tag.z != 0.0f) {
         float oz = fmaf(c.x, o.x, fmaf(c.y, o.y, fmaf(c.z, o.z, c.w)));
         float dz = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
         float t = __fdividef(-oz, dz);
@@ -174,7 +166,8 @@ __device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 k
         float oy = fmaf(b.x, o.x, fmaf(b.y, o.y, fmaf(b.z, o.z, b.w)));
         float dy = fmaf(b.x, d.x, fmaf(b.y, d.y, b.z * d.z));
         float u = fmaf(t, dx, ox), v = fmaf(t, dy, oy);
-        bool ok = (t > tmin) & (t < tmax) & (u >= 0.0f) & (v >= 0.0f) & (u + v <= 1.0f);
+        float edge = (tag.z > 1.5f) ? fmaxf(u, v) : u + v;
+        bool ok = (t > tmin) & (t < tmax) & (u >= 0.0f) & (v >= 0.0f) & (edge <= 1.0f);
         return ok ? t : -1.0f;
     }
     float3 oc = o - f3(a.x, a.y, a.z);
@@ -205,86 +198,96 @@ __device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tm
                          uint32_t& prim_hit) {
     const PathSceneD& g = *S.g;
     uint32_t* const stack = S.stack;
+    float best = tmax;
+    uint32_t best_prim = kInvalid;
+
+    auto leaf = [&](uint32_t first, uint32_t n) -> bool {
+        uint32_t k = 0;
+        for (; k + 2 <= n; k += 2) { // two primitives per step: independent FMA chains, loads up front
+            float4 a0, b0, c0, g0, a1, b1, c1, g1;
+            S.prim(first + k, a0, b0, c0, g0);
+            S.prim(first + k + 1, a1, b1, c1, g1);
+            float t0 = hit_prim(a0, b0, c0, g0, o, d, tmin, best);
+            float t1 = hit_prim(a1, b1, c1, g1, o, d, tmin, best);
+            if (t0 >= 0.0f) { best = t0; best_prim = __float_as_uint(g0.w); }
+            if (t1 >= 0.0f && t1 < best) { best = t1; best_prim = __float_as_uint(g1.w); }
+            if (ANY && best_prim != kInvalid) return true;
+        }
+        if (k < n) {
+            float4 a0, b0, c0, g0;
+            S.prim(first + k, a0, b0, c0, g0);
+            float t0 = hit_prim(a0, b0, c0, g0, o, d, tmin, best);
+            if (t0 >= 0.0f) { best = t0; best_prim = __float_as_uint(g0.w); }
+            if (ANY && best_prim != kInvalid) return true;
+        }
+        return false;
+    };
+
+    const uint2 root = S.node(0);
+    if (root.y & kLeafBit) { // the whole scene is one leaf (e.g. the Cornell configs): no boxes to test
+        leaf(root.x, root.y & ~kLeafBit);
+        t_hit = best;
+        prim_hit = best_prim;
+        return best_prim != kInvalid;
+    }
+
     float3 dd = d;
     if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
     if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
     if (fabsf(dd.z) < 1.0e-20f) dd.z = copysignf(1.0e-20f, dd.z);
-    const float3 inv = f3(1.0f / dd.x, 1.0f / dd.y, 1.0f / dd.z);
+    const float3 inv = f3(__fdividef(1.0f, dd.x), __fdividef(1.0f, dd.y), __fdividef(1.0f, dd.z));
     const uint32_t a = (dd.x < 0.0f ? 1u : 0u) | (dd.y < 0.0f ? 2u : 0u) | (dd.z < 0.0f ? 4u : 0u);
-    float best = tmax;
-    uint32_t best_prim = 0xffffffffu;
-
-    auto leaf = [&](uint32_t first, uint32_t n) -> bool {
-        for (uint32_t k = 0; k < n; ++k) {
-            uint32_t pi = S.prim_index(first + k);
-            float4 qa, qb, qc, qk;
-            S.prim(pi, qa, qb, qc, qk);
-            float t = hit_prim(qa, qb, qc, qk, o, d, tmin, best);
-            if (t >= 0.0f) {
-                best = t;
-                best_prim = pi;
-                if (ANY) return true;
-            }
-        }
-        return false;
-    };
     auto slab = [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float& tn, float& tf) {
         float x0 = (lox - o.x) * inv.x, x1 = (hix - o.x) * inv.x;
         float y0 = (loy - o.y) * inv.y, y1 = (hiy - o.y) * inv.y;
         float z0 = (loz - o.z) * inv.z, z1 = (hiz - o.z) * inv.z;
         tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
         tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-        tf = tf * 1.0000005f + 1.0e-6f; // conservative: never cull a cell the ray grazes
-        tn = tn - fabsf(tn) * 5.0e-7f - 1.0e-6f;
+        tf = tf * 1.000002f + 1.0e-5f; // conservative: never cull a cell the ray grazes
+        tn = tn - fabsf(tn) * 2.0e-6f - 1.0e-5f;
     };
-
-    uint2 root = S.node(0);
     {
         float tn, tf;
         slab(g.root_lo[0], g.root_lo[1], g.root_lo[2], g.root_lo[0] + g.root_size[0], g.root_lo[1] + g.root_size[1],
              g.root_lo[2] + g.root_size[2], tn, tf);
         if (tn > fminf(tf, best) || tf < tmin) return false;
     }
-    if (root.y & kLeafBit) {
-        leaf(root.x, root.y & ~kLeafBit);
-    } else {
-        int level = 0;
-        uint32_t ix = 0, iy = 0, iz = 0;
-        unsigned long long iters = 0;
-        stack[0] = root.x;
-        while (true) {
-            uint32_t i = uint32_t(iters >> (4 * level)) & 0xFu;
-            if (i >= 8u) {
-                if (level == 0) break;
-                --level;
-                ix >>= 1; iy >>= 1; iz >>= 1;
-                continue;
-            }
-            iters += 1ull << (4 * level);
-            uint32_t c = i ^ a;
-            uint2 rec = S.node(stack[level * kThreads] + c);
-            if (rec.y == kLeafBit) continue; // empty octant
-            uint32_t cx = 2u * ix + (c & 1u), cy = 2u * iy + ((c >> 1) & 1u), cz = 2u * iz + ((c >> 2) & 1u);
-            float scale = __int_as_float((127 - (level + 1)) << 23); // 2^-(level+1), exact
-            float sx = g.root_size[0] * scale, sy = g.root_size[1] * scale, sz = g.root_size[2] * scale;
-            float tn, tf;
-            slab(cell_edge(g.root_lo[0], sx, cx), cell_edge(g.root_lo[1], sy, cy), cell_edge(g.root_lo[2], sz, cz),
-                 cell_edge(g.root_lo[0], sx, cx + 1), cell_edge(g.root_lo[1], sy, cy + 1),
-                 cell_edge(g.root_lo[2], sz, cz + 1), tn, tf);
-            if (tn > fminf(tf, best) || tf < tmin) continue;
-            if (rec.y & kLeafBit) {
-                if (leaf(rec.x, rec.y & ~kLeafBit)) break;
-            } else {
-                ++level;
-                stack[level * kThreads] = rec.x;
-                ix = cx; iy = cy; iz = cz;
-                iters &= ~(0xFull << (4 * level));
-            }
+    int level = 0;
+    uint32_t ix = 0, iy = 0, iz = 0;
+    unsigned long long iters = 0;
+    stack[0] = root.x;
+    while (true) {
+        uint32_t i = uint32_t(iters >> (4 * level)) & 0xFu;
+        if (i >= 8u) {
+            if (level == 0) break;
+            --level;
+            ix >>= 1; iy >>= 1; iz >>= 1;
+            continue;
+        }
+        iters += 1ull << (4 * level);
+        uint32_t c = i ^ a;
+        uint2 rec = S.node(stack[level * kThreads] + c);
+        if (rec.y == kLeafBit) continue; // empty octant
+        uint32_t cx = 2u * ix + (c & 1u), cy = 2u * iy + ((c >> 1) & 1u), cz = 2u * iz + ((c >> 2) & 1u);
+        float scale = __int_as_float((127 - (level + 1)) << 23); // 2^-(level+1), exact
+        float sx = g.root_size[0] * scale, sy = g.root_size[1] * scale, sz = g.root_size[2] * scale;
+        float tn, tf;
+        slab(cell_edge(g.root_lo[0], sx, cx), cell_edge(g.root_lo[1], sy, cy), cell_edge(g.root_lo[2], sz, cz),
+             cell_edge(g.root_lo[0], sx, cx + 1), cell_edge(g.root_lo[1], sy, cy + 1), cell_edge(g.root_lo[2], sz, cz + 1),
+             tn, tf);
+        if (tn > fminf(tf, best) || tf < tmin) continue;
+        if (rec.y & kLeafBit) {
+            if (leaf(rec.x, rec.y & ~kLeafBit)) break;
+        } else {
+            ++level;
+            stack[level * kThreads] = rec.x;
+            ix = cx; iy = cy; iz = cz;
+            iters &= ~(0xFull << (4 * level));
         }
     }
     t_hit = best;
     prim_hit = best_prim;
-    return best_prim != 0xffffffffu;
+    return best_prim != kInvalid;
 }
 
 // ---- per-slot helpers ------------------------------------------------------------
@@ -312,38 +315,40 @@ __device__ __forceinline__ void camera_ray(const PassArgs& a, int x, int y, uint
     d = normalize(v);
 }
 
-// Warp-ballot compaction into NK queues with ONE atomic per CTA per queue.
-template <int NK> struct AppendSmem {
-    uint32_t wcount[NK][kWarps];
-    uint32_t wbase[NK][kWarps];
+// Warp-ballot compaction into a queue whose space the warp reserves in private chunks of
+// kChunk entries: one atomic per kChunk outputs, no block barrier. Must be called by all
+// 32 lanes of a converged warp.
+struct WarpCursor {
+    uint32_t pos, end; // warp-uniform
 };
 
-template <int NK>
-__device__ __forceinline__ void block_append(AppendSmem<NK>& sm, int kind, uint32_t value, uint32_t* const (&queue)[NK],
-                                             uint32_t* const (&counter)[NK]) {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t mine = 0;
-#pragma unroll
-    for (int k = 0; k < NK; ++k) {
-        uint32_t m = __ballot_sync(0xffffffffu, kind == k);
-        if (lane == 0) sm.wcount[k][warp] = __popc(m);
-        if (kind == k) mine = m;
+__device__ __forceinline__ void warp_append(WarpCursor& c, bool want, uint32_t value, uint32_t* __restrict__ queue,
+                                            uint32_t* __restrict__ counter) {
+    const uint32_t m = __ballot_sync(kFull, want);
+    if (m == 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+    const uint32_t room = c.end - c.pos, base0 = c.pos;
+    uint32_t base1 = 0;
+    if (n > room) { // the tail goes to a fresh chunk
+        if (lane == 0) base1 = atomicAdd(counter, kChunk);
+        base1 = __shfl_sync(kFull, base1, 0);
+        c.pos = base1 + (n - room);
+        c.end = base1 + kChunk;
+    } else {
+        c.pos += n;
     }
-    __syncthreads();
-    if (threadIdx.x < NK) {
-        const int k = threadIdx.x;
-        uint32_t total = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) total += sm.wcount[k][w];
-        uint32_t base = total ? atomicAdd(counter[k], total) : 0u;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            sm.wbase[k][w] = base;
-            base += sm.wcount[k][w];
-        }
-    }
-    __syncthreads();
-    if (kind >= 0) queue[kind][sm.wbase[kind][warp] + __popc(mine & ((1u << lane) - 1u))] = value;
+    if (want) queue[rank < room ? base0 + rank : base1 + (rank - room)] = value;
+}
+
+// Pad what is left of the warp's last chunk so that consumers can skip it.
+__device__ __forceinline__ void warp_flush(const WarpCursor& c, uint32_t* __restrict__ queue) {
+    for (uint32_t i = c.pos + (threadIdx.x & 31u); i < c.end; i += 32u) queue[i] = kInvalid;
+}
+
+__device__ __forceinline__ unsigned warp_sum(unsigned v) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
 }
 
 __device__ __forceinline__ void add_radiance(const PassArgs& a, uint32_t slot, float3 v) {
@@ -356,56 +361,84 @@ __device__ __forceinline__ void add_radiance(const PassArgs& a, uint32_t slot, f
 // ---- extend ------------------------------------------------------------------------
 template <bool FIRST, bool ALL>
 __global__ void __launch_bounds__(kThreads, 4) extend_kernel(const PassArgs a, const int bounce) {
-    __shared__ AppendSmem<3> app_sm;
     const SceneAccess<ALL> S = stage_scene<ALL>(a);
-
     const uint32_t n = FIRST ? a.n_slots : a.counts[bounce * 4 + Q_EXTEND];
     const uint32_t* __restrict__ qin = a.q[bounce & 1];
-    uint32_t* const queues[3] = {a.q[2], a.q[3], a.q[4]};
-    uint32_t* const counters[3] = {a.counts + bounce * 4 + Q_DIFFUSE, a.counts + bounce * 4 + Q_MIRROR,
-                                   a.counts + bounce * 4 + Q_GLASS};
+    WarpCursor cur0 = {0, 0}, cur1 = {0, 0}, cur2 = {0, 0};
+    uint32_t* const counters = a.counts + bounce * 4 + Q_DIFFUSE; // diffuse, mirror, glass are adjacent
     const uint32_t stride = gridDim.x * kThreads;
-    for (uint32_t base = blockIdx.x * kThreads; base < n; base += stride) {
-        const uint32_t q = base + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned traced = 0;
+
+    uint32_t q = blockIdx.x * kThreads + threadIdx.x;
+    // two-deep pipeline: slot index two iterations ahead, ray record one iteration ahead
+    uint32_t s_cur = kInvalid, s_nxt = kInvalid;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 r1 = make_float2(0.f, 0.f);
+    if (!FIRST) {
+        if (q < n) s_cur = qin[q];
+        if (q + stride < n && q + stride >= q) s_nxt = qin[q + stride];
+        if (s_cur != kInvalid) { r0 = a.ro[s_cur]; r1 = a.rd[s_cur]; }
+    }
+    for (; q - lane < n; q += stride) { // warp-uniform trip count
+        uint32_t s_nn = kInvalid;
+        float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 n1 = make_float2(0.f, 0.f);
+        if (!FIRST) {
+            const uint32_t q2 = q + 2u * stride;
+            if (q2 < n && q2 > q) s_nn = qin[q2];
+            if (s_nxt != kInvalid) { n0 = a.ro[s_nxt]; n1 = a.rd[s_nxt]; }
+        }
+        const uint32_t slot = FIRST ? q : s_cur;
         int kind = -1;
-        uint32_t slot = 0;
-        if (q < n) {
-            slot = FIRST ? q : qin[q];
-            float3 o, d;
-            bool live = true;
+        bool live = FIRST ? (q < n) : (slot != kInvalid);
+        float3 o, d;
+        if (live) {
             if (FIRST) {
                 int x, y;
                 uint32_t sample;
                 live = slot_pixel(a, slot, x, y, sample);
                 if (live) camera_ray(a, x, y, sample, o, d);
             } else {
-                float4 r0 = a.ro[slot];
-                float2 r1 = a.rd[slot];
                 o = f3(r0.x, r0.y, r0.z);
                 d = f3(r0.w, r1.x, r1.y);
             }
-            if (live) {
-                float t = FLT_MAX;
-                uint32_t prim = 0xffffffffu;
-                bool hit = traverse<false, ALL>(S, o, d, 0.0f, FLT_MAX, t, prim);
-                a.hit[slot] = make_uint2(__float_as_uint(t), prim);
-                if (hit) {
-                    const float4 tag = S.prim_tag(prim); // material class rides in the hot record
-                    int bsdf = __float_as_int(tag.y);
-                    if (bsdf == G19_BSDF_EMITTER) {
-                        // emission counts on camera rays and after specular bounces only (NEE covers the rest)
-                        float4 T = FIRST ? make_float4(1.f, 1.f, 1.f, 0.f) : a.tp[slot];
-                        if (FIRST || (__float_as_uint(T.w) & 1u)) {
-                            const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
-                            add_radiance(a, slot, f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]));
-                        }
-                    } else {
-                        kind = bsdf;
+        }
+        if (live) {
+            float t = FLT_MAX;
+            uint32_t prim = kInvalid;
+            ++traced;
+            const bool hit = traverse<false, ALL>(S, o, d, 0.0f, FLT_MAX, t, prim);
+            a.hit[slot] = make_uint2(__float_as_uint(t), prim);
+            if (hit) {
+                const float4 tag = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 4 * (size_t)prim + 3);
+                const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
+                if (bsdf == G19_BSDF_EMITTER) {
+                    // emission counts on camera rays and after specular bounces only (NEE covers the rest)
+                    const float4 T = FIRST ? make_float4(1.f, 1.f, 1.f, 0.f) : a.tp[slot];
+                    if (FIRST || (__float_as_uint(T.w) & 1u)) {
+                        const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
+                        add_radiance(a, slot, f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]));
                     }
+                } else {
+                    kind = bsdf;
                 }
             }
         }
-        block_append<3>(app_sm, kind, slot, queues, counters);
+        warp_append(cur0, kind == G19_BSDF_DIFFUSE, slot, a.q[2], counters + 0);
+        warp_append(cur1, kind == G19_BSDF_MIRROR, slot, a.q[3], counters + 1);
+        warp_append(cur2, kind == G19_BSDF_GLASS, slot, a.q[4], counters + 2);
+        if (!FIRST) {
+            s_cur = s_nxt; s_nxt = s_nn;
+            r0 = n0; r1 = n1;
+        }
+    }
+    warp_flush(cur0, a.q[2]);
+    warp_flush(cur1, a.q[3]);
+    warp_flush(cur2, a.q[4]);
+    if (!FIRST) {
+        traced = warp_sum(traced);
+        if (lane == 0 && traced) atomicAdd(a.totals + 0, (unsigned long long)traced);
     }
 }
 
@@ -418,25 +451,54 @@ __device__ __forceinline__ void onb(float3 n, float3& t, float3& b) { // Duff et
     b = f3(bb, s + n.y * n.y * a, -n.y);
 }
 
+struct ShadeIn { // what one surface interaction reads from the wavefront state
+    uint2 hit;
+    float4 r0;
+    float2 r1;
+    float4 tp;
+};
+
+template <bool FIRST> __device__ __forceinline__ void load_shade_in(const PassArgs& a, uint32_t slot, ShadeIn& in) {
+    in.hit = a.hit[slot];
+    if (!FIRST) {
+        in.r0 = a.ro[slot];
+        in.r1 = a.rd[slot];
+        in.tp = a.tp[slot];
+    }
+}
+
 template <int KIND, bool FIRST, bool ALL>
 __global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_kernel(const PassArgs a, const int bounce) {
-    __shared__ AppendSmem<1> app_sm;
     SceneAccess<ALL> S;
     if (KIND == Q_DIFFUSE) S = stage_scene<ALL>(a); // shadow rays traverse
-
     const uint32_t n = a.counts[bounce * 4 + KIND];
     const uint32_t* __restrict__ qin = a.q[1 + KIND];
-    uint32_t* const queues[1] = {a.q[(bounce + 1) & 1]};
-    uint32_t* const counters[1] = {a.counts + (bounce + 1) * 4 + Q_EXTEND};
+    uint32_t* __restrict__ qout = a.q[(bounce + 1) & 1];
+    uint32_t* __restrict__ cout = a.counts + (bounce + 1) * 4 + Q_EXTEND;
     const bool more = bounce + 1 < a.max_depth;
-    unsigned shadow_rays = 0, lit = 0;
+    WarpCursor cur = {0, 0};
+    unsigned shadow_rays = 0, lit = 0, calls = 0;
     const uint32_t stride = gridDim.x * kThreads;
-    for (uint32_t base = blockIdx.x * kThreads; base < n; base += stride) {
-        const uint32_t q = base + threadIdx.x;
-        int kind = -1;
-        uint32_t slot = 0;
-        if (q < n) {
-            slot = qin[q];
+    const uint32_t lane = threadIdx.x & 31u;
+
+    uint32_t q = blockIdx.x * kThreads + threadIdx.x;
+    uint32_t s_cur = kInvalid, s_nxt = kInvalid;
+    ShadeIn in = {};
+    if (q < n) s_cur = qin[q];
+    if (q + stride < n && q + stride >= q) s_nxt = qin[q + stride];
+    if (s_cur != kInvalid) load_shade_in<FIRST>(a, s_cur, in);
+    for (; q - lane < n; q += stride) {
+        uint32_t s_nn = kInvalid;
+        ShadeIn nx = {};
+        {
+            const uint32_t q2 = q + 2u * stride;
+            if (q2 < n && q2 > q) s_nn = qin[q2];
+            if (s_nxt != kInvalid) load_shade_in<FIRST>(a, s_nxt, nx);
+        }
+        const uint32_t slot = s_cur;
+        bool go_on = false;
+        if (slot != kInvalid) {
+            ++calls;
             int x, y;
             uint32_t sample;
             slot_pixel(a, slot, x, y, sample);
@@ -445,16 +507,12 @@ __global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_ker
                 camera_ray(a, x, y, sample, o, d);
                 T = f3(1.f, 1.f, 1.f);
             } else {
-                float4 r0 = a.ro[slot];
-                float2 r1 = a.rd[slot];
-                float4 tp = a.tp[slot];
-                o = f3(r0.x, r0.y, r0.z);
-                d = f3(r0.w, r1.x, r1.y);
-                T = f3(tp.x, tp.y, tp.z);
+                o = f3(in.r0.x, in.r0.y, in.r0.z);
+                d = f3(in.r0.w, in.r1.x, in.r1.y);
+                T = f3(in.tp.x, in.tp.y, in.tp.z);
             }
-            const uint2 h = a.hit[slot];
-            const float t = __uint_as_float(h.x);
-            const uint32_t prim = h.y;
+            const float t = __uint_as_float(in.hit.x);
+            const uint32_t prim = in.hit.y;
             const float3 p = o + d * t;
             const PrimCold cold = a.scene.cold[prim];
             const MaterialD mat = a.scene.materials[cold.material];
@@ -463,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_ker
                 const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 4 * (size_t)prim);
                 const float4 q3 = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 4 * (size_t)prim + 3);
                 if (q3.z != 0.0f) ng = f3(cold.n[0], cold.n[1], cold.n[2]);
-                else ng = (p - f3(q0.x, q0.y, q0.z)) * (1.0f / q0.w);
+                else ng = (p - f3(q0.x, q0.y, q0.z)) * __fdividef(1.0f, q0.w);
             }
             const bool entering = dot(ng, d) < 0.0f;
             const float3 nf = entering ? ng : -ng; // normal on the side the ray arrives from
@@ -485,8 +543,9 @@ __global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_ker
                                    lt.v0[2] + lt.e1[2] * b1 + lt.e2[2] * b2);
                     float3 w = yl - p;
                     float dist2 = dot(w, w);
-                    float dist = sqrtf(dist2);
-                    w = w * (1.0f / dist);
+                    float inv_dist = rsqrtf(dist2);
+                    float dist = dist2 * inv_dist;
+                    w = w * inv_dist;
                     float cs = dot(nf, w);
                     float cl = fabsf(dot(f3(lt.n[0], lt.n[1], lt.n[2]), w));
                     if (cs > 0.0f && cl > 0.0f && dist > 2.0f * kRayEps) {
@@ -496,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_ker
                         bool blocked = traverse<true, ALL>(S, p + nf * kRayEps, w, 0.0f, dist - 2.0f * kRayEps, tt, pp);
                         if (!blocked) {
                             ++lit;
-                            float gterm = cs * cl * lt.area / (dist2 * lt.pdf_pick) * (1.0f / kPi);
+                            float gterm = cs * cl * lt.area * __fdividef(1.0f, dist2 * lt.pdf_pick) * (1.0f / kPi);
                             add_radiance(a, slot, f3(T.x * albedo.x * lt.emission[0] * gterm,
                                                      T.y * albedo.y * lt.emission[1] * gterm,
                                                      T.z * albedo.z * lt.emission[2] * gterm));
@@ -505,9 +564,10 @@ __global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_ker
                 }
                 // cosine-weighted bounce: pdf cancels cos/pi, throughput *= albedo
                 float u3 = u01(r.z), u4 = u01(r.w);
-                float rr = sqrtf(u3), phi = 2.0f * kPi * u4;
+                float rr = sqrtf(u3), phi = 2.0f * kPi * u4 - kPi; // [-pi, pi): MUFU range
                 float sp, cp;
-                sincosf(phi, &sp, &cp);
+                __sincosf(phi, &sp, &cp);
+                sp = -sp; cp = -cp; // shift back by pi
                 float3 tx, ty;
                 onb(nf, tx, ty);
                 nd = normalize(tx * (rr * cp) + ty * (rr * sp) + nf * sqrtf(fmaxf(0.0f, 1.0f - u3)));
@@ -545,20 +605,22 @@ __global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_ker
                 a.ro[slot] = make_float4(no.x, no.y, no.z, nd.x);
                 a.rd[slot] = make_float2(nd.y, nd.z);
                 a.tp[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(flags));
-                kind = 0;
+                go_on = true;
             }
         }
-        block_append<1>(app_sm, kind, slot, queues, counters);
+        warp_append(cur, go_on, slot, qout, cout);
+        s_cur = s_nxt; s_nxt = s_nn;
+        in = nx;
     }
-    if (KIND == Q_DIFFUSE) {
-        for (int off = 16; off > 0; off >>= 1) {
-            shadow_rays += __shfl_xor_sync(0xffffffffu, shadow_rays, off);
-            lit += __shfl_xor_sync(0xffffffffu, lit, off);
-        }
-        if ((threadIdx.x & 31) == 0 && shadow_rays) {
-            atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
-            atomicAdd(a.totals + 4, (unsigned long long)lit);
-        }
+    warp_flush(cur, qout);
+    calls = warp_sum(calls);
+    shadow_rays = warp_sum(shadow_rays);
+    lit = warp_sum(lit);
+    if (lane == 0 && calls) {
+        atomicAdd(a.totals + 2, (unsigned long long)calls);
+        if (FIRST) atomicAdd(a.totals + 3, (unsigned long long)calls);
+        if (shadow_rays) atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
+        if (lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
     }
 }
 
@@ -601,20 +663,9 @@ __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) 
         a.accum[(size_t)npix + lp] = acc1;
         a.accum[2 * (size_t)npix + lp] = acc2;
     }
-    // fold this pass's queue lengths into the running totals and clear them
-    if (blockIdx.x == 0) {
-        for (int i = threadIdx.x; i < (kMaxPathDepth + 1) * 4; i += kThreads) {
-            uint32_t v = a.counts[i];
-            if (v) {
-                if ((i & 3) == Q_EXTEND) atomicAdd(a.totals + 0, (unsigned long long)v);
-                else {
-                    atomicAdd(a.totals + 2, (unsigned long long)v);
-                    if (i < 4) atomicAdd(a.totals + 3, (unsigned long long)v);
-                }
-                a.counts[i] = 0;
-            }
-        }
-    }
+    // the pass is over: clear its queue lengths for the next one
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < (kMaxPathDepth + 1) * 4; i += kThreads) a.counts[i] = 0;
 }
 
 __global__ void __launch_bounds__(kThreads) resolve_kernel(TileMap map, const float* __restrict__ accum, int spp,
@@ -624,14 +675,12 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(TileMap map, const fl
     if (lp >= npix) return;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float v = accum[(size_t)c * npix + lp] / float(spp);
+        float v = __fdiv_rn(accum[(size_t)c * npix + lp], float(spp));
         rad_l[3 * (size_t)lp + c] = v;
         float cl = fminf(fmaxf(v, 0.0f), 1.0f);
         rgb_l[3 * (size_t)lp + c] = (uint8_t)(int)(255.0f * cl); // truncation, as Image::setPixel
     }
 }
-
-} // namespace
 
 // Persistent grids: SM count x the CTAs the occupancy calculator says are resident.
 template <typename K> static int resident_grid(K kernel, size_t smem, int sm_count) {
@@ -644,12 +693,11 @@ template <typename K> static int resident_grid(K kernel, size_t smem, int sm_cou
 size_t path_smem_bytes(const PassArgs& a, bool with_scene) {
     if (!with_scene) return 0;
     size_t nb = (size_t(a.stage_nodes) * 8 + 15) & ~size_t(15);
-    size_t ib = (size_t(a.stage_index) * 4 + 15) & ~size_t(15);
-    return nb + ib + size_t(a.stage_prims) * 64 + size_t(a.stack_levels) * kThreads * 4 + 16;
+    return nb + size_t(a.stage_prims) * 64 + size_t(a.stack_levels) * kThreads * 4 + 16;
 }
 
 static bool all_staged(const PassArgs& a) {
-    return a.stage_nodes >= a.scene.n_nodes && a.stage_index >= a.scene.n_index && a.stage_prims >= a.scene.n_prims;
+    return a.stage_nodes >= a.scene.n_nodes && a.stage_prims >= a.scene.n_index;
 }
 
 // The grid of a persistent kernel = SM count x resident CTAs, cached per (kernel, smem size).
@@ -667,6 +715,8 @@ template <typename K> static void launch_persistent(K kernel, const PassArgs& a,
     }
     kernel<<<grid, kThreads, smem, s>>>(a, bounce);
 }
+
+} // namespace
 
 void launch_extend(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a, true);
