@@ -54,12 +54,14 @@ static_assert(sizeof(RefEntityD) == 192, "RefEntityD layout");
 struct alignas(16) PrimHot {
     float q[16];
 };
-// Cold shading record, 32 B: geometric normal (triangles), material, entity id.
+// Cold shading record, 32 B = 2 x float4: everything a surface interaction needs in ONE hop
+// from the hit record -- geometric normal (triangles), index of refraction, albedo, and the
+// material index (emitters look their radiance up in materials[]).
 struct alignas(16) PrimCold {
     float n[3];
+    float ior;
+    float albedo[3];
     int32_t material; // index into materials[]
-    int32_t entity;
-    int32_t pad[3];
 };
 struct alignas(16) MaterialD {
     float albedo[3];

@@ -94,7 +94,7 @@ void add_triangle(std::vector<BuildPrim>& out, const HostTri& t, int material, i
     if (len > 0) { nx /= len; ny /= len; nz /= len; }
     p.cold.n[0] = float(nx); p.cold.n[1] = float(ny); p.cold.n[2] = float(nz);
     p.cold.material = material;
-    p.cold.entity = entity;
+    (void)entity;
     for (int k = 0; k < 3; ++k) {
         p.box.lo[k] = std::min(v0[k], std::min(v1[k], v2[k]));
         p.box.hi[k] = std::max(v0[k], std::max(v1[k], v2[k]));
@@ -111,7 +111,7 @@ void add_sphere(std::vector<BuildPrim>& out, const HostEntity& e, int material, 
     q[14] = 0.0f; // kind = sphere
     p.tri = false;
     p.cold.material = material;
-    p.cold.entity = entity;
+    (void)entity;
     for (int k = 0; k < 3; ++k) {
         p.box.lo[k] = c[k] - e.radius;
         p.box.hi[k] = c[k] + e.radius;
@@ -165,6 +165,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         // material index and class ride in the spare words of the hot record
         auto tag = [&](BuildPrim& p) {
             int32_t mat_bits = mi, bsdf_bits = m.bsdf;
+            p.cold.ior = m.ior;
+            p.cold.albedo[0] = m.albedo[0]; p.cold.albedo[1] = m.albedo[1]; p.cold.albedo[2] = m.albedo[2];
             std::memcpy(&p.hot.q[12], &mat_bits, 4);
             std::memcpy(&p.hot.q[13], &bsdf_bits, 4);
         };
