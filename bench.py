@@ -293,10 +293,12 @@ def main():
     n_launch = {"extend": agg["launch"][abi.K_EXTEND], "shade": agg["launch"][abi.K_SHADE],
                 "accumulate": agg["launch"][abi.K_ACCUM]}
     achieved = bytes_cls[top] / (ms_cls[top] * 1e-3) / 1e9 if ms_cls[top] > 0 else 0.0
-    traffic = None
+    traffic, issue_pct = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(top)
+            tj = json.load(f)
+            traffic = tj.get(top)
+            issue_pct = tj.get("issue_active_pct", {}).get(top)
     except Exception:
         pass
     total_bytes = sum(bytes_cls.values())
@@ -306,6 +308,7 @@ def main():
         "bytes_per_launch": bytes_cls[top] / max(1, n_launch[top]),
         "avg_launch_ms": ms_cls[top] / max(1, n_launch[top]),
         "share_of_step": ms_cls[top] / max(1e-9, sum(cls_ms)),
+        "binding_resource": "issue slots (ncu: smsp__issue_active %s%% of peak, DRAM ~15%%) -- see DESIGN.md section 5" % issue_pct,
         "per_class": {k: {"ms_per_step": ms_cls[k] / args.steps, "launches_per_step": n_launch[k] / args.steps,
                           "algorithmic_GB_per_step": bytes_cls[k] / args.steps / 1e9,
                           "GBps": (bytes_cls[k] / (ms_cls[k] * 1e-3) / 1e9) if ms_cls[k] > 0 else None}
