@@ -17,6 +17,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -261,7 +263,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     }
 
     // ---- linear octree, breadth first ------------------------------------------
-    const int kLeafMax = 8;
+    int kLeafMax = 8;
+    if (const char* v = std::getenv("G19_LEAF_MAX")) kLeafMax = std::max(1, std::atoi(v)); // tuning knob
     float root_lo[3] = {float(scene.rmin.x), float(scene.rmin.y), float(scene.rmin.z)};
     float root_hi[3] = {float(scene.rmax.x), float(scene.rmax.y), float(scene.rmax.z)};
     for (int k = 0; k < 3; ++k) { // the root box must enclose every primitive
@@ -331,6 +334,19 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         frontier.swap(next);
     }
 
+    if (std::getenv("G19_DEBUG_TREE")) {
+        size_t leaves = 0, empty = 0, biggest = 0;
+        for (const PathNodeD& n : nodes)
+            if (n.count & kLeafBit) {
+                size_t c = n.count & ~kLeafBit;
+                if (c) { ++leaves; biggest = std::max(biggest, c); } else ++empty;
+            }
+        std::fprintf(stderr, "[g19] path octree: %zu prims, %zu nodes, depth %d, %zu leaves (+%zu empty), %zu refs "
+                             "(%.2f per prim, %.1f per leaf, max %zu)\n",
+                     prims.size(), nodes.size(), tree_depth, leaves, empty, index.size(),
+                     double(index.size()) / double(std::max<size_t>(1, prims.size())),
+                     double(index.size()) / double(std::max<size_t>(1, leaves)), biggest);
+    }
     std::vector<PrimHot> hot(prims.size());
     std::vector<PrimCold> cold(prims.size());
     for (size_t i = 0; i < prims.size(); ++i) {
@@ -530,10 +546,12 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     clk.begin();
     launch_resolve(a.map, pa.accum, done_spp > 0 ? done_spp : 1, static_cast<float*>(w.rad_l.p),
                    static_cast<uint8_t*>(w.rgb_l.p), s);
-    launch_untile(a.map, a.d_rgb ? static_cast<uint8_t*>(w.rgb_l.p) : nullptr, nullptr,
-                  a.d_rad ? static_cast<float*>(w.rad_l.p) : nullptr, a.d_rgb, nullptr, a.d_rad, s);
+    const bool to_frame = a.d_rgb || a.d_rad;
+    if (to_frame)
+        launch_untile(a.map, a.d_rgb ? static_cast<uint8_t*>(w.rgb_l.p) : nullptr, nullptr,
+                      a.d_rad ? static_cast<float*>(w.rad_l.p) : nullptr, a.d_rgb, nullptr, a.d_rad, s);
     clk.end(G19_K_OTHER);
-    stats.class_launches[G19_K_OTHER] += 2;
+    stats.class_launches[G19_K_OTHER] += to_frame ? 2 : 1;
     if (a.t_rad) PATH_CUDA(cudaMemcpyAsync(a.t_rad, w.rad_l.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (a.t_rgb) PATH_CUDA(cudaMemcpyAsync(a.t_rgb, w.rgb_l.p, npix * 3, cudaMemcpyDeviceToDevice, s));
     PATH_CUDA(cudaGetLastError());

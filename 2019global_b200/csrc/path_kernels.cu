@@ -224,66 +224,90 @@ __device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tm
     };
 
     const uint2 root = S.node(0);
-    if (root.y & kLeafBit) { // the whole scene is one leaf (e.g. the Cornell configs): no boxes to test
+    // ALL = the scene is ONE leaf and fully staged (the Cornell configs): the tree walk below is
+    // compiled out of those kernels, which keeps them at 4 (extend) / 3 (shade) CTAs per SM.
+    if (ALL || (root.y & kLeafBit)) {
         leaf(root.x, root.y & ~kLeafBit);
         t_hit = best;
         prim_hit = best_prim;
         return best_prim != kInvalid;
     }
+    if (ALL) return false; // unreachable; lets the compiler drop the walk
 
+    // Parametric front-to-back walk (after Revelles et al. 2000). In the frame where the ray
+    // direction is positive on every axis (octant bits XOR a), a cell is described per axis by
+    // the ray parameters of its entry plane t0, mid plane tm and exit plane t1. The first child
+    // is the one whose mid planes lie before the entry point; the next child is reached through
+    // the exit plane with the smallest parameter. Only the (at most four) children the ray
+    // pierces are visited, strictly in order, so the walk stops at the first leaf whose hit lies
+    // inside its own cell. Per level the state is one 4-bit child code; the planes are recomputed
+    // from the integer cell coordinates with the builder's own cell_edge expression.
     float3 dd = d;
     if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
     if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
     if (fabsf(dd.z) < 1.0e-20f) dd.z = copysignf(1.0e-20f, dd.z);
     const float3 inv = f3(__fdividef(1.0f, dd.x), __fdividef(1.0f, dd.y), __fdividef(1.0f, dd.z));
     const uint32_t a = (dd.x < 0.0f ? 1u : 0u) | (dd.y < 0.0f ? 2u : 0u) | (dd.z < 0.0f ? 4u : 0u);
-    auto slab = [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float& tn, float& tf) {
-        float x0 = (lox - o.x) * inv.x, x1 = (hix - o.x) * inv.x;
-        float y0 = (loy - o.y) * inv.y, y1 = (hiy - o.y) * inv.y;
-        float z0 = (loz - o.z) * inv.z, z1 = (hiz - o.z) * inv.z;
-        tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
-        tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-        tf = tf * 1.000002f + 1.0e-5f; // conservative: never cull a cell the ray grazes
-        tn = tn - fabsf(tn) * 2.0e-6f - 1.0e-5f;
-    };
-    {
-        float tn, tf;
-        slab(g.root_lo[0], g.root_lo[1], g.root_lo[2], g.root_lo[0] + g.root_size[0], g.root_lo[1] + g.root_size[1],
-             g.root_lo[2] + g.root_size[2], tn, tf);
-        if (tn > fminf(tf, best) || tf < tmin) return false;
-    }
     int level = 0;
     uint32_t ix = 0, iy = 0, iz = 0;
-    unsigned long long iters = 0;
+    float t0x, t0y, t0z, tmx, tmy, tmz, t1x, t1y, t1z;
+    auto planes = [&]() { // entry / mid / exit parameters of the cell (level; ix,iy,iz)
+        const float s1 = __int_as_float((127 - (level + 1)) << 23); // 2^-(level+1), exact
+        const float hx = g.root_size[0] * s1, hy = g.root_size[1] * s1, hz = g.root_size[2] * s1;
+        float ax = (cell_edge(g.root_lo[0], hx, 2u * ix) - o.x) * inv.x, bx = (cell_edge(g.root_lo[0], hx, 2u * ix + 2u) - o.x) * inv.x;
+        float ay = (cell_edge(g.root_lo[1], hy, 2u * iy) - o.y) * inv.y, by = (cell_edge(g.root_lo[1], hy, 2u * iy + 2u) - o.y) * inv.y;
+        float az = (cell_edge(g.root_lo[2], hz, 2u * iz) - o.z) * inv.z, bz = (cell_edge(g.root_lo[2], hz, 2u * iz + 2u) - o.z) * inv.z;
+        t0x = fminf(ax, bx); t1x = fmaxf(ax, bx);
+        t0y = fminf(ay, by); t1y = fmaxf(ay, by);
+        t0z = fminf(az, bz); t1z = fmaxf(az, bz);
+        tmx = (cell_edge(g.root_lo[0], hx, 2u * ix + 1u) - o.x) * inv.x;
+        tmy = (cell_edge(g.root_lo[1], hy, 2u * iy + 1u) - o.y) * inv.y;
+        tmz = (cell_edge(g.root_lo[2], hz, 2u * iz + 1u) - o.z) * inv.z;
+    };
+    planes();
+    {
+        const float tn = fmaxf(fmaxf(t0x, t0y), t0z), tf = fminf(fminf(t1x, t1y), t1z);
+        if (tn > fminf(tf, best) + 1.0e-5f || tf < tmin) return false;
+    }
+    unsigned long long codes = 0xFull; // 4 bits per level: 0xF = not started, else current child (mirrored)
     stack[0] = root.x;
     while (true) {
-        uint32_t i = uint32_t(iters >> (4 * level)) & 0xFu;
-        if (i >= 8u) {
-            if (level == 0) break;
-            --level;
-            ix >>= 1; iy >>= 1; iz >>= 1;
-            continue;
-        }
-        iters += 1ull << (4 * level);
-        uint32_t c = i ^ a;
-        uint2 rec = S.node(stack[level * kThreads] + c);
-        if (rec.y == kLeafBit) continue; // empty octant
-        uint32_t cx = 2u * ix + (c & 1u), cy = 2u * iy + ((c >> 1) & 1u), cz = 2u * iz + ((c >> 2) & 1u);
-        float scale = __int_as_float((127 - (level + 1)) << 23); // 2^-(level+1), exact
-        float sx = g.root_size[0] * scale, sy = g.root_size[1] * scale, sz = g.root_size[2] * scale;
-        float tn, tf;
-        slab(cell_edge(g.root_lo[0], sx, cx), cell_edge(g.root_lo[1], sy, cy), cell_edge(g.root_lo[2], sz, cz),
-             cell_edge(g.root_lo[0], sx, cx + 1), cell_edge(g.root_lo[1], sy, cy + 1), cell_edge(g.root_lo[2], sz, cz + 1),
-             tn, tf);
-        if (tn > fminf(tf, best) || tf < tmin) continue;
-        if (rec.y & kLeafBit) {
-            if (leaf(rec.x, rec.y & ~kLeafBit)) break;
+        uint32_t cur = uint32_t(codes >> (4 * level)) & 0xFu;
+        bool leave = false;
+        if (cur == 0xFu) {
+            const float te = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), tmin);
+            cur = (tmx < te ? 1u : 0u) | (tmy < te ? 2u : 0u) | (tmz < te ? 4u : 0u);
         } else {
+            const float ex = (cur & 1u) ? t1x : tmx, ey = (cur & 2u) ? t1y : tmy, ez = (cur & 4u) ? t1z : tmz;
+            const uint32_t bit = (ex <= ey && ex <= ez) ? 1u : (ey <= ez ? 2u : 4u);
+            leave = (cur & bit) != 0u;
+            cur |= bit;
+        }
+        if (!leave) {
+            const float cen = fmaxf(fmaxf((cur & 1u) ? tmx : t0x, (cur & 2u) ? tmy : t0y), (cur & 4u) ? tmz : t0z);
+            const float cex = fminf(fminf((cur & 1u) ? t1x : tmx, (cur & 2u) ? t1y : tmy), (cur & 4u) ? t1z : tmz);
+            if (cen > best + fabsf(best) * 2.0e-6f + 1.0e-5f) break; // everything from here on is farther than the hit
+            codes = (codes & ~(0xFull << (4 * level))) | ((unsigned long long)cur << (4 * level));
+            if (cex < tmin) continue;
+            const uint32_t c = cur ^ a;
+            const uint2 rec = S.node(stack[level * kThreads] + c);
+            if (rec.y == kLeafBit) continue; // empty octant
+            if (rec.y & kLeafBit) {
+                if (leaf(rec.x, rec.y & ~kLeafBit)) break;
+                if (best_prim != kInvalid && best <= cex) break; // the hit lies inside this cell: nothing nearer exists
+                continue;
+            }
             ++level;
             stack[level * kThreads] = rec.x;
-            ix = cx; iy = cy; iz = cz;
-            iters &= ~(0xFull << (4 * level));
+            ix = 2u * ix + (c & 1u); iy = 2u * iy + ((c >> 1) & 1u); iz = 2u * iz + ((c >> 2) & 1u);
+            codes |= 0xFull << (4 * level);
+            planes();
+            continue;
         }
+        if (level == 0) break;
+        --level;
+        ix >>= 1; iy >>= 1; iz >>= 1;
+        planes();
     }
     t_hit = best;
     prim_hit = best_prim;
@@ -374,7 +398,7 @@ __device__ __forceinline__ void add_radiance(const PassArgs& a, uint32_t slot, f
 
 // ---- extend ------------------------------------------------------------------------
 template <bool FIRST, bool ALL>
-__global__ void __launch_bounds__(kThreads, 4) extend_kernel(const PassArgs a, const int bounce) {
+__global__ void __launch_bounds__(kThreads, ALL ? 4 : 3) extend_kernel(const PassArgs a, const int bounce) {
     const SceneAccess<ALL> S = stage_scene<ALL>(a);
     const uint32_t n = FIRST ? a.n_slots : a.counts[bounce * 4 + Q_EXTEND];
     const uint32_t* __restrict__ qin = a.q[bounce & 1];
@@ -482,7 +506,7 @@ template <bool FIRST> __device__ __forceinline__ void load_shade_in(const PassAr
 }
 
 template <int KIND, bool FIRST, bool ALL>
-__global__ void __launch_bounds__(kThreads, KIND == Q_DIFFUSE ? 3 : 4) shade_kernel(const PassArgs a, const int bounce) {
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2)) shade_kernel(const PassArgs a, const int bounce) {
     SceneAccess<ALL> S;
     if (KIND == Q_DIFFUSE) S = stage_scene<ALL>(a); // shadow rays traverse
     const uint32_t n = a.counts[bounce * 4 + KIND];
@@ -710,8 +734,8 @@ size_t path_smem_bytes(const PassArgs& a, bool with_scene) {
     return nb + size_t(a.stage_prims) * 64 + size_t(a.stack_levels) * kThreads * 4 + 16;
 }
 
-static bool all_staged(const PassArgs& a) {
-    return a.stage_nodes >= a.scene.n_nodes && a.stage_prims >= a.scene.n_index;
+static bool all_staged(const PassArgs& a) { // one leaf, everything in shared memory
+    return a.scene.n_nodes == 1 && a.stage_nodes >= 1 && a.stage_prims >= a.scene.n_index;
 }
 
 // The grid of a persistent kernel = SM count x resident CTAs, cached per (kernel, smem size).

@@ -200,9 +200,11 @@ def main():
     rt.start()
     stream = torch.cuda.current_stream().cuda_stream
 
+    # One payload per rank = its compact tile arrays [float radiance | RGB888], padded to rank 0's
+    # length: ONE gather (grouped ncclSend/ncclRecv) per frame carries both outputs.
     pad = g19dist.padded_len(W, H, world)
-    t_rad = torch.zeros(pad * 3, dtype=torch.float32, device=dev)
-    t_rgb = torch.zeros(pad * 3, dtype=torch.uint8, device=dev)
+    rad_bytes = pad * 3 * 4
+    payload = torch.zeros(rad_bytes + pad * 3, dtype=torch.uint8, device=dev)
     f_rad = torch.zeros(H * W * 3, dtype=torch.float32, device=dev) if rank == 0 else None
     f_rgb = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev) if rank == 0 else None
     host_rgb = torch.empty(H * W * 3, dtype=torch.uint8).pin_memory() if rank == 0 else None
@@ -211,16 +213,13 @@ def main():
         return rt.params(W, H, mode=abi.MODE_PATH, spp=SPP, max_depth=DEPTH, seed=SEED, rank=rank, world=world,
                          spp_per_pass=args.spp_per_pass, profile=profile)
 
-    def untile_rad(r, payload, frame):
-        rt.untile(W, H, r, world, t_rad=payload.data_ptr(), d_rad=frame.data_ptr(), stream=stream)
-
-    def untile_rgb(r, payload, frame):
-        rt.untile(W, H, r, world, t_rgb=payload.data_ptr(), d_rgb=frame.data_ptr(), stream=stream)
+    def untile_both(r, buf, _frame):
+        rt.untile(W, H, r, world, t_rad=buf.data_ptr(), t_rgb=buf.data_ptr() + rad_bytes, d_rad=f_rad.data_ptr(),
+                  d_rgb=f_rgb.data_ptr(), stream=stream)
 
     def step(profile=0):
-        rt.render_tiles(params(profile), t_rgb=t_rgb.data_ptr(), t_rad=t_rad.data_ptr(), stream=stream)
-        g19dist.gather_frame(t_rad, W, H, 3, f_rad, untile_rad)
-        g19dist.gather_frame(t_rgb, W, H, 3, f_rgb, untile_rgb)
+        rt.render_tiles(params(profile), t_rad=payload.data_ptr(), t_rgb=payload.data_ptr() + rad_bytes, stream=stream)
+        g19dist.gather_frame(payload, W, H, 3, f_rgb, untile_both)
 
     def barrier():
         if world > 1:
@@ -258,7 +257,8 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.stop()
     st = rt.stats()
-    launches = sum_over_ranks(float(st.kernel_launches)) * args.steps
+    # this library's kernels inside the timed region: every rank's render + rank 0's untile per payload
+    launches = (sum_over_ranks(float(st.kernel_launches)) + world) * args.steps
     value = SAMPLES_PER_STEP / (ms * 1e-3) / 1e6
 
     # ---- per-kernel-class CUDA-event times (same steps, event brackets on) --------------------
