@@ -554,6 +554,12 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     stats.class_launches[G19_K_OTHER] += to_frame ? 2 : 1;
     if (a.t_rad) PATH_CUDA(cudaMemcpyAsync(a.t_rad, w.rad_l.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (a.t_rgb) PATH_CUDA(cudaMemcpyAsync(a.t_rgb, w.rgb_l.p, npix * 3, cudaMemcpyDeviceToDevice, s));
+    if (const char* le = path_launch_error()) {
+        err = le;
+        path_clear_launch_error();
+        cudaGetLastError();
+        return G19_ERR_CUDA;
+    }
     PATH_CUDA(cudaGetLastError());
     for (int k = 0; k < 8; ++k) stats.kernel_launches += stats.class_launches[k];
     // owned in-frame pixels

@@ -134,5 +134,7 @@ void launch_extend(const PassArgs& a, int bounce, int sm_count, cudaStream_t s);
 void launch_shade(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s);
 void launch_accumulate(const PassArgs& a, cudaStream_t s);
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s);
+const char* path_launch_error(); // first failed launch/attribute call since the last clear, or nullptr
+void path_clear_launch_error();
 
 } // namespace g19

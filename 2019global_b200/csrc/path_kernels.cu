@@ -39,6 +39,7 @@
 #include "path.h"
 
 #include <cfloat>
+#include <cstdio>
 
 namespace g19 {
 namespace {
@@ -494,14 +495,67 @@ struct ShadeIn { // what one surface interaction reads from the wavefront state
     float4 r0;
     float2 r1;
     float4 tp;
+    float l0, l1, l2; // radiance gathered so far (diffuse only: the light sample adds to it)
 };
 
-template <bool FIRST> __device__ __forceinline__ void load_shade_in(const PassArgs& a, uint32_t slot, ShadeIn& in) {
-    in.hit = a.hit[slot];
+// Asynchronous prefetch of the NEXT slot's state into shared memory (LDGSTS): a register
+// prefetch gets sunk to its first use by the compiler (ncu: 20 % of the kernel's stall samples
+// sat on that one instruction); a cp.async cannot be, and it holds no registers while in flight.
+// Two buffers per thread, each thread only ever touches its own column.
+struct ShadeStage {
+    float4 ro[2][kThreads];
+    float4 tp[2][kThreads];
+    float2 rd[2][kThreads];
+    uint2 hit[2][kThreads];
+    float L[2][3][kThreads];
+};
+
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// On the camera segment nothing is read but the hit: the ray is regenerated, throughput is 1 and
+// the slot's radiance is still zero (an emitter hit would have ended the path in extend).
+template <int KIND, bool FIRST>
+__device__ __forceinline__ void prefetch_shade_in(const PassArgs& a, uint32_t slot, ShadeStage& st, int buf) {
+    const int t = threadIdx.x;
+    if (slot != kInvalid) {
+        cp_async8(&st.hit[buf][t], a.hit + slot);
+        if (!FIRST) {
+            cp_async16(&st.ro[buf][t], a.ro + slot);
+            cp_async8(&st.rd[buf][t], a.rd + slot);
+            cp_async16(&st.tp[buf][t], a.tp + slot);
+            if (KIND == Q_DIFFUSE) {
+                cp_async4(&st.L[buf][0][t], a.L + slot);
+                cp_async4(&st.L[buf][1][t], a.L + a.plane + slot);
+                cp_async4(&st.L[buf][2][t], a.L + 2 * a.plane + slot);
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+template <int KIND, bool FIRST>
+__device__ __forceinline__ void read_shade_in(const ShadeStage& st, int buf, ShadeIn& in) {
+    const int t = threadIdx.x;
+    in.hit = st.hit[buf][t];
     if (!FIRST) {
-        in.r0 = a.ro[slot];
-        in.r1 = a.rd[slot];
-        in.tp = a.tp[slot];
+        in.r0 = st.ro[buf][t];
+        in.r1 = st.rd[buf][t];
+        in.tp = st.tp[buf][t];
+        if (KIND == Q_DIFFUSE) {
+            in.l0 = st.L[buf][0][t];
+            in.l1 = st.L[buf][1][t];
+            in.l2 = st.L[buf][2][t];
+        }
     }
 }
 
@@ -519,23 +573,26 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
 
+    __shared__ ShadeStage stage;
     uint32_t q = blockIdx.x * kThreads + threadIdx.x;
     uint32_t s_cur = kInvalid, s_nxt = kInvalid;
-    ShadeIn in = {};
     if (q < n) s_cur = qin[q];
     if (q + stride < n && q + stride >= q) s_nxt = qin[q + stride];
-    if (s_cur != kInvalid) load_shade_in<FIRST>(a, s_cur, in);
+    int buf = 0;
+    prefetch_shade_in<KIND, FIRST>(a, s_cur, stage, 0);
     for (; q - lane < n; q += stride) {
         uint32_t s_nn = kInvalid;
-        ShadeIn nx = {};
         {
             const uint32_t q2 = q + 2u * stride;
             if (q2 < n && q2 > q) s_nn = qin[q2];
-            if (s_nxt != kInvalid) load_shade_in<FIRST>(a, s_nxt, nx);
         }
+        prefetch_shade_in<KIND, FIRST>(a, s_nxt, stage, buf ^ 1); // next slot's state, in flight during this body
+        cp_async_wait<1>();                                       // this slot's state has landed
         const uint32_t slot = s_cur;
         bool go_on = false;
         if (slot != kInvalid) {
+            ShadeIn in = {}; // camera segment: radiance so far is zero
+            read_shade_in<KIND, FIRST>(stage, buf, in);
             ++calls;
             int x, y;
             uint32_t sample;
@@ -594,9 +651,10 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2
                         if (!blocked) {
                             ++lit;
                             float gterm = cs * cl * lt.area * __fdividef(1.0f, dist2 * lt.pdf_pick) * (1.0f / kPi);
-                            add_radiance(a, slot, f3(T.x * albedo.x * lt.emission[0] * gterm,
-                                                     T.y * albedo.y * lt.emission[1] * gterm,
-                                                     T.z * albedo.z * lt.emission[2] * gterm));
+                            // the old value came in with the prefetched state: store only, no stall
+                            a.L[slot] = in.l0 + T.x * albedo.x * lt.emission[0] * gterm;
+                            a.L[a.plane + slot] = in.l1 + T.y * albedo.y * lt.emission[1] * gterm;
+                            a.L[2 * a.plane + slot] = in.l2 + T.z * albedo.z * lt.emission[2] * gterm;
                         }
                     }
                 }
@@ -648,8 +706,9 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2
         }
         warp_append(cur, go_on, slot, qout, cout);
         s_cur = s_nxt; s_nxt = s_nn;
-        in = nx;
+        buf ^= 1;
     }
+    cp_async_wait<0>();
     warp_flush(cur, qout);
     calls = warp_sum(calls);
     shadow_rays = warp_sum(shadow_rays);
@@ -738,6 +797,13 @@ static bool all_staged(const PassArgs& a) { // one leaf, everything in shared me
     return a.scene.n_nodes == 1 && a.stage_nodes >= 1 && a.stage_prims >= a.scene.n_index;
 }
 
+static char g_launch_error[256] = "";
+static void note_launch_error(const char* what, cudaError_t e, size_t smem, int grid) {
+    if (!g_launch_error[0])
+        snprintf(g_launch_error, sizeof g_launch_error, "%s: %s (dynamic smem %zu B, grid %d)", what, cudaGetErrorString(e),
+                 smem, grid);
+}
+
 // The grid of a persistent kernel = SM count x resident CTAs, cached per (kernel, smem size).
 template <typename K> static void launch_persistent(K kernel, const PassArgs& a, int bounce, size_t smem, int sm_count,
                                                     cudaStream_t s) {
@@ -748,10 +814,17 @@ template <typename K> static void launch_persistent(K kernel, const PassArgs& a,
     for (int i = 0; i < n_cache; ++i)
         if (cache[i].fn == (const void*)kernel && cache[i].smem == smem) grid = cache[i].grid;
     if (!grid) {
+        // static (prefetch stage) + dynamic (scene prefix, stack) shared memory may exceed 48 KB.
+        // The attribute is a CAP: always raise it to the same ceiling, never to this scene's size
+        // (a smaller later scene would otherwise lower it under a cached larger launch).
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        if (e != cudaSuccess) note_launch_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e, smem, 0);
         grid = resident_grid(kernel, smem, sm_count);
         if (n_cache < 64) cache[n_cache++] = Entry{(const void*)kernel, smem, grid};
     }
     kernel<<<grid, kThreads, smem, s>>>(a, bounce);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) note_launch_error("persistent kernel launch", e, smem, grid);
 }
 
 } // namespace
@@ -787,6 +860,9 @@ void launch_shade(const PassArgs& a, int bounce, int kind, int sm_count, cudaStr
     default: launch_shade_k<Q_GLASS>(a, bounce, sm_count, s); break;
     }
 }
+
+const char* path_launch_error() { return g_launch_error[0] ? g_launch_error : nullptr; }
+void path_clear_launch_error() { g_launch_error[0] = 0; }
 
 void launch_accumulate(const PassArgs& a, cudaStream_t s) {
     int blocks = (a.map.n_local_pix + kThreads - 1) / kThreads;
