@@ -400,8 +400,9 @@ __device__ __forceinline__ void add_radiance(const PassArgs& a, uint32_t slot, f
 // ---- extend ------------------------------------------------------------------------
 template <bool FIRST, bool ALL>
 __global__ void __launch_bounds__(kThreads, ALL ? 4 : 3) extend_kernel(const PassArgs a, const int bounce) {
-    const SceneAccess<ALL> S = stage_scene<ALL>(a);
     const uint32_t n = FIRST ? a.n_slots : a.counts[bounce * 4 + Q_EXTEND];
+    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave before staging anything
+    const SceneAccess<ALL> S = stage_scene<ALL>(a);
     const uint32_t* __restrict__ qin = a.q[bounce & 1];
     WarpCursor cur0 = {0, 0}, cur1 = {0, 0}, cur2 = {0, 0};
     uint32_t* const counters = a.counts + bounce * 4 + Q_DIFFUSE; // diffuse, mirror, glass are adjacent
@@ -561,9 +562,10 @@ __device__ __forceinline__ void read_shade_in(const ShadeStage& st, int buf, Sha
 
 template <int KIND, bool FIRST, bool ALL>
 __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2)) shade_kernel(const PassArgs a, const int bounce) {
+    const uint32_t n = a.counts[bounce * 4 + KIND];
+    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave before staging anything
     SceneAccess<ALL> S;
     if (KIND == Q_DIFFUSE) S = stage_scene<ALL>(a); // shadow rays traverse
-    const uint32_t n = a.counts[bounce * 4 + KIND];
     const uint32_t* __restrict__ qin = a.q[1 + KIND];
     uint32_t* __restrict__ qout = a.q[(bounce + 1) & 1];
     uint32_t* __restrict__ cout = a.counts + (bounce + 1) * 4 + Q_EXTEND;

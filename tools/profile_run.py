@@ -14,6 +14,7 @@ ap.add_argument("--w", type=int, default=1920)
 ap.add_argument("--h", type=int, default=1080)
 ap.add_argument("--mode", default="PATH")
 ap.add_argument("--frames", type=int, default=1)
+ap.add_argument("--profile", type=int, default=0)
 a = ap.parse_args()
 g19 = importlib.import_module("2019global_b200")
 abi = g19.abi
@@ -22,7 +23,10 @@ rt = g19.RayTracer(cam, light, device=0)
 rt.setScene(sc)
 rt.start()
 for _ in range(a.frames):
-    out = rt.run(a.w, a.h, mode=getattr(abi, "MODE_" + a.mode), want=("rgb",), spp=a.spp, max_depth=a.depth, seed=0)
+    out = rt.run(a.w, a.h, mode=getattr(abi, "MODE_" + a.mode), want=("rgb",), spp=a.spp, max_depth=a.depth, seed=0, profile=a.profile)
 st = rt.stats()
 print("ok: %.2f ms, %d samples, %d extend, %d shadow segments, %d launches" % (
     st.render_ms, st.samples, st.extend_segments, st.shadow_segments, st.kernel_launches))
+if a.profile:
+    print("  class ms:", {abi.CLASS_NAMES[k]: round(st.class_ms[k], 2) for k in range(7) if st.class_launches[k]},
+          "launches:", {abi.CLASS_NAMES[k]: st.class_launches[k] for k in range(7) if st.class_launches[k]})
