@@ -107,9 +107,9 @@ def cpu_path_oracle(threads, budget_s=12.0):
         t = time.perf_counter()
         binding.path_render(chk, cam, W, H, SPP, DEPTH, seed=SEED, window=(x0, y0, x0 + cw, y0 + ch), threads=threads)
         dt = time.perf_counter() - t
-        if dt >= budget_s / 4 or cw >= 768:
+        if dt >= budget_s / 4 or (cw, ch) == (W, H):
             break
-        cw, ch = cw * 2, ch * 2
+        cw, ch = (cw * 2, ch * 2) if cw * 2 <= 1536 else (W, H)  # ... 768x432, 1536x864, then the whole frame
     n = cw * ch * SPP
     return n / dt / 1e6, "centred %dx%d crop of the 1920x1080 frame, %d spp, depth %d (%d paths, %.1f s)" % (
         cw, ch, SPP, DEPTH, n, dt)
