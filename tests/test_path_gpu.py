@@ -140,3 +140,25 @@ def test_cancel_between_passes(g19, abi):
     t.join()
     assert rt.stats().samples < w * h * 4096
     assert 0.0 <= rt.progress() <= 1.0
+
+
+def test_zoo_every_entity_kind(g19, abi, oracle):
+    """PATH mode over one entity of every reference class (analytic spheres, single triangles, the
+    rectangle/box pairs with the reference's p4 = -p3 geometry, tessellated sphere/quad/cube/cone),
+    one of them emitting: primitive extraction and the octree must agree with the brute-force oracle."""
+    from util import zoo
+    sc = zoo(g19)
+    sc.push_back(g19.ImpTriangle((-6, -9, 9), (-6, 9, 9), (6, 0, 9), (1, 1, 1), bsdf=abi.BSDF_EMITTER,
+                                 emission=(6.0, 6.0, 6.0)))
+    sc.push_back(g19.ExpQuad((2, 0, -3), 6, 8, 0.2, (0.8, 0.8, 0.8)))
+    cam = g19.Camera((-10, 0, 0), (1, 0, 0), 0.1)
+    w, h = 120, 120
+    rt, got, st = _gpu(g19, abi, sc, cam, (0, 0, 0), w, h, spp=8, max_depth=4, seed=21)
+    exp, segs = binding.path_render(mirror(oracle, sc), cam, w, h, 8, 4, seed=21)
+    assert exp.mean() > 0.01
+    err = rel_rmse(got["radiance"], exp)
+    print("zoo: same-seed relRMSE %.3e, segments gpu %d/%d cpu %d/%d" % (err, st.extend_segments, st.shadow_segments,
+                                                                          segs[0], segs[1]))
+    assert err <= 1e-2
+    assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
+    assert abs(int(st.shadow_segments) - segs[1]) <= 1e-3 * segs[1] + 2
