@@ -1,7 +1,7 @@
 """ctypes mirror of include/g19.h (struct layouts and enum values only)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enum g19_entity_kind (reference include/entities.h, one value per class)
 IMP_SPHERE, IMP_TRIANGLE, EXP_RECTANGLE, EXP_BOX, EXP_SPHERE, EXP_QUAD, EXP_CUBE, EXP_CONE = range(8)
@@ -15,7 +15,7 @@ SCENE_DEFAULT, SCENE_CORNELL, SCENE_CORNELL_GLASS, SCENE_HEIGHTFIELD = range(4)
 # status
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NO_SCENE, ERR_CANCELLED, ERR_LIMIT, ERR_REJECTED = range(8)
 K_EXTEND, K_SHADE, K_SHADOW, K_ACCUM, K_REF_VIS, K_REF_SHADE, K_OTHER = range(7)
-CLASS_NAMES = ["extend", "shade", "shadow", "accumulate", "ref_visibility", "ref_shade", "other", "_"]
+CLASS_NAMES = ["raygen_extend", "bounce", "shadow", "accumulate", "ref_visibility", "ref_shade", "other", "_"]
 
 
 class EntityDesc(C.Structure):
@@ -59,7 +59,8 @@ class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("extend_segments", C.c_uint64), ("shadow_segments", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("class_ms", C.c_double * 8),
                 ("class_launches", C.c_uint64 * 8), ("node_tests", C.c_uint64), ("prim_tests", C.c_uint64),
-                ("shade_calls", C.c_uint64), ("shade_calls_first", C.c_uint64), ("lit_samples", C.c_uint64)]
+                ("shade_calls", C.c_uint64), ("shade_calls_first", C.c_uint64), ("lit_samples", C.c_uint64),
+                ("radiance_reads", C.c_uint64)]
 
 
 def d3(v):

@@ -397,8 +397,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &w.ro, &w.rd, &w.tp,
-                           &w.hit, &w.L, &w.queues, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &w.hp, &w.dw, &w.tp,
+                           &w.L, &w.queues, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
         d->release();
     if (w.events) {
         for (int i = 0; i < w.n_events; ++i) cudaEventDestroy(w.events[i]);
@@ -458,12 +458,11 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         }                                                                      \
     } while (0)
     if (P > w.capacity) {
-        PATH_CUDA(w.ro.ensure(P * sizeof(float4)));
-        PATH_CUDA(w.rd.ensure(P * sizeof(float2)));
+        PATH_CUDA(w.hp.ensure(P * sizeof(float4)));
+        PATH_CUDA(w.dw.ensure(P * sizeof(float4)));
         PATH_CUDA(w.tp.ensure(P * sizeof(float4)));
-        PATH_CUDA(w.hit.ensure(P * sizeof(uint2)));
         PATH_CUDA(w.L.ensure(P * 3 * sizeof(float)));
-        PATH_CUDA(w.queues.ensure((P + kQueueSlack) * 5 * sizeof(uint32_t)));
+        PATH_CUDA(w.queues.ensure((P + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
         w.capacity = P;
         PATH_CUDA(cudaMemsetAsync(w.L.p, 0, P * 3 * sizeof(float), s));
     }
@@ -494,14 +493,15 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa.map = a.map;
     pa.seed = p.seed;
     pa.max_depth = p.max_depth;
-    pa.ro = static_cast<float4*>(w.ro.p);
-    pa.rd = static_cast<float2*>(w.rd.p);
+    pa.hp = static_cast<float4*>(w.hp.p);
+    pa.dw = static_cast<float4*>(w.dw.p);
     pa.tp = static_cast<float4*>(w.tp.p);
-    pa.hit = static_cast<uint2*>(w.hit.p);
     pa.L = static_cast<float*>(w.L.p);
     pa.plane = plane;
     pa.queue_cap = plane + kQueueSlack;
-    for (int k = 0; k < 5; ++k) pa.q[k] = static_cast<uint32_t*>(w.queues.p) + size_t(k) * pa.queue_cap;
+    for (int k = 0; k < kNumQueues; ++k) pa.q[k] = static_cast<uint32_t*>(w.queues.p) + size_t(k) * pa.queue_cap;
+    pa.kind_mask = (b.has_bsdf[G19_BSDF_DIFFUSE] ? 1u : 0u) | (b.has_bsdf[G19_BSDF_MIRROR] ? 2u : 0u) |
+                   (b.has_bsdf[G19_BSDF_GLASS] ? 4u : 0u);
     pa.counts = static_cast<uint32_t*>(w.counts.p);
     pa.totals = static_cast<unsigned long long*>(w.totals.p);
     pa.accum = static_cast<float*>(w.accum.p);
@@ -509,6 +509,9 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     // stage the breadth-first prefix of the tree and the first primitives (<= ~24 KB)
     pa.stage_nodes = std::min(b.view.n_nodes, 1024);
     pa.stage_prims = std::min(b.view.n_index, 192); // leaf-ordered hot records
+    // flat scene (one leaf, all of it staged): the shading records ride along
+    pa.stage_cold = (b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= pa.stage_prims)
+                        ? b.view.n_prims : 0;
     pa.stack_levels = b.view.tree_depth + 1;
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
@@ -520,17 +523,16 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         pa.sample_base = base;
         pa.spp_pass = std::min(spp_pass, p.spp - base);
         pa.n_slots = uint32_t(npix * size_t(pa.spp_pass));
+        clk.begin();
+        launch_raygen_extend(pa, a.sm_count, s); // camera segment
+        clk.end(G19_K_EXTEND);
+        stats.class_launches[G19_K_EXTEND] += 1;
         for (int bounce = 0; bounce < p.max_depth; ++bounce) {
-            clk.begin();
-            launch_extend(pa, bounce, a.sm_count, s);
-            clk.end(G19_K_EXTEND);
-            stats.class_launches[G19_K_EXTEND] += 1;
             clk.begin();
             int n = 0;
             for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
                 if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
-                launch_shade(pa, bounce, kind, a.sm_count, s);
-                ++n;
+                if (launch_bounce(pa, bounce, kind, a.sm_count, s)) ++n;
             }
             clk.end(G19_K_SHADE);
             stats.class_launches[G19_K_SHADE] += n;
@@ -589,6 +591,7 @@ int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
     stats.shade_calls = h[2];
     stats.shade_calls_first = h[3];
     stats.lit_samples = h[4];
+    stats.radiance_reads = h[5];
     for (int i = 0; i + 1 < w.used_events; i += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, w.events[i], w.events[i + 1]) == cudaSuccess) stats.class_ms[w.event_class[i / 2]] += ms;

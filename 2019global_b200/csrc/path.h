@@ -28,12 +28,12 @@ namespace g19 {
 
 constexpr int kMaxPathDepth = 64;    // segments per path
 constexpr int kMaxTreeDepth = 14;    // linear-octree levels below the root
-constexpr int kNumQueues = 4;        // extend, diffuse, mirror, glass
+constexpr int kNumQueues = 6;        // (diffuse, mirror, glass) x two bounce parities
 // Queue entries are reserved in warp-private chunks; a launch can leave at most one partly used
 // chunk per warp and queue behind (padded with an invalid marker): 2 Mi entries of slack cover
 // 148 SMs x 64 warps x 64 entries x 3 producer kernels.
 constexpr size_t kQueueSlack = size_t(2) << 20;
-enum { Q_EXTEND = 0, Q_DIFFUSE = 1, Q_MIRROR = 2, Q_GLASS = 3 };
+enum { Q_DIFFUSE = 1, Q_MIRROR = 2, Q_GLASS = 3 }; // = g19_bsdf + 1; column of PassArgs::counts
 
 struct PathSceneD {
     const PathNodeD* nodes;
@@ -66,12 +66,11 @@ struct PathSceneBuffers {
 // SoA wavefront state for one pass of P path slots (slot = sample_in_pass * n_local_pix + local_pixel).
 struct PathWork {
     size_t capacity = 0;       // slots
-    DeviceArray ro;            // float4[P]: origin.xyz, dir.x
-    DeviceArray rd;            // float2[P]: dir.y, dir.z
-    DeviceArray tp;            // float4[P]: throughput.rgb, flags (bit0: last bounce specular)
-    DeviceArray hit;           // uint2[P] : t (float bits), primitive (0xffffffff = miss)
+    DeviceArray hp;            // float4[P]: hit point of the path's current vertex, primitive id bits
+    DeviceArray dw;            // float4[P]: direction the path arrived with, global pixel index bits
+    DeviceArray tp;            // float4[P]: throughput.rgb, sample index bits
     DeviceArray L;             // float[3][P]: radiance gathered by the path so far
-    DeviceArray queues;        // uint32[5][P + slack]: extend A, extend B, diffuse, mirror, glass
+    DeviceArray queues;        // uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
     DeviceArray counts;        // uint32[kMaxPathDepth+1][4] queue lengths per bounce
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
     DeviceArray accum;         // float[3][n_local_pix]
@@ -115,23 +114,24 @@ struct PassArgs {
     int32_t sample_base;   // first sample index of this pass
     int32_t max_depth;
     uint32_t n_slots;      // spp_pass * n_local_pix
-    float4* ro;
-    float2* rd;
-    float4* tp;
-    uint2* hit;
+    float4* hp;            // vertex: hit point, primitive
+    float4* dw;            // vertex: incoming direction, pixel
+    float4* tp;            // throughput, sample (not written for the camera segment: 1, slot / n_local_pix)
     float* L;              // 3 planes of capacity `plane`
     size_t plane;          // slots per plane (capacity)
-    uint32_t* q[5];
+    uint32_t* q[6];        // [bounce parity * 3 + (kind - 1)]
+    uint32_t kind_mask;    // bit (kind - 1): the scene has a material of that class
     size_t queue_cap;      // entries per queue (P + chunk slack)
     uint32_t* counts;      // [kMaxPathDepth+1][4]
     unsigned long long* totals;
     float* accum;          // 3 planes of n_local_pix
     // shared-memory staging (see path_kernels.cu stage_scene)
-    int32_t stage_nodes, stage_prims, stack_levels;
+    int32_t stage_nodes, stage_prims, stage_cold, stack_levels;
 };
 
-void launch_extend(const PassArgs& a, int bounce, int sm_count, cudaStream_t s);
-void launch_shade(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s);
+void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s);
+// false = nothing to launch for this (bounce, kind): specular vertices on the last segment
+bool launch_bounce(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s);
 void launch_accumulate(const PassArgs& a, cudaStream_t s);
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s);
 const char* path_launch_error(); // first failed launch/attribute call since the last clear, or nullptr

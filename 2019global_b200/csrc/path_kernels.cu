@@ -2,36 +2,46 @@
 //
 // One pass traces P = spp_pass * n_local_pix camera paths, bounce by bounce:
 //
-//   extend<FIRST>   ray generation (bounce 0: regenerated from the pixel index,
-//                   no ray record is read) + linear-octree traversal + primitive
-//                   intersection; writes the 8-byte hit record; sorts the slot
-//                   into a per-material queue by warp-ballot compaction;
-//                   emitters are terminated in place
-//   shade<KIND>     one launch per material queue (diffuse / mirror / glass):
-//                   next-event estimation with an inline any-hit traversal,
-//                   BSDF sampling, writes the 40-byte ray record of the next
-//                   segment and appends the slot to the next extend queue
+//   raygen_extend   camera ray from the pixel index + linear-octree traversal + primitive
+//                   intersection; writes the 32-byte vertex record (hit point, primitive,
+//                   incoming direction, pixel); sorts the slot into a per-material queue by
+//                   warp-ballot compaction; directly visible emitters end the path in place
+//   bounce<KIND>    one launch per material queue and bounce (diffuse / mirror / glass):
+//                   next-event estimation, BSDF sampling, AND the trace of the continuation
+//                   ray by the thread that sampled it, then the same sort of the new vertex
+//                   into the next bounce's material queues. There is no ray record and no
+//                   separate extend launch after the camera segment: a queue entry always
+//                   produces exactly one continuation ray, so compacting between "shade" and
+//                   "extend" would only re-read what the thread already holds in registers.
 //   accumulate      per pixel, in sample order, radiance -> accumulation buffer
 //   resolve         mean, clamp, truncating RGB888 store (Image::setPixel,
 //                   reference include/image.h:14-16)
 //
-// State lives in vectorised SoA buffers indexed by path slot (PassArgs);
-// queues hold slot indices. Every launch is a persistent grid (SM count x
-// resident CTAs) that reads its queue length from device memory, so a frame is
-// enqueued without a single host round trip. The RNG is Philox4x32-10 keyed on
-// (global pixel, sample, bounce, stream): results do not depend on queue
-// order, pass size or how tiles are split across GPUs.
+// State lives in vectorised SoA buffers indexed by path slot (PassArgs); queues hold slot
+// indices. Every launch is a persistent grid (SM count x resident CTAs) that reads its queue
+// length from device memory, so a frame is enqueued without a single host round trip. The RNG
+// is Philox4x32-10 keyed on (global pixel, sample, bounce, stream): results do not depend on
+// queue order, pass size or how tiles are split across GPUs.
 //
-// What the ncu captures of round 1 drove (profiles/):
-//   * the kernels are issue-bound, not HBM-bound -> triangle test by a precomputed affine map
-//     (6 dot products, one MUFU division, no branches), coplanar triangle pairs merged into
-//     parallelograms by the builder, leaf primitives stored contiguously (no index hop),
-//     two primitives per leaf-loop iteration (independent FMA chains)
-//   * barrier stalls from block-level compaction -> queue space is reserved in warp-private
-//     64-entry chunks: one atomic per 64 outputs, no __syncthreads, unused tail padded with
-//     an invalid marker that consumers skip
-//   * long-scoreboard stalls on the queue -> ray dependent loads -> two-deep software pipeline
-//     (slot index two iterations ahead, ray record one iteration ahead)
+// What the ncu captures drove (profiles/):
+//   round 1  * the kernels are issue-bound, not HBM-bound -> triangle test by a precomputed
+//              affine map (6 dot products, one MUFU division, no branches), coplanar triangle
+//              pairs merged into parallelograms by the builder, leaf primitives stored
+//              contiguously (no index hop)
+//            * barrier stalls from block-level compaction -> queue space is reserved in
+//              warp-private 64-entry chunks: one atomic per 64 outputs, no __syncthreads
+//            * long-scoreboard stalls on queue -> state dependent loads -> cp.async prefetch of
+//              the next slot's state into shared memory
+//   session 2 (profiles/r01b_*): ALU pipe 47 %, FMA pipe 28 %, issue 67 % -- a dependent-
+//              latency bound at 6 warps per scheduler, i.e. time ~ instructions per vertex:
+//            * shade + extend fused (see above): one queue pop, one state load, one
+//              compaction per vertex instead of two of each
+//            * (pixel, sample) ride in the spare words of the vertex record instead of being
+//              recomputed by two integer divisions per vertex
+//            * flat scenes (one staged leaf): the shadow ray and the continuation ray leave
+//              the same point, so ONE loop over the primitives tests both -- the origin half
+//              of the affine map (9 of 18 FMAs) and the primitive loads are shared, and the
+//              two rays are independent instruction chains
 //
 // Scene access: the breadth-first prefix of the node array and of the leaf-ordered primitive
 // records is staged into shared memory at kernel start with cp.async.bulk (TMA bulk copy, one
@@ -80,14 +90,16 @@ __device__ __forceinline__ float3 normalize(float3 v) { return v * rsqrtf(dot(v,
 // ---- shared-memory scene prefix ----------------------------------------------
 // Dynamic shared memory, sized on the host to what the scene needs (PassArgs::stage_*):
 //   [nodes: stage_nodes x 8 B][leaf-ordered hot prims: stage_prims x 64 B]
+//   [cold records: stage_cold x 32 B (flat scenes only)]
 //   [traversal stack: stack_levels x kThreads x 4 B][mbarrier: 8 B]
-// A Cornell box stages whole (about 0.5 KB) and leaves the SM free for more CTAs.
+// A Cornell box stages whole (about 0.8 KB) and leaves the SM free for more CTAs.
 extern __shared__ __align__(16) unsigned char g19_dyn_smem[];
 
 template <bool ALL> struct SceneAccess {
     const PathSceneD* g;
     const uint2* nodes_s;
     const float4* hot_s;
+    const float4* cold_s;
     uint32_t* stack;
     int n_nodes_s, n_prims_s;
     __device__ __forceinline__ uint2 node(uint32_t i) const {
@@ -103,6 +115,20 @@ template <bool ALL> struct SceneAccess {
             a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); t = __ldg(p + 3);
         }
     }
+    // shading record of primitive id `prim`: (normal, ior), (albedo, material)
+    __device__ __forceinline__ void cold(uint32_t prim, float4& c0, float4& c1) const {
+        if (ALL) {
+            c0 = cold_s[2 * prim]; c1 = cold_s[2 * prim + 1];
+        } else {
+            const float4* p = reinterpret_cast<const float4*>(g->cold) + 2 * (size_t)prim;
+            c0 = __ldg(p); c1 = __ldg(p + 1);
+        }
+    }
+    // row 0 / row 3 of the hot record BY PRIMITIVE ID (flat scenes: leaf order == id order)
+    __device__ __forceinline__ float4 hot_row(uint32_t prim, int row) const {
+        if (ALL) return hot_s[4 * prim + row];
+        return __ldg(reinterpret_cast<const float4*>(g->hot) + 4 * (size_t)prim + row);
+    }
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,11 +143,14 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
     const uint32_t pb = uint32_t(a.stage_prims) * 64u;
+    const uint32_t cb = ALL ? uint32_t(a.stage_cold) * 32u : 0u;
     unsigned char* base = g19_dyn_smem;
     acc.nodes_s = reinterpret_cast<const uint2*>(base);
     acc.hot_s = reinterpret_cast<const float4*>(base + nb);
-    acc.stack = reinterpret_cast<uint32_t*>(base + nb + pb) + threadIdx.x;
-    unsigned long long* barp = reinterpret_cast<unsigned long long*>(base + nb + pb + uint32_t(a.stack_levels) * kThreads * 4u);
+    acc.cold_s = reinterpret_cast<const float4*>(base + nb + pb);
+    acc.stack = reinterpret_cast<uint32_t*>(base + nb + pb + cb) + threadIdx.x;
+    unsigned long long* barp =
+        reinterpret_cast<unsigned long long*>(base + nb + pb + cb + uint32_t(a.stack_levels) * kThreads * 4u);
     const uint32_t bar = smem_addr(barp);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -129,7 +158,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + pb) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + pb + cb) : "memory");
         if (nb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(base)),
@@ -139,6 +168,11 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(base + nb)),
                          "l"(g.hot_leaf), "r"(pb), "r"(bar)
+                         : "memory");
+        if (cb)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(base + nb + pb)),
+                         "l"(g.cold), "r"(cb), "r"(bar)
                          : "memory");
     }
     uint32_t done = 0; // everyone waits for phase 0 of the barrier
@@ -152,35 +186,74 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
 }
 
 // ---- primitive intersection ---------------------------------------------------
-// Returns t in (tmin, tmax) or -1. Triangles / parallelograms: the ray is mapped into the
-// primitive's own (b1, b2, h) frame by the precomputed affine rows -- 6 dot products, one
-// fast division, no branches. Spheres: unit direction, discriminant from the perpendicular
-// offset. tag.z = kind: 0 sphere, 1 triangle (b1+b2 <= 1), 2 parallelogram (b1, b2 <= 1).
-__device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 tag, float3 o, float3 d, float tmin,
-                                          float tmax) {
-    if (tag.z != 0.0f) {
-        float oz = fmaf(c.x, o.x, fmaf(c.y, o.y, fmaf(c.z, o.z, c.w)));
-        float dz = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
-        float t = __fdividef(-oz, dz);
-        float ox = fmaf(a.x, o.x, fmaf(a.y, o.y, fmaf(a.z, o.z, a.w)));
-        float dx = fmaf(a.x, d.x, fmaf(a.y, d.y, a.z * d.z));
-        float oy = fmaf(b.x, o.x, fmaf(b.y, o.y, fmaf(b.z, o.z, b.w)));
-        float dy = fmaf(b.x, d.x, fmaf(b.y, d.y, b.z * d.z));
-        float u = fmaf(t, dx, ox), v = fmaf(t, dy, oy);
-        float edge = (tag.z > 1.5f) ? fmaxf(u, v) : u + v;
-        bool ok = (t > tmin) & (t < tmax) & (u >= 0.0f) & (v >= 0.0f) & (edge <= 1.0f);
-        return ok ? t : -1.0f;
-    }
-    float3 oc = o - f3(a.x, a.y, a.z);
+// Triangles / parallelograms: the ray is mapped into the primitive's own (b1, b2, h) frame by
+// the precomputed affine rows -- the ORIGIN half (three 4-term dot products) is shared by every
+// ray that leaves the same point, the DIRECTION half costs 9 FMAs, one fast division, 2 FMAs and
+// 5 compares per ray. tag.z = kind: 0 sphere, 1 triangle (b1+b2 <= 1), 2 parallelogram
+// (b1, b2 <= 1). Spheres: unit direction, discriminant from the perpendicular offset.
+struct PlaneOrigin {
+    float ox, oy, oz;
+};
+__device__ __forceinline__ PlaneOrigin plane_origin(float4 a, float4 b, float4 c, float3 o) {
+    PlaneOrigin r;
+    r.oz = fmaf(c.x, o.x, fmaf(c.y, o.y, fmaf(c.z, o.z, c.w)));
+    r.ox = fmaf(a.x, o.x, fmaf(a.y, o.y, fmaf(a.z, o.z, a.w)));
+    r.oy = fmaf(b.x, o.x, fmaf(b.y, o.y, fmaf(b.z, o.z, b.w)));
+    return r;
+}
+// t in (0, tmax) or -1
+__device__ __forceinline__ float plane_hit(float4 a, float4 b, float4 c, float kind, PlaneOrigin po, float3 d, float tmax) {
+    float dz = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
+    float t = __fdividef(-po.oz, dz);
+    float dx = fmaf(a.x, d.x, fmaf(a.y, d.y, a.z * d.z));
+    float dy = fmaf(b.x, d.x, fmaf(b.y, d.y, b.z * d.z));
+    float u = fmaf(t, dx, po.ox), v = fmaf(t, dy, po.oy);
+    float edge = (kind > 1.5f) ? fmaxf(u, v) : u + v;
+    bool ok = (t > 0.0f) & (t < tmax) & (u >= 0.0f) & (v >= 0.0f) & (edge <= 1.0f);
+    return ok ? t : -1.0f;
+}
+__device__ __forceinline__ float sphere_hit(float3 oc, float radius, float3 d, float tmax) {
     float bq = dot(oc, d);
     float3 l = oc - d * bq;
-    float disc = a.w * a.w - dot(l, l);
-    if (disc < 0.0f) return -1.0f;
-    float sq = sqrtf(disc);
+    float disc = radius * radius - dot(l, l);
+    float sq = sqrtf(fmaxf(disc, 0.0f));
     float t0 = -bq - sq, t1 = -bq + sq;
-    if (t0 > tmin && t0 < tmax) return t0;
-    if (t1 > tmin && t1 < tmax) return t1;
-    return -1.0f;
+    float t = (t0 > 0.0f) ? t0 : t1; // the near root if it lies ahead, else the far one
+    bool ok = (disc >= 0.0f) & (t > 0.0f) & (t < tmax);
+    return ok ? t : -1.0f;
+}
+__device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 tag, float3 o, float3 d, float tmax) {
+    if (tag.z != 0.0f) return plane_hit(a, b, c, tag.z, plane_origin(a, b, c, o), d, tmax);
+    return sphere_hit(o - f3(a.x, a.y, a.z), a.w, d, tmax);
+}
+
+// Flat scene (ONE leaf, fully staged): nearest hit of ray (o, d1) within tmax1 and, when DUAL,
+// any hit of ray (o, d0) within tmax0 -- both leave the same point, so one pass over the
+// primitives serves both. A ray with tmax <= 0 is switched off. Returns the leaf position
+// (== primitive id in a flat scene) of the nearest hit in best_k.
+template <bool DUAL>
+__device__ __forceinline__ void trace_flat(const SceneAccess<true>& S, uint32_t n, float3 o, float3 d1, float tmax1,
+                                           float3 d0, float tmax0, float& best, uint32_t& best_k, bool& occluded) {
+    best = tmax1;
+    best_k = kInvalid;
+    bool occ = false;
+#pragma unroll 2
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 a = S.hot_s[4 * k], b = S.hot_s[4 * k + 1], c = S.hot_s[4 * k + 2], g = S.hot_s[4 * k + 3];
+        float t1, t0 = -1.0f;
+        if (g.z != 0.0f) { // warp-uniform: every lane walks the same list
+            const PlaneOrigin po = plane_origin(a, b, c, o);
+            t1 = plane_hit(a, b, c, g.z, po, d1, best);
+            if (DUAL) t0 = plane_hit(a, b, c, g.z, po, d0, tmax0);
+        } else {
+            const float3 oc = o - f3(a.x, a.y, a.z);
+            t1 = sphere_hit(oc, a.w, d1, best);
+            if (DUAL) t0 = sphere_hit(oc, a.w, d0, tmax0);
+        }
+        if (t1 >= 0.0f) { best = t1; best_k = k; }
+        if (DUAL) occ |= (t0 >= 0.0f);
+    }
+    occluded = occ;
 }
 
 // Cell edge: the SAME expression as cell_edge() in path.cu (no FMA contraction).
@@ -194,13 +267,15 @@ __device__ __forceinline__ float cell_edge(float root_lo, float size_at_level, u
 // bounds everything behind it. Per level the kernel keeps the child base index
 // on a short stack in shared memory (one column per thread, conflict free), a
 // 4-bit child counter packed in a register, and the integer cell coordinates.
-template <bool ANY, bool ALL>
-__device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tmin, float tmax, float& t_hit,
+// `any` = stop at the first hit (shadow rays).
+template <bool ALL>
+__device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tmax, bool any, float& t_hit,
                          uint32_t& prim_hit) {
     const PathSceneD& g = *S.g;
     uint32_t* const stack = S.stack;
     float best = tmax;
     uint32_t best_prim = kInvalid;
+    const float tmin = 0.0f;
 
     auto leaf = [&](uint32_t first, uint32_t n) -> bool {
         uint32_t k = 0;
@@ -208,32 +283,29 @@ __device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tm
             float4 a0, b0, c0, g0, a1, b1, c1, g1;
             S.prim(first + k, a0, b0, c0, g0);
             S.prim(first + k + 1, a1, b1, c1, g1);
-            float t0 = hit_prim(a0, b0, c0, g0, o, d, tmin, best);
-            float t1 = hit_prim(a1, b1, c1, g1, o, d, tmin, best);
+            float t0 = hit_prim(a0, b0, c0, g0, o, d, best);
+            float t1 = hit_prim(a1, b1, c1, g1, o, d, best);
             if (t0 >= 0.0f) { best = t0; best_prim = __float_as_uint(g0.w); }
             if (t1 >= 0.0f && t1 < best) { best = t1; best_prim = __float_as_uint(g1.w); }
-            if (ANY && best_prim != kInvalid) return true;
+            if (any && best_prim != kInvalid) return true;
         }
         if (k < n) {
             float4 a0, b0, c0, g0;
             S.prim(first + k, a0, b0, c0, g0);
-            float t0 = hit_prim(a0, b0, c0, g0, o, d, tmin, best);
+            float t0 = hit_prim(a0, b0, c0, g0, o, d, best);
             if (t0 >= 0.0f) { best = t0; best_prim = __float_as_uint(g0.w); }
-            if (ANY && best_prim != kInvalid) return true;
+            if (any && best_prim != kInvalid) return true;
         }
         return false;
     };
 
     const uint2 root = S.node(0);
-    // ALL = the scene is ONE leaf and fully staged (the Cornell configs): the tree walk below is
-    // compiled out of those kernels, which keeps them at 4 (extend) / 3 (shade) CTAs per SM.
-    if (ALL || (root.y & kLeafBit)) {
+    if (root.y & kLeafBit) {
         leaf(root.x, root.y & ~kLeafBit);
         t_hit = best;
         prim_hit = best_prim;
         return best_prim != kInvalid;
     }
-    if (ALL) return false; // unreachable; lets the compiler drop the walk
 
     // Parametric front-to-back walk (after Revelles et al. 2000). In the frame where the ray
     // direction is positive on every axis (octant bits XOR a), a cell is described per axis by
@@ -268,7 +340,11 @@ __device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tm
     planes();
     {
         const float tn = fmaxf(fmaxf(t0x, t0y), t0z), tf = fminf(fminf(t1x, t1y), t1z);
-        if (tn > fminf(tf, best) + 1.0e-5f || tf < tmin) return false;
+        if (tn > fminf(tf, best) + 1.0e-5f || tf < tmin) {
+            t_hit = best;
+            prim_hit = kInvalid;
+            return false;
+        }
     }
     unsigned long long codes = 0xFull; // 4 bits per level: 0xF = not started, else current child (mirrored)
     stack[0] = root.x;
@@ -339,8 +415,8 @@ __device__ __forceinline__ bool slot_pixel(const PassArgs& a, uint32_t slot, int
 }
 
 // The reference pinhole (raytracer.h:26-30,41) with a uniform jitter inside the pixel.
-__device__ __forceinline__ void camera_ray(const PassArgs& a, int x, int y, uint32_t sample, float3& o, float3& d) {
-    uint32_t pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
+__device__ __forceinline__ void camera_ray(const PassArgs& a, int x, int y, uint32_t pixel, uint32_t sample, float3& o,
+                                           float3& d) {
     uint4 r = philox(pixel, sample, 0u, 0u, a.seed);
     float fx = (float(x) + u01(r.x)) * 0.0002f, fy = (float(y) + u01(r.y)) * 0.0002f;
     const PathCamera& c = a.cam;
@@ -397,92 +473,94 @@ __device__ __forceinline__ void add_radiance(const PassArgs& a, uint32_t slot, f
     L[2 * a.plane + slot] = l2 + v.z;
 }
 
-// ---- extend ------------------------------------------------------------------------
-template <bool FIRST, bool ALL>
-__global__ void __launch_bounds__(kThreads, ALL ? 4 : 3) extend_kernel(const PassArgs a, const int bounce) {
-    const uint32_t n = FIRST ? a.n_slots : a.counts[bounce * 4 + Q_EXTEND];
-    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave before staging anything
-    const SceneAccess<ALL> S = stage_scene<ALL>(a);
-    const uint32_t* __restrict__ qin = a.q[bounce & 1];
-    WarpCursor cur0 = {0, 0}, cur1 = {0, 0}, cur2 = {0, 0};
-    uint32_t* const counters = a.counts + bounce * 4 + Q_DIFFUSE; // diffuse, mirror, glass are adjacent
-    const uint32_t stride = gridDim.x * kThreads;
-    const uint32_t lane = threadIdx.x & 31u;
-    unsigned traced = 0;
+// The three material queues a launch feeds (the next bounce's), one warp-private cursor each.
+struct Sorter {
+    WarpCursor cur[3];
+    uint32_t* q[3];
+    uint32_t* counters; // diffuse, mirror, glass are adjacent
+    uint32_t mask;      // material classes the scene has
+    __device__ __forceinline__ void init(const PassArgs& a, int next_bounce) {
+        const int set = (next_bounce & 1) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            cur[k] = WarpCursor{0, 0};
+            q[k] = a.q[set + k];
+        }
+        counters = a.counts + next_bounce * 4 + Q_DIFFUSE;
+        mask = a.kind_mask;
+    }
+    // kind: G19_BSDF_DIFFUSE / MIRROR / GLASS, or -1 for "path ended"
+    __device__ __forceinline__ void push(int kind, uint32_t slot) {
+        if (mask & 1u) warp_append(cur[0], kind == G19_BSDF_DIFFUSE, slot, q[0], counters + 0);
+        if (mask & 2u) warp_append(cur[1], kind == G19_BSDF_MIRROR, slot, q[1], counters + 1);
+        if (mask & 4u) warp_append(cur[2], kind == G19_BSDF_GLASS, slot, q[2], counters + 2);
+    }
+    __device__ __forceinline__ void flush() {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (mask & (1u << k)) warp_flush(cur[k], q[k]);
+    }
+};
 
-    uint32_t q = blockIdx.x * kThreads + threadIdx.x;
-    // two-deep pipeline: slot index two iterations ahead, ray record one iteration ahead
-    uint32_t s_cur = kInvalid, s_nxt = kInvalid;
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 r1 = make_float2(0.f, 0.f);
-    if (!FIRST) {
-        if (q < n) s_cur = qin[q];
-        if (q + stride < n && q + stride >= q) s_nxt = qin[q + stride];
-        if (s_cur != kInvalid) { r0 = a.ro[s_cur]; r1 = a.rd[s_cur]; }
-    }
-    for (; q - lane < n; q += stride) { // warp-uniform trip count
-        uint32_t s_nn = kInvalid;
-        float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 n1 = make_float2(0.f, 0.f);
-        if (!FIRST) {
-            const uint32_t q2 = q + 2u * stride;
-            if (q2 < n && q2 > q) s_nn = qin[q2];
-            if (s_nxt != kInvalid) { n0 = a.ro[s_nxt]; n1 = a.rd[s_nxt]; }
-        }
-        const uint32_t slot = FIRST ? q : s_cur;
-        int kind = -1;
-        bool live = FIRST ? (q < n) : (slot != kInvalid);
-        float3 o, d;
-        if (live) {
-            if (FIRST) {
-                int x, y;
-                uint32_t sample;
-                live = slot_pixel(a, slot, x, y, sample);
-                if (live) camera_ray(a, x, y, sample, o, d);
-            } else {
-                o = f3(r0.x, r0.y, r0.z);
-                d = f3(r0.w, r1.x, r1.y);
-            }
-        }
-        if (live) {
-            float t = FLT_MAX;
-            uint32_t prim = kInvalid;
-            ++traced;
-            const bool hit = traverse<false, ALL>(S, o, d, 0.0f, FLT_MAX, t, prim);
-            a.hit[slot] = make_uint2(__float_as_uint(t), prim);
-            if (hit) {
-                const float4 tag = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 4 * (size_t)prim + 3);
-                const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
-                if (bsdf == G19_BSDF_EMITTER) {
-                    // emission counts on camera rays and after specular bounces only (NEE covers the rest)
-                    const float4 T = FIRST ? make_float4(1.f, 1.f, 1.f, 0.f) : a.tp[slot];
-                    if (FIRST || (__float_as_uint(T.w) & 1u)) {
-                        const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
-                        add_radiance(a, slot, f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]));
-                    }
-                } else {
-                    kind = bsdf;
-                }
-            }
-        }
-        warp_append(cur0, kind == G19_BSDF_DIFFUSE, slot, a.q[2], counters + 0);
-        warp_append(cur1, kind == G19_BSDF_MIRROR, slot, a.q[3], counters + 1);
-        warp_append(cur2, kind == G19_BSDF_GLASS, slot, a.q[4], counters + 2);
-        if (!FIRST) {
-            s_cur = s_nxt; s_nxt = s_nn;
-            r0 = n0; r1 = n1;
-        }
-    }
-    warp_flush(cur0, a.q[2]);
-    warp_flush(cur1, a.q[3]);
-    warp_flush(cur2, a.q[4]);
-    if (!FIRST) {
-        traced = warp_sum(traced);
-        if (lane == 0 && traced) atomicAdd(a.totals + 0, (unsigned long long)traced);
+// Nearest hit of one ray, flat or tree. Returns the primitive id and the bsdf/material tags.
+template <bool ALL>
+__device__ __forceinline__ bool nearest(const SceneAccess<ALL>& S, float3 o, float3 d, float& t, uint32_t& prim) {
+    if constexpr (ALL) {
+        bool occ;
+        trace_flat<false>(S, uint32_t(S.g->n_prims), o, d, FLT_MAX, d, -1.0f, t, prim, occ);
+        return prim != kInvalid;
+    } else {
+        return traverse<ALL>(S, o, d, FLT_MAX, false, t, prim);
     }
 }
 
-// ---- shade ---------------------------------------------------------------------------
+// What a new path vertex leaves behind for the next bounce (32 B + 16 B + queue entry).
+__device__ __forceinline__ void store_vertex(const PassArgs& a, uint32_t slot, float3 p, uint32_t prim, float3 d,
+                                             uint32_t pixel) {
+    a.hp[slot] = make_float4(p.x, p.y, p.z, __uint_as_float(prim));
+    a.dw[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+}
+
+// ---- raygen + extend (camera segment) ------------------------------------------------
+template <bool ALL> __global__ void __launch_bounds__(kThreads, ALL ? 4 : 3) raygen_extend_kernel(const PassArgs a) {
+    const uint32_t n = a.n_slots;
+    if (blockIdx.x * kThreads >= n) return;
+    const SceneAccess<ALL> S = stage_scene<ALL>(a);
+    Sorter out;
+    out.init(a, 0);
+    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q - lane < n; q += stride) { // warp-uniform trip count
+        const uint32_t slot = q;
+        int kind = -1;
+        if (q < n) {
+            int x, y;
+            uint32_t sample;
+            if (slot_pixel(a, slot, x, y, sample)) {
+                const uint32_t pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
+                float3 o, d;
+                camera_ray(a, x, y, pixel, sample, o, d);
+                float t;
+                uint32_t prim;
+                if (nearest<ALL>(S, o, d, t, prim)) {
+                    const float4 tag = S.hot_row(prim, 3);
+                    const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
+                    if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
+                        const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
+                        add_radiance(a, slot, f3(m.emission[0], m.emission[1], m.emission[2]));
+                    } else if (bsdf == G19_BSDF_DIFFUSE || a.max_depth > 1) {
+                        kind = bsdf;
+                        store_vertex(a, slot, o + d * t, prim, d, pixel);
+                    }
+                }
+            }
+        }
+        out.push(kind, slot);
+    }
+    out.flush();
+}
+
+// ---- bounce: shade + trace the continuation ray ------------------------------------------
 __device__ __forceinline__ void onb(float3 n, float3& t, float3& b) { // Duff et al. 2017
     float s = copysignf(1.0f, n.z);
     float a = -1.0f / (s + n.z);
@@ -491,31 +569,20 @@ __device__ __forceinline__ void onb(float3 n, float3& t, float3& b) { // Duff et
     b = f3(bb, s + n.y * n.y * a, -n.y);
 }
 
-struct ShadeIn { // what one surface interaction reads from the wavefront state
-    uint2 hit;
-    float4 r0;
-    float2 r1;
-    float4 tp;
-    float l0, l1, l2; // radiance gathered so far (diffuse only: the light sample adds to it)
-};
-
 // Asynchronous prefetch of the NEXT slot's state into shared memory (LDGSTS): a register
 // prefetch gets sunk to its first use by the compiler (ncu: 20 % of the kernel's stall samples
 // sat on that one instruction); a cp.async cannot be, and it holds no registers while in flight.
-// Two buffers per thread, each thread only ever touches its own column.
-struct ShadeStage {
-    float4 ro[2][kThreads];
-    float4 tp[2][kThreads];
-    float2 rd[2][kThreads];
-    uint2 hit[2][kThreads];
-    float L[2][3][kThreads];
+// Two buffers per thread, each thread only ever touches its own column. On the camera segment
+// throughput is 1 and the slot's radiance is still zero, so neither is read.
+template <bool TP, bool RAD> struct VertexStage {
+    float4 hp[2][kThreads];
+    float4 dw[2][kThreads];
+    float4 tp[TP ? 2 : 1][TP ? kThreads : 1];
+    float L[RAD ? 2 : 1][3][RAD ? kThreads : 1];
 };
 
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
@@ -523,112 +590,94 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// On the camera segment nothing is read but the hit: the ray is regenerated, throughput is 1 and
-// the slot's radiance is still zero (an emitter hit would have ended the path in extend).
-template <int KIND, bool FIRST>
-__device__ __forceinline__ void prefetch_shade_in(const PassArgs& a, uint32_t slot, ShadeStage& st, int buf) {
+template <bool TP, bool RAD>
+__device__ __forceinline__ void prefetch_vertex(const PassArgs& a, uint32_t slot, VertexStage<TP, RAD>& st, int buf) {
     const int t = threadIdx.x;
     if (slot != kInvalid) {
-        cp_async8(&st.hit[buf][t], a.hit + slot);
-        if (!FIRST) {
-            cp_async16(&st.ro[buf][t], a.ro + slot);
-            cp_async8(&st.rd[buf][t], a.rd + slot);
-            cp_async16(&st.tp[buf][t], a.tp + slot);
-            if (KIND == Q_DIFFUSE) {
-                cp_async4(&st.L[buf][0][t], a.L + slot);
-                cp_async4(&st.L[buf][1][t], a.L + a.plane + slot);
-                cp_async4(&st.L[buf][2][t], a.L + 2 * a.plane + slot);
-            }
+        cp_async16(&st.hp[buf][t], a.hp + slot);
+        cp_async16(&st.dw[buf][t], a.dw + slot);
+        if (TP) cp_async16(&st.tp[buf][t], a.tp + slot);
+        if (RAD) {
+            cp_async4(&st.L[buf][0][t], a.L + slot);
+            cp_async4(&st.L[buf][1][t], a.L + a.plane + slot);
+            cp_async4(&st.L[buf][2][t], a.L + 2 * a.plane + slot);
         }
     }
     cp_async_commit();
 }
 
-template <int KIND, bool FIRST>
-__device__ __forceinline__ void read_shade_in(const ShadeStage& st, int buf, ShadeIn& in) {
-    const int t = threadIdx.x;
-    in.hit = st.hit[buf][t];
-    if (!FIRST) {
-        in.r0 = st.ro[buf][t];
-        in.r1 = st.rd[buf][t];
-        in.tp = st.tp[buf][t];
-        if (KIND == Q_DIFFUSE) {
-            in.l0 = st.L[buf][0][t];
-            in.l1 = st.L[buf][1][t];
-            in.l2 = st.L[buf][2][t];
-        }
-    }
-}
-
-template <int KIND, bool FIRST, bool ALL>
-__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2)) shade_kernel(const PassArgs a, const int bounce) {
+// KIND: Q_DIFFUSE / Q_MIRROR / Q_GLASS. FIRST: the vertex of the camera segment. LAST: the path's
+// final segment ended here -- next-event estimation only, no continuation.
+template <int KIND, bool FIRST, bool LAST, bool ALL>
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 3) : (ALL ? 3 : 2))
+    bounce_kernel(const PassArgs a, const int bounce) {
+    constexpr bool kDiffuse = KIND == Q_DIFFUSE;
+    constexpr bool kTp = !FIRST, kRad = !FIRST && kDiffuse;
     const uint32_t n = a.counts[bounce * 4 + KIND];
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave before staging anything
-    SceneAccess<ALL> S;
-    if (KIND == Q_DIFFUSE) S = stage_scene<ALL>(a); // shadow rays traverse
-    const uint32_t* __restrict__ qin = a.q[1 + KIND];
-    uint32_t* __restrict__ qout = a.q[(bounce + 1) & 1];
-    uint32_t* __restrict__ cout = a.counts + (bounce + 1) * 4 + Q_EXTEND;
-    const bool more = bounce + 1 < a.max_depth;
-    WarpCursor cur = {0, 0};
-    unsigned shadow_rays = 0, lit = 0, calls = 0;
+    if (LAST && !kDiffuse) return;          // a specular vertex on the last segment contributes nothing
+    const SceneAccess<ALL> S = stage_scene<ALL>(a);
+    const uint32_t* __restrict__ qin = a.q[(bounce & 1) * 3 + (KIND - 1)];
+    Sorter out;
+    if (!LAST) out.init(a, bounce + 1);
+    unsigned traced = 0, shadow_rays = 0, lit = 0, calls = 0;
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_flat = uint32_t(a.scene.n_prims);
+    const bool next_last = bounce + 2 >= a.max_depth;
 
-    __shared__ ShadeStage stage;
+    __shared__ VertexStage<kTp, kRad> stage;
     uint32_t q = blockIdx.x * kThreads + threadIdx.x;
     uint32_t s_cur = kInvalid, s_nxt = kInvalid;
     if (q < n) s_cur = qin[q];
     if (q + stride < n && q + stride >= q) s_nxt = qin[q + stride];
     int buf = 0;
-    prefetch_shade_in<KIND, FIRST>(a, s_cur, stage, 0);
+    prefetch_vertex(a, s_cur, stage, 0);
     for (; q - lane < n; q += stride) {
         uint32_t s_nn = kInvalid;
         {
             const uint32_t q2 = q + 2u * stride;
             if (q2 < n && q2 > q) s_nn = qin[q2];
         }
-        prefetch_shade_in<KIND, FIRST>(a, s_nxt, stage, buf ^ 1); // next slot's state, in flight during this body
-        cp_async_wait<1>();                                       // this slot's state has landed
+        prefetch_vertex(a, s_nxt, stage, buf ^ 1); // next slot's state, in flight during this body
+        cp_async_wait<1>();                        // this slot's state has landed
         const uint32_t slot = s_cur;
-        bool go_on = false;
+        int kind_next = -1;
         if (slot != kInvalid) {
-            ShadeIn in = {}; // camera segment: radiance so far is zero
-            read_shade_in<KIND, FIRST>(stage, buf, in);
             ++calls;
-            int x, y;
+            const int tid = threadIdx.x;
+            const float4 hp = stage.hp[buf][tid], dw = stage.dw[buf][tid];
+            const float3 p = f3(hp.x, hp.y, hp.z), d = f3(dw.x, dw.y, dw.z);
+            const uint32_t prim = __float_as_uint(hp.w), pixel = __float_as_uint(dw.w);
+            float3 T = f3(1.f, 1.f, 1.f);
             uint32_t sample;
-            slot_pixel(a, slot, x, y, sample);
-            float3 o, d, T;
             if (FIRST) {
-                camera_ray(a, x, y, sample, o, d);
-                T = f3(1.f, 1.f, 1.f);
+                uint32_t lp;
+                sample = uint32_t(a.sample_base) + fast_div(slot, uint32_t(a.map.n_local_pix), lp);
             } else {
-                o = f3(in.r0.x, in.r0.y, in.r0.z);
-                d = f3(in.r0.w, in.r1.x, in.r1.y);
-                T = f3(in.tp.x, in.tp.y, in.tp.z);
+                const float4 tp = stage.tp[buf][tid];
+                T = f3(tp.x, tp.y, tp.z);
+                sample = __float_as_uint(tp.w);
             }
-            const float t = __uint_as_float(in.hit.x);
-            const uint32_t prim = in.hit.y;
-            const float3 p = o + d * t;
-            // one hop from the hit record: normal + ior, albedo + material (2 x 16 B, read-only path)
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(a.scene.cold) + 2 * (size_t)prim);
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(a.scene.cold) + 2 * (size_t)prim + 1);
+            float4 c0, c1; // (normal, ior), (albedo, material)
+            S.cold(prim, c0, c1);
             float3 ng = f3(c0.x, c0.y, c0.z);
             if (c0.x == 0.0f && c0.y == 0.0f && c0.z == 0.0f) { // spheres store no normal: (p - centre) / r
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.scene.hot) + 4 * (size_t)prim);
+                const float4 q0 = S.hot_row(prim, 0);
                 ng = (p - f3(q0.x, q0.y, q0.z)) * __fdividef(1.0f, q0.w);
             }
             const float ior = c0.w;
             const bool entering = dot(ng, d) < 0.0f;
             const float3 nf = entering ? ng : -ng; // normal on the side the ray arrives from
             const float3 albedo = f3(c1.x, c1.y, c1.z);
-            const uint32_t pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
             const uint4 r = philox(pixel, sample, uint32_t(bounce), 1u, a.seed);
-            float3 no, nd;
+            float3 no, nd = f3(0.f, 0.f, 1.f);
             uint32_t flags = 0;
-            if (KIND == Q_DIFFUSE) {
-                // next-event estimation: one light, one uniformly sampled point, one any-hit ray
+            // next-event estimation (diffuse only): one light, one uniformly sampled point
+            bool want_shadow = false;
+            float3 w = f3(0.f, 0.f, 1.f), lit_rgb = f3(0.f, 0.f, 0.f);
+            float tmax_s = -1.0f;
+            if (kDiffuse) {
                 if (a.scene.n_lights > 0) {
                     float pick = u01(r.x) * float(a.scene.n_lights);
                     int li = min(int(pick), a.scene.n_lights - 1);
@@ -638,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2
                     float b1 = su * (1.0f - u2), b2 = su * u2;
                     float3 yl = f3(lt.v0[0] + lt.e1[0] * b1 + lt.e2[0] * b2, lt.v0[1] + lt.e1[1] * b1 + lt.e2[1] * b2,
                                    lt.v0[2] + lt.e1[2] * b1 + lt.e2[2] * b2);
-                    float3 w = yl - p;
+                    w = yl - p;
                     float dist2 = dot(w, w);
                     float inv_dist = rsqrtf(dist2);
                     float dist = dist2 * inv_dist;
@@ -646,30 +695,25 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2
                     float cs = dot(nf, w);
                     float cl = fabsf(dot(f3(lt.n[0], lt.n[1], lt.n[2]), w));
                     if (cs > 0.0f && cl > 0.0f && dist > 2.0f * kRayEps) {
-                        float tt;
-                        uint32_t pp;
+                        want_shadow = true;
+                        tmax_s = dist - 2.0f * kRayEps;
+                        float gterm = cs * cl * lt.area * __fdividef(1.0f, dist2 * lt.pdf_pick) * (1.0f / kPi);
+                        lit_rgb = f3(T.x * albedo.x * lt.emission[0] * gterm, T.y * albedo.y * lt.emission[1] * gterm,
+                                     T.z * albedo.z * lt.emission[2] * gterm);
                         ++shadow_rays;
-                        bool blocked = traverse<true, ALL>(S, p + nf * kRayEps, w, 0.0f, dist - 2.0f * kRayEps, tt, pp);
-                        if (!blocked) {
-                            ++lit;
-                            float gterm = cs * cl * lt.area * __fdividef(1.0f, dist2 * lt.pdf_pick) * (1.0f / kPi);
-                            // the old value came in with the prefetched state: store only, no stall
-                            a.L[slot] = in.l0 + T.x * albedo.x * lt.emission[0] * gterm;
-                            a.L[a.plane + slot] = in.l1 + T.y * albedo.y * lt.emission[1] * gterm;
-                            a.L[2 * a.plane + slot] = in.l2 + T.z * albedo.z * lt.emission[2] * gterm;
-                        }
                     }
                 }
-                // cosine-weighted bounce: pdf cancels cos/pi, throughput *= albedo
-                float u3 = u01(r.z), u4 = u01(r.w);
-                float rr = sqrtf(u3), phi = 2.0f * kPi * u4 - kPi; // [-pi, pi): MUFU range
-                float sp, cp;
-                __sincosf(phi, &sp, &cp);
-                sp = -sp; cp = -cp; // shift back by pi
-                float3 tx, ty;
-                onb(nf, tx, ty);
-                nd = normalize(tx * (rr * cp) + ty * (rr * sp) + nf * sqrtf(fmaxf(0.0f, 1.0f - u3)));
                 no = p + nf * kRayEps;
+                if (!LAST) { // cosine-weighted bounce: pdf cancels cos/pi, throughput *= albedo
+                    float u3 = u01(r.z), u4 = u01(r.w);
+                    float rr = sqrtf(u3), phi = 2.0f * kPi * u4 - kPi; // [-pi, pi): MUFU range
+                    float sp, cp;
+                    __sincosf(phi, &sp, &cp);
+                    sp = -sp; cp = -cp; // shift back by pi
+                    float3 tx, ty;
+                    onb(nf, tx, ty);
+                    nd = normalize(tx * (rr * cp) + ty * (rr * sp) + nf * sqrtf(fmaxf(0.0f, 1.0f - u3)));
+                }
                 T = T * albedo;
             } else if (KIND == Q_MIRROR) {
                 nd = normalize(d - nf * (2.0f * dot(d, nf)));
@@ -699,27 +743,82 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : (ALL ? 3 : 2
                 T = T * albedo;
                 flags = 1u;
             }
-            if (more && (T.x > 0.0f || T.y > 0.0f || T.z > 0.0f)) {
-                a.ro[slot] = make_float4(no.x, no.y, no.z, nd.x);
-                a.rd[slot] = make_float2(nd.y, nd.z);
-                a.tp[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(flags));
-                go_on = true;
+            const bool cont = !LAST && (T.x > 0.0f || T.y > 0.0f || T.z > 0.0f);
+            if (cont) ++traced;
+
+            // ---- the rays of this vertex: shadow (any hit) and continuation (nearest hit) ----
+            bool blocked = false, hit = false;
+            float t_hit = FLT_MAX;
+            uint32_t prim_hit = kInvalid;
+            if constexpr (ALL) {
+                const SceneAccess<true>& F = S;
+                if (kDiffuse && !LAST) {
+                    if (want_shadow || cont)
+                        trace_flat<true>(F, n_flat, no, nd, cont ? FLT_MAX : -1.0f, w, tmax_s, t_hit, prim_hit, blocked);
+                } else if (kDiffuse) { // LAST: the shadow ray alone
+                    if (want_shadow) {
+                        bool unused;
+                        trace_flat<false>(F, n_flat, no, w, tmax_s, w, -1.0f, t_hit, prim_hit, unused);
+                        blocked = prim_hit != kInvalid;
+                    }
+                } else if (cont) {
+                    bool unused;
+                    trace_flat<false>(F, n_flat, no, nd, FLT_MAX, nd, -1.0f, t_hit, prim_hit, unused);
+                }
+                hit = cont && prim_hit != kInvalid;
+            } else {
+                // one inlined copy of the tree walk serves both rays: pass 0 = shadow, pass 1 = continuation
+                for (int pass = (kDiffuse && want_shadow) ? 0 : 1; pass < (cont ? 2 : 1); ++pass) {
+                    float tt;
+                    uint32_t pp;
+                    const bool any = pass == 0;
+                    const bool h = traverse<ALL>(S, no, any ? w : nd, any ? tmax_s : FLT_MAX, any, tt, pp);
+                    if (any) blocked = h;
+                    else { hit = h; t_hit = tt; prim_hit = pp; }
+                }
+            }
+            if (kDiffuse && want_shadow && !blocked) {
+                ++lit;
+                // the old value came in with the prefetched state: store only, no stall
+                float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f;
+                if (kRad) { l0 = stage.L[buf][0][tid]; l1 = stage.L[buf][1][tid]; l2 = stage.L[buf][2][tid]; }
+                a.L[slot] = l0 + lit_rgb.x;
+                a.L[a.plane + slot] = l1 + lit_rgb.y;
+                a.L[2 * a.plane + slot] = l2 + lit_rgb.z;
+            }
+            if (hit) {
+                const float4 tag = S.hot_row(prim_hit, 3);
+                const int bsdf = __float_as_int(tag.y);
+                if (bsdf == G19_BSDF_EMITTER) {
+                    // emission counts after specular bounces only (NEE covers the diffuse ones)
+                    if (flags & 1u) {
+                        const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
+                        add_radiance(a, slot, f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]));
+                    }
+                } else if (bsdf == G19_BSDF_DIFFUSE || !next_last) { // a specular vertex on the last segment adds nothing
+                    kind_next = bsdf;
+                    store_vertex(a, slot, no + nd * t_hit, prim_hit, nd, pixel);
+                    a.tp[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
+                }
             }
         }
-        warp_append(cur, go_on, slot, qout, cout);
+        if (!LAST) out.push(kind_next, slot);
         s_cur = s_nxt; s_nxt = s_nn;
         buf ^= 1;
     }
     cp_async_wait<0>();
-    warp_flush(cur, qout);
+    if (!LAST) out.flush();
     calls = warp_sum(calls);
+    traced = warp_sum(traced);
     shadow_rays = warp_sum(shadow_rays);
     lit = warp_sum(lit);
     if (lane == 0 && calls) {
         atomicAdd(a.totals + 2, (unsigned long long)calls);
         if (FIRST) atomicAdd(a.totals + 3, (unsigned long long)calls);
+        if (traced) atomicAdd(a.totals + 0, (unsigned long long)traced);
         if (shadow_rays) atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
         if (lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
+        if (kRad) atomicAdd(a.totals + 5, (unsigned long long)calls); // diffuse vertices that read L
     }
 }
 
@@ -789,14 +888,15 @@ template <typename K> static int resident_grid(K kernel, size_t smem, int sm_cou
     return per_sm * sm_count;
 }
 
-size_t path_smem_bytes(const PassArgs& a, bool with_scene) {
-    if (!with_scene) return 0;
-    size_t nb = (size_t(a.stage_nodes) * 8 + 15) & ~size_t(15);
-    return nb + size_t(a.stage_prims) * 64 + size_t(a.stack_levels) * kThreads * 4 + 16;
+static bool all_staged(const PassArgs& a) { // one leaf, everything in shared memory
+    return a.scene.n_nodes == 1 && a.stage_nodes >= 1 && a.stage_prims >= a.scene.n_index &&
+           a.scene.n_index == a.scene.n_prims && a.stage_cold >= a.scene.n_prims;
 }
 
-static bool all_staged(const PassArgs& a) { // one leaf, everything in shared memory
-    return a.scene.n_nodes == 1 && a.stage_nodes >= 1 && a.stage_prims >= a.scene.n_index;
+size_t path_smem_bytes(const PassArgs& a) {
+    size_t nb = (size_t(a.stage_nodes) * 8 + 15) & ~size_t(15);
+    size_t cb = all_staged(a) ? size_t(a.stage_cold) * 32 : 0;
+    return nb + size_t(a.stage_prims) * 64 + cb + size_t(a.stack_levels) * kThreads * 4 + 16;
 }
 
 static char g_launch_error[256] = "";
@@ -807,60 +907,76 @@ static void note_launch_error(const char* what, cudaError_t e, size_t smem, int 
 }
 
 // The grid of a persistent kernel = SM count x resident CTAs, cached per (kernel, smem size).
-template <typename K> static void launch_persistent(K kernel, const PassArgs& a, int bounce, size_t smem, int sm_count,
-                                                    cudaStream_t s) {
+template <typename K> static int persistent_grid(K kernel, size_t smem, int sm_count) {
     struct Entry { const void* fn; size_t smem; int grid; };
-    static Entry cache[64];
+    static Entry cache[128];
     static int n_cache = 0;
-    int grid = 0;
     for (int i = 0; i < n_cache; ++i)
-        if (cache[i].fn == (const void*)kernel && cache[i].smem == smem) grid = cache[i].grid;
-    if (!grid) {
-        // static (prefetch stage) + dynamic (scene prefix, stack) shared memory may exceed 48 KB.
-        // The attribute is a CAP: always raise it to the same ceiling, never to this scene's size
-        // (a smaller later scene would otherwise lower it under a cached larger launch).
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        if (e != cudaSuccess) note_launch_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e, smem, 0);
-        grid = resident_grid(kernel, smem, sm_count);
-        if (n_cache < 64) cache[n_cache++] = Entry{(const void*)kernel, smem, grid};
-    }
+        if (cache[i].fn == (const void*)kernel && cache[i].smem == smem) return cache[i].grid;
+    // static (prefetch stage) + dynamic (scene prefix, stack) shared memory may exceed 48 KB.
+    // The attribute is a CAP: always raise it to the same ceiling, never to this scene's size
+    // (a smaller later scene would otherwise lower it under a cached larger launch).
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (e != cudaSuccess) note_launch_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e, smem, 0);
+    const int grid = resident_grid(kernel, smem, sm_count);
+    if (n_cache < 128) cache[n_cache++] = Entry{(const void*)kernel, smem, grid};
+    return grid;
+}
+
+template <int KIND, bool FIRST, bool LAST, bool ALL>
+static void launch_bounce_k(const PassArgs& a, int bounce, size_t smem, int sm_count, cudaStream_t s) {
+    auto kernel = bounce_kernel<KIND, FIRST, LAST, ALL>;
+    const int grid = persistent_grid(kernel, smem, sm_count);
     kernel<<<grid, kThreads, smem, s>>>(a, bounce);
     cudaError_t e = cudaPeekAtLastError();
-    if (e != cudaSuccess) note_launch_error("persistent kernel launch", e, smem, grid);
+    if (e != cudaSuccess) note_launch_error("bounce kernel launch", e, smem, grid);
+}
+
+template <int KIND, bool ALL> static void launch_bounce_fl(const PassArgs& a, int bounce, size_t smem, int sm_count, cudaStream_t s) {
+    const bool first = bounce == 0, last = bounce + 1 >= a.max_depth;
+    if (first && last) launch_bounce_k<KIND, true, true, ALL>(a, bounce, smem, sm_count, s);
+    else if (first) launch_bounce_k<KIND, true, false, ALL>(a, bounce, smem, sm_count, s);
+    else if (last) launch_bounce_k<KIND, false, true, ALL>(a, bounce, smem, sm_count, s);
+    else launch_bounce_k<KIND, false, false, ALL>(a, bounce, smem, sm_count, s);
 }
 
 } // namespace
 
-void launch_extend(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
-    const size_t smem = path_smem_bytes(a, true);
+void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
+    const size_t smem = path_smem_bytes(a);
+    cudaError_t e;
+    int grid;
+    if (all_staged(a)) {
+        grid = persistent_grid(raygen_extend_kernel<true>, smem, sm_count);
+        raygen_extend_kernel<true><<<grid, kThreads, smem, s>>>(a);
+    } else {
+        grid = persistent_grid(raygen_extend_kernel<false>, smem, sm_count);
+        raygen_extend_kernel<false><<<grid, kThreads, smem, s>>>(a);
+    }
+    e = cudaPeekAtLastError();
+    if (e != cudaSuccess) note_launch_error("raygen_extend kernel launch", e, smem, grid);
+}
+
+bool launch_bounce(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s) {
+    const bool last = bounce + 1 >= a.max_depth;
+    if (last && kind != Q_DIFFUSE) return false; // nothing to do: no launch
+    const size_t smem = path_smem_bytes(a);
     const bool all = all_staged(a);
-    if (bounce == 0) {
-        if (all) launch_persistent(extend_kernel<true, true>, a, bounce, smem, sm_count, s);
-        else launch_persistent(extend_kernel<true, false>, a, bounce, smem, sm_count, s);
-    } else {
-        if (all) launch_persistent(extend_kernel<false, true>, a, bounce, smem, sm_count, s);
-        else launch_persistent(extend_kernel<false, false>, a, bounce, smem, sm_count, s);
-    }
-}
-
-template <int KIND> static void launch_shade_k(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
-    const size_t smem = path_smem_bytes(a, KIND == Q_DIFFUSE);
-    const bool all = all_staged(a), first = bounce == 0;
-    if (first) {
-        if (all) launch_persistent(shade_kernel<KIND, true, true>, a, bounce, smem, sm_count, s);
-        else launch_persistent(shade_kernel<KIND, true, false>, a, bounce, smem, sm_count, s);
-    } else {
-        if (all) launch_persistent(shade_kernel<KIND, false, true>, a, bounce, smem, sm_count, s);
-        else launch_persistent(shade_kernel<KIND, false, false>, a, bounce, smem, sm_count, s);
-    }
-}
-
-void launch_shade(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s) {
     switch (kind) {
-    case Q_DIFFUSE: launch_shade_k<Q_DIFFUSE>(a, bounce, sm_count, s); break;
-    case Q_MIRROR: launch_shade_k<Q_MIRROR>(a, bounce, sm_count, s); break;
-    default: launch_shade_k<Q_GLASS>(a, bounce, sm_count, s); break;
+    case Q_DIFFUSE:
+        if (all) launch_bounce_fl<Q_DIFFUSE, true>(a, bounce, smem, sm_count, s);
+        else launch_bounce_fl<Q_DIFFUSE, false>(a, bounce, smem, sm_count, s);
+        break;
+    case Q_MIRROR:
+        if (all) launch_bounce_fl<Q_MIRROR, true>(a, bounce, smem, sm_count, s);
+        else launch_bounce_fl<Q_MIRROR, false>(a, bounce, smem, sm_count, s);
+        break;
+    default:
+        if (all) launch_bounce_fl<Q_GLASS, true>(a, bounce, smem, sm_count, s);
+        else launch_bounce_fl<Q_GLASS, false>(a, bounce, smem, sm_count, s);
+        break;
     }
+    return true;
 }
 
 const char* path_launch_error() { return g_launch_error[0] ? g_launch_error : nullptr; }

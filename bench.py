@@ -264,7 +264,8 @@ def main():
     # ---- per-kernel-class CUDA-event times (same steps, event brackets on) --------------------
     barrier()
     cls_ms = [0.0] * 8
-    agg = {"extend": 0, "shadow": 0, "shade": 0, "shade_first": 0, "lit": 0, "samples": 0, "launch": [0] * 8}
+    agg = {"extend": 0, "shadow": 0, "shade": 0, "shade_first": 0, "lit": 0, "rad_reads": 0, "samples": 0,
+           "launch": [0] * 8}
     for _ in range(args.steps):
         step(profile=1)
         torch.cuda.synchronize()
@@ -277,20 +278,25 @@ def main():
         agg["shade"] += s.shade_calls
         agg["shade_first"] += s.shade_calls_first
         agg["lit"] += s.lit_samples
+        agg["rad_reads"] += s.radiance_reads
         agg["samples"] += s.samples
     barrier()
     # algorithmic HBM bytes per class, this rank
-    E, S0, C, C0, LIT = agg["extend"], agg["samples"], agg["shade"], agg["shade_first"], agg["lit"]
+    E, S0, C, C0, LIT, RR = agg["extend"], agg["samples"], agg["shade"], agg["shade_first"], agg["lit"], agg["rad_reads"]
     npix_local = g19.engine.tile_pixels(W, H, rank, world)
+    # vertex record = hit point+primitive 16 B, direction+pixel 16 B; + queue entry 4 B; throughput+sample 16 B
     bytes_cls = {
-        "extend": 12 * S0 + 40 * (E - S0),
-        "shade": 12 * C + 40 * (C - C0) + 44 * (E - S0) + 24 * LIT,
+        "raygen_extend": 36 * C0,                       # vertex + queue entry written per shaded camera hit
+        "bounce": (36 * C                               # queue entry + vertex read per shaded vertex
+                   + 16 * (C - C0) + 12 * RR            # throughput, radiance so far (past the camera segment)
+                   + 12 * LIT                           # radiance written per unoccluded light sample
+                   + 52 * (C - C0)),                    # vertex + throughput + queue entry of each continuation hit
         "accumulate": 24 * S0 + 24 * npix_local * max(1, agg["launch"][abi.K_ACCUM]),
     }
-    ms_cls = {"extend": cls_ms[abi.K_EXTEND], "shade": cls_ms[abi.K_SHADE], "accumulate": cls_ms[abi.K_ACCUM]}
+    ms_cls = {"raygen_extend": cls_ms[abi.K_EXTEND], "bounce": cls_ms[abi.K_SHADE], "accumulate": cls_ms[abi.K_ACCUM]}
     top = max(ms_cls, key=lambda k: ms_cls[k])
     peak, peak_src = measured_peak()
-    n_launch = {"extend": agg["launch"][abi.K_EXTEND], "shade": agg["launch"][abi.K_SHADE],
+    n_launch = {"raygen_extend": agg["launch"][abi.K_EXTEND], "bounce": agg["launch"][abi.K_SHADE],
                 "accumulate": agg["launch"][abi.K_ACCUM]}
     achieved = bytes_cls[top] / (ms_cls[top] * 1e-3) / 1e9 if ms_cls[top] > 0 else 0.0
     traffic, issue_pct = None, None

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define G19_ABI_VERSION 1
+#define G19_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -161,14 +161,17 @@ typedef struct g19_stats {
     uint64_t shadow_segments; /* any-hit rays                                 */
     uint64_t kernel_launches; /* kernels of this library launched by the call */
     double render_ms;         /* device time of the whole call (CUDA events)  */
-    /* per kernel class, only when params.profile: [raygen+extend, shade,
-     * shadow, accumulate, ref_visibility, ref_shade, other]                 */
+    /* per kernel class, only when params.profile: [raygen+extend (camera
+     * segment), bounce (shade + continuation trace), -, accumulate,
+     * ref_visibility, ref_shade, other]                                      */
     double class_ms[8];
     uint64_t class_launches[8];
     uint64_t node_tests, prim_tests; /* REF mode, only when profile           */
     uint64_t shade_calls;     /* PATH: surface interactions shaded            */
     uint64_t shade_calls_first; /* ... of which on the camera segment         */
     uint64_t lit_samples;     /* PATH: unoccluded next-event samples          */
+    uint64_t radiance_reads;  /* PATH: diffuse vertices past the camera segment (they read the
+                                 path's radiance so far; bench.py's byte model)               */
 } g19_stats;
 
 enum { G19_K_EXTEND = 0, G19_K_SHADE = 1, G19_K_SHADOW = 2, G19_K_ACCUM = 3,
