@@ -196,7 +196,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
                     float cy = l.e1[2] * l.e2[0] - l.e1[0] * l.e2[2];
                     float cz = l.e1[0] * l.e2[1] - l.e1[1] * l.e2[0];
                     l.area = 0.5f * std::sqrt(cx * cx + cy * cy + cz * cz);
-                    l.prim = int32_t(prims.size()) - 1;
+                    l.prim = -1; // (unused: primitive ids are final only after the merge / kind sort below)
                     l.n[0] = p.cold.n[0]; l.n[1] = p.cold.n[1]; l.n[2] = p.cold.n[2];
                     l.emission[0] = m.emission[0]; l.emission[1] = m.emission[1]; l.emission[2] = m.emission[2];
                     if (l.area > 0) lights.push_back(l);
@@ -242,6 +242,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
                         for (int k = 0; k < 3; ++k) { e1[k] = u[k] - s1[k]; e2[k] = v[k] - s1[k]; }
                         affine_rows(q.hot.q, s1, e1, e2);
                         q.hot.q[14] = 2.0f; // kind = parallelogram
+                        q.hot.q[3] -= 0.5f; // centred coordinates: inside <=> max(|b1|, |b2|) <= 1/2
+                        q.hot.q[7] -= 0.5f;
                         for (int k = 0; k < 3; ++k) {
                             q.box.lo[k] = std::min(A.box.lo[k], B.box.lo[k]);
                             q.box.hi[k] = std::max(A.box.hi[k], B.box.hi[k]);
@@ -347,6 +349,18 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
                      double(index.size()) / double(std::max<size_t>(1, prims.size())),
                      double(index.size()) / double(std::max<size_t>(1, leaves)), biggest);
     }
+    // A flat scene (the whole scene is one leaf) is sorted parallelograms | triangles | spheres so
+    // that the kernels walk three branch-free loops; the leaf position stays the primitive id.
+    int n_par = 0, n_tri = 0;
+    if (nodes.size() == 1) {
+        auto rank = [](const BuildPrim& p) { return p.hot.q[14] == 2.0f ? 0 : (p.hot.q[14] == 1.0f ? 1 : 2); };
+        std::stable_sort(prims.begin(), prims.end(), [&](const BuildPrim& x, const BuildPrim& y) { return rank(x) < rank(y); });
+        for (const BuildPrim& p : prims) {
+            if (rank(p) == 0) ++n_par;
+            else if (rank(p) == 1) ++n_tri;
+        }
+        for (size_t i = 0; i < index.size(); ++i) index[i] = uint32_t(i);
+    }
     std::vector<PrimHot> hot(prims.size());
     std::vector<PrimCold> cold(prims.size());
     for (size_t i = 0; i < prims.size(); ++i) {
@@ -389,6 +403,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     v.n_prims = int32_t(prims.size());
     v.n_lights = int32_t(lights.size());
     v.tree_depth = tree_depth;
+    v.n_par = n_par;
+    v.n_tri = n_tri;
     for (int k = 0; k < 3; ++k) {
         v.root_lo[k] = root_lo[k];
         v.root_size[k] = root_size[k];
@@ -512,6 +528,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     // flat scene (one leaf, all of it staged): the shading records ride along
     pa.stage_cold = (b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= pa.stage_prims)
                         ? b.view.n_prims : 0;
+    pa.stage_lights = (pa.stage_cold > 0 && b.view.n_lights <= 32) ? b.view.n_lights : 0;
+    if (b.view.n_lights > 32) pa.stage_cold = 0; // not a "flat, fully staged" scene: the generic kernels take it
     pa.stack_levels = b.view.tree_depth + 1;
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;

@@ -43,6 +43,7 @@ struct PathSceneD {
     const MaterialD* materials;
     const LightD* lights;
     int32_t n_nodes, n_index, n_prims, n_lights, tree_depth;
+    int32_t n_par, n_tri;    // flat scenes: primitives sorted parallelograms | triangles | spheres
     float root_lo[3], root_size[3];
 };
 
@@ -126,7 +127,7 @@ struct PassArgs {
     unsigned long long* totals;
     float* accum;          // 3 planes of n_local_pix
     // shared-memory staging (see path_kernels.cu stage_scene)
-    int32_t stage_nodes, stage_prims, stage_cold, stack_levels;
+    int32_t stage_nodes, stage_prims, stage_cold, stage_lights, stack_levels;
 };
 
 void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s);

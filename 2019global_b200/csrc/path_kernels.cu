@@ -90,7 +90,7 @@ __device__ __forceinline__ float3 normalize(float3 v) { return v * rsqrtf(dot(v,
 // ---- shared-memory scene prefix ----------------------------------------------
 // Dynamic shared memory, sized on the host to what the scene needs (PassArgs::stage_*):
 //   [nodes: stage_nodes x 8 B][leaf-ordered hot prims: stage_prims x 64 B]
-//   [cold records: stage_cold x 32 B (flat scenes only)]
+//   [cold records: stage_cold x 32 B][lights: stage_lights x 80 B]   (flat scenes only)
 //   [traversal stack: stack_levels x kThreads x 4 B][mbarrier: 8 B]
 // A Cornell box stages whole (about 0.8 KB) and leaves the SM free for more CTAs.
 extern __shared__ __align__(16) unsigned char g19_dyn_smem[];
@@ -100,6 +100,7 @@ template <bool ALL> struct SceneAccess {
     const uint2* nodes_s;
     const float4* hot_s;
     const float4* cold_s;
+    const float4* lights_s;
     uint32_t* stack;
     int n_nodes_s, n_prims_s;
     __device__ __forceinline__ uint2 node(uint32_t i) const {
@@ -124,6 +125,11 @@ template <bool ALL> struct SceneAccess {
             c0 = __ldg(p); c1 = __ldg(p + 1);
         }
     }
+    // area-light record = 5 x float4: (v0, area) (e1, pdf_pick) (e2, -) (n, -) (emission, -)
+    __device__ __forceinline__ const float4* light(int li) const {
+        if (ALL) return lights_s + 5 * li;
+        return reinterpret_cast<const float4*>(g->lights) + 5 * (size_t)li;
+    }
     // row 0 / row 3 of the hot record BY PRIMITIVE ID (flat scenes: leaf order == id order)
     __device__ __forceinline__ float4 hot_row(uint32_t prim, int row) const {
         if (ALL) return hot_s[4 * prim + row];
@@ -144,13 +150,15 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
     const uint32_t pb = uint32_t(a.stage_prims) * 64u;
     const uint32_t cb = ALL ? uint32_t(a.stage_cold) * 32u : 0u;
+    const uint32_t lb = ALL ? uint32_t(a.stage_lights) * 80u : 0u;
     unsigned char* base = g19_dyn_smem;
     acc.nodes_s = reinterpret_cast<const uint2*>(base);
     acc.hot_s = reinterpret_cast<const float4*>(base + nb);
     acc.cold_s = reinterpret_cast<const float4*>(base + nb + pb);
-    acc.stack = reinterpret_cast<uint32_t*>(base + nb + pb + cb) + threadIdx.x;
+    acc.lights_s = reinterpret_cast<const float4*>(base + nb + pb + cb);
+    acc.stack = reinterpret_cast<uint32_t*>(base + nb + pb + cb + lb) + threadIdx.x;
     unsigned long long* barp =
-        reinterpret_cast<unsigned long long*>(base + nb + pb + cb + uint32_t(a.stack_levels) * kThreads * 4u);
+        reinterpret_cast<unsigned long long*>(base + nb + pb + cb + lb + uint32_t(a.stack_levels) * kThreads * 4u);
     const uint32_t bar = smem_addr(barp);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -158,7 +166,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + pb + cb) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + pb + cb + lb) : "memory");
         if (nb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(base)),
@@ -174,6 +182,11 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
                              smem_addr(base + nb + pb)),
                          "l"(g.cold), "r"(cb), "r"(bar)
                          : "memory");
+        if (lb)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(base + nb + pb + cb)),
+                         "l"(g.lights), "r"(lb), "r"(bar)
+                         : "memory");
     }
     uint32_t done = 0; // everyone waits for phase 0 of the barrier
     while (!done) {
@@ -188,9 +201,14 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
 // ---- primitive intersection ---------------------------------------------------
 // Triangles / parallelograms: the ray is mapped into the primitive's own (b1, b2, h) frame by
 // the precomputed affine rows -- the ORIGIN half (three 4-term dot products) is shared by every
-// ray that leaves the same point, the DIRECTION half costs 9 FMAs, one fast division, 2 FMAs and
-// 5 compares per ray. tag.z = kind: 0 sphere, 1 triangle (b1+b2 <= 1), 2 parallelogram
-// (b1, b2 <= 1). Spheres: unit direction, discriminant from the perpendicular offset.
+// ray that leaves the same point, the DIRECTION half costs 9 FMAs, one fast division and 2 FMAs
+// per ray. The accept test is built for the ALU pipe, the busiest one (ncu: 50 % of its peak):
+//   * t in (0, tmax): ONE unsigned compare of the float bit patterns -- negative values, -0 and
+//     NaN all have larger patterns than any positive bound; a switched-off ray has bound 0
+//   * parallelogram (kind 2): the builder centres the coordinates, inside <=> max(|u|,|v|) <= 1/2
+//   * triangle (kind 1): inside <=> min(u, v, 1 - u - v) >= 0
+// Spheres: unit direction, discriminant from the perpendicular offset; the nearer root ahead of
+// the origin is the unsigned minimum of the two roots' bit patterns.
 struct PlaneOrigin {
     float ox, oy, oz;
 };
@@ -201,59 +219,80 @@ __device__ __forceinline__ PlaneOrigin plane_origin(float4 a, float4 b, float4 c
     r.oy = fmaf(b.x, o.x, fmaf(b.y, o.y, fmaf(b.z, o.z, b.w)));
     return r;
 }
-// t in (0, tmax) or -1
-__device__ __forceinline__ float plane_hit(float4 a, float4 b, float4 c, float kind, PlaneOrigin po, float3 d, float tmax) {
-    float dz = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
-    float t = __fdividef(-po.oz, dz);
-    float dx = fmaf(a.x, d.x, fmaf(a.y, d.y, a.z * d.z));
-    float dy = fmaf(b.x, d.x, fmaf(b.y, d.y, b.z * d.z));
-    float u = fmaf(t, dx, po.ox), v = fmaf(t, dy, po.oy);
-    float edge = (kind > 1.5f) ? fmaxf(u, v) : u + v;
-    bool ok = (t > 0.0f) & (t < tmax) & (u >= 0.0f) & (v >= 0.0f) & (edge <= 1.0f);
-    return ok ? t : -1.0f;
+// KIND 2 parallelogram, 1 triangle. Returns "hit inside and nearer than lim"; t_bits = pattern of t.
+template <int KIND>
+__device__ __forceinline__ bool plane_hit(float4 a, float4 b, float4 c, PlaneOrigin po, float3 d, uint32_t lim, uint32_t& t_bits) {
+    const float dz = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
+    const float t = __fdividef(-po.oz, dz);
+    const float dx = fmaf(a.x, d.x, fmaf(a.y, d.y, a.z * d.z));
+    const float dy = fmaf(b.x, d.x, fmaf(b.y, d.y, b.z * d.z));
+    const float u = fmaf(t, dx, po.ox), v = fmaf(t, dy, po.oy);
+    t_bits = __float_as_uint(t);
+    if (KIND == 2) return (fmaxf(fabsf(u), fabsf(v)) <= 0.5f) & (t_bits < lim);
+    return (fminf(fminf(u, v), 1.0f - (u + v)) >= 0.0f) & (t_bits < lim);
 }
-__device__ __forceinline__ float sphere_hit(float3 oc, float radius, float3 d, float tmax) {
-    float bq = dot(oc, d);
-    float3 l = oc - d * bq;
-    float disc = radius * radius - dot(l, l);
-    float sq = sqrtf(fmaxf(disc, 0.0f));
-    float t0 = -bq - sq, t1 = -bq + sq;
-    float t = (t0 > 0.0f) ? t0 : t1; // the near root if it lies ahead, else the far one
-    bool ok = (disc >= 0.0f) & (t > 0.0f) & (t < tmax);
-    return ok ? t : -1.0f;
+__device__ __forceinline__ bool sphere_hit(float3 oc, float radius, float3 d, uint32_t lim, uint32_t& t_bits) {
+    const float bq = dot(oc, d);
+    const float3 l = oc - d * bq;
+    const float disc = fmaf(radius, radius, -dot(l, l));
+    const float sq = sqrtf(disc); // NaN when the ray misses: fails the range test below
+    t_bits = min(__float_as_uint(-bq - sq), __float_as_uint(sq - bq));
+    return t_bits < lim;
 }
+__device__ __forceinline__ uint32_t range_limit(float tmax) { return tmax > 0.0f ? __float_as_uint(tmax) : 0u; }
+
+// generic form for the mixed leaves of a tree: t in (0, tmax) or -1
 __device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 tag, float3 o, float3 d, float tmax) {
-    if (tag.z != 0.0f) return plane_hit(a, b, c, tag.z, plane_origin(a, b, c, o), d, tmax);
-    return sphere_hit(o - f3(a.x, a.y, a.z), a.w, d, tmax);
+    uint32_t tb;
+    bool ok;
+    const uint32_t lim = __float_as_uint(tmax); // callers pass tmax > 0
+    if (tag.z != 0.0f) {
+        const PlaneOrigin po = plane_origin(a, b, c, o);
+        ok = tag.z > 1.5f ? plane_hit<2>(a, b, c, po, d, lim, tb) : plane_hit<1>(a, b, c, po, d, lim, tb);
+    } else {
+        ok = sphere_hit(o - f3(a.x, a.y, a.z), a.w, d, lim, tb);
+    }
+    return ok ? __uint_as_float(tb) : -1.0f;
 }
 
-// Flat scene (ONE leaf, fully staged): nearest hit of ray (o, d1) within tmax1 and, when DUAL,
-// any hit of ray (o, d0) within tmax0 -- both leave the same point, so one pass over the
-// primitives serves both. A ray with tmax <= 0 is switched off. Returns the leaf position
-// (== primitive id in a flat scene) of the nearest hit in best_k.
+// Flat scene (ONE leaf, fully staged, primitives sorted parallelograms | triangles | spheres by
+// the builder): nearest hit of ray (o, d1) within tmax1 and, when DUAL, any hit of ray (o, d0)
+// within tmax0 -- both leave the same point, so one pass over the primitives serves both. A ray
+// with tmax <= 0 is switched off. Three branch-free loops; the leaf position IS the primitive id.
 template <bool DUAL>
-__device__ __forceinline__ void trace_flat(const SceneAccess<true>& S, uint32_t n, float3 o, float3 d1, float tmax1,
-                                           float3 d0, float tmax0, float& best, uint32_t& best_k, bool& occluded) {
-    best = tmax1;
-    best_k = kInvalid;
-    bool occ = false;
+__device__ __forceinline__ void trace_flat(const SceneAccess<true>& S, float3 o, float3 d1, float tmax1, float3 d0,
+                                           float tmax0, float& best, uint32_t& best_k, bool& occluded) {
+    uint32_t lim1 = range_limit(tmax1), lim0 = DUAL ? range_limit(tmax0) : 0u;
+    uint32_t hit_k = kInvalid;
+    const uint32_t n_par = uint32_t(S.g->n_par), n_flat = n_par + uint32_t(S.g->n_tri), n = uint32_t(S.g->n_prims);
+    uint32_t k = 0;
 #pragma unroll 2
-    for (uint32_t k = 0; k < n; ++k) {
-        const float4 a = S.hot_s[4 * k], b = S.hot_s[4 * k + 1], c = S.hot_s[4 * k + 2], g = S.hot_s[4 * k + 3];
-        float t1, t0 = -1.0f;
-        if (g.z != 0.0f) { // warp-uniform: every lane walks the same list
-            const PlaneOrigin po = plane_origin(a, b, c, o);
-            t1 = plane_hit(a, b, c, g.z, po, d1, best);
-            if (DUAL) t0 = plane_hit(a, b, c, g.z, po, d0, tmax0);
-        } else {
-            const float3 oc = o - f3(a.x, a.y, a.z);
-            t1 = sphere_hit(oc, a.w, d1, best);
-            if (DUAL) t0 = sphere_hit(oc, a.w, d0, tmax0);
-        }
-        if (t1 >= 0.0f) { best = t1; best_k = k; }
-        if (DUAL) occ |= (t0 >= 0.0f);
+    for (; k < n_par; ++k) {
+        const float4 a = S.hot_s[4 * k], b = S.hot_s[4 * k + 1], c = S.hot_s[4 * k + 2];
+        const PlaneOrigin po = plane_origin(a, b, c, o);
+        uint32_t tb;
+        if (plane_hit<2>(a, b, c, po, d1, lim1, tb)) { lim1 = tb; hit_k = k; }
+        if (DUAL && plane_hit<2>(a, b, c, po, d0, lim0, tb)) lim0 = 0u;
     }
-    occluded = occ;
+#pragma unroll 2
+    for (; k < n_flat; ++k) {
+        const float4 a = S.hot_s[4 * k], b = S.hot_s[4 * k + 1], c = S.hot_s[4 * k + 2];
+        const PlaneOrigin po = plane_origin(a, b, c, o);
+        uint32_t tb;
+        if (plane_hit<1>(a, b, c, po, d1, lim1, tb)) { lim1 = tb; hit_k = k; }
+        if (DUAL && plane_hit<1>(a, b, c, po, d0, lim0, tb)) lim0 = 0u;
+    }
+#pragma unroll 2
+    for (; k < n; ++k) {
+        const float4 a = S.hot_s[4 * k];
+        const float3 oc = o - f3(a.x, a.y, a.z);
+        uint32_t tb;
+        if (sphere_hit(oc, a.w, d1, lim1, tb)) { lim1 = tb; hit_k = k; }
+        if (DUAL && sphere_hit(oc, a.w, d0, lim0, tb)) lim0 = 0u;
+    }
+    best = __uint_as_float(lim1);
+    best_k = hit_k;
+    occluded = DUAL && tmax0 > 0.0f && lim0 == 0u;
 }
 
 // Cell edge: the SAME expression as cell_edge() in path.cu (no FMA contraction).
@@ -507,7 +546,7 @@ template <bool ALL>
 __device__ __forceinline__ bool nearest(const SceneAccess<ALL>& S, float3 o, float3 d, float& t, uint32_t& prim) {
     if constexpr (ALL) {
         bool occ;
-        trace_flat<false>(S, uint32_t(S.g->n_prims), o, d, FLT_MAX, d, -1.0f, t, prim, occ);
+        trace_flat<false>(S, o, d, FLT_MAX, d, -1.0f, t, prim, occ);
         return prim != kInvalid;
     } else {
         return traverse<ALL>(S, o, d, FLT_MAX, false, t, prim);
@@ -623,7 +662,6 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 3) : 
     unsigned traced = 0, shadow_rays = 0, lit = 0, calls = 0;
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_flat = uint32_t(a.scene.n_prims);
     const bool next_last = bounce + 2 >= a.max_depth;
 
     __shared__ VertexStage<kTp, kRad> stage;
@@ -682,24 +720,24 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 3) : 
                     float pick = u01(r.x) * float(a.scene.n_lights);
                     int li = min(int(pick), a.scene.n_lights - 1);
                     float u1 = pick - float(li), u2 = u01(r.y);
-                    const LightD& lt = a.scene.lights[li];
+                    const float4* lt = S.light(li);
+                    const float4 l0 = lt[0], l1 = lt[1], l2 = lt[2], l3 = lt[3];
                     float su = sqrtf(u1);
                     float b1 = su * (1.0f - u2), b2 = su * u2;
-                    float3 yl = f3(lt.v0[0] + lt.e1[0] * b1 + lt.e2[0] * b2, lt.v0[1] + lt.e1[1] * b1 + lt.e2[1] * b2,
-                                   lt.v0[2] + lt.e1[2] * b1 + lt.e2[2] * b2);
+                    float3 yl = f3(l0.x + l1.x * b1 + l2.x * b2, l0.y + l1.y * b1 + l2.y * b2, l0.z + l1.z * b1 + l2.z * b2);
                     w = yl - p;
                     float dist2 = dot(w, w);
                     float inv_dist = rsqrtf(dist2);
                     float dist = dist2 * inv_dist;
                     w = w * inv_dist;
                     float cs = dot(nf, w);
-                    float cl = fabsf(dot(f3(lt.n[0], lt.n[1], lt.n[2]), w));
+                    float cl = fabsf(dot(f3(l3.x, l3.y, l3.z), w));
                     if (cs > 0.0f && cl > 0.0f && dist > 2.0f * kRayEps) {
                         want_shadow = true;
                         tmax_s = dist - 2.0f * kRayEps;
-                        float gterm = cs * cl * lt.area * __fdividef(1.0f, dist2 * lt.pdf_pick) * (1.0f / kPi);
-                        lit_rgb = f3(T.x * albedo.x * lt.emission[0] * gterm, T.y * albedo.y * lt.emission[1] * gterm,
-                                     T.z * albedo.z * lt.emission[2] * gterm);
+                        const float4 l4 = lt[4];
+                        float gterm = cs * cl * l0.w * __fdividef(1.0f, dist2 * l1.w) * (1.0f / kPi);
+                        lit_rgb = f3(T.x * albedo.x * l4.x * gterm, T.y * albedo.y * l4.y * gterm, T.z * albedo.z * l4.z * gterm);
                         ++shadow_rays;
                     }
                 }
@@ -754,16 +792,16 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 3) : 
                 const SceneAccess<true>& F = S;
                 if (kDiffuse && !LAST) {
                     if (want_shadow || cont)
-                        trace_flat<true>(F, n_flat, no, nd, cont ? FLT_MAX : -1.0f, w, tmax_s, t_hit, prim_hit, blocked);
+                        trace_flat<true>(F, no, nd, cont ? FLT_MAX : -1.0f, w, tmax_s, t_hit, prim_hit, blocked);
                 } else if (kDiffuse) { // LAST: the shadow ray alone
                     if (want_shadow) {
                         bool unused;
-                        trace_flat<false>(F, n_flat, no, w, tmax_s, w, -1.0f, t_hit, prim_hit, unused);
+                        trace_flat<false>(F, no, w, tmax_s, w, -1.0f, t_hit, prim_hit, unused);
                         blocked = prim_hit != kInvalid;
                     }
                 } else if (cont) {
                     bool unused;
-                    trace_flat<false>(F, n_flat, no, nd, FLT_MAX, nd, -1.0f, t_hit, prim_hit, unused);
+                    trace_flat<false>(F, no, nd, FLT_MAX, nd, -1.0f, t_hit, prim_hit, unused);
                 }
                 hit = cont && prim_hit != kInvalid;
             } else {
@@ -890,12 +928,12 @@ template <typename K> static int resident_grid(K kernel, size_t smem, int sm_cou
 
 static bool all_staged(const PassArgs& a) { // one leaf, everything in shared memory
     return a.scene.n_nodes == 1 && a.stage_nodes >= 1 && a.stage_prims >= a.scene.n_index &&
-           a.scene.n_index == a.scene.n_prims && a.stage_cold >= a.scene.n_prims;
+           a.scene.n_index == a.scene.n_prims && a.stage_cold >= a.scene.n_prims && a.stage_lights >= a.scene.n_lights;
 }
 
 size_t path_smem_bytes(const PassArgs& a) {
     size_t nb = (size_t(a.stage_nodes) * 8 + 15) & ~size_t(15);
-    size_t cb = all_staged(a) ? size_t(a.stage_cold) * 32 : 0;
+    size_t cb = all_staged(a) ? size_t(a.stage_cold) * 32 + size_t(a.stage_lights) * 80 : 0;
     return nb + size_t(a.stage_prims) * 64 + cb + size_t(a.stack_levels) * kThreads * 4 + 16;
 }
 
