@@ -28,6 +28,7 @@ UNITS = [
     ("builtin_scenes.cpp", []),
     ("ref_kernels.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("path_kernels.cu", ["--use_fast_math", "-Xptxas", "-v"]),
+    ("frame_kernels.cu", []),
     ("path.cu", []),
     ("engine.cu", []),
 ]

@@ -76,7 +76,41 @@ struct g19_ctx {
     bool stats_pending = false;
 };
 
+// A frame that several ranks write (include/g19.h "shared frame"): owner = the process that
+// allocated it (rank 0), importers map it through CUDA IPC and reach it over NVLink.
+struct g19_frame {
+    int device = 0;
+    bool owner = false;
+    int32_t w = 0, h = 0;
+    void* base = nullptr; // [flags 512 B][radiance w*h*3 floats, 256-aligned][rgb888 w*h*3]
+    size_t bytes = 0;
+    unsigned* flags = nullptr;
+    float* rad = nullptr;
+    uint8_t* rgb = nullptr;
+    unsigned epoch = 0; // frames rendered into it by THIS process (all ranks advance in lockstep)
+    cudaIpcMemHandle_t handle{};
+};
+
 namespace {
+
+struct FrameBlob { // what g19_frame_export ships to the other ranks
+    uint32_t magic;
+    int32_t w, h;
+    uint64_t bytes;
+    cudaIpcMemHandle_t handle;
+};
+constexpr uint32_t kFrameMagic = 0x46393147u; // "G19F"
+
+void frame_layout(g19_frame* f) {
+    size_t npx = size_t(f->w) * size_t(f->h);
+    size_t rad_off = 512, rgb_off = (rad_off + npx * 12 + 255) & ~size_t(255);
+    f->bytes = rgb_off + ((npx * 3 + 255) & ~size_t(255));
+    if (f->base) {
+        f->flags = static_cast<unsigned*>(f->base);
+        f->rad = reinterpret_cast<float*>(static_cast<char*>(f->base) + rad_off);
+        f->rgb = reinterpret_cast<uint8_t*>(static_cast<char*>(f->base) + rgb_off);
+    }
+}
 
 #define G19_CUDA(ctx, call)                                                                              \
     do {                                                                                                 \
@@ -244,7 +278,7 @@ struct ClassTimer { // CUDA-event timing of one kernel class (params.profile)
 
 int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p, const TileMap& map,
                uint8_t* d_rgb, int32_t* d_ids, float* d_rad, uint8_t* t_rgb, int32_t* t_ids, float* t_rad,
-               cudaStream_t s) {
+               cudaStream_t s, g19_frame* frame = nullptr) {
     RefCamera rc = make_camera(*cam, light, p->width);
     size_t n = size_t(map.n_local_pix);
     G19_CUDA(ctx, ctx->ids_l.ensure(n * sizeof(int32_t)));
@@ -268,9 +302,16 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
                      ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s);
     t.end(G19_K_REF_SHADE, 1);
     t.begin();
-    launch_untile(map, d_rgb ? ctx->rgb_l.as<uint8_t>() : nullptr, d_ids ? ctx->ids_l.as<int32_t>() : nullptr,
-                  d_rad ? ctx->colour_l.as<float>() : nullptr, d_rgb, d_ids, d_rad, s);
-    t.end(G19_K_OTHER, 1);
+    if (frame) { // shared frame: wait for the owner, scatter this rank's pixels into it, signal
+        launch_frame_acquire(frame->flags, frame->epoch - 1, s);
+        launch_untile(map, ctx->rgb_l.as<uint8_t>(), nullptr, ctx->colour_l.as<float>(), frame->rgb, nullptr, frame->rad, s);
+        launch_frame_signal(frame->flags, s);
+        t.end(G19_K_OTHER, 3);
+    } else {
+        launch_untile(map, d_rgb ? ctx->rgb_l.as<uint8_t>() : nullptr, d_ids ? ctx->ids_l.as<int32_t>() : nullptr,
+                      d_rad ? ctx->colour_l.as<float>() : nullptr, d_rgb, d_ids, d_rad, s);
+        t.end(G19_K_OTHER, 1);
+    }
     G19_CUDA(ctx, cudaGetLastError());
     if (t_rgb) G19_CUDA(ctx, cudaMemcpyAsync(t_rgb, ctx->rgb_l.p, n * 3, cudaMemcpyDeviceToDevice, s));
     if (t_ids) G19_CUDA(ctx, cudaMemcpyAsync(t_ids, ctx->ids_l.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
@@ -390,7 +431,7 @@ int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene) {
 
 static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p,
                       uint8_t* d_rgb, int32_t* d_ids, float* d_rad, uint8_t* t_rgb, int32_t* t_ids, float* t_rad,
-                      void* stream) {
+                      void* stream, g19_frame* frame = nullptr) {
     int rc = check_params(ctx, cam, p);
     if (rc != G19_OK) return rc;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -401,7 +442,8 @@ static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3]
     TileMap map = make_tile_map(p->width, p->height, p->rank, p->world);
     G19_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     if (p->mode == G19_MODE_REF) {
-        rc = render_ref(ctx, cam, light, p, map, d_rgb, d_ids, d_rad, t_rgb, t_ids, t_rad, s);
+        if (frame && map.n_local_pix == 0) launch_frame_signal(frame->flags, s); // no tiles: still counted
+        else rc = render_ref(ctx, cam, light, p, map, d_rgb, d_ids, d_rad, t_rgb, t_ids, t_rad, s, frame);
     } else {
         RefCamera rc64 = make_camera(*cam, light, p->width);
         PathRenderArgs a;
@@ -419,7 +461,14 @@ static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3]
         a.progress_milli = &ctx->progress_milli;
         a.cls0 = ctx->cls0;
         a.cls1 = ctx->cls1;
+        if (frame) {
+            a.frame_rgb = frame->rgb;
+            a.frame_rad = frame->rad;
+            a.frame_flags = frame->flags;
+            a.frame_need_consumed = frame->epoch - 1;
+        }
         std::string perr;
+        if (frame && map.n_local_pix == 0) launch_frame_signal(frame->flags, s); // no tiles: still counted
         rc = path_render(ctx->path, ctx->work, a, ctx->stats, perr);
         if (rc != G19_OK) ctx->err = perr;
     }
@@ -481,6 +530,149 @@ int g19_render(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     if (rad) G19_CUDA(ctx, cudaMemcpyAsync(rad, ctx->rad_f.p, npx * 12, cudaMemcpyDeviceToHost, s));
     G19_CUDA(ctx, cudaStreamSynchronize(s));
     return rc;
+}
+
+// ---- shared frame (multi-GPU, fused gather) ---------------------------------------------------
+int g19_frame_create(g19_ctx* ctx, int w, int h, g19_frame** out) {
+    if (!ctx || !out || w < 0 || h < 0) return G19_ERR_INVALID;
+    *out = nullptr;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    g19_frame* f = new (std::nothrow) g19_frame();
+    if (!f) return G19_ERR_INVALID;
+    f->device = ctx->device;
+    f->owner = true;
+    f->w = w;
+    f->h = h;
+    frame_layout(f);
+    cudaError_t e = cudaMalloc(&f->base, f->bytes);
+    if (e == cudaSuccess) e = cudaMemset(f->base, 0, f->bytes);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("g19_frame_create: ") + cudaGetErrorString(e);
+        if (f->base) cudaFree(f->base);
+        delete f;
+        return G19_ERR_CUDA;
+    }
+    frame_layout(f);
+    *out = f;
+    return G19_OK;
+}
+
+int g19_frame_export(g19_ctx* ctx, g19_frame* f, void* blob, size_t blob_bytes) {
+    if (!ctx || !f || !blob || !f->owner) return G19_ERR_INVALID;
+    if (blob_bytes < sizeof(FrameBlob)) {
+        ctx->err = "g19_frame_export: blob buffer smaller than G19_FRAME_BLOB_BYTES";
+        return G19_ERR_INVALID;
+    }
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    G19_CUDA(ctx, cudaIpcGetMemHandle(&f->handle, f->base));
+    FrameBlob b;
+    std::memset(&b, 0, sizeof b);
+    b.magic = kFrameMagic;
+    b.w = f->w;
+    b.h = f->h;
+    b.bytes = f->bytes;
+    b.handle = f->handle;
+    std::memset(blob, 0, blob_bytes);
+    std::memcpy(blob, &b, sizeof b);
+    return G19_OK;
+}
+
+int g19_frame_import(g19_ctx* ctx, const void* blob, size_t blob_bytes, g19_frame** out) {
+    if (!ctx || !blob || !out || blob_bytes < sizeof(FrameBlob)) return G19_ERR_INVALID;
+    *out = nullptr;
+    FrameBlob b;
+    std::memcpy(&b, blob, sizeof b);
+    if (b.magic != kFrameMagic) {
+        ctx->err = "g19_frame_import: not a frame blob";
+        return G19_ERR_INVALID;
+    }
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    g19_frame* f = new (std::nothrow) g19_frame();
+    if (!f) return G19_ERR_INVALID;
+    f->device = ctx->device;
+    f->owner = false;
+    f->w = b.w;
+    f->h = b.h;
+    cudaError_t e = cudaIpcOpenMemHandle(&f->base, b.handle, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("g19_frame_import: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e) +
+                   " (peer access over NVLink between the two devices is required)";
+        delete f;
+        return G19_ERR_CUDA;
+    }
+    frame_layout(f);
+    if (f->bytes != b.bytes) {
+        ctx->err = "g19_frame_import: layout mismatch";
+        cudaIpcCloseMemHandle(f->base);
+        delete f;
+        return G19_ERR_INVALID;
+    }
+    *out = f;
+    return G19_OK;
+}
+
+void g19_frame_destroy(g19_frame* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    cudaDeviceSynchronize();
+    if (f->base) {
+        if (f->owner) cudaFree(f->base);
+        else cudaIpcCloseMemHandle(f->base);
+    }
+    delete f;
+}
+
+int g19_frame_pointers(g19_frame* f, uint8_t** d_rgb, float** d_rad) {
+    if (!f) return G19_ERR_INVALID;
+    if (d_rgb) *d_rgb = f->rgb;
+    if (d_rad) *d_rad = f->rad;
+    return G19_OK;
+}
+
+int g19_render_to_frame(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p, g19_frame* f,
+                        void* stream) {
+    if (!ctx || !f || !p) return G19_ERR_INVALID;
+    if (p->width != f->w || p->height != f->h) {
+        ctx->err = "g19_render_to_frame: params do not match the frame size";
+        return G19_ERR_INVALID;
+    }
+    ++f->epoch;
+    int rc = render_any(ctx, cam, light, p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream, f);
+    if (rc != G19_OK && rc != G19_ERR_CANCELLED) --f->epoch;
+    return rc;
+}
+
+int g19_frame_wait(g19_ctx* ctx, g19_frame* f, int world, void* stream) {
+    if (!ctx || !f || !f->owner || world < 1) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    launch_frame_wait(f->flags, f->epoch * unsigned(world), static_cast<cudaStream_t>(stream));
+    G19_CUDA(ctx, cudaGetLastError());
+    return G19_OK;
+}
+
+int g19_frame_release(g19_ctx* ctx, g19_frame* f, void* stream) {
+    if (!ctx || !f || !f->owner) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    launch_frame_release(f->flags, f->epoch, static_cast<cudaStream_t>(stream));
+    G19_CUDA(ctx, cudaGetLastError());
+    return G19_OK;
+}
+
+int g19_frame_read(g19_ctx* ctx, g19_frame* f, uint8_t* rgb_out, float* rad_out, void* stream) {
+    if (!ctx || !f || !f->owner) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    size_t npx = size_t(f->w) * size_t(f->h);
+    if (rgb_out && npx) G19_CUDA(ctx, cudaMemcpyAsync(rgb_out, f->rgb, npx * 3, cudaMemcpyDefault, s));
+    if (rad_out && npx) G19_CUDA(ctx, cudaMemcpyAsync(rad_out, f->rad, npx * 12, cudaMemcpyDefault, s));
+    return G19_OK;
+}
+
+int g19_frame_timeouts(g19_ctx* ctx, g19_frame* f, unsigned* out) {
+    if (!ctx || !f || !out) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    G19_CUDA(ctx, cudaMemcpy(out, f->flags + 64, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return G19_OK;
 }
 
 int g19_get_stats(g19_ctx* ctx, g19_stats* out) {

@@ -78,4 +78,13 @@ void launch_probe_shade(const RefSceneD& scene, int32_t entity, int textured, co
 void launch_untile(const TileMap& map, const uint8_t* rgb_local, const int32_t* ids_local, const float* rad_local,
                    uint8_t* rgb_frame, int32_t* ids_frame, float* rad_frame, cudaStream_t stream);
 
+
+// ---- frame_kernels.cu: resolve fused with the multi-GPU framebuffer gather ----------------
+void launch_resolve_to_frame(const TileMap& map, const float* accum, int spp, uint8_t* rgb_frame, float* rad_frame,
+                             cudaStream_t stream);
+void launch_frame_signal(unsigned* flags, cudaStream_t stream);                  // arrived += 1 (system scope)
+void launch_frame_wait(unsigned* flags, unsigned target, cudaStream_t stream);   // owner: until arrived >= target
+void launch_frame_release(unsigned* flags, unsigned epoch, cudaStream_t stream); // owner: consumed = epoch
+void launch_frame_acquire(unsigned* flags, unsigned need, cudaStream_t stream);  // writer: until consumed >= need
+
 } // namespace g19

@@ -564,14 +564,24 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     }
     const int done_spp = int(stats.samples);
     clk.begin();
-    launch_resolve(a.map, pa.accum, done_spp > 0 ? done_spp : 1, static_cast<float*>(w.rad_l.p),
-                   static_cast<uint8_t*>(w.rgb_l.p), s);
-    const bool to_frame = a.d_rgb || a.d_rad;
-    if (to_frame)
-        launch_untile(a.map, a.d_rgb ? static_cast<uint8_t*>(w.rgb_l.p) : nullptr, nullptr,
-                      a.d_rad ? static_cast<float*>(w.rad_l.p) : nullptr, a.d_rgb, nullptr, a.d_rad, s);
-    clk.end(G19_K_OTHER);
-    stats.class_launches[G19_K_OTHER] += to_frame ? 2 : 1;
+    if (a.frame_flags) {
+        // fused resolve + untile + gather: wait until the owner is done with the previous frame,
+        // store this rank's pixels into the shared frame, then signal arrival
+        launch_frame_acquire(a.frame_flags, a.frame_need_consumed, s);
+        launch_resolve_to_frame(a.map, pa.accum, done_spp > 0 ? done_spp : 1, a.frame_rgb, a.frame_rad, s);
+        launch_frame_signal(a.frame_flags, s);
+        clk.end(G19_K_OTHER);
+        stats.class_launches[G19_K_OTHER] += 3;
+    } else {
+        launch_resolve(a.map, pa.accum, done_spp > 0 ? done_spp : 1, static_cast<float*>(w.rad_l.p),
+                       static_cast<uint8_t*>(w.rgb_l.p), s);
+        const bool to_frame = a.d_rgb || a.d_rad;
+        if (to_frame)
+            launch_untile(a.map, a.d_rgb ? static_cast<uint8_t*>(w.rgb_l.p) : nullptr, nullptr,
+                          a.d_rad ? static_cast<float*>(w.rad_l.p) : nullptr, a.d_rgb, nullptr, a.d_rad, s);
+        clk.end(G19_K_OTHER);
+        stats.class_launches[G19_K_OTHER] += to_frame ? 2 : 1;
+    }
     if (a.t_rad) PATH_CUDA(cudaMemcpyAsync(a.t_rad, w.rad_l.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (a.t_rgb) PATH_CUDA(cudaMemcpyAsync(a.t_rgb, w.rgb_l.p, npix * 3, cudaMemcpyDeviceToDevice, s));
     if (const char* le = path_launch_error()) {

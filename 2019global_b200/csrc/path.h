@@ -93,6 +93,11 @@ struct PathRenderArgs {
     int32_t* d_ids;
     uint8_t* t_rgb;   // compact local-pixel outputs (nullable)
     float* t_rad;
+    // shared frame (possibly a peer mapping of rank 0's memory): resolve stores straight into it
+    uint8_t* frame_rgb = nullptr;
+    float* frame_rad = nullptr;
+    unsigned* frame_flags = nullptr;
+    unsigned frame_need_consumed = 0;
     cudaStream_t stream;
     int sm_count;
     std::atomic<int>* cancel;

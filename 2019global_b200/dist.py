@@ -32,3 +32,22 @@ def gather_frame(local, w, h, channels, frame, untile, group=None):
 def padded_len(w, h, world):
     """Compact-array length every rank pads to (rank 0 owns the most tiles)."""
     return tiles.n_local_tiles(w, h, 0, world) * tiles.TILE_PIX
+
+
+def shared_frame(rt, w, h, group=None):
+    """One SharedFrame per job: rank 0 allocates it, the CUDA IPC blob travels by broadcast, every
+    other rank maps it. After this the data path needs no collective: each rank's resolve kernel
+    stores its pixels into rank 0's HBM over NVLink (engine.SharedFrame)."""
+    from .engine import SharedFrame
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if rank == 0:
+        f = SharedFrame.create(rt, w, h)
+        box = [f.blob()]
+    else:
+        f, box = None, [None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0, group=group)
+        if rank != 0:
+            f = SharedFrame.attach(rt, box[0], w, h)
+    return f

@@ -29,6 +29,9 @@ EXPORTS = [
     "g19_scene_get_entity", "g19_scene_entity_bbox", "g19_scene_entity_triangles", "g19_scene_builtin",
     "g19_create", "g19_destroy", "g19_last_error", "g19_upload_scene", "g19_render", "g19_render_device",
     "g19_get_stats", "g19_cancel", "g19_progress", "g19_probe_intersect", "g19_probe_candidates",
+    "g19_frame_create", "g19_frame_export", "g19_frame_import", "g19_frame_destroy", "g19_frame_pointers",
+    "g19_render_to_frame", "g19_frame_wait", "g19_frame_release", "g19_frame_timeouts",
+    "g19_frame_read",
 ]
 
 
@@ -72,6 +75,18 @@ def lib():
                                           C.c_void_p, C.c_void_p]
         L.g19_probe_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.POINTER(C.c_int)]
+        L.g19_frame_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.g19_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.g19_frame_import.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.g19_frame_destroy.restype = None
+        L.g19_frame_destroy.argtypes = [C.c_void_p]
+        L.g19_frame_pointers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.g19_render_to_frame.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_void_p, C.POINTER(abi.Params),
+                                          C.c_void_p, C.c_void_p]
+        L.g19_frame_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.g19_frame_release.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g19_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g19_frame_timeouts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint)]
         _lib = L
     return _lib
 
@@ -299,3 +314,67 @@ def _untile(self, w, h, rank, world, t_rgb=0, t_ids=0, t_rad=0, d_rgb=0, d_ids=0
 
 RayTracer.render_tiles = _render_tiles
 RayTracer.untile = _untile
+
+
+FRAME_BLOB_BYTES = 128
+
+
+class SharedFrame:
+    """A frame in the owner's HBM that every rank's resolve kernel stores into directly
+    (include/g19.h "shared frame"): SharedFrame.create on rank 0, .blob() shipped to the other
+    ranks by any transport, SharedFrame.attach there."""
+
+    def __init__(self, rt, handle, w, h, owner):
+        self.rt, self.h_, self.w, self.h, self.owner = rt, handle, w, h, owner
+
+    @classmethod
+    def create(cls, rt, w, h):
+        hd = C.c_void_p()
+        rt._check(rt._L.g19_frame_create(rt.h, w, h, C.byref(hd)))
+        return cls(rt, hd, w, h, True)
+
+    @classmethod
+    def attach(cls, rt, blob, w, h):
+        hd = C.c_void_p()
+        buf = C.create_string_buffer(bytes(blob), FRAME_BLOB_BYTES)
+        rt._check(rt._L.g19_frame_import(rt.h, buf, FRAME_BLOB_BYTES, C.byref(hd)))
+        return cls(rt, hd, w, h, False)
+
+    def blob(self):
+        buf = C.create_string_buffer(FRAME_BLOB_BYTES)
+        self.rt._check(self.rt._L.g19_frame_export(self.rt.h, self.h_, buf, FRAME_BLOB_BYTES))
+        return bytes(buf.raw)
+
+    def pointers(self):
+        """(rgb888, radiance) device pointers on the owner."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self.rt._check(self.rt._L.g19_frame_pointers(self.h_, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def render(self, p, stream=0):
+        """Every rank: render my tiles straight into the frame (asynchronous)."""
+        rt = self.rt
+        return rt._check(rt._L.g19_render_to_frame(rt.h, C.byref(rt.camera), abi.d3(rt.light), C.byref(p), self.h_,
+                                                   C.c_void_p(stream)), allow=(abi.ERR_CANCELLED,))
+
+    def wait(self, world, stream=0):
+        """Owner: everything enqueued on `stream` after this sees the complete frame."""
+        self.rt._check(self.rt._L.g19_frame_wait(self.rt.h, self.h_, world, C.c_void_p(stream)))
+
+    def read(self, rgb=0, rad=0, stream=0):
+        """Owner: enqueue copies of the frame to host (pinned) or device addresses (ints)."""
+        self.rt._check(self.rt._L.g19_frame_read(self.rt.h, self.h_, C.c_void_p(rgb), C.c_void_p(rad), C.c_void_p(stream)))
+
+    def release(self, stream=0):
+        """Owner: done reading; the ranks may overwrite the frame with the next one."""
+        self.rt._check(self.rt._L.g19_frame_release(self.rt.h, self.h_, C.c_void_p(stream)))
+
+    def timeouts(self):
+        v = C.c_uint(0)
+        self.rt._check(self.rt._L.g19_frame_timeouts(self.rt.h, self.h_, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h_ is not None:
+            self.rt._L.g19_frame_destroy(self.h_)
+            self.h_ = None

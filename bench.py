@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp-per-pass", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="frame", choices=["frame", "nccl"],
+                    help="frame: every rank's resolve kernel stores its pixels straight into rank 0's frame over "
+                         "NVLink (fused gather, no collective); nccl: compact tile arrays + torch.distributed.gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -217,9 +220,23 @@ def main():
         rt.untile(W, H, r, world, t_rad=buf.data_ptr(), t_rgb=buf.data_ptr() + rad_bytes, d_rad=f_rad.data_ptr(),
                   d_rgb=f_rgb.data_ptr(), stream=stream)
 
-    def step(profile=0):
+    shared = g19dist.shared_frame(rt, W, H) if args.gather == "frame" else None
+
+    def step(profile=0, read_host=False):
+        if shared is not None:
+            # fused: resolve stores into rank 0's frame (peer mapping), then a system-scope signal;
+            # rank 0 enqueues a wait -- no collective, no staging copy, no host round trip
+            shared.render(params(profile), stream=stream)
+            if rank == 0:
+                shared.wait(world, stream=stream)
+                if read_host:
+                    shared.read(rgb=host_rgb.data_ptr(), stream=stream)
+                shared.release(stream=stream)
+            return
         rt.render_tiles(params(profile), t_rad=payload.data_ptr(), t_rgb=payload.data_ptr() + rad_bytes, stream=stream)
         g19dist.gather_frame(payload, W, H, 3, f_rgb, untile_both)
+        if read_host and rank == 0:
+            host_rgb.copy_(f_rgb, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -257,8 +274,9 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.stop()
     st = rt.stats()
-    # this library's kernels inside the timed region: every rank's render + rank 0's untile per payload
-    launches = (sum_over_ranks(float(st.kernel_launches)) + world) * args.steps
+    # this library's kernels inside the timed region: every rank's render + rank 0's wait/release
+    # (frame) or its untile per payload (nccl)
+    launches = (sum_over_ranks(float(st.kernel_launches)) + (2 if shared is not None else world)) * args.steps
     value = SAMPLES_PER_STEP / (ms * 1e-3) / 1e6
 
     # ---- per-kernel-class CUDA-event times (same steps, event brackets on) --------------------
@@ -335,9 +353,7 @@ def main():
                    spp_per_pass=args.spp_per_pass)
     else:
         def e2e_step():
-            step()
-            if rank == 0:
-                host_rgb.copy_(f_rgb, non_blocking=True)
+            step(read_host=True)
             torch.cuda.synchronize()
     e2e_step()
     barrier()
@@ -348,7 +364,10 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     e2e = {"value": SAMPLES_PER_STEP / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": W * H * 3,
-           "api": "g19_render (host RGB888 out)" if world == 1 else "g19_render_tiles_device + NCCL gather + D2H on rank 0"}
+           "api": "g19_render (host RGB888 out)" if world == 1 else (
+               "g19_render_to_frame on every rank (peer stores into rank 0's frame over NVLink) + g19_frame_wait + "
+               "g19_frame_read into pinned host memory on rank 0" if shared is not None else
+               "g19_render_tiles_device + NCCL gather + D2H on rank 0")}
 
     if rank == 0:
         cpu = None
@@ -363,12 +382,21 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp": SPP, "max_depth": DEPTH, "seed": SEED,
                        "mode": "PATH", "tiles": "32x32 interleaved, rank = tile % world",
+                       "gather": ("shared frame: resolve kernels store into rank 0's HBM over NVLink, no collective"
+                                  if shared is not None else "nccl gather of compact tile arrays"),
                        "l2": "per-step wavefront state streams (%.1f GB algorithmic) far exceed the 126 MB L2; "
                              "no flush needed" % (world * total_bytes / args.steps / 1e9),
                        "frame_time_1080p_64spp_ms": ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
+    if shared is not None:
+        torch.cuda.synchronize()
+        if rank == 0 and shared.timeouts():
+            sys.stderr.write("bench.py: %d device-side frame spins timed out\n" % shared.timeouts())
+        if world > 1:
+            dist.barrier()
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -225,6 +225,37 @@ int g19_untile_device(g19_ctx* ctx, int width, int height, int rank, int world,
                       const uint8_t* d_tile_rgb, const int32_t* d_tile_ids, const float* d_tile_rad,
                       uint8_t* d_rgb888, int32_t* d_hit_id, float* d_radiance, void* stream);
 
+/* Shared frame: the same exchange WITHOUT a collective call or a staging copy. Rank 0 owns a
+ * frame in its HBM; the other ranks map it (CUDA IPC, reached over NVLink / NVSwitch) and their
+ * resolve kernel stores each finished pixel straight into place (RGB888 + float radiance), then
+ * signals a system-scope counter in the owner's memory. No counterpart in the reference (one
+ * process, one thread); the frame plays the role of RayTracer::_image (raytracer.h:25,93).
+ *   g19_frame_create    owner (rank 0) allocates                 -> Image(w,h), image.h:9
+ *   g19_frame_export    fills a G19_FRAME_BLOB_BYTES blob to ship to the other ranks (any transport)
+ *   g19_frame_import    another rank maps the owner's frame
+ *   g19_render_to_frame every rank, same (camera, params) except params->rank: render my tiles into
+ *                       the frame; asynchronous on `stream`; frames must be rendered in lockstep
+ *   g19_frame_wait      owner: enqueue a wait on `stream` until all `world` ranks have delivered the
+ *                       frame last passed to g19_render_to_frame; work enqueued behind it sees it whole
+ *   g19_frame_release   owner: enqueue "done reading this frame"; the other ranks' next resolve waits
+ *                       for it (device side, never the host) before overwriting pixels
+ *   g19_frame_read      owner: enqueue copies of the frame into host (pinned) or device buffers
+ *   g19_frame_pointers  owner's device pointers (row-major, row 0 = top)
+ *   g19_frame_timeouts  device-side spins that gave up after 5 s (a lost rank); 0 in a healthy run */
+typedef struct g19_frame g19_frame;
+#define G19_FRAME_BLOB_BYTES 128
+int g19_frame_create(g19_ctx* ctx, int width, int height, g19_frame** out);
+int g19_frame_export(g19_ctx* ctx, g19_frame* frame, void* blob, size_t blob_bytes);
+int g19_frame_import(g19_ctx* ctx, const void* blob, size_t blob_bytes, g19_frame** out);
+void g19_frame_destroy(g19_frame* frame);
+int g19_frame_pointers(g19_frame* frame, uint8_t** d_rgb888, float** d_radiance);
+int g19_render_to_frame(g19_ctx* ctx, const g19_camera* camera, const double light[3],
+                        const g19_params* params, g19_frame* frame, void* stream);
+int g19_frame_wait(g19_ctx* ctx, g19_frame* frame, int world, void* stream);
+int g19_frame_release(g19_ctx* ctx, g19_frame* frame, void* stream);
+int g19_frame_read(g19_ctx* ctx, g19_frame* frame, uint8_t* rgb888_out, float* radiance_out, void* stream);
+int g19_frame_timeouts(g19_ctx* ctx, g19_frame* frame, unsigned* out);
+
 /* RayTracer::stop()/running()                              raytracer.h:89-91 */
 int g19_cancel(g19_ctx* ctx);
 /* Fraction of the current render already enqueued+finished, 0..1.            */
