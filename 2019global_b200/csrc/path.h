@@ -37,8 +37,8 @@ enum { Q_DIFFUSE = 1, Q_MIRROR = 2, Q_GLASS = 3 }; // = g19_bsdf + 1; column of 
 
 struct PathSceneD {
     const PathNodeD* nodes;
-    const PrimHot* hot_leaf; // hot records in leaf order (n_index of them), id in q[15]
-    const PrimHot* hot;      // hot records by primitive id (shading: sphere centres)
+    const uint32_t* index;   // leaf lists: n_index primitive ids (a primitive appears in every leaf it overlaps)
+    const PrimHot* hot;      // 64-byte intersection records by primitive id
     const PrimCold* cold;
     const MaterialD* materials;
     const LightD* lights;

@@ -89,7 +89,7 @@ __device__ __forceinline__ float3 normalize(float3 v) { return v * rsqrtf(dot(v,
 
 // ---- shared-memory scene prefix ----------------------------------------------
 // Dynamic shared memory, sized on the host to what the scene needs (PassArgs::stage_*):
-//   [nodes: stage_nodes x 8 B][leaf-ordered hot prims: stage_prims x 64 B]
+//   [nodes: stage_nodes x 8 B][hot primitive records: stage_prims x 64 B (flat scenes only)]
 //   [cold records: stage_cold x 32 B][lights: stage_lights x 80 B]   (flat scenes only)
 //   [traversal stack: stack_levels x kThreads x 4 B][mbarrier: 8 B]
 // A Cornell box stages whole (about 0.8 KB) and leaves the SM free for more CTAs.
@@ -102,19 +102,10 @@ template <bool ALL> struct SceneAccess {
     const float4* cold_s;
     const float4* lights_s;
     uint32_t* stack;
-    int n_nodes_s, n_prims_s;
+    int n_nodes_s;
     __device__ __forceinline__ uint2 node(uint32_t i) const {
         if (ALL || i < (uint32_t)n_nodes_s) return nodes_s[i];
         return __ldg(reinterpret_cast<const uint2*>(g->nodes) + i);
-    }
-    // k-th record of the leaf-ordered array; row 3 = (material, bsdf, kind, primitive id)
-    __device__ __forceinline__ void prim(uint32_t k, float4& a, float4& b, float4& c, float4& t) const {
-        if (ALL || k < (uint32_t)n_prims_s) {
-            a = hot_s[4 * k]; b = hot_s[4 * k + 1]; c = hot_s[4 * k + 2]; t = hot_s[4 * k + 3];
-        } else {
-            const float4* p = reinterpret_cast<const float4*>(g->hot_leaf) + 4 * (size_t)k;
-            a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); t = __ldg(p + 3);
-        }
     }
     // shading record of primitive id `prim`: (normal, ior), (albedo, material)
     __device__ __forceinline__ void cold(uint32_t prim, float4& c0, float4& c1) const {
@@ -145,7 +136,6 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     SceneAccess<ALL> acc;
     acc.g = &a.scene;
     acc.n_nodes_s = a.stage_nodes;
-    acc.n_prims_s = a.stage_prims;
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
     const uint32_t pb = uint32_t(a.stage_prims) * 64u;
@@ -175,7 +165,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
         if (pb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(base + nb)),
-                         "l"(g.hot_leaf), "r"(pb), "r"(bar)
+                         "l"(g.hot), "r"(pb), "r"(bar)
                          : "memory");
         if (cb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -295,17 +285,30 @@ __device__ __forceinline__ void trace_flat(const SceneAccess<true>& S, float3 o,
     occluded = DUAL && tmax0 > 0.0f && lim0 == 0u;
 }
 
-// Cell edge: the SAME expression as cell_edge() in path.cu (no FMA contraction).
-__device__ __forceinline__ float cell_edge(float root_lo, float size_at_level, uint32_t i) {
-    return __fadd_rn(root_lo, __fmul_rn(float(i), size_at_level));
-}
-
-// Ordered traversal of the linear octree. Children are visited in the order
-// i = 0..7 -> octant i ^ a (a = sign mask of the direction): an octant can only
-// be occluded by octants that precede it in this order, so the first leaf hit
-// bounds everything behind it. Per level the kernel keeps the child base index
-// on a short stack in shared memory (one column per thread, conflict free), a
-// 4-bit child counter packed in a register, and the integer cell coordinates.
+// Ordered traversal of the linear octree (tree scenes). Parametric front-to-back walk (after
+// Revelles et al. 2000): in the frame where the ray direction is positive on every axis (octant
+// bits XOR a), a cell is described per axis by the ray parameters of its entry plane t0, mid
+// plane tm and exit plane t1. The first child is the one whose mid planes lie before the entry
+// point; the next child is reached through the exit plane with the smallest parameter. Only the
+// (at most four) children the ray pierces are visited, strictly in order, so the walk stops at
+// the first leaf whose hit lies inside its own cell.
+//
+// Per level the state is one 4-bit child code in a 64-bit register, the child base index on a
+// short stack in shared memory (one column per thread, conflict free) and the integer cell
+// coordinates. Plane parameters are linear in the plane index, t(i) = A + i * (B * 2^-(level+1))
+// with A = (root_lo - o) / d and B = root_size / d per axis, evaluated with one FMA each: the
+// planes a child shares with its parent get bit-identical parameters (same exact product), so
+// the walk is consistent from level to level.
+//
+// What the ncu capture of the 1M-triangle heightfield drove (profiles/r01b_heightfield_*):
+//   * 4.4 of 32 threads active per instruction: the one-big-loop form serialised "step",
+//     "descend", "test leaf" and "pop" branches -> WHILE-WHILE form: every lane first walks to
+//     its next non-empty leaf (lanes that found one wait at the reconvergence point), then all
+//     lanes test their leaves together
+//   * 443 MB of leaf-ordered primitive copies (6.9 references per primitive) streamed from DRAM
+//     -> leaves hold 4-byte indices into the 64-byte records: nodes + indices + records = 108 MB,
+//     L2-resident on B200 (126 MB)
+//   * 51 instructions per plane update -> 21 with the linear form
 // `any` = stop at the first hit (shadow rays).
 template <bool ALL>
 __device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tmax, bool any, float& t_hit,
@@ -314,116 +317,121 @@ __device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tm
     uint32_t* const stack = S.stack;
     float best = tmax;
     uint32_t best_prim = kInvalid;
-    const float tmin = 0.0f;
+    const uint32_t* __restrict__ index = g.index;
+    const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
 
-    auto leaf = [&](uint32_t first, uint32_t n) -> bool {
-        uint32_t k = 0;
-        for (; k + 2 <= n; k += 2) { // two primitives per step: independent FMA chains, loads up front
-            float4 a0, b0, c0, g0, a1, b1, c1, g1;
-            S.prim(first + k, a0, b0, c0, g0);
-            S.prim(first + k + 1, a1, b1, c1, g1);
-            float t0 = hit_prim(a0, b0, c0, g0, o, d, best);
-            float t1 = hit_prim(a1, b1, c1, g1, o, d, best);
-            if (t0 >= 0.0f) { best = t0; best_prim = __float_as_uint(g0.w); }
-            if (t1 >= 0.0f && t1 < best) { best = t1; best_prim = __float_as_uint(g1.w); }
-            if (any && best_prim != kInvalid) return true;
+    auto leaf = [&](uint32_t first, uint32_t n) {
+        // two primitives per step: independent FMA chains, all loads of the step issued up front
+        uint32_t id0 = __ldg(index + first), id1 = n > 1 ? __ldg(index + first + 1) : id0;
+        for (uint32_t k = 0; k < n; k += 2) {
+            const float4* p0 = hot + 4 * (size_t)id0;
+            const float4* p1 = hot + 4 * (size_t)id1;
+            const float4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), c0 = __ldg(p0 + 2), g0 = __ldg(p0 + 3);
+            const float4 a1 = __ldg(p1), b1 = __ldg(p1 + 1), c1 = __ldg(p1 + 2), g1 = __ldg(p1 + 3);
+            const uint32_t cur0 = id0, cur1 = id1;
+            const bool second = k + 1 < n;
+            if (k + 2 < n) id0 = __ldg(index + first + k + 2); // next step's indices while this one computes
+            if (k + 3 < n) id1 = __ldg(index + first + k + 3);
+            else id1 = id0;
+            const float t0 = hit_prim(a0, b0, c0, g0, o, d, best);
+            if (t0 >= 0.0f) { best = t0; best_prim = cur0; }
+            const float t1 = second ? hit_prim(a1, b1, c1, g1, o, d, best) : -1.0f;
+            if (t1 >= 0.0f) { best = t1; best_prim = cur1; }
+            if (any && best_prim != kInvalid) break;
         }
-        if (k < n) {
-            float4 a0, b0, c0, g0;
-            S.prim(first + k, a0, b0, c0, g0);
-            float t0 = hit_prim(a0, b0, c0, g0, o, d, best);
-            if (t0 >= 0.0f) { best = t0; best_prim = __float_as_uint(g0.w); }
-            if (any && best_prim != kInvalid) return true;
-        }
-        return false;
     };
 
     const uint2 root = S.node(0);
-    if (root.y & kLeafBit) {
+    if (root.y & kLeafBit) { // the whole scene is one leaf (but not staged as a flat scene)
         leaf(root.x, root.y & ~kLeafBit);
         t_hit = best;
         prim_hit = best_prim;
         return best_prim != kInvalid;
     }
 
-    // Parametric front-to-back walk (after Revelles et al. 2000). In the frame where the ray
-    // direction is positive on every axis (octant bits XOR a), a cell is described per axis by
-    // the ray parameters of its entry plane t0, mid plane tm and exit plane t1. The first child
-    // is the one whose mid planes lie before the entry point; the next child is reached through
-    // the exit plane with the smallest parameter. Only the (at most four) children the ray
-    // pierces are visited, strictly in order, so the walk stops at the first leaf whose hit lies
-    // inside its own cell. Per level the state is one 4-bit child code; the planes are recomputed
-    // from the integer cell coordinates with the builder's own cell_edge expression.
     float3 dd = d;
     if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
     if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
     if (fabsf(dd.z) < 1.0e-20f) dd.z = copysignf(1.0e-20f, dd.z);
     const float3 inv = f3(__fdividef(1.0f, dd.x), __fdividef(1.0f, dd.y), __fdividef(1.0f, dd.z));
     const uint32_t a = (dd.x < 0.0f ? 1u : 0u) | (dd.y < 0.0f ? 2u : 0u) | (dd.z < 0.0f ? 4u : 0u);
+    const float3 A = f3((g.root_lo[0] - o.x) * inv.x, (g.root_lo[1] - o.y) * inv.y, (g.root_lo[2] - o.z) * inv.z);
+    const float3 B = f3(g.root_size[0] * inv.x, g.root_size[1] * inv.y, g.root_size[2] * inv.z);
     int level = 0;
     uint32_t ix = 0, iy = 0, iz = 0;
     float t0x, t0y, t0z, tmx, tmy, tmz, t1x, t1y, t1z;
     auto planes = [&]() { // entry / mid / exit parameters of the cell (level; ix,iy,iz)
         const float s1 = __int_as_float((127 - (level + 1)) << 23); // 2^-(level+1), exact
-        const float hx = g.root_size[0] * s1, hy = g.root_size[1] * s1, hz = g.root_size[2] * s1;
-        float ax = (cell_edge(g.root_lo[0], hx, 2u * ix) - o.x) * inv.x, bx = (cell_edge(g.root_lo[0], hx, 2u * ix + 2u) - o.x) * inv.x;
-        float ay = (cell_edge(g.root_lo[1], hy, 2u * iy) - o.y) * inv.y, by = (cell_edge(g.root_lo[1], hy, 2u * iy + 2u) - o.y) * inv.y;
-        float az = (cell_edge(g.root_lo[2], hz, 2u * iz) - o.z) * inv.z, bz = (cell_edge(g.root_lo[2], hz, 2u * iz + 2u) - o.z) * inv.z;
+        const float hx = B.x * s1, hy = B.y * s1, hz = B.z * s1;
+        const float fx = float(2u * ix), fy = float(2u * iy), fz = float(2u * iz);
+        const float ax = fmaf(fx, hx, A.x), bx = fmaf(fx + 2.0f, hx, A.x);
+        const float ay = fmaf(fy, hy, A.y), by = fmaf(fy + 2.0f, hy, A.y);
+        const float az = fmaf(fz, hz, A.z), bz = fmaf(fz + 2.0f, hz, A.z);
         t0x = fminf(ax, bx); t1x = fmaxf(ax, bx);
         t0y = fminf(ay, by); t1y = fmaxf(ay, by);
         t0z = fminf(az, bz); t1z = fmaxf(az, bz);
-        tmx = (cell_edge(g.root_lo[0], hx, 2u * ix + 1u) - o.x) * inv.x;
-        tmy = (cell_edge(g.root_lo[1], hy, 2u * iy + 1u) - o.y) * inv.y;
-        tmz = (cell_edge(g.root_lo[2], hz, 2u * iz + 1u) - o.z) * inv.z;
+        tmx = fmaf(fx + 1.0f, hx, A.x);
+        tmy = fmaf(fy + 1.0f, hy, A.y);
+        tmz = fmaf(fz + 1.0f, hz, A.z);
     };
     planes();
+    bool done = false;
     {
         const float tn = fmaxf(fmaxf(t0x, t0y), t0z), tf = fminf(fminf(t1x, t1y), t1z);
-        if (tn > fminf(tf, best) + 1.0e-5f || tf < tmin) {
-            t_hit = best;
-            prim_hit = kInvalid;
-            return false;
-        }
+        if (tn > fminf(tf, best) + 1.0e-5f || tf < 0.0f) done = true;
     }
     unsigned long long codes = 0xFull; // 4 bits per level: 0xF = not started, else current child (mirrored)
     stack[0] = root.x;
-    while (true) {
-        uint32_t cur = uint32_t(codes >> (4 * level)) & 0xFu;
-        bool leave = false;
-        if (cur == 0xFu) {
-            const float te = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), tmin);
-            cur = (tmx < te ? 1u : 0u) | (tmy < te ? 2u : 0u) | (tmz < te ? 4u : 0u);
-        } else {
-            const float ex = (cur & 1u) ? t1x : tmx, ey = (cur & 2u) ? t1y : tmy, ez = (cur & 4u) ? t1z : tmz;
-            const uint32_t bit = (ex <= ey && ex <= ez) ? 1u : (ey <= ez ? 2u : 4u);
-            leave = (cur & bit) != 0u;
-            cur |= bit;
-        }
-        if (!leave) {
+    uint32_t leaf_first = 0, leaf_n = 0;
+    float leaf_exit = 0.0f;
+    while (!done) {
+        // ---- walk: until this lane stands in a non-empty leaf or has left the tree ----
+        while (!done && leaf_n == 0u) {
+            uint32_t cur = uint32_t(codes >> (4 * level)) & 0xFu;
+            bool leave = false;
+            if (cur == 0xFu) {
+                const float te = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), 0.0f);
+                cur = (tmx < te ? 1u : 0u) | (tmy < te ? 2u : 0u) | (tmz < te ? 4u : 0u);
+            } else {
+                const float ex = (cur & 1u) ? t1x : tmx, ey = (cur & 2u) ? t1y : tmy, ez = (cur & 4u) ? t1z : tmz;
+                const uint32_t bit = (ex <= ey && ex <= ez) ? 1u : (ey <= ez ? 2u : 4u);
+                leave = (cur & bit) != 0u;
+                cur |= bit;
+            }
+            if (leave) { // the ray left this cell: back to the parent
+                if (level == 0) { done = true; break; }
+                --level;
+                ix >>= 1; iy >>= 1; iz >>= 1;
+                planes();
+                continue;
+            }
             const float cen = fmaxf(fmaxf((cur & 1u) ? tmx : t0x, (cur & 2u) ? tmy : t0y), (cur & 4u) ? tmz : t0z);
             const float cex = fminf(fminf((cur & 1u) ? t1x : tmx, (cur & 2u) ? t1y : tmy), (cur & 4u) ? t1z : tmz);
-            if (cen > best + fabsf(best) * 2.0e-6f + 1.0e-5f) break; // everything from here on is farther than the hit
+            if (cen > best + fabsf(best) * 2.0e-6f + 1.0e-5f) { done = true; break; } // everything from here on is farther
             codes = (codes & ~(0xFull << (4 * level))) | ((unsigned long long)cur << (4 * level));
-            if (cex < tmin) continue;
+            if (cex < 0.0f) continue;
             const uint32_t c = cur ^ a;
             const uint2 rec = S.node(stack[level * kThreads] + c);
             if (rec.y == kLeafBit) continue; // empty octant
             if (rec.y & kLeafBit) {
-                if (leaf(rec.x, rec.y & ~kLeafBit)) break;
-                if (best_prim != kInvalid && best <= cex) break; // the hit lies inside this cell: nothing nearer exists
-                continue;
+                leaf_first = rec.x;
+                leaf_n = rec.y & ~kLeafBit;
+                leaf_exit = cex;
+                continue; // ends the walk phase
             }
             ++level;
             stack[level * kThreads] = rec.x;
             ix = 2u * ix + (c & 1u); iy = 2u * iy + ((c >> 1) & 1u); iz = 2u * iz + ((c >> 2) & 1u);
             codes |= 0xFull << (4 * level);
             planes();
-            continue;
         }
-        if (level == 0) break;
-        --level;
-        ix >>= 1; iy >>= 1; iz >>= 1;
-        planes();
+        // ---- test: all lanes that stand in a leaf test its primitives together ----
+        if (leaf_n != 0u) {
+            leaf(leaf_first, leaf_n);
+            leaf_n = 0u;
+            // any hit ends a shadow ray; a hit inside its own cell cannot be beaten by a later cell
+            if (best_prim != kInvalid && (any || best <= leaf_exit)) done = true;
+        }
     }
     t_hit = best;
     prim_hit = best_prim;
@@ -561,7 +569,7 @@ __device__ __forceinline__ void store_vertex(const PassArgs& a, uint32_t slot, f
 }
 
 // ---- raygen + extend (camera segment) ------------------------------------------------
-template <bool ALL> __global__ void __launch_bounds__(kThreads, ALL ? 4 : 3) raygen_extend_kernel(const PassArgs a) {
+template <bool ALL> __global__ void __launch_bounds__(kThreads, ALL ? 4 : 2) raygen_extend_kernel(const PassArgs a) {
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
     const SceneAccess<ALL> S = stage_scene<ALL>(a);
@@ -648,7 +656,7 @@ __device__ __forceinline__ void prefetch_vertex(const PassArgs& a, uint32_t slot
 // KIND: Q_DIFFUSE / Q_MIRROR / Q_GLASS. FIRST: the vertex of the camera segment. LAST: the path's
 // final segment ended here -- next-event estimation only, no continuation.
 template <int KIND, bool FIRST, bool LAST, bool ALL>
-__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 3) : (ALL ? 3 : 2))
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 2) : (ALL ? 3 : 2))
     bounce_kernel(const PassArgs a, const int bounce) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
     constexpr bool kTp = !FIRST, kRad = !FIRST && kDiffuse;
