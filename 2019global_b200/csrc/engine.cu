@@ -48,7 +48,15 @@ struct DevBuf {
 
 } // namespace
 
+struct ProgressHook { // g19_render_progressive -> render_any
+    g19_pass_fn fn = nullptr;
+    void* user = nullptr;
+    uint8_t* h_rgb = nullptr;
+    int min_interval_ms = 0;
+};
+
 struct g19_ctx {
+    ProgressHook hook;
     int device = 0;
     cudaStream_t stream = nullptr; // used by the host-pointer entry points
     std::string err;
@@ -461,6 +469,12 @@ static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3]
         a.progress_milli = &ctx->progress_milli;
         a.cls0 = ctx->cls0;
         a.cls1 = ctx->cls1;
+        if (ctx->hook.fn) {
+            a.on_pass = ctx->hook.fn;
+            a.pass_user = ctx->hook.user;
+            a.h_rgb = ctx->hook.h_rgb;
+            a.min_interval_ms = ctx->hook.min_interval_ms;
+        }
         if (frame) {
             a.frame_rgb = frame->rgb;
             a.frame_rad = frame->rad;
@@ -475,7 +489,7 @@ static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3]
     if (rc != G19_OK && rc != G19_ERR_CANCELLED) return rc;
     G19_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     ctx->stats_pending = true;
-    ctx->progress_milli.store(1000);
+    if (rc == G19_OK) ctx->progress_milli.store(1000);
     return rc;
 }
 
@@ -673,6 +687,23 @@ int g19_frame_timeouts(g19_ctx* ctx, g19_frame* f, unsigned* out) {
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
     G19_CUDA(ctx, cudaMemcpy(out, f->flags + 64, sizeof(unsigned), cudaMemcpyDeviceToHost));
     return G19_OK;
+}
+
+int g19_render_progressive(g19_ctx* ctx, const g19_camera* cam, const double light[3], const g19_params* p,
+                           uint8_t* rgb, float* rad, g19_pass_fn on_pass, void* user, int min_interval_ms) {
+    if (!ctx || !rgb) return G19_ERR_INVALID;
+    ctx->hook.fn = on_pass;
+    ctx->hook.user = user;
+    ctx->hook.h_rgb = rgb;
+    ctx->hook.min_interval_ms = min_interval_ms < 0 ? 0 : min_interval_ms;
+    int rc = g19_render(ctx, cam, light, p, rgb, nullptr, rad);
+    ctx->hook = ProgressHook{};
+    if ((rc == G19_OK || rc == G19_ERR_CANCELLED) && on_pass) {
+        double done = 1.0;
+        if (rc == G19_ERR_CANCELLED) g19_progress(ctx, &done);
+        on_pass(user, rc == G19_OK ? 1.0 : done, rgb); // the final (or last complete) image
+    }
+    return rc;
 }
 
 int g19_get_stats(g19_ctx* ctx, g19_stats* out) {

@@ -16,6 +16,7 @@
 #include "path.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -526,6 +527,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa.stack_levels = b.view.tree_depth + 1;
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
+    auto last_refresh = std::chrono::steady_clock::now();
     for (int base = 0; base < p.spp; base += spp_pass) {
         if (a.cancel && a.cancel->load()) { // RayTracer::stop(): honoured between passes
             rc = G19_ERR_CANCELLED;
@@ -554,6 +556,22 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         stats.class_launches[G19_K_ACCUM] += 1;
         stats.samples += uint64_t(pa.spp_pass); // scaled by owned pixels below
         if (a.progress_milli) a.progress_milli->store(int(1000.0 * double(base + pa.spp_pass) / double(p.spp)));
+        if (a.on_pass && a.d_rgb && a.h_rgb && base + pa.spp_pass < p.spp) {
+            // progressive refresh: the host stays at most one pass ahead of the device (that is also
+            // the cancellation latency), and repaints no more often than the caller asked for
+            PATH_CUDA(cudaStreamSynchronize(s));
+            const auto now = std::chrono::steady_clock::now();
+            if (std::chrono::duration<double, std::milli>(now - last_refresh).count() >= double(a.min_interval_ms)) {
+                last_refresh = now;
+                const int so_far = base + pa.spp_pass;
+                launch_resolve(a.map, pa.accum, so_far, static_cast<float*>(w.rad_l.p), static_cast<uint8_t*>(w.rgb_l.p), s);
+                launch_untile(a.map, static_cast<uint8_t*>(w.rgb_l.p), nullptr, nullptr, a.d_rgb, nullptr, nullptr, s);
+                PATH_CUDA(cudaMemcpyAsync(a.h_rgb, a.d_rgb, size_t(a.map.w) * size_t(a.map.h) * 3, cudaMemcpyDeviceToHost, s));
+                PATH_CUDA(cudaStreamSynchronize(s));
+                stats.class_launches[G19_K_OTHER] += 2;
+                if (a.on_pass(a.pass_user, double(so_far) / double(p.spp), a.h_rgb) != 0) a.cancel->store(1);
+            }
+        }
     }
     const int done_spp = int(stats.samples);
     clk.begin();

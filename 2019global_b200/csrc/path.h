@@ -98,6 +98,11 @@ struct PathRenderArgs {
     float* frame_rad = nullptr;
     unsigned* frame_flags = nullptr;
     unsigned frame_need_consumed = 0;
+    // progressive refresh (g19_render_progressive): d_rgb is resolved and copied to h_rgb between passes
+    g19_pass_fn on_pass = nullptr;
+    void* pass_user = nullptr;
+    uint8_t* h_rgb = nullptr;
+    int min_interval_ms = 0;
     cudaStream_t stream;
     int sm_count;
     std::atomic<int>* cancel;

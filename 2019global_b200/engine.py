@@ -31,8 +31,12 @@ EXPORTS = [
     "g19_get_stats", "g19_cancel", "g19_progress", "g19_probe_intersect", "g19_probe_candidates",
     "g19_frame_create", "g19_frame_export", "g19_frame_import", "g19_frame_destroy", "g19_frame_pointers",
     "g19_render_to_frame", "g19_frame_wait", "g19_frame_release", "g19_frame_timeouts",
-    "g19_frame_read",
+    "g19_frame_read", "g19_render_progressive", "g19_render_tiles_device", "g19_untile_device", "g19_tile_pixels",
+    "g19_probe_texcoord", "g19_probe_shade", "g19_entity_bbox", "g19_entity_triangles",
 ]
+
+
+PASS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, C.POINTER(C.c_uint8))  # g19_pass_fn
 
 
 class G19Error(RuntimeError):
@@ -75,6 +79,8 @@ def lib():
                                           C.c_void_p, C.c_void_p]
         L.g19_probe_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.POINTER(C.c_int)]
+        L.g19_render_progressive.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_void_p, C.POINTER(abi.Params),
+                                             C.c_void_p, C.c_void_p, PASS_FN, C.c_void_p, C.c_int]
         L.g19_frame_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.g19_frame_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.g19_frame_import.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -256,6 +262,22 @@ class RayTracer:
         self._check(self._L.g19_render(self.h, C.byref(self.camera), abi.d3(self.light), C.byref(p), _ptr(rgb),
                                        _ptr(ids), _ptr(rad)), allow=(abi.ERR_CANCELLED,))
         return {"rgb": rgb, "ids": ids, "radiance": rad}
+
+    def run_progressive(self, w, h, on_pass, min_interval_ms=32, mode=abi.MODE_PATH, want_radiance=False, **kw):
+        """run() with the viewer's repaint hook (g19_render_progressive): on_pass(fraction, rgb) is called
+        with the samples-so-far image (a (h,w,3) uint8 view, valid during the call); return True to cancel."""
+        if not self._running:
+            return {"rgb": np.zeros((h, w, 3), np.uint8)}
+        p = self.params(w, h, mode, **kw)
+        rgb = np.zeros((h, w, 3), np.uint8)
+        rad = np.zeros((h, w, 3), np.float32) if want_radiance else None
+
+        def hook(_user, fraction, _px):
+            return 1 if on_pass(fraction, rgb) else 0
+        cb = PASS_FN(hook)
+        self._check(self._L.g19_render_progressive(self.h, C.byref(self.camera), abi.d3(self.light), C.byref(p), _ptr(rgb),
+                                                   _ptr(rad), cb, None, int(min_interval_ms)), allow=(abi.ERR_CANCELLED,))
+        return {"rgb": rgb, "radiance": rad}
 
     def run_device(self, p, d_rgb=0, d_ids=0, d_rad=0, stream=0):
         """Asynchronous render into device pointers (ints, e.g. torch.Tensor.data_ptr())."""

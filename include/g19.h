@@ -197,6 +197,18 @@ int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene);
 int g19_render(g19_ctx* ctx, const g19_camera* camera, const double light[3],
                const g19_params* params, uint8_t* rgb888_out, int32_t* hit_id_out,
                float* radiance_out);
+/* Progressive form of g19_render -- the reference's "incremental rendering" intent
+ * (raytracer.h:31): the Qt viewer repaints from getImage() every 32 ms while run() is in flight
+ * (viewer.h:18-21,36-43). After a wavefront pass, once at least min_interval_ms have gone by
+ * since the last refresh, the image of the samples so far is resolved into rgb888_out and
+ * on_pass(user, fraction, rgb888_out) is called on the calling thread; a non-zero return cancels
+ * like g19_cancel (latency: one pass). The last call has fraction 1.0 and the final image. REF
+ * mode is a single pass: one call. radiance_out (nullable) receives the final radiance only.   */
+typedef int (*g19_pass_fn)(void* user, double fraction, const uint8_t* rgb888);
+int g19_render_progressive(g19_ctx* ctx, const g19_camera* camera, const double light[3],
+                           const g19_params* params, uint8_t* rgb888_out, float* radiance_out,
+                           g19_pass_fn on_pass, void* user, int min_interval_ms);
+
 /* Same with DEVICE pointers (HBM-resident outputs) on `stream` (a
  * cudaStream_t, NULL = legacy default). Asynchronous w.r.t. the host unless
  * params->profile; stats (nullable) are complete after the stream is synced. */

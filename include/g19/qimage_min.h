@@ -3,8 +3,12 @@
 // when Qt is not installed (this container, the GPU box); with Qt present
 // image.h includes the real <QImage> and the Qt viewer paints it unchanged.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <string>
 #include <vector>
+
+#include "g19/image_io.h"
 
 typedef uint32_t QRgb;
 inline int qRed(QRgb c) { return (c >> 16) & 0xff; }
@@ -32,6 +36,10 @@ class QImage {
         return qRgb(p[0], p[1], p[2]);
     }
     void fill(Qt::GlobalColor) { std::fill(_px.begin(), _px.end(), uint8_t(0)); }
+    // QImage::save(fileName, format): "PNG" (what gui.h:41-44 asks for) or "PPM"; null = by extension
+    bool save(const std::string& file, const char* format = nullptr) const {
+        return g19::io::save_rgb888(file, format, _px.data(), _w, _h, size_t(_stride));
+    }
   private:
     int _w, _h, _stride;
     std::vector<uint8_t> _px;

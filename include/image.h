@@ -4,6 +4,7 @@
 // store; RayTracer::run fills whole scanlines from the engine's RGB888 output.
 #pragma once
 #include <cstring>
+#include <string>
 #include "g19/compat.h"
 
 struct Image {
@@ -30,6 +31,8 @@ struct Image {
         for (int y = 0; y < h; ++y) std::memcpy(_image.scanLine(y), rgb888 + size_t(y) * size_t(w) * 3, size_t(w) * 3);
     }
     const uint8_t* row(int y) const { return _image.constScanLine(y); }
+    // (addition) what the reference's "Save as..." does through the viewer: getImage().save(file, "PNG") (gui.h:39-45)
+    bool save(const std::string& file, const char* format = nullptr) const { return _image.save(file.c_str(), format); }
 
   private:
     QImage _image;

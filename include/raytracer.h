@@ -26,7 +26,7 @@ class RayTracer {
         : _camera(camera), _light(light), _image(std::make_shared<Image>(0, 0)), _engine(std::make_shared<Engine>()) {}
     RayTracer(const RayTracer& o)
         : _running(o._running.load()), _scene(o._scene), _camera(o._camera), _light(o._light), _image(o._image),
-          _engine(o._engine), _mode(o._mode), _spp(o._spp), _depth(o._depth), _seed(o._seed) {}
+          _engine(o._engine), _mode(o._mode), _spp(o._spp), _depth(o._depth), _seed(o._seed), _refresh_ms(o._refresh_ms) {}
 
     void setScene(const Octree* scene) { _scene = scene; }
 
@@ -54,9 +54,18 @@ class RayTracer {
         p.width = w; p.height = h; p.mode = _mode; p.spp = _spp; p.max_depth = _depth; p.seed = _seed;
         p.rank = 0; p.world = 1;
         std::vector<uint8_t> rgb(size_t(w) * size_t(h) * 3);
-        int rc = g19_render(e.ctx.get(), &cam, light, &p, rgb.data(), nullptr, nullptr);
-        if (rc != G19_OK && rc != G19_ERR_CANCELLED) g19::detail::check(rc, e.ctx.get(), "g19_render");
-        _image->setRows(rgb.data());
+        // incremental rendering (reference raytracer.h:31): the viewer repaints from getImage() every
+        // 32 ms (viewer.h:18-21); each refresh copies the samples-so-far image into the live Image
+        struct Live { Image* image; int refreshes; } live = {_image.get(), 0};
+        int rc = g19_render_progressive(e.ctx.get(), &cam, light, &p, rgb.data(), nullptr,
+                                        [](void* u, double, const uint8_t* px) -> int {
+                                            Live* l = static_cast<Live*>(u);
+                                            l->image->setRows(px);
+                                            ++l->refreshes;
+                                            return 0;
+                                        }, &live, _refresh_ms);
+        if (rc != G19_OK && rc != G19_ERR_CANCELLED) g19::detail::check(rc, e.ctx.get(), "g19_render_progressive");
+        e.refreshes = live.refreshes;
         g19_get_stats(e.ctx.get(), &e.stats);
     }
 
@@ -73,6 +82,8 @@ class RayTracer {
     void setPathTracing(int spp, int max_depth, unsigned seed = 0) { _mode = G19_MODE_PATH; _spp = spp; _depth = max_depth; _seed = seed; }
     void setReferenceMode() { _mode = G19_MODE_REF; }
     g19_stats lastStats() const { return _engine->stats; }
+    void setRefreshInterval(int ms) { _refresh_ms = ms; } // progressive refresh period (default: the viewer's 32 ms timer)
+    int lastRefreshes() const { return _engine->refreshes; }
 
   private:
     struct Engine {
@@ -81,6 +92,7 @@ class RayTracer {
         const g19_scene* scene = nullptr;
         unsigned version = 0;
         g19_stats stats = {};
+        int refreshes = 0;
     };
     std::atomic<bool> _running{false};
     const Octree* _scene = nullptr;
@@ -90,4 +102,5 @@ class RayTracer {
     std::shared_ptr<Engine> _engine;
     int _mode = G19_MODE_REF, _spp = 1, _depth = 1;
     unsigned _seed = 0;
+    int _refresh_ms = 32;
 };

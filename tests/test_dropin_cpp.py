@@ -64,3 +64,11 @@ def test_headless_driver_path_mode(tmp_path):
     r = subprocess.run([BIN, out, "96", "64", "--path", "4", "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert _ppm(out).shape == (64, 96, 3)
+    # progressive refreshes into the live Image (viewer.h:18-21) + "Save as... PNG" (gui.h:39-45)
+    png = str(tmp_path / "p.png")
+    r = subprocess.run([BIN, png, "640", "360", "--path", "256", "4", "--refresh", "0"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    n = int(r.stdout.split(" progressive refreshes")[0].split()[-1])
+    assert n >= 3, r.stdout
+    assert open(png, "rb").read(8) == b"\x89PNG\r\n\x1a\n"

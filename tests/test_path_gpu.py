@@ -162,3 +162,48 @@ def test_zoo_every_entity_kind(g19, abi, oracle):
     assert err <= 1e-2
     assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
     assert abs(int(st.shadow_segments) - segs[1]) <= 1e-3 * segs[1] + 2
+
+
+def test_progressive_refreshes_and_cancel(g19, abi):
+    """g19_render_progressive: the viewer's repaint hook (raytracer.h:31, viewer.h:18-21). Refreshes carry
+    growing fractions and ever more converged images; the result equals the plain render; returning
+    non-zero from the hook cancels within one pass."""
+    w, h = 160, 96
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h)
+    rt = g19.RayTracer(cam, light)
+    rt.setScene(sc)
+    rt.start()
+    plain = rt.run(w, h, mode=abi.MODE_PATH, want=("rgb", "radiance"), spp=24, max_depth=4, seed=2, spp_per_pass=2)
+    seen = []
+
+    def on_pass(fraction, rgb):
+        seen.append((fraction, rgb.copy()))
+        return False
+    out = rt.run_progressive(w, h, on_pass, min_interval_ms=0, want_radiance=True, spp=24, max_depth=4, seed=2, spp_per_pass=2)
+    fr = [f for f, _ in seen]
+    assert len(seen) == 12 and fr == sorted(fr) and fr[-1] == 1.0 and abs(fr[0] - 2 / 24) < 1e-9
+    assert np.array_equal(out["rgb"], plain["rgb"]) and out["radiance"].tobytes() == plain["radiance"].tobytes()
+    assert np.array_equal(seen[-1][1], plain["rgb"])
+    err = [np.abs(img.astype(int) - plain["rgb"].astype(int)).mean() for _, img in seen]
+    assert err[0] > err[5] > err[-1] == 0
+    # a long interval: only the final refresh
+    seen.clear()
+    rt.run_progressive(w, h, on_pass, min_interval_ms=60000, spp=8, max_depth=3, spp_per_pass=2)
+    assert [f for f, _ in seen] == [1.0]
+    # cancel from the hook after the second refresh
+    seen.clear()
+
+    def stop_after_two(fraction, rgb):
+        seen.append(fraction)
+        return len(seen) == 2
+    rt.run_progressive(w, h, stop_after_two, min_interval_ms=0, spp=64, max_depth=4, spp_per_pass=2)
+    assert len(seen) == 3 and seen[1] == 4 / 64 and seen[2] < 0.2  # two refreshes + the closing call
+    assert rt.stats().samples < w * h * 64
+    # REF mode: one pass, one call
+    seen.clear()
+    sc1, cam1, light1 = g19.Octree.builtin(abi.SCENE_DEFAULT)
+    rt1 = g19.RayTracer(cam1, light1)
+    rt1.setScene(sc1)
+    rt1.start()
+    r = rt1.run_progressive(200, 200, lambda f, rgb: seen.append(f) or False, mode=abi.MODE_REF)
+    assert seen == [1.0] and np.array_equal(r["rgb"], rt1.run(200, 200)["rgb"])

@@ -1,7 +1,7 @@
 // g19_headless.cpp -- what reference main.cpp:19-62 + viewer.h:46-61 do, minus Qt:
 // build the default scene through the interface headers (include/*.h), start the
 // ray tracer on a worker thread, run(500,500), write the frame as binary PPM.
-//   g19_headless out.ppm [width height] [--path spp depth]
+//   g19_headless out.ppm|out.png [width height] [--path spp depth] [--refresh ms]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +32,8 @@ int main(int argc, char** argv) {
     scene.push_back(s3);
     raytracer.setScene(&scene);
     if (spp > 0) raytracer.setPathTracing(spp, depth);
+    for (int i = 2; i + 1 < argc; ++i)
+        if (!std::strcmp(argv[i], "--refresh")) raytracer.setRefreshInterval(std::atoi(argv[i + 1]));
 
     RayTracer worker_copy(raytracer); // Gui/Viewer copy the tracer by value
     worker_copy.start();
@@ -43,12 +45,9 @@ int main(int argc, char** argv) {
     });
     t.join();
     std::shared_ptr<Image> img = worker_copy.getImage();
-    FILE* f = std::fopen(out, "wb");
-    if (!f) return 2;
-    std::fprintf(f, "P6\n%d %d\n255\n", img->width(), img->height());
-    for (int y = 0; y < img->height(); ++y) std::fwrite(img->row(y), 1, size_t(img->width()) * 3, f);
-    std::fclose(f);
-    std::printf("%dx%d in %.4f seconds -> %s\n", img->width(), img->height(), seconds, out);
+    if (!img->save(out)) return 2; // .png (what the reference's "Save as..." writes, gui.h:39-45) or .ppm
+    std::printf("%dx%d in %.4f seconds, %d progressive refreshes -> %s\n", img->width(), img->height(), seconds,
+                worker_copy.lastRefreshes(), out);
     // interface check: the host-callable virtuals answer through the GPU probes
     glm::dvec3 p, n;
     Ray r(glm::dvec3{-10, 0, 0}, glm::dvec3{13, 4, 4});
