@@ -29,6 +29,7 @@ UNITS = [
     ("ref_kernels.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("path_kernels.cu", ["--use_fast_math", "-Xptxas", "-v"]),
     ("frame_kernels.cu", []),
+    ("tree_build.cu", []),
     ("path.cu", []),
     ("engine.cu", []),
 ]

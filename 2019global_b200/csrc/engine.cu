@@ -827,6 +827,21 @@ int g19_probe_shade(g19_ctx* ctx, int32_t entity, int textured, const double ray
     return rc;
 }
 
+int g19_probe_path_tree(g19_ctx* ctx, uint32_t* nodes_out, uint32_t max_nodes, uint32_t* index_out, uint32_t max_index,
+                        uint32_t* n_nodes, uint32_t* n_index) {
+    if (!ctx || !n_nodes || !n_index) return G19_ERR_INVALID;
+    if (!ctx->has_scene) return G19_ERR_NO_SCENE;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    const PathSceneD& v = ctx->path.view;
+    *n_nodes = uint32_t(v.n_nodes);
+    *n_index = uint32_t(v.n_index);
+    if (nodes_out && max_nodes >= *n_nodes)
+        G19_CUDA(ctx, cudaMemcpy(nodes_out, v.nodes, size_t(v.n_nodes) * sizeof(PathNodeD), cudaMemcpyDeviceToHost));
+    if (index_out && max_index >= *n_index && v.n_index > 0)
+        G19_CUDA(ctx, cudaMemcpy(index_out, v.index, size_t(v.n_index) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return G19_OK;
+}
+
 int g19_probe_candidates(g19_ctx* ctx, const double origin[3], const double dir[3], int32_t* out_ids, int max_out,
                          int* out_n) {
     if (!ctx || !origin || !dir || !out_n || max_out < 0) return G19_ERR_INVALID;

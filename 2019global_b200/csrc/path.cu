@@ -143,6 +143,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 }
 
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream, std::string& err) {
+    const auto t_start = std::chrono::steady_clock::now();
     std::vector<BuildPrim> prims;
     std::vector<MaterialD> materials;
     std::vector<LightD> lights;
@@ -265,6 +266,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         return G19_ERR_LIMIT;
     }
 
+    const auto t_prims = std::chrono::steady_clock::now();
     // ---- linear octree, breadth first ------------------------------------------
     int kLeafMax = 16; // measured on the 1M-triangle heightfield: 4 / 8 / 16 / 32 -> 49.7 / 43.7 / 41.5 / 42.2 ms per 8.3 M paths
     if (const char* v = std::getenv("G19_LEAF_MAX")) kLeafMax = std::max(1, std::atoi(v)); // tuning knob
@@ -281,9 +283,46 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         while (root_lo[k] + root_size[k] < root_hi[k]) root_size[k] = std::nextafter(root_size[k], INFINITY);
         if (!(root_size[k] > 0)) root_size[k] = 1.0f;
     }
+    // Large scenes build the tree on the device (tree_build.cu: same rules, bit-identical result);
+    // small ones -- and G19_TREE_BUILD=host -- here. The host builder is also the test's checker.
+    bool on_device = prims.size() >= 4096;
+    if (const char* v = std::getenv("G19_TREE_BUILD")) on_device = std::strcmp(v, "device") == 0;
+    PathNodeD* dev_nodes = nullptr;
+    uint32_t* dev_index = nullptr;
+    uint32_t dev_n_nodes = 0, dev_n_index = 0;
+    int dev_depth = 0;
+    if (on_device) {
+        std::vector<float> boxes(prims.size() * 6);
+        for (size_t i = 0; i < prims.size(); ++i)
+            for (int k = 0; k < 3; ++k) {
+                boxes[6 * i + k] = prims[i].box.lo[k];
+                boxes[6 * i + 3 + k] = prims[i].box.hi[k];
+            }
+        DeviceArray d_boxes;
+        cudaError_t be = d_boxes.ensure(boxes.size() * sizeof(float) + 16);
+        if (be == cudaSuccess) be = cudaMemcpyAsync(d_boxes.p, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+        if (be == cudaSuccess) be = cudaStreamSynchronize(stream);
+        if (be != cudaSuccess) {
+            err = std::string("path_upload (boxes): ") + cudaGetErrorString(be);
+            d_boxes.release();
+            return G19_ERR_CUDA;
+        }
+        int rc = path_build_tree_device(static_cast<const float*>(d_boxes.p), uint32_t(prims.size()), root_lo, root_size, kLeafMax,
+                                        kMaxTreeDepth, stream, &dev_nodes, &dev_n_nodes, &dev_index, &dev_n_index, &dev_depth, err);
+        d_boxes.release();
+        if (rc != G19_OK) return rc;
+        if (dev_n_nodes == 1) { // a flat scene after all: the host path sorts it by kind
+            cudaFree(dev_nodes);
+            cudaFree(dev_index);
+            dev_nodes = nullptr;
+            dev_index = nullptr;
+            on_device = false;
+        }
+    }
     std::vector<PathNodeD> nodes(1);
     std::vector<uint32_t> index;
     std::vector<Pending> frontier(1), next;
+    if (on_device) frontier.clear();
     frontier[0].node = 0;
     frontier[0].level = 0;
     frontier[0].ix = frontier[0].iy = frontier[0].iz = 0;
@@ -337,7 +376,18 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         frontier.swap(next);
     }
 
+    const auto t_tree = std::chrono::steady_clock::now();
+    if (std::getenv("G19_DEBUG_TREE") && on_device) { // statistics need the arrays on the host
+        nodes.resize(dev_n_nodes);
+        index.resize(dev_n_index);
+        cudaMemcpy(nodes.data(), dev_nodes, size_t(dev_n_nodes) * sizeof(PathNodeD), cudaMemcpyDeviceToHost);
+        cudaMemcpy(index.data(), dev_index, size_t(dev_n_index) * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        tree_depth = dev_depth;
+    }
     if (std::getenv("G19_DEBUG_TREE")) {
+        std::fprintf(stderr, "[g19] path_upload: %zu primitives extracted in %.1f ms, tree built on the %s in %.1f ms\n", prims.size(),
+                     std::chrono::duration<double, std::milli>(t_prims - t_start).count(), on_device ? "device" : "host",
+                     std::chrono::duration<double, std::milli>(t_tree - t_prims).count());
         size_t leaves = 0, empty = 0, biggest = 0;
         for (const PathNodeD& n : nodes)
             if (n.count & kLeafBit) {
@@ -353,7 +403,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     // A flat scene (the whole scene is one leaf) is sorted parallelograms | triangles | spheres so
     // that the kernels walk three branch-free loops; the leaf position stays the primitive id.
     int n_par = 0, n_tri = 0;
-    if (nodes.size() == 1) {
+    if (!on_device && nodes.size() == 1) {
         auto rank = [](const BuildPrim& p) { return p.hot.q[14] == 2.0f ? 0 : (p.hot.q[14] == 1.0f ? 1 : 2); };
         std::stable_sort(prims.begin(), prims.end(), [&](const BuildPrim& x, const BuildPrim& y) { return rank(x) < rank(y); });
         for (const BuildPrim& p : prims) {
@@ -374,8 +424,16 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, stream);
     };
     cudaError_t e;
-    if ((e = up(b.nodes, nodes.data(), nodes.size() * sizeof(PathNodeD))) != cudaSuccess ||
-        (e = up(b.prim_index, index.data(), index.size() * sizeof(uint32_t))) != cudaSuccess ||
+    if (on_device) { // the arrays are already in HBM: adopt them
+        b.nodes.release();
+        b.prim_index.release();
+        b.nodes.p = dev_nodes;
+        b.nodes.bytes = size_t(dev_n_nodes) * sizeof(PathNodeD);
+        b.prim_index.p = dev_index;
+        b.prim_index.bytes = size_t(dev_n_index) * sizeof(uint32_t);
+    }
+    if ((!on_device && ((e = up(b.nodes, nodes.data(), nodes.size() * sizeof(PathNodeD))) != cudaSuccess ||
+                        (e = up(b.prim_index, index.data(), index.size() * sizeof(uint32_t))) != cudaSuccess)) ||
         (e = up(b.hot, hot.data(), hot.size() * sizeof(PrimHot))) != cudaSuccess ||
         (e = up(b.cold, cold.data(), cold.size() * sizeof(PrimCold))) != cudaSuccess ||
         (e = up(b.materials, materials.data(), materials.size() * sizeof(MaterialD))) != cudaSuccess ||
@@ -391,8 +449,9 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     v.cold = static_cast<const PrimCold*>(b.cold.p);
     v.materials = static_cast<const MaterialD*>(b.materials.p);
     v.lights = static_cast<const LightD*>(b.lights.p);
-    v.n_nodes = int32_t(nodes.size());
-    v.n_index = int32_t(index.size());
+    v.n_nodes = on_device ? int32_t(dev_n_nodes) : int32_t(nodes.size());
+    v.n_index = on_device ? int32_t(dev_n_index) : int32_t(index.size());
+    if (on_device) tree_depth = dev_depth;
     v.n_prims = int32_t(prims.size());
     v.n_lights = int32_t(lights.size());
     v.tree_depth = tree_depth;

@@ -110,6 +110,10 @@ struct PathRenderArgs {
     cudaEvent_t cls0, cls1;
 };
 
+// tree_build.cu: the linear octree built level by level on the device (same rules as path.cu's host builder)
+int path_build_tree_device(const float* d_boxes, uint32_t n_prims, const float root_lo[3], const float root_size[3],
+                           int leaf_max, int max_depth, cudaStream_t s, PathNodeD** d_nodes, uint32_t* n_nodes,
+                           uint32_t** d_index, uint32_t* n_index, int* tree_depth, std::string& err);
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream, std::string& err);
 int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err);
 int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err);

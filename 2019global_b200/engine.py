@@ -32,7 +32,7 @@ EXPORTS = [
     "g19_frame_create", "g19_frame_export", "g19_frame_import", "g19_frame_destroy", "g19_frame_pointers",
     "g19_render_to_frame", "g19_frame_wait", "g19_frame_release", "g19_frame_timeouts",
     "g19_frame_read", "g19_render_progressive", "g19_render_tiles_device", "g19_untile_device", "g19_tile_pixels",
-    "g19_probe_texcoord", "g19_probe_shade", "g19_entity_bbox", "g19_entity_triangles",
+    "g19_probe_texcoord", "g19_probe_shade", "g19_probe_path_tree", "g19_entity_bbox", "g19_entity_triangles",
 ]
 
 
@@ -77,6 +77,8 @@ def lib():
         L.g19_progress.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.g19_probe_intersect.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
+        L.g19_probe_path_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                          C.POINTER(C.c_uint32)]
         L.g19_probe_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.POINTER(C.c_int)]
         L.g19_render_progressive.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_void_p, C.POINTER(abi.Params),
@@ -305,6 +307,15 @@ class RayTracer:
         nrm = np.zeros((n, 3))
         self._check(self._L.g19_probe_intersect(self.h, entity, n, _ptr(o), _ptr(d), _ptr(hit), _ptr(pts), _ptr(nrm)))
         return hit, pts, nrm
+
+    def path_tree(self):
+        """(nodes (n,2) uint32, index (m,) uint32) of the linear octree PATH mode traverses."""
+        nn, ni = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._L.g19_probe_path_tree(self.h, None, 0, None, 0, C.byref(nn), C.byref(ni)))
+        nodes = np.zeros((nn.value, 2), np.uint32)
+        index = np.zeros(max(ni.value, 1), np.uint32)
+        self._check(self._L.g19_probe_path_tree(self.h, _ptr(nodes), nn.value, _ptr(index), ni.value, C.byref(nn), C.byref(ni)))
+        return nodes, index[:ni.value]
 
     def probe_candidates(self, o, d, max_out=1 << 16):
         out = np.zeros(max_out, np.int32)

@@ -284,6 +284,13 @@ int g19_probe_intersect(g19_ctx* ctx, int32_t entity, int n, const double* origi
 int g19_probe_candidates(g19_ctx* ctx, const double origin[3], const double dir[3],
                          int32_t* out_ids, int max_out, int* out_n);
 
+/* The linear octree PATH mode traverses (the engine's own build of what Octree::push_back,
+ * octree.h:20-43,75-129, builds for the reference; large scenes build it on the GPU): node records
+ * (first, count|leaf bit31) as 2 x uint32 each, and the concatenated leaf primitive lists. Pass
+ * NULL / 0 to query the sizes.                                                                  */
+int g19_probe_path_tree(g19_ctx* ctx, uint32_t* nodes_out, uint32_t max_nodes, uint32_t* index_out,
+                        uint32_t max_index, uint32_t* n_nodes, uint32_t* n_index);
+
 /* Entity::getTextureCoord(point)                           entities.h:32    */
 int g19_probe_texcoord(g19_ctx* ctx, int32_t entity, int n, const double* points, int32_t* out_uv);
 /* Material::blinn_phong_texture / blinn_phong              material.h:31-62.
