@@ -50,6 +50,7 @@
 
 #include <cfloat>
 #include <cstdio>
+#include <mutex>
 
 namespace g19 {
 namespace {
@@ -952,20 +953,25 @@ static void note_launch_error(const char* what, cudaError_t e, size_t smem, int 
                  smem, grid);
 }
 
-// The grid of a persistent kernel = SM count x resident CTAs, cached per (kernel, smem size).
+// The grid of a persistent kernel = SM count x resident CTAs, cached per (device, kernel, smem size):
+// function attributes are per device, and one process may drive several (one g19_ctx each).
 template <typename K> static int persistent_grid(K kernel, size_t smem, int sm_count) {
-    struct Entry { const void* fn; size_t smem; int grid; };
-    static Entry cache[128];
+    struct Entry { int device; const void* fn; size_t smem; int grid; };
+    static Entry cache[256];
     static int n_cache = 0;
+    static std::mutex lock;
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> guard(lock);
     for (int i = 0; i < n_cache; ++i)
-        if (cache[i].fn == (const void*)kernel && cache[i].smem == smem) return cache[i].grid;
+        if (cache[i].device == device && cache[i].fn == (const void*)kernel && cache[i].smem == smem) return cache[i].grid;
     // static (prefetch stage) + dynamic (scene prefix, stack) shared memory may exceed 48 KB.
     // The attribute is a CAP: always raise it to the same ceiling, never to this scene's size
     // (a smaller later scene would otherwise lower it under a cached larger launch).
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     if (e != cudaSuccess) note_launch_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e, smem, 0);
     const int grid = resident_grid(kernel, smem, sm_count);
-    if (n_cache < 128) cache[n_cache++] = Entry{(const void*)kernel, smem, grid};
+    if (n_cache < 256) cache[n_cache++] = Entry{device, (const void*)kernel, smem, grid};
     return grid;
 }
 
