@@ -466,7 +466,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
     for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &w.hp, &w.dw, &w.tp,
-                           &w.L, &w.queues, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
+                           &w.L, &w.queues, &w.rays, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
         d->release();
     if (w.events) {
         for (int i = 0; i < w.n_events; ++i) cudaEventDestroy(w.events[i]);
@@ -535,12 +535,12 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         PATH_CUDA(cudaMemsetAsync(w.L.p, 0, P * 3 * sizeof(float), s));
     }
     const size_t plane = w.capacity;
-    PATH_CUDA(w.counts.ensure((kMaxPathDepth + 1) * 4 * sizeof(uint32_t)));
+    PATH_CUDA(w.counts.ensure((kMaxPathDepth + 1) * 5 * sizeof(uint32_t)));
     PATH_CUDA(w.totals.ensure(8 * sizeof(unsigned long long)));
     PATH_CUDA(w.accum.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rad_l.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rgb_l.ensure(npix * 3));
-    PATH_CUDA(cudaMemsetAsync(w.counts.p, 0, (kMaxPathDepth + 1) * 4 * sizeof(uint32_t), s));
+    PATH_CUDA(cudaMemsetAsync(w.counts.p, 0, (kMaxPathDepth + 1) * 5 * sizeof(uint32_t), s));
     PATH_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(unsigned long long), s));
     PATH_CUDA(cudaMemsetAsync(w.accum.p, 0, npix * 3 * sizeof(float), s));
     if (p.profile && !w.events) {
@@ -584,6 +584,18 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa.stage_lights = (pa.stage_cold > 0 && b.view.n_lights <= 32) ? b.view.n_lights : 0;
     if (b.view.n_lights > 32) pa.stage_cold = 0; // not a "flat, fully staged" scene: the generic kernels take it
     pa.stack_levels = b.view.tree_depth + 1;
+    // tree scenes: the bounce kernels queue their rays (2 per vertex at most) for trace_kernel
+    pa.refill = 8;
+    if (const char* v = std::getenv("G19_REFILL")) pa.refill = std::max(1, std::min(32, std::atoi(v))); // tuning knob
+    const bool fused = path_scene_is_flat(pa); // flat scenes trace inside the bounce kernels
+    pa.ray0 = pa.ray1 = pa.ray2 = nullptr;
+    if (!fused) {
+        const size_t ray_cap = 2 * plane + kQueueSlack;
+        PATH_CUDA(w.rays.ensure(3 * ray_cap * sizeof(float4)));
+        pa.ray0 = static_cast<float4*>(w.rays.p);
+        pa.ray1 = pa.ray0 + ray_cap;
+        pa.ray2 = pa.ray1 + ray_cap;
+    }
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
     auto last_refresh = std::chrono::steady_clock::now();
@@ -605,6 +617,10 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
                 if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
                 if (launch_bounce(pa, bounce, kind, a.sm_count, s)) ++n;
+            }
+            if (!fused && n > 0) { // tree scenes: one walk over the rays this bounce's vertices produced
+                launch_trace(pa, bounce, a.sm_count, s);
+                ++n;
             }
             clk.end(G19_K_SHADE);
             stats.class_launches[G19_K_SHADE] += n;

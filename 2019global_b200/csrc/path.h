@@ -33,7 +33,7 @@ constexpr int kNumQueues = 6;        // (diffuse, mirror, glass) x two bounce pa
 // chunk per warp and queue behind (padded with an invalid marker): 2 Mi entries of slack cover
 // 148 SMs x 64 warps x 64 entries x 3 producer kernels.
 constexpr size_t kQueueSlack = size_t(2) << 20;
-enum { Q_DIFFUSE = 1, Q_MIRROR = 2, Q_GLASS = 3 }; // = g19_bsdf + 1; column of PassArgs::counts
+enum { Q_RAYS = 0, Q_DIFFUSE = 1, Q_MIRROR = 2, Q_GLASS = 3 }; // column of PassArgs::counts (material = g19_bsdf + 1)
 
 struct PathSceneD {
     const PathNodeD* nodes;
@@ -72,7 +72,8 @@ struct PathWork {
     DeviceArray tp;            // float4[P]: throughput.rgb, sample index bits
     DeviceArray L;             // float[3][P]: radiance gathered by the path so far
     DeviceArray queues;        // uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
-    DeviceArray counts;        // uint32[kMaxPathDepth+1][4] queue lengths per bounce
+    DeviceArray rays;          // float4[3][2P + slack]: ray queue of one bounce (tree scenes only)
+    DeviceArray counts;        // uint32[kMaxPathDepth+1][5]: queue lengths per bounce + ray fetch cursors
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
     DeviceArray accum;         // float[3][n_local_pix]
     DeviceArray rad_l, rgb_l;  // resolved local-pixel outputs
@@ -137,16 +138,22 @@ struct PassArgs {
     uint32_t* q[6];        // [bounce parity * 3 + (kind - 1)]
     uint32_t kind_mask;    // bit (kind - 1): the scene has a material of that class
     size_t queue_cap;      // entries per queue (P + chunk slack)
-    uint32_t* counts;      // [kMaxPathDepth+1][4]
+    float4* ray0;          // tree scenes: the bounce's ray queue (origin, tmax)
+    float4* ray1;          //   (direction, slot | flags)
+    float4* ray2;          //   (light sample rgb) of shadow rays
+    uint32_t* counts;      // [kMaxPathDepth+1][4] queue lengths (column 0: rays) + [kMaxPathDepth+1] fetch cursors
     unsigned long long* totals;
     float* accum;          // 3 planes of n_local_pix
     // shared-memory staging (see path_kernels.cu stage_scene)
     int32_t stage_nodes, stage_prims, stage_cold, stage_lights, stack_levels;
+    int32_t refill;        // trace_kernel: idle lanes per warp that trigger a fetch of new rays
 };
 
 void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s);
 // false = nothing to launch for this (bounce, kind): specular vertices on the last segment
 bool launch_bounce(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s);
+void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s); // tree scenes: after the bounce's shade launches
+bool path_scene_is_flat(const PassArgs& a);
 void launch_accumulate(const PassArgs& a, cudaStream_t s);
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s);
 const char* path_launch_error(); // first failed launch/attribute call since the last clear, or nullptr

@@ -61,6 +61,9 @@ constexpr uint32_t kInvalid = 0xffffffffu; // padding entry of a queue / "no pri
 constexpr uint32_t kChunk = 64;            // queue entries reserved per atomic (>= 32)
 constexpr float kRayEps = 1.0e-3f;         // origin offset along the normal (scene units)
 constexpr float kPi = 3.14159265358979323846f;
+constexpr uint32_t kRayShadow = 0x80000000u;   // ray record flags riding on the slot index (< 2^30)
+constexpr uint32_t kRaySpecular = 0x40000000u; // the continuation ray leaves a specular vertex
+constexpr uint32_t kRaySlotMask = 0x3fffffffu;
 
 // ---- Philox4x32-10 (Salmon et al. 2011); identical integer stream in oracle/path_oracle.c
 __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0) {
@@ -311,18 +314,43 @@ __device__ __forceinline__ void trace_flat(const SceneAccess<true>& S, float3 o,
 //     L2-resident on B200 (126 MB)
 //   * 51 instructions per plane update -> 21 with the linear form
 // `any` = stop at the first hit (shadow rays).
-template <bool ALL>
-__device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tmax, bool any, float& t_hit,
-                         uint32_t& prim_hit) {
-    const PathSceneD& g = *S.g;
-    uint32_t* const stack = S.stack;
-    float best = tmax;
-    uint32_t best_prim = kInvalid;
-    const uint32_t* __restrict__ index = g.index;
-    const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
+// The walk as a resumable state machine: init() places the ray at the root, step() advances it
+// to its next non-empty leaf and tests that leaf (one while-while round), returning true when
+// the ray is finished. traverse() below runs it to completion; trace_kernel interleaves the
+// steps of 32 rays per warp and hands a finished lane the next ray of the queue.
+struct TreeWalk {
+    float3 o, d, A, B;
+    float best;
+    uint32_t best_prim, a;
+    int level;
+    uint32_t ix, iy, iz;
+    float t0x, t0y, t0z, tmx, tmy, tmz, t1x, t1y, t1z;
+    unsigned long long codes; // 4 bits per level: 0xF = not started, else current child (mirrored)
+    uint32_t leaf_first, leaf_n; // the part of the current leaf's list still to be tested
+    float leaf_exit;             // parameter at which the ray leaves the current leaf's cell
+    bool any;
 
-    auto leaf = [&](uint32_t first, uint32_t n) {
-        // two primitives per step: independent FMA chains, all loads of the step issued up front
+    __device__ __forceinline__ void planes() { // entry / mid / exit parameters of the cell (level; ix,iy,iz)
+        const float s1 = __int_as_float((127 - (level + 1)) << 23); // 2^-(level+1), exact
+        const float hx = B.x * s1, hy = B.y * s1, hz = B.z * s1;
+        const float fx = float(2u * ix), fy = float(2u * iy), fz = float(2u * iz);
+        const float ax = fmaf(fx, hx, A.x), bx = fmaf(fx + 2.0f, hx, A.x);
+        const float ay = fmaf(fy, hy, A.y), by = fmaf(fy + 2.0f, hy, A.y);
+        const float az = fmaf(fz, hz, A.z), bz = fmaf(fz + 2.0f, hz, A.z);
+        t0x = fminf(ax, bx); t1x = fmaxf(ax, bx);
+        t0y = fminf(ay, by); t1y = fmaxf(ay, by);
+        t0z = fminf(az, bz); t1z = fmaxf(az, bz);
+        tmx = fmaf(fx + 1.0f, hx, A.x);
+        tmy = fmaf(fy + 1.0f, hy, A.y);
+        tmz = fmaf(fz + 1.0f, hz, A.z);
+    }
+
+    // tests up to `limit` primitives of the list [first, first + n), two per step (independent FMA
+    // chains, all loads of the step issued up front)
+    __device__ __forceinline__ void leaf(const PathSceneD& g, uint32_t first, uint32_t n, uint32_t limit) {
+        const uint32_t* __restrict__ index = g.index;
+        const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
+        if (n > limit) n = limit;
         uint32_t id0 = __ldg(index + first), id1 = n > 1 ? __ldg(index + first + 1) : id0;
         for (uint32_t k = 0; k < n; k += 2) {
             const float4* p0 = hot + 4 * (size_t)id0;
@@ -340,103 +368,133 @@ __device__ bool traverse(const SceneAccess<ALL>& S, float3 o, float3 d, float tm
             if (t1 >= 0.0f) { best = t1; best_prim = cur1; }
             if (any && best_prim != kInvalid) break;
         }
-    };
-
-    const uint2 root = S.node(0);
-    if (root.y & kLeafBit) { // the whole scene is one leaf (but not staged as a flat scene)
-        leaf(root.x, root.y & ~kLeafBit);
-        t_hit = best;
-        prim_hit = best_prim;
-        return best_prim != kInvalid;
     }
 
-    float3 dd = d;
-    if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
-    if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
-    if (fabsf(dd.z) < 1.0e-20f) dd.z = copysignf(1.0e-20f, dd.z);
-    const float3 inv = f3(__fdividef(1.0f, dd.x), __fdividef(1.0f, dd.y), __fdividef(1.0f, dd.z));
-    const uint32_t a = (dd.x < 0.0f ? 1u : 0u) | (dd.y < 0.0f ? 2u : 0u) | (dd.z < 0.0f ? 4u : 0u);
-    const float3 A = f3((g.root_lo[0] - o.x) * inv.x, (g.root_lo[1] - o.y) * inv.y, (g.root_lo[2] - o.z) * inv.z);
-    const float3 B = f3(g.root_size[0] * inv.x, g.root_size[1] * inv.y, g.root_size[2] * inv.z);
-    int level = 0;
-    uint32_t ix = 0, iy = 0, iz = 0;
-    float t0x, t0y, t0z, tmx, tmy, tmz, t1x, t1y, t1z;
-    auto planes = [&]() { // entry / mid / exit parameters of the cell (level; ix,iy,iz)
-        const float s1 = __int_as_float((127 - (level + 1)) << 23); // 2^-(level+1), exact
-        const float hx = B.x * s1, hy = B.y * s1, hz = B.z * s1;
-        const float fx = float(2u * ix), fy = float(2u * iy), fz = float(2u * iz);
-        const float ax = fmaf(fx, hx, A.x), bx = fmaf(fx + 2.0f, hx, A.x);
-        const float ay = fmaf(fy, hy, A.y), by = fmaf(fy + 2.0f, hy, A.y);
-        const float az = fmaf(fz, hz, A.z), bz = fmaf(fz + 2.0f, hz, A.z);
-        t0x = fminf(ax, bx); t1x = fmaxf(ax, bx);
-        t0y = fminf(ay, by); t1y = fmaxf(ay, by);
-        t0z = fminf(az, bz); t1z = fmaxf(az, bz);
-        tmx = fmaf(fx + 1.0f, hx, A.x);
-        tmy = fmaf(fy + 1.0f, hy, A.y);
-        tmz = fmaf(fz + 1.0f, hz, A.z);
-    };
-    planes();
-    bool done = false;
-    {
+    // returns true when the ray is already finished (missed the root box, or the scene is one leaf)
+    template <bool ALL>
+    __device__ __forceinline__ bool init(const SceneAccess<ALL>& S, float3 o_, float3 d_, float tmax, bool any_) {
+        const PathSceneD& g = *S.g;
+        o = o_;
+        d = d_;
+        best = tmax;
+        best_prim = kInvalid;
+        any = any_;
+        const uint2 root = S.node(0);
+        leaf_n = 0;
+        if (root.y & kLeafBit) { // the whole scene is one leaf (but not staged as a flat scene)
+            leaf(g, root.x, root.y & ~kLeafBit, 0x7fffffffu);
+            return true;
+        }
+        float3 dd = d;
+        if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
+        if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
+        if (fabsf(dd.z) < 1.0e-20f) dd.z = copysignf(1.0e-20f, dd.z);
+        const float3 inv = f3(__fdividef(1.0f, dd.x), __fdividef(1.0f, dd.y), __fdividef(1.0f, dd.z));
+        a = (dd.x < 0.0f ? 1u : 0u) | (dd.y < 0.0f ? 2u : 0u) | (dd.z < 0.0f ? 4u : 0u);
+        A = f3((g.root_lo[0] - o.x) * inv.x, (g.root_lo[1] - o.y) * inv.y, (g.root_lo[2] - o.z) * inv.z);
+        B = f3(g.root_size[0] * inv.x, g.root_size[1] * inv.y, g.root_size[2] * inv.z);
+        level = 0;
+        ix = iy = iz = 0;
+        planes();
         const float tn = fmaxf(fmaxf(t0x, t0y), t0z), tf = fminf(fminf(t1x, t1y), t1z);
-        if (tn > fminf(tf, best) + 1.0e-5f || tf < 0.0f) done = true;
+        if (tn > fminf(tf, best) + 1.0e-5f || tf < 0.0f) return true;
+        codes = 0xFull;
+        S.stack[0] = root.x;
+        return false;
     }
-    unsigned long long codes = 0xFull; // 4 bits per level: 0xF = not started, else current child (mirrored)
-    stack[0] = root.x;
-    uint32_t leaf_first = 0, leaf_n = 0;
-    float leaf_exit = 0.0f;
-    while (!done) {
-        // ---- walk: until this lane stands in a non-empty leaf or has left the tree ----
-        while (!done && leaf_n == 0u) {
-            uint32_t cur = uint32_t(codes >> (4 * level)) & 0xFu;
-            bool leave = false;
-            if (cur == 0xFu) {
+
+    // One ROUND, built so that the 32 rays of a warp stay in step: exactly kWalkSteps cell moves
+    // towards the next non-empty leaf (predicated off for lanes that have arrived or are finished),
+    // then one batch of at most kLeafBatch primitives of the current leaf. MUST be called by all 32
+    // lanes of the warp (`active` = this lane has a ray): the loop re-converges the warp at every
+    // move -- with `continue`/`break` in a data-dependent loop the lanes drifted apart and ran the
+    // loop body in ~2.5 separate groups of 5.6 lanes (ncu, profiles/r01_tuning_log.md).
+    // Returns true when the lane's ray is finished.
+    static constexpr int kWalkSteps = 4;
+    static constexpr uint32_t kLeafBatch = 4;
+    template <bool ALL> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
+        uint32_t* const stack = S.stack;
+        bool done = false;
+#pragma unroll 1
+        for (int it = 0; it < kWalkSteps; ++it) {
+            __syncwarp();
+            if (active && !done && leaf_n == 0u) {
+                // first child / next child, both evaluated branch-free (a branch here made the
+                // compiler run the rest of the move once per side: ncu, 2 x 5.6 lanes)
+                const uint32_t old = uint32_t(codes >> (4 * level)) & 0xFu;
+                const bool fresh = old == 0xFu;
                 const float te = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), 0.0f);
-                cur = (tmx < te ? 1u : 0u) | (tmy < te ? 2u : 0u) | (tmz < te ? 4u : 0u);
-            } else {
-                const float ex = (cur & 1u) ? t1x : tmx, ey = (cur & 2u) ? t1y : tmy, ez = (cur & 4u) ? t1z : tmz;
+                const uint32_t first = (tmx < te ? 1u : 0u) | (tmy < te ? 2u : 0u) | (tmz < te ? 4u : 0u);
+                const float ex = (old & 1u) ? t1x : tmx, ey = (old & 2u) ? t1y : tmy, ez = (old & 4u) ? t1z : tmz;
                 const uint32_t bit = (ex <= ey && ex <= ez) ? 1u : (ey <= ez ? 2u : 4u);
-                leave = (cur & bit) != 0u;
-                cur |= bit;
+                const bool leave = !fresh && (old & bit) != 0u;
+                const uint32_t cur = fresh ? first : (old | bit);
+                bool moved = false;
+                if (leave) { // the ray left this cell: back to the parent
+                    if (level == 0) {
+                        done = true;
+                    } else {
+                        --level;
+                        ix >>= 1; iy >>= 1; iz >>= 1;
+                        moved = true;
+                    }
+                } else {
+                    const float cen = fmaxf(fmaxf((cur & 1u) ? tmx : t0x, (cur & 2u) ? tmy : t0y), (cur & 4u) ? tmz : t0z);
+                    const float cex = fminf(fminf((cur & 1u) ? t1x : tmx, (cur & 2u) ? t1y : tmy), (cur & 4u) ? t1z : tmz);
+                    if (cen > best + fabsf(best) * 2.0e-6f + 1.0e-5f) {
+                        done = true; // everything from here on is farther than the hit
+                    } else {
+                        codes = (codes & ~(0xFull << (4 * level))) | ((unsigned long long)cur << (4 * level));
+                        if (cex >= 0.0f) {
+                            const uint32_t c = cur ^ a;
+                            const uint2 rec = S.node(stack[level * kThreads] + c);
+                            if (rec.y != kLeafBit) { // not an empty octant
+                                if (rec.y & kLeafBit) {
+                                    leaf_first = rec.x;
+                                    leaf_n = rec.y & ~kLeafBit;
+                                    leaf_exit = cex;
+                                } else {
+                                    ++level;
+                                    stack[level * kThreads] = rec.x;
+                                    ix = 2u * ix + (c & 1u); iy = 2u * iy + ((c >> 1) & 1u); iz = 2u * iz + ((c >> 2) & 1u);
+                                    codes |= 0xFull << (4 * level);
+                                    moved = true;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (moved) planes();
             }
-            if (leave) { // the ray left this cell: back to the parent
-                if (level == 0) { done = true; break; }
-                --level;
-                ix >>= 1; iy >>= 1; iz >>= 1;
-                planes();
-                continue;
-            }
-            const float cen = fmaxf(fmaxf((cur & 1u) ? tmx : t0x, (cur & 2u) ? tmy : t0y), (cur & 4u) ? tmz : t0z);
-            const float cex = fminf(fminf((cur & 1u) ? t1x : tmx, (cur & 2u) ? t1y : tmy), (cur & 4u) ? t1z : tmz);
-            if (cen > best + fabsf(best) * 2.0e-6f + 1.0e-5f) { done = true; break; } // everything from here on is farther
-            codes = (codes & ~(0xFull << (4 * level))) | ((unsigned long long)cur << (4 * level));
-            if (cex < 0.0f) continue;
-            const uint32_t c = cur ^ a;
-            const uint2 rec = S.node(stack[level * kThreads] + c);
-            if (rec.y == kLeafBit) continue; // empty octant
-            if (rec.y & kLeafBit) {
-                leaf_first = rec.x;
-                leaf_n = rec.y & ~kLeafBit;
-                leaf_exit = cex;
-                continue; // ends the walk phase
-            }
-            ++level;
-            stack[level * kThreads] = rec.x;
-            ix = 2u * ix + (c & 1u); iy = 2u * iy + ((c >> 1) & 1u); iz = 2u * iz + ((c >> 2) & 1u);
-            codes |= 0xFull << (4 * level);
-            planes();
         }
-        // ---- test: all lanes that stand in a leaf test its primitives together ----
-        if (leaf_n != 0u) {
-            leaf(leaf_first, leaf_n);
-            leaf_n = 0u;
-            // any hit ends a shadow ray; a hit inside its own cell cannot be beaten by a later cell
-            if (best_prim != kInvalid && (any || best <= leaf_exit)) done = true;
+        __syncwarp();
+        // ---- test: the next batch of the current leaf's primitives ----
+        if (active && !done && leaf_n != 0u) {
+            leaf(*S.g, leaf_first, leaf_n, kLeafBatch);
+            const uint32_t tested = leaf_n < kLeafBatch ? leaf_n : kLeafBatch;
+            leaf_first += tested;
+            leaf_n -= tested;
+            if (any && best_prim != kInvalid) done = true;                                // any hit ends a shadow ray
+            else if (leaf_n == 0u && best_prim != kInvalid && best <= leaf_exit) done = true; // a hit inside its own cell cannot be beaten
         }
+        __syncwarp();
+        return done;
     }
-    t_hit = best;
-    prim_hit = best_prim;
-    return best_prim != kInvalid;
+};
+
+// Runs the walks of a whole warp to completion; MUST be called by all 32 lanes (`active` = this
+// lane has a ray). Used for camera rays; secondary rays go through trace_kernel.
+template <bool ALL>
+__device__ bool traverse(const SceneAccess<ALL>& S, bool active, float3 o, float3 d, float tmax, bool any, float& t_hit,
+                         uint32_t& prim_hit) {
+    TreeWalk w = {};
+    w.best_prim = kInvalid;
+    bool busy = active && !w.init(S, o, d, tmax, any);
+    while (__any_sync(kFull, busy))
+        if (w.step(S, busy)) busy = false;
+    t_hit = w.best;
+    prim_hit = w.best_prim;
+    return active && w.best_prim != kInvalid;
 }
 
 // ---- per-slot helpers ------------------------------------------------------------
@@ -500,6 +558,26 @@ __device__ __forceinline__ void warp_append(WarpCursor& c, bool want, uint32_t v
     if (want) queue[rank < room ? base0 + rank : base1 + (rank - room)] = value;
 }
 
+// Same reservation, for records wider than a queue entry: returns the lane's position (kInvalid
+// for lanes that do not want one); the caller writes the record.
+__device__ __forceinline__ uint32_t warp_reserve(WarpCursor& c, bool want, uint32_t* __restrict__ counter) {
+    const uint32_t m = __ballot_sync(kFull, want);
+    if (m == 0) return kInvalid;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+    const uint32_t room = c.end - c.pos, base0 = c.pos;
+    uint32_t base1 = 0;
+    if (n > room) {
+        if (lane == 0) base1 = atomicAdd(counter, kChunk);
+        base1 = __shfl_sync(kFull, base1, 0);
+        c.pos = base1 + (n - room);
+        c.end = base1 + kChunk;
+    } else {
+        c.pos += n;
+    }
+    return want ? (rank < room ? base0 + rank : base1 + (rank - room)) : kInvalid;
+}
+
 // Pad what is left of the warp's last chunk so that consumers can skip it.
 __device__ __forceinline__ void warp_flush(const WarpCursor& c, uint32_t* __restrict__ queue) {
     for (uint32_t i = c.pos + (threadIdx.x & 31u); i < c.end; i += 32u) queue[i] = kInvalid;
@@ -550,15 +628,15 @@ struct Sorter {
     }
 };
 
-// Nearest hit of one ray, flat or tree. Returns the primitive id and the bsdf/material tags.
+// Nearest hit of one ray, flat or tree. Called by all 32 lanes; `active` = the lane has a ray.
 template <bool ALL>
-__device__ __forceinline__ bool nearest(const SceneAccess<ALL>& S, float3 o, float3 d, float& t, uint32_t& prim) {
+__device__ __forceinline__ bool nearest(const SceneAccess<ALL>& S, bool active, float3 o, float3 d, float& t, uint32_t& prim) {
     if constexpr (ALL) {
         bool occ;
-        trace_flat<false>(S, o, d, FLT_MAX, d, -1.0f, t, prim, occ);
+        trace_flat<false>(S, o, d, active ? FLT_MAX : -1.0f, d, -1.0f, t, prim, occ);
         return prim != kInvalid;
     } else {
-        return traverse<ALL>(S, o, d, FLT_MAX, false, t, prim);
+        return traverse<ALL>(S, active, o, d, FLT_MAX, false, t, prim);
     }
 }
 
@@ -581,26 +659,29 @@ template <bool ALL> __global__ void __launch_bounds__(kThreads, ALL ? 4 : 2) ray
     for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q - lane < n; q += stride) { // warp-uniform trip count
         const uint32_t slot = q;
         int kind = -1;
+        bool live = false;
+        uint32_t pixel = 0;
+        float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
         if (q < n) {
             int x, y;
             uint32_t sample;
-            if (slot_pixel(a, slot, x, y, sample)) {
-                const uint32_t pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
-                float3 o, d;
+            live = slot_pixel(a, slot, x, y, sample);
+            if (live) {
+                pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
                 camera_ray(a, x, y, pixel, sample, o, d);
-                float t;
-                uint32_t prim;
-                if (nearest<ALL>(S, o, d, t, prim)) {
-                    const float4 tag = S.hot_row(prim, 3);
-                    const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
-                    if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
-                        const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
-                        add_radiance(a, slot, f3(m.emission[0], m.emission[1], m.emission[2]));
-                    } else if (bsdf == G19_BSDF_DIFFUSE || a.max_depth > 1) {
-                        kind = bsdf;
-                        store_vertex(a, slot, o + d * t, prim, d, pixel);
-                    }
-                }
+            }
+        }
+        float t;
+        uint32_t prim;
+        if (nearest<ALL>(S, live, o, d, t, prim)) { // all 32 lanes walk together
+            const float4 tag = S.hot_row(prim, 3);
+            const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
+            if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
+                const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
+                add_radiance(a, slot, f3(m.emission[0], m.emission[1], m.emission[2]));
+            } else if (bsdf == G19_BSDF_DIFFUSE || a.max_depth > 1) {
+                kind = bsdf;
+                store_vertex(a, slot, o + d * t, prim, d, pixel);
             }
         }
         out.push(kind, slot);
@@ -657,17 +738,24 @@ __device__ __forceinline__ void prefetch_vertex(const PassArgs& a, uint32_t slot
 // KIND: Q_DIFFUSE / Q_MIRROR / Q_GLASS. FIRST: the vertex of the camera segment. LAST: the path's
 // final segment ended here -- next-event estimation only, no continuation.
 template <int KIND, bool FIRST, bool LAST, bool ALL>
-__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 2) : (ALL ? 3 : 2))
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3)
     bounce_kernel(const PassArgs a, const int bounce) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
-    constexpr bool kTp = !FIRST, kRad = !FIRST && kDiffuse;
+    constexpr bool kTp = !FIRST, kRadStat = !FIRST && kDiffuse, kRad = ALL && kRadStat; // tree scenes: trace_kernel adds the light sample
     const uint32_t n = a.counts[bounce * 4 + KIND];
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave before staging anything
     if (LAST && !kDiffuse) return;          // a specular vertex on the last segment contributes nothing
-    const SceneAccess<ALL> S = stage_scene<ALL>(a);
+    // Flat scenes trace their rays right here. Tree scenes only shade: their rays go to the bounce's
+    // ray queue and trace_kernel walks them with dynamic fetch (a heavy tail of long walks would
+    // otherwise hold the other 31 lanes of the warp -- ncu: 3.4 of 32 lanes active).
+    SceneAccess<ALL> S;
+    if constexpr (ALL) S = stage_scene<ALL>(a);
+    else S.g = &a.scene;
     const uint32_t* __restrict__ qin = a.q[(bounce & 1) * 3 + (KIND - 1)];
     Sorter out;
-    if (!LAST) out.init(a, bounce + 1);
+    if (ALL && !LAST) out.init(a, bounce + 1);
+    WarpCursor ray_cur = {0, 0};
+    uint32_t* const ray_counter = a.counts + bounce * 4 + Q_RAYS;
     unsigned traced = 0, shadow_rays = 0, lit = 0, calls = 0;
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
@@ -690,6 +778,10 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 2) : 
         cp_async_wait<1>();                        // this slot's state has landed
         const uint32_t slot = s_cur;
         int kind_next = -1;
+        bool ray_shadow = false, ray_cont = false; // tree scenes: rays to enqueue
+        float3 ray_o = f3(0.f, 0.f, 0.f), ray_w = f3(0.f, 0.f, 1.f), ray_d = f3(0.f, 0.f, 1.f), ray_rgb = f3(0.f, 0.f, 0.f);
+        float ray_tmax = 0.0f;
+        uint32_t ray_flags = 0;
         if (slot != kInvalid) {
             ++calls;
             const int tid = threadIdx.x;
@@ -794,6 +886,10 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 2) : 
             if (cont) ++traced;
 
             // ---- the rays of this vertex: shadow (any hit) and continuation (nearest hit) ----
+            if (!ALL) {
+                ray_o = no; ray_w = w; ray_d = nd; ray_rgb = lit_rgb; ray_tmax = tmax_s;
+                ray_flags = (flags & 1u) ? kRaySpecular : 0u;
+            }
             bool blocked = false, hit = false;
             float t_hit = FLT_MAX;
             uint32_t prim_hit = kInvalid;
@@ -814,17 +910,16 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 2) : 
                 }
                 hit = cont && prim_hit != kInvalid;
             } else {
-                // one inlined copy of the tree walk serves both rays: pass 0 = shadow, pass 1 = continuation
-                for (int pass = (kDiffuse && want_shadow) ? 0 : 1; pass < (cont ? 2 : 1); ++pass) {
-                    float tt;
-                    uint32_t pp;
-                    const bool any = pass == 0;
-                    const bool h = traverse<ALL>(S, no, any ? w : nd, any ? tmax_s : FLT_MAX, any, tt, pp);
-                    if (any) blocked = h;
-                    else { hit = h; t_hit = tt; prim_hit = pp; }
+                // the continuation vertex's direction / pixel / throughput / sample are known now;
+                // trace_kernel adds the hit point and primitive (or ends the path)
+                ray_shadow = kDiffuse && want_shadow;
+                ray_cont = cont;
+                if (cont) {
+                    a.dw[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
+                    a.tp[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
                 }
             }
-            if (kDiffuse && want_shadow && !blocked) {
+            if (ALL && kDiffuse && want_shadow && !blocked) {
                 ++lit;
                 // the old value came in with the prefetched state: store only, no stall
                 float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f;
@@ -849,12 +944,31 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 2) : 
                 }
             }
         }
-        if (!LAST) out.push(kind_next, slot);
+        if constexpr (ALL) {
+            if (!LAST) out.push(kind_next, slot);
+        } else {
+            // ray records: (origin, tmax) (direction, slot | kRayShadow | kRaySpecular) (light sample rgb)
+            const uint32_t is = warp_reserve(ray_cur, ray_shadow, ray_counter);
+            if (is != kInvalid) {
+                a.ray0[is] = make_float4(ray_o.x, ray_o.y, ray_o.z, ray_tmax);
+                a.ray1[is] = make_float4(ray_w.x, ray_w.y, ray_w.z, __uint_as_float(slot | kRayShadow));
+                a.ray2[is] = make_float4(ray_rgb.x, ray_rgb.y, ray_rgb.z, 0.0f);
+            }
+            const uint32_t ic = warp_reserve(ray_cur, ray_cont, ray_counter);
+            if (ic != kInvalid) {
+                a.ray0[ic] = make_float4(ray_o.x, ray_o.y, ray_o.z, FLT_MAX);
+                a.ray1[ic] = make_float4(ray_d.x, ray_d.y, ray_d.z, __uint_as_float(slot | ray_flags));
+            }
+        }
         s_cur = s_nxt; s_nxt = s_nn;
         buf ^= 1;
     }
     cp_async_wait<0>();
-    if (!LAST) out.flush();
+    if constexpr (ALL) {
+        if (!LAST) out.flush();
+    } else {
+        for (uint32_t i = ray_cur.pos + lane; i < ray_cur.end; i += 32u) a.ray1[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalid));
+    }
     calls = warp_sum(calls);
     traced = warp_sum(traced);
     shadow_rays = warp_sum(shadow_rays);
@@ -865,8 +979,104 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? (ALL ? 4 : 2) : 
         if (traced) atomicAdd(a.totals + 0, (unsigned long long)traced);
         if (shadow_rays) atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
         if (lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
-        if (kRad) atomicAdd(a.totals + 5, (unsigned long long)calls); // diffuse vertices that read L
+        if (kRadStat) atomicAdd(a.totals + 5, (unsigned long long)calls); // diffuse vertices that read L
     }
+}
+
+// ---- trace (tree scenes): persistent walk with dynamic ray fetch -----------------------------
+// One launch per bounce over the ray queue the bounce kernels filled. Every lane owns at most one
+// ray; a round = every lane with a ray walks to its next non-empty leaf and tests it (TreeWalk::step).
+// Lanes whose ray finished deliver the result -- shadow ray: add the light sample unless occluded;
+// continuation ray: hit point + primitive into the vertex record, slot into its material queue --
+// and, once PassArgs::refill lanes are idle, the warp pulls that many new rays with ONE atomic. A warp's
+// time is then the sum of its rays' rounds / 32, not 32 x the longest walk.
+
+__global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, const int bounce) {
+    const uint32_t n = a.counts[bounce * 4 + Q_RAYS];
+    if (n == 0) return;
+    const SceneAccess<false> S = stage_scene<false>(a);
+    const bool sort = bounce + 1 < a.max_depth;
+    const bool next_last = bounce + 2 >= a.max_depth;
+    Sorter out;
+    out.init(a, bounce + 1);
+    uint32_t* const fetch = a.counts + (kMaxPathDepth + 1) * 4 + bounce;
+    const uint32_t lane = threadIdx.x & 31u;
+    TreeWalk w = {};
+    bool have = false, more = true;
+    uint32_t tag = 0; // slot | flags of the lane's ray
+    float3 rgb = f3(0.f, 0.f, 0.f);
+    int pend_kind = -1;
+    uint32_t pend_slot = 0;
+    unsigned lit = 0;
+    while (true) {
+        // (converged) deliver the slots whose continuation ray found a surface
+        if (sort && __any_sync(kFull, pend_kind >= 0)) {
+            out.push(pend_kind, pend_slot);
+            pend_kind = -1;
+        }
+        const uint32_t idle = __ballot_sync(kFull, !have);
+        if (more && idle != 0u && (__popc(idle) >= a.refill || idle == kFull)) {
+            const uint32_t cnt = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(fetch, cnt);
+            base = __shfl_sync(kFull, base, 0);
+            if (base + cnt >= n) more = false; // the queue is drained (warp-uniform)
+            const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+            if (!have && i < n) {
+                const float4 r1 = a.ray1[i];
+                tag = __float_as_uint(r1.w);
+                if (tag != kInvalid) { // not the padding of a producer's last chunk
+                    const float4 r0 = a.ray0[i];
+                    const bool shadow = (tag & kRayShadow) != 0u;
+                    if (shadow) {
+                        const float4 r2 = a.ray2[i];
+                        rgb = f3(r2.x, r2.y, r2.z);
+                    }
+                    have = true;
+                    if (w.init(S, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, shadow)) have = false, pend_kind = -2; // finished at once
+                }
+            }
+        }
+        // a ray that finished inside init() (missed the root box / one-leaf scene) is delivered like any other
+        bool finished = pend_kind == -2;
+        if (finished) pend_kind = -1;
+        if (__ballot_sync(kFull, have || finished) == 0u) {
+            if (!more) break;
+            continue;
+        }
+        if (w.step(S, have)) { // all 32 lanes: one round
+            finished = true;
+            have = false;
+        }
+        if (finished) {
+            const uint32_t slot = tag & kRaySlotMask;
+            if (tag & kRayShadow) {
+                if (w.best_prim == kInvalid) { // unoccluded: the light sample counts
+                    ++lit;
+                    add_radiance(a, slot, rgb);
+                }
+            } else if (w.best_prim != kInvalid) {
+                const float4 t4 = S.hot_row(w.best_prim, 3);
+                const int bsdf = __float_as_int(t4.y);
+                if (bsdf == G19_BSDF_EMITTER) {
+                    // emission counts after specular bounces only (NEE covers the diffuse ones)
+                    if (tag & kRaySpecular) {
+                        const float4 T = a.tp[slot];
+                        const MaterialD& m = a.scene.materials[__float_as_int(t4.x)];
+                        add_radiance(a, slot, f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]));
+                    }
+                } else if (bsdf == G19_BSDF_DIFFUSE || !next_last) {
+                    const float3 p = w.o + w.d * w.best;
+                    a.hp[slot] = make_float4(p.x, p.y, p.z, __uint_as_float(w.best_prim));
+                    pend_kind = bsdf;
+                    pend_slot = slot;
+                }
+            }
+        }
+    }
+    if (sort) out.flush();
+    lit = warp_sum(lit);
+    if (lane == 0 && lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
 }
 
 // ---- accumulate / resolve ---------------------------------------------------------------
@@ -910,7 +1120,7 @@ __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) 
     }
     // the pass is over: clear its queue lengths for the next one
     if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < (kMaxPathDepth + 1) * 4; i += kThreads) a.counts[i] = 0;
+        for (int i = threadIdx.x; i < (kMaxPathDepth + 1) * 5; i += kThreads) a.counts[i] = 0; // queue lengths + fetch cursors
 }
 
 __global__ void __launch_bounds__(kThreads) resolve_kernel(TileMap map, const float* __restrict__ accum, int spp,
@@ -1009,11 +1219,21 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
     if (e != cudaSuccess) note_launch_error("raygen_extend kernel launch", e, smem, grid);
 }
 
+void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
+    const size_t smem = path_smem_bytes(a);
+    const int grid = persistent_grid(trace_kernel, smem, sm_count);
+    trace_kernel<<<grid, kThreads, smem, s>>>(a, bounce);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) note_launch_error("trace kernel launch", e, smem, grid);
+}
+
+bool path_scene_is_flat(const PassArgs& a) { return all_staged(a); }
+
 bool launch_bounce(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s) {
     const bool last = bounce + 1 >= a.max_depth;
     if (last && kind != Q_DIFFUSE) return false; // nothing to do: no launch
-    const size_t smem = path_smem_bytes(a);
     const bool all = all_staged(a);
+    const size_t smem = all ? path_smem_bytes(a) : 0; // tree scenes only shade here: no scene staging
     switch (kind) {
     case Q_DIFFUSE:
         if (all) launch_bounce_fl<Q_DIFFUSE, true>(a, bounce, smem, sm_count, s);

@@ -22,7 +22,7 @@
 #include "path.h"
 
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <chrono>
 #include <cmath>
@@ -40,7 +40,6 @@ struct Lane8 {
 struct Lane8Add {
     __host__ __device__ Lane8 operator()(const Lane8& a, const Lane8& b) const {
         Lane8 r;
-#pragma unroll
         for (int k = 0; k < 8; ++k) r.v[k] = a.v[k] + b.v[k];
         return r;
     }
@@ -48,7 +47,6 @@ struct Lane8Add {
 struct MaskToLanes {
     __host__ __device__ Lane8 operator()(uint8_t m) const {
         Lane8 r;
-#pragma unroll
         for (int k = 0; k < 8; ++k) r.v[k] = (m >> k) & 1u;
         return r;
     }
@@ -305,7 +303,7 @@ int path_build_tree_device(const float* d_boxes, uint32_t n_prims, const float r
         uint32_t Rn = 0;
         TB_CUDA(cudaMemcpyAsync(&Rn, f_off[nxt].as<uint32_t>() + Fn, 4, cudaMemcpyDeviceToHost, s));
         if (R) { // rank of every ref among its node's refs, per child: one exclusive scan of 8-lane counters
-            cub::TransformInputIterator<Lane8, MaskToLanes, const uint8_t*> lanes(mask.as<uint8_t>(), MaskToLanes());
+            auto lanes = thrust::make_transform_iterator(static_cast<const uint8_t*>(mask.as<uint8_t>()), MaskToLanes());
             size_t need = 0;
             Lane8 zero = {};
             TB_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, need, lanes, pos.as<Lane8>(), Lane8Add(), zero, R, s));
