@@ -1,7 +1,7 @@
 """ctypes mirror of include/g19.h (struct layouts and enum values only)."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enum g19_entity_kind (reference include/entities.h, one value per class)
 IMP_SPHERE, IMP_TRIANGLE, EXP_RECTANGLE, EXP_BOX, EXP_SPHERE, EXP_QUAD, EXP_CUBE, EXP_CONE = range(8)
@@ -52,7 +52,7 @@ class Camera(C.Structure):
 class Params(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mode", C.c_int32), ("spp", C.c_int32),
                 ("max_depth", C.c_int32), ("seed", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("spp_per_pass", C.c_int32), ("profile", C.c_int32)]
+                ("spp_per_pass", C.c_int32), ("profile", C.c_int32), ("pixels_per_pass", C.c_int32)]
 
 
 class Stats(C.Structure):

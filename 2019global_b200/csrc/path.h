@@ -129,7 +129,9 @@ struct PassArgs {
     int32_t spp_pass;      // samples in this pass
     int32_t sample_base;   // first sample index of this pass
     int32_t max_depth;
-    uint32_t n_slots;      // spp_pass * n_local_pix
+    uint32_t n_slots;      // spp_pass * pix_count
+    uint32_t pix_base;     // the pass covers local pixels [pix_base, pix_base + pix_count)
+    uint32_t pix_count;
     float4* hp;            // vertex: hit point, primitive
     float4* dw;            // vertex: incoming direction, pixel
     float4* tp;            // throughput, sample (not written for the camera segment: 1, slot / n_local_pix)

@@ -134,6 +134,14 @@ template <bool ALL> struct SceneAccess {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch: a pass is a chain of 7 to 40 short persistent kernels, each
+// depending on the previous one's queues. Every kernel lets its successor be scheduled as soon as
+// CTAs retire (launch_dependents, first instruction), does whatever does not depend on earlier
+// kernels (staging the scene into shared memory), and only then waits for the predecessor's
+// memory (griddepcontrol.wait): launch latency and prologue hide under the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Stage the scene prefix with TMA bulk copies (cp.async.bulk) completing on one mbarrier.
 template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(const PassArgs& a) {
     const PathSceneD& g = a.scene;
@@ -510,7 +518,8 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, uint32_t& r
 
 __device__ __forceinline__ bool slot_pixel(const PassArgs& a, uint32_t slot, int& x, int& y, uint32_t& sample) {
     uint32_t lp, tx;
-    uint32_t s = fast_div(slot, (uint32_t)a.map.n_local_pix, lp);
+    uint32_t s = fast_div(slot, a.pix_count, lp); // slot = sample in pass * window size + pixel in window
+    lp += a.pix_base;
     sample = (uint32_t)a.sample_base + s;
     uint32_t lt = lp >> 10, in = lp & 1023u;
     uint32_t t = lt * (uint32_t)a.map.world + (uint32_t)a.map.rank;
@@ -649,9 +658,11 @@ __device__ __forceinline__ void store_vertex(const PassArgs& a, uint32_t slot, f
 
 // ---- raygen + extend (camera segment) ------------------------------------------------
 template <bool ALL> __global__ void __launch_bounds__(kThreads, ALL ? 4 : 2) raygen_extend_kernel(const PassArgs a) {
+    pdl_launch_dependents();
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
     const SceneAccess<ALL> S = stage_scene<ALL>(a);
+    pdl_wait(); // the previous pass's accumulate cleared the queue lengths and the radiance planes
     Sorter out;
     out.init(a, 0);
     const uint32_t stride = gridDim.x * kThreads;
@@ -742,15 +753,17 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3)
     bounce_kernel(const PassArgs a, const int bounce) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
     constexpr bool kTp = !FIRST, kRadStat = !FIRST && kDiffuse, kRad = ALL && kRadStat; // tree scenes: trace_kernel adds the light sample
-    const uint32_t n = a.counts[bounce * 4 + KIND];
-    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave before staging anything
-    if (LAST && !kDiffuse) return;          // a specular vertex on the last segment contributes nothing
+    pdl_launch_dependents();
+    if (LAST && !kDiffuse) return; // a specular vertex on the last segment contributes nothing
     // Flat scenes trace their rays right here. Tree scenes only shade: their rays go to the bounce's
     // ray queue and trace_kernel walks them with dynamic fetch (a heavy tail of long walks would
     // otherwise hold the other 31 lanes of the warp -- ncu: 3.4 of 32 lanes active).
     SceneAccess<ALL> S;
-    if constexpr (ALL) S = stage_scene<ALL>(a);
+    if constexpr (ALL) S = stage_scene<ALL>(a); // does not depend on earlier kernels: overlaps their tail
     else S.g = &a.scene;
+    pdl_wait();
+    const uint32_t n = a.counts[bounce * 4 + KIND];
+    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     const uint32_t* __restrict__ qin = a.q[(bounce & 1) * 3 + (KIND - 1)];
     Sorter out;
     if (ALL && !LAST) out.init(a, bounce + 1);
@@ -792,7 +805,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3)
             uint32_t sample;
             if (FIRST) {
                 uint32_t lp;
-                sample = uint32_t(a.sample_base) + fast_div(slot, uint32_t(a.map.n_local_pix), lp);
+                sample = uint32_t(a.sample_base) + fast_div(slot, a.pix_count, lp);
             } else {
                 const float4 tp = stage.tp[buf][tid];
                 T = f3(tp.x, tp.y, tp.z);
@@ -992,9 +1005,11 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3)
 // time is then the sum of its rays' rounds / 32, not 32 x the longest walk.
 
 __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, const int bounce) {
+    pdl_launch_dependents();
+    const SceneAccess<false> S = stage_scene<false>(a);
+    pdl_wait();
     const uint32_t n = a.counts[bounce * 4 + Q_RAYS];
     if (n == 0) return;
-    const SceneAccess<false> S = stage_scene<false>(a);
     const bool sort = bounce + 1 < a.max_depth;
     const bool next_last = bounce + 2 >= a.max_depth;
     Sorter out;
@@ -1081,25 +1096,28 @@ __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, co
 
 // ---- accumulate / resolve ---------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) {
-    const uint32_t npix = (uint32_t)a.map.n_local_pix;
-    const uint32_t lp = blockIdx.x * kThreads + threadIdx.x;
-    if (lp < npix) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t npix = (uint32_t)a.map.n_local_pix, nwin = a.pix_count;
+    const uint32_t wp = blockIdx.x * kThreads + threadIdx.x; // pixel within the pass's window
+    if (wp < nwin) {
+        const uint32_t lp = a.pix_base + wp;
         float acc0 = a.accum[lp], acc1 = a.accum[(size_t)npix + lp], acc2 = a.accum[2 * (size_t)npix + lp];
-        float* L0 = a.L + lp;
-        float* L1 = a.L + a.plane + lp;
-        float* L2 = a.L + 2 * a.plane + lp;
+        float* L0 = a.L + wp;
+        float* L1 = a.L + a.plane + wp;
+        float* L2 = a.L + 2 * a.plane + wp;
         // strictly in sample order (independent of the pass split); loads batched four samples deep
         int s = 0;
         for (; s + 4 <= a.spp_pass; s += 4) {
             float v0[4], v1[4], v2[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                size_t i = (size_t)(s + k) * npix;
+                size_t i = (size_t)(s + k) * nwin;
                 v0[k] = L0[i]; v1[k] = L1[i]; v2[k] = L2[i];
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                size_t i = (size_t)(s + k) * npix;
+                size_t i = (size_t)(s + k) * nwin;
                 acc0 += v0[k]; acc1 += v1[k]; acc2 += v2[k];
                 if (v0[k] != 0.0f) L0[i] = 0.0f;
                 if (v1[k] != 0.0f) L1[i] = 0.0f;
@@ -1107,7 +1125,7 @@ __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) 
             }
         }
         for (; s < a.spp_pass; ++s) {
-            size_t i = (size_t)s * npix;
+            size_t i = (size_t)s * nwin;
             float v0 = L0[i], v1 = L1[i], v2 = L2[i];
             acc0 += v0; acc1 += v1; acc2 += v2;
             if (v0 != 0.0f) L0[i] = 0.0f;
@@ -1185,12 +1203,28 @@ template <typename K> static int persistent_grid(K kernel, size_t smem, int sm_c
     return grid;
 }
 
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in
+// the stream drains; it synchronises with pdl_wait() itself.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int KIND, bool FIRST, bool LAST, bool ALL>
 static void launch_bounce_k(const PassArgs& a, int bounce, size_t smem, int sm_count, cudaStream_t s) {
     auto kernel = bounce_kernel<KIND, FIRST, LAST, ALL>;
     const int grid = persistent_grid(kernel, smem, sm_count);
-    kernel<<<grid, kThreads, smem, s>>>(a, bounce);
-    cudaError_t e = cudaPeekAtLastError();
+    cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);
     if (e != cudaSuccess) note_launch_error("bounce kernel launch", e, smem, grid);
 }
 
@@ -1210,20 +1244,18 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
     int grid;
     if (all_staged(a)) {
         grid = persistent_grid(raygen_extend_kernel<true>, smem, sm_count);
-        raygen_extend_kernel<true><<<grid, kThreads, smem, s>>>(a);
+        e = launch_pdl(raygen_extend_kernel<true>, grid, smem, s, a);
     } else {
         grid = persistent_grid(raygen_extend_kernel<false>, smem, sm_count);
-        raygen_extend_kernel<false><<<grid, kThreads, smem, s>>>(a);
+        e = launch_pdl(raygen_extend_kernel<false>, grid, smem, s, a);
     }
-    e = cudaPeekAtLastError();
     if (e != cudaSuccess) note_launch_error("raygen_extend kernel launch", e, smem, grid);
 }
 
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a);
     const int grid = persistent_grid(trace_kernel, smem, sm_count);
-    trace_kernel<<<grid, kThreads, smem, s>>>(a, bounce);
-    cudaError_t e = cudaPeekAtLastError();
+    cudaError_t e = launch_pdl(trace_kernel, grid, smem, s, a, bounce);
     if (e != cudaSuccess) note_launch_error("trace kernel launch", e, smem, grid);
 }
 
@@ -1255,9 +1287,10 @@ const char* path_launch_error() { return g_launch_error[0] ? g_launch_error : nu
 void path_clear_launch_error() { g_launch_error[0] = 0; }
 
 void launch_accumulate(const PassArgs& a, cudaStream_t s) {
-    int blocks = (a.map.n_local_pix + kThreads - 1) / kThreads;
+    int blocks = int((a.pix_count + kThreads - 1) / kThreads);
     if (blocks < 1) blocks = 1;
-    accumulate_kernel<<<blocks, kThreads, 0, s>>>(a);
+    cudaError_t e = launch_pdl(accumulate_kernel, blocks, 0, s, a);
+    if (e != cudaSuccess) note_launch_error("accumulate kernel launch", e, 0, blocks);
 }
 
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s) {

@@ -249,8 +249,9 @@ class RayTracer:
         self._running = False
         self._L.g19_cancel(self.h)
 
-    def params(self, w, h, mode=abi.MODE_REF, spp=1, max_depth=1, seed=0, rank=0, world=1, spp_per_pass=0, profile=0):
-        return abi.Params(w, h, mode, spp, max_depth, seed, rank, world, spp_per_pass, profile)
+    def params(self, w, h, mode=abi.MODE_REF, spp=1, max_depth=1, seed=0, rank=0, world=1, spp_per_pass=0, profile=0,
+               pixels_per_pass=0):
+        return abi.Params(w, h, mode, spp, max_depth, seed, rank, world, spp_per_pass, profile, pixels_per_pass)
 
     def run(self, w, h, mode=abi.MODE_REF, want=("rgb",), out=None, **kw):
         """Blocking render into host arrays (the reference's run(w,h)). Returns a dict of numpy arrays."""

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define G19_ABI_VERSION 2
+#define G19_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -153,6 +153,9 @@ typedef struct g19_params {
     int32_t rank, world;
     int32_t spp_per_pass;  /* PATH: samples per wavefront pass (0 = auto)   */
     int32_t profile;       /* 1: time every kernel class with CUDA events   */
+    int32_t pixels_per_pass; /* PATH: pixels of this rank per wavefront pass, in whole
+                              32x32 tiles (0 = auto: the whole frame, or windows of it when
+                              the per-path state would outgrow the L2 cache)            */
 } g19_params;
 
 typedef struct g19_stats {

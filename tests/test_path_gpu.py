@@ -89,6 +89,11 @@ def test_deterministic_and_pass_invariant(g19, abi):
     for spp_pass in (1, 5, 12):
         c = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=12, max_depth=8, seed=5, spp_per_pass=spp_pass)
         assert a["radiance"].tobytes() == c["radiance"].tobytes(), spp_pass
+    # ... and of the pixel window a pass covers (whole 32x32 tiles of the rank's pixels)
+    for ppp, spp_pass in ((1024, 0), (3000, 5), (4096, 1)):
+        c = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=12, max_depth=8, seed=5, spp_per_pass=spp_pass,
+                   pixels_per_pass=ppp)
+        assert a["radiance"].tobytes() == c["radiance"].tobytes(), (ppp, spp_pass)
     d = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=12, max_depth=8, seed=6)
     assert a["radiance"].tobytes() != d["radiance"].tobytes()
 

@@ -15,6 +15,8 @@ ap.add_argument("--h", type=int, default=1080)
 ap.add_argument("--mode", default="PATH")
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--profile", type=int, default=0)
+ap.add_argument("--spp-per-pass", type=int, default=0)
+ap.add_argument("--pixels-per-pass", type=int, default=0)
 a = ap.parse_args()
 g19 = importlib.import_module("2019global_b200")
 abi = g19.abi
@@ -23,7 +25,7 @@ rt = g19.RayTracer(cam, light, device=0)
 rt.setScene(sc)
 rt.start()
 for _ in range(a.frames):
-    out = rt.run(a.w, a.h, mode=getattr(abi, "MODE_" + a.mode), want=("rgb",), spp=a.spp, max_depth=a.depth, seed=0, profile=a.profile)
+    out = rt.run(a.w, a.h, mode=getattr(abi, "MODE_" + a.mode), want=("rgb",), spp=a.spp, max_depth=a.depth, seed=0, profile=a.profile, spp_per_pass=a.spp_per_pass, pixels_per_pass=a.pixels_per_pass)
 st = rt.stats()
 print("ok: %.2f ms, %d samples, %d extend, %d shadow segments, %d launches" % (
     st.render_ms, st.samples, st.extend_segments, st.shadow_segments, st.kernel_launches))
