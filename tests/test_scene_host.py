@@ -23,7 +23,7 @@ def test_abi_struct_sizes(g19, abi):
     # mirrors of include/g19.h: g19_entity_desc, g19_camera, g19_params
     assert ctypes.sizeof(abi.EntityDesc) == 8 + 72 + 16 + 24 + 12 + 4
     assert ctypes.sizeof(abi.Camera) == 56
-    assert ctypes.sizeof(abi.Params) == 40
+    assert ctypes.sizeof(abi.Params) == 44
 
 
 def test_entity_geometry_matches_oracle_bits(g19, oracle):
