@@ -466,7 +466,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
     for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &w.hp, &w.dw, &w.tp,
-                           &w.L, &w.queues, &w.rays, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
+                           &w.L, &w.queues, &w.recs, &w.rays, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
         d->release();
     if (w.events) {
         for (int i = 0; i < w.n_events; ++i) cudaEventDestroy(w.events[i]);
@@ -505,13 +505,17 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     cudaStream_t s = a.stream;
     const size_t npix = size_t(a.map.n_local_pix);
     if (npix == 0) return G19_OK;
-    // Pass size: enough slots to fill the machine, few enough for the 60-byte-per-slot state to stay
-    // L2-resident (126 MB). Measured: the glass Cornell at depth 12 renders a 1080p frame in 82 / 97 /
-    // 116 / 146 ms with 2 / 4 / 8 / 33 M slots per pass -- deep bounces touch their slots sparsely, so
-    // they live off the cache; the depth-5 diffuse box is flat between 2 M and 8 M and 4 % slower at 2 M.
+    // Pass size. Flat scenes keep dense vertex records in their queues, so a bounce streams exactly
+    // the live vertices whatever the pass size: bigger passes only amortise launch tails (measured on
+    // B200, ms per 1080p x 64 spp frame at 2 / 4 / 8 / 16 M slots: Cornell depth 5 22.3 / 20.9 / 20.2 /
+    // 20.2, glass Cornell depth 12 64.4 / 52.0 / 47.7 / 49.3). Tree scenes still index their state by
+    // slot: deep bounces touch it sparsely and live off the L2 (126 MB), so their passes stay small.
     // A pass covers a WINDOW of the rank's pixels (whole 32x32 tiles) times spp_pass samples; frames
     // larger than the target are rendered window by window.
-    const size_t target = p.max_depth > 6 ? (size_t(1) << 21) : (size_t(1) << 22);
+    const bool flat_scene = b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= 192 &&
+                            b.view.n_lights <= 32;
+    size_t target = flat_scene ? (size_t(1) << 23) : (p.max_depth > 6 ? (size_t(1) << 21) : (size_t(1) << 22));
+    if (const char* v = std::getenv("G19_PASS_SLOTS")) target = std::max<size_t>(kTilePix, size_t(std::atoll(v))); // tuning knob
     size_t window = npix;
     if (p.pixels_per_pass > 0) window = std::min(npix, (size_t(p.pixels_per_pass) + kTilePix - 1) / kTilePix * kTilePix);
     else if (npix > target) window = target;
@@ -532,9 +536,6 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         }                                                                      \
     } while (0)
     if (P > w.capacity) {
-        PATH_CUDA(w.hp.ensure(P * sizeof(float4)));
-        PATH_CUDA(w.dw.ensure(P * sizeof(float4)));
-        PATH_CUDA(w.tp.ensure(P * sizeof(float4)));
         PATH_CUDA(w.L.ensure(P * 3 * sizeof(float)));
         PATH_CUDA(w.queues.ensure((P + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
         w.capacity = P;
@@ -567,9 +568,6 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa.map = a.map;
     pa.seed = p.seed;
     pa.max_depth = p.max_depth;
-    pa.hp = static_cast<float4*>(w.hp.p);
-    pa.dw = static_cast<float4*>(w.dw.p);
-    pa.tp = static_cast<float4*>(w.tp.p);
     pa.L = static_cast<float*>(w.L.p);
     pa.plane = plane;
     pa.queue_cap = plane + kQueueSlack;
@@ -595,6 +593,25 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     if (const char* v = std::getenv("G19_REFILL")) pa.refill = std::max(1, std::min(32, std::atoi(v))); // tuning knob
     const bool fused = path_scene_is_flat(pa); // flat scenes trace inside the bounce kernels
     pa.ray0 = pa.ray1 = pa.ray2 = nullptr;
+    pa.hp = pa.dw = pa.tp = nullptr;
+    pa.rec_hp = pa.rec_dw = pa.rec_tp = nullptr;
+    pa.rec_L = nullptr;
+    if (fused) {
+        // dense vertex records: three float4 planes and three float planes per queue
+        const size_t cap = pa.queue_cap, nq = kNumQueues;
+        PATH_CUDA(w.recs.ensure(nq * cap * (3 * sizeof(float4) + 3 * sizeof(float))));
+        pa.rec_hp = static_cast<float4*>(w.recs.p);
+        pa.rec_dw = pa.rec_hp + nq * cap;
+        pa.rec_tp = pa.rec_dw + nq * cap;
+        pa.rec_L = reinterpret_cast<float*>(pa.rec_tp + nq * cap);
+    } else {
+        PATH_CUDA(w.hp.ensure(plane * sizeof(float4)));
+        PATH_CUDA(w.dw.ensure(plane * sizeof(float4)));
+        PATH_CUDA(w.tp.ensure(plane * sizeof(float4)));
+        pa.hp = static_cast<float4*>(w.hp.p);
+        pa.dw = static_cast<float4*>(w.dw.p);
+        pa.tp = static_cast<float4*>(w.tp.p);
+    }
     if (!fused) {
         const size_t ray_cap = 2 * plane + kQueueSlack;
         PATH_CUDA(w.rays.ensure(3 * ray_cap * sizeof(float4)));
@@ -716,6 +733,7 @@ int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
     stats.shade_calls_first = h[3];
     stats.lit_samples = h[4];
     stats.radiance_reads = h[5];
+    stats.radiance_stores = h[6];
     for (int i = 0; i + 1 < w.used_events; i += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, w.events[i], w.events[i + 1]) == cudaSuccess) stats.class_ms[w.event_class[i / 2]] += ms;

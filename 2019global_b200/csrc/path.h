@@ -72,6 +72,8 @@ struct PathWork {
     DeviceArray tp;            // float4[P]: throughput.rgb, sample index bits
     DeviceArray L;             // float[3][P]: radiance gathered by the path so far
     DeviceArray queues;        // uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
+    DeviceArray recs;          // flat scenes: float4[3][6][P + slack] + float[6][3][P + slack] dense vertex records
+    size_t rec_capacity = 0;
     DeviceArray rays;          // float4[3][2P + slack]: ray queue of one bounce (tree scenes only)
     DeviceArray counts;        // uint32[kMaxPathDepth+1][5]: queue lengths per bounce + ray fetch cursors
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
@@ -140,6 +142,13 @@ struct PassArgs {
     uint32_t* q[6];        // [bounce parity * 3 + (kind - 1)]
     uint32_t kind_mask;    // bit (kind - 1): the scene has a material of that class
     size_t queue_cap;      // entries per queue (P + chunk slack)
+    // flat scenes: the queues hold the vertex records themselves (dense, 64 B per vertex); queue
+    // qi = bounce parity * 3 + (kind - 1) starts at qi * queue_cap in each plane. hp/dw/tp/q above
+    // then serve tree scenes only (slot-indexed), L is the accumulator input either way.
+    float4* rec_hp;        // hit point, primitive
+    float4* rec_dw;        // incoming direction, pixel
+    float4* rec_tp;        // throughput, sample
+    float* rec_L;          // radiance so far: 3 planes of queue_cap per queue
     float4* ray0;          // tree scenes: the bounce's ray queue (origin, tmax)
     float4* ray1;          //   (direction, slot | flags)
     float4* ray2;          //   (light sample rgb) of shadow rays

@@ -656,12 +656,12 @@ __device__ __forceinline__ void store_vertex(const PassArgs& a, uint32_t slot, f
     a.dw[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
 }
 
-// ---- raygen + extend (camera segment) ------------------------------------------------
-template <bool ALL> __global__ void __launch_bounds__(kThreads, ALL ? 4 : 2) raygen_extend_kernel(const PassArgs a) {
+// ---- raygen + extend (camera segment), tree scenes: slot-indexed state ----------------------
+__global__ void __launch_bounds__(kThreads, 2) raygen_extend_kernel(const PassArgs a) {
     pdl_launch_dependents();
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
-    const SceneAccess<ALL> S = stage_scene<ALL>(a);
+    const SceneAccess<false> S = stage_scene<false>(a);
     pdl_wait(); // the previous pass's accumulate cleared the queue lengths and the radiance planes
     Sorter out;
     out.init(a, 0);
@@ -684,7 +684,7 @@ template <bool ALL> __global__ void __launch_bounds__(kThreads, ALL ? 4 : 2) ray
         }
         float t;
         uint32_t prim;
-        if (nearest<ALL>(S, live, o, d, t, prim)) { // all 32 lanes walk together
+        if (nearest<false>(S, live, o, d, t, prim)) { // all 32 lanes walk together
             const float4 tag = S.hot_row(prim, 3);
             const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
             if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
@@ -709,18 +709,6 @@ __device__ __forceinline__ void onb(float3 n, float3& t, float3& b) { // Duff et
     b = f3(bb, s + n.y * n.y * a, -n.y);
 }
 
-// Asynchronous prefetch of the NEXT slot's state into shared memory (LDGSTS): a register
-// prefetch gets sunk to its first use by the compiler (ncu: 20 % of the kernel's stall samples
-// sat on that one instruction); a cp.async cannot be, and it holds no registers while in flight.
-// Two buffers per thread, each thread only ever touches its own column. On the camera segment
-// throughput is 1 and the slot's radiance is still zero, so neither is read.
-template <bool TP, bool RAD> struct VertexStage {
-    float4 hp[2][kThreads];
-    float4 dw[2][kThreads];
-    float4 tp[TP ? 2 : 1][TP ? kThreads : 1];
-    float L[RAD ? 2 : 1][3][RAD ? kThreads : 1];
-};
-
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
@@ -730,17 +718,243 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool TP, bool RAD>
-__device__ __forceinline__ void prefetch_vertex(const PassArgs& a, uint32_t slot, VertexStage<TP, RAD>& st, int buf) {
+// ---- shading of one path vertex (shared by the flat-scene and the tree-scene bounce kernels) ----
+// In: the vertex (hit point p on primitive prim, arrival direction d, throughput T). Out: the
+// next-event sample (direction w, length tmax_s, radiance lit_rgb if it turns out unoccluded) and
+// the continuation ray (origin no, direction nd, throughput T updated). flags bit 0: specular.
+struct Shaded {
+    float3 no, nd, w, lit_rgb, T;
+    float tmax_s;
+    bool want_shadow;
+    uint32_t flags;
+};
+template <int KIND, bool LAST, bool ALL>
+__device__ __forceinline__ Shaded shade_vertex(const PassArgs& a, const SceneAccess<ALL>& S, int bounce, float3 p, float3 d,
+                                               float3 T, uint32_t prim, uint32_t pixel, uint32_t sample) {
+    constexpr bool kDiffuse = KIND == Q_DIFFUSE;
+    Shaded o;
+    float4 c0, c1; // (normal, ior), (albedo, material)
+    S.cold(prim, c0, c1);
+    float3 ng = f3(c0.x, c0.y, c0.z);
+    if (c0.x == 0.0f && c0.y == 0.0f && c0.z == 0.0f) { // spheres store no normal: (p - centre) / r
+        const float4 q0 = S.hot_row(prim, 0);
+        ng = (p - f3(q0.x, q0.y, q0.z)) * __fdividef(1.0f, q0.w);
+    }
+    const float ior = c0.w;
+    const bool entering = dot(ng, d) < 0.0f;
+    const float3 nf = entering ? ng : -ng; // normal on the side the ray arrives from
+    const float3 albedo = f3(c1.x, c1.y, c1.z);
+    const uint4 r = philox(pixel, sample, uint32_t(bounce), 1u, a.seed);
+    o.nd = f3(0.f, 0.f, 1.f);
+    o.flags = 0;
+    o.want_shadow = false;
+    o.w = f3(0.f, 0.f, 1.f);
+    o.lit_rgb = f3(0.f, 0.f, 0.f);
+    o.tmax_s = -1.0f;
+    if (kDiffuse) {
+        // next-event estimation (diffuse only): one light, one uniformly sampled point
+        if (a.scene.n_lights > 0) {
+            float pick = u01(r.x) * float(a.scene.n_lights);
+            int li = min(int(pick), a.scene.n_lights - 1);
+            float u1 = pick - float(li), u2 = u01(r.y);
+            const float4* lt = S.light(li);
+            const float4 l0 = lt[0], l1 = lt[1], l2 = lt[2], l3 = lt[3];
+            float su = sqrtf(u1);
+            float b1 = su * (1.0f - u2), b2 = su * u2;
+            float3 yl = f3(l0.x + l1.x * b1 + l2.x * b2, l0.y + l1.y * b1 + l2.y * b2, l0.z + l1.z * b1 + l2.z * b2);
+            float3 w = yl - p;
+            float dist2 = dot(w, w);
+            float inv_dist = rsqrtf(dist2);
+            float dist = dist2 * inv_dist;
+            w = w * inv_dist;
+            o.w = w;
+            float cs = dot(nf, w);
+            float cl = fabsf(dot(f3(l3.x, l3.y, l3.z), w));
+            if (cs > 0.0f && cl > 0.0f && dist > 2.0f * kRayEps) {
+                o.want_shadow = true;
+                o.tmax_s = dist - 2.0f * kRayEps;
+                const float4 l4 = lt[4];
+                float gterm = cs * cl * l0.w * __fdividef(1.0f, dist2 * l1.w) * (1.0f / kPi);
+                o.lit_rgb = f3(T.x * albedo.x * l4.x * gterm, T.y * albedo.y * l4.y * gterm, T.z * albedo.z * l4.z * gterm);
+            }
+        }
+        o.no = p + nf * kRayEps;
+        if (!LAST) { // cosine-weighted bounce: pdf cancels cos/pi, throughput *= albedo
+            float u3 = u01(r.z), u4 = u01(r.w);
+            float rr = sqrtf(u3), phi = 2.0f * kPi * u4 - kPi; // [-pi, pi): MUFU range
+            float sp, cp;
+            __sincosf(phi, &sp, &cp);
+            sp = -sp; cp = -cp; // shift back by pi
+            float3 tx, ty;
+            onb(nf, tx, ty);
+            o.nd = normalize(tx * (rr * cp) + ty * (rr * sp) + nf * sqrtf(fmaxf(0.0f, 1.0f - u3)));
+        }
+        o.T = T * albedo;
+    } else if (KIND == Q_MIRROR) {
+        o.nd = normalize(d - nf * (2.0f * dot(d, nf)));
+        o.no = p + nf * kRayEps;
+        o.T = T * albedo;
+        o.flags = 1u;
+    } else { // dielectric
+        float etai = entering ? 1.0f : ior, etat = entering ? ior : 1.0f;
+        float eta = etai / etat;
+        float cosi = fminf(1.0f, -dot(d, nf));
+        float sin2t = eta * eta * fmaxf(0.0f, 1.0f - cosi * cosi);
+        float F = 1.0f;
+        float cost = 0.0f;
+        if (sin2t < 1.0f) {
+            cost = sqrtf(1.0f - sin2t);
+            float rs = (etai * cosi - etat * cost) / (etai * cosi + etat * cost);
+            float rp = (etai * cost - etat * cosi) / (etai * cost + etat * cosi);
+            F = 0.5f * (rs * rs + rp * rp);
+        }
+        if (u01(r.x) < F) {
+            o.nd = normalize(d + nf * (2.0f * cosi));
+            o.no = p + nf * kRayEps;
+        } else {
+            o.nd = normalize(d * eta + nf * (eta * cosi - cost));
+            o.no = p - nf * kRayEps;
+        }
+        o.T = T * albedo;
+        o.flags = 1u;
+    }
+    return o;
+}
+
+// ---- flat scenes: dense vertex records --------------------------------------------------
+// What the ncu capture of the slot-indexed state showed (profiles/r01c_ncu_pass_summary.json): the four
+// diffuse bounce launches of a Cornell pass execute 100 / 93 / 83 / 73 M warp instructions but all
+// take ~128 us -- as paths end, the survivors' slots thin out, every 16-byte state record still
+// costs a 32-byte sector (global load sectors per launch stay at 8 M), DRAM channel load becomes
+// uneven and long-scoreboard stalls grow 0.55 -> 1.97 per issue. So the QUEUES now hold the records
+// themselves: a vertex is written at the position its warp reserved in the next bounce's material
+// queue (slot, hit point + primitive, direction + pixel, throughput + sample, radiance so far --
+// 64 bytes, all planes coalesced) and read back from consecutive addresses; the path's radiance
+// travels with it and is stored to the slot's accumulator input exactly once, when the path ends.
+struct RecView {
+    uint32_t* slot;
+    float4 *hp, *dw, *tp;
+    float* L; // 3 planes of `cap`
+    size_t cap;
+};
+__device__ __forceinline__ RecView rec_queue(const PassArgs& a, int qi) { // qi = bounce parity * 3 + (kind - 1)
+    RecView r;
+    const size_t off = size_t(qi) * a.queue_cap;
+    r.slot = a.q[qi];
+    r.hp = a.rec_hp + off;
+    r.dw = a.rec_dw + off;
+    r.tp = a.rec_tp + off;
+    r.L = a.rec_L + 3 * off;
+    r.cap = a.queue_cap;
+    return r;
+}
+
+struct RecSorter { // the three record queues a launch feeds (the next bounce's)
+    WarpCursor cur[3];
+    uint32_t* counters;
+    uint32_t mask;
+    int set;
+    __device__ __forceinline__ void init(const PassArgs& a, int next_bounce) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cur[k] = WarpCursor{0, 0};
+        set = (next_bounce & 1) * 3;
+        counters = a.counts + next_bounce * 4 + Q_DIFFUSE;
+        mask = a.kind_mask;
+    }
+    // kind: G19_BSDF_DIFFUSE / MIRROR / GLASS, or -1 for "path ended". Returns the lane's position in
+    // its kind's queue (kInvalid for ended paths). Called by all 32 lanes.
+    __device__ __forceinline__ uint32_t reserve(int kind) {
+        uint32_t pos = kInvalid;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (mask & (1u << k)) {
+                const uint32_t p = warp_reserve(cur[k], kind == k, counters + k);
+                if (kind == k) pos = p;
+            }
+        return pos;
+    }
+    __device__ __forceinline__ void flush(const PassArgs& a) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (mask & (1u << k)) warp_flush(cur[k], a.q[set + k]);
+    }
+};
+
+// ---- raygen + extend, flat scenes ------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 4) raygen_extend_flat_kernel(const PassArgs a) {
+    pdl_launch_dependents();
+    const uint32_t n = a.n_slots;
+    if (blockIdx.x * kThreads >= n) return;
+    const SceneAccess<true> S = stage_scene<true>(a);
+    pdl_wait(); // the previous pass's accumulate cleared the queue lengths and the radiance planes
+    RecSorter out;
+    out.init(a, 0);
+    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q - lane < n; q += stride) { // warp-uniform trip count
+        const uint32_t slot = q;
+        int kind = -1;
+        bool live = false;
+        uint32_t pixel = 0, prim = kInvalid;
+        float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
+        float t = 0.0f;
+        if (q < n) {
+            int x, y;
+            uint32_t sample;
+            live = slot_pixel(a, slot, x, y, sample);
+            if (live) {
+                pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
+                camera_ray(a, x, y, pixel, sample, o, d);
+            }
+        }
+        if (nearest<true>(S, live, o, d, t, prim)) {
+            const float4 tag = S.hot_row(prim, 3);
+            const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
+            if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
+                const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
+                a.L[slot] = m.emission[0];
+                a.L[a.plane + slot] = m.emission[1];
+                a.L[2 * a.plane + slot] = m.emission[2];
+            } else if (bsdf == G19_BSDF_DIFFUSE || a.max_depth > 1) {
+                kind = bsdf;
+            }
+        }
+        const uint32_t pos = out.reserve(kind);
+        if (pos != kInvalid) { // throughput is 1 and the radiance 0 on the camera segment: not stored
+            const RecView r = rec_queue(a, kind);
+            const float3 p = o + d * t;
+            r.slot[pos] = slot;
+            r.hp[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(prim));
+            r.dw[pos] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+        }
+    }
+    out.flush(a);
+}
+
+// Asynchronous prefetch of the NEXT record into shared memory (LDGSTS): a register prefetch gets
+// sunk to its first use by the compiler (ncu: 20 % of the kernel's stall samples sat on that one
+// instruction); a cp.async cannot be, and it holds no registers while in flight. Two buffers per
+// thread, each thread only ever touches its own column. The records are dense, so the address of
+// the next one is known without loading anything first.
+template <bool FULL> struct RecStage {
+    uint32_t slot[2][kThreads];
+    float4 hp[2][kThreads];
+    float4 dw[2][kThreads];
+    float4 tp[FULL ? 2 : 1][FULL ? kThreads : 1];
+    float L[FULL ? 2 : 1][3][FULL ? kThreads : 1];
+};
+template <bool FULL>
+__device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, bool valid, RecStage<FULL>& st, int buf) {
     const int t = threadIdx.x;
-    if (slot != kInvalid) {
-        cp_async16(&st.hp[buf][t], a.hp + slot);
-        cp_async16(&st.dw[buf][t], a.dw + slot);
-        if (TP) cp_async16(&st.tp[buf][t], a.tp + slot);
-        if (RAD) {
-            cp_async4(&st.L[buf][0][t], a.L + slot);
-            cp_async4(&st.L[buf][1][t], a.L + a.plane + slot);
-            cp_async4(&st.L[buf][2][t], a.L + 2 * a.plane + slot);
+    if (valid) {
+        cp_async4(&st.slot[buf][t], r.slot + pos);
+        cp_async16(&st.hp[buf][t], r.hp + pos);
+        cp_async16(&st.dw[buf][t], r.dw + pos);
+        if (FULL) {
+            cp_async16(&st.tp[buf][t], r.tp + pos);
+            cp_async4(&st.L[buf][0][t], r.L + pos);
+            cp_async4(&st.L[buf][1][t], r.L + r.cap + pos);
+            cp_async4(&st.L[buf][2][t], r.L + 2 * r.cap + pos);
         }
     }
     cp_async_commit();
@@ -748,33 +962,177 @@ __device__ __forceinline__ void prefetch_vertex(const PassArgs& a, uint32_t slot
 
 // KIND: Q_DIFFUSE / Q_MIRROR / Q_GLASS. FIRST: the vertex of the camera segment. LAST: the path's
 // final segment ended here -- next-event estimation only, no continuation.
-template <int KIND, bool FIRST, bool LAST, bool ALL>
-__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3)
-    bounce_kernel(const PassArgs a, const int bounce) {
+// One launch per material queue and bounce: next-event estimation, BSDF sample, the trace of BOTH
+// rays in one loop over the staged primitives, and the new vertex record written straight into
+// the next bounce's material queue.
+template <int KIND, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_flat_kernel(const PassArgs a, const int bounce) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
-    constexpr bool kTp = !FIRST, kRadStat = !FIRST && kDiffuse, kRad = ALL && kRadStat; // tree scenes: trace_kernel adds the light sample
     pdl_launch_dependents();
     if (LAST && !kDiffuse) return; // a specular vertex on the last segment contributes nothing
-    // Flat scenes trace their rays right here. Tree scenes only shade: their rays go to the bounce's
-    // ray queue and trace_kernel walks them with dynamic fetch (a heavy tail of long walks would
-    // otherwise hold the other 31 lanes of the warp -- ncu: 3.4 of 32 lanes active).
-    SceneAccess<ALL> S;
-    if constexpr (ALL) S = stage_scene<ALL>(a); // does not depend on earlier kernels: overlaps their tail
-    else S.g = &a.scene;
+    const SceneAccess<true> S = stage_scene<true>(a); // does not depend on earlier kernels: overlaps their tail
+    pdl_wait();
+    const uint32_t n = a.counts[bounce * 4 + KIND];
+    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
+    const RecView in = rec_queue(a, (bounce & 1) * 3 + (KIND - 1));
+    RecSorter out;
+    if (!LAST) out.init(a, bounce + 1);
+    unsigned traced = 0, shadow_rays = 0, lit = 0, calls = 0, stored = 0;
+    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int tid = threadIdx.x;
+    const bool next_last = bounce + 2 >= a.max_depth;
+
+    __shared__ RecStage<!FIRST> stage;
+    uint32_t q = blockIdx.x * kThreads + threadIdx.x;
+    int buf = 0;
+    prefetch_rec(in, q, q < n, stage, 0);
+    for (; q - lane < n; q += stride) {
+        const uint32_t qn = q + stride;
+        prefetch_rec(in, qn, qn < n && qn > q, stage, buf ^ 1); // next record, in flight during this body
+        cp_async_wait<1>();                                     // this record has landed
+        const uint32_t slot = q < n ? stage.slot[buf][tid] : kInvalid;
+        int kind_next = -1;
+        float3 p_next = f3(0.f, 0.f, 0.f), d_next = f3(0.f, 0.f, 1.f), T = f3(1.f, 1.f, 1.f), Lp = f3(0.f, 0.f, 0.f);
+        uint32_t prim_next = kInvalid, pixel = 0, sample = 0;
+        if (slot != kInvalid) {
+            ++calls;
+            const float4 hp = stage.hp[buf][tid], dw = stage.dw[buf][tid];
+            const float3 p = f3(hp.x, hp.y, hp.z), d = f3(dw.x, dw.y, dw.z);
+            const uint32_t prim = __float_as_uint(hp.w);
+            pixel = __float_as_uint(dw.w);
+            if (FIRST) {
+                uint32_t lp;
+                sample = uint32_t(a.sample_base) + fast_div(slot, a.pix_count, lp);
+            } else {
+                const float4 tp = stage.tp[buf][tid];
+                T = f3(tp.x, tp.y, tp.z);
+                sample = __float_as_uint(tp.w);
+                Lp = f3(stage.L[buf][0][tid], stage.L[buf][1][tid], stage.L[buf][2][tid]);
+            }
+            const Shaded sh = shade_vertex<KIND, LAST, true>(a, S, bounce, p, d, T, prim, pixel, sample);
+            T = sh.T;
+            if (sh.want_shadow) ++shadow_rays;
+            const bool cont = !LAST && (T.x > 0.0f || T.y > 0.0f || T.z > 0.0f);
+            if (cont) ++traced;
+            // ---- the rays of this vertex: shadow (any hit) and continuation (nearest hit) ----
+            bool blocked = false;
+            float t_hit = FLT_MAX;
+            uint32_t prim_hit = kInvalid;
+            if (kDiffuse && !LAST) {
+                if (sh.want_shadow || cont)
+                    trace_flat<true>(S, sh.no, sh.nd, cont ? FLT_MAX : -1.0f, sh.w, sh.tmax_s, t_hit, prim_hit, blocked);
+            } else if (kDiffuse) { // LAST: the shadow ray alone
+                if (sh.want_shadow) {
+                    bool unused;
+                    trace_flat<false>(S, sh.no, sh.w, sh.tmax_s, sh.w, -1.0f, t_hit, prim_hit, unused);
+                    blocked = prim_hit != kInvalid;
+                }
+            } else if (cont) {
+                bool unused;
+                trace_flat<false>(S, sh.no, sh.nd, FLT_MAX, sh.nd, -1.0f, t_hit, prim_hit, unused);
+            }
+            const bool hit = cont && prim_hit != kInvalid;
+            if (kDiffuse && sh.want_shadow && !blocked) {
+                ++lit;
+                Lp = Lp + sh.lit_rgb;
+            }
+            if (hit) {
+                const float4 tag = S.hot_row(prim_hit, 3);
+                const int bsdf = __float_as_int(tag.y);
+                if (bsdf == G19_BSDF_EMITTER) {
+                    // emission counts after specular bounces only (NEE covers the diffuse ones)
+                    if (sh.flags & 1u) {
+                        const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
+                        Lp = Lp + f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]);
+                    }
+                } else if (bsdf == G19_BSDF_DIFFUSE || !next_last) { // a specular vertex on the last segment adds nothing
+                    kind_next = bsdf;
+                    p_next = sh.no + sh.nd * t_hit;
+                    d_next = sh.nd;
+                    prim_next = prim_hit;
+                }
+            }
+            if (kind_next < 0 && (Lp.x != 0.0f || Lp.y != 0.0f || Lp.z != 0.0f)) {
+                // the path ends here: its radiance goes to the slot's accumulator input, once
+                ++stored;
+                a.L[slot] = Lp.x;
+                a.L[a.plane + slot] = Lp.y;
+                a.L[2 * a.plane + slot] = Lp.z;
+            }
+        }
+        if (!LAST) {
+            const uint32_t pos = out.reserve(kind_next);
+            if (pos != kInvalid) {
+                const RecView r = rec_queue(a, out.set + kind_next);
+                r.slot[pos] = slot;
+                r.hp[pos] = make_float4(p_next.x, p_next.y, p_next.z, __uint_as_float(prim_next));
+                r.dw[pos] = make_float4(d_next.x, d_next.y, d_next.z, __uint_as_float(pixel));
+                r.tp[pos] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
+                r.L[pos] = Lp.x;
+                r.L[r.cap + pos] = Lp.y;
+                r.L[2 * r.cap + pos] = Lp.z;
+            }
+        }
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
+    if (!LAST) out.flush(a);
+    calls = warp_sum(calls);
+    traced = warp_sum(traced);
+    shadow_rays = warp_sum(shadow_rays);
+    lit = warp_sum(lit);
+    stored = warp_sum(stored);
+    if (lane == 0 && calls) {
+        atomicAdd(a.totals + 2, (unsigned long long)calls);
+        if (FIRST) atomicAdd(a.totals + 3, (unsigned long long)calls);
+        if (traced) atomicAdd(a.totals + 0, (unsigned long long)traced);
+        if (shadow_rays) atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
+        if (lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
+        if (stored) atomicAdd(a.totals + 6, (unsigned long long)stored);
+    }
+}
+
+// ---- bounce, tree scenes: shade and queue the rays -----------------------------------------
+// Asynchronous prefetch of the NEXT slot's state into shared memory (see prefetch_rec); here the
+// state is indexed by slot, so the queue entry is loaded two iterations ahead.
+template <bool TP> struct VertexStage {
+    float4 hp[2][kThreads];
+    float4 dw[2][kThreads];
+    float4 tp[TP ? 2 : 1][TP ? kThreads : 1];
+};
+template <bool TP> __device__ __forceinline__ void prefetch_vertex(const PassArgs& a, uint32_t slot, VertexStage<TP>& st, int buf) {
+    const int t = threadIdx.x;
+    if (slot != kInvalid) {
+        cp_async16(&st.hp[buf][t], a.hp + slot);
+        cp_async16(&st.dw[buf][t], a.dw + slot);
+        if (TP) cp_async16(&st.tp[buf][t], a.tp + slot);
+    }
+    cp_async_commit();
+}
+
+// Tree scenes only shade here: the rays go to the bounce's ray queue and trace_kernel walks them
+// with dynamic fetch (a heavy tail of long walks would otherwise hold the other 31 lanes of the
+// warp -- ncu: 3.4 of 32 lanes active); trace_kernel also adds the light sample and delivers the
+// continuation vertex into the slot-indexed state and the next bounce's material queues.
+template <int KIND, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_kernel(const PassArgs a, const int bounce) {
+    constexpr bool kDiffuse = KIND == Q_DIFFUSE;
+    pdl_launch_dependents();
+    if (LAST && !kDiffuse) return; // a specular vertex on the last segment contributes nothing
+    SceneAccess<false> S;
+    S.g = &a.scene;
     pdl_wait();
     const uint32_t n = a.counts[bounce * 4 + KIND];
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     const uint32_t* __restrict__ qin = a.q[(bounce & 1) * 3 + (KIND - 1)];
-    Sorter out;
-    if (ALL && !LAST) out.init(a, bounce + 1);
     WarpCursor ray_cur = {0, 0};
     uint32_t* const ray_counter = a.counts + bounce * 4 + Q_RAYS;
-    unsigned traced = 0, shadow_rays = 0, lit = 0, calls = 0;
+    unsigned traced = 0, shadow_rays = 0, calls = 0;
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
-    const bool next_last = bounce + 2 >= a.max_depth;
 
-    __shared__ VertexStage<kTp, kRad> stage;
+    __shared__ VertexStage<!FIRST> stage;
     uint32_t q = blockIdx.x * kThreads + threadIdx.x;
     uint32_t s_cur = kInvalid, s_nxt = kInvalid;
     if (q < n) s_cur = qin[q];
@@ -790,8 +1148,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3)
         prefetch_vertex(a, s_nxt, stage, buf ^ 1); // next slot's state, in flight during this body
         cp_async_wait<1>();                        // this slot's state has landed
         const uint32_t slot = s_cur;
-        int kind_next = -1;
-        bool ray_shadow = false, ray_cont = false; // tree scenes: rays to enqueue
+        bool ray_shadow = false, ray_cont = false; // rays to enqueue
         float3 ray_o = f3(0.f, 0.f, 0.f), ray_w = f3(0.f, 0.f, 1.f), ray_d = f3(0.f, 0.f, 1.f), ray_rgb = f3(0.f, 0.f, 0.f);
         float ray_tmax = 0.0f;
         uint32_t ray_flags = 0;
@@ -811,188 +1168,48 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3)
                 T = f3(tp.x, tp.y, tp.z);
                 sample = __float_as_uint(tp.w);
             }
-            float4 c0, c1; // (normal, ior), (albedo, material)
-            S.cold(prim, c0, c1);
-            float3 ng = f3(c0.x, c0.y, c0.z);
-            if (c0.x == 0.0f && c0.y == 0.0f && c0.z == 0.0f) { // spheres store no normal: (p - centre) / r
-                const float4 q0 = S.hot_row(prim, 0);
-                ng = (p - f3(q0.x, q0.y, q0.z)) * __fdividef(1.0f, q0.w);
-            }
-            const float ior = c0.w;
-            const bool entering = dot(ng, d) < 0.0f;
-            const float3 nf = entering ? ng : -ng; // normal on the side the ray arrives from
-            const float3 albedo = f3(c1.x, c1.y, c1.z);
-            const uint4 r = philox(pixel, sample, uint32_t(bounce), 1u, a.seed);
-            float3 no, nd = f3(0.f, 0.f, 1.f);
-            uint32_t flags = 0;
-            // next-event estimation (diffuse only): one light, one uniformly sampled point
-            bool want_shadow = false;
-            float3 w = f3(0.f, 0.f, 1.f), lit_rgb = f3(0.f, 0.f, 0.f);
-            float tmax_s = -1.0f;
-            if (kDiffuse) {
-                if (a.scene.n_lights > 0) {
-                    float pick = u01(r.x) * float(a.scene.n_lights);
-                    int li = min(int(pick), a.scene.n_lights - 1);
-                    float u1 = pick - float(li), u2 = u01(r.y);
-                    const float4* lt = S.light(li);
-                    const float4 l0 = lt[0], l1 = lt[1], l2 = lt[2], l3 = lt[3];
-                    float su = sqrtf(u1);
-                    float b1 = su * (1.0f - u2), b2 = su * u2;
-                    float3 yl = f3(l0.x + l1.x * b1 + l2.x * b2, l0.y + l1.y * b1 + l2.y * b2, l0.z + l1.z * b1 + l2.z * b2);
-                    w = yl - p;
-                    float dist2 = dot(w, w);
-                    float inv_dist = rsqrtf(dist2);
-                    float dist = dist2 * inv_dist;
-                    w = w * inv_dist;
-                    float cs = dot(nf, w);
-                    float cl = fabsf(dot(f3(l3.x, l3.y, l3.z), w));
-                    if (cs > 0.0f && cl > 0.0f && dist > 2.0f * kRayEps) {
-                        want_shadow = true;
-                        tmax_s = dist - 2.0f * kRayEps;
-                        const float4 l4 = lt[4];
-                        float gterm = cs * cl * l0.w * __fdividef(1.0f, dist2 * l1.w) * (1.0f / kPi);
-                        lit_rgb = f3(T.x * albedo.x * l4.x * gterm, T.y * albedo.y * l4.y * gterm, T.z * albedo.z * l4.z * gterm);
-                        ++shadow_rays;
-                    }
-                }
-                no = p + nf * kRayEps;
-                if (!LAST) { // cosine-weighted bounce: pdf cancels cos/pi, throughput *= albedo
-                    float u3 = u01(r.z), u4 = u01(r.w);
-                    float rr = sqrtf(u3), phi = 2.0f * kPi * u4 - kPi; // [-pi, pi): MUFU range
-                    float sp, cp;
-                    __sincosf(phi, &sp, &cp);
-                    sp = -sp; cp = -cp; // shift back by pi
-                    float3 tx, ty;
-                    onb(nf, tx, ty);
-                    nd = normalize(tx * (rr * cp) + ty * (rr * sp) + nf * sqrtf(fmaxf(0.0f, 1.0f - u3)));
-                }
-                T = T * albedo;
-            } else if (KIND == Q_MIRROR) {
-                nd = normalize(d - nf * (2.0f * dot(d, nf)));
-                no = p + nf * kRayEps;
-                T = T * albedo;
-                flags = 1u;
-            } else { // dielectric
-                float etai = entering ? 1.0f : ior, etat = entering ? ior : 1.0f;
-                float eta = etai / etat;
-                float cosi = fminf(1.0f, -dot(d, nf));
-                float sin2t = eta * eta * fmaxf(0.0f, 1.0f - cosi * cosi);
-                float F = 1.0f;
-                float cost = 0.0f;
-                if (sin2t < 1.0f) {
-                    cost = sqrtf(1.0f - sin2t);
-                    float rs = (etai * cosi - etat * cost) / (etai * cosi + etat * cost);
-                    float rp = (etai * cost - etat * cosi) / (etai * cost + etat * cosi);
-                    F = 0.5f * (rs * rs + rp * rp);
-                }
-                if (u01(r.x) < F) {
-                    nd = normalize(d + nf * (2.0f * cosi));
-                    no = p + nf * kRayEps;
-                } else {
-                    nd = normalize(d * eta + nf * (eta * cosi - cost));
-                    no = p - nf * kRayEps;
-                }
-                T = T * albedo;
-                flags = 1u;
-            }
+            const Shaded sh = shade_vertex<KIND, LAST, false>(a, S, bounce, p, d, T, prim, pixel, sample);
+            T = sh.T;
             const bool cont = !LAST && (T.x > 0.0f || T.y > 0.0f || T.z > 0.0f);
             if (cont) ++traced;
-
-            // ---- the rays of this vertex: shadow (any hit) and continuation (nearest hit) ----
-            if (!ALL) {
-                ray_o = no; ray_w = w; ray_d = nd; ray_rgb = lit_rgb; ray_tmax = tmax_s;
-                ray_flags = (flags & 1u) ? kRaySpecular : 0u;
-            }
-            bool blocked = false, hit = false;
-            float t_hit = FLT_MAX;
-            uint32_t prim_hit = kInvalid;
-            if constexpr (ALL) {
-                const SceneAccess<true>& F = S;
-                if (kDiffuse && !LAST) {
-                    if (want_shadow || cont)
-                        trace_flat<true>(F, no, nd, cont ? FLT_MAX : -1.0f, w, tmax_s, t_hit, prim_hit, blocked);
-                } else if (kDiffuse) { // LAST: the shadow ray alone
-                    if (want_shadow) {
-                        bool unused;
-                        trace_flat<false>(F, no, w, tmax_s, w, -1.0f, t_hit, prim_hit, unused);
-                        blocked = prim_hit != kInvalid;
-                    }
-                } else if (cont) {
-                    bool unused;
-                    trace_flat<false>(F, no, nd, FLT_MAX, nd, -1.0f, t_hit, prim_hit, unused);
-                }
-                hit = cont && prim_hit != kInvalid;
-            } else {
-                // the continuation vertex's direction / pixel / throughput / sample are known now;
-                // trace_kernel adds the hit point and primitive (or ends the path)
-                ray_shadow = kDiffuse && want_shadow;
-                ray_cont = cont;
-                if (cont) {
-                    a.dw[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
-                    a.tp[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
-                }
-            }
-            if (ALL && kDiffuse && want_shadow && !blocked) {
-                ++lit;
-                // the old value came in with the prefetched state: store only, no stall
-                float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f;
-                if (kRad) { l0 = stage.L[buf][0][tid]; l1 = stage.L[buf][1][tid]; l2 = stage.L[buf][2][tid]; }
-                a.L[slot] = l0 + lit_rgb.x;
-                a.L[a.plane + slot] = l1 + lit_rgb.y;
-                a.L[2 * a.plane + slot] = l2 + lit_rgb.z;
-            }
-            if (hit) {
-                const float4 tag = S.hot_row(prim_hit, 3);
-                const int bsdf = __float_as_int(tag.y);
-                if (bsdf == G19_BSDF_EMITTER) {
-                    // emission counts after specular bounces only (NEE covers the diffuse ones)
-                    if (flags & 1u) {
-                        const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
-                        add_radiance(a, slot, f3(T.x * m.emission[0], T.y * m.emission[1], T.z * m.emission[2]));
-                    }
-                } else if (bsdf == G19_BSDF_DIFFUSE || !next_last) { // a specular vertex on the last segment adds nothing
-                    kind_next = bsdf;
-                    store_vertex(a, slot, no + nd * t_hit, prim_hit, nd, pixel);
-                    a.tp[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
-                }
+            if (sh.want_shadow) ++shadow_rays;
+            ray_o = sh.no; ray_w = sh.w; ray_d = sh.nd; ray_rgb = sh.lit_rgb; ray_tmax = sh.tmax_s;
+            ray_flags = (sh.flags & 1u) ? kRaySpecular : 0u;
+            // the continuation vertex's direction / pixel / throughput / sample are known now;
+            // trace_kernel adds the hit point and primitive (or ends the path)
+            ray_shadow = kDiffuse && sh.want_shadow;
+            ray_cont = cont;
+            if (cont) {
+                a.dw[slot] = make_float4(sh.nd.x, sh.nd.y, sh.nd.z, __uint_as_float(pixel));
+                a.tp[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
             }
         }
-        if constexpr (ALL) {
-            if (!LAST) out.push(kind_next, slot);
-        } else {
-            // ray records: (origin, tmax) (direction, slot | kRayShadow | kRaySpecular) (light sample rgb)
-            const uint32_t is = warp_reserve(ray_cur, ray_shadow, ray_counter);
-            if (is != kInvalid) {
-                a.ray0[is] = make_float4(ray_o.x, ray_o.y, ray_o.z, ray_tmax);
-                a.ray1[is] = make_float4(ray_w.x, ray_w.y, ray_w.z, __uint_as_float(slot | kRayShadow));
-                a.ray2[is] = make_float4(ray_rgb.x, ray_rgb.y, ray_rgb.z, 0.0f);
-            }
-            const uint32_t ic = warp_reserve(ray_cur, ray_cont, ray_counter);
-            if (ic != kInvalid) {
-                a.ray0[ic] = make_float4(ray_o.x, ray_o.y, ray_o.z, FLT_MAX);
-                a.ray1[ic] = make_float4(ray_d.x, ray_d.y, ray_d.z, __uint_as_float(slot | ray_flags));
-            }
+        // ray records: (origin, tmax) (direction, slot | kRayShadow | kRaySpecular) (light sample rgb)
+        const uint32_t is = warp_reserve(ray_cur, ray_shadow, ray_counter);
+        if (is != kInvalid) {
+            a.ray0[is] = make_float4(ray_o.x, ray_o.y, ray_o.z, ray_tmax);
+            a.ray1[is] = make_float4(ray_w.x, ray_w.y, ray_w.z, __uint_as_float(slot | kRayShadow));
+            a.ray2[is] = make_float4(ray_rgb.x, ray_rgb.y, ray_rgb.z, 0.0f);
+        }
+        const uint32_t ic = warp_reserve(ray_cur, ray_cont, ray_counter);
+        if (ic != kInvalid) {
+            a.ray0[ic] = make_float4(ray_o.x, ray_o.y, ray_o.z, FLT_MAX);
+            a.ray1[ic] = make_float4(ray_d.x, ray_d.y, ray_d.z, __uint_as_float(slot | ray_flags));
         }
         s_cur = s_nxt; s_nxt = s_nn;
         buf ^= 1;
     }
     cp_async_wait<0>();
-    if constexpr (ALL) {
-        if (!LAST) out.flush();
-    } else {
-        for (uint32_t i = ray_cur.pos + lane; i < ray_cur.end; i += 32u) a.ray1[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalid));
-    }
+    for (uint32_t i = ray_cur.pos + lane; i < ray_cur.end; i += 32u) a.ray1[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalid));
     calls = warp_sum(calls);
     traced = warp_sum(traced);
     shadow_rays = warp_sum(shadow_rays);
-    lit = warp_sum(lit);
     if (lane == 0 && calls) {
         atomicAdd(a.totals + 2, (unsigned long long)calls);
         if (FIRST) atomicAdd(a.totals + 3, (unsigned long long)calls);
         if (traced) atomicAdd(a.totals + 0, (unsigned long long)traced);
         if (shadow_rays) atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
-        if (lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
-        if (kRadStat) atomicAdd(a.totals + 5, (unsigned long long)calls); // diffuse vertices that read L
+        if (!FIRST && kDiffuse) atomicAdd(a.totals + 5, (unsigned long long)calls); // diffuse vertices whose light sample may read L
     }
 }
 
@@ -1222,7 +1439,9 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, size_t smem, c
 
 template <int KIND, bool FIRST, bool LAST, bool ALL>
 static void launch_bounce_k(const PassArgs& a, int bounce, size_t smem, int sm_count, cudaStream_t s) {
-    auto kernel = bounce_kernel<KIND, FIRST, LAST, ALL>;
+    void (*kernel)(PassArgs, int);
+    if constexpr (ALL) kernel = bounce_flat_kernel<KIND, FIRST, LAST>;
+    else kernel = bounce_kernel<KIND, FIRST, LAST>;
     const int grid = persistent_grid(kernel, smem, sm_count);
     cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);
     if (e != cudaSuccess) note_launch_error("bounce kernel launch", e, smem, grid);
@@ -1243,11 +1462,11 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
     cudaError_t e;
     int grid;
     if (all_staged(a)) {
-        grid = persistent_grid(raygen_extend_kernel<true>, smem, sm_count);
-        e = launch_pdl(raygen_extend_kernel<true>, grid, smem, s, a);
+        grid = persistent_grid(raygen_extend_flat_kernel, smem, sm_count);
+        e = launch_pdl(raygen_extend_flat_kernel, grid, smem, s, a);
     } else {
-        grid = persistent_grid(raygen_extend_kernel<false>, smem, sm_count);
-        e = launch_pdl(raygen_extend_kernel<false>, grid, smem, s, a);
+        grid = persistent_grid(raygen_extend_kernel, smem, sm_count);
+        e = launch_pdl(raygen_extend_kernel, grid, smem, s, a);
     }
     if (e != cudaSuccess) note_launch_error("raygen_extend kernel launch", e, smem, grid);
 }

@@ -282,7 +282,7 @@ def main():
     # ---- per-kernel-class CUDA-event times (same steps, event brackets on) --------------------
     barrier()
     cls_ms = [0.0] * 8
-    agg = {"extend": 0, "shadow": 0, "shade": 0, "shade_first": 0, "lit": 0, "rad_reads": 0, "samples": 0,
+    agg = {"extend": 0, "shadow": 0, "shade": 0, "shade_first": 0, "lit": 0, "rad_stores": 0, "samples": 0,
            "launch": [0] * 8}
     for _ in range(args.steps):
         step(profile=1)
@@ -296,19 +296,19 @@ def main():
         agg["shade"] += s.shade_calls
         agg["shade_first"] += s.shade_calls_first
         agg["lit"] += s.lit_samples
-        agg["rad_reads"] += s.radiance_reads
+        agg["rad_stores"] += s.radiance_stores
         agg["samples"] += s.samples
     barrier()
-    # algorithmic HBM bytes per class, this rank
-    E, S0, C, C0, LIT, RR = agg["extend"], agg["samples"], agg["shade"], agg["shade_first"], agg["lit"], agg["rad_reads"]
+    # algorithmic HBM bytes per class, this rank. Flat scenes keep DENSE vertex
+    # records in the material queues: slot 4 B + (hit point, primitive) 16 B + (direction, pixel) 16 B
+    # [+ (throughput, sample) 16 B + radiance so far 12 B past the camera segment]
+    E, S0, C, C0, LIT, ST = agg["extend"], agg["samples"], agg["shade"], agg["shade_first"], agg["lit"], agg["rad_stores"]
     npix_local = g19.engine.tile_pixels(W, H, rank, world)
-    # vertex record = hit point+primitive 16 B, direction+pixel 16 B; + queue entry 4 B; throughput+sample 16 B
     bytes_cls = {
-        "raygen_extend": 36 * C0,                       # vertex + queue entry written per shaded camera hit
-        "bounce": (36 * C                               # queue entry + vertex read per shaded vertex
-                   + 16 * (C - C0) + 12 * RR            # throughput, radiance so far (past the camera segment)
-                   + 12 * LIT                           # radiance written per unoccluded light sample
-                   + 52 * (C - C0)),                    # vertex + throughput + queue entry of each continuation hit
+        "raygen_extend": 36 * C0,                       # record written per shaded camera hit
+        "bounce": (36 * C0 + 64 * (C - C0)              # record read per shaded vertex
+                   + 64 * (C - C0)                      # record written per continuation hit (= vertices shaded later)
+                   + 12 * ST),                          # radiance delivered once per path that gathered any
         "accumulate": 24 * S0 + 24 * npix_local * max(1, agg["launch"][abi.K_ACCUM]),
     }
     ms_cls = {"raygen_extend": cls_ms[abi.K_EXTEND], "bounce": cls_ms[abi.K_SHADE], "accumulate": cls_ms[abi.K_ACCUM]}
