@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <limits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -418,6 +419,29 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
         hot[i] = prims[i].hot;
         cold[i] = prims[i].cold;
     }
+    // Flat scenes: the same records as primitive PAIRS for the packed-FP32 (FFMA2) loops of
+    // trace_flat -- planar pair = rows a, b, c with every coefficient a float2 (primitive 2j, 2j+1),
+    // 96 B; sphere pair = (-centre, radius^2) as float2s, 32 B. Each kind group is padded to an even
+    // count with NaNs: every comparison on a NaN fails, so a padding record is never hit.
+    std::vector<float> pairs;
+    if (!on_device && nodes.size() == 1) {
+        const float nan = std::numeric_limits<float>::quiet_NaN();
+        auto planar = [&](size_t first, size_t count) {
+            for (size_t k = 0; k < count; k += 2)
+                for (int c = 0; c < 12; ++c)
+                    for (size_t e = 0; e < 2; ++e) pairs.push_back(k + e < count ? hot[first + k + e].q[c] : nan);
+        };
+        planar(0, size_t(n_par));
+        planar(size_t(n_par), size_t(n_tri));
+        const size_t s0 = size_t(n_par) + size_t(n_tri), ns = hot.size() - s0;
+        for (size_t k = 0; k < ns; k += 2)
+            for (int c = 0; c < 4; ++c)
+                for (size_t e = 0; e < 2; ++e) {
+                    float v = nan;
+                    if (k + e < ns) v = c < 3 ? -hot[s0 + k + e].q[c] : hot[s0 + k + e].q[3] * hot[s0 + k + e].q[3];
+                    pairs.push_back(v);
+                }
+    }
     auto up = [&](DeviceArray& d, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = d.ensure(bytes ? bytes : 16);
         if (e != cudaSuccess || !bytes) return e;
@@ -436,6 +460,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
                         (e = up(b.prim_index, index.data(), index.size() * sizeof(uint32_t))) != cudaSuccess)) ||
         (e = up(b.hot, hot.data(), hot.size() * sizeof(PrimHot))) != cudaSuccess ||
         (e = up(b.cold, cold.data(), cold.size() * sizeof(PrimCold))) != cudaSuccess ||
+        (e = up(b.pairs, pairs.data(), pairs.size() * sizeof(float))) != cudaSuccess ||
         (e = up(b.materials, materials.data(), materials.size() * sizeof(MaterialD))) != cudaSuccess ||
         (e = up(b.lights, lights.data(), lights.size() * sizeof(LightD))) != cudaSuccess ||
         (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
@@ -457,6 +482,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     v.tree_depth = tree_depth;
     v.n_par = n_par;
     v.n_tri = n_tri;
+    v.pairs = static_cast<const float*>(b.pairs.p);
+    v.pairs_bytes = int32_t(pairs.size() * sizeof(float));
     for (int k = 0; k < 3; ++k) {
         v.root_lo[k] = root_lo[k];
         v.root_size[k] = root_size[k];
@@ -465,7 +492,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &w.hp, &w.dw, &w.tp,
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &w.hp, &w.dw, &w.tp,
                            &w.L, &w.queues, &w.recs, &w.rays, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
         d->release();
     if (w.events) {

@@ -44,6 +44,8 @@ struct PathSceneD {
     const LightD* lights;
     int32_t n_nodes, n_index, n_prims, n_lights, tree_depth;
     int32_t n_par, n_tri;    // flat scenes: primitives sorted parallelograms | triangles | spheres
+    const float* pairs;      // flat scenes: the same primitives as PAIRS for the packed-FP32 loops (path.cu build_pairs)
+    int32_t pairs_bytes;
     float root_lo[3], root_size[3];
 };
 
@@ -59,7 +61,7 @@ struct DeviceArray {
 };
 
 struct PathSceneBuffers {
-    DeviceArray nodes, prim_index, hot, cold, materials, lights;
+    DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs;
     PathSceneD view{};
     bool has_bsdf[4] = {false, false, false, false};
 };

@@ -105,6 +105,7 @@ template <bool ALL> struct SceneAccess {
     const float4* hot_s;
     const float4* cold_s;
     const float4* lights_s;
+    const ulonglong2* pairs_s; // flat scenes: primitive PAIRS, one float2 per coefficient (trace_flat)
     uint32_t* stack;
     int n_nodes_s;
     __device__ __forceinline__ uint2 node(uint32_t i) const {
@@ -153,14 +154,16 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     const uint32_t pb = uint32_t(a.stage_prims) * 64u;
     const uint32_t cb = ALL ? uint32_t(a.stage_cold) * 32u : 0u;
     const uint32_t lb = ALL ? uint32_t(a.stage_lights) * 80u : 0u;
+    const uint32_t qb = ALL ? uint32_t(g.pairs_bytes) : 0u;
     unsigned char* base = g19_dyn_smem;
     acc.nodes_s = reinterpret_cast<const uint2*>(base);
     acc.hot_s = reinterpret_cast<const float4*>(base + nb);
     acc.cold_s = reinterpret_cast<const float4*>(base + nb + pb);
     acc.lights_s = reinterpret_cast<const float4*>(base + nb + pb + cb);
-    acc.stack = reinterpret_cast<uint32_t*>(base + nb + pb + cb + lb) + threadIdx.x;
+    acc.pairs_s = reinterpret_cast<const ulonglong2*>(base + nb + pb + cb + lb);
+    acc.stack = reinterpret_cast<uint32_t*>(base + nb + pb + cb + lb + qb) + threadIdx.x;
     unsigned long long* barp =
-        reinterpret_cast<unsigned long long*>(base + nb + pb + cb + lb + uint32_t(a.stack_levels) * kThreads * 4u);
+        reinterpret_cast<unsigned long long*>(base + nb + pb + cb + lb + qb + uint32_t(a.stack_levels) * kThreads * 4u);
     const uint32_t bar = smem_addr(barp);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -168,7 +171,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + pb + cb + lb) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb + pb + cb + lb + qb) : "memory");
         if (nb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(base)),
@@ -188,6 +191,11 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(base + nb + pb + cb)),
                          "l"(g.lights), "r"(lb), "r"(bar)
+                         : "memory");
+        if (qb)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(base + nb + pb + cb + lb)),
+                         "l"(g.pairs), "r"(qb), "r"(bar)
                          : "memory");
     }
     uint32_t done = 0; // everyone waits for phase 0 of the barrier
@@ -257,40 +265,125 @@ __device__ __forceinline__ float hit_prim(float4 a, float4 b, float4 c, float4 t
     return ok ? __uint_as_float(tb) : -1.0f;
 }
 
+// ---- packed FP32 pairs (sm_100: FFMA2 / FMUL2 / FADD2) -----------------------------------
+// One issue slot carries two FP32 lanes; an operand built as pk(x, x) compiles to the scalar
+// broadcast form (R.F32), so only the primitive coefficients need to be stored as pairs. Measured
+// here (tools/ubench/ffma2.cu): 0.98 FFMA or 0.49 FFMA2 per cycle and scheduler, same 4-cycle
+// dependent latency -- the FMA pipe does the same work, the ISSUE slots halve, and issue slots are
+// what bounds these kernels (ncu: issue 71 %, FMA pipe 34 %, 40 % of the instructions FP32).
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 bc(float x) { return pk(x, x); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// A ray as the pair loops want it: direction and negated direction as scalars (broadcast operands).
+struct RayDir {
+    float x, y, z, nx, ny, nz;
+};
+__device__ __forceinline__ RayDir ray_dir(float3 d) { return RayDir{d.x, d.y, d.z, -d.x, -d.y, -d.z}; }
+
+// Two planar primitives at once. Pair record = 6 x ulonglong2: row a = (x,y | z,w), row b, row c,
+// every coefficient a float2 (primitive 2j, primitive 2j+1). Same operation order per lane as
+// plane_origin / plane_hit above, so the results are bit-identical to the scalar form.
+struct PlaneOrigin2 {
+    f2 ox, oy, oz;
+};
+__device__ __forceinline__ PlaneOrigin2 plane_origin2(const ulonglong2* r, float3 o) {
+    const f2 ox = bc(o.x), oy = bc(o.y), oz = bc(o.z);
+    const ulonglong2 a0 = r[0], a1 = r[1], b0 = r[2], b1 = r[3], c0 = r[4], c1 = r[5];
+    PlaneOrigin2 p;
+    p.oz = fma2(c0.x, ox, fma2(c0.y, oy, fma2(c1.x, oz, c1.y)));
+    p.ox = fma2(a0.x, ox, fma2(a0.y, oy, fma2(a1.x, oz, a1.y)));
+    p.oy = fma2(b0.x, ox, fma2(b0.y, oy, fma2(b1.x, oz, b1.y)));
+    return p;
+}
+// t = -h(o) / h'(d) is formed as h(o) * rcp(h'(-d)): no negation of a pair is needed.
+__device__ __forceinline__ void plane_uvt2(const ulonglong2* r, const PlaneOrigin2& po, const RayDir& d, f2& u, f2& v, f2& t) {
+    const ulonglong2 a0 = r[0], a1 = r[1], b0 = r[2], b1 = r[3], c0 = r[4], c1 = r[5];
+    const f2 ndz = fma2(c0.x, bc(d.nx), fma2(c0.y, bc(d.ny), mul2(c1.x, bc(d.nz))));
+    float z0, z1;
+    upk(ndz, z0, z1);
+    t = mul2(po.oz, pk(rcp_fast(z0), rcp_fast(z1)));
+    const f2 dx = fma2(a0.x, bc(d.x), fma2(a0.y, bc(d.y), mul2(a1.x, bc(d.z))));
+    const f2 dy = fma2(b0.x, bc(d.x), fma2(b0.y, bc(d.y), mul2(b1.x, bc(d.z))));
+    u = fma2(t, dx, po.ox);
+    v = fma2(t, dy, po.oy);
+}
+template <int KIND> __device__ __forceinline__ bool plane_inside(float u, float v) {
+    if (KIND == 2) return fmaxf(fabsf(u), fabsf(v)) <= 0.5f;
+    return fminf(fminf(u, v), 1.0f - (u + v)) >= 0.0f;
+}
+
 // Flat scene (ONE leaf, fully staged, primitives sorted parallelograms | triangles | spheres by
 // the builder): nearest hit of ray (o, d1) within tmax1 and, when DUAL, any hit of ray (o, d0)
 // within tmax0 -- both leave the same point, so one pass over the primitives serves both. A ray
-// with tmax <= 0 is switched off. Three branch-free loops; the leaf position IS the primitive id.
+// with tmax <= 0 is switched off. Three branch-free loops over primitive PAIRS (each kind group is
+// padded to an even count with a NaN record that can never be hit); the position in its group IS
+// the primitive id.
+template <int KIND, bool DUAL>
+__device__ __forceinline__ void plane_pairs(const ulonglong2* rec, uint32_t n_pairs, uint32_t id0, float3 o, const RayDir& d1,
+                                            const RayDir& d0, uint32_t& lim1, uint32_t& lim0, uint32_t& hit_k) {
+#pragma unroll 1
+    for (uint32_t j = 0; j < n_pairs; ++j, rec += 6) {
+        const PlaneOrigin2 po = plane_origin2(rec, o);
+        f2 u, v, t;
+        plane_uvt2(rec, po, d1, u, v, t);
+        float ua, ub, va, vb, ta, tb;
+        upk(u, ua, ub); upk(v, va, vb); upk(t, ta, tb);
+        if (plane_inside<KIND>(ua, va) & (__float_as_uint(ta) < lim1)) { lim1 = __float_as_uint(ta); hit_k = id0 + 2u * j; }
+        if (plane_inside<KIND>(ub, vb) & (__float_as_uint(tb) < lim1)) { lim1 = __float_as_uint(tb); hit_k = id0 + 2u * j + 1u; }
+        if (DUAL) {
+            plane_uvt2(rec, po, d0, u, v, t);
+            upk(u, ua, ub); upk(v, va, vb); upk(t, ta, tb);
+            if ((plane_inside<KIND>(ua, va) & (__float_as_uint(ta) < lim0)) | (plane_inside<KIND>(ub, vb) & (__float_as_uint(tb) < lim0)))
+                lim0 = 0u;
+        }
+    }
+}
+// Sphere pair record = 2 x ulonglong2: (-cx, -cy | -cz, r^2). Unit direction, discriminant from the
+// perpendicular offset; the nearer root ahead of the origin is the unsigned minimum of the roots.
+__device__ __forceinline__ void sphere_roots2(f2 ocx, f2 ocy, f2 ocz, f2 rr, const RayDir& d, uint32_t& ta, uint32_t& tb) {
+    const f2 bq = fma2(ocz, bc(d.z), fma2(ocy, bc(d.y), mul2(ocx, bc(d.x))));
+    const f2 lx = fma2(bq, bc(d.nx), ocx), ly = fma2(bq, bc(d.ny), ocy), lz = fma2(bq, bc(d.nz), ocz);
+    const f2 disc = sub2(rr, fma2(lz, lz, fma2(ly, ly, mul2(lx, lx))));
+    float b0, b1, q0, q1;
+    upk(bq, b0, b1);
+    upk(disc, q0, q1);
+    const float s0 = sqrtf(q0), s1 = sqrtf(q1); // NaN when the ray misses: fails the range test
+    ta = min(__float_as_uint(-b0 - s0), __float_as_uint(s0 - b0));
+    tb = min(__float_as_uint(-b1 - s1), __float_as_uint(s1 - b1));
+}
 template <bool DUAL>
 __device__ __forceinline__ void trace_flat(const SceneAccess<true>& S, float3 o, float3 d1, float tmax1, float3 d0,
                                            float tmax0, float& best, uint32_t& best_k, bool& occluded) {
     uint32_t lim1 = range_limit(tmax1), lim0 = DUAL ? range_limit(tmax0) : 0u;
     uint32_t hit_k = kInvalid;
-    const uint32_t n_par = uint32_t(S.g->n_par), n_flat = n_par + uint32_t(S.g->n_tri), n = uint32_t(S.g->n_prims);
-    uint32_t k = 0;
-#pragma unroll 2
-    for (; k < n_par; ++k) {
-        const float4 a = S.hot_s[4 * k], b = S.hot_s[4 * k + 1], c = S.hot_s[4 * k + 2];
-        const PlaneOrigin po = plane_origin(a, b, c, o);
-        uint32_t tb;
-        if (plane_hit<2>(a, b, c, po, d1, lim1, tb)) { lim1 = tb; hit_k = k; }
-        if (DUAL && plane_hit<2>(a, b, c, po, d0, lim0, tb)) lim0 = 0u;
-    }
-#pragma unroll 2
-    for (; k < n_flat; ++k) {
-        const float4 a = S.hot_s[4 * k], b = S.hot_s[4 * k + 1], c = S.hot_s[4 * k + 2];
-        const PlaneOrigin po = plane_origin(a, b, c, o);
-        uint32_t tb;
-        if (plane_hit<1>(a, b, c, po, d1, lim1, tb)) { lim1 = tb; hit_k = k; }
-        if (DUAL && plane_hit<1>(a, b, c, po, d0, lim0, tb)) lim0 = 0u;
-    }
-#pragma unroll 2
-    for (; k < n; ++k) {
-        const float4 a = S.hot_s[4 * k];
-        const float3 oc = o - f3(a.x, a.y, a.z);
-        uint32_t tb;
-        if (sphere_hit(oc, a.w, d1, lim1, tb)) { lim1 = tb; hit_k = k; }
-        if (DUAL && sphere_hit(oc, a.w, d0, lim0, tb)) lim0 = 0u;
+    const uint32_t n_par = uint32_t(S.g->n_par), n_tri = uint32_t(S.g->n_tri), n = uint32_t(S.g->n_prims);
+    const uint32_t p_par = (n_par + 1u) >> 1, p_tri = (n_tri + 1u) >> 1, p_sph = (n - n_par - n_tri + 1u) >> 1;
+    const RayDir r1 = ray_dir(d1), r0 = ray_dir(d0);
+    const ulonglong2* rec = S.pairs_s;
+    plane_pairs<2, DUAL>(rec, p_par, 0u, o, r1, r0, lim1, lim0, hit_k);
+    rec += 6u * p_par;
+    plane_pairs<1, DUAL>(rec, p_tri, n_par, o, r1, r0, lim1, lim0, hit_k);
+    rec += 6u * p_tri;
+#pragma unroll 1
+    for (uint32_t j = 0; j < p_sph; ++j, rec += 2) {
+        const ulonglong2 c0 = rec[0], c1 = rec[1];
+        const f2 ocx = add2(c0.x, bc(o.x)), ocy = add2(c0.y, bc(o.y)), ocz = add2(c1.x, bc(o.z));
+        uint32_t ta, tb;
+        sphere_roots2(ocx, ocy, ocz, c1.y, r1, ta, tb);
+        const uint32_t id = n_par + n_tri + 2u * j;
+        if (ta < lim1) { lim1 = ta; hit_k = id; }
+        if (tb < lim1) { lim1 = tb; hit_k = id + 1u; }
+        if (DUAL) {
+            sphere_roots2(ocx, ocy, ocz, c1.y, r0, ta, tb);
+            if ((ta < lim0) | (tb < lim0)) lim0 = 0u;
+        }
     }
     best = __uint_as_float(lim1);
     best_k = hit_k;
@@ -546,6 +639,8 @@ __device__ __forceinline__ void camera_ray(const PassArgs& a, int x, int y, uint
 // 32 lanes of a converged warp.
 struct WarpCursor {
     uint32_t pos, end; // warp-uniform
+    uint32_t next;     // lane 0: base of the chunk reserved ahead of time (warp_reserve)
+    bool has_next;     // warp-uniform
 };
 
 __device__ __forceinline__ void warp_append(WarpCursor& c, bool want, uint32_t value, uint32_t* __restrict__ queue,
@@ -569,6 +664,13 @@ __device__ __forceinline__ void warp_append(WarpCursor& c, bool want, uint32_t v
 
 // Same reservation, for records wider than a queue entry: returns the lane's position (kInvalid
 // for lanes that do not want one); the caller writes the record.
+// The chunk a warp will need NEXT is reserved ahead of time, as soon as an append could overflow
+// the current one (room < 32): ncu attributed 5.5 % of the bounce kernel's stall samples to the 16
+// instructions around this atomic -- its round trip to L2 was exposed once per 64 records. Now the
+// atomic is in flight during the ~800 instructions of the next vertex and its result is only read
+// at the next overflow. A warp that appends sparsely never gets close to the end of its chunk and
+// prefetches nothing; a dense producer leaves at most one unused chunk behind (warp_flush pads it).
+template <bool AHEAD = true>
 __device__ __forceinline__ uint32_t warp_reserve(WarpCursor& c, bool want, uint32_t* __restrict__ counter) {
     const uint32_t m = __ballot_sync(kFull, want);
     if (m == 0) return kInvalid;
@@ -577,12 +679,17 @@ __device__ __forceinline__ uint32_t warp_reserve(WarpCursor& c, bool want, uint3
     const uint32_t room = c.end - c.pos, base0 = c.pos;
     uint32_t base1 = 0;
     if (n > room) {
-        if (lane == 0) base1 = atomicAdd(counter, kChunk);
-        base1 = __shfl_sync(kFull, base1, 0);
+        if (!c.has_next && lane == 0) c.next = atomicAdd(counter, kChunk); // first chunk, or a sparse producer
+        base1 = __shfl_sync(kFull, c.next, 0);
+        c.has_next = false;
         c.pos = base1 + (n - room);
         c.end = base1 + kChunk;
     } else {
         c.pos += n;
+    }
+    if (AHEAD && !c.has_next && c.end - c.pos < 32u) { // the next append may overflow: fetch its chunk now
+        if (lane == 0) c.next = atomicAdd(counter, kChunk);
+        c.has_next = true;
     }
     return want ? (rank < room ? base0 + rank : base1 + (rank - room)) : kInvalid;
 }
@@ -590,6 +697,10 @@ __device__ __forceinline__ uint32_t warp_reserve(WarpCursor& c, bool want, uint3
 // Pad what is left of the warp's last chunk so that consumers can skip it.
 __device__ __forceinline__ void warp_flush(const WarpCursor& c, uint32_t* __restrict__ queue) {
     for (uint32_t i = c.pos + (threadIdx.x & 31u); i < c.end; i += 32u) queue[i] = kInvalid;
+    if (c.has_next) { // a chunk reserved ahead of time and never used
+        const uint32_t base = __shfl_sync(kFull, c.next, 0);
+        for (uint32_t i = threadIdx.x & 31u; i < kChunk; i += 32u) queue[base + i] = kInvalid;
+    }
 }
 
 __device__ __forceinline__ unsigned warp_sum(unsigned v) {
@@ -618,7 +729,7 @@ struct Sorter {
         const int set = (next_bounce & 1) * 3;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            cur[k] = WarpCursor{0, 0};
+            cur[k] = WarpCursor{0, 0, 0, false};
             q[k] = a.q[set + k];
         }
         counters = a.counts + next_bounce * 4 + Q_DIFFUSE;
@@ -849,45 +960,50 @@ __device__ __forceinline__ RecView rec_queue(const PassArgs& a, int qi) { // qi 
     return r;
 }
 
-struct RecSorter { // the three record queues a launch feeds (the next bounce's)
-    WarpCursor cur[3];
+// The record queues a launch feeds (the next bounce's). SPEC = the scene has mirror or glass
+// materials; a diffuse-only scene keeps one cursor (registers: the three-cursor form spilled).
+template <bool SPEC> struct RecSorter {
+    WarpCursor cur[SPEC ? 3 : 1];
     uint32_t* counters;
     uint32_t mask;
     int set;
     __device__ __forceinline__ void init(const PassArgs& a, int next_bounce) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) cur[k] = WarpCursor{0, 0};
+        for (int k = 0; k < (SPEC ? 3 : 1); ++k) cur[k] = WarpCursor{0, 0, 0, false};
         set = (next_bounce & 1) * 3;
         counters = a.counts + next_bounce * 4 + Q_DIFFUSE;
-        mask = a.kind_mask;
+        mask = SPEC ? a.kind_mask : 1u;
     }
     // kind: G19_BSDF_DIFFUSE / MIRROR / GLASS, or -1 for "path ended". Returns the lane's position in
     // its kind's queue (kInvalid for ended paths). Called by all 32 lanes.
     __device__ __forceinline__ uint32_t reserve(int kind) {
+        if (!SPEC) return warp_reserve(cur[0], kind == 0, counters);
         uint32_t pos = kInvalid;
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < (SPEC ? 3 : 1); ++k)
             if (mask & (1u << k)) {
-                const uint32_t p = warp_reserve(cur[k], kind == k, counters + k);
+                // the specular queues fill slowly: an unused chunk would halve their consumers' lane efficiency
+                const uint32_t p = k == 0 ? warp_reserve<true>(cur[k], kind == k, counters + k)
+                                          : warp_reserve<false>(cur[k], kind == k, counters + k);
                 if (kind == k) pos = p;
             }
         return pos;
     }
     __device__ __forceinline__ void flush(const PassArgs& a) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < (SPEC ? 3 : 1); ++k)
             if (mask & (1u << k)) warp_flush(cur[k], a.q[set + k]);
     }
 };
 
 // ---- raygen + extend, flat scenes ------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 4) raygen_extend_flat_kernel(const PassArgs a) {
+template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_extend_flat_kernel(const PassArgs a) {
     pdl_launch_dependents();
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
     const SceneAccess<true> S = stage_scene<true>(a);
     pdl_wait(); // the previous pass's accumulate cleared the queue lengths and the radiance planes
-    RecSorter out;
+    RecSorter<SPEC> out;
     out.init(a, 0);
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
@@ -965,7 +1081,7 @@ __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, boo
 // One launch per material queue and bounce: next-event estimation, BSDF sample, the trace of BOTH
 // rays in one loop over the staged primitives, and the new vertex record written straight into
 // the next bounce's material queue.
-template <int KIND, bool FIRST, bool LAST>
+template <int KIND, bool FIRST, bool LAST, bool SPEC>
 __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_flat_kernel(const PassArgs a, const int bounce) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
     pdl_launch_dependents();
@@ -975,9 +1091,11 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_fl
     const uint32_t n = a.counts[bounce * 4 + KIND];
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     const RecView in = rec_queue(a, (bounce & 1) * 3 + (KIND - 1));
-    RecSorter out;
+    RecSorter<SPEC> out;
     if (!LAST) out.init(a, bounce + 1);
-    unsigned traced = 0, shadow_rays = 0, lit = 0, calls = 0, stored = 0;
+    // statistics (g19_stats), two 16-bit counters per register (a thread runs < 2^16 iterations: the grid
+    // has > 10^5 threads and a queue < 2^32 entries): calls | traced << 16, shadow rays | lit << 16
+    uint32_t cnt_a = 0, cnt_b = 0, stored = 0;
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
     const int tid = threadIdx.x;
@@ -996,7 +1114,6 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_fl
         float3 p_next = f3(0.f, 0.f, 0.f), d_next = f3(0.f, 0.f, 1.f), T = f3(1.f, 1.f, 1.f), Lp = f3(0.f, 0.f, 0.f);
         uint32_t prim_next = kInvalid, pixel = 0, sample = 0;
         if (slot != kInvalid) {
-            ++calls;
             const float4 hp = stage.hp[buf][tid], dw = stage.dw[buf][tid];
             const float3 p = f3(hp.x, hp.y, hp.z), d = f3(dw.x, dw.y, dw.z);
             const uint32_t prim = __float_as_uint(hp.w);
@@ -1012,9 +1129,8 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_fl
             }
             const Shaded sh = shade_vertex<KIND, LAST, true>(a, S, bounce, p, d, T, prim, pixel, sample);
             T = sh.T;
-            if (sh.want_shadow) ++shadow_rays;
             const bool cont = !LAST && (T.x > 0.0f || T.y > 0.0f || T.z > 0.0f);
-            if (cont) ++traced;
+            cnt_a += 1u + (cont ? 0x10000u : 0u);
             // ---- the rays of this vertex: shadow (any hit) and continuation (nearest hit) ----
             bool blocked = false;
             float t_hit = FLT_MAX;
@@ -1033,10 +1149,9 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_fl
                 trace_flat<false>(S, sh.no, sh.nd, FLT_MAX, sh.nd, -1.0f, t_hit, prim_hit, unused);
             }
             const bool hit = cont && prim_hit != kInvalid;
-            if (kDiffuse && sh.want_shadow && !blocked) {
-                ++lit;
-                Lp = Lp + sh.lit_rgb;
-            }
+            const bool lit = kDiffuse && sh.want_shadow && !blocked;
+            if (kDiffuse) cnt_b += (sh.want_shadow ? 1u : 0u) + (lit ? 0x10000u : 0u);
+            if (lit) Lp = Lp + sh.lit_rgb;
             if (hit) {
                 const float4 tag = S.hot_row(prim_hit, 3);
                 const int bsdf = __float_as_int(tag.y);
@@ -1078,10 +1193,8 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_fl
     }
     cp_async_wait<0>();
     if (!LAST) out.flush(a);
-    calls = warp_sum(calls);
-    traced = warp_sum(traced);
-    shadow_rays = warp_sum(shadow_rays);
-    lit = warp_sum(lit);
+    const unsigned calls = warp_sum(cnt_a & 0xffffu), traced = warp_sum(cnt_a >> 16);
+    const unsigned shadow_rays = warp_sum(cnt_b & 0xffffu), lit = warp_sum(cnt_b >> 16);
     stored = warp_sum(stored);
     if (lane == 0 && calls) {
         atomicAdd(a.totals + 2, (unsigned long long)calls);
@@ -1126,7 +1239,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
     const uint32_t n = a.counts[bounce * 4 + KIND];
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     const uint32_t* __restrict__ qin = a.q[(bounce & 1) * 3 + (KIND - 1)];
-    WarpCursor ray_cur = {0, 0};
+    WarpCursor ray_cur = {0, 0, 0, false};
     uint32_t* const ray_counter = a.counts + bounce * 4 + Q_RAYS;
     unsigned traced = 0, shadow_rays = 0, calls = 0;
     const uint32_t stride = gridDim.x * kThreads;
@@ -1201,6 +1314,10 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
     }
     cp_async_wait<0>();
     for (uint32_t i = ray_cur.pos + lane; i < ray_cur.end; i += 32u) a.ray1[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalid));
+    if (ray_cur.has_next) { // a chunk reserved ahead of time and never used
+        const uint32_t base = __shfl_sync(kFull, ray_cur.next, 0);
+        for (uint32_t i = lane; i < kChunk; i += 32u) a.ray1[base + i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalid));
+    }
     calls = warp_sum(calls);
     traced = warp_sum(traced);
     shadow_rays = warp_sum(shadow_rays);
@@ -1387,7 +1504,7 @@ static bool all_staged(const PassArgs& a) { // one leaf, everything in shared me
 
 size_t path_smem_bytes(const PassArgs& a) {
     size_t nb = (size_t(a.stage_nodes) * 8 + 15) & ~size_t(15);
-    size_t cb = all_staged(a) ? size_t(a.stage_cold) * 32 + size_t(a.stage_lights) * 80 : 0;
+    size_t cb = all_staged(a) ? size_t(a.stage_cold) * 32 + size_t(a.stage_lights) * 80 + size_t(a.scene.pairs_bytes) : 0;
     return nb + size_t(a.stage_prims) * 64 + cb + size_t(a.stack_levels) * kThreads * 4 + 16;
 }
 
@@ -1440,8 +1557,12 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, size_t smem, c
 template <int KIND, bool FIRST, bool LAST, bool ALL>
 static void launch_bounce_k(const PassArgs& a, int bounce, size_t smem, int sm_count, cudaStream_t s) {
     void (*kernel)(PassArgs, int);
-    if constexpr (ALL) kernel = bounce_flat_kernel<KIND, FIRST, LAST>;
-    else kernel = bounce_kernel<KIND, FIRST, LAST>;
+    if constexpr (ALL) {
+        if constexpr (KIND == Q_DIFFUSE) kernel = (a.kind_mask & 6u) ? bounce_flat_kernel<KIND, FIRST, LAST, true> : bounce_flat_kernel<KIND, FIRST, LAST, false>;
+        else kernel = bounce_flat_kernel<KIND, FIRST, LAST, true>;
+    } else {
+        kernel = bounce_kernel<KIND, FIRST, LAST>;
+    }
     const int grid = persistent_grid(kernel, smem, sm_count);
     cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);
     if (e != cudaSuccess) note_launch_error("bounce kernel launch", e, smem, grid);
@@ -1462,8 +1583,9 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
     cudaError_t e;
     int grid;
     if (all_staged(a)) {
-        grid = persistent_grid(raygen_extend_flat_kernel, smem, sm_count);
-        e = launch_pdl(raygen_extend_flat_kernel, grid, smem, s, a);
+        auto kernel = (a.kind_mask & 6u) ? raygen_extend_flat_kernel<true> : raygen_extend_flat_kernel<false>;
+        grid = persistent_grid(kernel, smem, sm_count);
+        e = launch_pdl(kernel, grid, smem, s, a);
     } else {
         grid = persistent_grid(raygen_extend_kernel, smem, sm_count);
         e = launch_pdl(raygen_extend_kernel, grid, smem, s, a);
