@@ -563,10 +563,10 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         }                                                                      \
     } while (0)
     if (P > w.capacity) {
-        PATH_CUDA(w.L.ensure(P * 3 * sizeof(float)));
+        PATH_CUDA(w.L.ensure(P * 4 * sizeof(float))); // flat scenes: float4 per slot; tree scenes: three planes
         PATH_CUDA(w.queues.ensure((P + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
         w.capacity = P;
-        PATH_CUDA(cudaMemsetAsync(w.L.p, 0, P * 3 * sizeof(float), s));
+        PATH_CUDA(cudaMemsetAsync(w.L.p, 0, P * 4 * sizeof(float), s));
     }
     const size_t plane = w.capacity;
     PATH_CUDA(w.counts.ensure((kMaxPathDepth + 1) * 5 * sizeof(uint32_t)));

@@ -139,7 +139,8 @@ struct PassArgs {
     float4* hp;            // vertex: hit point, primitive
     float4* dw;            // vertex: incoming direction, pixel
     float4* tp;            // throughput, sample (not written for the camera segment: 1, slot / n_local_pix)
-    float* L;              // 3 planes of capacity `plane`
+    float* L;              // radiance of the slot's path: tree scenes 3 planes of `plane` floats (added to as the path
+                           // goes), flat scenes float4[plane] (stored once, when the path ends)
     size_t plane;          // slots per plane (capacity)
     uint32_t* q[6];        // [bounce parity * 3 + (kind - 1)]
     uint32_t kind_mask;    // bit (kind - 1): the scene has a material of that class

@@ -1028,9 +1028,7 @@ template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_exten
             const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
             if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
                 const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
-                a.L[slot] = m.emission[0];
-                a.L[a.plane + slot] = m.emission[1];
-                a.L[2 * a.plane + slot] = m.emission[2];
+                reinterpret_cast<float4*>(a.L)[slot] = make_float4(m.emission[0], m.emission[1], m.emission[2], 0.0f);
             } else if (bsdf == G19_BSDF_DIFFUSE || a.max_depth > 1) {
                 kind = bsdf;
             }
@@ -1171,9 +1169,9 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_fl
             if (kind_next < 0 && (Lp.x != 0.0f || Lp.y != 0.0f || Lp.z != 0.0f)) {
                 // the path ends here: its radiance goes to the slot's accumulator input, once
                 ++stored;
-                a.L[slot] = Lp.x;
-                a.L[a.plane + slot] = Lp.y;
-                a.L[2 * a.plane + slot] = Lp.z;
+                // (slots are scattered by now: ONE 16-byte store, not three 4-byte stores into three planes --
+                // the last bounce of the depth-12 glass box spent 148 us on 37 M instructions doing those)
+                reinterpret_cast<float4*>(a.L)[slot] = make_float4(Lp.x, Lp.y, Lp.z, 0.0f);
             }
         }
         if (!LAST) {
@@ -1429,7 +1427,8 @@ __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, co
 }
 
 // ---- accumulate / resolve ---------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) {
+// FLAT: the finished paths' radiance is a float4 per slot (flat scenes); otherwise three planes.
+template <bool FLAT> __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) {
     pdl_launch_dependents();
     pdl_wait();
     const uint32_t npix = (uint32_t)a.map.n_local_pix, nwin = a.pix_count;
@@ -1437,34 +1436,54 @@ __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) 
     if (wp < nwin) {
         const uint32_t lp = a.pix_base + wp;
         float acc0 = a.accum[lp], acc1 = a.accum[(size_t)npix + lp], acc2 = a.accum[2 * (size_t)npix + lp];
-        float* L0 = a.L + wp;
-        float* L1 = a.L + a.plane + wp;
-        float* L2 = a.L + 2 * a.plane + wp;
         // strictly in sample order (independent of the pass split); loads batched four samples deep
-        int s = 0;
-        for (; s + 4 <= a.spp_pass; s += 4) {
-            float v0[4], v1[4], v2[4];
+        if constexpr (FLAT) {
+            float4* L = reinterpret_cast<float4*>(a.L) + wp;
+            int s = 0;
+            for (; s + 4 <= a.spp_pass; s += 4) {
+                float4 v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                size_t i = (size_t)(s + k) * nwin;
-                v0[k] = L0[i]; v1[k] = L1[i]; v2[k] = L2[i];
-            }
+                for (int k = 0; k < 4; ++k) v[k] = L[(size_t)(s + k) * nwin];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                size_t i = (size_t)(s + k) * nwin;
-                acc0 += v0[k]; acc1 += v1[k]; acc2 += v2[k];
-                if (v0[k] != 0.0f) L0[i] = 0.0f;
-                if (v1[k] != 0.0f) L1[i] = 0.0f;
-                if (v2[k] != 0.0f) L2[i] = 0.0f;
+                for (int k = 0; k < 4; ++k) {
+                    acc0 += v[k].x; acc1 += v[k].y; acc2 += v[k].z;
+                    if (v[k].x != 0.0f || v[k].y != 0.0f || v[k].z != 0.0f) L[(size_t)(s + k) * nwin] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-        }
-        for (; s < a.spp_pass; ++s) {
-            size_t i = (size_t)s * nwin;
-            float v0 = L0[i], v1 = L1[i], v2 = L2[i];
-            acc0 += v0; acc1 += v1; acc2 += v2;
-            if (v0 != 0.0f) L0[i] = 0.0f;
-            if (v1 != 0.0f) L1[i] = 0.0f;
-            if (v2 != 0.0f) L2[i] = 0.0f;
+            for (; s < a.spp_pass; ++s) {
+                const float4 v = L[(size_t)s * nwin];
+                acc0 += v.x; acc1 += v.y; acc2 += v.z;
+                if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) L[(size_t)s * nwin] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            float* L0 = a.L + wp;
+            float* L1 = a.L + a.plane + wp;
+            float* L2 = a.L + 2 * a.plane + wp;
+            int s = 0;
+            for (; s + 4 <= a.spp_pass; s += 4) {
+                float v0[4], v1[4], v2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    size_t i = (size_t)(s + k) * nwin;
+                    v0[k] = L0[i]; v1[k] = L1[i]; v2[k] = L2[i];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    size_t i = (size_t)(s + k) * nwin;
+                    acc0 += v0[k]; acc1 += v1[k]; acc2 += v2[k];
+                    if (v0[k] != 0.0f) L0[i] = 0.0f;
+                    if (v1[k] != 0.0f) L1[i] = 0.0f;
+                    if (v2[k] != 0.0f) L2[i] = 0.0f;
+                }
+            }
+            for (; s < a.spp_pass; ++s) {
+                size_t i = (size_t)s * nwin;
+                float v0 = L0[i], v1 = L1[i], v2 = L2[i];
+                acc0 += v0; acc1 += v1; acc2 += v2;
+                if (v0 != 0.0f) L0[i] = 0.0f;
+                if (v1 != 0.0f) L1[i] = 0.0f;
+                if (v2 != 0.0f) L2[i] = 0.0f;
+            }
         }
         a.accum[lp] = acc0;
         a.accum[(size_t)npix + lp] = acc1;
@@ -1630,7 +1649,7 @@ void path_clear_launch_error() { g_launch_error[0] = 0; }
 void launch_accumulate(const PassArgs& a, cudaStream_t s) {
     int blocks = int((a.pix_count + kThreads - 1) / kThreads);
     if (blocks < 1) blocks = 1;
-    cudaError_t e = launch_pdl(accumulate_kernel, blocks, 0, s, a);
+    cudaError_t e = all_staged(a) ? launch_pdl(accumulate_kernel<true>, blocks, 0, s, a) : launch_pdl(accumulate_kernel<false>, blocks, 0, s, a);
     if (e != cudaSuccess) note_launch_error("accumulate kernel launch", e, 0, blocks);
 }
 
