@@ -646,6 +646,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         pa.ray1 = pa.ray0 + ray_cap;
         pa.ray2 = pa.ray1 + ray_cap;
     }
+    const bool merge_kinds = std::getenv("G19_NO_MERGE") == nullptr; // tuning knob: one launch per material queue
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
     auto last_refresh = std::chrono::steady_clock::now();
@@ -667,9 +668,13 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             for (int bounce = 0; bounce < p.max_depth; ++bounce) {
                 clk.begin();
                 int n = 0;
-                for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
-                    if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
-                    if (launch_bounce(pa, bounce, kind, a.sm_count, s)) ++n;
+                if (merge_kinds && launch_bounce_merged(pa, bounce, a.sm_count, s)) {
+                    n = 1;
+                } else {
+                    for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
+                        if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
+                        if (launch_bounce(pa, bounce, kind, a.sm_count, s)) ++n;
+                    }
                 }
                 if (!fused && n > 0) { // tree scenes: one walk over the rays this bounce's vertices produced
                     launch_trace(pa, bounce, a.sm_count, s);

@@ -166,6 +166,8 @@ struct PassArgs {
 void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s);
 // false = nothing to launch for this (bounce, kind): specular vertices on the last segment
 bool launch_bounce(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s);
+// flat scenes with mirror / glass: the three material queues of a bounce in one launch; false = not applicable
+bool launch_bounce_merged(const PassArgs& a, int bounce, int sm_count, cudaStream_t s);
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s); // tree scenes: after the bounce's shade launches
 bool path_scene_is_flat(const PassArgs& a);
 void launch_accumulate(const PassArgs& a, cudaStream_t s);

@@ -1080,27 +1080,21 @@ __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, boo
 // rays in one loop over the staged primitives, and the new vertex record written straight into
 // the next bounce's material queue.
 template <int KIND, bool FIRST, bool LAST, bool SPEC>
-__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_flat_kernel(const PassArgs a, const int bounce) {
+__device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bounce, const SceneAccess<true>& S, const uint32_t n,
+                                                 const uint32_t cta, const uint32_t n_cta, RecStage<!FIRST>& stage) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
-    pdl_launch_dependents();
-    if (LAST && !kDiffuse) return; // a specular vertex on the last segment contributes nothing
-    const SceneAccess<true> S = stage_scene<true>(a); // does not depend on earlier kernels: overlaps their tail
-    pdl_wait();
-    const uint32_t n = a.counts[bounce * 4 + KIND];
-    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     const RecView in = rec_queue(a, (bounce & 1) * 3 + (KIND - 1));
     RecSorter<SPEC> out;
     if (!LAST) out.init(a, bounce + 1);
     // statistics (g19_stats), two 16-bit counters per register (a thread runs < 2^16 iterations: the grid
     // has > 10^5 threads and a queue < 2^32 entries): calls | traced << 16, shadow rays | lit << 16
     uint32_t cnt_a = 0, cnt_b = 0, stored = 0;
-    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t stride = n_cta * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
     const int tid = threadIdx.x;
     const bool next_last = bounce + 2 >= a.max_depth;
 
-    __shared__ RecStage<!FIRST> stage;
-    uint32_t q = blockIdx.x * kThreads + threadIdx.x;
+    uint32_t q = cta * kThreads + threadIdx.x;
     int buf = 0;
     prefetch_rec(in, q, q < n, stage, 0);
     for (; q - lane < n; q += stride) {
@@ -1202,6 +1196,49 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_fl
         if (lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
         if (stored) atomicAdd(a.totals + 6, (unsigned long long)stored);
     }
+}
+
+// One material queue per launch (diffuse-only scenes, and the last bounce of any scene).
+template <int KIND, bool FIRST, bool LAST, bool SPEC>
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_flat_kernel(const PassArgs a, const int bounce) {
+    pdl_launch_dependents();
+    if (LAST && KIND != Q_DIFFUSE) return; // a specular vertex on the last segment contributes nothing
+    const SceneAccess<true> S = stage_scene<true>(a); // does not depend on earlier kernels: overlaps their tail
+    pdl_wait();
+    const uint32_t n = a.counts[bounce * 4 + KIND];
+    if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
+    __shared__ RecStage<!FIRST> stage;
+    bounce_flat_body<KIND, FIRST, LAST, SPEC>(a, bounce, S, n, blockIdx.x, gridDim.x, stage);
+}
+
+// All three material queues of one bounce in ONE launch (scenes with mirror / glass). The mirror and
+// glass queues of a Cornell box hold a few per cent of the vertices: as launches of their own they
+// ran 1-2 records per thread at 50-60 % issue utilisation with nothing to overlap their latency
+// (ncu, profiles/r01c: 25 + 35 us next to the diffuse launch's 216 us, 21 of 34 launches per pass).
+// Here the grid's CTAs are split between the queues in proportion to their estimated work, so the
+// specular vertices fill issue slots beside the diffuse ones and a pass is 13 launches, not 34.
+// The per-material queues and kernels' code are unchanged: a CTA runs exactly one KIND.
+template <bool FIRST>
+__global__ void __launch_bounds__(kThreads, 3) bounce_flat_all_kernel(const PassArgs a, const int bounce) {
+    pdl_launch_dependents();
+    const SceneAccess<true> S = stage_scene<true>(a);
+    pdl_wait();
+    const uint32_t n1 = a.counts[bounce * 4 + Q_DIFFUSE], n2 = a.counts[bounce * 4 + Q_MIRROR], n3 = a.counts[bounce * 4 + Q_GLASS];
+    // estimated work per queue entry relative to a diffuse vertex (two rays, light sample): measured
+    // instructions per entry, padding of the sparsely filled specular chunks included
+    const float w1 = float(n1), w2 = 0.45f * float(n2), w3 = 0.6f * float(n3);
+    const float total = w1 + w2 + w3;
+    if (total <= 0.0f) return;
+    const uint32_t G = gridDim.x;
+    uint32_t g2 = n2 ? max(1u, min(uint32_t(float(G) * w2 / total + 0.5f), (n2 + kThreads - 1) / kThreads)) : 0u;
+    uint32_t g3 = n3 ? max(1u, min(uint32_t(float(G) * w3 / total + 0.5f), (n3 + kThreads - 1) / kThreads)) : 0u;
+    if (g2 + g3 >= G) { g2 = min(g2, G / 3); g3 = min(g3, G / 3); }
+    const uint32_t g1 = n1 ? min(G - g2 - g3, (n1 + kThreads - 1) / kThreads) : 0u;
+    __shared__ RecStage<!FIRST> stage;
+    const uint32_t b = blockIdx.x;
+    if (b < g1) bounce_flat_body<Q_DIFFUSE, FIRST, false, true>(a, bounce, S, n1, b, g1, stage);
+    else if (b < g1 + g2) bounce_flat_body<Q_MIRROR, FIRST, false, true>(a, bounce, S, n2, b - g1, g2, stage);
+    else if (b < g1 + g2 + g3) bounce_flat_body<Q_GLASS, FIRST, false, true>(a, bounce, S, n3, b - g1 - g2, g3, stage);
 }
 
 // ---- bounce, tree scenes: shade and queue the rays -----------------------------------------
@@ -1620,6 +1657,18 @@ void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
 }
 
 bool path_scene_is_flat(const PassArgs& a) { return all_staged(a); }
+
+// Flat scenes with specular materials: one launch serves the three queues of a bounce (not the last).
+bool launch_bounce_merged(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
+    const bool first = bounce == 0, last = bounce + 1 >= a.max_depth;
+    if (!all_staged(a) || last || !(a.kind_mask & 6u)) return false;
+    const size_t smem = path_smem_bytes(a);
+    void (*kernel)(PassArgs, int) = first ? bounce_flat_all_kernel<true> : bounce_flat_all_kernel<false>;
+    const int grid = persistent_grid(kernel, smem, sm_count);
+    cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);
+    if (e != cudaSuccess) note_launch_error("merged bounce kernel launch", e, smem, grid);
+    return true;
+}
 
 bool launch_bounce(const PassArgs& a, int bounce, int kind, int sm_count, cudaStream_t s) {
     const bool last = bounce + 1 >= a.max_depth;
