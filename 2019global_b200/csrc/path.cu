@@ -492,9 +492,19 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &w.hp, &w.dw, &w.tp,
-                           &w.L, &w.queues, &w.recs, &w.rays, &w.counts, &w.totals, &w.accum, &w.rad_l, &w.rgb_l})
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &w.totals, &w.accum,
+                           &w.rad_l, &w.rgb_l})
         d->release();
+    for (PathLane& l : w.lane) {
+        for (DeviceArray* d : {&l.hp, &l.dw, &l.tp, &l.L, &l.queues, &l.recs, &l.rays, &l.counts}) d->release();
+        l.capacity = 0;
+    }
+    if (w.side) cudaStreamDestroy(w.side);
+    w.side = nullptr;
+    for (cudaEvent_t* e : {&w.ev_fork, &w.ev_join, &w.ev_acc[0], &w.ev_acc[1]}) {
+        if (*e) cudaEventDestroy(*e);
+        *e = nullptr;
+    }
     if (w.events) {
         for (int i = 0; i < w.n_events; ++i) cudaEventDestroy(w.events[i]);
         delete[] w.events;
@@ -562,19 +572,19 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             return G19_ERR_CUDA;                                               \
         }                                                                      \
     } while (0)
-    if (P > w.capacity) {
-        PATH_CUDA(w.L.ensure(P * 4 * sizeof(float))); // flat scenes: float4 per slot; tree scenes: three planes
-        PATH_CUDA(w.queues.ensure((P + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
-        w.capacity = P;
-        PATH_CUDA(cudaMemsetAsync(w.L.p, 0, P * 4 * sizeof(float), s));
+    // passes of this frame, and how many are kept in flight (see PathWork)
+    const size_t n_windows = (npix + window - 1) / window;
+    const size_t n_passes = n_windows * size_t((p.spp + spp_pass - 1) / spp_pass);
+    int n_lanes = (n_passes >= 2 && !p.profile && !a.on_pass) ? 2 : 1; // profiling and progressive refresh: one at a time
+    if (const char* v = std::getenv("G19_LANES")) n_lanes = std::max(1, std::min(n_lanes, std::atoi(v))); // tuning knob
+    if (n_lanes == 2 && !w.side) {
+        PATH_CUDA(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&w.ev_fork, &w.ev_join, &w.ev_acc[0], &w.ev_acc[1]}) PATH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
-    const size_t plane = w.capacity;
-    PATH_CUDA(w.counts.ensure((kMaxPathDepth + 1) * 5 * sizeof(uint32_t)));
     PATH_CUDA(w.totals.ensure(8 * sizeof(unsigned long long)));
     PATH_CUDA(w.accum.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rad_l.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rgb_l.ensure(npix * 3));
-    PATH_CUDA(cudaMemsetAsync(w.counts.p, 0, (kMaxPathDepth + 1) * 5 * sizeof(uint32_t), s));
     PATH_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(unsigned long long), s));
     PATH_CUDA(cudaMemsetAsync(w.accum.p, 0, npix * 3 * sizeof(float), s));
     if (p.profile && !w.events) {
@@ -584,121 +594,154 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     }
     w.used_events = 0;
 
-    PassArgs pa;
-    pa.scene = b.view;
+    PassArgs pa0;
+    pa0.scene = b.view;
     for (int k = 0; k < 3; ++k) {
-        pa.cam.pos[k] = float(a.cam.pos[k]);
-        pa.cam.top_left[k] = float(a.cam.top_left[k]);
-        pa.cam.left[k] = float(a.cam.left[k]);
-        pa.cam.up[k] = float(a.cam.up[k]);
+        pa0.cam.pos[k] = float(a.cam.pos[k]);
+        pa0.cam.top_left[k] = float(a.cam.top_left[k]);
+        pa0.cam.left[k] = float(a.cam.left[k]);
+        pa0.cam.up[k] = float(a.cam.up[k]);
     }
-    pa.map = a.map;
-    pa.seed = p.seed;
-    pa.max_depth = p.max_depth;
-    pa.L = static_cast<float*>(w.L.p);
-    pa.plane = plane;
-    pa.queue_cap = plane + kQueueSlack;
-    for (int k = 0; k < kNumQueues; ++k) pa.q[k] = static_cast<uint32_t*>(w.queues.p) + size_t(k) * pa.queue_cap;
-    pa.kind_mask = (b.has_bsdf[G19_BSDF_DIFFUSE] ? 1u : 0u) | (b.has_bsdf[G19_BSDF_MIRROR] ? 2u : 0u) |
-                   (b.has_bsdf[G19_BSDF_GLASS] ? 4u : 0u);
-    pa.counts = static_cast<uint32_t*>(w.counts.p);
-    pa.totals = static_cast<unsigned long long*>(w.totals.p);
-    pa.accum = static_cast<float*>(w.accum.p);
+    pa0.map = a.map;
+    pa0.seed = p.seed;
+    pa0.max_depth = p.max_depth;
+    pa0.kind_mask = (b.has_bsdf[G19_BSDF_DIFFUSE] ? 1u : 0u) | (b.has_bsdf[G19_BSDF_MIRROR] ? 2u : 0u) |
+                    (b.has_bsdf[G19_BSDF_GLASS] ? 4u : 0u);
+    pa0.totals = static_cast<unsigned long long*>(w.totals.p);
+    pa0.accum = static_cast<float*>(w.accum.p);
 
     // stage the breadth-first prefix of the tree and the first primitives (<= ~24 KB)
-    pa.stage_nodes = std::min(b.view.n_nodes, 1024);
+    pa0.stage_nodes = std::min(b.view.n_nodes, 1024);
     // flat scene (one leaf, <= 192 primitives): intersection + shading records and lights staged whole;
     // a tree scene reaches its primitives through leaf index lists, so only the node prefix is staged
     const bool flat = b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= 192;
-    pa.stage_prims = flat ? b.view.n_prims : 0;
-    pa.stage_cold = flat ? b.view.n_prims : 0;
-    pa.stage_lights = (pa.stage_cold > 0 && b.view.n_lights <= 32) ? b.view.n_lights : 0;
-    if (b.view.n_lights > 32) pa.stage_cold = 0; // not a "flat, fully staged" scene: the generic kernels take it
-    pa.stack_levels = b.view.tree_depth + 1;
+    pa0.stage_prims = flat ? b.view.n_prims : 0;
+    pa0.stage_cold = flat ? b.view.n_prims : 0;
+    pa0.stage_lights = (pa0.stage_cold > 0 && b.view.n_lights <= 32) ? b.view.n_lights : 0;
+    if (b.view.n_lights > 32) pa0.stage_cold = 0; // not a "flat, fully staged" scene: the generic kernels take it
+    pa0.stack_levels = b.view.tree_depth + 1;
     // tree scenes: the bounce kernels queue their rays (2 per vertex at most) for trace_kernel
-    pa.refill = 8;
-    if (const char* v = std::getenv("G19_REFILL")) pa.refill = std::max(1, std::min(32, std::atoi(v))); // tuning knob
-    const bool fused = path_scene_is_flat(pa); // flat scenes trace inside the bounce kernels
-    pa.ray0 = pa.ray1 = pa.ray2 = nullptr;
-    pa.hp = pa.dw = pa.tp = nullptr;
-    pa.rec_hp = pa.rec_dw = pa.rec_tp = nullptr;
-    pa.rec_L = nullptr;
-    if (fused) {
-        // dense vertex records: three float4 planes and three float planes per queue
-        const size_t cap = pa.queue_cap, nq = kNumQueues;
-        PATH_CUDA(w.recs.ensure(nq * cap * (3 * sizeof(float4) + 3 * sizeof(float))));
-        pa.rec_hp = static_cast<float4*>(w.recs.p);
-        pa.rec_dw = pa.rec_hp + nq * cap;
-        pa.rec_tp = pa.rec_dw + nq * cap;
-        pa.rec_L = reinterpret_cast<float*>(pa.rec_tp + nq * cap);
-    } else {
-        PATH_CUDA(w.hp.ensure(plane * sizeof(float4)));
-        PATH_CUDA(w.dw.ensure(plane * sizeof(float4)));
-        PATH_CUDA(w.tp.ensure(plane * sizeof(float4)));
-        pa.hp = static_cast<float4*>(w.hp.p);
-        pa.dw = static_cast<float4*>(w.dw.p);
-        pa.tp = static_cast<float4*>(w.tp.p);
+    pa0.refill = 8;
+    if (const char* v = std::getenv("G19_REFILL")) pa0.refill = std::max(1, std::min(32, std::atoi(v))); // tuning knob
+    const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
+
+    // per-lane buffers
+    PassArgs lanes[2] = {pa0, pa0};
+    cudaStream_t lane_stream[2] = {s, n_lanes == 2 ? w.side : s};
+    for (int li = 0; li < n_lanes; ++li) {
+        PathLane& l = w.lane[li];
+        PassArgs& pa = lanes[li];
+        if (P > l.capacity) {
+            PATH_CUDA(l.L.ensure(P * 4 * sizeof(float))); // flat scenes: float4 per slot; tree scenes: three planes
+            PATH_CUDA(l.queues.ensure((P + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
+            l.capacity = P;
+            PATH_CUDA(cudaMemsetAsync(l.L.p, 0, P * 4 * sizeof(float), s));
+        }
+        const size_t plane = l.capacity;
+        PATH_CUDA(l.counts.ensure((kMaxPathDepth + 1) * 5 * sizeof(uint32_t)));
+        PATH_CUDA(cudaMemsetAsync(l.counts.p, 0, (kMaxPathDepth + 1) * 5 * sizeof(uint32_t), s));
+        pa.L = static_cast<float*>(l.L.p);
+        pa.plane = plane;
+        pa.queue_cap = plane + kQueueSlack;
+        for (int k = 0; k < kNumQueues; ++k) pa.q[k] = static_cast<uint32_t*>(l.queues.p) + size_t(k) * pa.queue_cap;
+        pa.counts = static_cast<uint32_t*>(l.counts.p);
+        pa.ray0 = pa.ray1 = pa.ray2 = nullptr;
+        pa.hp = pa.dw = pa.tp = nullptr;
+        pa.rec_hp = pa.rec_dw = pa.rec_tp = nullptr;
+        pa.rec_L = nullptr;
+        if (fused) {
+            // dense vertex records: three float4 planes and three float planes per queue
+            const size_t cap = pa.queue_cap, nq = kNumQueues;
+            PATH_CUDA(l.recs.ensure(nq * cap * (3 * sizeof(float4) + 3 * sizeof(float))));
+            pa.rec_hp = static_cast<float4*>(l.recs.p);
+            pa.rec_dw = pa.rec_hp + nq * cap;
+            pa.rec_tp = pa.rec_dw + nq * cap;
+            pa.rec_L = reinterpret_cast<float*>(pa.rec_tp + nq * cap);
+        } else {
+            PATH_CUDA(l.hp.ensure(plane * sizeof(float4)));
+            PATH_CUDA(l.dw.ensure(plane * sizeof(float4)));
+            PATH_CUDA(l.tp.ensure(plane * sizeof(float4)));
+            pa.hp = static_cast<float4*>(l.hp.p);
+            pa.dw = static_cast<float4*>(l.dw.p);
+            pa.tp = static_cast<float4*>(l.tp.p);
+            const size_t ray_cap = 2 * plane + kQueueSlack;
+            PATH_CUDA(l.rays.ensure(3 * ray_cap * sizeof(float4)));
+            pa.ray0 = static_cast<float4*>(l.rays.p);
+            pa.ray1 = pa.ray0 + ray_cap;
+            pa.ray2 = pa.ray1 + ray_cap;
+        }
     }
-    if (!fused) {
-        const size_t ray_cap = 2 * plane + kQueueSlack;
-        PATH_CUDA(w.rays.ensure(3 * ray_cap * sizeof(float4)));
-        pa.ray0 = static_cast<float4*>(w.rays.p);
-        pa.ray1 = pa.ray0 + ray_cap;
-        pa.ray2 = pa.ray1 + ray_cap;
+    if (n_lanes == 2) { // lane 1 starts after everything enqueued so far on the caller's stream
+        PATH_CUDA(cudaEventRecord(w.ev_fork, s));
+        PATH_CUDA(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
     }
     const bool merge_kinds = std::getenv("G19_NO_MERGE") == nullptr; // tuning knob: one launch per material queue
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
     auto last_refresh = std::chrono::steady_clock::now();
+    size_t pass_index = 0;
+    bool acc_recorded[2] = {false, false};
+    int batch_spp = 0;
     for (int base = 0; base < p.spp; base += spp_pass) {
         if (a.cancel && a.cancel->load()) { // RayTracer::stop(): honoured between passes
             rc = G19_ERR_CANCELLED;
             break;
         }
-        pa.sample_base = base;
-        pa.spp_pass = std::min(spp_pass, p.spp - base);
-        for (size_t pix0 = 0; pix0 < npix; pix0 += window) { // the windows of this sample batch
+        batch_spp = std::min(spp_pass, p.spp - base);
+        for (size_t pix0 = 0; pix0 < npix; pix0 += window, ++pass_index) { // the windows of this sample batch
+            const int li = n_lanes == 2 ? int(pass_index & 1) : 0;
+            PassArgs& pa = lanes[li];
+            cudaStream_t ls = lane_stream[li];
+            clk.s = ls;
+            pa.sample_base = base;
+            pa.spp_pass = batch_spp;
             pa.pix_base = uint32_t(pix0);
             pa.pix_count = uint32_t(std::min(window, npix - pix0));
             pa.n_slots = uint32_t(size_t(pa.pix_count) * size_t(pa.spp_pass));
             clk.begin();
-            launch_raygen_extend(pa, a.sm_count, s); // camera segment
+            launch_raygen_extend(pa, a.sm_count, ls); // camera segment
             clk.end(G19_K_EXTEND);
             stats.class_launches[G19_K_EXTEND] += 1;
             for (int bounce = 0; bounce < p.max_depth; ++bounce) {
                 clk.begin();
                 int n = 0;
-                if (merge_kinds && launch_bounce_merged(pa, bounce, a.sm_count, s)) {
+                if (merge_kinds && launch_bounce_merged(pa, bounce, a.sm_count, ls)) {
                     n = 1;
                 } else {
                     for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
                         if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
-                        if (launch_bounce(pa, bounce, kind, a.sm_count, s)) ++n;
+                        if (launch_bounce(pa, bounce, kind, a.sm_count, ls)) ++n;
                     }
                 }
                 if (!fused && n > 0) { // tree scenes: one walk over the rays this bounce's vertices produced
-                    launch_trace(pa, bounce, a.sm_count, s);
+                    launch_trace(pa, bounce, a.sm_count, ls);
                     ++n;
                 }
                 clk.end(G19_K_SHADE);
                 stats.class_launches[G19_K_SHADE] += n;
             }
+            // the per-pixel sums are taken in pass order whichever lane a pass ran on
+            if (n_lanes == 2 && acc_recorded[li ^ 1]) PATH_CUDA(cudaStreamWaitEvent(ls, w.ev_acc[li ^ 1], 0));
             clk.begin();
-            launch_accumulate(pa, s);
+            launch_accumulate(pa, ls);
             clk.end(G19_K_ACCUM);
             stats.class_launches[G19_K_ACCUM] += 1;
+            if (n_lanes == 2) {
+                PATH_CUDA(cudaEventRecord(w.ev_acc[li], ls));
+                acc_recorded[li] = true;
+            }
         }
-        stats.samples += uint64_t(pa.spp_pass); // scaled by owned pixels below
-        if (a.progress_milli) a.progress_milli->store(int(1000.0 * double(base + pa.spp_pass) / double(p.spp)));
-        if (a.on_pass && a.d_rgb && a.h_rgb && base + pa.spp_pass < p.spp) {
+        stats.samples += uint64_t(batch_spp); // scaled by owned pixels below
+        if (a.progress_milli) a.progress_milli->store(int(1000.0 * double(base + batch_spp) / double(p.spp)));
+        if (a.on_pass && a.d_rgb && a.h_rgb && base + batch_spp < p.spp) {
             // progressive refresh: the host stays at most one pass ahead of the device (that is also
             // the cancellation latency), and repaints no more often than the caller asked for
             PATH_CUDA(cudaStreamSynchronize(s));
             const auto now = std::chrono::steady_clock::now();
             if (std::chrono::duration<double, std::milli>(now - last_refresh).count() >= double(a.min_interval_ms)) {
                 last_refresh = now;
-                const int so_far = base + pa.spp_pass;
-                launch_resolve(a.map, pa.accum, so_far, static_cast<float*>(w.rad_l.p), static_cast<uint8_t*>(w.rgb_l.p), s);
+                const int so_far = base + batch_spp;
+                launch_resolve(a.map, pa0.accum, so_far, static_cast<float*>(w.rad_l.p), static_cast<uint8_t*>(w.rgb_l.p), s);
                 launch_untile(a.map, static_cast<uint8_t*>(w.rgb_l.p), nullptr, nullptr, a.d_rgb, nullptr, nullptr, s);
                 PATH_CUDA(cudaMemcpyAsync(a.h_rgb, a.d_rgb, size_t(a.map.w) * size_t(a.map.h) * 3, cudaMemcpyDeviceToHost, s));
                 PATH_CUDA(cudaStreamSynchronize(s));
@@ -707,18 +750,23 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             }
         }
     }
+    if (n_lanes == 2) { // join: the caller's stream continues after lane 1
+        PATH_CUDA(cudaEventRecord(w.ev_join, w.side));
+        PATH_CUDA(cudaStreamWaitEvent(s, w.ev_join, 0));
+    }
+    clk.s = s;
     const int done_spp = int(stats.samples);
     clk.begin();
     if (a.frame_flags) {
         // fused resolve + untile + gather: wait until the owner is done with the previous frame,
         // store this rank's pixels into the shared frame, then signal arrival
         launch_frame_acquire(a.frame_flags, a.frame_need_consumed, s);
-        launch_resolve_to_frame(a.map, pa.accum, done_spp > 0 ? done_spp : 1, a.frame_rgb, a.frame_rad, s);
+        launch_resolve_to_frame(a.map, pa0.accum, done_spp > 0 ? done_spp : 1, a.frame_rgb, a.frame_rad, s);
         launch_frame_signal(a.frame_flags, s);
         clk.end(G19_K_OTHER);
         stats.class_launches[G19_K_OTHER] += 3;
     } else {
-        launch_resolve(a.map, pa.accum, done_spp > 0 ? done_spp : 1, static_cast<float*>(w.rad_l.p),
+        launch_resolve(a.map, pa0.accum, done_spp > 0 ? done_spp : 1, static_cast<float*>(w.rad_l.p),
                        static_cast<uint8_t*>(w.rgb_l.p), s);
         const bool to_frame = a.d_rgb || a.d_rad;
         if (to_frame)

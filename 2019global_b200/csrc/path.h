@@ -66,18 +66,26 @@ struct PathSceneBuffers {
     bool has_bsdf[4] = {false, false, false, false};
 };
 
-// SoA wavefront state for one pass of P path slots (slot = sample_in_pass * n_local_pix + local_pixel).
-struct PathWork {
+// Wavefront state of ONE pass in flight (P path slots, slot = sample_in_pass * window + pixel_in_window).
+struct PathLane {
     size_t capacity = 0;       // slots
-    DeviceArray hp;            // float4[P]: hit point of the path's current vertex, primitive id bits
-    DeviceArray dw;            // float4[P]: direction the path arrived with, global pixel index bits
-    DeviceArray tp;            // float4[P]: throughput.rgb, sample index bits
-    DeviceArray L;             // float[3][P]: radiance gathered by the path so far
+    DeviceArray hp, dw, tp;    // tree scenes: float4[P] vertex state by slot (hit point+primitive, direction+pixel, throughput+sample)
+    DeviceArray L;             // radiance of the slot's path: float4[P] (flat scenes) / float[3][P] (tree scenes)
     DeviceArray queues;        // uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
     DeviceArray recs;          // flat scenes: float4[3][6][P + slack] + float[6][3][P + slack] dense vertex records
-    size_t rec_capacity = 0;
     DeviceArray rays;          // float4[3][2P + slack]: ray queue of one bounce (tree scenes only)
     DeviceArray counts;        // uint32[kMaxPathDepth+1][5]: queue lengths per bounce + ray fetch cursors
+};
+
+// Two passes are kept in flight, each on its own stream with its own PathLane: a pass is a chain of
+// 7-40 dependent kernels, every one of which ends in a tail where SMs idle (ncu: sm__cycles_active
+// 84-95 % of elapsed; the deep bounces of tree scenes run a handful of long rays at 15 % issue
+// utilisation) -- the other pass's kernels fill those holes. Only `accumulate` is ordered across
+// the lanes (events), so the per-pixel sums are still taken in sample order.
+struct PathWork {
+    PathLane lane[2];
+    cudaStream_t side = nullptr;          // lane 1's stream (lane 0 runs on the caller's)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_acc[2] = {nullptr, nullptr};
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
     DeviceArray accum;         // float[3][n_local_pix]
     DeviceArray rad_l, rgb_l;  // resolved local-pixel outputs

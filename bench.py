@@ -317,12 +317,22 @@ def main():
     n_launch = {"raygen_extend": agg["launch"][abi.K_EXTEND], "bounce": agg["launch"][abi.K_SHADE],
                 "accumulate": agg["launch"][abi.K_ACCUM]}
     achieved = bytes_cls[top] / (ms_cls[top] * 1e-3) / 1e9 if ms_cls[top] > 0 else 0.0
-    traffic, issue_pct = None, None
+    traffic, issue_pct, issue = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tj = json.load(f)
             traffic = tj.get(top)
             issue_pct = tj.get("issue_active_pct", {}).get(top)
+            # the issue-slot roofline (SURVEY.md 8(d) "issue bound"): warp instructions per launch (ncu, same
+            # pass size as this run's) over the live launch time, against SMs x 4 schedulers x SM clock
+            winst = tj.get("warp_inst_per_launch", {}).get(top)
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            props = torch.cuda.get_device_properties(local)
+            if winst and ms_cls[top] > 0:
+                peak_i = props.multi_processor_count * 4 * sm_hz
+                ach_i = winst / (ms_cls[top] / max(1, n_launch[top]) * 1e-3)
+                issue = {"warp_inst_per_launch": winst, "achieved_Ginst_s": ach_i / 1e9, "peak_Ginst_s": peak_i / 1e9,
+                         "frac": ach_i / peak_i, "source": "profiles/roofline_traffic.json (ncu smsp__inst_executed.sum)"}
     except Exception:
         pass
     total_bytes = sum(bytes_cls.values())
@@ -332,7 +342,8 @@ def main():
         "bytes_per_launch": bytes_cls[top] / max(1, n_launch[top]),
         "avg_launch_ms": ms_cls[top] / max(1, n_launch[top]),
         "share_of_step": ms_cls[top] / max(1e-9, sum(cls_ms)),
-        "binding_resource": "issue slots (ncu: smsp__issue_active %s%% of peak, DRAM ~15%%) -- see DESIGN.md section 5" % issue_pct,
+        "binding_resource": "issue slots (ncu: smsp__issue_active %s%% of peak) -- see DESIGN.md section 5" % issue_pct,
+        "issue": issue,
         "per_class": {k: {"ms_per_step": ms_cls[k] / args.steps, "launches_per_step": n_launch[k] / args.steps,
                           "algorithmic_GB_per_step": bytes_cls[k] / args.steps / 1e9,
                           "GBps": (bytes_cls[k] / (ms_cls[k] * 1e-3) / 1e9) if ms_cls[k] > 0 else None}

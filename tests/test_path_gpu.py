@@ -212,3 +212,36 @@ def test_progressive_refreshes_and_cancel(g19, abi):
     rt1.start()
     r = rt1.run_progressive(200, 200, lambda f, rgb: seen.append(f) or False, mode=abi.MODE_REF)
     assert seen == [1.0] and np.array_equal(r["rgb"], rt1.run(200, 200)["rgb"])
+
+
+@pytest.mark.parametrize("n_quads,n_tris,n_spheres", [(1, 0, 0), (0, 1, 1), (1, 1, 1), (2, 3, 2), (3, 2, 3), (0, 0, 2)])
+def test_flat_scene_pair_padding(g19, abi, oracle, n_quads, n_tris, n_spheres):
+    """Flat scenes run their primitives two at a time through the packed-FP32 loops; each kind group
+    (parallelograms | triangles | spheres) is padded to an even count with a NaN record. Odd and even
+    group sizes, empty groups and every BSDF class must agree with the brute-force oracle."""
+    sc = g19.Octree((-20,) * 3, (20,) * 3)
+    # the emitter: one triangle overhead (always present; counts as a triangle of the scene)
+    sc.push_back(g19.ImpTriangle((-4, -6, 7), (-4, 6, 7), (8, 0, 7), (1, 1, 1), bsdf=abi.BSDF_EMITTER, emission=(9.0, 8.0, 7.0)))
+    quads = [((6, -8, -8), (6, 8, -8), (6, 8, 8), (6, -8, 8)),      # back wall
+             ((-8, -8, -1.5), (6, -8, -1.5), (6, 8, -1.5), (-8, 8, -1.5)),  # floor
+             ((-8, 7, -8), (6, 7, -8), (6, 7, 8), (-8, 7, 8))]      # side wall
+    for a, b, c, d in quads[:n_quads]:  # two coplanar triangles each: the builder merges them into one parallelogram
+        sc.push_back(g19.ImpTriangle(a, b, c, (0.7, 0.6, 0.5)))
+        sc.push_back(g19.ImpTriangle(a, c, d, (0.7, 0.6, 0.5)))
+    tris = [((2, -3, -1), (2, 3, -1), (2, 0, 4)), ((3, -6, 0), (4, -2, -1), (3, -4, 4)), ((1, 2, -1), (3, 5, 0), (2, 3, 4))]
+    for k, (a, b, c) in enumerate(tris[:n_tris]):
+        sc.push_back(g19.ImpTriangle(a, b, c, (0.2 + 0.3 * k, 0.8, 0.4)))
+    spheres = [((2, 2, 1), 1.5, abi.BSDF_DIFFUSE), ((1, -3, 2), 1.2, abi.BSDF_MIRROR), ((-1, 0, 0.5), 1.0, abi.BSDF_GLASS)]
+    for pos, r, bsdf in spheres[:n_spheres]:
+        sc.push_back(g19.ImpSphere(pos, r, (0.9, 0.9, 0.9), bsdf=bsdf))
+    cam = g19.Camera((-10, 0, 0), (1, 0, 0), 0.02)
+    w, h, spp, depth = 96, 64, 8, 6
+    rt, got, st = _gpu(g19, abi, sc, cam, (0, 0, 0), w, h, spp=spp, max_depth=depth, seed=5)
+    exp, segs = binding.path_render(mirror(oracle, sc), cam, w, h, spp, depth, seed=5)
+    assert exp.mean() > 0.005
+    err = rel_rmse(got["radiance"], exp)
+    print("pairs (%d,%d,%d): same-seed relRMSE %.3e, segments gpu %d/%d cpu %d/%d" % (
+        n_quads, n_tris, n_spheres, err, st.extend_segments, st.shadow_segments, segs[0], segs[1]))
+    assert err <= 1e-2
+    assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
+    assert abs(int(st.shadow_segments) - segs[1]) <= 1e-3 * segs[1] + 2
