@@ -499,12 +499,16 @@ void path_release(PathSceneBuffers& b, PathWork& w) {
         for (DeviceArray* d : {&l.hp, &l.dw, &l.tp, &l.L, &l.queues, &l.recs, &l.rays, &l.counts}) d->release();
         l.capacity = 0;
     }
-    if (w.side) cudaStreamDestroy(w.side);
-    w.side = nullptr;
-    for (cudaEvent_t* e : {&w.ev_fork, &w.ev_join, &w.ev_acc[0], &w.ev_acc[1]}) {
-        if (*e) cudaEventDestroy(*e);
-        *e = nullptr;
+    for (int i = 0; i < kMaxLanes; ++i) {
+        if (w.side[i]) cudaStreamDestroy(w.side[i]);
+        w.side[i] = nullptr;
+        for (cudaEvent_t* e : {&w.ev_join[i], &w.ev_acc[i]}) {
+            if (*e) cudaEventDestroy(*e);
+            *e = nullptr;
+        }
     }
+    if (w.ev_fork) cudaEventDestroy(w.ev_fork);
+    w.ev_fork = nullptr;
     if (w.events) {
         for (int i = 0; i < w.n_events; ++i) cudaEventDestroy(w.events[i]);
         delete[] w.events;
@@ -559,6 +563,11 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     int spp_pass = p.spp_per_pass;
     if (spp_pass <= 0) spp_pass = int(std::max<size_t>(1, target / window));
     spp_pass = std::min(spp_pass, p.spp);
+    // enough passes to keep kMaxLanes of them in flight (PathWork), as long as a pass still fills the machine
+    if (p.spp_per_pass <= 0)
+        while (spp_pass > 1 && ((npix + window - 1) / window) * size_t((p.spp + spp_pass - 1) / spp_pass) < size_t(kMaxLanes) &&
+               window * size_t((spp_pass + 1) / 2) >= (size_t(1) << 21))
+            spp_pass = (spp_pass + 1) / 2;
     const size_t P = window * size_t(spp_pass);
     if (P > 0xfffffff0ull) {
         err = "pass too large";
@@ -575,11 +584,16 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     // passes of this frame, and how many are kept in flight (see PathWork)
     const size_t n_windows = (npix + window - 1) / window;
     const size_t n_passes = n_windows * size_t((p.spp + spp_pass - 1) / spp_pass);
-    int n_lanes = (n_passes >= 2 && !p.profile && !a.on_pass) ? 2 : 1; // profiling and progressive refresh: one at a time
-    if (const char* v = std::getenv("G19_LANES")) n_lanes = std::max(1, std::min(n_lanes, std::atoi(v))); // tuning knob
-    if (n_lanes == 2 && !w.side) {
-        PATH_CUDA(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
-        for (cudaEvent_t* e : {&w.ev_fork, &w.ev_join, &w.ev_acc[0], &w.ev_acc[1]}) PATH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    int n_lanes = (p.profile || a.on_pass) ? 1 : int(std::min<size_t>(kMaxLanes, n_passes)); // profiling and progressive refresh: one at a time
+    if (const char* v = std::getenv("G19_LANES")) // tuning knob
+        n_lanes = std::max(1, std::min(std::min<int>(kMaxLanes, int(n_passes)), (p.profile || a.on_pass) ? 1 : std::atoi(v)));
+    if (n_lanes > 1 && !w.ev_fork) PATH_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < n_lanes; ++i) {
+        if (i > 0 && !w.side[i]) PATH_CUDA(cudaStreamCreateWithFlags(&w.side[i], cudaStreamNonBlocking));
+        if (n_lanes > 1 && !w.ev_acc[i]) {
+            PATH_CUDA(cudaEventCreateWithFlags(&w.ev_acc[i], cudaEventDisableTiming));
+            PATH_CUDA(cudaEventCreateWithFlags(&w.ev_join[i], cudaEventDisableTiming));
+        }
     }
     PATH_CUDA(w.totals.ensure(8 * sizeof(unsigned long long)));
     PATH_CUDA(w.accum.ensure(npix * 3 * sizeof(float)));
@@ -626,8 +640,9 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
 
     // per-lane buffers
-    PassArgs lanes[2] = {pa0, pa0};
-    cudaStream_t lane_stream[2] = {s, n_lanes == 2 ? w.side : s};
+    PassArgs lanes[kMaxLanes] = {pa0, pa0, pa0, pa0};
+    cudaStream_t lane_stream[kMaxLanes] = {s, s, s, s};
+    for (int i = 1; i < n_lanes; ++i) lane_stream[i] = w.side[i];
     for (int li = 0; li < n_lanes; ++li) {
         PathLane& l = w.lane[li];
         PassArgs& pa = lanes[li];
@@ -671,16 +686,16 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             pa.ray2 = pa.ray1 + ray_cap;
         }
     }
-    if (n_lanes == 2) { // lane 1 starts after everything enqueued so far on the caller's stream
+    if (n_lanes > 1) { // the other lanes start after everything enqueued so far on the caller's stream
         PATH_CUDA(cudaEventRecord(w.ev_fork, s));
-        PATH_CUDA(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
+        for (int i = 1; i < n_lanes; ++i) PATH_CUDA(cudaStreamWaitEvent(w.side[i], w.ev_fork, 0));
     }
     const bool merge_kinds = std::getenv("G19_NO_MERGE") == nullptr; // tuning knob: one launch per material queue
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
     auto last_refresh = std::chrono::steady_clock::now();
     size_t pass_index = 0;
-    bool acc_recorded[2] = {false, false};
+    int prev_lane = -1; // lane of the previous pass
     int batch_spp = 0;
     for (int base = 0; base < p.spp; base += spp_pass) {
         if (a.cancel && a.cancel->load()) { // RayTracer::stop(): honoured between passes
@@ -689,7 +704,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         }
         batch_spp = std::min(spp_pass, p.spp - base);
         for (size_t pix0 = 0; pix0 < npix; pix0 += window, ++pass_index) { // the windows of this sample batch
-            const int li = n_lanes == 2 ? int(pass_index & 1) : 0;
+            const int li = int(pass_index % size_t(n_lanes));
             PassArgs& pa = lanes[li];
             cudaStream_t ls = lane_stream[li];
             clk.s = ls;
@@ -721,14 +736,14 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
                 stats.class_launches[G19_K_SHADE] += n;
             }
             // the per-pixel sums are taken in pass order whichever lane a pass ran on
-            if (n_lanes == 2 && acc_recorded[li ^ 1]) PATH_CUDA(cudaStreamWaitEvent(ls, w.ev_acc[li ^ 1], 0));
+            if (n_lanes > 1 && prev_lane >= 0) PATH_CUDA(cudaStreamWaitEvent(ls, w.ev_acc[prev_lane], 0));
             clk.begin();
             launch_accumulate(pa, ls);
             clk.end(G19_K_ACCUM);
             stats.class_launches[G19_K_ACCUM] += 1;
-            if (n_lanes == 2) {
+            if (n_lanes > 1) {
                 PATH_CUDA(cudaEventRecord(w.ev_acc[li], ls));
-                acc_recorded[li] = true;
+                prev_lane = li;
             }
         }
         stats.samples += uint64_t(batch_spp); // scaled by owned pixels below
@@ -750,9 +765,9 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             }
         }
     }
-    if (n_lanes == 2) { // join: the caller's stream continues after lane 1
-        PATH_CUDA(cudaEventRecord(w.ev_join, w.side));
-        PATH_CUDA(cudaStreamWaitEvent(s, w.ev_join, 0));
+    for (int i = 1; i < n_lanes; ++i) { // join: the caller's stream continues after the other lanes
+        PATH_CUDA(cudaEventRecord(w.ev_join[i], w.side[i]));
+        PATH_CUDA(cudaStreamWaitEvent(s, w.ev_join[i], 0));
     }
     clk.s = s;
     const int done_spp = int(stats.samples);

@@ -77,15 +77,16 @@ struct PathLane {
     DeviceArray counts;        // uint32[kMaxPathDepth+1][5]: queue lengths per bounce + ray fetch cursors
 };
 
-// Two passes are kept in flight, each on its own stream with its own PathLane: a pass is a chain of
+// Up to kMaxLanes passes are kept in flight, each on its own stream with its own PathLane: a pass is a chain of
 // 7-40 dependent kernels, every one of which ends in a tail where SMs idle (ncu: sm__cycles_active
 // 84-95 % of elapsed; the deep bounces of tree scenes run a handful of long rays at 15 % issue
 // utilisation) -- the other pass's kernels fill those holes. Only `accumulate` is ordered across
 // the lanes (events), so the per-pixel sums are still taken in sample order.
+constexpr int kMaxLanes = 4;
 struct PathWork {
-    PathLane lane[2];
-    cudaStream_t side = nullptr;          // lane 1's stream (lane 0 runs on the caller's)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_acc[2] = {nullptr, nullptr};
+    PathLane lane[kMaxLanes];
+    cudaStream_t side[kMaxLanes] = {}; // streams of lanes 1.. (lane 0 runs on the caller's; side[0] unused)
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {}, ev_acc[kMaxLanes] = {};
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
     DeviceArray accum;         // float[3][n_local_pix]
     DeviceArray rad_l, rgb_l;  // resolved local-pixel outputs

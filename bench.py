@@ -344,6 +344,8 @@ def main():
         "share_of_step": ms_cls[top] / max(1e-9, sum(cls_ms)),
         "binding_resource": "issue slots (ncu: smsp__issue_active %s%% of peak) -- see DESIGN.md section 5" % issue_pct,
         "issue": issue,
+        "note": "per-class times and shares are CUDA-event brackets taken with ONE pass in flight (params.profile); the timed "
+                "steps behind `value` keep up to four passes in flight on four streams, so ms_per_step < the sum of the classes",
         "per_class": {k: {"ms_per_step": ms_cls[k] / args.steps, "launches_per_step": n_launch[k] / args.steps,
                           "algorithmic_GB_per_step": bytes_cls[k] / args.steps / 1e9,
                           "GBps": (bytes_cls[k] / (ms_cls[k] * 1e-3) / 1e9) if ms_cls[k] > 0 else None}
