@@ -662,16 +662,15 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         pa.counts = static_cast<uint32_t*>(l.counts.p);
         pa.ray0 = pa.ray1 = pa.ray2 = nullptr;
         pa.hp = pa.dw = pa.tp = nullptr;
-        pa.rec_hp = pa.rec_dw = pa.rec_tp = nullptr;
-        pa.rec_L = nullptr;
+        pa.rec_ls = pa.rec_hp = pa.rec_dw = pa.rec_tp = nullptr;
         if (fused) {
-            // dense vertex records: three float4 planes and three float planes per queue
+            // dense vertex records: four float4 planes per queue
             const size_t cap = pa.queue_cap, nq = kNumQueues;
-            PATH_CUDA(l.recs.ensure(nq * cap * (3 * sizeof(float4) + 3 * sizeof(float))));
-            pa.rec_hp = static_cast<float4*>(l.recs.p);
+            PATH_CUDA(l.recs.ensure(nq * cap * 4 * sizeof(float4)));
+            pa.rec_ls = static_cast<float4*>(l.recs.p);
+            pa.rec_hp = pa.rec_ls + nq * cap;
             pa.rec_dw = pa.rec_hp + nq * cap;
             pa.rec_tp = pa.rec_dw + nq * cap;
-            pa.rec_L = reinterpret_cast<float*>(pa.rec_tp + nq * cap);
         } else {
             PATH_CUDA(l.hp.ensure(plane * sizeof(float4)));
             PATH_CUDA(l.dw.ensure(plane * sizeof(float4)));

@@ -72,7 +72,7 @@ struct PathLane {
     DeviceArray hp, dw, tp;    // tree scenes: float4[P] vertex state by slot (hit point+primitive, direction+pixel, throughput+sample)
     DeviceArray L;             // radiance of the slot's path: float4[P] (flat scenes) / float[3][P] (tree scenes)
     DeviceArray queues;        // uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
-    DeviceArray recs;          // flat scenes: float4[3][6][P + slack] + float[6][3][P + slack] dense vertex records
+    DeviceArray recs;          // flat scenes: float4[4][6][P + slack] dense vertex records
     DeviceArray rays;          // float4[3][2P + slack]: ray queue of one bounce (tree scenes only)
     DeviceArray counts;        // uint32[kMaxPathDepth+1][5]: queue lengths per bounce + ray fetch cursors
 };
@@ -154,13 +154,13 @@ struct PassArgs {
     uint32_t* q[6];        // [bounce parity * 3 + (kind - 1)]
     uint32_t kind_mask;    // bit (kind - 1): the scene has a material of that class
     size_t queue_cap;      // entries per queue (P + chunk slack)
-    // flat scenes: the queues hold the vertex records themselves (dense, 64 B per vertex); queue
-    // qi = bounce parity * 3 + (kind - 1) starts at qi * queue_cap in each plane. hp/dw/tp/q above
-    // then serve tree scenes only (slot-indexed), L is the accumulator input either way.
+    // flat scenes: the queues hold the vertex records themselves (dense, 64 B per vertex) in four float4
+    // planes; queue qi = bounce parity * 3 + (kind - 1) starts at qi * queue_cap in each plane. A padding
+    // entry has slot kInvalid. hp/dw/tp/q above then serve tree scenes only (slot-indexed).
+    float4* rec_ls;        // radiance so far, slot
     float4* rec_hp;        // hit point, primitive
     float4* rec_dw;        // incoming direction, pixel
     float4* rec_tp;        // throughput, sample
-    float* rec_L;          // radiance so far: 3 planes of queue_cap per queue
     float4* ray0;          // tree scenes: the bounce's ray queue (origin, tmax)
     float4* ray1;          //   (direction, slot | flags)
     float4* ray2;          //   (light sample rgb) of shadow rays

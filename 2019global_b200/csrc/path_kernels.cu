@@ -820,9 +820,6 @@ __device__ __forceinline__ void onb(float3 n, float3& t, float3& b) { // Duff et
     b = f3(bb, s + n.y * n.y * a, -n.y);
 }
 
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
@@ -942,21 +939,16 @@ __device__ __forceinline__ Shaded shade_vertex(const PassArgs& a, const SceneAcc
 // queue (slot, hit point + primitive, direction + pixel, throughput + sample, radiance so far --
 // 64 bytes, all planes coalesced) and read back from consecutive addresses; the path's radiance
 // travels with it and is stored to the slot's accumulator input exactly once, when the path ends.
-struct RecView {
-    uint32_t* slot;
-    float4 *hp, *dw, *tp;
-    float* L; // 3 planes of `cap`
-    size_t cap;
+struct RecView { // one queue: four float4 planes
+    float4 *ls, *hp, *dw, *tp; // (radiance so far | slot) (hit point | primitive) (direction | pixel) (throughput | sample)
 };
 __device__ __forceinline__ RecView rec_queue(const PassArgs& a, int qi) { // qi = bounce parity * 3 + (kind - 1)
     RecView r;
     const size_t off = size_t(qi) * a.queue_cap;
-    r.slot = a.q[qi];
+    r.ls = a.rec_ls + off;
     r.hp = a.rec_hp + off;
     r.dw = a.rec_dw + off;
     r.tp = a.rec_tp + off;
-    r.L = a.rec_L + 3 * off;
-    r.cap = a.queue_cap;
     return r;
 }
 
@@ -989,10 +981,21 @@ template <bool SPEC> struct RecSorter {
             }
         return pos;
     }
+    // pad what is left of the warp's chunks: an entry whose slot word is kInvalid is skipped by the consumer
     __device__ __forceinline__ void flush(const PassArgs& a) {
+        const uint32_t lane = threadIdx.x & 31u;
+        const float4 pad = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalid));
 #pragma unroll
         for (int k = 0; k < (SPEC ? 3 : 1); ++k)
-            if (mask & (1u << k)) warp_flush(cur[k], a.q[set + k]);
+            if (mask & (1u << k)) {
+                float4* ls = rec_queue(a, set + k).ls;
+                const WarpCursor& c = cur[k];
+                for (uint32_t i = c.pos + lane; i < c.end; i += 32u) ls[i] = pad;
+                if (c.has_next) { // a chunk reserved ahead of time and never used
+                    const uint32_t base = __shfl_sync(kFull, c.next, 0);
+                    for (uint32_t i = lane; i < kChunk; i += 32u) ls[base + i] = pad;
+                }
+            }
     }
 };
 
@@ -1037,7 +1040,7 @@ template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_exten
         if (pos != kInvalid) { // throughput is 1 and the radiance 0 on the camera segment: not stored
             const RecView r = rec_queue(a, kind);
             const float3 p = o + d * t;
-            r.slot[pos] = slot;
+            r.ls[pos] = make_float4(0.f, 0.f, 0.f, __uint_as_float(slot));
             r.hp[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(prim));
             r.dw[pos] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
         }
@@ -1051,25 +1054,19 @@ template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_exten
 // thread, each thread only ever touches its own column. The records are dense, so the address of
 // the next one is known without loading anything first.
 template <bool FULL> struct RecStage {
-    uint32_t slot[2][kThreads];
+    float4 ls[2][kThreads]; // radiance so far, slot
     float4 hp[2][kThreads];
     float4 dw[2][kThreads];
     float4 tp[FULL ? 2 : 1][FULL ? kThreads : 1];
-    float L[FULL ? 2 : 1][3][FULL ? kThreads : 1];
 };
 template <bool FULL>
 __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, bool valid, RecStage<FULL>& st, int buf) {
     const int t = threadIdx.x;
     if (valid) {
-        cp_async4(&st.slot[buf][t], r.slot + pos);
+        cp_async16(&st.ls[buf][t], r.ls + pos);
         cp_async16(&st.hp[buf][t], r.hp + pos);
         cp_async16(&st.dw[buf][t], r.dw + pos);
-        if (FULL) {
-            cp_async16(&st.tp[buf][t], r.tp + pos);
-            cp_async4(&st.L[buf][0][t], r.L + pos);
-            cp_async4(&st.L[buf][1][t], r.L + r.cap + pos);
-            cp_async4(&st.L[buf][2][t], r.L + 2 * r.cap + pos);
-        }
+        if (FULL) cp_async16(&st.tp[buf][t], r.tp + pos);
     }
     cp_async_commit();
 }
@@ -1101,7 +1098,8 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
         const uint32_t qn = q + stride;
         prefetch_rec(in, qn, qn < n && qn > q, stage, buf ^ 1); // next record, in flight during this body
         cp_async_wait<1>();                                     // this record has landed
-        const uint32_t slot = q < n ? stage.slot[buf][tid] : kInvalid;
+        const float4 ls = stage.ls[buf][tid];
+        const uint32_t slot = q < n ? __float_as_uint(ls.w) : kInvalid;
         int kind_next = -1;
         float3 p_next = f3(0.f, 0.f, 0.f), d_next = f3(0.f, 0.f, 1.f), T = f3(1.f, 1.f, 1.f), Lp = f3(0.f, 0.f, 0.f);
         uint32_t prim_next = kInvalid, pixel = 0, sample = 0;
@@ -1117,7 +1115,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
                 const float4 tp = stage.tp[buf][tid];
                 T = f3(tp.x, tp.y, tp.z);
                 sample = __float_as_uint(tp.w);
-                Lp = f3(stage.L[buf][0][tid], stage.L[buf][1][tid], stage.L[buf][2][tid]);
+                Lp = f3(ls.x, ls.y, ls.z);
             }
             const Shaded sh = shade_vertex<KIND, LAST, true>(a, S, bounce, p, d, T, prim, pixel, sample);
             T = sh.T;
@@ -1172,13 +1170,10 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
             const uint32_t pos = out.reserve(kind_next);
             if (pos != kInvalid) {
                 const RecView r = rec_queue(a, out.set + kind_next);
-                r.slot[pos] = slot;
+                r.ls[pos] = make_float4(Lp.x, Lp.y, Lp.z, __uint_as_float(slot));
                 r.hp[pos] = make_float4(p_next.x, p_next.y, p_next.z, __uint_as_float(prim_next));
                 r.dw[pos] = make_float4(d_next.x, d_next.y, d_next.z, __uint_as_float(pixel));
                 r.tp[pos] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
-                r.L[pos] = Lp.x;
-                r.L[r.cap + pos] = Lp.y;
-                r.L[2 * r.cap + pos] = Lp.z;
             }
         }
         buf ^= 1;

@@ -300,13 +300,13 @@ def main():
         agg["samples"] += s.samples
     barrier()
     # algorithmic HBM bytes per class, this rank. Flat scenes keep DENSE vertex
-    # records in the material queues: slot 4 B + (hit point, primitive) 16 B + (direction, pixel) 16 B
-    # [+ (throughput, sample) 16 B + radiance so far 12 B past the camera segment]
+    # records in the material queues, four float4 planes: (radiance so far | slot) (hit point | primitive)
+    # (direction | pixel) (throughput | sample); the camera segment neither writes nor reads the fourth
     E, S0, C, C0, LIT, ST = agg["extend"], agg["samples"], agg["shade"], agg["shade_first"], agg["lit"], agg["rad_stores"]
     npix_local = g19.engine.tile_pixels(W, H, rank, world)
     bytes_cls = {
-        "raygen_extend": 36 * C0,                       # record written per shaded camera hit
-        "bounce": (36 * C0 + 64 * (C - C0)              # record read per shaded vertex
+        "raygen_extend": 48 * C0,                       # record written per shaded camera hit
+        "bounce": (48 * C0 + 64 * (C - C0)              # record read per shaded vertex
                    + 64 * (C - C0)                      # record written per continuation hit (= vertices shaded later)
                    + 16 * ST),                          # radiance delivered once per path that gathered any (one float4)
         "accumulate": 32 * S0 + 24 * npix_local * max(1, agg["launch"][abi.K_ACCUM]),  # float4 read + zero-back per path
