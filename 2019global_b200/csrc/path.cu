@@ -651,7 +651,11 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             PATH_CUDA(l.queues.ensure((P + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
             l.capacity = P;
             PATH_CUDA(cudaMemsetAsync(l.L.p, 0, P * 4 * sizeof(float), s));
+            l.L_written_whole = false;
         }
+        // tree scenes ADD to zeroed planes (accumulate clears what it read); flat scenes store every slot
+        if (!fused && l.L_written_whole) PATH_CUDA(cudaMemsetAsync(l.L.p, 0, l.capacity * 4 * sizeof(float), s));
+        l.L_written_whole = fused;
         const size_t plane = l.capacity;
         PATH_CUDA(l.counts.ensure((kMaxPathDepth + 1) * 5 * sizeof(uint32_t)));
         PATH_CUDA(cudaMemsetAsync(l.counts.p, 0, (kMaxPathDepth + 1) * 5 * sizeof(uint32_t), s));

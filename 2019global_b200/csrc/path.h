@@ -69,6 +69,7 @@ struct PathSceneBuffers {
 // Wavefront state of ONE pass in flight (P path slots, slot = sample_in_pass * window + pixel_in_window).
 struct PathLane {
     size_t capacity = 0;       // slots
+    bool L_written_whole = false; // the last pass on this lane was a flat scene's: L holds its radiance, not zeros
     DeviceArray hp, dw, tp;    // tree scenes: float4[P] vertex state by slot (hit point+primitive, direction+pixel, throughput+sample)
     DeviceArray L;             // radiance of the slot's path: float4[P] (flat scenes) / float[3][P] (tree scenes)
     DeviceArray queues;        // uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces

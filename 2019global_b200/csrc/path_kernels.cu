@@ -1026,16 +1026,20 @@ template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_exten
                 camera_ray(a, x, y, pixel, sample, o, d);
             }
         }
+        float4 seen = make_float4(0.f, 0.f, 0.f, 0.f); // what a path that ends on the camera segment delivers
         if (nearest<true>(S, live, o, d, t, prim)) {
             const float4 tag = S.hot_row(prim, 3);
             const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
             if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
                 const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
-                reinterpret_cast<float4*>(a.L)[slot] = make_float4(m.emission[0], m.emission[1], m.emission[2], 0.0f);
+                seen = make_float4(m.emission[0], m.emission[1], m.emission[2], 0.0f);
             } else if (bsdf == G19_BSDF_DIFFUSE || a.max_depth > 1) {
                 kind = bsdf;
             }
         }
+        // Every slot of the pass gets its radiance stored exactly once, by whichever kernel ends its
+        // path (here: miss, emitter, or a slot outside the frame), so `accumulate` only reads.
+        if (q < n && kind < 0) reinterpret_cast<float4*>(a.L)[slot] = seen;
         const uint32_t pos = out.reserve(kind);
         if (pos != kInvalid) { // throughput is 1 and the radiance 0 on the camera segment: not stored
             const RecView r = rec_queue(a, kind);
@@ -1158,8 +1162,9 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
                     prim_next = prim_hit;
                 }
             }
-            if (kind_next < 0 && (Lp.x != 0.0f || Lp.y != 0.0f || Lp.z != 0.0f)) {
-                // the path ends here: its radiance goes to the slot's accumulator input, once
+            if (kind_next < 0) {
+                // the path ends here: its radiance goes to the slot's accumulator input, once (zero or not:
+                // accumulate does not clear what it read)
                 ++stored;
                 // (slots are scattered by now: ONE 16-byte store, not three 4-byte stores into three planes --
                 // the last bounce of the depth-12 glass box spent 148 us on 37 M instructions doing those)
@@ -1459,7 +1464,8 @@ __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, co
 }
 
 // ---- accumulate / resolve ---------------------------------------------------------------
-// FLAT: the finished paths' radiance is a float4 per slot (flat scenes); otherwise three planes.
+// FLAT: the finished paths' radiance is a float4 per slot, stored once for EVERY slot of the pass by the kernel
+// that ended its path, so it is only read here; otherwise three planes that paths add to and this kernel clears.
 template <bool FLAT> __global__ void __launch_bounds__(kThreads) accumulate_kernel(const PassArgs a) {
     pdl_launch_dependents();
     pdl_wait();
@@ -1477,15 +1483,11 @@ template <bool FLAT> __global__ void __launch_bounds__(kThreads) accumulate_kern
 #pragma unroll
                 for (int k = 0; k < 4; ++k) v[k] = L[(size_t)(s + k) * nwin];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    acc0 += v[k].x; acc1 += v[k].y; acc2 += v[k].z;
-                    if (v[k].x != 0.0f || v[k].y != 0.0f || v[k].z != 0.0f) L[(size_t)(s + k) * nwin] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int k = 0; k < 4; ++k) { acc0 += v[k].x; acc1 += v[k].y; acc2 += v[k].z; }
             }
             for (; s < a.spp_pass; ++s) {
                 const float4 v = L[(size_t)s * nwin];
                 acc0 += v.x; acc1 += v.y; acc2 += v.z;
-                if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) L[(size_t)s * nwin] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
             float* L0 = a.L + wp;

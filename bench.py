@@ -308,8 +308,8 @@ def main():
         "raygen_extend": 48 * C0,                       # record written per shaded camera hit
         "bounce": (48 * C0 + 64 * (C - C0)              # record read per shaded vertex
                    + 64 * (C - C0)                      # record written per continuation hit (= vertices shaded later)
-                   + 16 * ST),                          # radiance delivered once per path that gathered any (one float4)
-        "accumulate": 32 * S0 + 24 * npix_local * max(1, agg["launch"][abi.K_ACCUM]),  # float4 read + zero-back per path
+                   + 16 * ST),                          # radiance delivered once per path that ends in this kernel (one float4)
+        "accumulate": 16 * S0 + 24 * npix_local * max(1, agg["launch"][abi.K_ACCUM]),  # float4 read per path + accum read-modify-write
     }
     ms_cls = {"raygen_extend": cls_ms[abi.K_EXTEND], "bounce": cls_ms[abi.K_SHADE], "accumulate": cls_ms[abi.K_ACCUM]}
     top = max(ms_cls, key=lambda k: ms_cls[k])

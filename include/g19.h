@@ -175,8 +175,8 @@ typedef struct g19_stats {
     uint64_t lit_samples;     /* PATH: unoccluded next-event samples          */
     uint64_t radiance_reads;  /* PATH, tree scenes: diffuse vertices past the camera segment
                                  (their light sample reads the slot's radiance so far)        */
-    uint64_t radiance_stores; /* PATH, flat scenes: paths that ended with radiance to deliver
-                                 (one 12-byte store each; bench.py's byte model)              */
+    uint64_t radiance_stores; /* PATH, flat scenes: paths that ended in a bounce kernel (one
+                                 16-byte radiance store each; bench.py's byte model)          */
 } g19_stats;
 
 enum { G19_K_EXTEND = 0, G19_K_SHADE = 1, G19_K_SHADOW = 2, G19_K_ACCUM = 3,

@@ -268,3 +268,25 @@ def test_passes_in_flight_and_merged_launch_bit_identical(g19, abi, which, depth
         assert render().tobytes() == base.tobytes(), "lanes=" + lanes
     monkeypatch.setenv("G19_NO_MERGE", "1")
     assert render().tobytes() == base.tobytes(), "one launch per material queue"
+
+
+def test_flat_then_tree_scene_on_one_context(g19, abi):
+    """Flat scenes store every slot's radiance (accumulate only reads it); tree scenes add to zeroed planes
+    that accumulate clears. One context switching between the two must not carry anything over."""
+    w, h = 128, 96
+    kw = dict(mode=abi.MODE_PATH, want=("radiance",), spp=6, max_depth=4, seed=3, spp_per_pass=2)
+    scenes = [g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h), g19.Octree.builtin(abi.SCENE_HEIGHTFIELD, n=48, w=w, h=h)]
+    want = []
+    for sc, cam, light in scenes:  # each scene on a context of its own
+        rt = g19.RayTracer(cam, light)
+        rt.setScene(sc)
+        rt.start()
+        want.append(rt.run(w, h, **kw)["radiance"])
+        assert want[-1].mean() > 0.01
+    rt = g19.RayTracer(scenes[0][1], scenes[0][2])
+    rt.start()
+    for k in (0, 1, 0, 1, 1):
+        sc, cam, light = scenes[k]
+        rt.camera, rt.light = cam, tuple(light)
+        rt.setScene(sc)
+        assert rt.run(w, h, **kw)["radiance"].tobytes() == want[k].tobytes(), k
