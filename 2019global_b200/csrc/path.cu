@@ -548,14 +548,17 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     if (npix == 0) return G19_OK;
     // Pass size. Flat scenes keep dense vertex records in their queues, so a bounce streams exactly
     // the live vertices whatever the pass size: bigger passes only amortise launch tails (measured on
-    // B200, ms per 1080p x 64 spp frame at 2 / 4 / 8 / 16 M slots: Cornell depth 5 22.3 / 20.9 / 20.2 /
-    // 20.2, glass Cornell depth 12 64.4 / 52.0 / 47.7 / 49.3). Tree scenes still index their state by
-    // slot: deep bounces touch it sparsely and live off the L2 (126 MB), so their passes stay small.
+    // B200, ms per 1080p x 64 spp frame at 2 / 4 / 8 / 16 M slots, one pass in flight: Cornell depth 5
+    // 22.3 / 20.9 / 20.2 / 20.2, glass Cornell depth 12 64.4 / 52.0 / 47.7 / 49.3). Tree scenes index their
+    // state by slot; with four passes in flight the 1 M-triangle heightfield at depth 5 still prefers big
+    // passes (1 / 2 / 4 / 8 / 16 M slots: 166.9 / 142.8 / 128.0 / 121.0 / 117.4 ms per 1080p x 32 spp): its
+    // deep-bounce trace launches are a handful of long rays, and fewer, longer launches waste less.
+    // Deep tree renders keep smaller passes (their sparse slot accesses live off the 126 MB L2).
     // A pass covers a WINDOW of the rank's pixels (whole 32x32 tiles) times spp_pass samples; frames
     // larger than the target are rendered window by window.
     const bool flat_scene = b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= 192 &&
                             b.view.n_lights <= 32;
-    size_t target = flat_scene ? (size_t(1) << 23) : (p.max_depth > 6 ? (size_t(1) << 21) : (size_t(1) << 22));
+    size_t target = flat_scene ? (size_t(1) << 23) : (p.max_depth > 6 ? (size_t(1) << 22) : (size_t(1) << 24));
     if (const char* v = std::getenv("G19_PASS_SLOTS")) target = std::max<size_t>(kTilePix, size_t(std::atoll(v))); // tuning knob
     size_t window = npix;
     if (p.pixels_per_pass > 0) window = std::min(npix, (size_t(p.pixels_per_pass) + kTilePix - 1) / kTilePix * kTilePix);
@@ -565,7 +568,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     spp_pass = std::min(spp_pass, p.spp);
     // enough passes to keep kMaxLanes of them in flight (PathWork), as long as a pass still fills the machine
     if (p.spp_per_pass <= 0)
-        while (spp_pass > 1 && ((npix + window - 1) / window) * size_t((p.spp + spp_pass - 1) / spp_pass) < size_t(kMaxLanes) &&
+        while (spp_pass > 1 && ((npix + window - 1) / window) * size_t((p.spp + spp_pass - 1) / spp_pass) < size_t(4) &&
                window * size_t((spp_pass + 1) / 2) >= (size_t(1) << 21))
             spp_pass = (spp_pass + 1) / 2;
     const size_t P = window * size_t(spp_pass);
@@ -584,7 +587,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     // passes of this frame, and how many are kept in flight (see PathWork)
     const size_t n_windows = (npix + window - 1) / window;
     const size_t n_passes = n_windows * size_t((p.spp + spp_pass - 1) / spp_pass);
-    int n_lanes = (p.profile || a.on_pass) ? 1 : int(std::min<size_t>(kMaxLanes, n_passes)); // profiling and progressive refresh: one at a time
+    const int want_lanes = 4;
+    int n_lanes = (p.profile || a.on_pass) ? 1 : int(std::min<size_t>(want_lanes, n_passes)); // profiling and progressive refresh: one at a time
     if (const char* v = std::getenv("G19_LANES")) // tuning knob
         n_lanes = std::max(1, std::min(std::min<int>(kMaxLanes, int(n_passes)), (p.profile || a.on_pass) ? 1 : std::atoi(v)));
     if (n_lanes > 1 && !w.ev_fork) PATH_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
@@ -640,8 +644,12 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
 
     // per-lane buffers
-    PassArgs lanes[kMaxLanes] = {pa0, pa0, pa0, pa0};
-    cudaStream_t lane_stream[kMaxLanes] = {s, s, s, s};
+    PassArgs lanes[kMaxLanes];
+    cudaStream_t lane_stream[kMaxLanes];
+    for (int i = 0; i < kMaxLanes; ++i) {
+        lanes[i] = pa0;
+        lane_stream[i] = s;
+    }
     for (int i = 1; i < n_lanes; ++i) lane_stream[i] = w.side[i];
     for (int li = 0; li < n_lanes; ++li) {
         PathLane& l = w.lane[li];

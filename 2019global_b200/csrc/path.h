@@ -83,7 +83,7 @@ struct PathLane {
 // 84-95 % of elapsed; the deep bounces of tree scenes run a handful of long rays at 15 % issue
 // utilisation) -- the other pass's kernels fill those holes. Only `accumulate` is ordered across
 // the lanes (events), so the per-pixel sums are still taken in sample order.
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = 8;
 struct PathWork {
     PathLane lane[kMaxLanes];
     cudaStream_t side[kMaxLanes] = {}; // streams of lanes 1.. (lane 0 runs on the caller's; side[0] unused)
