@@ -269,7 +269,9 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
 
     const auto t_prims = std::chrono::steady_clock::now();
     // ---- linear octree, breadth first ------------------------------------------
-    int kLeafMax = 16; // measured on the 1M-triangle heightfield: 4 / 8 / 16 / 32 -> 49.7 / 43.7 / 41.5 / 42.2 ms per 8.3 M paths
+    // measured on the 1M-triangle heightfield, ms per 1080p x 32 spp frame at 4 / 6 / 8 / 12 / 16 / 32: 107.3 / 107.7 / 107.6 /
+    // 110.6 / 114.6 / 141.3 (an earlier walk, before the fixed-trip rounds, preferred 16)
+    int kLeafMax = 8;
     if (const char* v = std::getenv("G19_LEAF_MAX")) kLeafMax = std::max(1, std::atoi(v)); // tuning knob
     float root_lo[3] = {float(scene.rmin.x), float(scene.rmin.y), float(scene.rmin.z)};
     float root_hi[3] = {float(scene.rmax.x), float(scene.rmax.y), float(scene.rmax.z)};
