@@ -643,6 +643,10 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     // tree scenes: the bounce kernels queue their rays (2 per vertex at most) for trace_kernel
     pa0.refill = 8;
     if (const char* v = std::getenv("G19_REFILL")) pa0.refill = std::max(1, std::min(32, std::atoi(v))); // tuning knob
+    pa0.walk_steps = 4;
+    pa0.leaf_batch = 4;
+    if (const char* v = std::getenv("G19_WALK_STEPS")) pa0.walk_steps = std::max(1, std::min(16, std::atoi(v))); // tuning knob
+    if (const char* v = std::getenv("G19_LEAF_BATCH")) pa0.leaf_batch = std::max(1, std::min(16, std::atoi(v))); // tuning knob
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
 
     // per-lane buffers

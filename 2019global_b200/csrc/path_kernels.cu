@@ -109,6 +109,8 @@ template <bool ALL> struct SceneAccess {
     const ulonglong2* pairs_s; // flat scenes: primitive PAIRS, one float2 per coefficient (trace_flat)
     uint32_t* stack;
     int n_nodes_s;
+    int walk_steps;      // tree walk: cell moves per round
+    uint32_t leaf_batch; // tree walk: primitives tested per round
     __device__ __forceinline__ uint2 node(uint32_t i) const {
         if (ALL || i < (uint32_t)n_nodes_s) return nodes_s[i];
         return __ldg(reinterpret_cast<const uint2*>(g->nodes) + i);
@@ -150,6 +152,8 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     SceneAccess<ALL> acc;
     acc.g = &a.scene;
     acc.n_nodes_s = a.stage_nodes;
+    acc.walk_steps = a.walk_steps;
+    acc.leaf_batch = uint32_t(a.leaf_batch);
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
     const uint32_t pb = uint32_t(a.stage_prims) * 64u;
@@ -512,12 +516,12 @@ struct TreeWalk {
     // move -- with `continue`/`break` in a data-dependent loop the lanes drifted apart and ran the
     // loop body in ~2.5 separate groups of 5.6 lanes (ncu, profiles/r01_tuning_log.md).
     // Returns true when the lane's ray is finished.
-    static constexpr int kWalkSteps = 4;
-    static constexpr uint32_t kLeafBatch = 4;
     template <bool ALL> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
         uint32_t* const stack = S.stack;
         bool done = false;
 #pragma unroll 1
+        const int kWalkSteps = S.walk_steps;      // PassArgs::walk_steps (default 4)
+        const uint32_t kLeafBatch = S.leaf_batch; // PassArgs::leaf_batch (default 4)
         for (int it = 0; it < kWalkSteps; ++it) {
             __syncwarp();
             if (active && !done && leaf_n == 0u) {
