@@ -519,9 +519,9 @@ struct TreeWalk {
     template <bool ALL> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
         uint32_t* const stack = S.stack;
         bool done = false;
-#pragma unroll 1
         const int kWalkSteps = S.walk_steps;      // PassArgs::walk_steps (default 4)
         const uint32_t kLeafBatch = S.leaf_batch; // PassArgs::leaf_batch (default 4)
+#pragma unroll 1
         for (int it = 0; it < kWalkSteps; ++it) {
             __syncwarp();
             if (active && !done && leaf_n == 0u) {
@@ -675,8 +675,9 @@ __device__ __forceinline__ void warp_append(WarpCursor& c, bool want, uint32_t v
 // atomic is in flight during the ~800 instructions of the next vertex and its result is only read
 // at the next overflow. A warp that appends sparsely never gets close to the end of its chunk and
 // prefetches nothing; a dense producer leaves at most one unused chunk behind (warp_flush pads it).
-template <bool AHEAD = true>
+template <bool AHEAD = true, uint32_t CHUNK = kChunk>
 __device__ __forceinline__ uint32_t warp_reserve(WarpCursor& c, bool want, uint32_t* __restrict__ counter) {
+    static_assert(CHUNK >= 32u, "one append of a full warp must fit a fresh chunk");
     const uint32_t m = __ballot_sync(kFull, want);
     if (m == 0) return kInvalid;
     const uint32_t lane = threadIdx.x & 31u;
@@ -684,16 +685,16 @@ __device__ __forceinline__ uint32_t warp_reserve(WarpCursor& c, bool want, uint3
     const uint32_t room = c.end - c.pos, base0 = c.pos;
     uint32_t base1 = 0;
     if (n > room) {
-        if (!c.has_next && lane == 0) c.next = atomicAdd(counter, kChunk); // first chunk, or a sparse producer
+        if (!c.has_next && lane == 0) c.next = atomicAdd(counter, CHUNK); // first chunk, or a sparse producer
         base1 = __shfl_sync(kFull, c.next, 0);
         c.has_next = false;
         c.pos = base1 + (n - room);
-        c.end = base1 + kChunk;
+        c.end = base1 + CHUNK;
     } else {
         c.pos += n;
     }
     if (AHEAD && !c.has_next && c.end - c.pos < 32u) { // the next append may overflow: fetch its chunk now
-        if (lane == 0) c.next = atomicAdd(counter, kChunk);
+        if (lane == 0) c.next = atomicAdd(counter, CHUNK);
         c.has_next = true;
     }
     return want ? (rank < room ? base0 + rank : base1 + (rank - room)) : kInvalid;
@@ -979,9 +980,10 @@ template <bool SPEC> struct RecSorter {
 #pragma unroll
         for (int k = 0; k < (SPEC ? 3 : 1); ++k)
             if (mask & (1u << k)) {
-                // the specular queues fill slowly: an unused chunk would halve their consumers' lane efficiency
+                // the specular queues fill slowly (a few entries per warp and launch): no chunk ahead of
+                // time and 32-entry chunks, or their consumers would run on mostly padding
                 const uint32_t p = k == 0 ? warp_reserve<true>(cur[k], kind == k, counters + k)
-                                          : warp_reserve<false>(cur[k], kind == k, counters + k);
+                                          : warp_reserve<false, 32u>(cur[k], kind == k, counters + k);
                 if (kind == k) pos = p;
             }
         return pos;
@@ -1019,12 +1021,11 @@ template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_exten
         const uint32_t slot = q;
         int kind = -1;
         bool live = false;
-        uint32_t pixel = 0, prim = kInvalid;
+        uint32_t pixel = 0, prim = kInvalid, sample = 0;
         float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
         float t = 0.0f;
         if (q < n) {
             int x, y;
-            uint32_t sample;
             live = slot_pixel(a, slot, x, y, sample);
             if (live) {
                 pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
@@ -1049,7 +1050,7 @@ template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_exten
         if (pos != kInvalid) { // throughput is 1 and the radiance 0 on the camera segment: not stored
             const RecView r = rec_queue(a, kind);
             const float3 p = o + d * t;
-            r.ls[pos] = make_float4(0.f, 0.f, 0.f, __uint_as_float(slot));
+            r.ls[pos] = make_float4(__uint_as_float(sample), 0.f, 0.f, __uint_as_float(slot)); // radiance is 0 here: x carries the sample index
             r.hp[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(prim));
             r.dw[pos] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
         }
@@ -1118,8 +1119,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
             const uint32_t prim = __float_as_uint(hp.w);
             pixel = __float_as_uint(dw.w);
             if (FIRST) {
-                uint32_t lp;
-                sample = uint32_t(a.sample_base) + fast_div(slot, a.pix_count, lp);
+                sample = __float_as_uint(ls.x); // the camera record: no radiance yet, x carries the sample index
             } else {
                 const float4 tp = stage.tp[buf][tid];
                 T = f3(tp.x, tp.y, tp.z);
