@@ -1,51 +1,55 @@
 // path_kernels.cu -- the wavefront path tracer on sm_100a (G19_MODE_PATH).
 //
-// One pass traces P = spp_pass * n_local_pix camera paths, bounce by bounce:
+// One pass traces P = spp_pass * window camera paths, bounce by bounce; up to four passes are in
+// flight on their own streams (path.cu). Two families of kernels share the shading code:
 //
-//   raygen_extend   camera ray from the pixel index + linear-octree traversal + primitive
-//                   intersection; writes the 32-byte vertex record (hit point, primitive,
-//                   incoming direction, pixel); sorts the slot into a per-material queue by
-//                   warp-ballot compaction; directly visible emitters end the path in place
-//   bounce<KIND>    one launch per material queue and bounce (diffuse / mirror / glass):
-//                   next-event estimation, BSDF sampling, AND the trace of the continuation
-//                   ray by the thread that sampled it, then the same sort of the new vertex
-//                   into the next bounce's material queues. There is no ray record and no
-//                   separate extend launch after the camera segment: a queue entry always
-//                   produces exactly one continuation ray, so compacting between "shade" and
-//                   "extend" would only re-read what the thread already holds in registers.
-//   accumulate      per pixel, in sample order, radiance -> accumulation buffer
-//   resolve         mean, clamp, truncating RGB888 store (Image::setPixel,
-//                   reference include/image.h:14-16)
+// FLAT scenes (the whole scene is one leaf of <= 192 primitives, staged in shared memory):
+//   raygen_extend_flat   camera ray from the pixel index, nearest hit, vertex record written at the
+//                        position the warp's ballot compaction reserved in the material's queue
+//   bounce_flat<KIND>    one material queue of one bounce (diffuse / mirror / glass; scenes with
+//                        specular materials run the three queues of a bounce in ONE launch,
+//                        bounce_flat_all): next-event estimation, BSDF sample, the shadow ray and
+//                        the continuation ray traced in one loop over primitive PAIRS (packed
+//                        FP32), the new vertex record written into the next bounce's queue. The
+//                        queues hold the records themselves (four float4 planes), the path's
+//                        radiance rides in the record and is stored once when the path ends.
+// TREE scenes (linear octree in HBM / L2):
+//   raygen_extend        camera ray + ordered octree walk (all 32 lanes of a warp in fixed-trip rounds)
+//   bounce<KIND>         shades a queue of slot indices and queues the vertex's rays
+//   trace                persistent walk over the bounce's ray queue with dynamic ray fetch
+// Both:
+//   accumulate           per pixel, in sample order, radiance -> accumulation buffer
+//   resolve              mean, clamp, truncating RGB888 store (Image::setPixel, reference include/image.h:14-16)
 //
-// State lives in vectorised SoA buffers indexed by path slot (PassArgs); queues hold slot
-// indices. Every launch is a persistent grid (SM count x resident CTAs) that reads its queue
-// length from device memory, so a frame is enqueued without a single host round trip. The RNG
+// There is no separate extend launch after the camera segment: a queue entry always produces
+// exactly one continuation ray, so compacting between "shade" and "extend" would only re-read what
+// the thread already holds in registers. Every launch is a persistent grid (SM count x resident
+// CTAs) that reads its queue length from device memory and is chained to its predecessor by
+// programmatic dependent launch, so a frame is enqueued without a single host round trip. The RNG
 // is Philox4x32-10 keyed on (global pixel, sample, bounce, stream): results do not depend on
-// queue order, pass size or how tiles are split across GPUs.
+// queue order, pass size, passes in flight or how tiles are split across GPUs.
 //
-// What the ncu captures drove (profiles/):
-//   round 1  * the kernels are issue-bound, not HBM-bound -> triangle test by a precomputed
-//              affine map (6 dot products, one MUFU division, no branches), coplanar triangle
-//              pairs merged into parallelograms by the builder, leaf primitives stored
-//              contiguously (no index hop)
-//            * barrier stalls from block-level compaction -> queue space is reserved in
-//              warp-private 64-entry chunks: one atomic per 64 outputs, no __syncthreads
-//            * long-scoreboard stalls on queue -> state dependent loads -> cp.async prefetch of
-//              the next slot's state into shared memory
-//   session 2 (profiles/r01b_*): ALU pipe 47 %, FMA pipe 28 %, issue 67 % -- a dependent-
-//              latency bound at 6 warps per scheduler, i.e. time ~ instructions per vertex:
-//            * shade + extend fused (see above): one queue pop, one state load, one
-//              compaction per vertex instead of two of each
-//            * (pixel, sample) ride in the spare words of the vertex record instead of being
-//              recomputed by two integer divisions per vertex
-//            * flat scenes (one staged leaf): the shadow ray and the continuation ray leave
-//              the same point, so ONE loop over the primitives tests both -- the origin half
-//              of the affine map (9 of 18 FMAs) and the primitive loads are shared, and the
-//              two rays are independent instruction chains
+// What the ncu captures drove (profiles/r01_tuning_log.md has the numbers):
+//   session 1  * the kernels are issue-bound, not HBM-bound -> triangle test by a precomputed affine
+//                map (6 dot products, one MUFU reciprocal, no branches), coplanar triangle pairs
+//                merged into parallelograms by the builder
+//              * barrier stalls from block-level compaction -> queue space is reserved in
+//                warp-private 64-entry chunks: one atomic per 64 outputs, no __syncthreads
+//              * long-scoreboard stalls on queue -> state dependent loads -> cp.async prefetch of
+//                the next record into shared memory
+//   session 2  * shade + extend fused; (pixel, sample) ride in the spare words of the vertex record
+//              * flat scenes: the shadow ray and the continuation ray leave the same point, so ONE
+//                loop over the primitives tests both (shared origin half, shared loads)
+//              * tree scenes: while-while walk in converged rounds, dynamic ray fetch
+//   session 3  * slot-indexed state cost the same time per launch whatever the number of live
+//                paths (sector waste) -> dense vertex records in the queues
+//              * 40 % of the instructions FP32 at 70 % issue utilisation -> primitive pairs through
+//                FFMA2 / FMUL2 / FADD2
+//              * every kernel ends in a tail -> several passes in flight
 //
-// Scene access: the breadth-first prefix of the node array and of the leaf-ordered primitive
-// records is staged into shared memory at kernel start with cp.async.bulk (TMA bulk copy, one
-// mbarrier); anything beyond the staged prefix is read through L2 with read-only loads.
+// Scene access: flat scenes stage everything (records, pairs, shading records, lights) into shared
+// memory at kernel start with cp.async.bulk (TMA bulk copy, one mbarrier); tree scenes stage the
+// breadth-first prefix of the node array and read the rest through L2 with read-only loads.
 #include "path.h"
 
 #include <cfloat>
