@@ -172,6 +172,7 @@ struct PassArgs {
     int32_t stage_nodes, stage_prims, stage_cold, stage_lights, stack_levels;
     int32_t refill;        // trace_kernel: idle lanes per warp that trigger a fetch of new rays
     int32_t walk_steps, leaf_batch; // tree walk: cell moves / primitives tested per round (TreeWalk::step)
+    int32_t coop_leaf;     // tree walk: leaf tests spread over the whole warp (default; G19_COOP_LEAF=0: sequential)
 };
 
 void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s);

@@ -115,6 +115,7 @@ template <bool ALL> struct SceneAccess {
     int n_nodes_s;
     int walk_steps;      // tree walk: cell moves per round
     uint32_t leaf_batch; // tree walk: primitives tested per round
+    unsigned long long* coop; // tree walk, cooperative leaf tests: this warp's 32 result slots, or nullptr
     __device__ __forceinline__ uint2 node(uint32_t i) const {
         if (ALL || i < (uint32_t)n_nodes_s) return nodes_s[i];
         return __ldg(reinterpret_cast<const uint2*>(g->nodes) + i);
@@ -158,6 +159,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     acc.n_nodes_s = a.stage_nodes;
     acc.walk_steps = a.walk_steps;
     acc.leaf_batch = uint32_t(a.leaf_batch);
+    acc.coop = nullptr;
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
     const uint32_t pb = uint32_t(a.stage_prims) * 64u;
@@ -174,6 +176,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     unsigned long long* barp =
         reinterpret_cast<unsigned long long*>(base + nb + pb + cb + lb + qb + uint32_t(a.stack_levels) * kThreads * 4u);
     const uint32_t bar = smem_addr(barp);
+    if (!ALL && a.coop_leaf) acc.coop = barp + 2 + (threadIdx.x >> 5) * 32; // [barrier 8 B, pad 8 B][8 warps x 32 slots x 8 B]
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -520,7 +523,7 @@ struct TreeWalk {
     // move -- with `continue`/`break` in a data-dependent loop the lanes drifted apart and ran the
     // loop body in ~2.5 separate groups of 5.6 lanes (ncu, profiles/r01_tuning_log.md).
     // Returns true when the lane's ray is finished.
-    template <bool ALL> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
+    template <bool ALL, bool COOP> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
         uint32_t* const stack = S.stack;
         bool done = false;
         const int kWalkSteps = S.walk_steps;      // PassArgs::walk_steps (default 4)
@@ -579,7 +582,65 @@ struct TreeWalk {
         }
         __syncwarp();
         // ---- test: the next batch of the current leaf's primitives ----
-        if (active && !done && leaf_n != 0u) {
+        if constexpr (COOP) {
+            // COOPERATIVE form (default; G19_COOP_LEAF=0 selects the sequential one): ncu showed the leaf batches running at ~8 of 32 lanes (only
+            // the lanes that stand in a leaf) for 28 % of trace_kernel's instructions. Here the warp's pending
+            // (ray, primitive) pairs are spread over all 32 lanes: a lane looks up which ray task j belongs to
+            // (binary search over the inclusive prefix sum of the batch sizes), fetches that ray by shuffle,
+            // tests ONE primitive, and the nearest hit per ray is reduced with a 64-bit atomicMin on
+            // (t bits << 32 | primitive) in the warp's shared-memory slots. Same hits as the sequential form;
+            // a tie in t goes to the lower primitive id.
+            const uint32_t lane = threadIdx.x & 31u;
+            const bool mine = active && !done && leaf_n != 0u;
+            const uint32_t cnt = mine ? (leaf_n < kLeafBatch ? leaf_n : kLeafBatch) : 0u;
+            if (__ballot_sync(kFull, cnt != 0u) != 0u) {
+                uint32_t inc = cnt; // inclusive prefix sum over the lanes
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t v = __shfl_up_sync(kFull, inc, off);
+                    if (lane >= uint32_t(off)) inc += v;
+                }
+                const uint32_t total = __shfl_sync(kFull, inc, 31);
+                const uint32_t exc = inc - cnt;
+                S.coop[lane] = ~0ull;
+                __syncwarp();
+                const uint32_t* __restrict__ index = S.g->index;
+                const float4* __restrict__ hot = reinterpret_cast<const float4*>(S.g->hot);
+                for (uint32_t base = 0; base < total; base += 32u) {
+                    const uint32_t j = base + lane;
+                    uint32_t own = 0; // number of lanes whose tasks all lie before j = the owner of task j
+#pragma unroll
+                    for (int stepw = 16; stepw > 0; stepw >>= 1) {
+                        const uint32_t probe = __shfl_sync(kFull, inc, int(own) + stepw - 1);
+                        if (probe <= j) own += uint32_t(stepw);
+                    }
+                    const bool valid = j < total;
+                    if (!valid) own = 0;
+                    const uint32_t k = j - __shfl_sync(kFull, exc, int(own));
+                    const uint32_t lf = __shfl_sync(kFull, leaf_first, int(own));
+                    const float rox = __shfl_sync(kFull, o.x, int(own)), roy = __shfl_sync(kFull, o.y, int(own)), roz = __shfl_sync(kFull, o.z, int(own));
+                    const float rdx = __shfl_sync(kFull, d.x, int(own)), rdy = __shfl_sync(kFull, d.y, int(own)), rdz = __shfl_sync(kFull, d.z, int(own));
+                    const float rbest = __shfl_sync(kFull, best, int(own));
+                    if (valid) {
+                        const uint32_t id = __ldg(index + lf + k);
+                        const float4* pp = hot + 4 * (size_t)id;
+                        const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
+                        const float t = hit_prim(a0, b0, c0, g0, f3(rox, roy, roz), f3(rdx, rdy, rdz), rbest);
+                        if (t >= 0.0f) atomicMin(S.coop + own, ((unsigned long long)__float_as_uint(t) << 32) | id);
+                    }
+                }
+                __syncwarp();
+                if (cnt != 0u) {
+                    const unsigned long long r = S.coop[lane];
+                    if (r != ~0ull) { best = __uint_as_float(uint32_t(r >> 32)); best_prim = uint32_t(r); }
+                    leaf_first += cnt;
+                    leaf_n -= cnt;
+                    if (any && best_prim != kInvalid) done = true;
+                    else if (leaf_n == 0u && best_prim != kInvalid && best <= leaf_exit) done = true;
+                }
+                __syncwarp();
+            }
+        } else if (active && !done && leaf_n != 0u) { // sequential form: every lane tests its own leaf's primitives
             leaf(*S.g, leaf_first, leaf_n, kLeafBatch);
             const uint32_t tested = leaf_n < kLeafBatch ? leaf_n : kLeafBatch;
             leaf_first += tested;
@@ -594,14 +655,14 @@ struct TreeWalk {
 
 // Runs the walks of a whole warp to completion; MUST be called by all 32 lanes (`active` = this
 // lane has a ray). Used for camera rays; secondary rays go through trace_kernel.
-template <bool ALL>
+template <bool ALL, bool COOP>
 __device__ bool traverse(const SceneAccess<ALL>& S, bool active, float3 o, float3 d, float tmax, bool any, float& t_hit,
                          uint32_t& prim_hit) {
     TreeWalk w = {};
     w.best_prim = kInvalid;
     bool busy = active && !w.init(S, o, d, tmax, any);
     while (__any_sync(kFull, busy))
-        if (w.step(S, busy)) busy = false;
+        if (w.template step<ALL, COOP>(S, busy)) busy = false;
     t_hit = w.best;
     prim_hit = w.best_prim;
     return active && w.best_prim != kInvalid;
@@ -759,14 +820,14 @@ struct Sorter {
 };
 
 // Nearest hit of one ray, flat or tree. Called by all 32 lanes; `active` = the lane has a ray.
-template <bool ALL>
+template <bool ALL, bool COOP = false>
 __device__ __forceinline__ bool nearest(const SceneAccess<ALL>& S, bool active, float3 o, float3 d, float& t, uint32_t& prim) {
     if constexpr (ALL) {
         bool occ;
         trace_flat<false>(S, o, d, active ? FLT_MAX : -1.0f, d, -1.0f, t, prim, occ);
         return prim != kInvalid;
     } else {
-        return traverse<ALL>(S, active, o, d, FLT_MAX, false, t, prim);
+        return traverse<ALL, COOP>(S, active, o, d, FLT_MAX, false, t, prim);
     }
 }
 
@@ -778,7 +839,7 @@ __device__ __forceinline__ void store_vertex(const PassArgs& a, uint32_t slot, f
 }
 
 // ---- raygen + extend (camera segment), tree scenes: slot-indexed state ----------------------
-template <int OCC> __global__ void __launch_bounds__(kThreads, OCC) raygen_extend_kernel(const PassArgs a) {
+template <int OCC, bool COOP> __global__ void __launch_bounds__(kThreads, OCC) raygen_extend_kernel(const PassArgs a) {
     pdl_launch_dependents();
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
@@ -805,7 +866,7 @@ template <int OCC> __global__ void __launch_bounds__(kThreads, OCC) raygen_exten
         }
         float t;
         uint32_t prim;
-        if (nearest<false>(S, live, o, d, t, prim)) { // all 32 lanes walk together
+        if (nearest<false, COOP>(S, live, o, d, t, prim)) { // all 32 lanes walk together
             const float4 tag = S.hot_row(prim, 3);
             const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
             if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
@@ -1382,7 +1443,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
 // and, once PassArgs::refill lanes are idle, the warp pulls that many new rays with ONE atomic. A warp's
 // time is then the sum of its rays' rounds / 32, not 32 x the longest walk.
 
-__global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, const int bounce) {
+template <bool COOP> __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, const int bounce) {
     pdl_launch_dependents();
     const SceneAccess<false> S = stage_scene<false>(a);
     pdl_wait();
@@ -1437,7 +1498,7 @@ __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, co
             if (!more) break;
             continue;
         }
-        if (w.step(S, have)) { // all 32 lanes: one round
+        if (w.template step<false, COOP>(S, have)) { // all 32 lanes: one round
             finished = true;
             have = false;
         }
@@ -1567,7 +1628,8 @@ static bool all_staged(const PassArgs& a) { // one leaf, everything in shared me
 size_t path_smem_bytes(const PassArgs& a) {
     size_t nb = (size_t(a.stage_nodes) * 8 + 15) & ~size_t(15);
     size_t cb = all_staged(a) ? size_t(a.stage_cold) * 32 + size_t(a.stage_lights) * 80 + size_t(a.scene.pairs_bytes) : 0;
-    return nb + size_t(a.stage_prims) * 64 + cb + size_t(a.stack_levels) * kThreads * 4 + 16;
+    return nb + size_t(a.stage_prims) * 64 + cb + size_t(a.stack_levels) * kThreads * 4 + 16 +
+           (a.coop_leaf ? size_t(kThreads / 32) * 32 * 8 : 0);
 }
 
 static char g_launch_error[256] = "";
@@ -1651,7 +1713,8 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
     } else {
         static const int occ = [] { const char* v = std::getenv("G19_RAYGEN_OCC"); return v ? std::atoi(v) : 3; }(); // tuning knob
         // 3 CTAs per SM at 80 registers (68 bytes of spills) beat 2 at 95: 23.8 vs 26.4 ms per 66 M camera rays
-        void (*kernel)(PassArgs) = occ == 2 ? raygen_extend_kernel<2> : raygen_extend_kernel<3>;
+        void (*kernel)(PassArgs) = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true> : raygen_extend_kernel<3, true>)
+                                               : (occ == 2 ? raygen_extend_kernel<2, false> : raygen_extend_kernel<3, false>);
         grid = persistent_grid(kernel, smem, sm_count);
         e = launch_pdl(kernel, grid, smem, s, a);
     }
@@ -1660,8 +1723,9 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
 
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a);
-    const int grid = persistent_grid(trace_kernel, smem, sm_count);
-    cudaError_t e = launch_pdl(trace_kernel, grid, smem, s, a, bounce);
+    void (*kernel)(PassArgs, int) = a.coop_leaf ? trace_kernel<true> : trace_kernel<false>;
+    const int grid = persistent_grid(kernel, smem, sm_count);
+    cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);
     if (e != cudaSuccess) note_launch_error("trace kernel launch", e, smem, grid);
 }
 
