@@ -1,7 +1,7 @@
 """ctypes mirror of include/g19.h (struct layouts and enum values only)."""
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enum g19_entity_kind (reference include/entities.h, one value per class)
 IMP_SPHERE, IMP_TRIANGLE, EXP_RECTANGLE, EXP_BOX, EXP_SPHERE, EXP_QUAD, EXP_CUBE, EXP_CONE = range(8)
@@ -13,7 +13,7 @@ MODE_REF, MODE_PATH = 0, 1
 # enum g19_builtin_scene
 SCENE_DEFAULT, SCENE_CORNELL, SCENE_CORNELL_GLASS, SCENE_HEIGHTFIELD = range(4)
 # status
-OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NO_SCENE, ERR_CANCELLED, ERR_LIMIT, ERR_REJECTED = range(8)
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NO_SCENE, ERR_CANCELLED, ERR_LIMIT, ERR_REJECTED, ERR_TIMEOUT = range(9)
 K_EXTEND, K_SHADE, K_SHADOW, K_ACCUM, K_REF_VIS, K_REF_SHADE, K_OTHER = range(7)
 CLASS_NAMES = ["raygen_extend", "bounce", "shadow", "accumulate", "ref_visibility", "ref_shade", "other", "_"]
 

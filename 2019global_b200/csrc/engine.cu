@@ -24,7 +24,7 @@ using namespace g19;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error; // g19_last_error(NULL) reports the calling thread's last g19_create failure
 
 struct DevBuf {
     void* p = nullptr;
@@ -71,6 +71,7 @@ struct g19_ctx {
     int ref_depth = 0;
     // PATH view
     PathSceneBuffers path;
+    PathTuning tune; // environment read once in g19_create; g19_tune afterwards
 
     // per-render work buffers (local-pixel indexed)
     DevBuf ids_l, points_l, normals_l, rgb_l, colour_l, counters;
@@ -97,6 +98,9 @@ struct g19_frame {
     uint8_t* rgb = nullptr;
     unsigned epoch = 0; // frames rendered into it by THIS process (all ranks advance in lockstep)
     cudaIpcMemHandle_t handle{};
+    // sticky "a device-side wait gave up" word: pinned host memory of THIS process, mapped into the device
+    unsigned* h_status = nullptr;
+    unsigned* d_status = nullptr;
 };
 
 namespace {
@@ -118,6 +122,21 @@ void frame_layout(g19_frame* f) {
         f->rad = reinterpret_cast<float*>(static_cast<char*>(f->base) + rad_off);
         f->rgb = reinterpret_cast<uint8_t*>(static_cast<char*>(f->base) + rgb_off);
     }
+}
+
+int frame_status_alloc(g19_frame* f) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&f->h_status), 64, cudaHostAllocMapped) != cudaSuccess) return G19_ERR_CUDA;
+    *f->h_status = 0;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&f->d_status), f->h_status, 0) != cudaSuccess) return G19_ERR_CUDA;
+    return G19_OK;
+}
+// A frame on which a device-side wait timed out is dead: its pixels may be incomplete and a late signal of the
+// lost rank would count towards a later frame, so every further call refuses it.
+bool frame_dead(g19_ctx* ctx, const g19_frame* f) {
+    if (!f->h_status || *reinterpret_cast<volatile unsigned*>(f->h_status) == 0) return false;
+    ctx->err = "shared frame: a device-side wait gave up after 5 s (a rank was lost or fell behind); the frame may be "
+               "incomplete -- destroy it and create a new one";
+    return true;
 }
 
 #define G19_CUDA(ctx, call)                                                                              \
@@ -254,6 +273,12 @@ int check_params(g19_ctx* ctx, const g19_camera* cam, const g19_params* p) {
         ctx->err = "invalid camera/params";
         return G19_ERR_INVALID;
     }
+    // validated BEFORE anything is launched or signalled (a failed render must not leave a shared frame's
+    // arrival counter ahead of its epoch)
+    if (p->mode == G19_MODE_PATH && (p->spp < 1 || p->max_depth < 0 || p->max_depth > kMaxPathDepth)) {
+        ctx->err = "PATH mode needs spp >= 1 and 0 <= max_depth <= 64";
+        return G19_ERR_INVALID;
+    }
     if ((long long)p->width * p->height > (1ll << 30)) {
         ctx->err = "image larger than 2^30 pixels";
         return G19_ERR_LIMIT;
@@ -311,7 +336,7 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     t.end(G19_K_REF_SHADE, 1);
     t.begin();
     if (frame) { // shared frame: wait for the owner, scatter this rank's pixels into it, signal
-        launch_frame_acquire(frame->flags, frame->epoch - 1, s);
+        launch_frame_acquire(frame->flags, frame->epoch - 1, frame->d_status, s);
         launch_untile(map, ctx->rgb_l.as<uint8_t>(), nullptr, ctx->colour_l.as<float>(), frame->rgb, nullptr, frame->rad, s);
         launch_frame_signal(frame->flags, s);
         t.end(G19_K_OTHER, 3);
@@ -391,6 +416,7 @@ int g19_create(const int* devices, int n_devices, g19_ctx** out) {
     if (!ctx) return G19_ERR_INVALID;
     ctx->device = dev;
     ctx->sm_count = prop.multiProcessorCount;
+    path_tuning_from_env(ctx->tune);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaEventCreate(&ctx->cls0) != cudaSuccess || cudaEventCreate(&ctx->cls1) != cudaSuccess) {
@@ -428,7 +454,7 @@ int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene) {
     int rc = flatten_ref(ctx, *scene);
     if (rc != G19_OK) return rc;
     std::string perr;
-    rc = path_upload(ctx->path, *scene, ctx->stream, perr);
+    rc = path_upload(ctx->path, *scene, ctx->tune, ctx->stream, perr);
     if (rc != G19_OK) {
         ctx->err = perr;
         return rc;
@@ -455,6 +481,7 @@ static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3]
     } else {
         RefCamera rc64 = make_camera(*cam, light, p->width);
         PathRenderArgs a;
+        a.tune = ctx->tune;
         a.cam = rc64;
         a.params = *p;
         a.map = map;
@@ -479,12 +506,14 @@ static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3]
             a.frame_rgb = frame->rgb;
             a.frame_rad = frame->rad;
             a.frame_flags = frame->flags;
+            a.frame_status = frame->d_status;
             a.frame_need_consumed = frame->epoch - 1;
         }
         std::string perr;
-        if (frame && map.n_local_pix == 0) launch_frame_signal(frame->flags, s); // no tiles: still counted
         rc = path_render(ctx->path, ctx->work, a, ctx->stats, perr);
         if (rc != G19_OK) ctx->err = perr;
+        // a rank without tiles still counts as arrived -- signalled only once the render call has succeeded
+        if ((rc == G19_OK || rc == G19_ERR_CANCELLED) && frame && map.n_local_pix == 0) launch_frame_signal(frame->flags, s);
     }
     if (rc != G19_OK && rc != G19_ERR_CANCELLED) return rc;
     G19_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
@@ -567,6 +596,12 @@ int g19_frame_create(g19_ctx* ctx, int w, int h, g19_frame** out) {
         return G19_ERR_CUDA;
     }
     frame_layout(f);
+    if (frame_status_alloc(f) != G19_OK) {
+        ctx->err = "g19_frame_create: cudaHostAlloc of the status word failed";
+        cudaFree(f->base);
+        delete f;
+        return G19_ERR_CUDA;
+    }
     *out = f;
     return G19_OK;
 }
@@ -621,6 +656,12 @@ int g19_frame_import(g19_ctx* ctx, const void* blob, size_t blob_bytes, g19_fram
         delete f;
         return G19_ERR_INVALID;
     }
+    if (frame_status_alloc(f) != G19_OK) {
+        ctx->err = "g19_frame_import: cudaHostAlloc of the status word failed";
+        cudaIpcCloseMemHandle(f->base);
+        delete f;
+        return G19_ERR_CUDA;
+    }
     *out = f;
     return G19_OK;
 }
@@ -633,6 +674,7 @@ void g19_frame_destroy(g19_frame* f) {
         if (f->owner) cudaFree(f->base);
         else cudaIpcCloseMemHandle(f->base);
     }
+    if (f->h_status) cudaFreeHost(f->h_status);
     delete f;
 }
 
@@ -650,6 +692,7 @@ int g19_render_to_frame(g19_ctx* ctx, const g19_camera* cam, const double light[
         ctx->err = "g19_render_to_frame: params do not match the frame size";
         return G19_ERR_INVALID;
     }
+    if (frame_dead(ctx, f)) return G19_ERR_TIMEOUT;
     ++f->epoch;
     int rc = render_any(ctx, cam, light, p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream, f);
     if (rc != G19_OK && rc != G19_ERR_CANCELLED) --f->epoch;
@@ -658,14 +701,16 @@ int g19_render_to_frame(g19_ctx* ctx, const g19_camera* cam, const double light[
 
 int g19_frame_wait(g19_ctx* ctx, g19_frame* f, int world, void* stream) {
     if (!ctx || !f || !f->owner || world < 1) return G19_ERR_INVALID;
+    if (frame_dead(ctx, f)) return G19_ERR_TIMEOUT;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
-    launch_frame_wait(f->flags, f->epoch * unsigned(world), static_cast<cudaStream_t>(stream));
+    launch_frame_wait(f->flags, f->epoch * unsigned(world), f->d_status, static_cast<cudaStream_t>(stream));
     G19_CUDA(ctx, cudaGetLastError());
     return G19_OK;
 }
 
 int g19_frame_release(g19_ctx* ctx, g19_frame* f, void* stream) {
     if (!ctx || !f || !f->owner) return G19_ERR_INVALID;
+    if (frame_dead(ctx, f)) return G19_ERR_TIMEOUT;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
     launch_frame_release(f->flags, f->epoch, static_cast<cudaStream_t>(stream));
     G19_CUDA(ctx, cudaGetLastError());
@@ -674,6 +719,7 @@ int g19_frame_release(g19_ctx* ctx, g19_frame* f, void* stream) {
 
 int g19_frame_read(g19_ctx* ctx, g19_frame* f, uint8_t* rgb_out, float* rad_out, void* stream) {
     if (!ctx || !f || !f->owner) return G19_ERR_INVALID;
+    if (frame_dead(ctx, f)) return G19_ERR_TIMEOUT;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     size_t npx = size_t(f->w) * size_t(f->h);
@@ -686,6 +732,22 @@ int g19_frame_timeouts(g19_ctx* ctx, g19_frame* f, unsigned* out) {
     if (!ctx || !f || !out) return G19_ERR_INVALID;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
     G19_CUDA(ctx, cudaMemcpy(out, f->flags + 64, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return G19_OK;
+}
+
+int g19_frame_status(g19_ctx* ctx, g19_frame* f, void* stream) {
+    if (!ctx || !f) return G19_ERR_INVALID;
+    G19_CUDA(ctx, cudaSetDevice(ctx->device));
+    G19_CUDA(ctx, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return frame_dead(ctx, f) ? G19_ERR_TIMEOUT : G19_OK;
+}
+
+int g19_tune(g19_ctx* ctx, const char* key, const char* value) {
+    if (!ctx || !key) return G19_ERR_INVALID;
+    if (!path_tuning_set(ctx->tune, key, value)) {
+        ctx->err = std::string("g19_tune: unknown key '") + key + "'";
+        return G19_ERR_INVALID;
+    }
     return G19_OK;
 }
 

@@ -100,12 +100,23 @@ __global__ void frame_signal_kernel(unsigned* flags) {
     atomicAdd_system(flags, 1u);
 }
 
-__global__ void frame_wait_kernel(unsigned* flags, unsigned target) {
+// A spin that gives up poisons the frame: it counts the timeout in the owner's flags AND raises the sticky
+// status word in this process's mapped host memory, which every later g19_frame_* call refuses on
+// (G19_ERR_TIMEOUT) -- an incomplete frame is never handed out as G19_OK.
+__device__ __forceinline__ void frame_give_up(unsigned* flags, unsigned* status) {
+    atomicAdd_system(flags + 64, 1u);
+    if (status) {
+        *reinterpret_cast<volatile unsigned*>(status) = 1u;
+        __threadfence_system();
+    }
+}
+
+__global__ void frame_wait_kernel(unsigned* flags, unsigned target, unsigned* status) {
     const unsigned long long t0 = now_ns();
     while (int(ld_acquire_sys(flags) - target) < 0) {
         __nanosleep(200);
         if (now_ns() - t0 > kSpinLimitNs) {
-            atomicAdd_system(flags + 64, 1u);
+            frame_give_up(flags, status);
             break;
         }
     }
@@ -116,12 +127,12 @@ __global__ void frame_release_kernel(unsigned* flags, unsigned epoch) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags + 32), "r"(epoch) : "memory");
 }
 
-__global__ void frame_acquire_kernel(unsigned* flags, unsigned need_consumed) {
+__global__ void frame_acquire_kernel(unsigned* flags, unsigned need_consumed, unsigned* status) {
     const unsigned long long t0 = now_ns();
     while (int(ld_acquire_sys(flags + 32) - need_consumed) < 0) {
         __nanosleep(500);
         if (now_ns() - t0 > kSpinLimitNs) {
-            atomicAdd_system(flags + 64, 1u);
+            frame_give_up(flags, status);
             break;
         }
     }
@@ -136,8 +147,8 @@ void launch_resolve_to_frame(const TileMap& map, const float* accum, int spp, ui
     resolve_to_frame_kernel<<<(quads + kThreads - 1) / kThreads, kThreads, 0, s>>>(map, accum, spp, rgb_frame, rad_frame);
 }
 void launch_frame_signal(unsigned* flags, cudaStream_t s) { frame_signal_kernel<<<1, 1, 0, s>>>(flags); }
-void launch_frame_wait(unsigned* flags, unsigned target, cudaStream_t s) { frame_wait_kernel<<<1, 1, 0, s>>>(flags, target); }
+void launch_frame_wait(unsigned* flags, unsigned target, unsigned* status, cudaStream_t s) { frame_wait_kernel<<<1, 1, 0, s>>>(flags, target, status); }
 void launch_frame_release(unsigned* flags, unsigned epoch, cudaStream_t s) { frame_release_kernel<<<1, 1, 0, s>>>(flags, epoch); }
-void launch_frame_acquire(unsigned* flags, unsigned need, cudaStream_t s) { frame_acquire_kernel<<<1, 1, 0, s>>>(flags, need); }
+void launch_frame_acquire(unsigned* flags, unsigned need, unsigned* status, cudaStream_t s) { frame_acquire_kernel<<<1, 1, 0, s>>>(flags, need, status); }
 
 } // namespace g19

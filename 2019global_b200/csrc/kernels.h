@@ -83,8 +83,9 @@ void launch_untile(const TileMap& map, const uint8_t* rgb_local, const int32_t* 
 void launch_resolve_to_frame(const TileMap& map, const float* accum, int spp, uint8_t* rgb_frame, float* rad_frame,
                              cudaStream_t stream);
 void launch_frame_signal(unsigned* flags, cudaStream_t stream);                  // arrived += 1 (system scope)
-void launch_frame_wait(unsigned* flags, unsigned target, cudaStream_t stream);   // owner: until arrived >= target
+// `status` (nullable): a word in this process's mapped host memory that a spin which gives up (5 s) sets to 1
+void launch_frame_wait(unsigned* flags, unsigned target, unsigned* status, cudaStream_t stream);   // owner: until arrived >= target
 void launch_frame_release(unsigned* flags, unsigned epoch, cudaStream_t stream); // owner: consumed = epoch
-void launch_frame_acquire(unsigned* flags, unsigned need, cudaStream_t stream);  // writer: until consumed >= need
+void launch_frame_acquire(unsigned* flags, unsigned need, unsigned* status, cudaStream_t stream);  // writer: until consumed >= need
 
 } // namespace g19

@@ -16,6 +16,7 @@
 #include "path.h"
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <limits>
 #include <cmath>
@@ -143,7 +144,36 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
     return root_lo + float(i) * std::ldexp(root_size, -level);
 }
 
-int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream, std::string& err) {
+void path_tuning_from_env(PathTuning& t) {
+    static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree"};
+    for (const char* k : keys) {
+        std::string env = "G19_";
+        for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
+        if (const char* v = std::getenv(env.c_str())) path_tuning_set(t, k, v);
+    }
+}
+
+bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
+    const PathTuning def;
+    const std::string k = key ? key : "";
+    auto num = [&](int dflt, int lo, int hi) { return value ? std::max(lo, std::min(hi, std::atoi(value))) : dflt; };
+    if (k == "lanes") t.lanes = num(def.lanes, 1, kMaxLanes);
+    else if (k == "pass_slots") t.pass_slots = value ? std::max<long long>(kTilePix, std::atoll(value)) : 0;
+    else if (k == "no_merge") t.no_merge = value ? 1 : 0; // present = on (as the environment variable was)
+    else if (k == "leaf_max") t.leaf_max = num(def.leaf_max, 1, 1 << 20);
+    else if (k == "refill") t.refill = num(def.refill, 1, 32);
+    else if (k == "coop_leaf") t.coop_leaf = num(def.coop_leaf, 0, 1);
+    else if (k == "walk_steps") t.walk_steps = num(def.walk_steps, 1, 16);
+    else if (k == "leaf_batch") t.leaf_batch = num(def.leaf_batch, 0, 16);
+    else if (k == "raygen_occ") t.raygen_occ = num(def.raygen_occ, 2, 3);
+    else if (k == "tree_build") t.tree_build = !value ? -1 : (std::strcmp(value, "device") == 0 ? 1 : (std::strcmp(value, "host") == 0 ? 0 : -1));
+    else if (k == "debug_tree") t.debug_tree = value ? 1 : 0;
+    else return false;
+    return true;
+}
+
+int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err) {
     const auto t_start = std::chrono::steady_clock::now();
     std::vector<BuildPrim> prims;
     std::vector<MaterialD> materials;
@@ -271,8 +301,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     // ---- linear octree, breadth first ------------------------------------------
     // measured on the 1M-triangle heightfield, ms per 1080p x 32 spp frame at 4 / 6 / 8 / 12 / 16 / 32: 107.3 / 107.7 / 107.6 /
     // 110.6 / 114.6 / 141.3 (an earlier walk, before the fixed-trip rounds, preferred 16)
-    int kLeafMax = 8;
-    if (const char* v = std::getenv("G19_LEAF_MAX")) kLeafMax = std::max(1, std::atoi(v)); // tuning knob
+    const int kLeafMax = tune.leaf_max;
     float root_lo[3] = {float(scene.rmin.x), float(scene.rmin.y), float(scene.rmin.z)};
     float root_hi[3] = {float(scene.rmax.x), float(scene.rmax.y), float(scene.rmax.z)};
     for (int k = 0; k < 3; ++k) { // the root box must enclose every primitive
@@ -289,7 +318,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     // Large scenes build the tree on the device (tree_build.cu: same rules, bit-identical result);
     // small ones -- and G19_TREE_BUILD=host -- here. The host builder is also the test's checker.
     bool on_device = prims.size() >= 4096;
-    if (const char* v = std::getenv("G19_TREE_BUILD")) on_device = std::strcmp(v, "device") == 0;
+    if (tune.tree_build >= 0) on_device = tune.tree_build == 1;
     PathNodeD* dev_nodes = nullptr;
     uint32_t* dev_index = nullptr;
     uint32_t dev_n_nodes = 0, dev_n_index = 0;
@@ -324,13 +353,16 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     }
     std::vector<PathNodeD> nodes(1);
     std::vector<uint32_t> index;
-    std::vector<Pending> frontier(1), next;
-    if (on_device) frontier.clear();
-    frontier[0].node = 0;
-    frontier[0].level = 0;
-    frontier[0].ix = frontier[0].iy = frontier[0].iz = 0;
-    frontier[0].prims.resize(prims.size());
-    for (size_t i = 0; i < prims.size(); ++i) frontier[0].prims[i] = uint32_t(i);
+    std::vector<Pending> frontier, next;
+    if (!on_device) { // the host builder starts from the root; a device-built tree leaves the frontier empty
+        Pending root;
+        root.node = 0;
+        root.level = 0;
+        root.ix = root.iy = root.iz = 0;
+        root.prims.resize(prims.size());
+        for (size_t i = 0; i < prims.size(); ++i) root.prims[i] = uint32_t(i);
+        frontier.push_back(std::move(root));
+    }
     int tree_depth = 0;
     while (!frontier.empty()) {
         next.clear();
@@ -380,14 +412,14 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream
     }
 
     const auto t_tree = std::chrono::steady_clock::now();
-    if (std::getenv("G19_DEBUG_TREE") && on_device) { // statistics need the arrays on the host
+    if (tune.debug_tree && on_device) { // statistics need the arrays on the host
         nodes.resize(dev_n_nodes);
         index.resize(dev_n_index);
         cudaMemcpy(nodes.data(), dev_nodes, size_t(dev_n_nodes) * sizeof(PathNodeD), cudaMemcpyDeviceToHost);
         cudaMemcpy(index.data(), dev_index, size_t(dev_n_index) * sizeof(uint32_t), cudaMemcpyDeviceToHost);
         tree_depth = dev_depth;
     }
-    if (std::getenv("G19_DEBUG_TREE")) {
+    if (tune.debug_tree) {
         std::fprintf(stderr, "[g19] path_upload: %zu primitives extracted in %.1f ms, tree built on the %s in %.1f ms\n", prims.size(),
                      std::chrono::duration<double, std::milli>(t_prims - t_start).count(), on_device ? "device" : "host",
                      std::chrono::duration<double, std::milli>(t_tree - t_prims).count());
@@ -548,6 +580,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     cudaStream_t s = a.stream;
     const size_t npix = size_t(a.map.n_local_pix);
     if (npix == 0) return G19_OK;
+    path_clear_launch_error();
     // Pass size. Flat scenes keep dense vertex records in their queues, so a bounce streams exactly
     // the live vertices whatever the pass size: bigger passes only amortise launch tails (measured on
     // B200, ms per 1080p x 64 spp frame at 2 / 4 / 8 / 16 M slots, one pass in flight: Cornell depth 5
@@ -561,7 +594,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     const bool flat_scene = b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= 192 &&
                             b.view.n_lights <= 32;
     size_t target = flat_scene ? (size_t(1) << 23) : (p.max_depth > 6 ? (size_t(1) << 22) : (size_t(1) << 24));
-    if (const char* v = std::getenv("G19_PASS_SLOTS")) target = std::max<size_t>(kTilePix, size_t(std::atoll(v))); // tuning knob
+    if (a.tune.pass_slots > 0) target = size_t(a.tune.pass_slots); // tuning knob
     size_t window = npix;
     if (p.pixels_per_pass > 0) window = std::min(npix, (size_t(p.pixels_per_pass) + kTilePix - 1) / kTilePix * kTilePix);
     else if (npix > target) window = target;
@@ -589,10 +622,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     // passes of this frame, and how many are kept in flight (see PathWork)
     const size_t n_windows = (npix + window - 1) / window;
     const size_t n_passes = n_windows * size_t((p.spp + spp_pass - 1) / spp_pass);
-    const int want_lanes = 4;
-    int n_lanes = (p.profile || a.on_pass) ? 1 : int(std::min<size_t>(want_lanes, n_passes)); // profiling and progressive refresh: one at a time
-    if (const char* v = std::getenv("G19_LANES")) // tuning knob
-        n_lanes = std::max(1, std::min(std::min<int>(kMaxLanes, int(n_passes)), (p.profile || a.on_pass) ? 1 : std::atoi(v)));
+    const int n_lanes = (p.profile || a.on_pass) ? 1 : int(std::min<size_t>(size_t(a.tune.lanes), n_passes)); // profiling and progressive refresh: one at a time
     if (n_lanes > 1 && !w.ev_fork) PATH_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < n_lanes; ++i) {
         if (i > 0 && !w.side[i]) PATH_CUDA(cudaStreamCreateWithFlags(&w.side[i], cudaStreamNonBlocking));
@@ -641,16 +671,13 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     if (b.view.n_lights > 32) pa0.stage_cold = 0; // not a "flat, fully staged" scene: the generic kernels take it
     pa0.stack_levels = b.view.tree_depth + 1;
     // tree scenes: the bounce kernels queue their rays (2 per vertex at most) for trace_kernel
-    pa0.refill = 8;
-    if (const char* v = std::getenv("G19_REFILL")) pa0.refill = std::max(1, std::min(32, std::atoi(v))); // tuning knob
+    pa0.refill = a.tune.refill;
     // tree walk: leaf tests spread over the whole warp, 8 primitives per ray and round (heightfield 1080p x 32 spp:
     // sequential 4 per round 107.1 ms, cooperative 4 / 8 / 16 per round 115.4 / 104.9 / 105.4)
-    pa0.coop_leaf = 1;
-    if (const char* v = std::getenv("G19_COOP_LEAF")) pa0.coop_leaf = std::atoi(v) != 0; // tuning knob
-    pa0.walk_steps = 4;
-    pa0.leaf_batch = pa0.coop_leaf ? 16 : 4; // cooperative: the whole leaf in one go (leaf max 8 / 12 / 16 at batch 16: 97.7 / 96.9 / 97.8 ms)
-    if (const char* v = std::getenv("G19_WALK_STEPS")) pa0.walk_steps = std::max(1, std::min(16, std::atoi(v))); // tuning knob
-    if (const char* v = std::getenv("G19_LEAF_BATCH")) pa0.leaf_batch = std::max(1, std::min(16, std::atoi(v))); // tuning knob
+    pa0.coop_leaf = a.tune.coop_leaf;
+    pa0.walk_steps = a.tune.walk_steps;
+    pa0.leaf_batch = a.tune.leaf_batch > 0 ? a.tune.leaf_batch : (pa0.coop_leaf ? 16 : 4); // cooperative: the whole leaf in one go (leaf max 8 / 12 / 16 at batch 16: 97.7 / 96.9 / 97.8 ms)
+    pa0.raygen_occ = a.tune.raygen_occ;
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
 
     // per-lane buffers
@@ -711,7 +738,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         PATH_CUDA(cudaEventRecord(w.ev_fork, s));
         for (int i = 1; i < n_lanes; ++i) PATH_CUDA(cudaStreamWaitEvent(w.side[i], w.ev_fork, 0));
     }
-    const bool merge_kinds = std::getenv("G19_NO_MERGE") == nullptr; // tuning knob: one launch per material queue
+    const bool merge_kinds = !a.tune.no_merge; // tuning knob: one launch per material queue
     ClassClock clk{w, s, p.profile != 0};
     int rc = G19_OK;
     auto last_refresh = std::chrono::steady_clock::now();
@@ -796,7 +823,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     if (a.frame_flags) {
         // fused resolve + untile + gather: wait until the owner is done with the previous frame,
         // store this rank's pixels into the shared frame, then signal arrival
-        launch_frame_acquire(a.frame_flags, a.frame_need_consumed, s);
+        launch_frame_acquire(a.frame_flags, a.frame_need_consumed, a.frame_status, s);
         launch_resolve_to_frame(a.map, pa0.accum, done_spp > 0 ? done_spp : 1, a.frame_rgb, a.frame_rad, s);
         launch_frame_signal(a.frame_flags, s);
         clk.end(G19_K_OTHER);
@@ -817,6 +844,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         err = le;
         path_clear_launch_error();
         cudaGetLastError();
+        // a pass stopped half way: its lanes' radiance planes and queue lengths are dirty -- re-zero them before the next render
+        for (PathLane& l : w.lane) l.capacity = 0;
         return G19_ERR_CUDA;
     }
     PATH_CUDA(cudaGetLastError());

@@ -99,7 +99,26 @@ struct PathWork {
     cudaStream_t totals_stream = nullptr;
 };
 
+// Tuning knobs. Read ONCE from the environment at g19_create (G19_LANES, G19_PASS_SLOTS, ...),
+// changed afterwards only through g19_tune: no getenv on the render path.
+struct PathTuning {
+    int lanes = 4;            // passes kept in flight
+    long long pass_slots = 0; // path slots per pass (0 = auto)
+    int no_merge = 0;         // one launch per material queue instead of one per bounce
+    int leaf_max = 8;         // primitives per octree leaf (read at scene upload)
+    int refill = 8;           // trace_kernel: idle lanes per warp that trigger a ray fetch
+    int coop_leaf = 1;        // warp-cooperative leaf tests
+    int walk_steps = 4;       // cell moves per round of the tree walk
+    int leaf_batch = 0;       // primitives per ray and round (0 = auto: 16 cooperative, 4 sequential)
+    int raygen_occ = 3;       // CTAs per SM of the tree-scene camera-ray kernel
+    int tree_build = -1;      // -1 auto (device from 4096 primitives), 0 host, 1 device
+    int debug_tree = 0;       // print octree statistics at upload
+};
+void path_tuning_from_env(PathTuning& t);
+bool path_tuning_set(PathTuning& t, const char* key, const char* value); // false: unknown key
+
 struct PathRenderArgs {
+    PathTuning tune;
     RefCamera cam;
     g19_params params;
     TileMap map;
@@ -112,6 +131,7 @@ struct PathRenderArgs {
     uint8_t* frame_rgb = nullptr;
     float* frame_rad = nullptr;
     unsigned* frame_flags = nullptr;
+    unsigned* frame_status = nullptr; // mapped host word raised by a device-side wait that gives up
     unsigned frame_need_consumed = 0;
     // progressive refresh (g19_render_progressive): d_rgb is resolved and copied to h_rgb between passes
     g19_pass_fn on_pass = nullptr;
@@ -129,7 +149,7 @@ struct PathRenderArgs {
 int path_build_tree_device(const float* d_boxes, uint32_t n_prims, const float root_lo[3], const float root_size[3],
                            int leaf_max, int max_depth, cudaStream_t s, PathNodeD** d_nodes, uint32_t* n_nodes,
                            uint32_t** d_index, uint32_t* n_index, int* tree_depth, std::string& err);
-int path_upload(PathSceneBuffers& b, const g19_scene& scene, cudaStream_t stream, std::string& err);
+int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err);
 int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err);
 int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err);
 void path_release(PathSceneBuffers& b, PathWork& w);
@@ -173,6 +193,7 @@ struct PassArgs {
     int32_t refill;        // trace_kernel: idle lanes per warp that trigger a fetch of new rays
     int32_t walk_steps, leaf_batch; // tree walk: cell moves / primitives tested per round (TreeWalk::step)
     int32_t coop_leaf;     // tree walk: leaf tests spread over the whole warp (default; G19_COOP_LEAF=0: sequential)
+    int32_t raygen_occ;    // tree scenes: CTAs per SM of the camera-ray kernel (2 or 3)
 };
 
 void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s);

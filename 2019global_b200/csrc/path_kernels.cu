@@ -1632,7 +1632,9 @@ size_t path_smem_bytes(const PassArgs& a) {
            (a.coop_leaf ? size_t(kThreads / 32) * 32 * 8 : 0);
 }
 
-static char g_launch_error[256] = "";
+// per thread: launches are issued and their errors collected on the thread inside path_render, so several
+// g19_ctx driven from several threads never see (or race on) each other's failures
+static thread_local char g_launch_error[256] = "";
 static void note_launch_error(const char* what, cudaError_t e, size_t smem, int grid) {
     if (!g_launch_error[0])
         snprintf(g_launch_error, sizeof g_launch_error, "%s: %s (dynamic smem %zu B, grid %d)", what, cudaGetErrorString(e),
@@ -1711,7 +1713,7 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
         grid = persistent_grid(kernel, smem, sm_count);
         e = launch_pdl(kernel, grid, smem, s, a);
     } else {
-        static const int occ = [] { const char* v = std::getenv("G19_RAYGEN_OCC"); return v ? std::atoi(v) : 3; }(); // tuning knob
+        const int occ = a.raygen_occ; // tuning knob
         // 3 CTAs per SM at 80 registers (68 bytes of spills) beat 2 at 95: 23.8 vs 26.4 ms per 66 M camera rays
         void (*kernel)(PassArgs) = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true> : raygen_extend_kernel<3, true>)
                                                : (occ == 2 ? raygen_extend_kernel<2, false> : raygen_extend_kernel<3, false>);

@@ -33,6 +33,7 @@ EXPORTS = [
     "g19_render_to_frame", "g19_frame_wait", "g19_frame_release", "g19_frame_timeouts",
     "g19_frame_read", "g19_render_progressive", "g19_render_tiles_device", "g19_untile_device", "g19_tile_pixels",
     "g19_probe_texcoord", "g19_probe_shade", "g19_probe_path_tree", "g19_entity_bbox", "g19_entity_triangles",
+    "g19_frame_status", "g19_tune",
 ]
 
 
@@ -95,6 +96,8 @@ def lib():
         L.g19_frame_release.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.g19_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.g19_frame_timeouts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint)]
+        L.g19_frame_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.g19_tune.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         _lib = L
     return _lib
 
@@ -288,6 +291,11 @@ class RayTracer:
                                                      C.c_void_p(d_rgb), C.c_void_p(d_ids), C.c_void_p(d_rad),
                                                      C.c_void_p(stream)), allow=(abi.ERR_CANCELLED,))
 
+    def tune(self, key, value=None):
+        """g19_tune: set one tuning knob ("lanes", "no_merge", ...); value None = back to the default."""
+        v = None if value is None else str(value).encode()
+        self._check(self._L.g19_tune(self.h, key.encode(), v))
+
     def stats(self):
         s = abi.Stats()
         self._check(self._L.g19_get_stats(self.h, C.byref(s)))
@@ -402,6 +410,10 @@ class SharedFrame:
     def release(self, stream=0):
         """Owner: done reading; the ranks may overwrite the frame with the next one."""
         self.rt._check(self.rt._L.g19_frame_release(self.rt.h, self.h_, C.c_void_p(stream)))
+
+    def check(self, stream=0):
+        """Synchronise `stream`, then raise G19Error(ERR_TIMEOUT) if any device-side wait on this frame gave up."""
+        self.rt._check(self.rt._L.g19_frame_status(self.rt.h, self.h_, C.c_void_p(stream)))
 
     def timeouts(self):
         v = C.c_uint(0)

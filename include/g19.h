@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define G19_ABI_VERSION 3
+#define G19_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -34,7 +34,8 @@ enum {
     G19_ERR_NO_SCENE = 4,  /* render before g19_upload_scene                 */
     G19_ERR_CANCELLED = 5, /* g19_cancel observed; output is partial         */
     G19_ERR_LIMIT = 6,     /* scene exceeds a documented device-side limit   */
-    G19_ERR_REJECTED = 7   /* entity rejected by the root-overlap test       */
+    G19_ERR_REJECTED = 7,  /* entity rejected by the root-overlap test       */
+    G19_ERR_TIMEOUT = 8    /* shared frame: a device-side wait gave up (lost rank); the frame is dead */
 };
 
 /* ---- entities (reference include/entities.h) ---------------------------- */
@@ -258,7 +259,12 @@ int g19_untile_device(g19_ctx* ctx, int width, int height, int rank, int world,
  *                       for it (device side, never the host) before overwriting pixels
  *   g19_frame_read      owner: enqueue copies of the frame into host (pinned) or device buffers
  *   g19_frame_pointers  owner's device pointers (row-major, row 0 = top)
- *   g19_frame_timeouts  device-side spins that gave up after 5 s (a lost rank); 0 in a healthy run */
+ *   g19_frame_timeouts  device-side spins that gave up after 5 s (a lost rank); 0 in a healthy run
+ *   g19_frame_status    synchronises `stream`, then G19_OK or G19_ERR_TIMEOUT. A spin that gives up raises a sticky
+ *                       word in the calling process's mapped host memory; from then on EVERY g19_frame_* /
+ *                       g19_render_to_frame call on that frame returns G19_ERR_TIMEOUT (its pixels may be
+ *                       incomplete and a late arrival of the lost rank would count towards a later frame): destroy
+ *                       it and create a new one. Call g19_frame_status before trusting what g19_frame_read copied. */
 typedef struct g19_frame g19_frame;
 #define G19_FRAME_BLOB_BYTES 128
 int g19_frame_create(g19_ctx* ctx, int width, int height, g19_frame** out);
@@ -272,6 +278,13 @@ int g19_frame_wait(g19_ctx* ctx, g19_frame* frame, int world, void* stream);
 int g19_frame_release(g19_ctx* ctx, g19_frame* frame, void* stream);
 int g19_frame_read(g19_ctx* ctx, g19_frame* frame, uint8_t* rgb888_out, float* radiance_out, void* stream);
 int g19_frame_timeouts(g19_ctx* ctx, g19_frame* frame, unsigned* out);
+int g19_frame_status(g19_ctx* ctx, g19_frame* frame, void* stream);
+
+/* Tuning knobs: "lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf",
+ * "walk_steps", "leaf_batch", "raygen_occ", "tree_build", "debug_tree". g19_create reads them ONCE from the
+ * environment (G19_LANES, ...); this call changes one afterwards (value NULL = back to the default). Nothing
+ * on the render path reads the environment. No counterpart in the reference (it has no knobs). */
+int g19_tune(g19_ctx* ctx, const char* key, const char* value);
 
 /* RayTracer::stop()/running()                              raytracer.h:89-91 */
 int g19_cancel(g19_ctx* ctx);

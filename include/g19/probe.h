@@ -5,6 +5,7 @@
 // for one ray / one point. They exist for interface completeness and for
 // tests; RayTracer::run never goes through them.
 #pragma once
+#include <cstring>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -34,15 +35,51 @@ inline std::mutex& probe_mutex() {
     return m;
 }
 
+// What the probe context currently holds: a whole Octree's scene (handle, version) or a single entity's
+// descriptor -- repeated probes of the same thing skip the upload (callers hold probe_mutex()).
+struct ProbeCache {
+    unsigned long serial = 0; // Octree::_serial (process-unique, never reused), 0 = none
+    unsigned version = 0;
+    bool single = false;
+    g19_entity_desc desc;
+};
+inline ProbeCache& probe_cache() {
+    static ProbeCache c;
+    return c;
+}
+
+inline unsigned long next_serial() {
+    static std::mutex m;
+    static unsigned long n = 0;
+    std::lock_guard<std::mutex> lock(m);
+    return ++n;
+}
+
+inline void upload_cached(const g19_scene* s, unsigned long serial, unsigned version) {
+    ProbeCache& c = probe_cache();
+    if (!c.single && c.serial == serial && c.version == version) return;
+    c.serial = 0;
+    check(g19_upload_scene(probe_ctx(), s), probe_ctx(), "g19_upload_scene");
+    c.serial = serial;
+    c.version = version;
+    c.single = false;
+}
+
 // Uploads a scene holding exactly `d` (a root box that always accepts it).
 inline void load_single(const g19_entity_desc& d) {
+    ProbeCache& c = probe_cache();
+    if (c.single && std::memcmp(&c.desc, &d, sizeof d) == 0) return;
+    c.single = false;
+    c.serial = 0;
     const double lo[3] = {-1e30, -1e30, -1e30}, hi[3] = {1e30, 1e30, 1e30};
     g19_scene* s = nullptr;
     check(g19_scene_create(lo, hi, &s), nullptr, "g19_scene_create");
-    g19_scene_add_entity(s, &d, nullptr);
-    int rc = g19_upload_scene(probe_ctx(), s);
+    int rc = g19_scene_add_entity(s, &d, nullptr);
+    if (rc == G19_OK) rc = g19_upload_scene(probe_ctx(), s);
     g19_scene_destroy(s);
-    check(rc, probe_ctx(), "g19_upload_scene");
+    check(rc, probe_ctx(), "g19_scene_add_entity / g19_upload_scene");
+    std::memcpy(&c.desc, &d, sizeof d);
+    c.single = true;
 }
 
 inline bool intersect_one(const g19_entity_desc& d, glm::dvec3 o, glm::dvec3 dir, glm::dvec3& point, glm::dvec3& normal) {

@@ -26,7 +26,10 @@ class Octree {
 
     void push_back(Entity* object) {
         g19_entity_desc d = object->describe();
-        g19_scene_add_entity(_scene.get(), &d, nullptr); // a root-test reject is silent, as in octree.h:22-24
+        // a root-test reject is silent, as in octree.h:22-24 (the engine still numbers the entity); anything else
+        // means the engine did NOT number it, and appending it here would shift every later id
+        const int rc = g19_scene_add_entity(_scene.get(), &d, nullptr);
+        if (rc != G19_OK && rc != G19_ERR_REJECTED) g19::detail::check(rc, nullptr, "g19_scene_add_entity");
         _entities.push_back(object);
         ++_version;
     }
@@ -34,7 +37,7 @@ class Octree {
     std::vector<Entity*> intersect(const Ray& ray) const {
         std::lock_guard<std::mutex> lock(g19::detail::probe_mutex());
         g19_ctx* ctx = g19::detail::probe_ctx();
-        g19::detail::check(g19_upload_scene(ctx, _scene.get()), ctx, "g19_upload_scene");
+        g19::detail::upload_cached(_scene.get(), _serial, _version);
         const double o[3] = {ray.origin.x, ray.origin.y, ray.origin.z}, d[3] = {ray.dir.x, ray.dir.y, ray.dir.z};
         int n = 0;
         std::vector<int32_t> ids(1 << 16);
@@ -53,4 +56,5 @@ class Octree {
     std::shared_ptr<g19_scene> _scene;
     std::vector<Entity*> _entities; // id = push order, same numbering as the engine
     unsigned _version = 0;
+    unsigned long _serial = g19::detail::next_serial(); // identifies this Octree to the probe upload cache
 };

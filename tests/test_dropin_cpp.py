@@ -43,9 +43,11 @@ def test_headless_driver_reproduces_config1(tmp_path):
     assert r.returncode == 0, r.stderr
     img = _ppm(out)
     assert img.shape == (500, 500, 3)
-    # config-1 golden: <= 1 LSB, <= 0.1 % of shaded pixels exempt; in practice byte-exact
-    print("headless sha256 match:", hashlib.sha256(img.tobytes()).hexdigest() == C1_SHA, "|", r.stdout.strip())
-    assert (img.reshape(-1, 3).max(1) > 0).sum() == 14702 + 20806 + 17674 or True
+    # config-1 golden: the contract allows <= 1 LSB with <= 0.1 % of shaded pixels exempt
+    # (SURVEY 8(c)); on B200 with this toolchain the image is byte-exact, and that is what is asserted
+    assert hashlib.sha256(img.tobytes()).hexdigest() == C1_SHA, r.stdout
+    # every pixel the reference shades is non-black here (ambient term 0.1 * texture > 0), every miss is black
+    assert int((img.reshape(-1, 3).max(1) > 0).sum()) == 14702 + 20806 + 17674
     assert "ImpSphere::intersect -> 1" in r.stdout and "candidates 3" in r.stdout
     import importlib
     g19 = importlib.import_module("2019global_b200")
@@ -54,6 +56,11 @@ def test_headless_driver_reproduces_config1(tmp_path):
     rt.setScene(sc)
     rt.start()
     assert np.array_equal(rt.run(500, 500)["rgb"], img)  # same bytes as the Python front end
+    # ... and the same bytes as the CPU oracle (itself byte-equal to the compiled reference, test_oracle_ref.py)
+    from oracle import binding
+    from util import mirror
+    exp = mirror(binding.CheckerLib("oracle"), sc).trace(cam, light, 500, 500, want=("rgb",), threads=8)["rgb"]
+    assert np.array_equal(exp, img)
 
 
 @pytest.mark.gpu

@@ -248,7 +248,7 @@ def test_flat_scene_pair_padding(g19, abi, oracle, n_quads, n_tris, n_spheres):
 
 
 @pytest.mark.parametrize("which,depth", [("CORNELL", 5), ("CORNELL_GLASS", 9)])
-def test_passes_in_flight_and_merged_launch_bit_identical(g19, abi, which, depth, monkeypatch):
+def test_passes_in_flight_and_merged_launch_bit_identical(g19, abi, which, depth):
     """Up to four passes run concurrently on their own streams (PathWork lanes), and scenes with mirror /
     glass serve the three material queues of a bounce from one launch. Neither may change a bit: the
     accumulation stays in pass order (events) and every vertex is shaded by the same code."""
@@ -264,9 +264,9 @@ def test_passes_in_flight_and_merged_launch_bit_identical(g19, abi, which, depth
     base = render()  # default: four lanes, merged launch
     assert base.mean() > 0.05
     for lanes in ("1", "2", "3"):
-        monkeypatch.setenv("G19_LANES", lanes)
+        rt.tune("lanes", lanes)
         assert render().tobytes() == base.tobytes(), "lanes=" + lanes
-    monkeypatch.setenv("G19_NO_MERGE", "1")
+    rt.tune("no_merge", "1")
     assert render().tobytes() == base.tobytes(), "one launch per material queue"
 
 

@@ -41,8 +41,9 @@ def test_config1_default_scene(g19, abi, oracle):
     assert hist.tolist() == [196818, 14702, 20806, 17674]
     assert hashlib.sha256(exp["rgb"].tobytes()).hexdigest() == C1_SHA  # the oracle itself is pinned
     n_any, n_off = _check_colours(got["rgb"], exp["rgb"], exp["ids"])
-    same_hash = hashlib.sha256(got["rgb"].tobytes()).hexdigest() == C1_SHA
-    print("config-1: %d px differ by 1 LSB, %d by more; sha256 match: %s" % (n_any - n_off, n_off, same_hash))
+    # the contract is <= 1 LSB (checked above); on B200 with this toolchain the frame is byte-exact: assert it
+    assert n_any == 0, "%d px differ by 1 LSB, %d by more" % (n_any - n_off, n_off)
+    assert hashlib.sha256(got["rgb"].tobytes()).hexdigest() == C1_SHA
     # float colour is the unquantised value of the same pixel
     q = np.floor(255.0 * np.clip(got["radiance"].astype(np.float64), 0, 1) + 1e-4).astype(np.int32)
     assert np.abs(q - got["rgb"].astype(np.int32)).max() <= 1
