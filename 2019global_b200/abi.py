@@ -11,7 +11,7 @@ BSDF_DIFFUSE, BSDF_MIRROR, BSDF_GLASS, BSDF_EMITTER = range(4)
 # enum g19_mode
 MODE_REF, MODE_PATH = 0, 1
 # enum g19_builtin_scene
-SCENE_DEFAULT, SCENE_CORNELL, SCENE_CORNELL_GLASS, SCENE_HEIGHTFIELD = range(4)
+SCENE_DEFAULT, SCENE_CORNELL, SCENE_CORNELL_GLASS, SCENE_HEIGHTFIELD, SCENE_HEIGHTFIELD_ROOM = range(5)
 # status
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NO_SCENE, ERR_CANCELLED, ERR_LIMIT, ERR_REJECTED, ERR_TIMEOUT = range(9)
 K_EXTEND, K_SHADE, K_SHADOW, K_ACCUM, K_REF_VIS, K_REF_SHADE, K_OTHER = range(7)

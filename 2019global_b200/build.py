@@ -22,7 +22,10 @@ LIB = os.path.join(HERE, "lib2019global_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function"]
+          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function",
+          # hardened libstdc++ on the host side (bounds-checked operator[] etc.): every GPU test then also checks
+          # the scene / tree builders for out-of-range accesses; the cost is invisible next to the kernels
+          "-D_GLIBCXX_ASSERTIONS"]
 UNITS = [
     ("scene.cpp", []),
     ("builtin_scenes.cpp", []),

@@ -14,7 +14,9 @@
 //   G19_SCENE_CORNELL_GLASS  C3: same, one mirror and one glass (ior 1.5) sphere
 //   G19_SCENE_HEIGHTFIELD    C4: x = 6 + 1.5 sin(0.7y) cos(0.9z) over y,z in
 //                            [-8,8], n x n cells, 2 n^2 ImpTriangle entities
-//                            (n = 708 -> 1 002 528 triangles)
+//                            (n = 708 -> 1 002 528 triangles), lit by a panel behind the camera
+//   G19_SCENE_HEIGHTFIELD_ROOM  C4 as benchmarked: the same surface as the far wall of a closed
+//                            room with a ceiling light, so that paths live to the depth limit
 #include <cmath>
 
 #include "scene.h"
@@ -121,14 +123,30 @@ void cornell(g19_scene* s, bool glass) {
     add_sphere(s, -0.5, -2.6, -4.0, 2.f, white, glass ? G19_BSDF_GLASS : G19_BSDF_DIFFUSE);
 }
 
-void heightfield(g19_scene* s, int n) {
+void heightfield(g19_scene* s, int n, bool room) {
     const double grey[3] = {0.7, 0.7, 0.7}, lit[3] = {1.0, 1.0, 1.0};
+    if (room) {
+        // C4 as a CLOSED room (a scene where bounces survive): the surface is the far wall of a box
+        // x in [-12, 8], y,z in [-8, 8] with a ceiling light; walls first, light next, the mesh last (far-to-near
+        // does not apply: the mesh is the farthest thing the camera sees)
+        const double white[3] = {0.73, 0.73, 0.73}, red[3] = {0.65, 0.05, 0.05}, green[3] = {0.12, 0.45, 0.15};
+        const double x0 = -12, x1 = 8, y0 = -8, y1 = 8, z0 = -8, z1 = 8;
+        { double a[3] = {x1, y0, z0}, b[3] = {x1, y1, z0}, c[3] = {x1, y1, z1}, d[3] = {x1, y0, z1}; add_quad(s, a, b, c, d, white); }
+        { double a[3] = {x0, y0, z0}, b[3] = {x0, y0, z1}, c[3] = {x0, y1, z1}, d[3] = {x0, y1, z0}; add_quad(s, a, b, c, d, white); }
+        { double a[3] = {x0, y0, z0}, b[3] = {x1, y0, z0}, c[3] = {x1, y1, z0}, d[3] = {x0, y1, z0}; add_quad(s, a, b, c, d, white); }
+        { double a[3] = {x0, y0, z1}, b[3] = {x0, y1, z1}, c[3] = {x1, y1, z1}, d[3] = {x1, y0, z1}; add_quad(s, a, b, c, d, white); }
+        { double a[3] = {x0, y1, z0}, b[3] = {x1, y1, z0}, c[3] = {x1, y1, z1}, d[3] = {x0, y1, z1}; add_quad(s, a, b, c, d, red); }
+        { double a[3] = {x0, y0, z0}, b[3] = {x0, y0, z1}, c[3] = {x1, y0, z1}, d[3] = {x1, y0, z0}; add_quad(s, a, b, c, d, green); }
+        const double zl = z1 - 0.02;
+        double a[3] = {-5, -4, zl}, b[3] = {3, -4, zl}, c[3] = {3, 4, zl}, d[3] = {-5, 4, zl};
+        add_quad(s, a, b, c, d, lit, G19_BSDF_EMITTER, 9.f);
+    }
     auto vertex = [n](int j, int k, double* p) {
         double y = -8.0 + 16.0 * double(j) / double(n);
         double z = -8.0 + 16.0 * double(k) / double(n);
         set3(p, 6.0 + 1.5 * std::sin(0.7 * y) * std::cos(0.9 * z), y, z);
     };
-    s->ents.reserve(size_t(2) * n * n + 2);
+    s->ents.reserve(s->ents.size() + size_t(2) * n * n + 2);
     for (int k = 0; k < n; ++k) {
         for (int j = 0; j < n; ++j) {
             double a[3], b[3], c[3], d[3];
@@ -139,6 +157,7 @@ void heightfield(g19_scene* s, int n) {
             add_quad(s, a, b, c, d, grey);
         }
     }
+    if (room) return;
     // a large emitter behind and above the camera, facing the surface
     double a[3] = {-14, -9, -9}, b[3] = {-14, 9, -9}, c[3] = {-14, 9, 9}, d[3] = {-14, -9, 9};
     add_quad(s, a, b, c, d, lit, G19_BSDF_EMITTER, 2.f);
@@ -181,11 +200,12 @@ int make_builtin(int which, int n, int w, int h, g19_scene** out, g19_camera* ca
         if (light) set3(light, 1.0, 0.0, 5.5);
         break;
     case G19_SCENE_HEIGHTFIELD:
+    case G19_SCENE_HEIGHTFIELD_ROOM:
         if (n < 1 || n > 4096) {
             g19_scene_destroy(s);
             return G19_ERR_INVALID;
         }
-        heightfield(s, n);
+        heightfield(s, n, which == G19_SCENE_HEIGHTFIELD_ROOM);
         centred_camera(cam, -10, 0, 0, 0.2 * double(w) / 1920.0, w, h);
         if (light) set3(light, -10, 10, 10);
         break;

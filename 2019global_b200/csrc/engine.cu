@@ -290,6 +290,16 @@ int check_params(g19_ctx* ctx, const g19_camera* cam, const g19_params* p) {
     return G19_OK;
 }
 
+uint64_t owned_pixels(const TileMap& map) { // in-frame pixels owned by this rank
+    uint64_t owned = 0;
+    for (int lt = 0; lt < map.n_local_tiles; ++lt) {
+        int tile = lt * map.world + map.rank;
+        int ty = tile / map.tiles_x, tx = tile % map.tiles_x;
+        owned += uint64_t(std::min(kTile, map.w - tx * kTile)) * uint64_t(std::min(kTile, map.h - ty * kTile));
+    }
+    return owned;
+}
+
 struct ClassTimer { // CUDA-event timing of one kernel class (params.profile)
     g19_ctx* ctx;
     cudaStream_t s;
@@ -509,9 +519,51 @@ static int render_any(g19_ctx* ctx, const g19_camera* cam, const double light[3]
             a.frame_status = frame->d_status;
             a.frame_need_consumed = frame->epoch - 1;
         }
+        // primary-hit AOV (hit_id_out in PATH mode) and the depth-0 slice (max_depth = 0: the reference's own
+        // direct shade of the PATH primary hit, material.h:48-62) share REF mode's work buffers
+        const bool depth0 = p->max_depth == 0;
+        const size_t n = size_t(map.n_local_pix);
+        if ((d_ids || t_ids || depth0) && n > 0) {
+            G19_CUDA(ctx, ctx->ids_l.ensure(n * sizeof(int32_t)));
+            a.ids_l = ctx->ids_l.as<int32_t>();
+            if (depth0) {
+                G19_CUDA(ctx, ctx->points_l.ensure(n * 3 * sizeof(double)));
+                G19_CUDA(ctx, ctx->normals_l.ensure(n * 3 * sizeof(double)));
+                G19_CUDA(ctx, ctx->rgb_l.ensure(n * 3));
+                G19_CUDA(ctx, ctx->colour_l.ensure(n * 3 * sizeof(float)));
+                a.points_l = ctx->points_l.as<double>();
+                a.normals_l = ctx->normals_l.as<double>();
+                a.frame_flags = nullptr; // the shade below delivers into the frame, not path_render's resolve
+            }
+        }
         std::string perr;
         rc = path_render(ctx->path, ctx->work, a, ctx->stats, perr);
         if (rc != G19_OK) ctx->err = perr;
+        if (rc == G19_OK && n > 0 && depth0) {
+            launch_ref_shade(ctx->ref, rc64, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                             ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s);
+            if (frame) {
+                launch_frame_acquire(frame->flags, frame->epoch - 1, frame->d_status, s);
+                launch_untile(map, ctx->rgb_l.as<uint8_t>(), nullptr, ctx->colour_l.as<float>(), frame->rgb, nullptr, frame->rad, s);
+                launch_frame_signal(frame->flags, s);
+                ctx->stats.kernel_launches += 2;
+            } else {
+                launch_untile(map, d_rgb ? ctx->rgb_l.as<uint8_t>() : nullptr, d_ids ? ctx->ids_l.as<int32_t>() : nullptr,
+                              d_rad ? ctx->colour_l.as<float>() : nullptr, d_rgb, d_ids, d_rad, s);
+            }
+            ctx->stats.kernel_launches += 2;
+            G19_CUDA(ctx, cudaGetLastError());
+            if (t_rgb) G19_CUDA(ctx, cudaMemcpyAsync(t_rgb, ctx->rgb_l.p, n * 3, cudaMemcpyDeviceToDevice, s));
+            if (t_rad) G19_CUDA(ctx, cudaMemcpyAsync(t_rad, ctx->colour_l.p, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            if (t_ids) G19_CUDA(ctx, cudaMemcpyAsync(t_ids, ctx->ids_l.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+            ctx->stats.samples = ctx->stats.extend_segments = owned_pixels(map); // as REF mode: one depth-0 sample per owned pixel
+        } else if ((rc == G19_OK || rc == G19_ERR_CANCELLED) && n > 0 && (d_ids || t_ids)) {
+            if (d_ids) {
+                launch_untile(map, nullptr, ctx->ids_l.as<int32_t>(), nullptr, nullptr, d_ids, nullptr, s);
+                ctx->stats.kernel_launches += 1;
+            }
+            if (t_ids) G19_CUDA(ctx, cudaMemcpyAsync(t_ids, ctx->ids_l.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        }
         // a rank without tiles still counts as arrived -- signalled only once the render call has succeeded
         if ((rc == G19_OK || rc == G19_ERR_CANCELLED) && frame && map.n_local_pix == 0) launch_frame_signal(frame->flags, s);
     }

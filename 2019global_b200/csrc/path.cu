@@ -55,6 +55,8 @@ struct BuildPrim {
     Box box;
     float v[3][3]; // triangle corners (float), for the parallelogram merge
     bool tri;
+    int32_t ent[2]; // entity id (push order, as REF mode reports it); a merged parallelogram keeps both triangles' ids:
+                    // ent[0] owns the half b1 >= b2 of the parallelogram frame, ent[1] the half b1 < b2
 };
 
 // world -> (b1, b2, h) rows for the frame (v0; e1, e2): rows of [e1 e2 n]^-1, n = e1 x e2, translation -M v0
@@ -99,7 +101,7 @@ void add_triangle(std::vector<BuildPrim>& out, const HostTri& t, int material, i
     if (len > 0) { nx /= len; ny /= len; nz /= len; }
     p.cold.n[0] = float(nx); p.cold.n[1] = float(ny); p.cold.n[2] = float(nz);
     p.cold.material = material;
-    (void)entity;
+    p.ent[0] = p.ent[1] = entity;
     for (int k = 0; k < 3; ++k) {
         p.box.lo[k] = std::min(v0[k], std::min(v1[k], v2[k]));
         p.box.hi[k] = std::max(v0[k], std::max(v1[k], v2[k]));
@@ -116,7 +118,7 @@ void add_sphere(std::vector<BuildPrim>& out, const HostEntity& e, int material, 
     q[14] = 0.0f; // kind = sphere
     p.tri = false;
     p.cold.material = material;
-    (void)entity;
+    p.ent[0] = p.ent[1] = entity;
     for (int k = 0; k < 3; ++k) {
         p.box.lo[k] = c[k] - e.radius;
         p.box.hi[k] = c[k] + e.radius;
@@ -282,6 +284,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
                             q.box.hi[k] = std::max(A.box.hi[k], B.box.hi[k]);
                         }
                         q.tri = false;
+                        q.ent[0] = A.ent[0]; // A = (s1, s2, u): u sits at (b1, b2) = (1, 0), so A is the half b1 >= b2
+                        q.ent[1] = B.ent[0];
                         merged.push_back(q);
                         ++i;
                         done = true;
@@ -449,9 +453,12 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     }
     std::vector<PrimHot> hot(prims.size());
     std::vector<PrimCold> cold(prims.size());
+    std::vector<int32_t> prim_entity(2 * prims.size());
     for (size_t i = 0; i < prims.size(); ++i) {
         hot[i] = prims[i].hot;
         cold[i] = prims[i].cold;
+        prim_entity[2 * i] = prims[i].ent[0];
+        prim_entity[2 * i + 1] = prims[i].ent[1];
     }
     // Flat scenes: the same records as primitive PAIRS for the packed-FP32 (FFMA2) loops of
     // trace_flat -- planar pair = rows a, b, c with every coefficient a float2 (primitive 2j, 2j+1),
@@ -495,6 +502,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
         (e = up(b.hot, hot.data(), hot.size() * sizeof(PrimHot))) != cudaSuccess ||
         (e = up(b.cold, cold.data(), cold.size() * sizeof(PrimCold))) != cudaSuccess ||
         (e = up(b.pairs, pairs.data(), pairs.size() * sizeof(float))) != cudaSuccess ||
+        (e = up(b.prim_entity, prim_entity.data(), prim_entity.size() * sizeof(int32_t))) != cudaSuccess ||
         (e = up(b.materials, materials.data(), materials.size() * sizeof(MaterialD))) != cudaSuccess ||
         (e = up(b.lights, lights.data(), lights.size() * sizeof(LightD))) != cudaSuccess ||
         (e = cudaStreamSynchronize(stream)) != cudaSuccess) {
@@ -508,6 +516,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     v.cold = static_cast<const PrimCold*>(b.cold.p);
     v.materials = static_cast<const MaterialD*>(b.materials.p);
     v.lights = static_cast<const LightD*>(b.lights.p);
+    v.prim_entity = static_cast<const int32_t*>(b.prim_entity.p);
     v.n_nodes = on_device ? int32_t(dev_n_nodes) : int32_t(nodes.size());
     v.n_index = on_device ? int32_t(dev_n_index) : int32_t(index.size());
     if (on_device) tree_depth = dev_depth;
@@ -526,7 +535,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &w.totals, &w.accum,
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &w.totals, &w.accum,
                            &w.rad_l, &w.rgb_l})
         d->release();
     for (PathLane& l : w.lane) {
@@ -573,14 +582,62 @@ struct ClassClock { // non-blocking CUDA-event bracket around each launch group
 
 int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err) {
     const g19_params& p = a.params;
-    if (p.spp < 1 || p.max_depth < 1 || p.max_depth > kMaxPathDepth) {
-        err = "PATH mode needs spp >= 1 and 1 <= max_depth <= 64";
+    if (p.spp < 1 || p.max_depth < 0 || p.max_depth > kMaxPathDepth || (p.max_depth == 0 && !a.ids_l)) {
+        err = "PATH mode needs spp >= 1 and 0 <= max_depth <= 64";
         return G19_ERR_INVALID;
     }
     cudaStream_t s = a.stream;
     const size_t npix = size_t(a.map.n_local_pix);
     if (npix == 0) return G19_OK;
     path_clear_launch_error();
+    PassArgs pa0{};
+    pa0.scene = b.view;
+    for (int k = 0; k < 3; ++k) {
+        pa0.cam.pos[k] = float(a.cam.pos[k]);
+        pa0.cam.top_left[k] = float(a.cam.top_left[k]);
+        pa0.cam.left[k] = float(a.cam.left[k]);
+        pa0.cam.up[k] = float(a.cam.up[k]);
+    }
+    pa0.map = a.map;
+    pa0.seed = p.seed;
+    pa0.max_depth = p.max_depth;
+    pa0.kind_mask = (b.has_bsdf[G19_BSDF_DIFFUSE] ? 1u : 0u) | (b.has_bsdf[G19_BSDF_MIRROR] ? 2u : 0u) |
+                    (b.has_bsdf[G19_BSDF_GLASS] ? 4u : 0u);
+
+    // stage the breadth-first prefix of the tree and the first primitives (<= ~24 KB)
+    pa0.stage_nodes = std::min(b.view.n_nodes, 1024);
+    // flat scene (one leaf, <= 192 primitives): intersection + shading records and lights staged whole;
+    // a tree scene reaches its primitives through leaf index lists, so only the node prefix is staged
+    const bool flat = b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= 192;
+    pa0.stage_prims = flat ? b.view.n_prims : 0;
+    pa0.stage_cold = flat ? b.view.n_prims : 0;
+    pa0.stage_lights = (pa0.stage_cold > 0 && b.view.n_lights <= 32) ? b.view.n_lights : 0;
+    if (b.view.n_lights > 32) pa0.stage_cold = 0; // not a "flat, fully staged" scene: the generic kernels take it
+    pa0.stack_levels = b.view.tree_depth + 1;
+    // tree scenes: the bounce kernels queue their rays (2 per vertex at most) for trace_kernel
+    pa0.refill = a.tune.refill;
+    // tree walk: leaf tests spread over the whole warp, 8 primitives per ray and round (heightfield 1080p x 32 spp:
+    // sequential 4 per round 107.1 ms, cooperative 4 / 8 / 16 per round 115.4 / 104.9 / 105.4)
+    pa0.coop_leaf = a.tune.coop_leaf;
+    pa0.walk_steps = a.tune.walk_steps;
+    pa0.leaf_batch = a.tune.leaf_batch > 0 ? a.tune.leaf_batch : (pa0.coop_leaf ? 16 : 4); // cooperative: the whole leaf in one go (leaf max 8 / 12 / 16 at batch 16: 97.7 / 96.9 / 97.8 ms)
+    pa0.raygen_occ = a.tune.raygen_occ;
+    const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
+    // primary-hit AOV: the un-jittered ray of every pixel (the reference's ray) through this engine's structures
+    if (a.ids_l) {
+        launch_primary(pa0, a.ids_l, a.points_l, a.normals_l, a.sm_count, s);
+        stats.class_launches[G19_K_EXTEND] += 1;
+        stats.kernel_launches += 1;
+    }
+    if (p.max_depth == 0) { // depth-0 slice: nothing to bounce; the caller shades the primary hits (engine.cu)
+        if (const char* le = path_launch_error()) {
+            err = le;
+            path_clear_launch_error();
+            return G19_ERR_CUDA;
+        }
+        return G19_OK;
+    }
+
     // Pass size. Flat scenes keep dense vertex records in their queues, so a bounce streams exactly
     // the live vertices whatever the pass size: bigger passes only amortise launch tails (measured on
     // B200, ms per 1080p x 64 spp frame at 2 / 4 / 8 / 16 M slots, one pass in flight: Cornell depth 5
@@ -643,42 +700,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         for (int i = 0; i < w.n_events; ++i) PATH_CUDA(cudaEventCreate(&w.events[i]));
     }
     w.used_events = 0;
-
-    PassArgs pa0;
-    pa0.scene = b.view;
-    for (int k = 0; k < 3; ++k) {
-        pa0.cam.pos[k] = float(a.cam.pos[k]);
-        pa0.cam.top_left[k] = float(a.cam.top_left[k]);
-        pa0.cam.left[k] = float(a.cam.left[k]);
-        pa0.cam.up[k] = float(a.cam.up[k]);
-    }
-    pa0.map = a.map;
-    pa0.seed = p.seed;
-    pa0.max_depth = p.max_depth;
-    pa0.kind_mask = (b.has_bsdf[G19_BSDF_DIFFUSE] ? 1u : 0u) | (b.has_bsdf[G19_BSDF_MIRROR] ? 2u : 0u) |
-                    (b.has_bsdf[G19_BSDF_GLASS] ? 4u : 0u);
     pa0.totals = static_cast<unsigned long long*>(w.totals.p);
     pa0.accum = static_cast<float*>(w.accum.p);
-
-    // stage the breadth-first prefix of the tree and the first primitives (<= ~24 KB)
-    pa0.stage_nodes = std::min(b.view.n_nodes, 1024);
-    // flat scene (one leaf, <= 192 primitives): intersection + shading records and lights staged whole;
-    // a tree scene reaches its primitives through leaf index lists, so only the node prefix is staged
-    const bool flat = b.view.n_nodes == 1 && b.view.n_index == b.view.n_prims && b.view.n_prims <= 192;
-    pa0.stage_prims = flat ? b.view.n_prims : 0;
-    pa0.stage_cold = flat ? b.view.n_prims : 0;
-    pa0.stage_lights = (pa0.stage_cold > 0 && b.view.n_lights <= 32) ? b.view.n_lights : 0;
-    if (b.view.n_lights > 32) pa0.stage_cold = 0; // not a "flat, fully staged" scene: the generic kernels take it
-    pa0.stack_levels = b.view.tree_depth + 1;
-    // tree scenes: the bounce kernels queue their rays (2 per vertex at most) for trace_kernel
-    pa0.refill = a.tune.refill;
-    // tree walk: leaf tests spread over the whole warp, 8 primitives per ray and round (heightfield 1080p x 32 spp:
-    // sequential 4 per round 107.1 ms, cooperative 4 / 8 / 16 per round 115.4 / 104.9 / 105.4)
-    pa0.coop_leaf = a.tune.coop_leaf;
-    pa0.walk_steps = a.tune.walk_steps;
-    pa0.leaf_batch = a.tune.leaf_batch > 0 ? a.tune.leaf_batch : (pa0.coop_leaf ? 16 : 4); // cooperative: the whole leaf in one go (leaf max 8 / 12 / 16 at batch 16: 97.7 / 96.9 / 97.8 ms)
-    pa0.raygen_occ = a.tune.raygen_occ;
-    const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
 
     // per-lane buffers
     PassArgs lanes[kMaxLanes];

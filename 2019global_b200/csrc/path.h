@@ -46,6 +46,7 @@ struct PathSceneD {
     int32_t n_par, n_tri;    // flat scenes: primitives sorted parallelograms | triangles | spheres
     const float* pairs;      // flat scenes: the same primitives as PAIRS for the packed-FP32 loops (path.cu build_pairs)
     int32_t pairs_bytes;
+    const int32_t* prim_entity; // 2 per primitive: the entity id REF mode would report (both halves of a merged parallelogram)
     float root_lo[3], root_size[3];
 };
 
@@ -61,7 +62,7 @@ struct DeviceArray {
 };
 
 struct PathSceneBuffers {
-    DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs;
+    DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity;
     PathSceneD view{};
     bool has_bsdf[4] = {false, false, false, false};
 };
@@ -127,6 +128,11 @@ struct PathRenderArgs {
     int32_t* d_ids;
     uint8_t* t_rgb;   // compact local-pixel outputs (nullable)
     float* t_rad;
+    // primary-hit AOV (nullable): entity id / hit point / facing normal of the UN-jittered ray through each pixel
+    // corner -- the ray the reference casts (raytracer.h:41-43) -- by local pixel; points/normals as three FP64 planes
+    int32_t* ids_l = nullptr;
+    double* points_l = nullptr;
+    double* normals_l = nullptr;
     // shared frame (possibly a peer mapping of rank 0's memory): resolve stores straight into it
     uint8_t* frame_rgb = nullptr;
     float* frame_rad = nullptr;
@@ -204,6 +210,7 @@ bool launch_bounce_merged(const PassArgs& a, int bounce, int sm_count, cudaStrea
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s); // tree scenes: after the bounce's shade launches
 bool path_scene_is_flat(const PassArgs& a);
 void launch_accumulate(const PassArgs& a, cudaStream_t s);
+void launch_primary(const PassArgs& a, int32_t* ids_l, double* points_l, double* normals_l, int sm_count, cudaStream_t s);
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s);
 const char* path_launch_error(); // first failed launch/attribute call since the last clear, or nullptr
 void path_clear_launch_error();

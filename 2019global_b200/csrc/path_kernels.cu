@@ -52,6 +52,7 @@
 // breadth-first prefix of the node array and read the rest through L2 with read-only loads.
 #include "path.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
@@ -1533,6 +1534,74 @@ template <bool COOP> __global__ void __launch_bounds__(kThreads, 3) trace_kernel
     if (lane == 0 && lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
 }
 
+// ---- primary-hit AOV ------------------------------------------------------------------------
+// The ray the REFERENCE casts -- through the integer pixel corner, no jitter (raytracer.h:41-43) -- traced
+// through THIS engine's structures (flat pair loops / linear octree, nearest hit): entity id (push order, the
+// numbering REF mode reports), hit point and the normal turned towards the ray (what ImpTriangle::intersect
+// returns, entities.h:239-246; spheres: (p - centre) / r, entities.h:94). Ties PATH mode back to the pinned
+// mode: the ids must equal REF's wherever "last hit wins" coincides with "nearest hit" (tests/test_path_link.py),
+// and with max_depth = 0 these three arrays feed the reference's own shade (ref_shade_kernel), so the default
+// scene closes the loop through the PATH pipeline.
+template <bool ALL>
+__global__ void __launch_bounds__(kThreads, 2) primary_kernel(const PassArgs a, int32_t* __restrict__ ids, double* __restrict__ points,
+                                                              double* __restrict__ normals) {
+    const SceneAccess<ALL> S = stage_scene<ALL>(a);
+    const uint32_t n = uint32_t(a.map.n_local_pix);
+    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t lp = blockIdx.x * kThreads + threadIdx.x; lp - lane < n; lp += stride) { // warp-uniform trip count
+        bool live = false;
+        float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
+        if (lp < n) {
+            const uint32_t lt = lp >> 10, in = lp & 1023u;
+            uint32_t tx;
+            const uint32_t t = lt * uint32_t(a.map.world) + uint32_t(a.map.rank);
+            const uint32_t ty = fast_div(t, uint32_t(a.map.tiles_x), tx);
+            const int x = int(tx * kTile + (in & 31u)), y = int(ty * kTile + (in >> 5));
+            live = x < a.map.w && y < a.map.h;
+            if (live) {
+                const PathCamera& c = a.cam;
+                const float fx = float(x) * 0.0002f, fy = float(y) * 0.0002f;
+                o = f3(c.pos[0], c.pos[1], c.pos[2]);
+                d = normalize(f3(c.top_left[0] - c.left[0] * fx - c.up[0] * fy, c.top_left[1] - c.left[1] * fx - c.up[1] * fy,
+                                 c.top_left[2] - c.left[2] * fx - c.up[2] * fy));
+            }
+        }
+        float t;
+        uint32_t prim;
+        const bool hit = nearest<ALL, false>(S, live, o, d, t, prim); // all 32 lanes walk together
+        if (lp < n) {
+            int32_t id = -1;
+            double px = DBL_MAX, py = DBL_MAX, pz = DBL_MAX, nx = 0, ny = 0, nz = 0; // a miss looks like REF's (ref_visibility_kernel)
+            if (hit) {
+                const float3 p = o + d * t;
+                const float4 r0 = S.hot_row(prim, 0), tag = S.hot_row(prim, 3);
+                float4 c0, c1;
+                S.cold(prim, c0, c1);
+                float3 ng = f3(c0.x, c0.y, c0.z);
+                int half = 0;
+                if (tag.z == 0.0f) {
+                    ng = (p - f3(r0.x, r0.y, r0.z)) * __fdividef(1.0f, r0.w);
+                } else {
+                    if (tag.z > 1.5f) { // merged parallelogram: which of its two triangles (the builder's b1 >= b2 rule)
+                        const float4 r1 = S.hot_row(prim, 1);
+                        const float b1 = fmaf(r0.x, p.x, fmaf(r0.y, p.y, fmaf(r0.z, p.z, r0.w)));
+                        const float b2 = fmaf(r1.x, p.x, fmaf(r1.y, p.y, fmaf(r1.z, p.z, r1.w)));
+                        half = b1 >= b2 ? 0 : 1;
+                    }
+                    if (dot(ng, d) > 0.0f) ng = -ng;
+                }
+                id = a.scene.prim_entity[2 * size_t(prim) + half];
+                px = double(p.x); py = double(p.y); pz = double(p.z);
+                nx = double(ng.x); ny = double(ng.y); nz = double(ng.z);
+            }
+            ids[lp] = id;
+            if (points) { points[lp] = px; points[size_t(n) + lp] = py; points[2 * size_t(n) + lp] = pz; }
+            if (normals) { normals[lp] = nx; normals[size_t(n) + lp] = ny; normals[2 * size_t(n) + lp] = nz; }
+        }
+    }
+}
+
 // ---- accumulate / resolve ---------------------------------------------------------------
 // FLAT: the finished paths' radiance is a float4 per slot, stored once for EVERY slot of the pass by the kernel
 // that ended its path, so it is only read here; otherwise three planes that paths add to and this kernel clears.
@@ -1775,6 +1844,20 @@ void launch_accumulate(const PassArgs& a, cudaStream_t s) {
     if (blocks < 1) blocks = 1;
     cudaError_t e = all_staged(a) ? launch_pdl(accumulate_kernel<true>, blocks, 0, s, a) : launch_pdl(accumulate_kernel<false>, blocks, 0, s, a);
     if (e != cudaSuccess) note_launch_error("accumulate kernel launch", e, 0, blocks);
+}
+
+void launch_primary(const PassArgs& a, int32_t* ids_l, double* points_l, double* normals_l, int sm_count, cudaStream_t s) {
+    if (a.map.n_local_pix == 0) return;
+    PassArgs b = a;
+    b.coop_leaf = 0; // sequential leaf tests: no cooperative result slots needed
+    b.leaf_batch = 4;
+    const size_t smem = path_smem_bytes(b);
+    void (*kernel)(PassArgs, int32_t*, double*, double*) = all_staged(b) ? primary_kernel<true> : primary_kernel<false>;
+    int grid = persistent_grid(kernel, smem, sm_count);
+    grid = std::min(grid, (a.map.n_local_pix + kThreads - 1) / kThreads);
+    kernel<<<grid, kThreads, smem, s>>>(b, ids_l, points_l, normals_l);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) note_launch_error("primary kernel launch", e, smem, grid);
 }
 
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s) {

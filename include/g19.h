@@ -116,7 +116,8 @@ enum g19_builtin_scene {
     G19_SCENE_DEFAULT = 0,     /* main.cpp:24-57 literal (config 1)             */
     G19_SCENE_CORNELL = 1,     /* diffuse Cornell box + 2 spheres + area light  */
     G19_SCENE_CORNELL_GLASS = 2, /* same, one mirror + one glass sphere         */
-    G19_SCENE_HEIGHTFIELD = 3  /* n x n heightfield, 2 n^2 ... triangles        */
+    G19_SCENE_HEIGHTFIELD = 3, /* n x n heightfield, 2 n^2 ... triangles        */
+    G19_SCENE_HEIGHTFIELD_ROOM = 4 /* the same surface as the far wall of a closed room with a ceiling light */
 };
 typedef struct g19_camera {
     double pos[3];     /* Camera::pos      camera.h:12 */
@@ -146,7 +147,11 @@ typedef struct g19_params {
     int32_t width, height; /* RayTracer::run(w,h)  raytracer.h:23 */
     int32_t mode;          /* enum g19_mode */
     int32_t spp;           /* PATH: samples per pixel (REF: ignored, 1) */
-    int32_t max_depth;     /* PATH: max ray segments per camera path    */
+    int32_t max_depth;     /* PATH: max ray segments per camera path. 0 = the DEPTH-0 SLICE: one un-jittered
+                              ray through each pixel corner (raytracer.h:41-43) traced through PATH mode's own
+                              structures (nearest hit), then the reference's direct shade of that hit
+                              (getTextureCoord + Material::blinn_phong_texture, material.h:48-62) and its
+                              truncating store -- what RayTracer::run computes, through the PATH pipeline   */
     uint32_t seed;         /* PATH: RNG key; counter = (pixel, sample, bounce) */
     /* Image-tile sharding: 32x32 tiles, tile t belongs to rank
      * t % world. rank=0, world=1 renders everything. Pixels of other ranks
@@ -198,7 +203,10 @@ int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene);
  * Blocking; HOST pointers, each nullable:
  *   rgb888_out   w*h*3 bytes, row-major, row 0 = top (Image / QImage RGB888,
  *                image.h:9-16)
- *   hit_id_out   w*h int32: REF mode primary-hit entity id, -1 = miss
+ *   hit_id_out   w*h int32: primary-hit entity id (push order), -1 = miss. REF mode: the reference's
+ *                front object (last intersecting candidate). PATH mode: the NEAREST hit of the un-jittered
+ *                ray through the pixel corner -- the same ray, through PATH mode's own structures; equal to
+ *                REF's wherever "last hit" and "nearest hit" coincide (tests/test_path_link.py)
  *   radiance_out w*h*3 float: linear radiance (REF: the shaded colour)       */
 int g19_render(g19_ctx* ctx, const g19_camera* camera, const double light[3],
                const g19_params* params, uint8_t* rgb888_out, int32_t* hit_id_out,

@@ -55,14 +55,105 @@ typedef struct {
 
 typedef struct { v3 v0, e1, e2, n, emission; double area; } p_light;
 
+/* Uniform grid over the primitives' bounding boxes (large scenes only). It is an ACCELERATOR of this oracle's own
+ * brute-force loops, not a restatement of anything: closest() / occluded() through it return exactly what the
+ * loops over every primitive return (tests/test_path_oracle.py checks bit-equality of whole frames), and it shares
+ * nothing with the octree the CUDA tracer walks (a 3-D DDA over equal cells here, a parametric octree walk there). */
+typedef struct {
+    int on;
+    double lo[3], cell[3], inv_cell[3];
+    int res[3];
+    int* start; /* CSR: cell c holds refs[start[c] .. start[c+1]) */
+    int* refs;
+} p_grid;
+
 typedef struct {
     int n_prims, n_lights;
     p_prim* prims;
     p_light* lights;
+    p_grid grid;
 } p_scene;
+
+static int g_accel = 0; /* 0 auto (grid from 512 primitives), 1 brute force, 2 grid always */
+void g19o_path_set_accel(int mode) { g_accel = mode; }
 
 static double clamp01(double v) { return v < 0 ? 0 : (v > 1 ? 1 : v); }
 static v3 fround(d3 p) { return V((double)(float)p.x, (double)(float)p.y, (double)(float)p.z); }
+
+static void prim_box(const p_prim* p, double lo[3], double hi[3]) {
+    if (p->is_tri) {
+        v3 a = p->v0, b = vadd(p->v0, p->e1), c = vadd(p->v0, p->e2);
+        lo[0] = fmin(a.x, fmin(b.x, c.x)); hi[0] = fmax(a.x, fmax(b.x, c.x));
+        lo[1] = fmin(a.y, fmin(b.y, c.y)); hi[1] = fmax(a.y, fmax(b.y, c.y));
+        lo[2] = fmin(a.z, fmin(b.z, c.z)); hi[2] = fmax(a.z, fmax(b.z, c.z));
+    } else {
+        lo[0] = p->c.x - p->r; hi[0] = p->c.x + p->r;
+        lo[1] = p->c.y - p->r; hi[1] = p->c.y + p->r;
+        lo[2] = p->c.z - p->r; hi[2] = p->c.z + p->r;
+    }
+}
+
+static void cell_range(const p_grid* g, const double lo[3], const double hi[3], int c0[3], int c1[3]) {
+    for (int k = 0; k < 3; ++k) { /* boxes are padded by a hundredth of a cell: a hit on a cell wall is listed on both sides */
+        double a = (lo[k] - g->lo[k]) * g->inv_cell[k] - 0.01, b = (hi[k] - g->lo[k]) * g->inv_cell[k] + 0.01;
+        int ia = (int)floor(a), ib = (int)floor(b);
+        c0[k] = ia < 0 ? 0 : (ia >= g->res[k] ? g->res[k] - 1 : ia);
+        c1[k] = ib < 0 ? 0 : (ib >= g->res[k] ? g->res[k] - 1 : ib);
+    }
+}
+
+static void build_grid(p_scene* ps) {
+    p_grid* g = &ps->grid;
+    memset(g, 0, sizeof *g);
+    if (g_accel == 1 || ps->n_prims == 0 || (g_accel == 0 && ps->n_prims < 512)) return;
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int i = 0; i < ps->n_prims; ++i) {
+        double a[3], b[3];
+        prim_box(&ps->prims[i], a, b);
+        for (int k = 0; k < 3; ++k) { lo[k] = fmin(lo[k], a[k]); hi[k] = fmax(hi[k], b[k]); }
+    }
+    double ext[3], vol = 1;
+    for (int k = 0; k < 3; ++k) {
+        double pad = 1e-6 * fmax(1.0, hi[k] - lo[k]);
+        lo[k] -= pad; hi[k] += pad;
+        ext[k] = hi[k] - lo[k];
+        vol *= ext[k];
+    }
+    double s = cbrt(vol / (2.0 * ps->n_prims)); /* about two cells per primitive */
+    size_t cells = 1;
+    for (int k = 0; k < 3; ++k) {
+        int r = (int)ceil(ext[k] / s);
+        g->res[k] = r < 1 ? 1 : (r > 512 ? 512 : r);
+        g->lo[k] = lo[k];
+        g->cell[k] = ext[k] / g->res[k];
+        g->inv_cell[k] = 1.0 / g->cell[k];
+        cells *= (size_t)g->res[k];
+    }
+    g->start = calloc(cells + 1, sizeof(int));
+    for (int pass = 0; pass < 2; ++pass) { /* count, then fill (primitive order is kept inside a cell) */
+        for (int i = 0; i < ps->n_prims; ++i) {
+            double a[3], b[3];
+            int c0[3], c1[3];
+            prim_box(&ps->prims[i], a, b);
+            cell_range(g, a, b, c0, c1);
+            for (int z = c0[2]; z <= c1[2]; ++z)
+                for (int y = c0[1]; y <= c1[1]; ++y)
+                    for (int x = c0[0]; x <= c1[0]; ++x) {
+                        size_t c = ((size_t)z * g->res[1] + y) * g->res[0] + x;
+                        if (pass == 0) g->start[c + 1]++;
+                        else g->refs[g->start[c]++] = i;
+                    }
+        }
+        if (pass == 0) {
+            for (size_t c = 0; c < cells; ++c) g->start[c + 1] += g->start[c];
+            g->refs = malloc(((size_t)g->start[cells] + 1) * sizeof(int));
+        } else {
+            for (size_t c = cells; c > 0; --c) g->start[c] = g->start[c - 1]; /* undo the fill cursor shift */
+            g->start[0] = 0;
+        }
+    }
+    g->on = 1;
+}
 
 static p_scene* build_prims(const o_scene* s) {
     p_scene* ps = calloc(1, sizeof *ps);
@@ -111,10 +202,11 @@ static p_scene* build_prims(const o_scene* s) {
             }
         }
     }
+    build_grid(ps);
     return ps;
 }
 
-static void free_prims(p_scene* ps) { free(ps->prims); free(ps->lights); free(ps); }
+static void free_prims(p_scene* ps) { free(ps->prims); free(ps->lights); free(ps->grid.start); free(ps->grid.refs); free(ps); }
 
 /* Philox4x32-10, key = (seed, "2019") */
 static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t out[4]) {
@@ -156,9 +248,81 @@ static double hit_prim(const p_prim* p, v3 o, v3 d, double tmin, double tmax) {
     return -1;
 }
 
+/* 3-D DDA (Amanatides & Woo 1987) over the grid. visit(cell) is inlined in the two callers below. */
+typedef struct {
+    int c[3], step[3], out[3];
+    double tmax[3], tdelta[3], t;
+} dda;
+
+static int dda_init(const p_grid* g, v3 o, v3 d, double tlimit, dda* w) {
+    double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    double t0 = 0.0, t1 = tlimit;
+    for (int k = 0; k < 3; ++k) { /* clip the ray to the grid box */
+        double hi = g->lo[k] + g->cell[k] * g->res[k];
+        if (dd[k] == 0.0) {
+            if (oo[k] < g->lo[k] || oo[k] > hi) return 0;
+        } else {
+            double a = (g->lo[k] - oo[k]) / dd[k], b = (hi - oo[k]) / dd[k];
+            if (a > b) { double q = a; a = b; b = q; }
+            if (a > t0) t0 = a;
+            if (b < t1) t1 = b;
+        }
+    }
+    if (t0 > t1) return 0;
+    w->t = t0;
+    for (int k = 0; k < 3; ++k) {
+        double pk = oo[k] + t0 * dd[k];
+        int c = (int)floor((pk - g->lo[k]) * g->inv_cell[k]);
+        c = c < 0 ? 0 : (c >= g->res[k] ? g->res[k] - 1 : c);
+        w->c[k] = c;
+        if (dd[k] > 0) {
+            w->step[k] = 1; w->out[k] = g->res[k];
+            w->tdelta[k] = g->cell[k] / dd[k];
+            w->tmax[k] = (g->lo[k] + (c + 1) * g->cell[k] - oo[k]) / dd[k];
+        } else if (dd[k] < 0) {
+            w->step[k] = -1; w->out[k] = -1;
+            w->tdelta[k] = -g->cell[k] / dd[k];
+            w->tmax[k] = (g->lo[k] + c * g->cell[k] - oo[k]) / dd[k];
+        } else {
+            w->step[k] = 0; w->out[k] = -1;
+            w->tdelta[k] = DBL_MAX; w->tmax[k] = DBL_MAX;
+        }
+    }
+    return 1;
+}
+/* leaves the current cell; returns 0 when the ray leaves the grid. On return w->t = parameter of the new cell's entry. */
+static int dda_next(dda* w) {
+    int k = (w->tmax[0] <= w->tmax[1]) ? (w->tmax[0] <= w->tmax[2] ? 0 : 2) : (w->tmax[1] <= w->tmax[2] ? 1 : 2);
+    w->t = w->tmax[k];
+    w->c[k] += w->step[k];
+    if (w->c[k] == w->out[k]) return 0;
+    w->tmax[k] += w->tdelta[k];
+    return 1;
+}
+static double dda_exit(const dda* w) { return fmin(w->tmax[0], fmin(w->tmax[1], w->tmax[2])); }
+
 static int closest(const p_scene* s, v3 o, v3 d, double* t_out) {
     double best = DBL_MAX;
     int bi = -1;
+    if (s->grid.on) {
+        const p_grid* g = &s->grid;
+        dda w;
+        if (dda_init(g, o, d, DBL_MAX, &w)) {
+            const double slack = 0.02 * fmin(g->cell[0], fmin(g->cell[1], g->cell[2])); /* lists are padded by 0.01 cell */
+            do {
+                size_t c = ((size_t)w.c[2] * g->res[1] + w.c[1]) * g->res[0] + w.c[0];
+                for (int r = g->start[c]; r < g->start[c + 1]; ++r) {
+                    int i = g->refs[r];
+                    double t = hit_prim(&s->prims[i], o, d, 0.0, DBL_MAX);
+                    /* the brute-force loop keeps the FIRST primitive among equal t: lowest index */
+                    if (t >= 0 && (t < best || (t == best && i < bi))) { best = t; bi = i; }
+                }
+                if (best < dda_exit(&w) - slack) break; /* nothing in a later cell can be nearer */
+            } while (dda_next(&w));
+        }
+        *t_out = best;
+        return bi;
+    }
     for (int i = 0; i < s->n_prims; ++i) {
         double t = hit_prim(&s->prims[i], o, d, 0.0, best);
         if (t >= 0) { best = t; bi = i; }
@@ -167,6 +331,19 @@ static int closest(const p_scene* s, v3 o, v3 d, double* t_out) {
     return bi;
 }
 static int occluded(const p_scene* s, v3 o, v3 d, double tmax) {
+    if (s->grid.on) {
+        const p_grid* g = &s->grid;
+        dda w;
+        if (!dda_init(g, o, d, tmax, &w)) return 0;
+        const double slack = 0.02 * fmin(g->cell[0], fmin(g->cell[1], g->cell[2]));
+        do {
+            if (w.t > tmax + slack) break;
+            size_t c = ((size_t)w.c[2] * g->res[1] + w.c[1]) * g->res[0] + w.c[0];
+            for (int r = g->start[c]; r < g->start[c + 1]; ++r)
+                if (hit_prim(&s->prims[g->refs[r]], o, d, 0.0, tmax) >= 0) return 1;
+        } while (dda_next(&w));
+        return 0;
+    }
     for (int i = 0; i < s->n_prims; ++i)
         if (hit_prim(&s->prims[i], o, d, 0.0, tmax) >= 0) return 1;
     return 0;
@@ -293,29 +470,49 @@ static void* rows(void* arg) {
     return NULL;
 }
 
+static void camera_basis(const g19_camera* cam, int w, v3* cpos, v3* up, v3* left, v3* top_left);
+
+/* Primary-hit AOV: the reference's own ray (integer pixel corner, no jitter, raytracer.h:41-43) against every
+ * PATH primitive, nearest hit with t > 0. ids = entity (push order), points / normals row-major AoS triples;
+ * the normal is turned towards the ray for triangles (entities.h:239-246) and is (p - c) / r for spheres
+ * (entities.h:94); a miss is id -1, point DBL_MAX, normal 0 like ref_restate.c's g19o_trace. */
+int g19o_path_primary(void* scene, const g19_camera* cam, int w, int h, int32_t* ids, double* points, double* normals) {
+    const o_scene* os = scene;
+    p_scene* ps = build_prims(os);
+    v3 cpos, up, left, top_left;
+    camera_basis(cam, w, &cpos, &up, &left, &top_left);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            size_t i = (size_t)y * (size_t)w + (size_t)x;
+            double fx = (double)x * 0.0002, fy = (double)y * 0.0002;
+            v3 d = vnorm(vsub(vsub(top_left, vmul(left, fx)), vmul(up, fy)));
+            double t;
+            int pi = closest(ps, cpos, d, &t);
+            v3 p = V(DBL_MAX, DBL_MAX, DBL_MAX), n = V(0, 0, 0);
+            int id = -1;
+            if (pi >= 0) {
+                const p_prim* pr = &ps->prims[pi];
+                id = pr->entity;
+                p = vadd(cpos, vmul(d, t));
+                if (pr->is_tri) n = vdot(pr->n, d) > 0 ? vmul(pr->n, -1) : pr->n;
+                else n = vmul(vsub(p, pr->c), 1.0 / pr->r);
+            }
+            if (ids) ids[i] = id;
+            if (points) { points[3 * i] = p.x; points[3 * i + 1] = p.y; points[3 * i + 2] = p.z; }
+            if (normals) { normals[3 * i] = n.x; normals[3 * i + 1] = n.y; normals[3 * i + 2] = n.z; }
+        }
+    free_prims(ps);
+    return 0;
+}
+
 /* Renders the window [x0,x1) x [y0,y1) of a w x h frame; pixels outside are left
  * untouched. segs[0] = extend segments, segs[1] = shadow segments. */
 int g19o_path_render(void* scene, const g19_camera* cam, int w, int h, int spp, int max_depth, uint32_t seed, int x0,
                      int y0, int x1, int y1, float* radiance, uint64_t* segs, int nthreads) {
     const o_scene* os = scene;
     p_scene* ps = build_prims(os);
-    /* camera basis: same expressions as ref_restate.c g19o_trace (raytracer.h:26-30) */
-    v3 cpos = V(cam->pos[0], cam->pos[1], cam->pos[2]);
-    v3 up = V(0, 0, 1.0);
-    v3 fwd = vsub(V(cam->look_at[0], cam->look_at[1], cam->look_at[2]), cpos);
-    {
-        double tx = fwd.x * fwd.x, ty = fwd.y * fwd.y, tz = fwd.z * fwd.z;
-        fwd = vmul(fwd, 1.0 / sqrt(tx + ty + tz));
-    }
-    v3 left = V(up.y * fwd.z - fwd.y * up.z, up.z * fwd.x - fwd.z * up.x, up.x * fwd.y - fwd.x * up.y);
-    {
-        double tx = left.x * left.x, ty = left.y * left.y, tz = left.z * left.z;
-        left = vmul(left, 1.0 / sqrt(tx + ty + tz));
-    }
-    v3 t = vadd(cpos, V(cam->focal * fwd.x, cam->focal * fwd.y, cam->focal * fwd.z));
-    t = vadd(t, vmul(vmul(vmul(left, (double)w), 0.5), 0.0002));
-    t = vadd(t, vmul(vmul(vmul(up, (double)w), 0.5), 0.0002));
-    v3 top_left = vsub(t, cpos);
+    v3 cpos, up, left, top_left;
+    camera_basis(cam, w, &cpos, &up, &left, &top_left);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     static job jobs[256];
@@ -335,4 +532,27 @@ int g19o_path_render(void* scene, const g19_camera* cam, int w, int h, int spp, 
     }
     free_prims(ps);
     return 0;
+}
+
+/* camera basis: same expressions as ref_restate.c g19o_trace (raytracer.h:26-30) */
+static void camera_basis(const g19_camera* cam, int w, v3* cpos_out, v3* up_out, v3* left_out, v3* top_left_out) {
+    v3 cpos = V(cam->pos[0], cam->pos[1], cam->pos[2]);
+    v3 up = V(0, 0, 1.0);
+    v3 fwd = vsub(V(cam->look_at[0], cam->look_at[1], cam->look_at[2]), cpos);
+    {
+        double tx = fwd.x * fwd.x, ty = fwd.y * fwd.y, tz = fwd.z * fwd.z;
+        fwd = vmul(fwd, 1.0 / sqrt(tx + ty + tz));
+    }
+    v3 left = V(up.y * fwd.z - fwd.y * up.z, up.z * fwd.x - fwd.z * up.x, up.x * fwd.y - fwd.x * up.y);
+    {
+        double tx = left.x * left.x, ty = left.y * left.y, tz = left.z * left.z;
+        left = vmul(left, 1.0 / sqrt(tx + ty + tz));
+    }
+    v3 t = vadd(cpos, V(cam->focal * fwd.x, cam->focal * fwd.y, cam->focal * fwd.z));
+    t = vadd(t, vmul(vmul(vmul(left, (double)w), 0.5), 0.0002));
+    t = vadd(t, vmul(vmul(vmul(up, (double)w), 0.5), 0.0002));
+    *cpos_out = cpos;
+    *up_out = up;
+    *left_out = left;
+    *top_left_out = vsub(t, cpos);
 }

@@ -769,6 +769,38 @@ int g19o_trace(void* h, const g19_camera* cam, const double light[3], int w, int
     return 0;
 }
 
+/* raytracer.h:76-82 on its own: getTextureCoord + blinn_phong_texture + setPixel for pixels whose front object
+ * (ids, points, normals: row-major, AoS triples) was found elsewhere -- tests feed it the PATH oracle's primary
+ * hits to check that PATH mode's depth-0 slice reduces to the reference's shade. */
+int g19o_shade_pixels(void* h, const g19_camera* cam, const double light[3], int w, int hgt, const int32_t* ids,
+                      const double* points, const double* normals, uint8_t* rgb) {
+    const o_scene* s = h;
+    d3 cpos = P(cam->pos);
+    d3 up = D3(0, 0, 1.0);
+    d3 forward = normalize(sub(P(cam->look_at), cpos));
+    d3 left = normalize(cross(up, forward));
+    d3 t = add(cpos, smul(cam->focal, forward));
+    t = add(t, muls(muls(muls(left, (double)w), 0.5), 0.0002));
+    t = add(t, muls(muls(muls(up, (double)w), 0.5), 0.0002));
+    d3 top_left = sub(t, cpos);
+    for (int y = 0; y < hgt; ++y)
+        for (int x = 0; x < w; ++x) {
+            size_t i = (size_t)y * (size_t)w + (size_t)x;
+            d3 c = D3(0, 0, 0);
+            int front = ids[i];
+            if (front >= 0 && front < s->n_ent) {
+                d3 dir = normalize(sub(sub(top_left, muls(muls(left, (double)x), 0.0002)), muls(muls(up, (double)y), 0.0002)));
+                d3 ip = D3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+                d3 nn = D3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+                int u, v;
+                texcoord(&s->ent[front], ip, &u, &v);
+                c = shade(s->ent[front].color, dir, P(light), ip, nn, u, v);
+            }
+            quantise(c, rgb + 3 * i);
+        }
+    return 0;
+}
+
 /* whole-frame convenience with the same signature as g19ref_render */
 int g19o_render(void* h, const g19_camera* cam, const double light[3], int w, int hgt, uint8_t* rgb) {
     return g19o_trace(h, cam, light, w, hgt, 0, hgt, NULL, NULL, NULL, rgb, 1);

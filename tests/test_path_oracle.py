@@ -53,3 +53,38 @@ def test_energy_is_bounded(g19, abi, oracle):
     sc, cam, _ = g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h)
     rad, _ = binding.path_render(mirror(oracle, sc), cam, w, h, 16, 8, seed=2)
     assert np.isfinite(rad).all() and rad.min() >= 0 and rad.max() <= 17.0 * 1.0001
+
+
+def test_grid_accelerator_is_bit_identical_to_brute_force(g19, abi, oracle):
+    """Large scenes (bench.py's C4 windows) go through a uniform grid inside the oracle; it must return exactly what
+    the loop over every primitive returns -- radiance, segment counts and the primary-hit AOV, bit for bit."""
+    from util import zoo
+    cases = [(g19.Octree.builtin(abi.SCENE_CORNELL_GLASS, w=64, h=36), 64, 36, 8, 9),
+             (g19.Octree.builtin(abi.SCENE_HEIGHTFIELD, n=40, w=64, h=36), 64, 36, 4, 5),
+             (g19.Octree.builtin(abi.SCENE_HEIGHTFIELD_ROOM, n=40, w=64, h=36), 64, 36, 4, 5),
+             ((zoo(g19), g19.Camera((-10, 0, 0), (1, 0, 0), 0.02), None), 48, 48, 4, 4)]
+    try:
+        for (sc, cam, _), w, h, spp, depth in cases:
+            chk = mirror(oracle, sc)
+            out = []
+            for mode in (1, 2):  # brute force, grid always
+                oracle.lib.g19o_path_set_accel(mode)
+                rad, segs = binding.path_render(chk, cam, w, h, spp, depth, seed=3, threads=4)
+                ids, pts, nrm = binding.path_primary(chk, cam, w, h)
+                out.append((rad.tobytes(), segs, ids.tobytes(), pts.tobytes(), nrm.tobytes()))
+            assert out[0] == out[1]
+    finally:
+        oracle.lib.g19o_path_set_accel(0)
+
+
+def test_oracle_scene_generator_equals_the_products(g19, abi):
+    """bench.py's CPU legs build their scenes with oracle/oracle_scenes.c (so the reference arm never loads the
+    product library): every descriptor, the camera and the light must equal the product generator's."""
+    for which, n, w, h in ((abi.SCENE_DEFAULT, 0, 500, 500), (abi.SCENE_CORNELL, 0, 1920, 1080), (abi.SCENE_CORNELL_GLASS, 0, 640, 360),
+                           (abi.SCENE_HEIGHTFIELD, 24, 320, 200), (abi.SCENE_HEIGHTFIELD_ROOM, 24, 3840, 2160)):
+        sc, cam, light = g19.Octree.builtin(which, n=n, w=w, h=h)
+        descs, cam2, light2 = binding.builtin_descs(which, n, w, h)
+        mine = sc.entities()
+        assert len(mine) == len(descs)
+        assert all(bytes(a) == bytes(b) for a, b in zip(mine, descs))
+        assert bytes(cam) == bytes(cam2) and tuple(light) == tuple(light2)
