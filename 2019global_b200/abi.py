@@ -10,6 +10,8 @@ KIND_NAMES = ["ImpSphere", "ImpTriangle", "ExpRectangle", "ExpBox", "ExpSphere",
 BSDF_DIFFUSE, BSDF_MIRROR, BSDF_GLASS, BSDF_EMITTER = range(4)
 # enum g19_mode
 MODE_REF, MODE_PATH = 0, 1
+# enum g19_shapes
+SHAPES_REF, SHAPES_FIXED = 0, 1
 # enum g19_builtin_scene
 SCENE_DEFAULT, SCENE_CORNELL, SCENE_CORNELL_GLASS, SCENE_HEIGHTFIELD, SCENE_HEIGHTFIELD_ROOM = range(5)
 # status

@@ -29,6 +29,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-ccbin", "/usr/bin/g++", "-I", os.p
 UNITS = [
     ("scene.cpp", []),
     ("builtin_scenes.cpp", []),
+    ("fixed_shapes.cpp", []),
     ("ref_kernels.cu", ["-fmad=false", "-Xptxas", "-v"]),
     ("path_kernels.cu", ["--use_fast_math", "-Xptxas", "-v"]),
     ("frame_kernels.cu", []),

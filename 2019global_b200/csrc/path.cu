@@ -211,14 +211,19 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
             add_sphere(prims, e, mi, int(ei));
             tag(prims.back());
         } else {
-            for (size_t t = size_t(e.first_tested); t < e.tris.size(); ++t) {
-                add_triangle(prims, e.tris[t], mi, int(ei));
+            // the triangles REF mode tests (from `first_tested`: ExpSphere skips its first one) -- or, with
+            // G19_SHAPES_FIXED, the triangles the constructor meant to build (fixed_shapes.cpp)
+            std::vector<HostTri> fixed;
+            const bool use_fixed = scene.shapes == G19_SHAPES_FIXED && fixed_triangles(e.desc, fixed);
+            const std::vector<HostTri>& tris = use_fixed ? fixed : e.tris;
+            for (size_t t = use_fixed ? 0 : size_t(e.first_tested); t < tris.size(); ++t) {
+                add_triangle(prims, tris[t], mi, int(ei));
                 tag(prims.back());
                 if (m.bsdf == G19_BSDF_EMITTER) {
                     const BuildPrim& p = prims.back();
                     LightD l;
                     std::memset(&l, 0, sizeof l);
-                    const HostTri& ht = e.tris[t];
+                    const HostTri& ht = tris[t];
                     const float fv0[3] = {float(ht.p1.x), float(ht.p1.y), float(ht.p1.z)};
                     const float fv1[3] = {float(ht.p2.x), float(ht.p2.y), float(ht.p2.z)};
                     const float fv2[3] = {float(ht.p3.x), float(ht.p3.y), float(ht.p3.z)};

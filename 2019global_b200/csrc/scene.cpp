@@ -360,6 +360,12 @@ int g19_scene_add_entity(g19_scene* s, const g19_entity_desc* d, int32_t* out_in
 
 int g19_scene_entity_count(const g19_scene* s) { return s ? int(s->ents.size()) : 0; }
 
+int g19_scene_set_shapes(g19_scene* s, int shapes) {
+    if (!s || (shapes != G19_SHAPES_REF && shapes != G19_SHAPES_FIXED)) return G19_ERR_INVALID;
+    s->shapes = shapes;
+    return G19_OK;
+}
+
 int g19_scene_get_entity(const g19_scene* s, int32_t i, g19_entity_desc* out) {
     if (!s || !out || i < 0 || size_t(i) >= s->ents.size()) return G19_ERR_INVALID;
     *out = s->ents[i].desc;

@@ -59,6 +59,7 @@ struct HostNode {
 } // namespace g19
 
 struct g19_scene {
+    int shapes = 0; // enum g19_shapes: which triangles PATH mode extracts from the composite entities
     g19::V3 rmin, rmax;
     std::vector<g19::HostEntity> ents;
     std::vector<g19::HostNode> nodes; // nodes[0] = root
@@ -71,6 +72,10 @@ bool build_entity(const g19_entity_desc& d, HostEntity& out);
 // Octree::push_back (octree.h:20-30). Returns false when rejected by the root test.
 bool push_back(g19_scene& s, int32_t entity);
 int max_depth(const g19_scene& s);
+
+// G19_SHAPES_FIXED (fixed_shapes.cpp): the triangles the entity's constructor meant to build; false = the
+// reference's own triangles are right (or the entity has none) and PATH mode keeps them.
+bool fixed_triangles(const g19_entity_desc& d, std::vector<HostTri>& out);
 
 // Procedural scenes of BASELINE.json `configs`.
 int make_builtin(int which, int n, int w, int h, g19_scene** out, g19_camera* cam, double light[3]);

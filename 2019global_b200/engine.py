@@ -33,7 +33,7 @@ EXPORTS = [
     "g19_render_to_frame", "g19_frame_wait", "g19_frame_release", "g19_frame_timeouts",
     "g19_frame_read", "g19_render_progressive", "g19_render_tiles_device", "g19_untile_device", "g19_tile_pixels",
     "g19_probe_texcoord", "g19_probe_shade", "g19_probe_path_tree", "g19_entity_bbox", "g19_entity_triangles",
-    "g19_frame_status", "g19_tune",
+    "g19_frame_status", "g19_tune", "g19_scene_set_shapes",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
         L.g19_scene_add_entity.argtypes = [C.c_void_p, C.POINTER(abi.EntityDesc), C.POINTER(C.c_int32)]
         L.g19_scene_get_entity.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.EntityDesc)]
         L.g19_scene_entity_count.argtypes = [C.c_void_p]
+        L.g19_scene_set_shapes.argtypes = [C.c_void_p, C.c_int]
         L.g19_scene_entity_bbox.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.g19_scene_entity_triangles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int]
         L.g19_upload_scene.argtypes = [C.c_void_p, C.c_void_p]
@@ -184,6 +185,13 @@ class Octree:
         if rc not in (abi.OK, abi.ERR_REJECTED):
             raise G19Error(rc, "g19_scene_add_entity")
         return idx.value, rc == abi.OK
+
+    def set_shapes(self, fixed):
+        """g19_scene_set_shapes: PATH mode traces the composites as their constructors meant them (True) or the
+        reference's own triangles, bugs included (False, the default). REF mode is unaffected."""
+        rc = self._L.g19_scene_set_shapes(self.h, abi.SHAPES_FIXED if fixed else abi.SHAPES_REF)
+        if rc != abi.OK:
+            raise G19Error(rc, "g19_scene_set_shapes")
 
     def __len__(self):
         return self._L.g19_scene_entity_count(self.h)

@@ -106,6 +106,15 @@ int g19_scene_entity_bbox(const g19_scene* scene, int32_t index, double out_min_
  * each. Returns the count; writes at most max_tris. IMP_SPHERE returns 0.   */
 int g19_scene_entity_triangles(const g19_scene* scene, int32_t index, double* out, int max_tris);
 
+/* Which triangles G19_MODE_PATH extracts from the composite entities (applies at the next g19_upload_scene;
+ * G19_MODE_REF always traces the reference's own, bugs included):
+ *   G19_SHAPES_REF    what the reference's constructors build -- ExpRectangle's p4 = -p3 (entities.h:319),
+ *                     ExpSphere tessellated around -pos and without its first triangle (entities.h:475-482,520),
+ *                     ExpQuad's doubled pos.z (entities.h:586), ExpCone's hard-coded direction (entities.h:825)
+ *   G19_SHAPES_FIXED  what they were meant to build (csrc/fixed_shapes.cpp), behind the same entity ids          */
+enum g19_shapes { G19_SHAPES_REF = 0, G19_SHAPES_FIXED = 1 };
+int g19_scene_set_shapes(g19_scene* scene, int shapes);
+
 /* Stateless forms of the two calls above, for one entity outside any scene
  * (what an Entity subclass needs to fill its public members at construction). */
 int g19_entity_bbox(const g19_entity_desc* desc, double out_min_max[6]);

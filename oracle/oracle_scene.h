@@ -48,6 +48,7 @@ typedef struct {
     o_node* root;
     int n_ent, cap;
     o_entity* ent;
+    int shapes; /* enum g19_shapes: which triangles the PATH oracle extracts from composites (REF restatement: unaffected) */
 } o_scene;
 
 #endif

@@ -155,10 +155,107 @@ static void build_grid(p_scene* ps) {
     g->on = 1;
 }
 
+/* G19_SHAPES_FIXED: the triangles the composite constructors MEANT to build (see the table in
+ * 2019global_b200/csrc/fixed_shapes.cpp; reference include/entities.h:308-324, 379-406, 457-506, 579-590, 821-899).
+ * Written against the reference's constructor arguments, in the same operation order as the product's generator so
+ * that both round to the same float vertices. Returns the number of triangles (9 doubles each) or -1 when the
+ * reference's own triangles are right. */
+static int fixed_tris(const g19_entity_desc* d, double* out /* up to 200 x 9 */) {
+    const double kPi = 3.14159265358979323846;
+    const double px = d->p[0], py = d->p[1], pz = d->p[2];
+    int n = 0;
+#define TRI(ax, ay, az, bx, by, bz, cx, cy, cz)                                                  \
+    do {                                                                                         \
+        double* t_ = out + 9 * n++;                                                              \
+        t_[0] = ax; t_[1] = ay; t_[2] = az; t_[3] = bx; t_[4] = by; t_[5] = bz; t_[6] = cx; t_[7] = cy; t_[8] = cz; \
+    } while (0)
+#define RECT(ax, ay, az, bx, by, bz, cx, cy, cz)                                                 \
+    do {                                                                                         \
+        TRI(ax, ay, az, bx, by, bz, cx, cy, cz);                                                 \
+        TRI(ax, ay, az, bx, by, bz, ((ax) + (bx)) - (cx), ((ay) + (by)) - (cy), ((az) + (bz)) - (cz)); \
+    } while (0)
+    switch (d->kind) {
+    case G19_EXP_RECTANGLE:
+        RECT(px, py, pz, d->p[3], d->p[4], d->p[5], d->p[6], d->p[7], d->p[8]);
+        return n;
+    case G19_EXP_BOX: {
+        const double x0 = px, y0 = py, z0 = pz, x1 = d->p[3], y1 = d->p[4], z1 = d->p[5];
+        RECT(x0, y0, z0, x1, y1, z0, x1, y0, z0);
+        RECT(x0, y0, z1, x1, y1, z1, x1, y0, z1);
+        RECT(x0, y0, z0, x1, y0, z1, x1, y0, z0);
+        RECT(x0, y1, z0, x1, y1, z1, x1, y1, z0);
+        RECT(x0, y0, z0, x0, y1, z1, x0, y1, z0);
+        RECT(x1, y0, z0, x1, y1, z1, x1, y1, z0);
+        return n;
+    }
+    case G19_EXP_SPHERE: {
+        const double r = (double)d->f[0];
+        enum { STACKS = 10, SECTORS = 10 };
+        double v[(STACKS + 1) * (SECTORS + 1)][3];
+        int k = 0;
+        for (int i = 0; i <= STACKS; ++i) {
+            const double phi = kPi / 2 - (double)i * (kPi / STACKS);
+            const double ring = r * cos(phi), z = r * sin(phi);
+            for (int j = 0; j <= SECTORS; ++j, ++k) {
+                const double theta = (double)j * (2 * kPi / SECTORS);
+                v[k][0] = px + ring * cos(theta); v[k][1] = py + ring * sin(theta); v[k][2] = pz + z;
+            }
+        }
+        for (int i = 0; i < STACKS; ++i) {
+            int k1 = i * (SECTORS + 1), k2 = k1 + SECTORS + 1;
+            for (int j = 0; j < SECTORS; ++j, ++k1, ++k2) {
+                if (i != 0) TRI(v[k1][0], v[k1][1], v[k1][2], v[k2][0], v[k2][1], v[k2][2], v[k1 + 1][0], v[k1 + 1][1], v[k1 + 1][2]);
+                if (i != STACKS - 1) TRI(v[k1 + 1][0], v[k1 + 1][1], v[k1 + 1][2], v[k2][0], v[k2][1], v[k2][2], v[k2 + 1][0], v[k2 + 1][1], v[k2 + 1][2]);
+            }
+        }
+        return n;
+    }
+    case G19_EXP_QUAD: {
+        const double hw = (double)d->f[0] / 2, hl = (double)d->f[1] / 2, a = (double)d->f[2];
+        const double c = cos(a), s = sin(a);
+        const double v0[3] = {px + hw * c, py + hl, pz + hw * s}, v1[3] = {px - hw * c, py + hl, pz - hw * s};
+        const double v2[3] = {px + hw * c, py - hl, pz + hw * s}, v3[3] = {px - hw * c, py - hl, pz - hw * s};
+        TRI(v1[0], v1[1], v1[2], v2[0], v2[1], v2[2], v0[0], v0[1], v0[2]);
+        TRI(v1[0], v1[1], v1[2], v3[0], v3[1], v3[2], v2[0], v2[1], v2[2]);
+        return n;
+    }
+    case G19_EXP_CONE: {
+        const double h = (double)d->f[0], r = (double)d->f[1];
+        v3 axis = V(d->p[3], d->p[4], d->p[5]);
+        double l = sqrt(axis.x * axis.x + axis.y * axis.y + axis.z * axis.z);
+        if (l > 0) axis = vmul(axis, 1.0 / l);
+        if (axis.x == 0 && axis.y == 0 && axis.z == 0) axis = V(0, 0, -1);
+        const v3 centre = vadd(V(px, py, pz), vmul(axis, h));
+        const v3 helper = fabs(axis.x) < 0.9 ? V(1, 0, 0) : V(0, 1, 0);
+        v3 u = vcross(axis, helper);
+        l = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
+        if (l > 0) u = vmul(u, 1.0 / l);
+        const v3 w = vcross(axis, u);
+        enum { N = 50 };
+        double rim[N + 1][3];
+        for (int i = 0; i <= N; ++i) {
+            const double ang = (double)i * (2 * kPi / N);
+            const double cu = r * cos(ang), cw = r * sin(ang);
+            rim[i][0] = centre.x + cu * u.x + cw * w.x; rim[i][1] = centre.y + cu * u.y + cw * w.y; rim[i][2] = centre.z + cu * u.z + cw * w.z;
+        }
+        for (int i = 0; i < N; ++i) {
+            TRI(px, py, pz, rim[i][0], rim[i][1], rim[i][2], rim[i + 1][0], rim[i + 1][1], rim[i + 1][2]);
+            TRI(centre.x, centre.y, centre.z, rim[i][0], rim[i][1], rim[i][2], rim[i + 1][0], rim[i + 1][1], rim[i + 1][2]);
+        }
+        return n;
+    }
+    default: return -1;
+    }
+#undef TRI
+#undef RECT
+}
+
+void g19o_scene_set_shapes(void* h, int shapes) { ((o_scene*)h)->shapes = shapes; }
+
 static p_scene* build_prims(const o_scene* s) {
     p_scene* ps = calloc(1, sizeof *ps);
     int cap = 0;
-    for (int i = 0; i < s->n_ent; ++i) cap += s->ent[i].ntri + 1;
+    for (int i = 0; i < s->n_ent; ++i) cap += (s->ent[i].ntri > 200 ? s->ent[i].ntri : 200) + 1;
     ps->prims = calloc((size_t)cap + 1, sizeof(p_prim));
     ps->lights = calloc((size_t)cap + 1, sizeof(p_light));
     for (int i = 0; i < s->n_ent; ++i) {
@@ -180,14 +277,24 @@ static p_scene* build_prims(const o_scene* s) {
             continue;
         }
         int from = (e->kind == G19_EXP_SPHERE) ? 1 : 0; /* the triangles REF mode tests */
-        for (int t = from; t < e->ntri; ++t) {
+        double fx[200 * 9];
+        int ntri = e->ntri;
+        const int nfixed = s->shapes == G19_SHAPES_FIXED ? fixed_tris(&e->desc, fx) : -1;
+        if (nfixed >= 0) { from = 0; ntri = nfixed; }
+        for (int t = from; t < ntri; ++t) {
             p_prim p = base;
             p.is_tri = 1;
-            v3 a = fround(e->tris[t].p1), b = fround(e->tris[t].p2), c = fround(e->tris[t].p3);
+            d3 q1, q2, q3;
+            if (nfixed >= 0) {
+                const double* f = fx + 9 * t;
+                q1 = (d3){f[0], f[1], f[2]}; q2 = (d3){f[3], f[4], f[5]}; q3 = (d3){f[6], f[7], f[8]};
+            } else {
+                q1 = e->tris[t].p1; q2 = e->tris[t].p2; q3 = e->tris[t].p3;
+            }
+            v3 a = fround(q1), b = fround(q2), c = fround(q3);
             p.v0 = a;
             p.e1 = V((double)(float)(b.x - a.x), (double)(float)(b.y - a.y), (double)(float)(b.z - a.z));
             p.e2 = V((double)(float)(c.x - a.x), (double)(float)(c.y - a.y), (double)(float)(c.z - a.z));
-            d3 q1 = e->tris[t].p1, q2 = e->tris[t].p2, q3 = e->tris[t].p3;
             v3 n = vcross(V(q2.x - q1.x, q2.y - q1.y, q2.z - q1.z), V(q3.x - q1.x, q3.y - q1.y, q3.z - q1.z));
             double len = sqrt(vdot(n, n));
             if (len > 0) n = vmul(n, 1.0 / len);

@@ -1,0 +1,110 @@
+"""G19_SHAPES_FIXED: PATH mode traces the composite entities as their constructors MEANT to
+build them -- same entity ids, REF mode untouched.
+
+Reference constructors and their bugs: ExpRectangle p4 = -p3 (reference include/entities.h:319 vs :312), ExpBox made of
+those rectangles (:399-406), ExpSphere tessellated around -pos and without its first triangle (:475-482, :520), ExpQuad
+rotating about the origin and adding pos.z twice (:583-586), ExpCone overwriting the caller's direction (:825).
+The checks are geometric (they hold for the intended shape and fail for the buggy one), on the oracle without a GPU
+and on the CUDA tracer against the oracle.
+"""
+import numpy as np
+import pytest
+
+from util import mirror, rel_rmse
+
+SPHERE_POS, SPHERE_R = (-2.0, 3.0, 1.0), 2.0
+CONE_POS, CONE_DIR, CONE_H, CONE_R = (0.0, -3.0, 3.0), (0.3, 0.2, -1.0), 4.0, 1.5
+RECT = ((1.0, 0.0, -3.0), (1.0, 3.0, -1.0), (1.0, 3.0, -3.0))  # p1, p2 diagonal, p3 the right-angle corner: x = 1 plane
+BOX = ((-1.0, -6.0, -4.0), (1.0, -4.5, -2.5))
+QUAD_POS, QUAD_W, QUAD_L, QUAD_A = (2.0, 0.0, 4.5), 2.0, 3.0, 1.2
+
+
+def shapes_scene(g19, abi):
+    sc = g19.Octree((-20,) * 3, (20,) * 3)
+    sc.push_back(g19.ExpSphere(SPHERE_POS, SPHERE_R, (0.8, 0.3, 0.3)))                 # 0
+    sc.push_back(g19.ExpCone(CONE_POS, CONE_DIR, CONE_H, CONE_R, (0.3, 0.8, 0.3)))     # 1
+    sc.push_back(g19.ExpRectangle(*RECT, color=(0.3, 0.3, 0.8)))                       # 2
+    sc.push_back(g19.ExpBox(*BOX, color=(0.8, 0.8, 0.3)))                              # 3
+    sc.push_back(g19.ExpQuad(QUAD_POS, QUAD_W, QUAD_L, QUAD_A, (0.3, 0.8, 0.8)))       # 4
+    sc.push_back(g19.ExpCube((4.0, 5.0, -4.0), 2.0, 2.0, 2.0, (0.8, 0.3, 0.8)))        # 5: right in the reference already
+    # a light panel behind the camera so that the PATH image is not black
+    a, b, c, d = (-14, -9, -9), (-14, 9, -9), (-14, 9, 9), (-14, -9, 9)
+    sc.push_back(g19.ImpTriangle(a, b, c, color=(1, 1, 1), bsdf=abi.BSDF_EMITTER, emission=(3, 3, 3)))
+    sc.push_back(g19.ImpTriangle(a, c, d, color=(1, 1, 1), bsdf=abi.BSDF_EMITTER, emission=(3, 3, 3)))
+    cam = g19.Camera((-12, 0, 0), (1, 0, 0), 0.016)  # 128 px wide: half-angle ~39 degrees
+    return sc, cam
+
+
+def check_geometry(ids, pts):
+    """Every primary hit lies on the INTENDED surface of its entity."""
+    n_hit = np.bincount(ids[ids >= 0].ravel(), minlength=8)
+    assert (n_hit[:6] > 40).all(), n_hit
+    p = pts[ids == 0] - np.array(SPHERE_POS)  # inscribed 10 x 10 polyhedron of the sphere AROUND pos
+    dist = np.linalg.norm(p, axis=1)
+    assert dist.max() <= SPHERE_R + 1e-5 and dist.min() >= 0.9 * SPHERE_R
+    axis = np.array(CONE_DIR) / np.linalg.norm(CONE_DIR)  # the CALLER's direction
+    q = pts[ids == 1] - np.array(CONE_POS)
+    along = q @ axis
+    radial = np.linalg.norm(q - along[:, None] * axis, axis=1)
+    assert along.min() >= -1e-5 and along.max() <= CONE_H + 1e-5
+    assert (radial <= CONE_R * along / CONE_H + 1e-4).all()  # inside the cone (side faces are chords: slightly inside)
+    r = pts[ids == 2]  # the rectangle p1, p3, p2, p4 = p1 + p2 - p3 in the plane x = 1
+    assert np.abs(r[:, 0] - 1.0).max() < 1e-5
+    assert r[:, 1].min() >= -1e-5 and r[:, 1].max() <= 3 + 1e-5 and r[:, 2].min() >= -3 - 1e-5 and r[:, 2].max() <= -1 + 1e-5
+    assert (r[:, 1] < 1.0).any() and (r[:, 2] > -2.0).any() and ((r[:, 1] < 1.5) & (r[:, 2] > -2.0)).any()  # both halves present
+    b = pts[ids == 3]  # on the box's surface
+    lo, hi = np.array(BOX[0]), np.array(BOX[1])
+    assert (b >= lo - 1e-5).all() and (b <= hi + 1e-5).all()
+    assert (np.minimum(np.abs(b - lo), np.abs(b - hi)).min(axis=1) < 1e-4).all()
+    k = pts[ids == 4] - np.array(QUAD_POS)  # w x l quad centred on pos, width along (cos a, 0, sin a), length along y
+    wdir = np.array([np.cos(QUAD_A), 0.0, np.sin(QUAD_A)])
+    ndir = np.array([-np.sin(QUAD_A), 0.0, np.cos(QUAD_A)])
+    assert np.abs(k @ ndir).max() < 1e-4 and np.abs(k @ wdir).max() <= QUAD_W / 2 + 1e-4 and np.abs(k[:, 1]).max() <= QUAD_L / 2 + 1e-4
+
+
+def test_oracle_fixed_shapes_are_the_intended_surfaces(g19, abi, oracle):
+    from oracle import binding
+    sc, cam = shapes_scene(g19, abi)
+    chk = mirror(oracle, sc)
+    oracle.lib.g19o_scene_set_shapes(chk.h, abi.SHAPES_FIXED)
+    ids, pts, _ = binding.path_primary(chk, cam, 128, 128)
+    check_geometry(ids, pts)
+    oracle.lib.g19o_scene_set_shapes(chk.h, abi.SHAPES_REF)  # the reference's own triangles fail the same checks
+    ids_r, pts_r, _ = binding.path_primary(chk, cam, 128, 128)
+    with pytest.raises(AssertionError):
+        check_geometry(ids_r, pts_r)
+    # the ExpCube and the light are the same in both modes
+    assert np.array_equal(ids == 5, ids_r == 5) or ((ids == 5) ^ (ids_r == 5)).sum() < 200  # (occluders in front differ)
+
+
+@pytest.mark.gpu
+def test_gpu_fixed_shapes_vs_oracle(g19, abi, oracle):
+    from oracle import binding
+    w = h = 128
+    sc, cam = shapes_scene(g19, abi)
+    chk = mirror(oracle, sc)
+    rt = g19.RayTracer(cam, (-10, 10, 10))
+    rt.setScene(sc)
+    rt.start()
+    ref_before = rt.run(w, h, want=("ids", "rgb"))
+    base = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance", "ids"), spp=32, max_depth=4, seed=2)
+    sc.set_shapes(True)
+    rt.setScene(sc)
+    oracle.lib.g19o_scene_set_shapes(chk.h, abi.SHAPES_FIXED)
+    got = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance", "ids"), spp=32, max_depth=4, seed=2)
+    exp, segs = binding.path_render(chk, cam, w, h, 32, 4, seed=2)
+    ids, pts, _ = binding.path_primary(chk, cam, w, h)
+    assert exp.mean() > 0.01
+    assert rel_rmse(got["radiance"], exp) <= 1e-2
+    st = rt.stats()
+    assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
+    assert (got["ids"] != ids).sum() <= 0.01 * w * h  # silhouettes / shared edges only
+    check_geometry(np.where(got["ids"] == ids, ids, -1), pts)
+    assert got["radiance"].tobytes() != base["radiance"].tobytes()  # the flag does change what PATH mode traces
+    # ... and changes nothing in REF mode
+    ref_after = rt.run(w, h, want=("ids", "rgb"))
+    assert np.array_equal(ref_before["ids"], ref_after["ids"]) and np.array_equal(ref_before["rgb"], ref_after["rgb"])
+    sc.set_shapes(False)
+    rt.setScene(sc)
+    again = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=32, max_depth=4, seed=2)
+    assert again["radiance"].tobytes() == base["radiance"].tobytes()
