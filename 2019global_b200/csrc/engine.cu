@@ -5,7 +5,9 @@
 // and renders with run(w,h); here the ctx owns the flattened scene in HBM and
 // g19_render* is run(). There is no CPU path: every entry point that computes
 // launches CUDA kernels, and g19_create fails when no device is usable.
+#include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -64,6 +66,7 @@ struct g19_ctx {
     std::atomic<int> progress_milli{0};
     int sm_count = 148;
     bool has_scene = false;
+    bool host_call = false; // inside g19_render / g19_render_progressive: the caller blocks, so REF mode may render in bands
 
     // REF view
     DevBuf ref_nodes, ref_ents, ref_entities, ref_tris;
@@ -336,14 +339,57 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
         G19_CUDA(ctx, cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s));
     }
     ClassTimer t{ctx, s, p->profile != 0};
-    t.begin();
-    launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                          ctx->normals_l.as<double>(), counters, s);
-    t.end(G19_K_REF_VIS, 1);
-    t.begin();
-    launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                     ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s);
-    t.end(G19_K_REF_SHADE, 1);
+    // The reference fills its Image pixel by pixel and polls _running per pixel (raytracer.h:32-33), so stop() and
+    // the viewer's 32 ms repaint see a frame in progress. On a heavy scene (the 1 M-entity heightfield takes seconds)
+    // the host-pointer entry points therefore render BAND by band of whole tile rows: between bands the host
+    // checks the cancel flag, publishes progress and -- for g19_render_progressive -- refreshes the caller's image.
+    // Light scenes and the device-pointer entry points (asynchronous by contract) stay one launch.
+    const bool banded = ctx->host_call && !frame && map.n_local_tiles >= 64 && (ctx->ref.n_nodes > 512 || ctx->ref.n_entities > 4096);
+    int rc_band = G19_OK;
+    if (!banded) {
+        t.begin();
+        launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                              ctx->normals_l.as<double>(), counters, s);
+        t.end(G19_K_REF_VIS, 1);
+        t.begin();
+        launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                         ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s);
+        t.end(G19_K_REF_SHADE, 1);
+    } else {
+        // pixels a cancelled render never reaches stay "no hit, black" (Image(w,h) starts black, image.h:9)
+        G19_CUDA(ctx, cudaMemsetAsync(ctx->ids_l.p, 0xff, n * sizeof(int32_t), s));
+        G19_CUDA(ctx, cudaMemsetAsync(ctx->rgb_l.p, 0, n * 3, s));
+        G19_CUDA(ctx, cudaMemsetAsync(ctx->colour_l.p, 0, n * 3 * sizeof(float), s));
+        const int tiles_per_band = std::max(map.tiles_x / std::max(1, map.world), (map.n_local_tiles + 63) / 64); // about one tile row
+        auto last_refresh = std::chrono::steady_clock::now();
+        for (int t0 = 0; t0 < map.n_local_tiles; t0 += tiles_per_band) {
+            if (ctx->cancel.load()) { // RayTracer::stop()
+                rc_band = G19_ERR_CANCELLED;
+                break;
+            }
+            const int lp0 = t0 * kTilePix, lp1 = std::min(map.n_local_tiles, t0 + tiles_per_band) * kTilePix;
+            t.begin();
+            launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                                  ctx->normals_l.as<double>(), counters, s, lp0, lp1);
+            t.end(G19_K_REF_VIS, 1);
+            t.begin();
+            launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                             ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s, lp0, lp1);
+            t.end(G19_K_REF_SHADE, 1);
+            G19_CUDA(ctx, cudaStreamSynchronize(s)); // the host stays one band ahead at most: that is the cancel latency
+            ctx->progress_milli.store(int(1000.0 * double(lp1) / double(map.n_local_pix)));
+            const auto now = std::chrono::steady_clock::now();
+            if (ctx->hook.fn && d_rgb && ctx->hook.h_rgb && lp1 < map.n_local_pix &&
+                std::chrono::duration<double, std::milli>(now - last_refresh).count() >= double(ctx->hook.min_interval_ms)) {
+                last_refresh = now;
+                launch_untile(map, ctx->rgb_l.as<uint8_t>(), nullptr, nullptr, d_rgb, nullptr, nullptr, s);
+                G19_CUDA(ctx, cudaMemcpyAsync(ctx->hook.h_rgb, d_rgb, size_t(map.w) * size_t(map.h) * 3, cudaMemcpyDeviceToHost, s));
+                G19_CUDA(ctx, cudaStreamSynchronize(s));
+                ctx->stats.kernel_launches += 1;
+                if (ctx->hook.fn(ctx->hook.user, double(lp1) / double(map.n_local_pix), ctx->hook.h_rgb) != 0) ctx->cancel.store(1);
+            }
+        }
+    }
     t.begin();
     if (frame) { // shared frame: wait for the owner, scatter this rank's pixels into it, signal
         launch_frame_acquire(frame->flags, frame->epoch - 1, frame->d_status, s);
@@ -377,7 +423,7 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     }
     ctx->stats.samples = owned;
     ctx->stats.extend_segments = owned;
-    return G19_OK;
+    return rc_band;
 }
 
 } // namespace
@@ -617,8 +663,10 @@ int g19_render(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
         if (ids) G19_CUDA(ctx, cudaMemcpyAsync(ctx->ids_f.p, ids, npx * 4, cudaMemcpyHostToDevice, s));
         if (rad) G19_CUDA(ctx, cudaMemcpyAsync(ctx->rad_f.p, rad, npx * 12, cudaMemcpyHostToDevice, s));
     }
+    ctx->host_call = true;
     rc = g19_render_device(ctx, cam, light, p, rgb ? ctx->rgb_f.as<uint8_t>() : nullptr,
                            ids ? ctx->ids_f.as<int32_t>() : nullptr, rad ? ctx->rad_f.as<float>() : nullptr, s);
+    ctx->host_call = false;
     if (rc != G19_OK && rc != G19_ERR_CANCELLED) return rc;
     if (rgb) G19_CUDA(ctx, cudaMemcpyAsync(rgb, ctx->rgb_f.p, npx * 3, cudaMemcpyDeviceToHost, s));
     if (ids) G19_CUDA(ctx, cudaMemcpyAsync(ids, ctx->ids_f.p, npx * 4, cudaMemcpyDeviceToHost, s));

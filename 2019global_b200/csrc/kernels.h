@@ -55,12 +55,15 @@ struct RefSceneD {
 // ---- ref_kernels.cu ------------------------------------------------------
 // raygen + octree traversal + entity intersection + front-object selection
 // (raytracer.h:41-74). Outputs are indexed by local pixel.
+// [lp0, lp1) = the band of this rank's local pixels to render (lp1 < 0: all): the host-pointer entry points render
+// heavy scenes band by band so that stop() and the viewer's repaint see the frame grow (raytracer.h:32-33).
 void launch_ref_visibility(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, int32_t* ids,
                            double* points, double* normals, unsigned long long* counters /*nullable: [node,prim]*/,
-                           cudaStream_t stream);
+                           cudaStream_t stream, int lp0 = 0, int lp1 = -1);
 // getTextureCoord + blinn_phong_texture + RGB888 quantisation (raytracer.h:76-82).
 void launch_ref_shade(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, const int32_t* ids,
-                      const double* points, const double* normals, uint8_t* rgb, float* colour, cudaStream_t stream);
+                      const double* points, const double* normals, uint8_t* rgb, float* colour, cudaStream_t stream,
+                      int lp0 = 0, int lp1 = -1);
 // Probes: Entity::intersect on n rays; Octree::intersect candidate list of one ray.
 void launch_probe_intersect(const RefSceneD& scene, int32_t entity, int n, const double* origins, const double* dirs,
                             int32_t* hit, double* points, double* normals, cudaStream_t stream);

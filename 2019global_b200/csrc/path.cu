@@ -148,7 +148,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -171,6 +171,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "raygen_occ") t.raygen_occ = num(def.raygen_occ, 2, 3);
     else if (k == "tree_build") t.tree_build = !value ? -1 : (std::strcmp(value, "device") == 0 ? 1 : (std::strcmp(value, "host") == 0 ? 0 : -1));
     else if (k == "debug_tree") t.debug_tree = value ? 1 : 0;
+    else if (k == "walk") t.walk = num(def.walk, 0, 1);
     else return false;
     return true;
 }
@@ -535,6 +536,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     for (int k = 0; k < 3; ++k) {
         v.root_lo[k] = root_lo[k];
         v.root_size[k] = root_size[k];
+        v.grid_scale[k] = float(double(1 << kMaxTreeDepth) / double(root_size[k]));
     }
     return G19_OK;
 }
@@ -627,6 +629,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa0.walk_steps = a.tune.walk_steps;
     pa0.leaf_batch = a.tune.leaf_batch > 0 ? a.tune.leaf_batch : (pa0.coop_leaf ? 16 : 4); // cooperative: the whole leaf in one go (leaf max 8 / 12 / 16 at batch 16: 97.7 / 96.9 / 97.8 ms)
     pa0.raygen_occ = a.tune.raygen_occ;
+    pa0.walk = a.tune.walk ? (p.profile ? 2 : 1) : 0; // the new walk counts its node / primitive tests under params.profile
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
     // primary-hit AOV: the un-jittered ray of every pixel (the reference's ray) through this engine's structures
     if (a.ids_l) {
@@ -693,14 +696,14 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             PATH_CUDA(cudaEventCreateWithFlags(&w.ev_join[i], cudaEventDisableTiming));
         }
     }
-    PATH_CUDA(w.totals.ensure(8 * sizeof(unsigned long long)));
+    PATH_CUDA(w.totals.ensure(10 * sizeof(unsigned long long)));
     PATH_CUDA(w.accum.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rad_l.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rgb_l.ensure(npix * 3));
-    PATH_CUDA(cudaMemsetAsync(w.totals.p, 0, 8 * sizeof(unsigned long long), s));
+    PATH_CUDA(cudaMemsetAsync(w.totals.p, 0, 10 * sizeof(unsigned long long), s));
     PATH_CUDA(cudaMemsetAsync(w.accum.p, 0, npix * 3 * sizeof(float), s));
     if (p.profile && !w.events) {
-        w.n_events = 8192;
+        w.n_events = 65536;
         w.events = new cudaEvent_t[w.n_events];
         for (int i = 0; i < w.n_events; ++i) PATH_CUDA(cudaEventCreate(&w.events[i]));
     }
@@ -894,7 +897,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
 
 int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
     if (!w.totals_pending) return G19_OK;
-    unsigned long long h[8];
+    unsigned long long h[10];
     cudaError_t e = cudaMemcpy(h, w.totals.p, sizeof h, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) {
         err = std::string("path_finish_stats: ") + cudaGetErrorString(e);
@@ -907,6 +910,8 @@ int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
     stats.lit_samples = h[4];
     stats.radiance_reads = h[5];
     stats.radiance_stores = h[6];
+    stats.node_tests = h[7]; // tree scenes under params.profile: octree node records visited / primitive tests (TreeWalk2<COUNT>)
+    stats.prim_tests = h[8];
     for (int i = 0; i + 1 < w.used_events; i += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, w.events[i], w.events[i + 1]) == cudaSuccess) stats.class_ms[w.event_class[i / 2]] += ms;

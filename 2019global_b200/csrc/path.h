@@ -48,6 +48,7 @@ struct PathSceneD {
     int32_t pairs_bytes;
     const int32_t* prim_entity; // 2 per primitive: the entity id REF mode would report (both halves of a merged parallelogram)
     float root_lo[3], root_size[3];
+    float grid_scale[3];     // 2^kMaxTreeDepth / root_size: world position -> coordinate on the finest octree grid
 };
 
 struct PathCamera { // float copies of the reference basis (RefCamera)
@@ -95,7 +96,7 @@ struct PathWork {
     // event pool for params.profile
     cudaEvent_t* events = nullptr;
     int n_events = 0, used_events = 0;
-    int event_class[4096];
+    int event_class[32768];
     bool totals_pending = false;
     cudaStream_t totals_stream = nullptr;
 };
@@ -114,6 +115,7 @@ struct PathTuning {
     int raygen_occ = 3;       // CTAs per SM of the tree-scene camera-ray kernel
     int tree_build = -1;      // -1 auto (device from 4096 primitives), 0 host, 1 device
     int debug_tree = 0;       // print octree statistics at upload
+    int walk = 1;             // tree walk: 1 = point-location restart walk (TreeWalk2), 0 = parametric stack walk (TreeWalk)
 };
 void path_tuning_from_env(PathTuning& t);
 bool path_tuning_set(PathTuning& t, const char* key, const char* value); // false: unknown key
@@ -200,6 +202,7 @@ struct PassArgs {
     int32_t walk_steps, leaf_batch; // tree walk: cell moves / primitives tested per round (TreeWalk::step)
     int32_t coop_leaf;     // tree walk: leaf tests spread over the whole warp (default; G19_COOP_LEAF=0: sequential)
     int32_t raygen_occ;    // tree scenes: CTAs per SM of the camera-ray kernel (2 or 3)
+    int32_t walk;          // tree walk variant (PathTuning::walk); +2 when the walk counts its node / primitive tests
 };
 
 void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s);

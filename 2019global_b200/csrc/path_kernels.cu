@@ -71,6 +71,11 @@ constexpr uint32_t kRayShadow = 0x80000000u;   // ray record flags riding on the
 constexpr uint32_t kRaySpecular = 0x40000000u; // the continuation ray leaves a specular vertex
 constexpr uint32_t kRaySlotMask = 0x3fffffffu;
 
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
+}
+
 // ---- Philox4x32-10 (Salmon et al. 2011); identical integer stream in oracle/path_oracle.c
 __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0) {
     uint32_t k1 = 0x32303139u; // "2019"
@@ -654,18 +659,270 @@ struct TreeWalk {
     }
 };
 
+// ---- TreeWalk2: point-location restart walk ---------------------------------------------------
+// What the round-1 capture of the parametric walk above showed (profiles/r01f_tree_kernels_ncu.json): ~870 warp
+// instructions per ray at 13.7 of 32 lanes, 62 % of them cell MOVES at ~130 instructions each -- every move
+// recomputes nine plane parameters, edits a 64-bit code word with variable shifts and runs a four-way
+// leave / descend / skip / arrive decision, and going from one leaf to a neighbour under another ancestor costs one
+// move per level up plus one per level down. This walk keeps the ray's position as INTEGER coordinates (X, Y, Z) on
+// the finest grid of the octree (2^14 cells per axis; node boxes are implicit, so a cell of level l is the top l
+// bits) and does three cheap things per visited cell:
+//   descend   from the deepest ancestor still valid for (X, Y, Z) -- its child base sits on the per-thread stack in
+//             shared memory -- follow the coordinate bits down to the leaf or empty cell: three bit extracts, one
+//             8-byte node record, ~12 instructions per level, typically 1-3 levels
+//   exit      the parameter at which the ray leaves the cell: one FMA per axis on the same linear plane form
+//             t(i) = A + i * (B * 2^-level) as before (shared planes get bit-identical parameters), minimum of three
+//   advance   step the exit axis' coordinate to the neighbouring cell (exact integer arithmetic: no epsilon nudging),
+//             re-derive the other two from the exit point clamped to the current cell's range, and find the common
+//             ancestor with one XOR + CLZ
+// -- no plane registers, no code word, no pops. Cells are visited strictly in ray order, so the walk still stops at
+// the first leaf whose hit lies inside its own cell. COUNT: node records visited and primitives tested are tallied
+// for the issue-roofline model; instantiated only under params.profile.
+template <bool COUNT> struct TreeWalk2 {
+    float3 o, d, A, B;
+    float best;
+    uint32_t best_prim;
+    uint32_t X, Y, Z;            // position on the finest grid
+    uint32_t lv;                 // deepest level whose stack entry (child base) is valid for (X, Y, Z)
+    float t_exit;                // where the ray leaves the current cell (valid while an advance is pending)
+    uint32_t leaf_first, leaf_n; // the part of the current leaf's list still to be tested
+    float leaf_exit;
+    uint32_t state;              // bit 0: any-hit ray; bit 1: advance pending; bits 2-3: exit axis
+    uint32_t n_node, n_prim;     // COUNT only
+
+    template <bool ALL>
+    __device__ __forceinline__ bool init(const SceneAccess<ALL>& S, float3 o_, float3 d_, float tmax, bool any_) {
+        const PathSceneD& g = *S.g;
+        o = o_;
+        d = d_;
+        best = tmax;
+        best_prim = kInvalid;
+        state = any_ ? 1u : 0u;
+        leaf_n = 0;
+        const uint2 root = S.node(0);
+        if (root.y & kLeafBit) { // the whole scene is one leaf (but not staged as a flat scene)
+            TreeWalk w0 = {};
+            w0.o = o; w0.d = d; w0.best = best; w0.best_prim = kInvalid; w0.any = any_;
+            w0.leaf(g, root.x, root.y & ~kLeafBit, 0x7fffffffu);
+            best = w0.best;
+            best_prim = w0.best_prim;
+            return true;
+        }
+        // slab clip against the root box; an axis the ray (almost) does not move along never produces an exit
+        float tn = 0.0f, tf = best;
+        bool miss = false;
+        const float inf = __int_as_float(0x7f800000);
+#define G19_AXIS(c, k)                                                                  \
+        if (fabsf(d.c) < 1.0e-12f) {                                                    \
+            miss |= o.c < g.root_lo[k] || o.c > g.root_lo[k] + g.root_size[k];          \
+            A.c = inf; B.c = 0.0f;                                                      \
+        } else {                                                                        \
+            const float inv = __fdividef(1.0f, d.c);                                    \
+            A.c = (g.root_lo[k] - o.c) * inv;                                           \
+            B.c = g.root_size[k] * inv;                                                 \
+            const float t1 = A.c + B.c;                                                 \
+            tn = fmaxf(tn, fminf(A.c, t1));                                             \
+            tf = fminf(tf, fmaxf(A.c, t1));                                             \
+        }
+        G19_AXIS(x, 0) G19_AXIS(y, 1) G19_AXIS(z, 2)
+#undef G19_AXIS
+        if (miss || tn > tf + 1.0e-5f) return true;
+        const int hi = (1 << kMaxTreeDepth) - 1;
+        X = uint32_t(min(max(__float2int_rd((fmaf(d.x, tn, o.x) - g.root_lo[0]) * g.grid_scale[0]), 0), hi));
+        Y = uint32_t(min(max(__float2int_rd((fmaf(d.y, tn, o.y) - g.root_lo[1]) * g.grid_scale[1]), 0), hi));
+        Z = uint32_t(min(max(__float2int_rd((fmaf(d.z, tn, o.z) - g.root_lo[2]) * g.grid_scale[2]), 0), hi));
+        lv = 0;
+        S.stack[0] = root.x;
+        if (COUNT) n_node = n_prim = 0;
+        return false;
+    }
+
+    // One ROUND for the 32 rays of a warp (MUST be called by all lanes, `active` = this lane has a ray): walk_steps
+    // times [advance out of the finished cell, descend to the next leaf / empty cell, compute its exit], then one
+    // batch of at most leaf_batch primitives of the lanes that stand in a leaf. Returns true when the lane's ray is
+    // finished.
+    template <bool ALL, bool COOP> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
+        uint32_t* const stack = S.stack;
+        const PathSceneD& g = *S.g;
+        bool done = false;
+        const int kWalkSteps = S.walk_steps;
+        const uint32_t kLeafBatch = S.leaf_batch;
+#pragma unroll 1
+        for (int it = 0; it < kWalkSteps; ++it) {
+            __syncwarp();
+            bool walking = active && !done && leaf_n == 0u;
+            if (walking && (state & 2u)) {
+                // ---- advance: out of the current cell through its exit face ----
+                const uint32_t s = uint32_t(kMaxTreeDepth - 1) - lv; // the cell is at level lv + 1: it spans 2^s fine cells per axis
+                const uint32_t axis = (state >> 2) & 3u;
+                const uint32_t mask = (1u << s) - 1u;
+                const int hi = (1 << kMaxTreeDepth) - 1;
+                // the exit point on the finest grid, held inside the current cell (it IS on the cell's boundary)
+                int nx = __float2int_rd((fmaf(d.x, t_exit, o.x) - g.root_lo[0]) * g.grid_scale[0]);
+                int ny = __float2int_rd((fmaf(d.y, t_exit, o.y) - g.root_lo[1]) * g.grid_scale[1]);
+                int nz = __float2int_rd((fmaf(d.z, t_exit, o.z) - g.root_lo[2]) * g.grid_scale[2]);
+                const int x0 = int(X & ~mask), y0 = int(Y & ~mask), z0 = int(Z & ~mask);
+                nx = min(max(nx, x0), x0 + int(mask));
+                ny = min(max(ny, y0), y0 + int(mask));
+                nz = min(max(nz, z0), z0 + int(mask));
+                // ... and one cell further along the exit axis
+                if (axis == 0u) nx = d.x > 0.0f ? x0 + int(mask) + 1 : x0 - 1;
+                else if (axis == 1u) ny = d.y > 0.0f ? y0 + int(mask) + 1 : y0 - 1;
+                else nz = d.z > 0.0f ? z0 + int(mask) + 1 : z0 - 1;
+                if ((nx | ny | nz) < 0 || nx > hi || ny > hi || nz > hi) {
+                    done = true; // left the root box
+                    walking = false;
+                } else {
+                    const uint32_t diff = (X ^ uint32_t(nx)) | (Y ^ uint32_t(ny)) | (Z ^ uint32_t(nz));
+                    // highest differing bit h = 31 - clz: the level-m ancestors agree for m <= kMaxTreeDepth - 1 - h
+                    lv = min(lv, uint32_t(__clz(int(diff))) - uint32_t(32 - kMaxTreeDepth));
+                    X = uint32_t(nx); Y = uint32_t(ny); Z = uint32_t(nz);
+                }
+                state &= ~2u;
+            }
+            // ---- descend to the leaf / empty cell that holds (X, Y, Z) ----
+            bool desc = walking;
+            uint32_t k = lv;
+            uint2 rec = make_uint2(0u, kLeafBit);
+            while (__any_sync(kFull, desc)) {
+                if (desc) {
+                    const uint32_t sh = uint32_t(kMaxTreeDepth - 1) - k;
+                    const uint32_t c = ((X >> sh) & 1u) | (((Y >> sh) & 1u) << 1) | (((Z >> sh) & 1u) << 2);
+                    rec = S.node(stack[k * kThreads] + c);
+                    if (COUNT) ++n_node;
+                    if ((rec.y & kLeafBit) || k + 1u >= uint32_t(kMaxTreeDepth)) {
+                        desc = false;
+                    } else {
+                        ++k;
+                        stack[k * kThreads] = rec.x;
+                    }
+                }
+            }
+            if (walking) {
+                lv = k;
+                // ---- exit parameter of the cell (level lv + 1): the far plane per axis, linear in the plane index ----
+                const uint32_t sh = uint32_t(kMaxTreeDepth - 1) - k;
+                const float s1 = __int_as_float((127 - int(k + 1u)) << 23); // 2^-(level), exact
+                const float fx = float((X >> sh) + (d.x > 0.0f ? 1u : 0u)), fy = float((Y >> sh) + (d.y > 0.0f ? 1u : 0u)),
+                            fz = float((Z >> sh) + (d.z > 0.0f ? 1u : 0u));
+                const float tx = fmaf(fx, B.x * s1, A.x), ty = fmaf(fy, B.y * s1, A.y), tz = fmaf(fz, B.z * s1, A.z);
+                const uint32_t axis = (tx <= ty && tx <= tz) ? 0u : (ty <= tz ? 1u : 2u);
+                t_exit = fminf(fminf(tx, ty), tz);
+                state = (state & 1u) | 2u | (axis << 2);
+                if (rec.y != kLeafBit) { // a leaf with primitives
+                    leaf_first = rec.x;
+                    leaf_n = rec.y & ~kLeafBit;
+                    leaf_exit = t_exit;
+                } else if (t_exit >= best) {
+                    done = true; // empty cell, and everything beyond it is farther than the hit / the ray's end
+                }
+            }
+        }
+        __syncwarp();
+        // ---- test: the next batch of the current leaf's primitives (same two forms as TreeWalk::step) ----
+        const bool any = (state & 1u) != 0u;
+        if constexpr (COOP) {
+            const uint32_t lane = threadIdx.x & 31u;
+            const bool mine = active && !done && leaf_n != 0u;
+            const uint32_t cnt = mine ? (leaf_n < kLeafBatch ? leaf_n : kLeafBatch) : 0u;
+            if (__ballot_sync(kFull, cnt != 0u) != 0u) {
+                uint32_t inc = cnt; // inclusive prefix sum over the lanes
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t v = __shfl_up_sync(kFull, inc, off);
+                    if (lane >= uint32_t(off)) inc += v;
+                }
+                const uint32_t total = __shfl_sync(kFull, inc, 31);
+                const uint32_t exc = inc - cnt;
+                S.coop[lane] = ~0ull;
+                __syncwarp();
+                const uint32_t* __restrict__ index = g.index;
+                const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
+                for (uint32_t base = 0; base < total; base += 32u) {
+                    const uint32_t j = base + lane;
+                    uint32_t own = 0; // number of lanes whose tasks all lie before j = the owner of task j
+#pragma unroll
+                    for (int stepw = 16; stepw > 0; stepw >>= 1) {
+                        const uint32_t probe = __shfl_sync(kFull, inc, int(own) + stepw - 1);
+                        if (probe <= j) own += uint32_t(stepw);
+                    }
+                    const bool valid = j < total;
+                    if (!valid) own = 0;
+                    const uint32_t kk = j - __shfl_sync(kFull, exc, int(own));
+                    const uint32_t lf = __shfl_sync(kFull, leaf_first, int(own));
+                    const float rox = __shfl_sync(kFull, o.x, int(own)), roy = __shfl_sync(kFull, o.y, int(own)), roz = __shfl_sync(kFull, o.z, int(own));
+                    const float rdx = __shfl_sync(kFull, d.x, int(own)), rdy = __shfl_sync(kFull, d.y, int(own)), rdz = __shfl_sync(kFull, d.z, int(own));
+                    const float rbest = __shfl_sync(kFull, best, int(own));
+                    if (valid) {
+                        const uint32_t id = __ldg(index + lf + kk);
+                        const float4* pp = hot + 4 * (size_t)id;
+                        const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
+                        const float t = hit_prim(a0, b0, c0, g0, f3(rox, roy, roz), f3(rdx, rdy, rdz), rbest);
+                        if (t >= 0.0f) atomicMin(S.coop + own, ((unsigned long long)__float_as_uint(t) << 32) | id);
+                    }
+                }
+                __syncwarp();
+                if (cnt != 0u) {
+                    const unsigned long long r = S.coop[lane];
+                    if (r != ~0ull) { best = __uint_as_float(uint32_t(r >> 32)); best_prim = uint32_t(r); }
+                    if (COUNT) n_prim += cnt;
+                    leaf_first += cnt;
+                    leaf_n -= cnt;
+                    if (any && best_prim != kInvalid) done = true;
+                    else if (leaf_n == 0u && leaf_exit >= best) done = true; // the hit lies inside this cell / the ray ends here
+                }
+                __syncwarp();
+            }
+        } else if (active && !done && leaf_n != 0u) { // sequential form: every lane tests its own leaf's primitives
+            TreeWalk w0 = {};
+            w0.o = o; w0.d = d; w0.best = best; w0.best_prim = best_prim; w0.any = any;
+            w0.leaf(g, leaf_first, leaf_n, kLeafBatch);
+            best = w0.best;
+            best_prim = w0.best_prim;
+            const uint32_t tested = leaf_n < kLeafBatch ? leaf_n : kLeafBatch;
+            if (COUNT) n_prim += tested;
+            leaf_first += tested;
+            leaf_n -= tested;
+            if (any && best_prim != kInvalid) done = true;
+            else if (leaf_n == 0u && leaf_exit >= best) done = true;
+        }
+        __syncwarp();
+        return done;
+    }
+};
+
+template <int WALK> struct WalkOf { using type = TreeWalk; };
+template <> struct WalkOf<1> { using type = TreeWalk2<false>; };
+template <> struct WalkOf<2> { using type = TreeWalk2<true>; };
+template <typename W> __device__ __forceinline__ void walk_counts(const W&, unsigned&, unsigned&) {}
+template <> __device__ __forceinline__ void walk_counts(const TreeWalk2<true>& w, unsigned& nodes, unsigned& prims) {
+    nodes += w.n_node;
+    prims += w.n_prim;
+}
+// tallies of finished rays -> totals[7] (node records visited), totals[8] (primitive tests)
+__device__ __forceinline__ void flush_walk_counts(const PassArgs& a, unsigned nodes, unsigned prims) {
+    nodes = warp_sum_u(nodes);
+    prims = warp_sum_u(prims);
+    if ((threadIdx.x & 31u) == 0u && (nodes | prims)) {
+        atomicAdd(a.totals + 7, (unsigned long long)nodes);
+        atomicAdd(a.totals + 8, (unsigned long long)prims);
+    }
+}
+
 // Runs the walks of a whole warp to completion; MUST be called by all 32 lanes (`active` = this
 // lane has a ray). Used for camera rays; secondary rays go through trace_kernel.
-template <bool ALL, bool COOP>
+template <bool ALL, bool COOP, int WALK = 0>
 __device__ bool traverse(const SceneAccess<ALL>& S, bool active, float3 o, float3 d, float tmax, bool any, float& t_hit,
-                         uint32_t& prim_hit) {
-    TreeWalk w = {};
+                         uint32_t& prim_hit, unsigned* n_node = nullptr, unsigned* n_prim = nullptr) {
+    typename WalkOf<WALK>::type w = {};
     w.best_prim = kInvalid;
     bool busy = active && !w.init(S, o, d, tmax, any);
+    const bool walked = busy;
     while (__any_sync(kFull, busy))
         if (w.template step<ALL, COOP>(S, busy)) busy = false;
     t_hit = w.best;
     prim_hit = w.best_prim;
+    if (WALK == 2 && walked && n_node) walk_counts(w, *n_node, *n_prim);
     return active && w.best_prim != kInvalid;
 }
 
@@ -821,14 +1078,15 @@ struct Sorter {
 };
 
 // Nearest hit of one ray, flat or tree. Called by all 32 lanes; `active` = the lane has a ray.
-template <bool ALL, bool COOP = false>
-__device__ __forceinline__ bool nearest(const SceneAccess<ALL>& S, bool active, float3 o, float3 d, float& t, uint32_t& prim) {
+template <bool ALL, bool COOP = false, int WALK = 0>
+__device__ __forceinline__ bool nearest(const SceneAccess<ALL>& S, bool active, float3 o, float3 d, float& t, uint32_t& prim,
+                                        unsigned* n_node = nullptr, unsigned* n_prim = nullptr) {
     if constexpr (ALL) {
         bool occ;
         trace_flat<false>(S, o, d, active ? FLT_MAX : -1.0f, d, -1.0f, t, prim, occ);
         return prim != kInvalid;
     } else {
-        return traverse<ALL, COOP>(S, active, o, d, FLT_MAX, false, t, prim);
+        return traverse<ALL, COOP, WALK>(S, active, o, d, FLT_MAX, false, t, prim, n_node, n_prim);
     }
 }
 
@@ -840,7 +1098,7 @@ __device__ __forceinline__ void store_vertex(const PassArgs& a, uint32_t slot, f
 }
 
 // ---- raygen + extend (camera segment), tree scenes: slot-indexed state ----------------------
-template <int OCC, bool COOP> __global__ void __launch_bounds__(kThreads, OCC) raygen_extend_kernel(const PassArgs a) {
+template <int OCC, bool COOP, int WALK> __global__ void __launch_bounds__(kThreads, OCC) raygen_extend_kernel(const PassArgs a) {
     pdl_launch_dependents();
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
@@ -848,6 +1106,7 @@ template <int OCC, bool COOP> __global__ void __launch_bounds__(kThreads, OCC) r
     pdl_wait(); // the previous pass's accumulate cleared the queue lengths and the radiance planes
     Sorter out;
     out.init(a, 0);
+    unsigned cnt_node = 0, cnt_prim = 0;
     const uint32_t stride = gridDim.x * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q - lane < n; q += stride) { // warp-uniform trip count
@@ -867,7 +1126,7 @@ template <int OCC, bool COOP> __global__ void __launch_bounds__(kThreads, OCC) r
         }
         float t;
         uint32_t prim;
-        if (nearest<false, COOP>(S, live, o, d, t, prim)) { // all 32 lanes walk together
+        if (nearest<false, COOP, WALK>(S, live, o, d, t, prim, &cnt_node, &cnt_prim)) { // all 32 lanes walk together
             const float4 tag = S.hot_row(prim, 3);
             const int bsdf = __float_as_int(tag.y); // material class rides in the hot record
             if (bsdf == G19_BSDF_EMITTER) {          // directly visible light: the path ends here
@@ -881,6 +1140,7 @@ template <int OCC, bool COOP> __global__ void __launch_bounds__(kThreads, OCC) r
         out.push(kind, slot);
     }
     out.flush();
+    if (WALK == 2) flush_walk_counts(a, cnt_node, cnt_prim);
 }
 
 // ---- bounce: shade + trace the continuation ray ------------------------------------------
@@ -1444,7 +1704,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
 // and, once PassArgs::refill lanes are idle, the warp pulls that many new rays with ONE atomic. A warp's
 // time is then the sum of its rays' rounds / 32, not 32 x the longest walk.
 
-template <bool COOP> __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, const int bounce) {
+template <bool COOP, int WALK> __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, const int bounce) {
     pdl_launch_dependents();
     const SceneAccess<false> S = stage_scene<false>(a);
     pdl_wait();
@@ -1456,7 +1716,8 @@ template <bool COOP> __global__ void __launch_bounds__(kThreads, 3) trace_kernel
     out.init(a, bounce + 1);
     uint32_t* const fetch = a.counts + (kMaxPathDepth + 1) * 4 + bounce;
     const uint32_t lane = threadIdx.x & 31u;
-    TreeWalk w = {};
+    typename WalkOf<WALK>::type w = {};
+    unsigned cnt_node = 0, cnt_prim = 0;
     bool have = false, more = true;
     uint32_t tag = 0; // slot | flags of the lane's ray
     float3 rgb = f3(0.f, 0.f, 0.f);
@@ -1504,6 +1765,7 @@ template <bool COOP> __global__ void __launch_bounds__(kThreads, 3) trace_kernel
             have = false;
         }
         if (finished) {
+            if (WALK == 2) walk_counts(w, cnt_node, cnt_prim);
             const uint32_t slot = tag & kRaySlotMask;
             if (tag & kRayShadow) {
                 if (w.best_prim == kInvalid) { // unoccluded: the light sample counts
@@ -1532,6 +1794,7 @@ template <bool COOP> __global__ void __launch_bounds__(kThreads, 3) trace_kernel
     if (sort) out.flush();
     lit = warp_sum(lit);
     if (lane == 0 && lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
+    if (WALK == 2) flush_walk_counts(a, cnt_node, cnt_prim);
 }
 
 // ---- primary-hit AOV ------------------------------------------------------------------------
@@ -1569,7 +1832,7 @@ __global__ void __launch_bounds__(kThreads, 2) primary_kernel(const PassArgs a, 
         }
         float t;
         uint32_t prim;
-        const bool hit = nearest<ALL, false>(S, live, o, d, t, prim); // all 32 lanes walk together
+        const bool hit = nearest<ALL, false, 1>(S, live, o, d, t, prim); // all 32 lanes walk together
         if (lp < n) {
             int32_t id = -1;
             double px = DBL_MAX, py = DBL_MAX, pz = DBL_MAX, nx = 0, ny = 0, nz = 0; // a miss looks like REF's (ref_visibility_kernel)
@@ -1784,8 +2047,12 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
     } else {
         const int occ = a.raygen_occ; // tuning knob
         // 3 CTAs per SM at 80 registers (68 bytes of spills) beat 2 at 95: 23.8 vs 26.4 ms per 66 M camera rays
-        void (*kernel)(PassArgs) = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true> : raygen_extend_kernel<3, true>)
-                                               : (occ == 2 ? raygen_extend_kernel<2, false> : raygen_extend_kernel<3, false>);
+        void (*kernel)(PassArgs);
+        if (a.walk == 2) kernel = a.coop_leaf ? raygen_extend_kernel<3, true, 2> : raygen_extend_kernel<3, false, 2>;
+        else if (a.walk == 1) kernel = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true, 1> : raygen_extend_kernel<3, true, 1>)
+                                                   : (occ == 2 ? raygen_extend_kernel<2, false, 1> : raygen_extend_kernel<3, false, 1>);
+        else kernel = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true, 0> : raygen_extend_kernel<3, true, 0>)
+                                  : (occ == 2 ? raygen_extend_kernel<2, false, 0> : raygen_extend_kernel<3, false, 0>);
         grid = persistent_grid(kernel, smem, sm_count);
         e = launch_pdl(kernel, grid, smem, s, a);
     }
@@ -1794,7 +2061,10 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
 
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a);
-    void (*kernel)(PassArgs, int) = a.coop_leaf ? trace_kernel<true> : trace_kernel<false>;
+    void (*kernel)(PassArgs, int);
+    if (a.walk == 2) kernel = a.coop_leaf ? trace_kernel<true, 2> : trace_kernel<false, 2>;
+    else if (a.walk == 1) kernel = a.coop_leaf ? trace_kernel<true, 1> : trace_kernel<false, 1>;
+    else kernel = a.coop_leaf ? trace_kernel<true, 0> : trace_kernel<false, 0>;
     const int grid = persistent_grid(kernel, smem, sm_count);
     cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);
     if (e != cudaSuccess) note_launch_error("trace kernel launch", e, smem, grid);

@@ -23,6 +23,8 @@
 // line/triangle tests against triangles derived from the child's min/max
 // (including its p4 = -p3 construction bug), derived on the fly in registers
 // rather than stored (168 B x 12 per node would dwarf the 64 B node record).
+#include <algorithm>
+
 #include "kernels.h"
 
 #include <cfloat>
@@ -76,58 +78,95 @@ __device__ __forceinline__ Tri tri_load(const RefTriD* __restrict__ t) {
     return r;
 }
 
-// ImpTriangle(p1,p2,p3) derived members, entities.h:138-148
-__device__ __forceinline__ Tri tri_make(D3 p1, D3 p2, D3 p3) {
-    Tri r;
-    r.p1 = p1; r.p2 = p2; r.p3 = p3;
-    D3 e1 = p2 - p1, e2 = p3 - p1;
-    r.n = unit(cross3(e1, e2));
-    r.pos = 0.5 * (0.5 * (p1 + p2) + p3);
-    r.e1x = float(e1.x); r.e1y = float(e1.y); r.e1z = float(e1.z);
-    r.e2x = float(e2.x); r.e2y = float(e2.y); r.e2z = float(e2.z);
-    return r;
-}
-
 // glm::length(d) < 1e-3 without paying for the sqrt in the common case.
 __device__ __forceinline__ bool shorter_than_eps(D3 d) {
     double q = dot3(d, d);
     return (q < 1.0e-5) && (sqrt(q) < 1.0e-3);
 }
 
-// ImpTriangle::intersect, entities.h:150-249. `facing` = normal as returned.
-__device__ __forceinline__ bool tri_hit(const Tri& t, D3 o, D3 dir, D3& point, D3& facing) {
-    double nd = dot3(t.n, dir);
-    if (nd == 0) return false;
+// The inside test of ImpTriangle::intersect (entities.h:182-237) decides with a LOOSE threshold: the three
+// unit normals d_i = normalize(cross(p_i - p, p_j - p)) must pairwise agree to |d_i - d_j|^2 < 1e-3. For a point
+// inside the triangle the d_i are equal (|d_i - d_j|^2 ~ 1e-30), outside two of them are opposite (~4); only
+// within ~1e-3 of an edge does the value come anywhere near the threshold. Three FP64 square roots and three
+// FP64 divisions per test (the normalisations) are therefore almost always spent on a foregone conclusion.
+// inside_verdict() decides from the UN-normalised cross products when the conclusion is safe:
+//     |d1 - d2|^2 = 2 - 2 cos,  cos = (c1 . c2) / sqrt(|c1|^2 |c2|^2);   < 1e-3  <=>  cos > 1 - 5e-4
+// and returns "undecided" whenever cos is within 5e-7 of that bound (a million times the rounding error of the
+// exact evaluation), or a cross product is degenerate / not finite -- then the caller runs the reference's own
+// arithmetic. Every hit boolean is still the reference's, bit for bit (tests/test_ref_gpu.py probes 20 000 rays
+// per entity class, and whole frames at 1080p against the compiled reference).
+__device__ __forceinline__ int inside_verdict(D3 c1, D3 c2, D3 c3) { // 1 inside, 0 outside, -1 undecided
+    const double n1 = dot3(c1, c1), n2 = dot3(c2, c2), n3 = dot3(c3, c3);
+    if (!(n1 > 1.0e-200 && n2 > 1.0e-200 && n3 > 1.0e-200 && n1 < 1.0e200 && n2 < 1.0e200 && n3 < 1.0e200)) return -1;
+    const double s12 = dot3(c1, c2), s23 = dot3(c2, c3);
+    const double k = (1.0 - 5.0e-4) * (1.0 - 5.0e-4), k_hi = k + 1.0e-6, k_lo = k - 1.0e-6;
+    const double q12 = s12 * s12, q23 = s23 * s23, m12 = n1 * n2, m23 = n2 * n3;
+    const bool yes12 = s12 > 0 && q12 > k_hi * m12, no12 = s12 <= 0 || q12 < k_lo * m12;
+    const bool yes23 = s23 > 0 && q23 > k_hi * m23, no23 = s23 <= 0 || q23 < k_lo * m23;
+    if (no12 || no23) return 0;   // c1 && c2 is false as soon as one of them certainly is
+    if (yes12 && yes23) return 1;
+    return -1;
+}
+
+// the reference's own evaluation (dead `length < eps` branches kept: they fire only through NaNs)
+__device__ __noinline__ bool inside_exact(D3 c1, D3 c2, D3 c3) {
+    D3 d1 = unit(c1), d2 = unit(c2), d3 = unit(c3);
+    if (shorter_than_eps(d1) || shorter_than_eps(d2) || shorter_than_eps(d3)) return true;
+    D3 a = d1 - d2, b = d2 - d3;
+    bool c1ok = sqr(a.x) + sqr(a.y) + sqr(a.z) < 1.0e-3;
+    bool c2ok = sqr(b.x) + sqr(b.y) + sqr(b.z) < 1.0e-3;
+    return c1ok && c2ok;
+}
+
+// where the ray's LINE meets the triangle's plane: the float solve of entities.h:154-166
+__device__ __forceinline__ D3 plane_point(float e1x, float e1y, float e1z, float e2x, float e2y, float e2z, D3 pos, D3 o, D3 dir) {
     // A = transpose(mat3(edge1, edge2, -dir)) in float; only row 2 of inverse(A) is consumed
     float m02 = float(-dir.x), m12 = float(-dir.y), m22 = float(-dir.z);
-    float m00 = t.e1x, m10 = t.e1y, m20 = t.e1z;
-    float m01 = t.e2x, m11 = t.e2y, m21 = t.e2z;
+    float m00 = e1x, m10 = e1y, m20 = e1z;
+    float m01 = e2x, m11 = e2y, m21 = e2z;
     float det = +m00 * (m11 * m22 - m21 * m12) - m10 * (m01 * m22 - m21 * m02) + m20 * (m01 * m12 - m11 * m02);
     float ood = 1.0f / det;
     float i20 = +(m10 * m21 - m20 * m11) * ood;
     float i21 = -(m00 * m21 - m20 * m01) * ood;
     float i22 = +(m00 * m11 - m10 * m01) * ood;
-    D3 rhs = o - t.pos;
+    D3 rhs = o - pos;
     float vx = float(rhs.x), vy = float(rhs.y), vz = float(rhs.z);
     float solz = i20 * vx + i21 * vy + i22 * vz;
-    D3 p = o + double(solz) * dir;
+    return o + double(solz) * dir;
+}
 
-    D3 d1 = unit(cross3(t.p1 - p, t.p2 - p));
-    D3 d2 = unit(cross3(t.p2 - p, t.p3 - p));
-    D3 d3 = unit(cross3(t.p3 - p, t.p1 - p));
-    bool hit;
-    if (shorter_than_eps(d1) || shorter_than_eps(d2) || shorter_than_eps(d3)) {
-        hit = true;
-    } else {
-        D3 a = d1 - d2, b = d2 - d3;
-        bool c1 = sqr(a.x) + sqr(a.y) + sqr(a.z) < 1.0e-3;
-        bool c2 = sqr(b.x) + sqr(b.y) + sqr(b.z) < 1.0e-3;
-        hit = c1 && c2;
-    }
+// ImpTriangle::intersect, entities.h:150-249. `facing` = normal as returned.
+__device__ __forceinline__ bool tri_hit(const Tri& t, D3 o, D3 dir, D3& point, D3& facing) {
+    double nd = dot3(t.n, dir);
+    if (nd == 0) return false;
+    D3 p = plane_point(t.e1x, t.e1y, t.e1z, t.e2x, t.e2y, t.e2z, t.pos, o, dir);
+    D3 c1 = cross3(t.p1 - p, t.p2 - p), c2 = cross3(t.p2 - p, t.p3 - p), c3 = cross3(t.p3 - p, t.p1 - p);
+    const int verdict = inside_verdict(c1, c2, c3);
+    const bool hit = verdict < 0 ? inside_exact(c1, c2, c3) : verdict != 0;
     if (!hit) return false;
     point = p;
     facing = (nd < 0) ? t.n : -t.n; // dot(ray.dir, normal) < 0 -- same products, same sum
     return true;
+}
+
+// The same test for a face triangle of a node box (octree.h:141-146 builds an ExpBox per child per ray and keeps
+// only the boolean): the members ImpTriangle derives at construction (entities.h:138-148) are computed here, and
+// the normal is only normalised when its product with the direction is too close to zero to call.
+__device__ __forceinline__ bool node_tri_hit(D3 p1, D3 p2, D3 p3, D3 o, D3 dir) {
+    D3 e1 = p2 - p1, e2 = p3 - p1;
+    D3 n = cross3(e1, e2);
+    // reference: dot(normalize(n), dir) == 0 -> no hit. The normalisation scales the three products by one factor
+    // (relative error 1e-16 each), so a sum that is clearly non-zero stays non-zero.
+    const double tx = n.x * dir.x, ty = n.y * dir.y, tz = n.z * dir.z;
+    const double nd_un = tx + ty + tz;
+    if (!(fabs(nd_un) > 1.0e-9 * (fabs(tx) + fabs(ty) + fabs(tz)))) {
+        if (dot3(unit(n), dir) == 0) return false;
+    }
+    D3 pos = 0.5 * (0.5 * (p1 + p2) + p3);
+    D3 p = plane_point(float(e1.x), float(e1.y), float(e1.z), float(e2.x), float(e2.y), float(e2.z), pos, o, dir);
+    D3 c1 = cross3(p1 - p, p2 - p), c2 = cross3(p2 - p, p3 - p), c3 = cross3(p3 - p, p1 - p);
+    const int verdict = inside_verdict(c1, c2, c3);
+    return verdict < 0 ? inside_exact(c1, c2, c3) : verdict != 0;
 }
 
 // ImpSphere::intersect, entities.h:53-96
@@ -209,27 +248,31 @@ __device__ bool entity_hit(const RefSceneD& s, int ei, D3 o, D3 dir, D3& point, 
 
 // ExpBox(min,max).intersect(ray) as a boolean (octree.h:141-146). The twelve
 // triangles are those of entities.h:399-406 with ExpRectangle's p4 = 0+(0-p3).
-__device__ bool node_box_hit(const RefNodeD* __restrict__ nd, D3 o, D3 dir) {
+// One of them: face f (0..5), `second` = the (p1, p2, p4) triangle of that face's ExpRectangle.
+__device__ __forceinline__ bool node_face_tri_hit(const RefNodeD* __restrict__ nd, int f, bool second, D3 o, D3 dir) {
     const D3 mn = ld3(nd->mn), mx = ld3(nd->mx);
-    const D3 origin = mk(0, 0, 0);
+    // faces: (dlb,urb,ulb) (dlb,ult,dlt) (dlb,drt,dlt) (urt,ulb,ult) (urt,drb,drt) (urt,dlt,drt)
+    D3 p1 = (f < 3) ? mn : mx, p2, p3;
+    switch (f) {
+    case 0: p2 = mk(mx.x, mn.y, mx.z); p3 = mk(mn.x, mn.y, mx.z); break;
+    case 1: p2 = mk(mn.x, mx.y, mx.z); p3 = mk(mn.x, mx.y, mn.z); break;
+    case 2: p2 = mk(mx.x, mx.y, mn.z); p3 = mk(mn.x, mx.y, mn.z); break;
+    case 3: p2 = mk(mn.x, mn.y, mx.z); p3 = mk(mn.x, mx.y, mx.z); break;
+    case 4: p2 = mk(mx.x, mn.y, mn.z); p3 = mk(mx.x, mx.y, mn.z); break;
+    default: p2 = mk(mn.x, mx.y, mn.z); p3 = mk(mx.x, mx.y, mn.z); break;
+    }
+    if (second) {
+        const D3 origin = mk(0, 0, 0);
+        p3 = origin + (origin - p3); // p4
+    }
+    return node_tri_hit(p1, p2, p3, o, dir);
+}
+
+__device__ bool node_box_hit(const RefNodeD* __restrict__ nd, D3 o, D3 dir) {
 #pragma unroll 1
     for (int f = 0; f < 6; ++f) {
-        // faces: (dlb,urb,ulb) (dlb,ult,dlt) (dlb,drt,dlt) (urt,ulb,ult) (urt,drb,drt) (urt,dlt,drt)
-        D3 p1 = (f < 3) ? mn : mx, p2, p3;
-        switch (f) {
-        case 0: p2 = mk(mx.x, mn.y, mx.z); p3 = mk(mn.x, mn.y, mx.z); break;
-        case 1: p2 = mk(mn.x, mx.y, mx.z); p3 = mk(mn.x, mx.y, mn.z); break;
-        case 2: p2 = mk(mx.x, mx.y, mn.z); p3 = mk(mn.x, mx.y, mn.z); break;
-        case 3: p2 = mk(mn.x, mn.y, mx.z); p3 = mk(mn.x, mx.y, mx.z); break;
-        case 4: p2 = mk(mx.x, mn.y, mn.z); p3 = mk(mx.x, mx.y, mn.z); break;
-        default: p2 = mk(mn.x, mx.y, mn.z); p3 = mk(mx.x, mx.y, mn.z); break;
-        }
-        D3 pt, nn;
-        Tri t = tri_make(p1, p2, p3);
-        if (tri_hit(t, o, dir, pt, nn)) return true;
-        D3 p4 = origin + (origin - p3);
-        t = tri_make(p1, p2, p4);
-        if (tri_hit(t, o, dir, pt, nn)) return true;
+        if (node_face_tri_hit(nd, f, false, o, dir)) return true;
+        if (node_face_tri_hit(nd, f, true, o, dir)) return true;
     }
     return false;
 }
@@ -293,12 +336,12 @@ __device__ int trace_front(const RefSceneD& s, D3 o, D3 dir, D3& point, D3& norm
     return -1;
 }
 
-__global__ void __launch_bounds__(128) ref_visibility_kernel(RefSceneD s, RefCamera cam, TileMap map,
+__global__ void __launch_bounds__(128) ref_visibility_kernel(RefSceneD s, RefCamera cam, TileMap map, int lp0, int lp1,
                                                              int32_t* __restrict__ ids, double* __restrict__ points,
                                                              double* __restrict__ normals,
                                                              unsigned long long* __restrict__ counters) {
-    int lp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lp >= map.n_local_pix) return;
+    int lp = lp0 + blockIdx.x * blockDim.x + threadIdx.x; // the band [lp0, lp1) of this rank's local pixels
+    if (lp >= lp1) return;
     int x, y;
     unsigned node_tests = 0, prim_tests = 0;
     int id = -1;
@@ -321,6 +364,126 @@ __global__ void __launch_bounds__(128) ref_visibility_kernel(RefSceneD s, RefCam
             prim_tests += __shfl_xor_sync(0xffffffffu, prim_tests, off);
         }
         if ((threadIdx.x & 31) == 0) {
+            atomicAdd(counters + 0, (unsigned long long)node_tests);
+            atomicAdd(counters + 1, (unsigned long long)prim_tests);
+        }
+    }
+}
+
+// ---- one WARP per ray -----------------------------------------------------------------------------
+// What the capture of ref_visibility_kernel on the 1 002 528-entity heightfield showed (profiles/r02a_ref_visibility_ncu.json):
+// 2.44 s for 518 400 rays, but only 5.6 G warp instructions at 1.54 of 32 lanes, warps active 3.6 % of the time -- the
+// AVERAGE ray costs ~40 triangle tests, a handful of rays walk thousands of nodes of the reference's entity-losing
+// tree with twelve FP64 triangle tests per child, and the frame waits for the longest serial chain. The work of one
+// ray parallelises perfectly: the 8 x 12 face triangles of a node's children are independent tests (octree.h:141-146
+// only keeps the boolean) and so are the entities of a leaf list (the LAST hit wins, raytracer.h:58: the highest list
+// position among the hits). So a warp takes one ray: 96 node-triangle tests in three passes of 32 lanes, leaf lists
+// 32 entities at a time from the back. Same device functions, same visiting order (children 7 -> 0, stack of
+// unvisited hit children), so the ids, points and normals are the thread-per-ray kernel's, bit for bit.
+__device__ int trace_front_warp(const RefSceneD& s, D3 o, D3 dir, D3& point, D3& normal, int* st_node, int* st_mask,
+                                unsigned& node_tests, unsigned& prim_tests) {
+    const unsigned lane = threadIdx.x & 31u;
+    int level = 0;
+    if (lane == 0) { st_node[0] = 0; st_mask[0] = -1; }
+    __syncwarp();
+    while (level >= 0) {
+        const RefNodeD* __restrict__ nd = s.nodes + st_node[level];
+        const int first = nd->first_child;
+        if (first < 0) { // leaf: its entity list from the back, 32 at a time; the first hit met is the reference's last
+            const int n = nd->ent_count;
+            const int32_t* __restrict__ list = s.ents + nd->ent_offset;
+            for (int base = 0; base < n; base += 32) {
+                const int k = n - 1 - (base + int(lane));
+                bool h = false;
+                D3 p = mk(0, 0, 0), nn = mk(0, 0, 0);
+                int ei = -1;
+                if (k >= 0) {
+                    ei = list[k];
+                    h = entity_hit(s, ei, o, dir, p, nn, prim_tests);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, h);
+                if (m) {
+                    const int src = __ffs(int(m)) - 1;
+                    point = mk(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src), __shfl_sync(0xffffffffu, p.z, src));
+                    normal = mk(__shfl_sync(0xffffffffu, nn.x, src), __shfl_sync(0xffffffffu, nn.y, src), __shfl_sync(0xffffffffu, nn.z, src));
+                    return __shfl_sync(0xffffffffu, ei, src);
+                }
+            }
+            --level;
+            continue;
+        }
+        int mask = st_mask[level];
+        __syncwarp();
+        if (mask < 0) { // the box tests of this node's non-empty children: 8 x 12 triangle tests over the lanes
+            unsigned found = 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+                const int t = pass * 32 + int(lane);
+                const int c = t / 12, tri = t - 12 * c;
+                const RefNodeD* __restrict__ ch = s.nodes + first + c;
+                bool h = false;
+                if (ch->ent_count != 0) {
+                    if (tri == 0) ++node_tests;
+                    h = node_face_tri_hit(ch, tri >> 1, (tri & 1) != 0, o, dir);
+                }
+                found |= __reduce_or_sync(0xffffffffu, h ? (1u << c) : 0u);
+            }
+            mask = int(found);
+        }
+        if (mask == 0) {
+            --level;
+            continue;
+        }
+        const int c = 31 - __clz(mask); // children 7 -> 0: the reverse of the reference's DFS
+        __syncwarp();
+        if (lane == 0) {
+            st_mask[level] = mask & ~(1 << c);
+            if (level + 1 < kMaxRefDepth) {
+                st_node[level + 1] = first + c;
+                st_mask[level + 1] = -1;
+            }
+        }
+        __syncwarp();
+        if (level + 1 < kMaxRefDepth) ++level;
+    }
+    return -1;
+}
+
+constexpr int kRefWarps = 4; // warps per CTA of the warp-per-ray kernel
+__global__ void __launch_bounds__(kRefWarps * 32) ref_visibility_warp_kernel(RefSceneD s, RefCamera cam, TileMap map, int lp0, int lp1,
+                                                                            int32_t* __restrict__ ids, double* __restrict__ points,
+                                                                            double* __restrict__ normals,
+                                                                            unsigned long long* __restrict__ counters) {
+    __shared__ int st_node[kRefWarps][kMaxRefDepth];
+    __shared__ int st_mask[kRefWarps][kMaxRefDepth];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * kRefWarps;
+    unsigned node_tests = 0, prim_tests = 0;
+    for (int lp = lp0 + blockIdx.x * kRefWarps + wib; lp < lp1; lp += n_warps) {
+        int x, y;
+        int id = -1;
+        D3 point = mk(DBL_MAX, DBL_MAX, DBL_MAX), normal = mk(0, 0, 0);
+        if (local_to_pixel(map, lp, x, y)) {
+            D3 o = ld3(cam.pos);
+            D3 dir = pixel_dir(cam, x, y);
+            id = trace_front_warp(s, o, dir, point, normal, st_node[wib], st_mask[wib], node_tests, prim_tests);
+            if (id < 0) { point = mk(DBL_MAX, DBL_MAX, DBL_MAX); normal = mk(0, 0, 0); }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            ids[lp] = id;
+            if (points) {
+                points[lp] = point.x; points[map.n_local_pix + lp] = point.y; points[2 * (size_t)map.n_local_pix + lp] = point.z;
+                normals[lp] = normal.x; normals[map.n_local_pix + lp] = normal.y; normals[2 * (size_t)map.n_local_pix + lp] = normal.z;
+            }
+        }
+    }
+    if (counters) {
+        for (int off = 16; off > 0; off >>= 1) {
+            node_tests += __shfl_xor_sync(0xffffffffu, node_tests, off);
+            prim_tests += __shfl_xor_sync(0xffffffffu, prim_tests, off);
+        }
+        if (lane == 0) {
             atomicAdd(counters + 0, (unsigned long long)node_tests);
             atomicAdd(counters + 1, (unsigned long long)prim_tests);
         }
@@ -439,13 +602,13 @@ __device__ D3 blinn_phong_texture(D3 color, D3 dir, D3 light, D3 ip, D3 normal, 
     return mk(std_min(out.x, 1.0), std_min(out.y, 1.0), std_min(out.z, 1.0));
 }
 
-__global__ void __launch_bounds__(128) ref_shade_kernel(RefSceneD s, RefCamera cam, TileMap map,
+__global__ void __launch_bounds__(128) ref_shade_kernel(RefSceneD s, RefCamera cam, TileMap map, int lp0, int lp1,
                                                         const int32_t* __restrict__ ids,
                                                         const double* __restrict__ points,
                                                         const double* __restrict__ normals, uint8_t* __restrict__ rgb,
                                                         float* __restrict__ colour) {
-    int lp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lp >= map.n_local_pix) return;
+    int lp = lp0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= lp1) return;
     int x, y;
     D3 c = mk(0, 0, 0);
     int id = ids[lp];
@@ -591,17 +754,26 @@ inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; 
 } // namespace
 
 void launch_ref_visibility(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, int32_t* ids,
-                           double* points, double* normals, unsigned long long* counters, cudaStream_t stream) {
-    if (map.n_local_pix == 0) return;
-    ref_visibility_kernel<<<blocks_for(map.n_local_pix, 128), 128, 0, stream>>>(scene, cam, map, ids, points, normals,
-                                                                                 counters);
+                           double* points, double* normals, unsigned long long* counters, cudaStream_t stream, int lp0,
+                           int lp1) {
+    if (lp1 < 0) lp1 = map.n_local_pix;
+    if (lp1 <= lp0) return;
+    if (scene.n_nodes > 1) { // the tree has split: one warp per ray (node tests and leaf lists spread over the lanes)
+        const int blocks = std::min(blocks_for(lp1 - lp0, kRefWarps), 148 * 16);
+        ref_visibility_warp_kernel<<<blocks, kRefWarps * 32, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals, counters);
+        return;
+    }
+    ref_visibility_kernel<<<blocks_for(lp1 - lp0, 128), 128, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals,
+                                                                           counters);
 }
 
 void launch_ref_shade(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, const int32_t* ids,
-                      const double* points, const double* normals, uint8_t* rgb, float* colour, cudaStream_t stream) {
-    if (map.n_local_pix == 0) return;
-    ref_shade_kernel<<<blocks_for(map.n_local_pix, 128), 128, 0, stream>>>(scene, cam, map, ids, points, normals, rgb,
-                                                                            colour);
+                      const double* points, const double* normals, uint8_t* rgb, float* colour, cudaStream_t stream,
+                      int lp0, int lp1) {
+    if (lp1 < 0) lp1 = map.n_local_pix;
+    if (lp1 <= lp0) return;
+    ref_shade_kernel<<<blocks_for(lp1 - lp0, 128), 128, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals, rgb,
+                                                                      colour);
 }
 
 void launch_probe_intersect(const RefSceneD& scene, int32_t entity, int n, const double* origins, const double* dirs,

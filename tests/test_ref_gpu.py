@@ -152,3 +152,39 @@ def test_empty_and_errors(g19, abi):
     rt.stop()
     assert not rt.running()
     assert (rt.run(8, 8)["rgb"] == 0).all()  # run() before start(): nothing renders (raytracer.h:32)
+
+
+def test_ref_banded_render_refresh_and_cancel(g19, abi):
+    """The reference polls _running per pixel and fills its Image row by row (raytracer.h:32-33): on a heavy scene the
+    host-pointer entry points render REF mode in bands of tile rows -- same pixels as the single launch, progress and
+    refreshes in between, and a cancel leaves the rows not reached black."""
+    import torch
+    w, h = 640, 352  # 20 x 11 tiles
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_HEIGHTFIELD_ROOM, n=64, w=w, h=h)  # 8206 entities: "heavy"
+    rt = g19.RayTracer(cam, light)
+    rt.setScene(sc)
+    rt.start()
+    banded = rt.run(w, h, want=("rgb", "ids"))
+    d_ids = torch.zeros(h * w, dtype=torch.int32, device="cuda")
+    d_rgb = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda")
+    rt.run_device(rt.params(w, h), d_rgb=d_rgb.data_ptr(), d_ids=d_ids.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(banded["ids"].ravel(), d_ids.cpu().numpy())      # one launch == bands
+    assert np.array_equal(banded["rgb"].ravel(), d_rgb.cpu().numpy())
+    assert (banded["ids"] >= 0).mean() > 0.9
+    seen = []
+
+    def on_pass(fraction, rgb):
+        seen.append((fraction, int((rgb.reshape(h, w, 3).max(2) > 0).any(1).sum())))  # rows with something in them
+        return len(seen) >= 3  # cancel at the third refresh
+
+    part = rt.run_progressive(w, h, on_pass, min_interval_ms=0, mode=abi.MODE_REF)
+    assert len(seen) >= 3
+    fr = [f for f, _ in seen]
+    assert fr[0] < fr[1] < fr[2] < 1.0 or fr[-1] < 1.0
+    rows = [r for _, r in seen]
+    assert rows[0] < rows[1] < rows[2] <= h
+    filled = (part["rgb"].max(2) > 0).any(1)
+    assert 0 < filled.sum() < h and not filled[-32:].any()                  # the last tile row was never reached
+    top = filled.sum() // 32 * 32 - 32
+    assert np.array_equal(part["rgb"][:top], banded["rgb"][:top])           # what was rendered is the same image
