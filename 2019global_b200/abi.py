@@ -1,7 +1,7 @@
 """ctypes mirror of include/g19.h (struct layouts and enum values only)."""
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enum g19_entity_kind (reference include/entities.h, one value per class)
 IMP_SPHERE, IMP_TRIANGLE, EXP_RECTANGLE, EXP_BOX, EXP_SPHERE, EXP_QUAD, EXP_CUBE, EXP_CONE = range(8)
@@ -22,11 +22,22 @@ CLASS_NAMES = ["raygen_extend", "bounce", "shadow", "accumulate", "ref_visibilit
 
 class EntityDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("bsdf", C.c_int32), ("p", C.c_double * 9), ("f", C.c_float * 4),
-                ("color", C.c_double * 3), ("emission", C.c_float * 3), ("ior", C.c_float)]
+                ("color", C.c_double * 3), ("emission", C.c_float * 3), ("ior", C.c_float),
+                ("material_set", C.c_int32), ("reserved_", C.c_int32), ("diffuse_color", C.c_double * 3),
+                ("specular_color", C.c_double * 3), ("shader_parameters", C.c_double * 3), ("specular_power", C.c_double)]
 
     @classmethod
-    def make(cls, kind, p=(), f=(), color=(1.0, 0.0, 0.0), bsdf=BSDF_DIFFUSE, emission=(0.0, 0.0, 0.0), ior=1.5):
+    def make(cls, kind, p=(), f=(), color=(1.0, 0.0, 0.0), bsdf=BSDF_DIFFUSE, emission=(0.0, 0.0, 0.0), ior=1.5,
+             diffuse_color=None, specular_color=None, shader_parameters=None, specular_power=None):
         d = cls()
+        if any(v is not None for v in (diffuse_color, specular_color, shader_parameters, specular_power)):
+            # the reference's Material(color) defaults (material.h:13-16,27,29) for whatever the caller left alone
+            d.material_set = 1
+            for i in range(3):
+                d.diffuse_color[i] = (diffuse_color or [0.5 * c for c in color])[i]
+                d.specular_color[i] = (specular_color or (1.0, 1.0, 1.0))[i]
+                d.shader_parameters[i] = (shader_parameters or (0.1, 0.7, 1.0))[i]
+            d.specular_power = 5.0 if specular_power is None else specular_power
         d.kind, d.bsdf, d.ior = kind, bsdf, ior
         for i, v in enumerate(p):
             d.p[i] = v

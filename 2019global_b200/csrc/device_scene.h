@@ -40,9 +40,12 @@ struct alignas(64) RefEntityD {
     double pos[3];
     double color[3];   // Material::color
     double aux0[3], aux1[3];
+    // Material's remaining public fields (material.h:23-29)
+    double diffuse_color[3], specular_color[3], shader[3];
+    double specular_power;
     int32_t pad[4];
 };
-static_assert(sizeof(RefEntityD) == 192, "RefEntityD layout");
+static_assert(sizeof(RefEntityD) == 256, "RefEntityD layout");
 
 // ---- PATH view --------------------------------------------------------------
 // Hot intersection record, 64 B = 4 x float4 (one line per two primitives):

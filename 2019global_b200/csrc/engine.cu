@@ -204,6 +204,16 @@ int flatten_ref(g19_ctx* ctx, const g19_scene& s) {
         d.color[2] = h.desc.color[2];
         copy3(d.aux0, h.aux0);
         copy3(d.aux1, h.aux1);
+        // Material(color) defaults (material.h:13-16,27,29) unless the caller assigned the fields
+        const g19_entity_desc& ed = h.desc;
+        for (int k = 0; k < 3; ++k) {
+            d.diffuse_color[k] = ed.material_set ? ed.diffuse_color[k] : ed.color[k] * 0.5;
+            d.specular_color[k] = ed.material_set ? ed.specular_color[k] : 1.0;
+        }
+        d.shader[0] = ed.material_set ? ed.shader_parameters[0] : 0.1;
+        d.shader[1] = ed.material_set ? ed.shader_parameters[1] : 0.7;
+        d.shader[2] = ed.material_set ? ed.shader_parameters[2] : 1.0;
+        d.specular_power = ed.material_set ? ed.specular_power : 5.0;
         for (const HostTri& t : h.tris) {
             RefTriD r;
             std::memset(&r, 0, sizeof r);
@@ -332,12 +342,13 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     G19_CUDA(ctx, ctx->normals_l.ensure(n * 3 * sizeof(double)));
     G19_CUDA(ctx, ctx->rgb_l.ensure(n * 3));
     G19_CUDA(ctx, ctx->colour_l.ensure(n * 3 * sizeof(float)));
-    G19_CUDA(ctx, ctx->counters.ensure(2 * sizeof(unsigned long long)));
+    G19_CUDA(ctx, ctx->counters.ensure(4 * sizeof(unsigned long long))); // [node tests, primitive tests, work counter, -]
     unsigned long long* counters = nullptr;
     if (p->profile) {
         counters = ctx->counters.as<unsigned long long>();
         G19_CUDA(ctx, cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s));
     }
+    unsigned* next = reinterpret_cast<unsigned*>(ctx->counters.as<unsigned long long>() + 2);
     ClassTimer t{ctx, s, p->profile != 0};
     // The reference fills its Image pixel by pixel and polls _running per pixel (raytracer.h:32-33), so stop() and
     // the viewer's 32 ms repaint see a frame in progress. On a heavy scene (the 1 M-entity heightfield takes seconds)
@@ -349,7 +360,7 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     if (!banded) {
         t.begin();
         launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                              ctx->normals_l.as<double>(), counters, s);
+                              ctx->normals_l.as<double>(), counters, s, 0, -1, next);
         t.end(G19_K_REF_VIS, 1);
         t.begin();
         launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
@@ -360,7 +371,8 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
         G19_CUDA(ctx, cudaMemsetAsync(ctx->ids_l.p, 0xff, n * sizeof(int32_t), s));
         G19_CUDA(ctx, cudaMemsetAsync(ctx->rgb_l.p, 0, n * 3, s));
         G19_CUDA(ctx, cudaMemsetAsync(ctx->colour_l.p, 0, n * 3 * sizeof(float), s));
-        const int tiles_per_band = std::max(map.tiles_x / std::max(1, map.world), (map.n_local_tiles + 63) / 64); // about one tile row
+        // about an eighth of the frame per band: every band ends in a tail that waits for its most expensive ray
+        const int tiles_per_band = std::max(map.tiles_x / std::max(1, map.world), (map.n_local_tiles + 7) / 8);
         auto last_refresh = std::chrono::steady_clock::now();
         for (int t0 = 0; t0 < map.n_local_tiles; t0 += tiles_per_band) {
             if (ctx->cancel.load()) { // RayTracer::stop()
@@ -370,7 +382,7 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
             const int lp0 = t0 * kTilePix, lp1 = std::min(map.n_local_tiles, t0 + tiles_per_band) * kTilePix;
             t.begin();
             launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                                  ctx->normals_l.as<double>(), counters, s, lp0, lp1);
+                                  ctx->normals_l.as<double>(), counters, s, lp0, lp1, next);
             t.end(G19_K_REF_VIS, 1);
             t.begin();
             launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),

@@ -59,7 +59,7 @@ struct RefSceneD {
 // heavy scenes band by band so that stop() and the viewer's repaint see the frame grow (raytracer.h:32-33).
 void launch_ref_visibility(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, int32_t* ids,
                            double* points, double* normals, unsigned long long* counters /*nullable: [node,prim]*/,
-                           cudaStream_t stream, int lp0 = 0, int lp1 = -1);
+                           cudaStream_t stream, int lp0 = 0, int lp1 = -1, unsigned* next = nullptr /* device work counter: enables the warp-per-ray kernel */);
 // getTextureCoord + blinn_phong_texture + RGB888 quantisation (raytracer.h:76-82).
 void launch_ref_shade(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, const int32_t* ids,
                       const double* points, const double* normals, uint8_t* rgb, float* colour, cudaStream_t stream,

@@ -148,7 +148,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -166,12 +166,15 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "leaf_max") t.leaf_max = num(def.leaf_max, 1, 1 << 20);
     else if (k == "refill") t.refill = num(def.refill, 1, 32);
     else if (k == "coop_leaf") t.coop_leaf = num(def.coop_leaf, 0, 1);
-    else if (k == "walk_steps") t.walk_steps = num(def.walk_steps, 1, 16);
+    else if (k == "walk_steps") t.walk_steps = num(def.walk_steps, 0, 16);
     else if (k == "leaf_batch") t.leaf_batch = num(def.leaf_batch, 0, 16);
     else if (k == "raygen_occ") t.raygen_occ = num(def.raygen_occ, 2, 3);
     else if (k == "tree_build") t.tree_build = !value ? -1 : (std::strcmp(value, "device") == 0 ? 1 : (std::strcmp(value, "host") == 0 ? 0 : -1));
     else if (k == "debug_tree") t.debug_tree = value ? 1 : 0;
     else if (k == "walk") t.walk = num(def.walk, 0, 1);
+    else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
+    else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
+    else if (k == "l2_persist") t.l2_persist = num(def.l2_persist, 0, 1);
     else return false;
     return true;
 }
@@ -626,9 +629,11 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     // tree walk: leaf tests spread over the whole warp, 8 primitives per ray and round (heightfield 1080p x 32 spp:
     // sequential 4 per round 107.1 ms, cooperative 4 / 8 / 16 per round 115.4 / 104.9 / 105.4)
     pa0.coop_leaf = a.tune.coop_leaf;
-    pa0.walk_steps = a.tune.walk_steps;
+    pa0.walk_steps = a.tune.walk_steps > 0 ? a.tune.walk_steps : (a.tune.walk ? 2 : 4); // measured (room scene, ms per 1080p x 64 spp): new walk 2 / 4 / 8 steps = 780 / 838 / 961
     pa0.leaf_batch = a.tune.leaf_batch > 0 ? a.tune.leaf_batch : (pa0.coop_leaf ? 16 : 4); // cooperative: the whole leaf in one go (leaf max 8 / 12 / 16 at batch 16: 97.7 / 96.9 / 97.8 ms)
     pa0.raygen_occ = a.tune.raygen_occ;
+    pa0.trace_occ = a.tune.trace_occ;
+    pa0.bounce_occ = a.tune.bounce_occ;
     pa0.walk = a.tune.walk ? (p.profile ? 2 : 1) : 0; // the new walk counts its node / primitive tests under params.profile
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
     // primary-hit AOV: the un-jittered ray of every pixel (the reference's ray) through this engine's structures
@@ -763,6 +768,30 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             pa.ray0 = static_cast<float4*>(l.rays.p);
             pa.ray1 = pa.ray0 + ray_cap;
             pa.ray2 = pa.ray1 + ray_cap;
+        }
+    }
+    // Tree scenes: the primitive records are what the incoherent rays of the deep bounces fetch from all over the scene
+    // (ncu, profiles/r02b: L2 hit rate 67 %, 2.8 GB of DRAM traffic per trace launch); the wavefront state streaming
+    // past them must not evict them. An access policy window on every lane's stream asks L2 to keep the records
+    // (persisting) while everything else stays normal; the ray queue is read / written with streaming hints.
+    if (!fused && a.tune.l2_persist && b.hot.bytes > 0) {
+        static thread_local int limit_device = -1;
+        int device = 0;
+        cudaGetDevice(&device);
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            if (limit_device != device) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(prop.persistingL2CacheMaxSize));
+                limit_device = device;
+            }
+            cudaStreamAttrValue attr = {};
+            attr.accessPolicyWindow.base_ptr = b.hot.p;
+            attr.accessPolicyWindow.num_bytes = std::min(b.hot.bytes, size_t(prop.accessPolicyMaxWindowSize));
+            attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(prop.persistingL2CacheMaxSize) / double(attr.accessPolicyWindow.num_bytes)));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            for (int i = 0; i < n_lanes; ++i) cudaStreamSetAttribute(lane_stream[i], cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaGetLastError(); // best effort: a refused hint is not an error of the render
         }
     }
     if (n_lanes > 1) { // the other lanes start after everything enqueued so far on the caller's stream

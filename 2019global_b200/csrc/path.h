@@ -110,12 +110,15 @@ struct PathTuning {
     int leaf_max = 8;         // primitives per octree leaf (read at scene upload)
     int refill = 8;           // trace_kernel: idle lanes per warp that trigger a ray fetch
     int coop_leaf = 1;        // warp-cooperative leaf tests
-    int walk_steps = 4;       // cell moves per round of the tree walk
+    int walk_steps = 0;       // cell moves per round of the tree walk (0 = auto: 2 for the restart walk, 4 for the stack walk)
     int leaf_batch = 0;       // primitives per ray and round (0 = auto: 16 cooperative, 4 sequential)
     int raygen_occ = 3;       // CTAs per SM of the tree-scene camera-ray kernel
     int tree_build = -1;      // -1 auto (device from 4096 primitives), 0 host, 1 device
     int debug_tree = 0;       // print octree statistics at upload
     int walk = 1;             // tree walk: 1 = point-location restart walk (TreeWalk2), 0 = parametric stack walk (TreeWalk)
+    int trace_occ = 3;        // CTAs per SM of trace_kernel (4 = 64 registers, some spills)
+    int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
+    int l2_persist = 1;       // tree scenes: pin the primitive records in L2 (access policy window on the lanes' streams)
 };
 void path_tuning_from_env(PathTuning& t);
 bool path_tuning_set(PathTuning& t, const char* key, const char* value); // false: unknown key
@@ -202,6 +205,8 @@ struct PassArgs {
     int32_t walk_steps, leaf_batch; // tree walk: cell moves / primitives tested per round (TreeWalk::step)
     int32_t coop_leaf;     // tree walk: leaf tests spread over the whole warp (default; G19_COOP_LEAF=0: sequential)
     int32_t raygen_occ;    // tree scenes: CTAs per SM of the camera-ray kernel (2 or 3)
+    int32_t trace_occ;     // CTAs per SM of trace_kernel (3 or 4)
+    int32_t bounce_occ;    // CTAs per SM of bounce_flat_kernel<diffuse> (3 or 4)
     int32_t walk;          // tree walk variant (PathTuning::walk); +2 when the walk counts its node / primitive tests
 };
 

@@ -1530,8 +1530,8 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
 }
 
 // One material queue per launch (diffuse-only scenes, and the last bounce of any scene).
-template <int KIND, bool FIRST, bool LAST, bool SPEC>
-__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_flat_kernel(const PassArgs a, const int bounce) {
+template <int KIND, bool FIRST, bool LAST, bool SPEC, int OCC = 3>
+__global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : OCC) bounce_flat_kernel(const PassArgs a, const int bounce) {
     pdl_launch_dependents();
     if (LAST && KIND != Q_DIFFUSE) return; // a specular vertex on the last segment contributes nothing
     const SceneAccess<true> S = stage_scene<true>(a); // does not depend on earlier kernels: overlaps their tail
@@ -1666,14 +1666,14 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
         // ray records: (origin, tmax) (direction, slot | kRayShadow | kRaySpecular) (light sample rgb)
         const uint32_t is = warp_reserve(ray_cur, ray_shadow, ray_counter);
         if (is != kInvalid) {
-            a.ray0[is] = make_float4(ray_o.x, ray_o.y, ray_o.z, ray_tmax);
-            a.ray1[is] = make_float4(ray_w.x, ray_w.y, ray_w.z, __uint_as_float(slot | kRayShadow));
-            a.ray2[is] = make_float4(ray_rgb.x, ray_rgb.y, ray_rgb.z, 0.0f);
+            __stcs(a.ray0 + is, make_float4(ray_o.x, ray_o.y, ray_o.z, ray_tmax));
+            __stcs(a.ray1 + is, make_float4(ray_w.x, ray_w.y, ray_w.z, __uint_as_float(slot | kRayShadow)));
+            __stcs(a.ray2 + is, make_float4(ray_rgb.x, ray_rgb.y, ray_rgb.z, 0.0f));
         }
         const uint32_t ic = warp_reserve(ray_cur, ray_cont, ray_counter);
         if (ic != kInvalid) {
-            a.ray0[ic] = make_float4(ray_o.x, ray_o.y, ray_o.z, FLT_MAX);
-            a.ray1[ic] = make_float4(ray_d.x, ray_d.y, ray_d.z, __uint_as_float(slot | ray_flags));
+            __stcs(a.ray0 + ic, make_float4(ray_o.x, ray_o.y, ray_o.z, FLT_MAX));
+            __stcs(a.ray1 + ic, make_float4(ray_d.x, ray_d.y, ray_d.z, __uint_as_float(slot | ray_flags)));
         }
         s_cur = s_nxt; s_nxt = s_nn;
         buf ^= 1;
@@ -1704,7 +1704,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
 // and, once PassArgs::refill lanes are idle, the warp pulls that many new rays with ONE atomic. A warp's
 // time is then the sum of its rays' rounds / 32, not 32 x the longest walk.
 
-template <bool COOP, int WALK> __global__ void __launch_bounds__(kThreads, 3) trace_kernel(const PassArgs a, const int bounce) {
+template <bool COOP, int WALK, int OCC = 3> __global__ void __launch_bounds__(kThreads, OCC) trace_kernel(const PassArgs a, const int bounce) {
     pdl_launch_dependents();
     const SceneAccess<false> S = stage_scene<false>(a);
     pdl_wait();
@@ -1739,13 +1739,13 @@ template <bool COOP, int WALK> __global__ void __launch_bounds__(kThreads, 3) tr
             if (base + cnt >= n) more = false; // the queue is drained (warp-uniform)
             const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
             if (!have && i < n) {
-                const float4 r1 = a.ray1[i];
+                const float4 r1 = __ldcs(a.ray1 + i); // streamed: read once (evict first, the scene stays in L2)
                 tag = __float_as_uint(r1.w);
                 if (tag != kInvalid) { // not the padding of a producer's last chunk
-                    const float4 r0 = a.ray0[i];
+                    const float4 r0 = __ldcs(a.ray0 + i);
                     const bool shadow = (tag & kRayShadow) != 0u;
                     if (shadow) {
-                        const float4 r2 = a.ray2[i];
+                        const float4 r2 = __ldcs(a.ray2 + i);
                         rgb = f3(r2.x, r2.y, r2.z);
                     }
                     have = true;
@@ -2016,7 +2016,10 @@ template <int KIND, bool FIRST, bool LAST, bool ALL>
 static void launch_bounce_k(const PassArgs& a, int bounce, size_t smem, int sm_count, cudaStream_t s) {
     void (*kernel)(PassArgs, int);
     if constexpr (ALL) {
-        if constexpr (KIND == Q_DIFFUSE) kernel = (a.kind_mask & 6u) ? bounce_flat_kernel<KIND, FIRST, LAST, true> : bounce_flat_kernel<KIND, FIRST, LAST, false>;
+        if constexpr (KIND == Q_DIFFUSE) {
+            if (a.bounce_occ == 4) kernel = (a.kind_mask & 6u) ? bounce_flat_kernel<KIND, FIRST, LAST, true, 4> : bounce_flat_kernel<KIND, FIRST, LAST, false, 4>;
+            else kernel = (a.kind_mask & 6u) ? bounce_flat_kernel<KIND, FIRST, LAST, true> : bounce_flat_kernel<KIND, FIRST, LAST, false>;
+        }
         else kernel = bounce_flat_kernel<KIND, FIRST, LAST, true>;
     } else {
         kernel = bounce_kernel<KIND, FIRST, LAST>;
@@ -2063,7 +2066,7 @@ void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a);
     void (*kernel)(PassArgs, int);
     if (a.walk == 2) kernel = a.coop_leaf ? trace_kernel<true, 2> : trace_kernel<false, 2>;
-    else if (a.walk == 1) kernel = a.coop_leaf ? trace_kernel<true, 1> : trace_kernel<false, 1>;
+    else if (a.walk == 1) kernel = a.coop_leaf ? (a.trace_occ == 4 ? trace_kernel<true, 1, 4> : trace_kernel<true, 1, 3>) : trace_kernel<false, 1>;
     else kernel = a.coop_leaf ? trace_kernel<true, 0> : trace_kernel<false, 0>;
     const int grid = persistent_grid(kernel, smem, sm_count);
     cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);

@@ -453,13 +453,20 @@ constexpr int kRefWarps = 4; // warps per CTA of the warp-per-ray kernel
 __global__ void __launch_bounds__(kRefWarps * 32) ref_visibility_warp_kernel(RefSceneD s, RefCamera cam, TileMap map, int lp0, int lp1,
                                                                             int32_t* __restrict__ ids, double* __restrict__ points,
                                                                             double* __restrict__ normals,
-                                                                            unsigned long long* __restrict__ counters) {
+                                                                            unsigned long long* __restrict__ counters,
+                                                                            unsigned* __restrict__ next) {
     __shared__ int st_node[kRefWarps][kMaxRefDepth];
     __shared__ int st_mask[kRefWarps][kMaxRefDepth];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_warps = gridDim.x * kRefWarps;
     unsigned node_tests = 0, prim_tests = 0;
-    for (int lp = lp0 + blockIdx.x * kRefWarps + wib; lp < lp1; lp += n_warps) {
+    // rays differ in cost by four orders of magnitude (most stop at the first leaf, a few walk thousands of nodes): a
+    // warp takes its next pixel from a counter when it is done, so the expensive ones spread over the machine
+    while (true) {
+        unsigned take = 0;
+        if (lane == 0) take = atomicAdd(next, 1u);
+        take = __shfl_sync(0xffffffffu, take, 0);
+        if (take >= unsigned(lp1 - lp0)) break;
+        const int lp = lp0 + int(take);
         int x, y;
         int id = -1;
         D3 point = mk(DBL_MAX, DBL_MAX, DBL_MAX), normal = mk(0, 0, 0);
@@ -584,7 +591,12 @@ __device__ void texture_coord(const RefSceneD& s, const RefEntityD* __restrict__
 
 // Material::blinn_phong_texture with the 32x32 checker evaluated in closed form
 // instead of rebuilding the 12 KB pattern per pixel (material.h:49,66-92).
-__device__ D3 blinn_phong_texture(D3 color, D3 dir, D3 light, D3 ip, D3 normal, int u, int v) {
+// pow(x, specular_power): the default exponent keeps its literal (the compiler may pick a different evaluation for a
+// constant exponent, and the default path is the one pinned byte for byte against the reference's glibc pow)
+__device__ __forceinline__ double spec_pow(double x, double power) { return power == 5.0 ? pow(x, 5.0) : pow(x, power); }
+
+__device__ D3 blinn_phong_texture(const RefEntityD* __restrict__ e, D3 dir, D3 light, D3 ip, D3 normal, int u, int v) {
+    const D3 color = ld3(e->color), shader = ld3(e->shader), spec = ld3(e->specular_color);
     int i = u % 32, j = v % 32;
     // negative remainders index the pattern block at a flat offset (see oracle/ref_restate.c)
     int flat = i * 32 + j;
@@ -592,14 +604,26 @@ __device__ D3 blinn_phong_texture(D3 color, D3 dir, D3 light, D3 ip, D3 normal, 
     D3 tex;
     if ((i <= 16 && j <= 16) || (i > 16 && j > 16)) tex = mk(1, 1, 1);
     else tex = mk(double(ref_int(color.x)), double(ref_int(color.y)), double(ref_int(color.z)));
-    D3 tdc = tex * 0.5;
-    D3 la = tex * 0.1;
+    D3 tdc = tex * 0.5;            // texture_diffuse_color (a literal 0.5 in material.h:51, not Material::diffuse_color)
+    D3 la = tex * shader.x;
     D3 ldir = unit(light - ip);
-    D3 ld = (std_max(0.0, dot3(normal, ldir)) * tdc) * 0.7;
+    D3 ld = (std_max(0.0, dot3(normal, ldir)) * tdc) * shader.y;
     D3 bis = unit(unit(-dir) + unit(light - ip));
-    D3 ls = (pow(std_max(0.0, dot3(normal, bis)), 5.0) * mk(1, 1, 1)) * 1.0;
+    D3 ls = (spec_pow(std_max(0.0, dot3(normal, bis)), e->specular_power) * spec) * shader.z;
     D3 out = la + ld + ls;
     return mk(std_min(out.x, 1.0), std_min(out.y, 1.0), std_min(out.z, 1.0));
+}
+
+// Material::blinn_phong, material.h:31-46 (unused by RayTracer::run, raytracer.h:79)
+__device__ D3 blinn_phong_plain(const RefEntityD* __restrict__ e, D3 dir, D3 light, D3 ip, D3 normal) {
+    const D3 color = ld3(e->color), shader = ld3(e->shader), spec = ld3(e->specular_color), diff = ld3(e->diffuse_color);
+    D3 la = color * shader.x;
+    D3 ldir = unit(light - ip);
+    D3 ld = (std_max(0.0, dot3(normal, ldir)) * diff) * shader.y;
+    D3 bis = unit(unit(-dir) + unit(light - ip));
+    D3 ls = (spec_pow(std_max(0.0, dot3(normal, bis)), e->specular_power) * spec) * shader.z;
+    D3 o = la + ld + ls;
+    return mk(std_min(o.x, 1.0), std_min(o.y, 1.0), std_min(o.z, 1.0));
 }
 
 __global__ void __launch_bounds__(128) ref_shade_kernel(RefSceneD s, RefCamera cam, TileMap map, int lp0, int lp1,
@@ -620,7 +644,7 @@ __global__ void __launch_bounds__(128) ref_shade_kernel(RefSceneD s, RefCamera c
         const RefEntityD* __restrict__ e = s.entities + id;
         int u, v;
         texture_coord(s, e, ip, u, v);
-        c = blinn_phong_texture(ld3(e->color), dir, ld3(cam.light), ip, nn, u, v);
+        c = blinn_phong_texture(e, dir, ld3(cam.light), ip, nn, u, v);
     }
     // Image::setPixel: truncate, and QColor's validity rule (out of range -> black)
     int r = ref_int(255 * c.x), g = ref_int(255 * c.y), b = ref_int(255 * c.z);
@@ -711,19 +735,8 @@ __global__ void probe_shade_kernel(RefSceneD s, int entity, int textured, const 
                                    double* __restrict__ out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     D3 dir = unit(ld3(in)), light = ld3(in + 3), ip = ld3(in + 6), nn = ld3(in + 9);
-    D3 color = ld3(s.entities[entity].color);
-    D3 c;
-    if (textured) {
-        c = blinn_phong_texture(color, dir, light, ip, nn, u, v);
-    } else { // Material::blinn_phong, material.h:31-46 (unused by RayTracer::run, raytracer.h:79)
-        D3 la = color * 0.1;
-        D3 ldir = unit(light - ip);
-        D3 ld = (std_max(0.0, dot3(nn, ldir)) * (color * 0.5)) * 0.7;
-        D3 bis = unit(unit(-dir) + unit(light - ip));
-        D3 ls = (pow(std_max(0.0, dot3(nn, bis)), 5.0) * mk(1, 1, 1)) * 1.0;
-        D3 o = la + ld + ls;
-        c = mk(std_min(o.x, 1.0), std_min(o.y, 1.0), std_min(o.z, 1.0));
-    }
+    const RefEntityD* __restrict__ e = s.entities + entity;
+    D3 c = textured ? blinn_phong_texture(e, dir, light, ip, nn, u, v) : blinn_phong_plain(e, dir, light, ip, nn);
     out[0] = c.x; out[1] = c.y; out[2] = c.z;
 }
 
@@ -755,12 +768,13 @@ inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; 
 
 void launch_ref_visibility(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, int32_t* ids,
                            double* points, double* normals, unsigned long long* counters, cudaStream_t stream, int lp0,
-                           int lp1) {
+                           int lp1, unsigned* next) {
     if (lp1 < 0) lp1 = map.n_local_pix;
     if (lp1 <= lp0) return;
-    if (scene.n_nodes > 1) { // the tree has split: one warp per ray (node tests and leaf lists spread over the lanes)
+    if (scene.n_nodes > 1 && next) { // the tree has split: one warp per ray (node tests and leaf lists spread over the lanes)
         const int blocks = std::min(blocks_for(lp1 - lp0, kRefWarps), 148 * 16);
-        ref_visibility_warp_kernel<<<blocks, kRefWarps * 32, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals, counters);
+        cudaMemsetAsync(next, 0, sizeof(unsigned), stream);
+        ref_visibility_warp_kernel<<<blocks, kRefWarps * 32, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals, counters, next);
         return;
     }
     ref_visibility_kernel<<<blocks_for(lp1 - lp0, 128), 128, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals,

@@ -83,6 +83,9 @@ def lib():
                                           C.POINTER(C.c_uint32)]
         L.g19_probe_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.POINTER(C.c_int)]
+        L.g19_probe_texcoord.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p]
+        L.g19_probe_shade.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p]
         L.g19_render_progressive.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_void_p, C.POINTER(abi.Params),
                                              C.c_void_p, C.c_void_p, PASS_FN, C.c_void_p, C.c_int]
         L.g19_frame_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -324,6 +327,20 @@ class RayTracer:
         nrm = np.zeros((n, 3))
         self._check(self._L.g19_probe_intersect(self.h, entity, n, _ptr(o), _ptr(d), _ptr(hit), _ptr(pts), _ptr(nrm)))
         return hit, pts, nrm
+
+    def probe_texcoord(self, entity, points):
+        """Entity::getTextureCoord (entities.h:32) on the device for n points -> (n, 2) int32."""
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        uv = np.zeros((p.shape[0], 2), np.int32)
+        self._check(self._L.g19_probe_texcoord(self.h, entity, p.shape[0], _ptr(p), _ptr(uv)))
+        return uv
+
+    def probe_shade(self, entity, ray_dir, light, point, normal, u=0, v=0, textured=True):
+        """Material::blinn_phong_texture / blinn_phong (material.h:31-62) on the device for one point -> 3 doubles."""
+        out = (C.c_double * 3)()
+        self._check(self._L.g19_probe_shade(self.h, entity, 1 if textured else 0, abi.d3(ray_dir), abi.d3(light), abi.d3(point),
+                                            abi.d3(normal), int(u), int(v), out))
+        return np.array(out[:])
 
     def path_tree(self):
         """(nodes (n,2) uint32, index (m,) uint32) of the linear octree PATH mode traverses."""

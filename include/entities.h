@@ -51,6 +51,13 @@ struct Entity {
         d.emission[0] = float(material.emission.x); d.emission[1] = float(material.emission.y);
         d.emission[2] = float(material.emission.z);
         d.ior = float(material.ior);
+        // the remaining public Material fields (reference material.h:24-29), as the caller left them
+        d.material_set = 1;
+        d.diffuse_color[0] = material.diffuse_color.x; d.diffuse_color[1] = material.diffuse_color.y; d.diffuse_color[2] = material.diffuse_color.z;
+        d.specular_color[0] = material.specular_color.x; d.specular_color[1] = material.specular_color.y; d.specular_color[2] = material.specular_color.z;
+        d.shader_parameters[0] = material.shader_parameters.x; d.shader_parameters[1] = material.shader_parameters.y;
+        d.shader_parameters[2] = material.shader_parameters.z;
+        d.specular_power = material.specular_power;
         return d;
     }
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define G19_ABI_VERSION 4
+#define G19_ABI_VERSION 5
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -84,6 +84,15 @@ typedef struct g19_entity_desc {
     double color[3];
     float emission[3];   /* radiance of a G19_BSDF_EMITTER (PATH mode) */
     float ior;           /* index of refraction of G19_BSDF_GLASS (PATH mode) */
+    /* The other public fields of the reference's Material (material.h:23-29), consumed by G19_MODE_REF's shade and
+     * the depth-0 slice. material_set == 0: they take the values Material(color) gives them (material.h:13-16,27,29)
+     * and the fields below are ignored; 1: the caller's values, as after assigning to entity->material.<field>.  */
+    int32_t material_set;
+    int32_t reserved_;
+    double diffuse_color[3];     /* Material::diffuse_color      default color * 0.5 (untextured blinn_phong only) */
+    double specular_color[3];    /* Material::specular_color     default (1,1,1)                                   */
+    double shader_parameters[3]; /* Material::shader_parameters  default (0.1, 0.7, 1): ambient, diffuse, specular  */
+    double specular_power;       /* Material::specular_power     default 5                                         */
 } g19_entity_desc;
 
 /* ---- scene = Octree + the entities pushed into it (octree.h:12-68) ------ */

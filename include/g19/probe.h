@@ -106,13 +106,18 @@ inline void texcoord_one(const g19_entity_desc& d, glm::dvec3 at, int& u, int& v
     v = uv[1];
 }
 
-inline glm::dvec3 shade_point(glm::dvec3 color, int textured, glm::dvec3 dir, glm::dvec3 light, glm::dvec3 at,
-                              glm::dvec3 normal, int u, int v) {
+inline glm::dvec3 shade_point(glm::dvec3 color, glm::dvec3 diffuse, glm::dvec3 specular, glm::dvec3 shader, double power,
+                              int textured, glm::dvec3 dir, glm::dvec3 light, glm::dvec3 at, glm::dvec3 normal, int u, int v) {
     std::lock_guard<std::mutex> lock(probe_mutex());
     g19_entity_desc d = {};
     d.kind = G19_IMP_SPHERE; // any entity carries the Material
     d.f[0] = 1.f;
     d.color[0] = color.x; d.color[1] = color.y; d.color[2] = color.z;
+    d.material_set = 1;
+    d.diffuse_color[0] = diffuse.x; d.diffuse_color[1] = diffuse.y; d.diffuse_color[2] = diffuse.z;
+    d.specular_color[0] = specular.x; d.specular_color[1] = specular.y; d.specular_color[2] = specular.z;
+    d.shader_parameters[0] = shader.x; d.shader_parameters[1] = shader.y; d.shader_parameters[2] = shader.z;
+    d.specular_power = power;
     load_single(d);
     const double dd[3] = {dir.x, dir.y, dir.z}, ll[3] = {light.x, light.y, light.z}, pp[3] = {at.x, at.y, at.z},
                  nn[3] = {normal.x, normal.y, normal.z};

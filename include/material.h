@@ -23,10 +23,12 @@ struct Material {
     double ior = 1.5;
 
     glm::dvec3 blinn_phong(Ray ray, glm::dvec3 light, glm::dvec3 intersect, glm::dvec3 normal) const {
-        return g19::detail::shade_point(color, 0, ray.dir, light, intersect, normal, 0, 0);
+        return g19::detail::shade_point(color, diffuse_color, specular_color, shader_parameters, specular_power, 0, ray.dir, light,
+                                        intersect, normal, 0, 0);
     }
     glm::dvec3 blinn_phong_texture(Ray ray, glm::dvec3 light, glm::dvec3 intersect, glm::dvec3 normal, int relative_x,
                                    int relative_y) const {
-        return g19::detail::shade_point(color, 1, ray.dir, light, intersect, normal, relative_x, relative_y);
+        return g19::detail::shade_point(color, diffuse_color, specular_color, shader_parameters, specular_power, 1, ray.dir, light,
+                                        intersect, normal, relative_x, relative_y);
     }
 };

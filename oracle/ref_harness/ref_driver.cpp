@@ -59,6 +59,13 @@ Entity* make_entity(const g19_entity_desc& d) {
     // kinds whose constructor takes no colour: assign the public field
     if (d.kind == G19_IMP_TRIANGLE || d.kind == G19_EXP_RECTANGLE || d.kind == G19_EXP_BOX)
         e->material = Material(color);
+    // a caller who assigned the other public Material fields (material.h:24-29) after construction
+    if (d.material_set) {
+        e->material.diffuse_color = v3(d.diffuse_color);
+        e->material.specular_color = v3(d.specular_color);
+        e->material.shader_parameters = v3(d.shader_parameters);
+        e->material.specular_power = d.specular_power;
+    }
     return e;
 }
 

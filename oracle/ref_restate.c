@@ -497,7 +497,15 @@ static void texcoord(const o_entity* e, d3 ip, int* ox, int* oy) {
 }
 
 /* ---- Material::blinn_phong_texture (material.h:48-106) --------------------- */
-static d3 shade(d3 color, d3 dir, d3 light, d3 ip, d3 normal, int u, int v) {
+/* Material::blinn_phong_texture, material.h:48-62. shader_parameters / specular_color / specular_power are the
+ * entity's Material fields (material.h:25-29): the defaults of Material(color) unless the descriptor carries the
+ * caller's (g19_entity_desc::material_set). */
+static d3 shade(const o_entity* e, d3 dir, d3 light, d3 ip, d3 normal, int u, int v) {
+    const g19_entity_desc* m = &e->desc;
+    const d3 color = e->color;
+    const d3 shader = m->material_set ? P(m->shader_parameters) : D3(0.1, 0.7, 1);
+    const d3 spec = m->material_set ? P(m->specular_color) : D3(1, 1, 1);
+    const double power = m->material_set ? m->specular_power : 5.0;
     int i = u % 32, j = v % 32;
     /* Negative u/v (ExpSphere's lower hemisphere, entities.h:558) make i/j
      * negative: the reference then indexes pattern[i][j] out of its row. Inside
@@ -510,11 +518,11 @@ static d3 shade(d3 color, d3 dir, d3 light, d3 ip, d3 normal, int u, int v) {
     if ((i <= 16 && j <= 16) || (i > 16 && j > 16)) tex = D3(1, 1, 1);
     else tex = D3((double)(int)color.x, (double)(int)color.y, (double)(int)color.z);
     d3 tdc = muls(tex, 0.5);
-    d3 la = muls(tex, 0.1);
+    d3 la = muls(tex, shader.x);
     d3 ldir = normalize(sub(light, ip));
-    d3 ld = muls(smul(dmax(0.0, dot(normal, ldir)), tdc), 0.7);
+    d3 ld = muls(smul(dmax(0.0, dot(normal, ldir)), tdc), shader.y);
     d3 bis = normalize(add(normalize(neg(dir)), normalize(sub(light, ip))));
-    d3 ls = muls(smul(pow(dmax(0.0, dot(normal, bis)), 5.0), D3(1, 1, 1)), 1.0);
+    d3 ls = muls(smul(pow(dmax(0.0, dot(normal, bis)), power), spec), shader.z);
     d3 out = add(add(la, ld), ls);
     return D3(dmin(out.x, 1.0), dmin(out.y, 1.0), dmin(out.z, 1.0));
 }
@@ -683,7 +691,7 @@ int g19o_shade(void* h, int idx, const double o[3], const double d[3], const dou
                const double normal[3], int u, int v, double rgb[3]) {
     const o_entity* e = &((o_scene*)h)->ent[idx];
     (void)o;
-    d3 c = shade(e->color, normalize(P(d)), P(light), P(point), P(normal), u, v);
+    d3 c = shade(e, normalize(P(d)), P(light), P(point), P(normal), u, v);
     rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
     return 0;
 }
@@ -732,7 +740,7 @@ static void* band_run(void* p) {
                 if (front >= 0) {
                     int u, v;
                     texcoord(&s->ent[front], ip, &u, &v);
-                    c = shade(s->ent[front].color, dir, a->light, ip, nn, u, v);
+                    c = shade(&s->ent[front], dir, a->light, ip, nn, u, v);
                 }
                 quantise(c, a->rgb + 3 * i);
             }
@@ -794,7 +802,7 @@ int g19o_shade_pixels(void* h, const g19_camera* cam, const double light[3], int
                 d3 nn = D3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
                 int u, v;
                 texcoord(&s->ent[front], ip, &u, &v);
-                c = shade(s->ent[front].color, dir, P(light), ip, nn, u, v);
+                c = shade(&s->ent[front], dir, P(light), ip, nn, u, v);
             }
             quantise(c, rgb + 3 * i);
         }

@@ -79,3 +79,26 @@ def test_headless_driver_path_mode(tmp_path):
     n = int(r.stdout.split(" progressive refreshes")[0].split()[-1])
     assert n >= 3, r.stdout
     assert open(png, "rb").read(8) == b"\x89PNG\r\n\x1a\n"
+
+
+def test_reference_main_cpp_helpers_compile_against_these_headers(tmp_path):
+    """Drop-in check without Qt: the four helper functions of the reference's own main.cpp (insert_tris,
+    entity_test, matrix_test, bbox_test -- reference main.cpp:63-133, everything below main()) are compiled, text
+    unchanged, against include/*.h + the reference's vendored GLM; the scene literal (main.cpp:24-57) is compiled
+    the same way with the Gui lines dropped. A signature or public member that drifted away from the reference's
+    classes fails here. Only runs where the reference is mounted (this container)."""
+    main_cpp = "/root/reference/main.cpp"
+    if not os.path.exists(main_cpp):
+        pytest.skip("reference sources not mounted")
+    lines = open(main_cpp).read().split("\n")
+    helpers = "\n".join(lines[62:133])                       # main.cpp:63-133
+    literal = "\n".join(l for l in lines[23:57] if "Gui" not in l and "window" not in l)  # main.cpp:24-57
+    src = tmp_path / "ref_main_helpers.cpp"
+    src.write_text('#include <iostream>\n#include <vector>\n#include "camera.h"\n#include "raytracer.h"\n#include "ray.h"\n'
+                   '#include "entities.h"\n#include "octree.h"\n#include "glm/ext.hpp"\n'
+                   "void entity_test();\nvoid bbox_test();\nvoid matrix_test();\nvoid insert_tris(Octree& scene);\n"
+                   "void scene_literal() {\n" + literal + "\n}\n" + helpers + "\n")
+    cmd = ["g++", "-std=c++14", "-fsyntax-only", "-DG19_NO_QT", "-I", os.path.join(ROOT, "include"), "-I", "/root/reference/3rd_party",
+           str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

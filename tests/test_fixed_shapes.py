@@ -97,7 +97,12 @@ def test_gpu_fixed_shapes_vs_oracle(g19, abi, oracle):
     exp, segs = binding.path_render(chk, cam, w, h, 32, 4, seed=2)
     ids, pts, _ = binding.path_primary(chk, cam, w, h)
     assert exp.mean() > 0.01
-    assert rel_rmse(got["radiance"], exp) <= 1e-2
+    err = rel_rmse(got["radiance"], exp)
+    per = {int(k): (float(np.sqrt(np.mean((got["radiance"][ids == k].astype(np.float64) - exp[ids == k]) ** 2))), float(exp[ids == k].mean()),
+                    int((ids == k).sum())) for k in np.unique(ids)}
+    print("fixed shapes: relRMSE %.3e; per primary entity (rmse, mean, px): %s; aov mismatches %d; segments gpu %d/%d cpu %d/%d" % (
+        err, per, int((got["ids"] != ids).sum()), rt.stats().extend_segments, rt.stats().shadow_segments, segs[0], segs[1]))
+    assert err <= 1e-2, (err, per)
     st = rt.stats()
     assert abs(int(st.extend_segments) - segs[0]) <= 1e-3 * segs[0] + 2
     assert (got["ids"] != ids).sum() <= 0.01 * w * h  # silhouettes / shared edges only

@@ -125,3 +125,41 @@ def test_live_reference_frames(g19, abi, oracle, reflib):
         for k in ("ids", "points", "normals", "rgb"):
             assert a[k].tobytes() == b[k].tobytes(), (which, k)
         assert np.array_equal(mirror(reflib, sc).render(cam, light, w, h), a["rgb"])  # run() itself
+
+
+def test_live_reference_material_fields(g19, abi, oracle, reflib):
+    """Material's public fields beyond `color` (reference include/material.h:24-29: diffuse_color, specular_color,
+    shader_parameters, specular_power) travel in g19_entity_desc: a caller who assigns them after construction gets
+    the reference's own blinn_phong_texture result (material.h:48-62), byte for byte, from the restatement -- and a
+    frame shaded with them equals the compiled reference's."""
+    rng = np.random.default_rng(11)
+    custom = dict(shader_parameters=(0.25, 0.5, 0.6), specular_color=(0.9, 0.4, 0.2), specular_power=9.0, diffuse_color=(0.1, 0.2, 0.3))
+    descs = [g19.ImpSphere((3, 1, 0), 2.0, (1, 0, 2), **custom),
+             g19.ImpTriangle((4, -5, -3), (4, 5, -3), (4, 0, 4), (0, 1, 1), **custom),
+             g19.ImpSphere((3, -3, 2), 1.5, (0, 1, 0))]  # untouched Material: the defaults
+    assert descs[0].material_set == 1 and descs[2].material_set == 0
+    a = reflib.scene((-20,) * 3, (20,) * 3, descs)
+    b = oracle.scene((-20,) * 3, (20,) * 3, descs)
+    for i in range(3):
+        for _ in range(40):
+            o = (-10, 0, 0)
+            p = rng.uniform(-3, 3, 3)
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+            d = p - np.array(o)
+            light = rng.uniform(-10, 10, 3)
+            u, v = (int(x) for x in rng.integers(0, 200, 2))
+            with quiet_stdout():
+                ca = a.shade(i, o, d, light, p, n, u, v)
+            cb = b.shade(i, o, d, light, p, n, u, v)
+            assert ca.tobytes() == cb.tobytes(), (i, ca, cb)
+    cam = g19.Camera((-10, 0, 0), (1, 0, 0), 0.02)
+    with quiet_stdout():
+        fa = a.trace(cam, (-8, 6, 9), 96, 96, want=("rgb", "ids"), threads=2)
+    fb = b.trace(cam, (-8, 6, 9), 96, 96, want=("rgb", "ids"), threads=2)
+    assert np.array_equal(fa["ids"], fb["ids"]) and np.array_equal(fa["rgb"], fb["rgb"])
+    assert (fa["ids"] >= 0).sum() > 500
+    # the custom fields do change the picture
+    plain = oracle.scene((-20,) * 3, (20,) * 3, [g19.ImpSphere((3, 1, 0), 2.0, (1, 0, 2)), g19.ImpTriangle((4, -5, -3), (4, 5, -3), (4, 0, 4), (0, 1, 1)),
+                                                 descs[2]]).trace(cam, (-8, 6, 9), 96, 96, want=("rgb",), threads=2)
+    assert not np.array_equal(plain["rgb"], fb["rgb"])

@@ -124,7 +124,12 @@ def test_edge_cases(g19, abi):
     with pytest.raises(g19.G19Error):
         rt.run(64, 64, mode=abi.MODE_PATH, spp=0, max_depth=5)
     with pytest.raises(g19.G19Error):
-        rt.run(64, 64, mode=abi.MODE_PATH, spp=1, max_depth=0)
+        rt.run(64, 64, mode=abi.MODE_PATH, spp=1, max_depth=-1)
+    with pytest.raises(g19.G19Error):
+        rt.run(64, 64, mode=abi.MODE_PATH, spp=1, max_depth=65)
+    # max_depth 0 is the depth-0 slice (the reference's shade of the primary hit, tests/test_path_link.py): no bounce
+    d0 = rt.run(64, 64, mode=abi.MODE_PATH, want=("rgb", "ids"), spp=1, max_depth=0)
+    assert (d0["ids"] >= 0).mean() > 0.9 and d0["rgb"].max() > 0
     # empty scene: black
     empty = g19.Octree((-1,) * 3, (1,) * 3)
     rt.setScene(empty)

@@ -173,10 +173,19 @@ def test_gpu_primary_aov_vs_path_oracle(g19, abi, oracle, which, w, h, n):
     # FP32 vs FP64: only silhouette / shared-edge pixels may differ
     assert neq.sum() <= 0.01 * w * h, int(neq.sum())
     assert not (neq & _interior(ids)).any()
-    exp = binding.shade_pixels(chk, cam, light, ids, pts, nrm)
+    # The GPU's hit point is FP32 (~1e-5 off the FP64 one) and getTextureCoord truncates to an integer checker cell:
+    # where the image grid lines up with the texture grid (the default scene's quad faces the camera head on) whole
+    # rows of pixels sit ON a cell boundary and flip with the last bit. So a pixel is right when it equals the
+    # reference's shade of SOME point within 2e-5 of the oracle's hit point (27 probes: the point and its neighbours).
     same = ~neq & (ids >= 0)
-    d = np.abs(got["rgb"].astype(int) - exp.astype(int)).max(2)
-    assert (d[same] > 1).sum() <= 0.005 * max(1, same.sum()), "%d of %d" % (int((d[same] > 1).sum()), int(same.sum()))
+    best = np.full(ids.shape, 255, np.int64)
+    for dx in (-2e-5, 0.0, 2e-5):
+        for dy in (-2e-5, 0.0, 2e-5):
+            for dz in (-2e-5, 0.0, 2e-5):
+                moved = np.where(ids[..., None] >= 0, pts + np.array([dx, dy, dz]), pts)
+                exp = binding.shade_pixels(chk, cam, light, ids, moved, nrm)
+                best = np.minimum(best, np.abs(got["rgb"].astype(int) - exp.astype(int)).max(2))
+    assert (best[same] > 1).sum() <= 0.002 * max(1, same.sum()), "%d of %d" % (int((best[same] > 1).sum()), int(same.sum()))
 
 
 @pytest.mark.gpu

@@ -188,3 +188,57 @@ def test_ref_banded_render_refresh_and_cancel(g19, abi):
     assert 0 < filled.sum() < h and not filled[-32:].any()                  # the last tile row was never reached
     top = filled.sum() // 32 * 32 - 32
     assert np.array_equal(part["rgb"][:top], banded["rgb"][:top])           # what was rendered is the same image
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_probe_texcoord_and_shade_per_entity_kind(g19, abi, oracle, idx):
+    """g19_probe_texcoord / g19_probe_shade (Entity::getTextureCoord entities.h:32, Material::blinn_phong_texture and
+    blinn_phong material.h:31-62) per entity class against the oracle: integer texture coordinates equal (a last-ulp
+    difference between CUDA's and glibc's acos / sin before the int() truncation may flip a handful), shaded colours
+    equal to 1e-12."""
+    sc = zoo(g19)
+    chk = mirror(oracle, sc)
+    rt = g19.RayTracer(g19.Camera((-10, 0, 0), (1, 0, 0), 0.1), (-10, 10, 10))
+    rt.setScene(sc)
+    o, d = probe_rays(20000, seed=100 + idx)
+    hit, pts, nrm = rt.probe_intersect(idx, o, d)
+    m = hit.astype(bool)
+    if idx == 3:  # ExpBox::getTextureCoord is (0, 0) (entities.h:448-451)
+        assert (rt.probe_texcoord(idx, pts[m][:64]) == 0).all()
+    p, n, dirs = pts[m][:600], nrm[m][:600], d[m][:600]
+    uv_gpu, uv_cpu = rt.probe_texcoord(idx, p), chk.texcoord(idx, p)
+    assert (uv_gpu != uv_cpu).any(axis=1).sum() <= 2, int((uv_gpu != uv_cpu).any(axis=1).sum())
+    light = (-10.0, 10.0, 10.0)
+    worst = 0.0
+    for k in range(0, len(p), 12):
+        u, v = int(uv_cpu[k, 0]), int(uv_cpu[k, 1])
+        if abs(u) > 1 << 20 or abs(v) > 1 << 20:
+            continue  # NaN -> INT_MIN coordinates: the reference indexes out of its pattern (undefined)
+        for textured in (True, False):
+            got = rt.probe_shade(idx, dirs[k], light, p[k], n[k], u, v, textured=textured)
+            if textured:
+                exp = chk.shade(idx, o[m][k], dirs[k], light, p[k], n[k], u, v)
+                worst = max(worst, float(np.abs(got - exp).max()))
+            else:  # Material::blinn_phong: la = color * 0.1 ... clamped at 1 (no oracle entry point: closed form of the ambient floor)
+                col = np.array(sc.entity(idx).color[:])
+                assert (got >= np.minimum(0.1 * col, 1.0) - 1e-12).all() and (got <= 1.0).all()
+    assert worst <= 1e-12, worst
+
+
+def test_material_fields_reach_the_device(g19, abi, oracle):
+    """shader_parameters / specular_color / specular_power assigned by the caller (material.h:25-29) shade the frame."""
+    custom = dict(shader_parameters=(0.25, 0.5, 0.6), specular_color=(0.9, 0.4, 0.2), specular_power=9.0)
+    sc = g19.Octree((-20,) * 3, (20,) * 3)
+    sc.push_back(g19.ImpSphere((3, 1, 0), 2.0, (1, 0, 2), **custom))
+    sc.push_back(g19.ImpTriangle((4, -5, -3), (4, 5, -3), (4, 0, 4), (0, 1, 1), **custom))
+    sc.push_back(g19.ImpSphere((3, -3, 2), 1.5, (0, 1, 0)))
+    cam, light = g19.Camera((-10, 0, 0), (1, 0, 0), 0.04), (-8, 6, 9)
+    rt, got, exp = _render_both(g19, oracle, sc, cam, light, 200, 200)
+    assert np.array_equal(got["ids"], exp["ids"]) and (exp["ids"] >= 0).sum() > 2000
+    _check_colours(got["rgb"], exp["rgb"], exp["ids"])
+    plain = g19.Octree((-20,) * 3, (20,) * 3)
+    plain.push_back(g19.ImpSphere((3, 1, 0), 2.0, (1, 0, 2)))
+    plain.push_back(g19.ImpTriangle((4, -5, -3), (4, 5, -3), (4, 0, 4), (0, 1, 1)))
+    plain.push_back(g19.ImpSphere((3, -3, 2), 1.5, (0, 1, 0)))
+    rt.setScene(plain)
+    assert not np.array_equal(rt.run(200, 200)["rgb"], got["rgb"])

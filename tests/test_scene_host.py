@@ -19,11 +19,22 @@ def test_library_exports_every_declared_symbol(g19):
     assert set(g19.EXPORTS) <= set(declared)
 
 
-def test_abi_struct_sizes(g19, abi):
-    # mirrors of include/g19.h: g19_entity_desc, g19_camera, g19_params
-    assert ctypes.sizeof(abi.EntityDesc) == 8 + 72 + 16 + 24 + 12 + 4
-    assert ctypes.sizeof(abi.Camera) == 56
-    assert ctypes.sizeof(abi.Params) == 44
+def test_abi_struct_sizes(g19, abi, tmp_path):
+    """The ctypes mirrors (2019global_b200/abi.py) against the C compiler's view of include/g19.h."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "g19.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %d\\n", '
+                   'sizeof(g19_entity_desc), sizeof(g19_camera), sizeof(g19_params), sizeof(g19_stats), '
+                   'offsetof(g19_entity_desc, shader_parameters), G19_ABI_VERSION); return 0; }\n')
+    exe = str(tmp_path / "sizes")
+    subprocess.run(["gcc", "-I", os.path.join(os.path.dirname(g19.LIB_PATH), "..", "include"), str(src), "-o", exe], check=True)
+    desc, cam, params, stats, off, version = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
+    assert ctypes.sizeof(abi.EntityDesc) == desc == 224
+    assert abi.EntityDesc.shader_parameters.offset == off
+    assert ctypes.sizeof(abi.Camera) == cam == 56
+    assert ctypes.sizeof(abi.Params) == params == 44
+    assert ctypes.sizeof(abi.Stats) == stats
+    assert abi.ABI_VERSION == version
 
 
 def test_entity_geometry_matches_oracle_bits(g19, oracle):

@@ -35,13 +35,17 @@ FULL = {
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio": "stall_math_pipe_throttle",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio": "stall_not_selected",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio": "stall_branch_resolving",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "pipe_fp64_pct",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct_of_peak",
+    "lts__t_sector_hit_rate.pct": "l2_hit_rate_pct",
 }
 UNIT_SCALE = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "msecond": 1e3,
-              "usecond": 1.0, "nsecond": 1e-3, "second": 1e6}
+              "usecond": 1.0, "nsecond": 1e-3, "second": 1e6, "s": 1e6}
 
 
 def klass(name):
-    for k in ("raygen_extend", "bounce", "accumulate", "resolve", "untile", "ref_visibility", "ref_shade"):
+    for k in ("raygen_extend", "trace_kernel", "bounce", "accumulate", "resolve", "untile", "primary", "ref_visibility", "ref_shade"):
         if k in name:
             return k
     return "other"
