@@ -329,6 +329,7 @@ struct ClassTimer { // CUDA-event timing of one kernel class (params.profile)
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->cls0, ctx->cls1);
         ctx->stats.class_ms[cls] += ms;
+        if (ctx->tune.debug_tree && cls == G19_K_REF_VIS) std::fprintf(stderr, "[g19] REF visibility launch: %.2f ms\n", ms);
     }
 };
 
@@ -346,7 +347,7 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     unsigned long long* counters = nullptr;
     if (p->profile) {
         counters = ctx->counters.as<unsigned long long>();
-        G19_CUDA(ctx, cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s));
+        G19_CUDA(ctx, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), s));
     }
     unsigned* next = reinterpret_cast<unsigned*>(ctx->counters.as<unsigned long long>() + 2);
     ClassTimer t{ctx, s, p->profile != 0};
@@ -419,11 +420,12 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     if (t_rad) G19_CUDA(ctx, cudaMemcpyAsync(t_rad, ctx->colour_l.p, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ctx->stats.samples = 0;
     if (p->profile) {
-        unsigned long long h[2] = {0, 0};
+        unsigned long long h[4] = {0, 0, 0, 0};
         G19_CUDA(ctx, cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, s));
         G19_CUDA(ctx, cudaStreamSynchronize(s));
         ctx->stats.node_tests = h[0];
         ctx->stats.prim_tests = h[1];
+        if (ctx->tune.debug_tree) std::fprintf(stderr, "[g19] REF: the most expensive ray tested %llu child boxes\n", h[3]);
     }
     // in-frame pixels owned by this rank
     uint64_t owned = 0;
@@ -519,10 +521,15 @@ int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene) {
     if (!ctx || !scene) return G19_ERR_INVALID;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->has_scene = false;
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = flatten_ref(ctx, *scene);
     if (rc != G19_OK) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     std::string perr;
     rc = path_upload(ctx->path, *scene, ctx->tune, ctx->stream, perr);
+    if (ctx->tune.debug_tree)
+        std::fprintf(stderr, "[g19] upload: REF view %.1f ms, PATH view %.1f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     if (rc != G19_OK) {
         ctx->err = perr;
         return rc;

@@ -148,7 +148,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -174,6 +174,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "walk") t.walk = num(def.walk, 0, 1);
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
+    else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
     else if (k == "l2_persist") t.l2_persist = num(def.l2_persist, 0, 1);
     else return false;
     return true;
@@ -532,6 +533,21 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     v.n_prims = int32_t(prims.size());
     v.n_lights = int32_t(lights.size());
     v.tree_depth = tree_depth;
+    // direct index over the first levels for the walk's descents (only worth it for a deep tree)
+    v.top = nullptr;
+    v.top_level = std::min(tune.top_level, tree_depth - 2);
+    if (v.top_level >= 3) {
+        cudaError_t te = b.top.ensure((size_t(1) << (3 * v.top_level)) * sizeof(uint2));
+        if (te == cudaSuccess && path_build_top_table(v.nodes, v.top_level, static_cast<uint2*>(b.top.p), stream) == G19_OK &&
+            cudaStreamSynchronize(stream) == cudaSuccess) {
+            v.top = static_cast<const uint2*>(b.top.p);
+        } else {
+            cudaGetLastError();
+            v.top_level = 0;
+        }
+    } else {
+        v.top_level = 0;
+    }
     v.n_par = n_par;
     v.n_tri = n_tri;
     v.pairs = static_cast<const float*>(b.pairs.p);
@@ -545,7 +561,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &w.totals, &w.accum,
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &w.totals, &w.accum,
                            &w.rad_l, &w.rgb_l})
         d->release();
     for (PathLane& l : w.lane) {
@@ -729,7 +745,6 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         PassArgs& pa = lanes[li];
         if (P > l.capacity) {
             PATH_CUDA(l.L.ensure(P * 4 * sizeof(float))); // flat scenes: float4 per slot; tree scenes: three planes
-            PATH_CUDA(l.queues.ensure((P + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
             l.capacity = P;
             PATH_CUDA(cudaMemsetAsync(l.L.p, 0, P * 4 * sizeof(float), s));
             l.L_written_whole = false;
@@ -743,20 +758,25 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         pa.L = static_cast<float*>(l.L.p);
         pa.plane = plane;
         pa.queue_cap = plane + kQueueSlack;
-        for (int k = 0; k < kNumQueues; ++k) pa.q[k] = static_cast<uint32_t*>(l.queues.p) + size_t(k) * pa.queue_cap;
+        pa.spec_cap = 0;
+        for (int k = 0; k < kNumQueues; ++k) pa.q[k] = nullptr;
         pa.counts = static_cast<uint32_t*>(l.counts.p);
         pa.ray0 = pa.ray1 = pa.ray2 = nullptr;
         pa.hp = pa.dw = pa.tp = nullptr;
         pa.rec_ls = pa.rec_hp = pa.rec_dw = pa.rec_tp = nullptr;
         if (fused) {
-            // dense vertex records: four float4 planes per queue
-            const size_t cap = pa.queue_cap, nq = kNumQueues;
-            PATH_CUDA(l.recs.ensure(nq * cap * 4 * sizeof(float4)));
+            // dense vertex records, four float4 planes: per bounce parity the diffuse array and -- only when the scene has
+            // mirror or glass -- the array those two share (a bounce holds at most P vertices over its queues together)
+            pa.spec_cap = (pa0.kind_mask & 6u) ? plane + 2 * kQueueSlack : 0;
+            const size_t per_plane = 2 * (pa.queue_cap + pa.spec_cap);
+            PATH_CUDA(l.recs.ensure(per_plane * 4 * sizeof(float4)));
             pa.rec_ls = static_cast<float4*>(l.recs.p);
-            pa.rec_hp = pa.rec_ls + nq * cap;
-            pa.rec_dw = pa.rec_hp + nq * cap;
-            pa.rec_tp = pa.rec_dw + nq * cap;
+            pa.rec_hp = pa.rec_ls + per_plane;
+            pa.rec_dw = pa.rec_hp + per_plane;
+            pa.rec_tp = pa.rec_dw + per_plane;
         } else {
+            PATH_CUDA(l.queues.ensure((plane + kQueueSlack) * kNumQueues * sizeof(uint32_t)));
+            for (int k = 0; k < kNumQueues; ++k) pa.q[k] = static_cast<uint32_t*>(l.queues.p) + size_t(k) * pa.queue_cap;
             PATH_CUDA(l.hp.ensure(plane * sizeof(float4)));
             PATH_CUDA(l.dw.ensure(plane * sizeof(float4)));
             PATH_CUDA(l.tp.ensure(plane * sizeof(float4)));

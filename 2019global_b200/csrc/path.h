@@ -49,6 +49,8 @@ struct PathSceneD {
     const int32_t* prim_entity; // 2 per primitive: the entity id REF mode would report (both halves of a merged parallelogram)
     float root_lo[3], root_size[3];
     float grid_scale[3];     // 2^kMaxTreeDepth / root_size: world position -> coordinate on the finest octree grid
+    const uint2* top;        // direct index over the first top_level levels (tree_build.cu top_table_kernel), or nullptr
+    int32_t top_level;
 };
 
 struct PathCamera { // float copies of the reference basis (RefCamera)
@@ -63,7 +65,7 @@ struct DeviceArray {
 };
 
 struct PathSceneBuffers {
-    DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity;
+    DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity, top;
     PathSceneD view{};
     bool has_bsdf[4] = {false, false, false, false};
 };
@@ -74,8 +76,8 @@ struct PathLane {
     bool L_written_whole = false; // the last pass on this lane was a flat scene's: L holds its radiance, not zeros
     DeviceArray hp, dw, tp;    // tree scenes: float4[P] vertex state by slot (hit point+primitive, direction+pixel, throughput+sample)
     DeviceArray L;             // radiance of the slot's path: float4[P] (flat scenes) / float[3][P] (tree scenes)
-    DeviceArray queues;        // uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
-    DeviceArray recs;          // flat scenes: float4[4][6][P + slack] dense vertex records
+    DeviceArray queues;        // tree scenes: uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
+    DeviceArray recs;          // flat scenes: float4[4][2][(P + slack) + (P + 2 slack | 0)] dense vertex records
     DeviceArray rays;          // float4[3][2P + slack]: ray queue of one bounce (tree scenes only)
     DeviceArray counts;        // uint32[kMaxPathDepth+1][5]: queue lengths per bounce + ray fetch cursors
 };
@@ -116,9 +118,12 @@ struct PathTuning {
     int tree_build = -1;      // -1 auto (device from 4096 primitives), 0 host, 1 device
     int debug_tree = 0;       // print octree statistics at upload
     int walk = 1;             // tree walk: 1 = point-location restart walk (TreeWalk2), 0 = parametric stack walk (TreeWalk)
-    int trace_occ = 3;        // CTAs per SM of trace_kernel (4 = 64 registers, some spills)
+    int trace_occ = 4;        // CTAs per SM of trace_kernel (4 = 64 registers, 114 bytes of spills: the walk is bound by memory
+                              // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
-    int l2_persist = 1;       // tree scenes: pin the primitive records in L2 (access policy window on the lanes' streams)
+    int top_level = 6;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2)
+    int l2_persist = 0;       // tree scenes: pin the primitive records in L2 (access policy window on the lanes' streams). Measured
+                              // on the room scene: 869 ms with the window, 775 ms without -- the set-aside starves everything else; off
 };
 void path_tuning_from_env(PathTuning& t);
 bool path_tuning_set(PathTuning& t, const char* key, const char* value); // false: unknown key
@@ -160,6 +165,7 @@ struct PathRenderArgs {
 int path_build_tree_device(const float* d_boxes, uint32_t n_prims, const float root_lo[3], const float root_size[3],
                            int leaf_max, int max_depth, cudaStream_t s, PathNodeD** d_nodes, uint32_t* n_nodes,
                            uint32_t** d_index, uint32_t* n_index, int* tree_depth, std::string& err);
+int path_build_top_table(const PathNodeD* d_nodes, int top_level, uint2* d_table, cudaStream_t s);
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err);
 int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err);
 int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err);
@@ -185,10 +191,12 @@ struct PassArgs {
     size_t plane;          // slots per plane (capacity)
     uint32_t* q[6];        // [bounce parity * 3 + (kind - 1)]
     uint32_t kind_mask;    // bit (kind - 1): the scene has a material of that class
-    size_t queue_cap;      // entries per queue (P + chunk slack)
+    size_t queue_cap;      // entries per queue (P + chunk slack); flat scenes: of the diffuse record array
+    size_t spec_cap;       // flat scenes: entries of the array mirror and glass share (P + 2 x slack), 0 = no specular material
     // flat scenes: the queues hold the vertex records themselves (dense, 64 B per vertex) in four float4
-    // planes; queue qi = bounce parity * 3 + (kind - 1) starts at qi * queue_cap in each plane. A padding
-    // entry has slot kInvalid. hp/dw/tp/q above then serve tree scenes only (slot-indexed).
+    // planes of 2 x (queue_cap + spec_cap) entries: per bounce parity the diffuse array, then the array mirror
+    // (upwards) and glass (downwards) share -- path_kernels.cu rec_queue. A padding entry has slot kInvalid.
+    // hp/dw/tp/q above then serve tree scenes only (slot-indexed).
     float4* rec_ls;        // radiance so far, slot
     float4* rec_hp;        // hit point, primitive
     float4* rec_dw;        // incoming direction, pixel

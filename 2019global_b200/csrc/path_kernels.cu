@@ -76,6 +76,18 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
     return v;
 }
 
+// Streaming (evict-first) 16-byte accesses for data that is written once and read once far later (ray queue records).
+// Through INTEGER registers: the records carry slot indices and flags in the bit patterns of their w words, which look
+// like denormals -- the float4 overloads of __ldcs / __stcs are free to flush them (measured: every shadow ray then
+// delivered to slot 0).
+__device__ __forceinline__ void st_stream(float4* p, float x, float y, float z, uint32_t w_bits) {
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), w_bits));
+}
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+
 // ---- Philox4x32-10 (Salmon et al. 2011); identical integer stream in oracle/path_oracle.c
 __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0) {
     uint32_t k1 = 0x32303139u; // "2019"
@@ -784,6 +796,22 @@ template <bool COUNT> struct TreeWalk2 {
             bool desc = walking;
             uint32_t k = lv;
             uint2 rec = make_uint2(0u, kLeafBit);
+            // a descent that would start above the top table's level starts IN the table: one load instead of a
+            // chain of top_level dependent ones
+            const uint32_t top_level = uint32_t(g.top_level);
+            if (desc && k < top_level) {
+                const uint32_t sh = uint32_t(kMaxTreeDepth) - top_level;
+                rec = __ldg(g.top + ((((size_t(Z >> sh) << top_level) | (Y >> sh)) << top_level) | (X >> sh)));
+                if (COUNT) ++n_node;
+                if (rec.y & kLeafBit) {
+                    k = ((rec.y >> 24) & 0xfu) - 1u; // the covering leaf / empty cell sits at that (coarser) level
+                    rec.y &= 0x80ffffffu;
+                    desc = false;
+                } else {
+                    k = top_level;
+                    stack[k * kThreads] = rec.x;
+                }
+            }
             while (__any_sync(kFull, desc)) {
                 if (desc) {
                     const uint32_t sh = uint32_t(kMaxTreeDepth - 1) - k;
@@ -1271,12 +1299,25 @@ __device__ __forceinline__ Shaded shade_vertex(const PassArgs& a, const SceneAcc
 // queue (slot, hit point + primitive, direction + pixel, throughput + sample, radiance so far --
 // 64 bytes, all planes coalesced) and read back from consecutive addresses; the path's radiance
 // travels with it and is stored to the slot's accumulator input exactly once, when the path ends.
-struct RecView { // one queue: four float4 planes
+// A bounce holds at most P vertices over its three material queues together, so the queues of a bounce parity share
+// storage instead of being P entries each (16 GB reserved for a 14-primitive scene): the diffuse queue has
+// an array of its own (P + slack entries), mirror and glass share ONE array of P + 2 x slack entries -- mirror grows
+// from its bottom, glass from its top downwards (entry q of the glass queue lives at top - q: consecutive lanes still
+// touch consecutive 16-byte words). A diffuse-only scene allocates no specular array at all.
+struct RecView { // one queue: four float4 planes; entry q is at plane[q * dir]
     float4 *ls, *hp, *dw, *tp; // (radiance so far | slot) (hit point | primitive) (direction | pixel) (throughput | sample)
+    int dir;
+    __device__ __forceinline__ ptrdiff_t at(uint32_t q) const { return dir > 0 ? ptrdiff_t(q) : -ptrdiff_t(q); }
 };
 __device__ __forceinline__ RecView rec_queue(const PassArgs& a, int qi) { // qi = bounce parity * 3 + (kind - 1)
     RecView r;
-    const size_t off = size_t(qi) * a.queue_cap;
+    const int parity = qi >= 3 ? 1 : 0, kind = qi - 3 * parity;
+    size_t off = size_t(parity) * (a.queue_cap + a.spec_cap);
+    r.dir = 1;
+    if (kind != 0) {
+        off += a.queue_cap;                                      // the shared specular array of this parity
+        if (kind == 2) { off += a.spec_cap - 1; r.dir = -1; }   // glass: from the top, downwards
+    }
     r.ls = a.rec_ls + off;
     r.hp = a.rec_hp + off;
     r.dw = a.rec_dw + off;
@@ -1321,12 +1362,12 @@ template <bool SPEC> struct RecSorter {
 #pragma unroll
         for (int k = 0; k < (SPEC ? 3 : 1); ++k)
             if (mask & (1u << k)) {
-                float4* ls = rec_queue(a, set + k).ls;
+                const RecView r = rec_queue(a, set + k);
                 const WarpCursor& c = cur[k];
-                for (uint32_t i = c.pos + lane; i < c.end; i += 32u) ls[i] = pad;
+                for (uint32_t i = c.pos + lane; i < c.end; i += 32u) r.ls[r.at(i)] = pad;
                 if (c.has_next) { // a chunk reserved ahead of time and never used
                     const uint32_t base = __shfl_sync(kFull, c.next, 0);
-                    for (uint32_t i = lane; i < kChunk; i += 32u) ls[base + i] = pad;
+                    for (uint32_t i = lane; i < kChunk; i += 32u) r.ls[r.at(base + i)] = pad;
                 }
             }
     }
@@ -1376,9 +1417,10 @@ template <bool SPEC> __global__ void __launch_bounds__(kThreads, 4) raygen_exten
         if (pos != kInvalid) { // throughput is 1 and the radiance 0 on the camera segment: not stored
             const RecView r = rec_queue(a, kind);
             const float3 p = o + d * t;
-            r.ls[pos] = make_float4(__uint_as_float(sample), 0.f, 0.f, __uint_as_float(slot)); // radiance is 0 here: x carries the sample index
-            r.hp[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(prim));
-            r.dw[pos] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+            const ptrdiff_t at = r.at(pos);
+            r.ls[at] = make_float4(__uint_as_float(sample), 0.f, 0.f, __uint_as_float(slot)); // radiance is 0 here: x carries the sample index
+            r.hp[at] = make_float4(p.x, p.y, p.z, __uint_as_float(prim));
+            r.dw[at] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
         }
     }
     out.flush(a);
@@ -1399,10 +1441,11 @@ template <bool FULL>
 __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, bool valid, RecStage<FULL>& st, int buf) {
     const int t = threadIdx.x;
     if (valid) {
-        cp_async16(&st.ls[buf][t], r.ls + pos);
-        cp_async16(&st.hp[buf][t], r.hp + pos);
-        cp_async16(&st.dw[buf][t], r.dw + pos);
-        if (FULL) cp_async16(&st.tp[buf][t], r.tp + pos);
+        const ptrdiff_t at = r.at(pos);
+        cp_async16(&st.ls[buf][t], r.ls + at);
+        cp_async16(&st.hp[buf][t], r.hp + at);
+        cp_async16(&st.dw[buf][t], r.dw + at);
+        if (FULL) cp_async16(&st.tp[buf][t], r.tp + at);
     }
     cp_async_commit();
 }
@@ -1506,10 +1549,11 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
             const uint32_t pos = out.reserve(kind_next);
             if (pos != kInvalid) {
                 const RecView r = rec_queue(a, out.set + kind_next);
-                r.ls[pos] = make_float4(Lp.x, Lp.y, Lp.z, __uint_as_float(slot));
-                r.hp[pos] = make_float4(p_next.x, p_next.y, p_next.z, __uint_as_float(prim_next));
-                r.dw[pos] = make_float4(d_next.x, d_next.y, d_next.z, __uint_as_float(pixel));
-                r.tp[pos] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
+                const ptrdiff_t at = r.at(pos);
+                r.ls[at] = make_float4(Lp.x, Lp.y, Lp.z, __uint_as_float(slot));
+                r.hp[at] = make_float4(p_next.x, p_next.y, p_next.z, __uint_as_float(prim_next));
+                r.dw[at] = make_float4(d_next.x, d_next.y, d_next.z, __uint_as_float(pixel));
+                r.tp[at] = make_float4(T.x, T.y, T.z, __uint_as_float(sample));
             }
         }
         buf ^= 1;
@@ -1666,14 +1710,14 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
         // ray records: (origin, tmax) (direction, slot | kRayShadow | kRaySpecular) (light sample rgb)
         const uint32_t is = warp_reserve(ray_cur, ray_shadow, ray_counter);
         if (is != kInvalid) {
-            __stcs(a.ray0 + is, make_float4(ray_o.x, ray_o.y, ray_o.z, ray_tmax));
-            __stcs(a.ray1 + is, make_float4(ray_w.x, ray_w.y, ray_w.z, __uint_as_float(slot | kRayShadow)));
-            __stcs(a.ray2 + is, make_float4(ray_rgb.x, ray_rgb.y, ray_rgb.z, 0.0f));
+            st_stream(a.ray0 + is, ray_o.x, ray_o.y, ray_o.z, __float_as_uint(ray_tmax));
+            st_stream(a.ray1 + is, ray_w.x, ray_w.y, ray_w.z, slot | kRayShadow);
+            st_stream(a.ray2 + is, ray_rgb.x, ray_rgb.y, ray_rgb.z, 0u);
         }
         const uint32_t ic = warp_reserve(ray_cur, ray_cont, ray_counter);
         if (ic != kInvalid) {
-            __stcs(a.ray0 + ic, make_float4(ray_o.x, ray_o.y, ray_o.z, FLT_MAX));
-            __stcs(a.ray1 + ic, make_float4(ray_d.x, ray_d.y, ray_d.z, __uint_as_float(slot | ray_flags)));
+            st_stream(a.ray0 + ic, ray_o.x, ray_o.y, ray_o.z, __float_as_uint(FLT_MAX));
+            st_stream(a.ray1 + ic, ray_d.x, ray_d.y, ray_d.z, slot | ray_flags);
         }
         s_cur = s_nxt; s_nxt = s_nn;
         buf ^= 1;
@@ -1739,13 +1783,13 @@ template <bool COOP, int WALK, int OCC = 3> __global__ void __launch_bounds__(kT
             if (base + cnt >= n) more = false; // the queue is drained (warp-uniform)
             const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
             if (!have && i < n) {
-                const float4 r1 = __ldcs(a.ray1 + i); // streamed: read once (evict first, the scene stays in L2)
+                const float4 r1 = ld_stream(a.ray1 + i); // streamed: read once (evict first, the scene stays in L2)
                 tag = __float_as_uint(r1.w);
                 if (tag != kInvalid) { // not the padding of a producer's last chunk
-                    const float4 r0 = __ldcs(a.ray0 + i);
+                    const float4 r0 = ld_stream(a.ray0 + i);
                     const bool shadow = (tag & kRayShadow) != 0u;
                     if (shadow) {
-                        const float4 r2 = __ldcs(a.ray2 + i);
+                        const float4 r2 = ld_stream(a.ray2 + i);
                         rgb = f3(r2.x, r2.y, r2.z);
                     }
                     have = true;

@@ -473,8 +473,14 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_visibility_warp_kernel(Ref
         if (local_to_pixel(map, lp, x, y)) {
             D3 o = ld3(cam.pos);
             D3 dir = pixel_dir(cam, x, y);
+            const unsigned before = node_tests;
             id = trace_front_warp(s, o, dir, point, normal, st_node[wib], st_mask[wib], node_tests, prim_tests);
             if (id < 0) { point = mk(DBL_MAX, DBL_MAX, DBL_MAX); normal = mk(0, 0, 0); }
+            if (counters) { // profile: the most expensive ray of the launch, in child-box tests (lanes count disjoint children)
+                unsigned mine = node_tests - before;
+                for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+                if (lane == 0) atomicMax(counters + 3, (unsigned long long)mine);
+            }
         }
         __syncwarp();
         if (lane == 0) {

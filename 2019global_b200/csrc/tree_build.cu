@@ -347,4 +347,35 @@ int path_build_tree_device(const float* d_boxes, uint32_t n_prims, const float r
 #undef TB_CUDA
 }
 
+
+// ---- top table: direct index over the first levels of the octree -----------------------------------------------
+// The walk's descents are a chain of DEPENDENT node loads, one per level (ncu, profiles/r02b: 23 % of trace_kernel's
+// stall samples sit on the instruction behind that load, 7 of 32 lanes active). For every cell of level `top_level`
+// this table holds the record of the deepest node on the way to it -- the cell's own node, or the leaf / empty node
+// of a coarser level that covers it, with that level in bits 24-27 of the count word -- so a descent starts with
+// ONE load instead of top_level of them.
+__global__ void top_table_kernel(const PathNodeD* __restrict__ nodes, int top_level, uint2* __restrict__ table) {
+    const uint32_t n = 1u << top_level;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n * n) return;
+    const uint32_t x = i & (n - 1u), y = (i >> top_level) & (n - 1u), z = i >> (2 * top_level);
+    uint2 rec = make_uint2(nodes[0].first, nodes[0].count);
+    int level = 0;
+    while (level < top_level && !(rec.y & kLeafBit)) {
+        const int sh = top_level - 1 - level;
+        const uint32_t c = ((x >> sh) & 1u) | (((y >> sh) & 1u) << 1) | (((z >> sh) & 1u) << 2);
+        const PathNodeD nd = nodes[rec.x + c];
+        rec = make_uint2(nd.first, nd.count);
+        ++level;
+    }
+    if (rec.y & kLeafBit) rec.y |= uint32_t(level) << 24; // leaf counts stay far below 2^24
+    table[i] = rec;
+}
+
+int path_build_top_table(const PathNodeD* d_nodes, int top_level, uint2* d_table, cudaStream_t s) {
+    const uint32_t cells = 1u << (3 * top_level);
+    top_table_kernel<<<(cells + 255) / 256, 256, 0, s>>>(d_nodes, top_level, d_table);
+    return cudaGetLastError() == cudaSuccess ? G19_OK : G19_ERR_CUDA;
+}
+
 } // namespace g19
