@@ -84,6 +84,8 @@ struct g19_ctx {
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t cls0 = nullptr, cls1 = nullptr;
+    cudaStream_t side = nullptr;                   // REF mode: the second band in flight
+    cudaEvent_t ev_band[2] = {nullptr, nullptr}, ev_ready = nullptr;
     g19_stats stats{};
     bool stats_pending = false;
 };
@@ -343,7 +345,7 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     G19_CUDA(ctx, ctx->normals_l.ensure(n * 3 * sizeof(double)));
     G19_CUDA(ctx, ctx->rgb_l.ensure(n * 3));
     G19_CUDA(ctx, ctx->colour_l.ensure(n * 3 * sizeof(float)));
-    G19_CUDA(ctx, ctx->counters.ensure(4 * sizeof(unsigned long long))); // [node tests, primitive tests, work counter, -]
+    G19_CUDA(ctx, ctx->counters.ensure(8 * sizeof(unsigned long long))); // [node tests, primitive tests, work counter, max per ray, work counter of the second band in flight, ...]
     unsigned long long* counters = nullptr;
     if (p->profile) {
         counters = ctx->counters.as<unsigned long long>();
@@ -372,35 +374,84 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
         G19_CUDA(ctx, cudaMemsetAsync(ctx->ids_l.p, 0xff, n * sizeof(int32_t), s));
         G19_CUDA(ctx, cudaMemsetAsync(ctx->rgb_l.p, 0, n * 3, s));
         G19_CUDA(ctx, cudaMemsetAsync(ctx->colour_l.p, 0, n * 3 * sizeof(float), s));
-        // about an eighth of the frame per band: every band ends in a tail that waits for its most expensive ray
+        // About an eighth of the frame per band. Every band ends in a tail that waits for its most expensive ray (on the
+        // 1 M-entity heightfield ONE ray tests 318 932 child boxes while the average ray tests 10), so two bands are kept
+        // in flight on two streams: the tail of one hides under the bulk of the next, and the host -- which handles
+        // cancel / progress / refresh for a band once its event has fired -- is at most two bands ahead of the device.
         const int tiles_per_band = std::max(map.tiles_x / std::max(1, map.world), (map.n_local_tiles + 7) / 8);
+        // (one band at a time under params.profile -- its per-class event brackets need one launch at a time -- and while a
+        // refresh hook is installed: a progressive caller is shown whole bands in order, never half of the next one)
+        const bool overlap = !p->profile && !ctx->hook.fn;
+        if (overlap) {
+            if (!ctx->side) G19_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+            for (cudaEvent_t* e : {&ctx->ev_band[0], &ctx->ev_band[1], &ctx->ev_ready})
+                if (!*e) G19_CUDA(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+            G19_CUDA(ctx, cudaEventRecord(ctx->ev_ready, s)); // the clears above
+            G19_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_ready, 0));
+        }
         auto last_refresh = std::chrono::steady_clock::now();
-        for (int t0 = 0; t0 < map.n_local_tiles; t0 += tiles_per_band) {
-            if (ctx->cancel.load()) { // RayTracer::stop()
-                rc_band = G19_ERR_CANCELLED;
-                break;
-            }
-            const int lp0 = t0 * kTilePix, lp1 = std::min(map.n_local_tiles, t0 + tiles_per_band) * kTilePix;
-            t.begin();
-            launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                                  ctx->normals_l.as<double>(), counters, s, lp0, lp1, next);
-            t.end(G19_K_REF_VIS, 1);
-            t.begin();
-            launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                             ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s, lp0, lp1);
-            t.end(G19_K_REF_SHADE, 1);
-            G19_CUDA(ctx, cudaStreamSynchronize(s)); // the host stays one band ahead at most: that is the cancel latency
-            ctx->progress_milli.store(int(1000.0 * double(lp1) / double(map.n_local_pix)));
+        // what the host does once band `done_lp1` is complete: progress, refresh, cancel from the hook
+        auto after_band = [&](int done_lp1) -> int {
+            ctx->progress_milli.store(int(1000.0 * double(done_lp1) / double(map.n_local_pix)));
             const auto now = std::chrono::steady_clock::now();
-            if (ctx->hook.fn && d_rgb && ctx->hook.h_rgb && lp1 < map.n_local_pix &&
+            if (ctx->hook.fn && d_rgb && ctx->hook.h_rgb && done_lp1 < map.n_local_pix &&
                 std::chrono::duration<double, std::milli>(now - last_refresh).count() >= double(ctx->hook.min_interval_ms)) {
                 last_refresh = now;
                 launch_untile(map, ctx->rgb_l.as<uint8_t>(), nullptr, nullptr, d_rgb, nullptr, nullptr, s);
                 G19_CUDA(ctx, cudaMemcpyAsync(ctx->hook.h_rgb, d_rgb, size_t(map.w) * size_t(map.h) * 3, cudaMemcpyDeviceToHost, s));
                 G19_CUDA(ctx, cudaStreamSynchronize(s));
                 ctx->stats.kernel_launches += 1;
-                if (ctx->hook.fn(ctx->hook.user, double(lp1) / double(map.n_local_pix), ctx->hook.h_rgb) != 0) ctx->cancel.store(1);
+                if (ctx->hook.fn(ctx->hook.user, double(done_lp1) / double(map.n_local_pix), ctx->hook.h_rgb) != 0) ctx->cancel.store(1);
             }
+            return G19_OK;
+        };
+        int band = 0, pending_lp1[2] = {0, 0};
+        bool pending[2] = {false, false};
+        for (int t0 = 0; t0 < map.n_local_tiles; t0 += tiles_per_band, ++band) {
+            if (ctx->cancel.load()) { // RayTracer::stop()
+                rc_band = G19_ERR_CANCELLED;
+                break;
+            }
+            const int lp0 = t0 * kTilePix, lp1 = std::min(map.n_local_tiles, t0 + tiles_per_band) * kTilePix;
+            const int slot = overlap ? (band & 1) : 0;
+            cudaStream_t bs = slot ? ctx->side : s;
+            if (overlap && pending[slot]) { // this stream's previous band (two bands ago) must be done before its slot is reused
+                G19_CUDA(ctx, cudaEventSynchronize(ctx->ev_band[slot]));
+                pending[slot] = false;
+                int rc2 = after_band(pending_lp1[slot]);
+                if (rc2 != G19_OK) return rc2;
+                if (ctx->cancel.load()) { rc_band = G19_ERR_CANCELLED; break; }
+            }
+            t.s = bs;
+            t.begin();
+            launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                                  ctx->normals_l.as<double>(), counters, bs, lp0, lp1, next + 4 * slot);
+            t.end(G19_K_REF_VIS, 1);
+            t.begin();
+            launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
+                             ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), bs, lp0, lp1);
+            t.end(G19_K_REF_SHADE, 1);
+            if (overlap) {
+                G19_CUDA(ctx, cudaEventRecord(ctx->ev_band[slot], bs));
+                pending[slot] = true;
+                pending_lp1[slot] = lp1;
+            } else {
+                G19_CUDA(ctx, cudaStreamSynchronize(s)); // the host stays one band ahead at most: that is the cancel latency
+                int rc2 = after_band(lp1);
+                if (rc2 != G19_OK) return rc2;
+            }
+        }
+        t.s = s;
+        if (overlap) { // drain in band order, then let the caller's stream continue behind both
+            for (int k = 0; k < 2; ++k) {
+                const int slot = (band + k) & 1;
+                if (!pending[slot]) continue;
+                G19_CUDA(ctx, cudaEventSynchronize(ctx->ev_band[slot]));
+                pending[slot] = false;
+                after_band(pending_lp1[slot]);
+            }
+            G19_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->side));
+            G19_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0));
         }
     }
     t.begin();
@@ -511,6 +562,9 @@ void g19_destroy(g19_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->cls0) cudaEventDestroy(ctx->cls0);
     if (ctx->cls1) cudaEventDestroy(ctx->cls1);
+    for (cudaEvent_t e : {ctx->ev_band[0], ctx->ev_band[1], ctx->ev_ready})
+        if (e) cudaEventDestroy(e);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -11,7 +11,7 @@
 //   * light: triangle emitters, next-event estimation at diffuse hits, emission
 //     counted on camera rays and after specular bounces only
 //   * max_depth = maximum number of ray segments along the camera path
-//   * RNG: Philox4x32-10, counter (pixel, sample, bounce, stream), key (seed, K)
+//   * RNG: Philox4x32-7, counter (pixel, sample, bounce, stream), key (seed, K)
 #pragma once
 
 #include <atomic>

@@ -26,7 +26,7 @@
 // the thread already holds in registers. Every launch is a persistent grid (SM count x resident
 // CTAs) that reads its queue length from device memory and is chained to its predecessor by
 // programmatic dependent launch, so a frame is enqueued without a single host round trip. The RNG
-// is Philox4x32-10 keyed on (global pixel, sample, bounce, stream): results do not depend on
+// is Philox4x32-7 keyed on (global pixel, sample, bounce, stream): results do not depend on
 // queue order, pass size, passes in flight or how tiles are split across GPUs.
 //
 // What the ncu captures drove (profiles/r01_tuning_log.md has the numbers):
@@ -88,11 +88,12 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
     return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
 }
 
-// ---- Philox4x32-10 (Salmon et al. 2011); identical integer stream in oracle/path_oracle.c
+// ---- Philox4x32-7 (Salmon et al. 2011: the fewest rounds that pass BigCrush; three rounds = 36 instructions per vertex
+// fewer than the -10 variant of round 1); identical integer stream in oracle/path_oracle.c
 __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0) {
     uint32_t k1 = 0x32303139u; // "2019"
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;

@@ -370,6 +370,65 @@ __global__ void __launch_bounds__(128) ref_visibility_kernel(RefSceneD s, RefCam
     }
 }
 
+// Three face-triangle tests of a node's children at once, stage by stage over small arrays: after unrolling, the three
+// FP64 chains are independent instruction streams inside the same basic blocks, which is what lets the scheduler
+// interleave them (three calls of node_face_tri_hit stay three serial chains: each one is its own branchy region).
+// Test t = pass * 32 + lane: child t / 12, face (t % 12) / 2, second triangle of the face's ExpRectangle when odd.
+// Same arithmetic per test as node_face_tri_hit / node_tri_hit. Returns the children (bits) this lane found hit.
+__device__ __forceinline__ unsigned node_children_hits3(const RefNodeD* __restrict__ children, D3 o, D3 dir, unsigned lane,
+                                                        unsigned& node_tests) {
+    D3 p1[3], p2[3], p3[3];
+    bool live[3];
+    unsigned bit[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int t = k * 32 + int(lane);
+        const int c = t / 12, tri = t - 12 * c, f = tri >> 1;
+        const RefNodeD* __restrict__ ch = children + c;
+        live[k] = ch->ent_count != 0;
+        bit[k] = 1u << c;
+        if (live[k] && tri == 0) ++node_tests;
+        const D3 mn = ld3(ch->mn), mx = ld3(ch->mx);
+        // corner codes per face (bit 0 / 1 / 2: take max.x / max.y / max.z), entities.h:399-406:
+        // faces (dlb,urb,ulb) (dlb,ult,dlt) (dlb,drt,dlt) (urt,ulb,ult) (urt,drb,drt) (urt,dlt,drt)
+        const unsigned c2 = (0x118f5u >> (3 * f)) & 7u; // p2: 5, 6, 3, 4, 1, 2
+        const unsigned c3 = (0x1bc94u >> (3 * f)) & 7u; // p3: 4, 2, 2, 6, 3, 3
+        p1[k] = (f < 3) ? mn : mx;
+        p2[k] = mk((c2 & 1u) ? mx.x : mn.x, (c2 & 2u) ? mx.y : mn.y, (c2 & 4u) ? mx.z : mn.z);
+        const D3 q3 = mk((c3 & 1u) ? mx.x : mn.x, (c3 & 2u) ? mx.y : mn.y, (c3 & 4u) ? mx.z : mn.z);
+        const D3 origin = mk(0, 0, 0);
+        const D3 p4 = origin + (origin - q3); // ExpRectangle::p4 with pos still at the origin (entities.h:319)
+        p3[k] = (tri & 1) ? p4 : q3;
+    }
+    D3 e1[3], e2[3];
+    bool dead[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        e1[k] = p2[k] - p1[k];
+        e2[k] = p3[k] - p1[k];
+        const D3 n = cross3(e1[k], e2[k]);
+        const double tx = n.x * dir.x, ty = n.y * dir.y, tz = n.z * dir.z;
+        const double nd_un = tx + ty + tz;
+        dead[k] = false;
+        if (!(fabs(nd_un) > 1.0e-9 * (fabs(tx) + fabs(ty) + fabs(tz)))) dead[k] = dot3(unit(n), dir) == 0; // rare: see node_tri_hit
+    }
+    D3 p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const D3 pos = 0.5 * (0.5 * (p1[k] + p2[k]) + p3[k]);
+        p[k] = plane_point(float(e1[k].x), float(e1[k].y), float(e1[k].z), float(e2[k].x), float(e2[k].y), float(e2[k].z), pos, o, dir);
+    }
+    unsigned found = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const D3 c1 = cross3(p1[k] - p[k], p2[k] - p[k]), c2 = cross3(p2[k] - p[k], p3[k] - p[k]), c3 = cross3(p3[k] - p[k], p1[k] - p[k]);
+        const int verdict = inside_verdict(c1, c2, c3);
+        const bool in = verdict < 0 ? inside_exact(c1, c2, c3) : verdict != 0;
+        if (live[k] && !dead[k] && in) found |= bit[k];
+    }
+    return found;
+}
+
 // ---- one WARP per ray -----------------------------------------------------------------------------
 // What the capture of ref_visibility_kernel on the 1 002 528-entity heightfield showed (profiles/r02a_ref_visibility_ncu.json):
 // 2.44 s for 518 400 rays, but only 5.6 G warp instructions at 1.54 of 32 lanes, warps active 3.6 % of the time -- the
@@ -415,20 +474,11 @@ __device__ int trace_front_warp(const RefSceneD& s, D3 o, D3 dir, D3& point, D3&
         int mask = st_mask[level];
         __syncwarp();
         if (mask < 0) { // the box tests of this node's non-empty children: 8 x 12 triangle tests over the lanes
-            unsigned found = 0;
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-                const int t = pass * 32 + int(lane);
-                const int c = t / 12, tri = t - 12 * c;
-                const RefNodeD* __restrict__ ch = s.nodes + first + c;
-                bool h = false;
-                if (ch->ent_count != 0) {
-                    if (tri == 0) ++node_tests;
-                    h = node_face_tri_hit(ch, tri >> 1, (tri & 1) != 0, o, dir);
-                }
-                found |= __reduce_or_sync(0xffffffffu, h ? (1u << c) : 0u);
-            }
-            mask = int(found);
+            // three tests per lane, evaluated as three interleaved FP64 chains: one warp walks a heavy ray alone (the
+            // most expensive ray of the 1 M-entity frame tests 318 932 child boxes, profiles/r02e), and nothing else
+            // hides the latency of ~200 dependent double-precision operations per test
+            const unsigned mine = node_children_hits3(s.nodes + first, o, dir, lane, node_tests);
+            mask = int(__reduce_or_sync(0xffffffffu, mine));
         }
         if (mask == 0) {
             --level;
