@@ -78,6 +78,7 @@ struct g19_ctx {
 
     // per-render work buffers (local-pixel indexed)
     DevBuf ids_l, points_l, normals_l, rgb_l, colour_l, counters;
+    DevBuf heavy; // REF mode: heavy-ray lists, one set per band in flight (RefHeavyD)
     // frame buffers for the host-pointer entry point
     DevBuf rgb_f, ids_f, rad_f;
     PathWork work;
@@ -349,9 +350,26 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     unsigned long long* counters = nullptr;
     if (p->profile) {
         counters = ctx->counters.as<unsigned long long>();
-        G19_CUDA(ctx, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), s));
+        G19_CUDA(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), s));
     }
     unsigned* next = reinterpret_cast<unsigned*>(ctx->counters.as<unsigned long long>() + 2);
+    // heavy-ray lists (ref_heavy_kernel), one set per band in flight
+    constexpr int kHeavyCap = 4096;
+    RefHeavyD heavy[2] = {};
+    if (ctx->tune.ref_heavy > 0 && ctx->ref.n_nodes > 1) {
+        const size_t set = (ref_heavy_bytes(kHeavyCap) + 255) / 256 * 256;
+        G19_CUDA(ctx, ctx->heavy.ensure(2 * set));
+        for (int k = 0; k < 2; ++k) {
+            char* base = static_cast<char*>(ctx->heavy.p) + k * set;
+            heavy[k].count = reinterpret_cast<unsigned*>(base);
+            heavy[k].lp = reinterpret_cast<int32_t*>(base + 64);
+            heavy[k].best = reinterpret_cast<unsigned*>(base + 64 + size_t(kHeavyCap) * 4);
+            heavy[k].lock = reinterpret_cast<int*>(base + 64 + size_t(kHeavyCap) * 8);
+            heavy[k].masks = reinterpret_cast<unsigned short*>(base + 64 + size_t(kHeavyCap) * 12);
+            heavy[k].cap = kHeavyCap;
+            heavy[k].budget = ctx->tune.ref_heavy;
+        }
+    }
     ClassTimer t{ctx, s, p->profile != 0};
     // The reference fills its Image pixel by pixel and polls _running per pixel (raytracer.h:32-33), so stop() and
     // the viewer's 32 ms repaint see a frame in progress. On a heavy scene (the 1 M-entity heightfield takes seconds)
@@ -363,8 +381,8 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     if (!banded) {
         t.begin();
         launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                              ctx->normals_l.as<double>(), counters, s, 0, -1, next);
-        t.end(G19_K_REF_VIS, 1);
+                              ctx->normals_l.as<double>(), counters, s, 0, -1, next, &heavy[0]);
+        t.end(G19_K_REF_VIS, heavy[0].budget > 0 ? 2 : 1);
         t.begin();
         launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
                          ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), s);
@@ -425,8 +443,8 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
             t.s = bs;
             t.begin();
             launch_ref_visibility(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
-                                  ctx->normals_l.as<double>(), counters, bs, lp0, lp1, next + 4 * slot);
-            t.end(G19_K_REF_VIS, 1);
+                                  ctx->normals_l.as<double>(), counters, bs, lp0, lp1, next + 4 * slot, &heavy[slot]);
+            t.end(G19_K_REF_VIS, heavy[slot].budget > 0 ? 2 : 1);
             t.begin();
             launch_ref_shade(ctx->ref, rc, map, ctx->ids_l.as<int32_t>(), ctx->points_l.as<double>(),
                              ctx->normals_l.as<double>(), ctx->rgb_l.as<uint8_t>(), ctx->colour_l.as<float>(), bs, lp0, lp1);
@@ -471,12 +489,13 @@ int render_ref(g19_ctx* ctx, const g19_camera* cam, const double light[3], const
     if (t_rad) G19_CUDA(ctx, cudaMemcpyAsync(t_rad, ctx->colour_l.p, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ctx->stats.samples = 0;
     if (p->profile) {
-        unsigned long long h[4] = {0, 0, 0, 0};
+        unsigned long long h[8] = {};
         G19_CUDA(ctx, cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, s));
         G19_CUDA(ctx, cudaStreamSynchronize(s));
         ctx->stats.node_tests = h[0];
         ctx->stats.prim_tests = h[1];
-        if (ctx->tune.debug_tree) std::fprintf(stderr, "[g19] REF: the most expensive ray tested %llu child boxes\n", h[3]);
+        if (ctx->tune.debug_tree)
+            std::fprintf(stderr, "[g19] REF: the most expensive single-warp walk tested %llu child boxes; %llu heavy rays were spread over many warps\n", h[3], h[5]);
     }
     // in-frame pixels owned by this rank
     uint64_t owned = 0;
@@ -553,7 +572,7 @@ void g19_destroy(g19_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&ctx->ref_nodes, &ctx->ref_ents, &ctx->ref_entities, &ctx->ref_tris, &ctx->ids_l, &ctx->points_l,
+    for (DevBuf* b : {&ctx->heavy, &ctx->ref_nodes, &ctx->ref_ents, &ctx->ref_entities, &ctx->ref_tris, &ctx->ids_l, &ctx->points_l,
                       &ctx->normals_l, &ctx->rgb_l, &ctx->colour_l, &ctx->counters, &ctx->rgb_f, &ctx->ids_f,
                       &ctx->rad_f})
         b->release();

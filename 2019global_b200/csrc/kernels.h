@@ -57,9 +57,24 @@ struct RefSceneD {
 // (raytracer.h:41-74). Outputs are indexed by local pixel.
 // [lp0, lp1) = the band of this rank's local pixels to render (lp1 < 0: all): the host-pointer entry points render
 // heavy scenes band by band so that stop() and the viewer's repaint see the frame grow (raytracer.h:32-33).
+// Heavy rays (ref_heavy_kernel): a ray whose walk exceeds `budget` node expansions is put on a list and spread over
+// many warps, one subtree of level kHeavyLevel each. Device buffers, one set per band in flight.
+constexpr int kHeavyLevel = 4;
+constexpr int kHeavyTasks = 1 << (3 * kHeavyLevel);       // subtrees per ray
+constexpr int kHeavyCache = 1 + 8 + 64 + 512;             // child-box masks of the nodes above the subtrees
+struct RefHeavyD {
+    unsigned* count;        // [0] rays appended (may run past cap), [1] task counter
+    int32_t* lp;            // [cap] local pixel of each heavy ray
+    unsigned* best;         // [cap] lowest subtree code with a published hit (0xffffffff: none)
+    int* lock;              // [cap]
+    unsigned short* masks;  // [cap][kHeavyCache]
+    int cap, budget;        // budget 0 = off
+};
+inline size_t ref_heavy_bytes(int cap) { return 64 + size_t(cap) * (4 + 4 + 4 + 2 * kHeavyCache + 2); }
 void launch_ref_visibility(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, int32_t* ids,
                            double* points, double* normals, unsigned long long* counters /*nullable: [node,prim]*/,
-                           cudaStream_t stream, int lp0 = 0, int lp1 = -1, unsigned* next = nullptr /* device work counter: enables the warp-per-ray kernel */);
+                           cudaStream_t stream, int lp0 = 0, int lp1 = -1, unsigned* next = nullptr /* device work counter: enables the warp-per-ray kernel */,
+                           const RefHeavyD* heavy = nullptr);
 // getTextureCoord + blinn_phong_texture + RGB888 quantisation (raytracer.h:76-82).
 void launch_ref_shade(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, const int32_t* ids,
                       const double* points, const double* normals, uint8_t* rgb, float* colour, cudaStream_t stream,

@@ -122,6 +122,7 @@ struct PathTuning {
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
     int top_level = 6;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2)
+    int ref_heavy = 128;      // REF mode: node expansions after which a ray is spread over many warps (ref_heavy_kernel; 0 = never)
     int l2_persist = 0;       // tree scenes: pin the primitive records in L2 (access policy window on the lanes' streams). Measured
                               // on the room scene: 869 ms with the window, 775 ms without -- the set-aside starves everything else; off
 };

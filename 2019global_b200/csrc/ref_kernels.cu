@@ -439,11 +439,18 @@ __device__ __forceinline__ unsigned node_children_hits3(const RefNodeD* __restri
 // position among the hits). So a warp takes one ray: 96 node-triangle tests in three passes of 32 lanes, leaf lists
 // 32 entities at a time from the back. Same device functions, same visiting order (children 7 -> 0, stack of
 // unvisited hit children), so the ids, points and normals are the thread-per-ray kernel's, bit for bit.
+// start / level_cap: the walk covers the subtree under node `start`, whose depth in the tree is kMaxRefDepth - level_cap
+// (0 / kMaxRefDepth: the whole tree). budget > 0: give up after that many node expansions and return kWalkOverBudget
+// (the ray goes to the heavy list). poll != nullptr: another warp of the same ray may publish a hit in a subtree that
+// comes EARLIER in the reversed order (a lower rank than `rank`): this walk is moot then and returns kWalkMoot.
+constexpr int kWalkOverBudget = -2, kWalkMoot = -3;
 __device__ int trace_front_warp(const RefSceneD& s, D3 o, D3 dir, D3& point, D3& normal, int* st_node, int* st_mask,
-                                unsigned& node_tests, unsigned& prim_tests) {
+                                unsigned& node_tests, unsigned& prim_tests, int start = 0, int level_cap = kMaxRefDepth,
+                                int budget = 0, const unsigned* poll = nullptr, unsigned rank = 0) {
     const unsigned lane = threadIdx.x & 31u;
     int level = 0;
-    if (lane == 0) { st_node[0] = 0; st_mask[0] = -1; }
+    int rounds = 0;
+    if (lane == 0) { st_node[0] = start; st_mask[0] = -1; }
     __syncwarp();
     while (level >= 0) {
         const RefNodeD* __restrict__ nd = s.nodes + st_node[level];
@@ -477,6 +484,10 @@ __device__ int trace_front_warp(const RefSceneD& s, D3 o, D3 dir, D3& point, D3&
             // three tests per lane, evaluated as three interleaved FP64 chains: one warp walks a heavy ray alone (the
             // most expensive ray of the 1 M-entity frame tests 318 932 child boxes, profiles/r02e), and nothing else
             // hides the latency of ~200 dependent double-precision operations per test
+            if (budget > 0 && ++rounds > budget) return kWalkOverBudget;
+            if (poll) { // warp-uniform: every lane reads the same word
+                if (*reinterpret_cast<const volatile unsigned*>(poll) < rank) return kWalkMoot;
+            }
             const unsigned mine = node_children_hits3(s.nodes + first, o, dir, lane, node_tests);
             mask = int(__reduce_or_sync(0xffffffffu, mine));
         }
@@ -488,13 +499,13 @@ __device__ int trace_front_warp(const RefSceneD& s, D3 o, D3 dir, D3& point, D3&
         __syncwarp();
         if (lane == 0) {
             st_mask[level] = mask & ~(1 << c);
-            if (level + 1 < kMaxRefDepth) {
+            if (level + 1 < level_cap) {
                 st_node[level + 1] = first + c;
                 st_mask[level + 1] = -1;
             }
         }
         __syncwarp();
-        if (level + 1 < kMaxRefDepth) ++level;
+        if (level + 1 < level_cap) ++level;
     }
     return -1;
 }
@@ -504,7 +515,7 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_visibility_warp_kernel(Ref
                                                                             int32_t* __restrict__ ids, double* __restrict__ points,
                                                                             double* __restrict__ normals,
                                                                             unsigned long long* __restrict__ counters,
-                                                                            unsigned* __restrict__ next) {
+                                                                            unsigned* __restrict__ next, RefHeavyD heavy) {
     __shared__ int st_node[kRefWarps][kMaxRefDepth];
     __shared__ int st_mask[kRefWarps][kMaxRefDepth];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -524,8 +535,22 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_visibility_warp_kernel(Ref
             D3 o = ld3(cam.pos);
             D3 dir = pixel_dir(cam, x, y);
             const unsigned before = node_tests;
-            id = trace_front_warp(s, o, dir, point, normal, st_node[wib], st_mask[wib], node_tests, prim_tests);
-            if (id < 0) { point = mk(DBL_MAX, DBL_MAX, DBL_MAX); normal = mk(0, 0, 0); }
+            id = trace_front_warp(s, o, dir, point, normal, st_node[wib], st_mask[wib], node_tests, prim_tests, 0, kMaxRefDepth,
+                                  heavy.budget);
+            if (id == kWalkOverBudget) {
+                // a heavy ray: ref_heavy_kernel spreads it over many warps (it starts over: the rounds spent here are
+                // the price of finding out). No room left in the list: walk it to the end right here.
+                unsigned at = 0;
+                if (lane == 0) at = atomicAdd(heavy.count, 1u);
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (at < unsigned(heavy.cap)) {
+                    if (lane == 0) heavy.lp[at] = lp;
+                    id = -1;
+                } else {
+                    id = trace_front_warp(s, o, dir, point, normal, st_node[wib], st_mask[wib], node_tests, prim_tests);
+                }
+            }
+            if (id < 0) { point = mk(DBL_MAX, DBL_MAX, DBL_MAX); normal = mk(0, 0, 0); } // (a heavy ray reads "no hit" until its hit is published)
             if (counters) { // profile: the most expensive ray of the launch, in child-box tests (lanes count disjoint children)
                 unsigned mine = node_tests - before;
                 for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
@@ -549,6 +574,102 @@ __global__ void __launch_bounds__(kRefWarps * 32) ref_visibility_warp_kernel(Ref
         if (lane == 0) {
             atomicAdd(counters + 0, (unsigned long long)node_tests);
             atomicAdd(counters + 1, (unsigned long long)prim_tests);
+        }
+    }
+}
+
+// ---- heavy rays: ONE ray over many warps ------------------------------------------------------------
+// Rays differ in cost by five orders of magnitude on the 1 M-entity heightfield: the average ray expands 1.25 nodes,
+// the heaviest 39 866 (318 932 child-box tests, ~10 us of dependent FP64 arithmetic each), and with one warp per ray a
+// 1080p frame waited 380 ms for that single walk (profiles/r02_tuning_log.md). The reversed walk is a depth-first
+// search whose answer is "the first hit in visiting order", so it splits by subtree: task (ray, code) walks the subtree
+// whose path from the root is the four child choices in `code` -- digit 0 is child 7, the child visited first -- and the
+// ray's answer is the hit of the LOWEST code that has one. Tasks are handed out in code order from a counter; a hit is
+// published under a per-ray lock together with its rank, and every walk of a higher rank gives up as soon as it sees
+// one (trace_front_warp's poll), which is the early termination of the serial walk. The child-box masks of the four
+// levels above the subtrees are computed once per ray by whichever task gets there first and kept in a small table
+// (0 = not computed yet; two warps racing compute the same value). Same device functions as the serial walk, same
+// visiting order inside every subtree: ids, points and normals are bit for bit what one warp would have found.
+__global__ void __launch_bounds__(kRefWarps * 32) ref_heavy_kernel(RefSceneD s, RefCamera cam, TileMap map, int32_t* __restrict__ ids,
+                                                                  double* __restrict__ points, double* __restrict__ normals,
+                                                                  unsigned long long* __restrict__ counters, RefHeavyD heavy) {
+    __shared__ int st_node[kRefWarps][kMaxRefDepth];
+    __shared__ int st_mask[kRefWarps][kMaxRefDepth];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned n_heavy = min(*heavy.count, unsigned(heavy.cap));
+    if (n_heavy == 0) return;
+    unsigned node_tests = 0, prim_tests = 0;
+    const D3 o = ld3(cam.pos);
+    while (true) {
+        unsigned take = 0;
+        if (lane == 0) take = atomicAdd(heavy.count + 1, 1u);
+        take = __shfl_sync(0xffffffffu, take, 0);
+        const unsigned h = take >> (3 * kHeavyLevel);
+        if (h >= n_heavy) break;
+        const unsigned code = take & unsigned(kHeavyTasks - 1);
+        if (*reinterpret_cast<const volatile unsigned*>(heavy.best + h) < code) continue; // a hit earlier in the order exists already
+        const int lp = heavy.lp[h];
+        int x, y;
+        local_to_pixel(map, lp, x, y);
+        const D3 dir = pixel_dir(cam, x, y);
+        unsigned short* cache = heavy.masks + size_t(h) * kHeavyCache;
+        int node = 0, at = 0, level_base = 0, depth = 0;
+        bool walk = true, leaf_here = false;
+        for (int l = 0; l < kHeavyLevel; ++l) {
+            const RefNodeD* __restrict__ nd = s.nodes + node;
+            const int first = nd->first_child;
+            const unsigned below = code & ((1u << (3 * (kHeavyLevel - l))) - 1u);
+            if (first < 0) { // a leaf above the split level: the first task under it takes it, the others have nothing to do
+                leaf_here = true;
+                walk = below == 0u;
+                break;
+            }
+            const unsigned digit = (code >> (3 * (kHeavyLevel - 1 - l))) & 7u;
+            const int c = 7 - int(digit);
+            unsigned m = reinterpret_cast<const volatile unsigned short*>(cache)[level_base + at];
+            if (!(m & 0x100u)) {
+                const unsigned mine = node_children_hits3(s.nodes + first, o, dir, unsigned(lane), node_tests);
+                m = 0x100u | __reduce_or_sync(0xffffffffu, mine);
+                if (lane == 0) reinterpret_cast<volatile unsigned short*>(cache)[level_base + at] = (unsigned short)m;
+            }
+            if (!((m >> c) & 1u)) { walk = false; break; }
+            node = first + c;
+            level_base += 1 << (3 * l);
+            at = at * 8 + int(digit);
+            depth = l + 1;
+        }
+        (void)leaf_here;
+        if (!walk) continue;
+        D3 point = mk(0, 0, 0), normal = mk(0, 0, 0);
+        __syncwarp();
+        const int id = trace_front_warp(s, o, dir, point, normal, st_node[wib], st_mask[wib], node_tests, prim_tests, node,
+                                        kMaxRefDepth - depth, 0, heavy.best + h, code);
+        if (id >= 0 && lane == 0) { // publish: the lowest rank wins
+            while (atomicCAS(heavy.lock + h, 0, 1) != 0) {}
+            __threadfence();
+            if (code < *reinterpret_cast<volatile unsigned*>(heavy.best + h)) {
+                ids[lp] = id;
+                if (points) {
+                    points[lp] = point.x; points[map.n_local_pix + lp] = point.y; points[2 * (size_t)map.n_local_pix + lp] = point.z;
+                    normals[lp] = normal.x; normals[map.n_local_pix + lp] = normal.y; normals[2 * (size_t)map.n_local_pix + lp] = normal.z;
+                }
+                __threadfence();
+                *reinterpret_cast<volatile unsigned*>(heavy.best + h) = code;
+            }
+            __threadfence();
+            atomicExch(heavy.lock + h, 0);
+        }
+        __syncwarp();
+    }
+    if (counters) {
+        for (int off = 16; off > 0; off >>= 1) {
+            node_tests += __shfl_xor_sync(0xffffffffu, node_tests, off);
+            prim_tests += __shfl_xor_sync(0xffffffffu, prim_tests, off);
+        }
+        if (lane == 0) {
+            atomicAdd(counters + 0, (unsigned long long)node_tests);
+            atomicAdd(counters + 1, (unsigned long long)prim_tests);
+            if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(counters + 5, (unsigned long long)n_heavy); // heavy rays of the frame
         }
     }
 }
@@ -824,13 +945,23 @@ inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; 
 
 void launch_ref_visibility(const RefSceneD& scene, const RefCamera& cam, const TileMap& map, int32_t* ids,
                            double* points, double* normals, unsigned long long* counters, cudaStream_t stream, int lp0,
-                           int lp1, unsigned* next) {
+                           int lp1, unsigned* next, const RefHeavyD* heavy) {
     if (lp1 < 0) lp1 = map.n_local_pix;
     if (lp1 <= lp0) return;
     if (scene.n_nodes > 1 && next) { // the tree has split: one warp per ray (node tests and leaf lists spread over the lanes)
         const int blocks = std::min(blocks_for(lp1 - lp0, kRefWarps), 148 * 16);
         cudaMemsetAsync(next, 0, sizeof(unsigned), stream);
-        ref_visibility_warp_kernel<<<blocks, kRefWarps * 32, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals, counters, next);
+        RefHeavyD hv{};
+        if (heavy && heavy->budget > 0 && heavy->cap > 0) {
+            hv = *heavy;
+            cudaMemsetAsync(hv.count, 0, 2 * sizeof(unsigned), stream);
+            cudaMemsetAsync(hv.best, 0xff, size_t(hv.cap) * sizeof(unsigned), stream);
+            cudaMemsetAsync(hv.lock, 0, size_t(hv.cap) * sizeof(int), stream);
+            cudaMemsetAsync(hv.masks, 0, size_t(hv.cap) * kHeavyCache * sizeof(unsigned short), stream);
+        }
+        ref_visibility_warp_kernel<<<blocks, kRefWarps * 32, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals, counters, next, hv);
+        // the heavy rays of this band, each spread over many warps (a grid that finds the list empty leaves at once)
+        if (hv.budget > 0) ref_heavy_kernel<<<148 * 4, kRefWarps * 32, 0, stream>>>(scene, cam, map, ids, points, normals, counters, hv);
         return;
     }
     ref_visibility_kernel<<<blocks_for(lp1 - lp0, 128), 128, 0, stream>>>(scene, cam, map, lp0, lp1, ids, points, normals,

@@ -124,6 +124,35 @@ def test_heightfield_primary_hits(g19, abi, oracle):
     assert (exp["ids"] >= 0).sum() > 1000
 
 
+@pytest.mark.parametrize("which,n,w,h", [("HEIGHTFIELD_ROOM", 64, 640, 352), ("HEIGHTFIELD", 48, 160, 90), ("CORNELL", 0, 480, 270)])
+def test_heavy_ray_split_bit_identical(g19, abi, oracle, which, n, w, h):
+    """ref_heavy_kernel: a ray whose walk exceeds the budget is spread over many warps, one level-4 subtree each, and the
+    hit of the lowest subtree code wins -- the first hit of the reversed walk (raytracer.h:53-74: the LAST candidate
+    that intersects). With a budget of 1 or 3 node expansions nearly every ray of a split tree takes that path (the
+    list holds 4096 rays per launch, the rest walk serially): ids and colours must equal the serial walk's and the
+    oracle's, whole-frame launch and banded host render alike."""
+    import torch
+    sc, cam, light = g19.Octree.builtin(getattr(abi, "SCENE_" + which), n=n, w=w, h=h)
+    exp = mirror(oracle, sc).trace(cam, light, w, h, want=("ids",), threads=8)["ids"]
+    outs = []
+    for budget in ("0", "1", "3", "128"):
+        rt = g19.RayTracer(cam, light)
+        rt.tune("ref_heavy", budget)
+        rt.setScene(sc)
+        rt.start()
+        got = rt.run(w, h, want=("rgb", "ids"))
+        assert np.array_equal(got["ids"], exp), "budget %s: %d ids differ" % (budget, int((got["ids"] != exp).sum()))
+        d_ids = torch.zeros(h * w, dtype=torch.int32, device="cuda")
+        d_rgb = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda")
+        rt.run_device(rt.params(w, h), d_rgb=d_rgb.data_ptr(), d_ids=d_ids.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_ids.cpu().numpy(), exp.ravel())
+        assert np.array_equal(d_rgb.cpu().numpy(), got["rgb"].ravel())
+        outs.append(got["rgb"])
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])  # hit points and normals feed the shading: same colours, byte for byte
+
+
 def test_tile_sharding_equals_single(g19, abi):
     w, h = 333, 217  # ragged: partial tiles on both edges
     sc, cam, light = g19.Octree.builtin(abi.SCENE_DEFAULT)
