@@ -34,6 +34,7 @@ UNITS = [
     ("path_kernels.cu", ["--use_fast_math", "-Xptxas", "-v"]),
     ("frame_kernels.cu", []),
     ("tree_build.cu", []),
+    ("ray_sort.cu", []),
     ("path.cu", []),
     ("engine.cu", []),
 ]

@@ -148,7 +148,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -175,6 +175,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
     else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
+    else if (k == "sort_rays") t.sort_rays = num(def.sort_rays, 0, 1);
     else if (k == "ref_heavy") t.ref_heavy = num(def.ref_heavy, 0, 1 << 30);
     else if (k == "l2_persist") t.l2_persist = num(def.l2_persist, 0, 1);
     else return false;
@@ -183,6 +184,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
 
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err) {
     const auto t_start = std::chrono::steady_clock::now();
+    ++b.upload_serial;
     std::vector<BuildPrim> prims;
     std::vector<MaterialD> materials;
     std::vector<LightD> lights;
@@ -563,10 +565,15 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
     for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &w.totals, &w.accum,
-                           &w.rad_l, &w.rgb_l})
+                           &w.rad_l, &w.rgb_l, &w.iota})
         d->release();
+    w.iota_n = 0;
+    w.ray_hint_d.release();
+    if (w.ray_hint_h) cudaFreeHost(w.ray_hint_h);
+    w.ray_hint_h = nullptr;
+    w.hint_key = 0;
     for (PathLane& l : w.lane) {
-        for (DeviceArray* d : {&l.hp, &l.dw, &l.tp, &l.L, &l.queues, &l.recs, &l.rays, &l.counts}) d->release();
+        for (DeviceArray* d : {&l.hp, &l.dw, &l.tp, &l.L, &l.queues, &l.recs, &l.rays, &l.counts, &l.rkeys, &l.perm, &l.sort_tmp}) d->release();
         l.capacity = 0;
     }
     for (int i = 0; i < kMaxLanes; ++i) {
@@ -789,6 +796,33 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             pa.ray0 = static_cast<float4*>(l.rays.p);
             pa.ray1 = pa.ray0 + ray_cap;
             pa.ray2 = pa.ray1 + ray_cap;
+            pa.rkey = nullptr;
+            pa.perm = nullptr;
+            pa.perm_n = 0;
+            pa.ray_hint = nullptr;
+            if (a.tune.sort_rays && p.max_depth > 1) {
+                PATH_CUDA(l.rkeys.ensure(2 * ray_cap * sizeof(uint16_t)));
+                PATH_CUDA(l.perm.ensure(ray_cap * sizeof(uint32_t)));
+                PATH_CUDA(l.sort_tmp.ensure(ray_sort_temp_bytes(ray_cap)));
+                if (w.iota_n < ray_cap) {
+                    PATH_CUDA(w.iota.ensure(ray_cap * sizeof(uint32_t)));
+                    launch_iota(static_cast<uint32_t*>(w.iota.p), ray_cap, s);
+                    w.iota_n = ray_cap;
+                }
+                pa.rkey = static_cast<uint16_t*>(l.rkeys.p);
+                pa.perm = static_cast<uint32_t*>(l.perm.p);
+                // the hints of the last frame of this workload (scene upload, pass size, depth)
+                const unsigned long long key = (b.upload_serial << 40) ^ (static_cast<unsigned long long>(P) << 8) ^ static_cast<unsigned long long>(p.max_depth);
+                if (!w.ray_hint_h) PATH_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.ray_hint_h), (kMaxPathDepth + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+                if (!w.ray_hint_d.p || w.hint_key != key) {
+                    PATH_CUDA(w.ray_hint_d.ensure((kMaxPathDepth + 1) * sizeof(uint32_t)));
+                    PATH_CUDA(cudaStreamSynchronize(s)); // (a copy of the previous workload's hints may still be in flight)
+                    PATH_CUDA(cudaMemsetAsync(w.ray_hint_d.p, 0, (kMaxPathDepth + 1) * sizeof(uint32_t), s));
+                    std::memset(w.ray_hint_h, 0, (kMaxPathDepth + 1) * sizeof(uint32_t));
+                    w.hint_key = key;
+                }
+                pa.ray_hint = static_cast<uint32_t*>(w.ray_hint_d.p);
+            }
         }
     }
     // Tree scenes: the primitive records are what the incoherent rays of the deep bounces fetch from all over the scene
@@ -849,16 +883,35 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             for (int bounce = 0; bounce < p.max_depth; ++bounce) {
                 clk.begin();
                 int n = 0;
+                // the first bounce's rays leave the camera rays' hit points in pixel order: coherent as they are
+                // ... and a queue that stayed short the last time is walked in a blink: not worth three more launches.
+                const size_t ray_cap = 2 * pa.plane + kQueueSlack;
+                size_t n_sort = 0;
+                if (!fused && pa.rkey && bounce > 0) {
+                    const uint32_t hint = w.ray_hint_h[bounce]; // 0 = not known yet: the whole queue
+                    n_sort = hint == 0 ? ray_cap : std::min(ray_cap, size_t(hint) + size_t(hint) / 8 + 65536);
+                    if (hint != 0 && hint < (1u << 19)) n_sort = 0;
+                }
+                const bool sort_this = n_sort > 0;
+                PassArgs pb = pa;
+                pb.perm_n = uint32_t(n_sort);
+                if (!sort_this) pb.rkey = nullptr, pb.perm = nullptr;
+                if (sort_this) PATH_CUDA(cudaMemsetAsync(pa.rkey, 0xff, n_sort * sizeof(uint16_t), ls));
                 if (merge_kinds && launch_bounce_merged(pa, bounce, a.sm_count, ls)) {
                     n = 1;
                 } else {
                     for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
                         if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
-                        if (launch_bounce(pa, bounce, kind, a.sm_count, ls)) ++n;
+                        if (launch_bounce(pb, bounce, kind, a.sm_count, ls)) ++n;
                     }
                 }
                 if (!fused && n > 0) { // tree scenes: one walk over the rays this bounce's vertices produced
-                    launch_trace(pa, bounce, a.sm_count, ls);
+                    if (sort_this) {
+                        PATH_CUDA(launch_ray_sort(w.lane[li].sort_tmp.p, w.lane[li].sort_tmp.bytes, pa.rkey, pa.rkey + ray_cap,
+                                                  static_cast<const uint32_t*>(w.iota.p), static_cast<uint32_t*>(w.lane[li].perm.p), n_sort, ls));
+                        n += 3; // histogram + two one-sweep passes
+                    }
+                    launch_trace(pb, bounce, a.sm_count, ls);
                     ++n;
                 }
                 clk.end(G19_K_SHADE);
@@ -899,6 +952,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         PATH_CUDA(cudaStreamWaitEvent(s, w.ev_join[i], 0));
     }
     clk.s = s;
+    if (!fused && w.ray_hint_h && w.ray_hint_d.p && lanes[0].ray_hint)
+        PATH_CUDA(cudaMemcpyAsync(w.ray_hint_h, w.ray_hint_d.p, (kMaxPathDepth + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     const int done_spp = int(stats.samples);
     clk.begin();
     if (a.frame_flags) {

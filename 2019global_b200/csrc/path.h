@@ -68,6 +68,7 @@ struct PathSceneBuffers {
     DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity, top;
     PathSceneD view{};
     bool has_bsdf[4] = {false, false, false, false};
+    unsigned long long upload_serial = 0; // counts path_upload calls: a new number = a different scene
 };
 
 // Wavefront state of ONE pass in flight (P path slots, slot = sample_in_pass * window + pixel_in_window).
@@ -79,6 +80,7 @@ struct PathLane {
     DeviceArray queues;        // tree scenes: uint32[6][P + slack]: (diffuse, mirror, glass) of even / odd bounces
     DeviceArray recs;          // flat scenes: float4[4][2][(P + slack) + (P + 2 slack | 0)] dense vertex records
     DeviceArray rays;          // float4[3][2P + slack]: ray queue of one bounce (tree scenes only)
+    DeviceArray rkeys, perm, sort_tmp; // ray_sort.cu: uint16[2][2P + slack] keys (in | sorted), uint32[2P + slack] fetch order, CUB scratch
     DeviceArray counts;        // uint32[kMaxPathDepth+1][5]: queue lengths per bounce + ray fetch cursors
 };
 
@@ -95,6 +97,14 @@ struct PathWork {
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
     DeviceArray accum;         // float[3][n_local_pix]
     DeviceArray rad_l, rgb_l;  // resolved local-pixel outputs
+    DeviceArray iota;          // uint32[2P + slack] 0, 1, 2, ...: the values the ray sort permutes
+    size_t iota_n = 0;
+    // How many rays each bounce queued the last time this workload was rendered: the ray sort covers that many entries
+    // (+ a margin) instead of the queue's capacity. Kept as a running maximum on the device (trace_kernel), copied to
+    // pinned host memory at the end of a frame; a stale or missing hint costs speed, never correctness.
+    DeviceArray ray_hint_d;    // uint32[kMaxPathDepth + 1]
+    uint32_t* ray_hint_h = nullptr;
+    unsigned long long hint_key = 0; // (scene, pass size, depth) the hints belong to
     // event pool for params.profile
     cudaEvent_t* events = nullptr;
     int n_events = 0, used_events = 0;
@@ -121,7 +131,8 @@ struct PathTuning {
     int trace_occ = 4;        // CTAs per SM of trace_kernel (4 = 64 registers, 114 bytes of spills: the walk is bound by memory
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
-    int top_level = 6;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2)
+    int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
+    int sort_rays = 1;        // tree scenes: reorder each bounce's ray queue by origin cell / kind / octant before the walk (ray_sort.cu)
     int ref_heavy = 128;      // REF mode: node expansions after which a ray is spread over many warps (ref_heavy_kernel; 0 = never)
     int l2_persist = 0;       // tree scenes: pin the primitive records in L2 (access policy window on the lanes' streams). Measured
                               // on the room scene: 869 ms with the window, 775 ms without -- the set-aside starves everything else; off
@@ -205,6 +216,10 @@ struct PassArgs {
     float4* ray0;          // tree scenes: the bounce's ray queue (origin, tmax)
     float4* ray1;          //   (direction, slot | flags)
     float4* ray2;          //   (light sample rgb) of shadow rays
+    uint16_t* rkey;        //   sort key per queued ray (ray_sort.cu), nullptr = rays are walked in queue order
+    const uint32_t* perm;  //   the order trace_kernel fetches the first perm_n rays in (sorted by key); the rest in queue order
+    uint32_t perm_n;
+    uint32_t* ray_hint;    //   [bounce] running maximum of the rays queued (nullable)
     uint32_t* counts;      // [kMaxPathDepth+1][4] queue lengths (column 0: rays) + [kMaxPathDepth+1] fetch cursors
     unsigned long long* totals;
     float* accum;          // 3 planes of n_local_pix
@@ -225,6 +240,11 @@ bool launch_bounce(const PassArgs& a, int bounce, int kind, int sm_count, cudaSt
 // flat scenes with mirror / glass: the three material queues of a bounce in one launch; false = not applicable
 bool launch_bounce_merged(const PassArgs& a, int bounce, int sm_count, cudaStream_t s);
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s); // tree scenes: after the bounce's shade launches
+// ray_sort.cu
+size_t ray_sort_temp_bytes(size_t n);
+void launch_iota(uint32_t* out, size_t n, cudaStream_t s);
+cudaError_t launch_ray_sort(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out, const uint32_t* iota,
+                            uint32_t* perm, size_t n, cudaStream_t s);
 bool path_scene_is_flat(const PassArgs& a);
 void launch_accumulate(const PassArgs& a, cudaStream_t s);
 void launch_primary(const PassArgs& a, int32_t* ids_l, double* points_l, double* normals_l, int sm_count, cudaStream_t s);

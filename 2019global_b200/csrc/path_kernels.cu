@@ -1639,6 +1639,25 @@ template <bool TP> __device__ __forceinline__ void prefetch_vertex(const PassArg
 // with dynamic fetch (a heavy tail of long walks would otherwise hold the other 31 lanes of the
 // warp -- ncu: 3.4 of 32 lanes active); trace_kernel also adds the light sample and delivers the
 // continuation vertex into the slot-indexed state and the next bounce's material queues.
+// Sort key of a queued ray (ray_sort.cu): where it starts, on a 32^3 grid over the root box, in Morton order.
+// Shadow rays (they all aim at the lights): 1 | 15 bits; continuation rays: 0 | 12 bits (16^3 cells) | direction octant.
+__device__ __forceinline__ uint32_t spread5(uint32_t x) { // bit k -> bit 3k
+    x = (x | (x << 8)) & 0x100fu;
+    x = (x | (x << 4)) & 0x10c3u;
+    x = (x | (x << 2)) & 0x1249u;
+    return x;
+}
+__device__ __forceinline__ uint32_t ray_sort_key(const PathSceneD& g, float3 o, float3 d, bool shadow) {
+    const int sh = kMaxTreeDepth - 5;
+    const uint32_t x = uint32_t(min(max(__float2int_rd((o.x - g.root_lo[0]) * g.grid_scale[0]) >> sh, 0), 31));
+    const uint32_t y = uint32_t(min(max(__float2int_rd((o.y - g.root_lo[1]) * g.grid_scale[1]) >> sh, 0), 31));
+    const uint32_t z = uint32_t(min(max(__float2int_rd((o.z - g.root_lo[2]) * g.grid_scale[2]) >> sh, 0), 31));
+    const uint32_t m = spread5(x) | (spread5(y) << 1) | (spread5(z) << 2);
+    if (shadow) return 0x8000u | m;
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    return ((m >> 3) << 3) | oct;
+}
+
 template <int KIND, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_kernel(const PassArgs a, const int bounce) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
@@ -1714,11 +1733,13 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : 3) bounce_ke
             st_stream(a.ray0 + is, ray_o.x, ray_o.y, ray_o.z, __float_as_uint(ray_tmax));
             st_stream(a.ray1 + is, ray_w.x, ray_w.y, ray_w.z, slot | kRayShadow);
             st_stream(a.ray2 + is, ray_rgb.x, ray_rgb.y, ray_rgb.z, 0u);
+            if (a.rkey) a.rkey[is] = (uint16_t)ray_sort_key(a.scene, ray_o, ray_w, true);
         }
         const uint32_t ic = warp_reserve(ray_cur, ray_cont, ray_counter);
         if (ic != kInvalid) {
             st_stream(a.ray0 + ic, ray_o.x, ray_o.y, ray_o.z, __float_as_uint(FLT_MAX));
             st_stream(a.ray1 + ic, ray_d.x, ray_d.y, ray_d.z, slot | ray_flags);
+            if (a.rkey) a.rkey[ic] = (uint16_t)ray_sort_key(a.scene, ray_o, ray_d, false);
         }
         s_cur = s_nxt; s_nxt = s_nn;
         buf ^= 1;
@@ -1754,6 +1775,7 @@ template <bool COOP, int WALK, int OCC = 3> __global__ void __launch_bounds__(kT
     const SceneAccess<false> S = stage_scene<false>(a);
     pdl_wait();
     const uint32_t n = a.counts[bounce * 4 + Q_RAYS];
+    if (a.ray_hint && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(a.ray_hint + bounce, n);
     if (n == 0) return;
     const bool sort = bounce + 1 < a.max_depth;
     const bool next_last = bounce + 2 >= a.max_depth;
@@ -1782,8 +1804,9 @@ template <bool COOP, int WALK, int OCC = 3> __global__ void __launch_bounds__(kT
             if (lane == 0) base = atomicAdd(fetch, cnt);
             base = __shfl_sync(kFull, base, 0);
             if (base + cnt >= n) more = false; // the queue is drained (warp-uniform)
-            const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
-            if (!have && i < n) {
+            const uint32_t at = base + __popc(idle & ((1u << lane) - 1u));
+            if (!have && at < n) {
+                const uint32_t i = at < a.perm_n ? __ldg(a.perm + at) : at; // sorted by origin cell (ray_sort.cu) / queue order
                 const float4 r1 = ld_stream(a.ray1 + i); // streamed: read once (evict first, the scene stays in L2)
                 tag = __float_as_uint(r1.w);
                 if (tag != kInvalid) { // not the padding of a producer's last chunk
