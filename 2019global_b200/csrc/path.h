@@ -132,6 +132,7 @@ struct PathTuning {
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
     int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
+    int upload_threads = 0;   // host threads of the primitive extraction at scene upload (0 = auto: one below 32 Ki entities, else up to 16)
     int sort_rays = 1;        // tree scenes: reorder each bounce's ray queue by origin cell / kind / octant before the walk (ray_sort.cu)
     int ref_heavy = 128;      // REF mode: node expansions after which a ray is spread over many warps (ref_heavy_kernel; 0 = never)
     int l2_persist = 0;       // tree scenes: pin the primitive records in L2 (access policy window on the lanes' streams). Measured

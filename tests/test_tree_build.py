@@ -62,3 +62,30 @@ def test_device_build_small_and_empty_scenes(g19, abi):
     rt_e, nodes_e, index_e = _tree(g19, abi, empty, cam, light, "device")
     assert nodes_e.shape[0] == 1 and index_e.size == 0
     assert (rt_e.run(40, 24, mode=abi.MODE_PATH, want=("radiance",), spp=2, max_depth=3)["radiance"] == 0).all()
+
+
+def test_upload_threads_do_not_change_the_scene(g19, abi):
+    """Scene upload extracts primitives on several host threads (a range of entities each, joined in entity order with
+    the material folding applied across the seams): tree, leaf references and radiance must not depend on their number.
+    The zoo mixes materials, spheres and triangle composites; the heightfield is the many-entity case; sort_rays on/off
+    (tree scenes walk each bounce's rays in origin-cell order) must agree bit for bit as well."""
+    w, h = 96, 54
+    from util import zoo
+    scenes = [g19.Octree.builtin(abi.SCENE_HEIGHTFIELD_ROOM, n=40, w=w, h=h)]
+    cam = g19.Camera((-10, 0, 0), (1, 0, 0), 0.1)
+    scenes.append((zoo(g19), cam, (-10, 10, 10)))
+    for sc, cam, light in scenes:
+        outs = []
+        for threads, sort in ((1, 1), (3, 1), (7, 0), (16, 1)):
+            rt = g19.RayTracer(cam, light)
+            rt.tune("upload_threads", threads)
+            rt.tune("sort_rays", sort)
+            rt.tune("tree_build", "host")
+            rt.setScene(sc)
+            rt.start()
+            nodes, index = rt.path_tree()
+            rad = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=3, max_depth=4, seed=9)["radiance"]
+            outs.append((nodes, index, rad))
+        for nodes, index, rad in outs[1:]:
+            assert np.array_equal(nodes, outs[0][0]) and np.array_equal(index, outs[0][1])
+            assert rad.tobytes() == outs[0][2].tobytes()
