@@ -35,6 +35,7 @@ UNITS = [
     ("frame_kernels.cu", []),
     ("tree_build.cu", []),
     ("ray_sort.cu", []),
+    ("bvh_build.cu", []),
     ("path.cu", []),
     ("engine.cu", []),
 ]

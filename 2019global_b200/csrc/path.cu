@@ -172,7 +172,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "raygen_occ") t.raygen_occ = num(def.raygen_occ, 2, 3);
     else if (k == "tree_build") t.tree_build = !value ? -1 : (std::strcmp(value, "device") == 0 ? 1 : (std::strcmp(value, "host") == 0 ? 0 : -1));
     else if (k == "debug_tree") t.debug_tree = value ? 1 : 0;
-    else if (k == "walk") t.walk = num(def.walk, 0, 1);
+    else if (k == "walk") { t.walk = num(def.walk, 0, 3); if (t.walk == 2) t.walk = 1; }
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
     else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
@@ -623,6 +623,67 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     } else {
         v.top_level = 0;
     }
+    // bounding-volume hierarchy for tune walk=3 (tree scenes only)
+    v.bvh_nodes = nullptr;
+    v.bvh_prims = nullptr;
+    v.bvh_big = nullptr;
+    v.n_big = 0;
+    v.bvh_root = 0xffffffffu;
+    if (tune.walk == 3 && v.n_nodes > 1) {
+        const auto t_bvh = std::chrono::steady_clock::now();
+        // primitives much larger than the rest stay out of the hierarchy: at most 64, larger than 1/32 of the root box
+        float root_max = std::max(root_size[0], std::max(root_size[1], root_size[2]));
+        std::vector<std::pair<float, uint32_t>> large;
+        for (size_t i = 0; i < prims.size(); ++i) {
+            const Box& bx = prims[i].box;
+            const float ext = std::max(bx.hi[0] - bx.lo[0], std::max(bx.hi[1] - bx.lo[1], bx.hi[2] - bx.lo[2]));
+            if (ext > root_max * (1.0f / 32.0f)) large.emplace_back(ext, uint32_t(i));
+        }
+        std::sort(large.begin(), large.end(), [](const std::pair<float, uint32_t>& x, const std::pair<float, uint32_t>& y) {
+            return x.first > y.first || (x.first == y.first && x.second < y.second);
+        });
+        if (large.size() > 64) large.resize(64);
+        std::vector<uint32_t> big_ids;
+        std::vector<char> is_big(prims.size(), 0);
+        for (auto& l : large) { big_ids.push_back(l.second); is_big[l.second] = 1; }
+        std::sort(big_ids.begin(), big_ids.end());
+        std::vector<uint32_t> small_ids;
+        small_ids.reserve(prims.size());
+        for (size_t i = 0; i < prims.size(); ++i)
+            if (!is_big[i]) small_ids.push_back(uint32_t(i));
+        std::vector<float> boxes(prims.size() * 6);
+        for (size_t i = 0; i < prims.size(); ++i)
+            for (int k = 0; k < 3; ++k) {
+                boxes[6 * i + k] = prims[i].box.lo[k];
+                boxes[6 * i + 3 + k] = prims[i].box.hi[k];
+            }
+        DeviceArray d_boxes, d_small;
+        cudaError_t be = d_boxes.ensure(boxes.size() * sizeof(float) + 16);
+        if (be == cudaSuccess) be = d_small.ensure(small_ids.size() * sizeof(uint32_t) + 16);
+        if (be == cudaSuccess) be = cudaMemcpyAsync(d_boxes.p, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+        if (be == cudaSuccess && !small_ids.empty())
+            be = cudaMemcpyAsync(d_small.p, small_ids.data(), small_ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
+        if (be == cudaSuccess) be = up(b.bvh_big, big_ids.data(), big_ids.size() * sizeof(uint32_t));
+        if (be == cudaSuccess) be = cudaStreamSynchronize(stream);
+        int rc = G19_OK;
+        if (be != cudaSuccess) {
+            err = std::string("path_upload (bvh): ") + cudaGetErrorString(be);
+            rc = G19_ERR_CUDA;
+        } else {
+            rc = path_build_bvh_device(static_cast<const float*>(d_boxes.p), static_cast<const uint32_t*>(d_small.p), uint32_t(small_ids.size()),
+                                       root_lo, root_size, v.hot, 4, stream, b.bvh_nodes, b.bvh_prims, &v.bvh_root, err);
+        }
+        d_boxes.release();
+        d_small.release();
+        if (rc != G19_OK) return rc;
+        v.bvh_nodes = static_cast<const float4*>(b.bvh_nodes.p);
+        v.bvh_prims = static_cast<const float4*>(b.bvh_prims.p);
+        v.bvh_big = static_cast<const uint32_t*>(b.bvh_big.p);
+        v.n_big = int32_t(big_ids.size());
+        if (tune.debug_tree)
+            std::fprintf(stderr, "[g19] path bvh: %zu primitives in the hierarchy, %zu kept out (big), built in %.1f ms\n", small_ids.size(),
+                         big_ids.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_bvh).count());
+    }
     v.n_par = n_par;
     v.n_tri = n_tri;
     v.pairs = static_cast<const float*>(b.pairs.p);
@@ -636,7 +697,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &w.totals, &w.accum,
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &b.bvh_nodes, &b.bvh_prims, &b.bvh_big, &w.totals, &w.accum,
                            &w.rad_l, &w.rgb_l, &w.iota})
         d->release();
     w.iota_n = 0;
@@ -731,6 +792,10 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa0.trace_occ = a.tune.trace_occ;
     pa0.bounce_occ = a.tune.bounce_occ;
     pa0.walk = a.tune.walk ? (p.profile ? 2 : 1) : 0; // the new walk counts its node / primitive tests under params.profile
+    if (a.tune.walk == 3 && b.view.bvh_root != 0xffffffffu && b.view.bvh_nodes) {
+        pa0.walk = 3; // bounding-volume hierarchy (no test counts under params.profile)
+        if (a.tune.walk_steps <= 0) pa0.walk_steps = 6;
+    }
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
     // primary-hit AOV: the un-jittered ray of every pixel (the reference's ray) through this engine's structures
     if (a.ids_l) {

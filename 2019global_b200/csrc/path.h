@@ -51,6 +51,12 @@ struct PathSceneD {
     float grid_scale[3];     // 2^kMaxTreeDepth / root_size: world position -> coordinate on the finest octree grid
     const uint2* top;        // direct index over the first top_level levels (tree_build.cu top_table_kernel), or nullptr
     int32_t top_level;
+    // bounding-volume hierarchy (bvh_build.cu), the structure tune walk=3 traverses; nullptr = not built
+    const float4* bvh_nodes; // 4 x float4 per internal node: both children's boxes and references
+    const float4* bvh_prims; // the hot records in leaf order, original primitive id in row 3 .w
+    const uint32_t* bvh_big; // primitives kept out of the hierarchy (much larger than the rest): tested up front
+    int32_t n_big;
+    uint32_t bvh_root;       // node index, leaf reference, or 0xffffffff (nothing in the hierarchy)
 };
 
 struct PathCamera { // float copies of the reference basis (RefCamera)
@@ -66,6 +72,7 @@ struct DeviceArray {
 
 struct PathSceneBuffers {
     DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity, top;
+    DeviceArray bvh_nodes, bvh_prims, bvh_big;
     PathSceneD view{};
     bool has_bsdf[4] = {false, false, false, false};
     unsigned long long upload_serial = 0; // counts path_upload calls: a new number = a different scene
@@ -127,7 +134,8 @@ struct PathTuning {
     int raygen_occ = 3;       // CTAs per SM of the tree-scene camera-ray kernel
     int tree_build = -1;      // -1 auto (device from 4096 primitives), 0 host, 1 device
     int debug_tree = 0;       // print octree statistics at upload
-    int walk = 1;             // tree walk: 1 = point-location restart walk (TreeWalk2), 0 = parametric stack walk (TreeWalk)
+    int walk = 1;             // tree walk: 1 = point-location restart walk over the octree (TreeWalk2), 0 = parametric stack walk (TreeWalk),
+                              // 3 = bounding-volume hierarchy (BvhWalk, bvh_build.cu)
     int trace_occ = 4;        // CTAs per SM of trace_kernel (4 = 64 registers, 114 bytes of spills: the walk is bound by memory
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
@@ -178,6 +186,10 @@ struct PathRenderArgs {
 int path_build_tree_device(const float* d_boxes, uint32_t n_prims, const float root_lo[3], const float root_size[3],
                            int leaf_max, int max_depth, cudaStream_t s, PathNodeD** d_nodes, uint32_t* n_nodes,
                            uint32_t** d_index, uint32_t* n_index, int* tree_depth, std::string& err);
+// bvh_build.cu
+int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t n, const float root_lo[3], const float root_size[3],
+                          const PrimHot* d_hot, int leaf_max, cudaStream_t s, DeviceArray& nodes, DeviceArray& prims, uint32_t* root,
+                          std::string& err);
 int path_build_top_table(const PathNodeD* d_nodes, int top_level, uint2* d_table, cudaStream_t s);
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err);
 int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err);

@@ -920,9 +920,117 @@ template <bool COUNT> struct TreeWalk2 {
     }
 };
 
+// ---- BvhWalk: bounding-volume hierarchy (bvh_build.cu) --------------------------------------------------
+// Same resumable interface as the octree walks (init / step / best / best_prim), so trace_kernel's dynamic ray fetch and
+// the camera-ray kernel use it unchanged. A round = walk_steps node visits (a node record is both children's boxes: two
+// slab tests against [0, nearest hit so far], descend into the nearer child that is hit, push the other) followed by one
+// leaf visit for the lanes that stand at a leaf (1-4 primitives, contiguous 64-byte records in leaf order: one load
+// chain). Fixed-trip and predicated like the octree rounds, so the warp re-converges after every visit. The stack of
+// postponed children lives in local memory (L1): an LBVH over 30-bit Morton codes is at most ~40 levels deep.
+// The few primitives the host kept out of the hierarchy (walls around a mesh: their boxes would cover every level above
+// them) are tested first -- which also gives the walk a finite nearest-hit bound from its first node on.
+constexpr uint32_t kBvhLeaf = 0x80000000u, kBvhDone = 0xffffffffu;
+constexpr int kBvhStack = 64;
+struct BvhWalk {
+    float3 o, d, idir, ood;
+    float best;
+    uint32_t best_prim;
+    uint32_t cur;  // node index, kBvhLeaf | (count - 1) << 28 | first, or kBvhDone
+    uint32_t any;
+    int sp;
+    uint32_t stk[kBvhStack];
+
+    __device__ __forceinline__ void pop() { cur = sp > 0 ? stk[--sp] : kBvhDone; }
+
+    template <bool ALL>
+    __device__ __forceinline__ bool init(const SceneAccess<ALL>& S, float3 o_, float3 d_, float tmax, bool any_) {
+        const PathSceneD& g = *S.g;
+        o = o_;
+        d = d_;
+        best = tmax;
+        best_prim = kInvalid;
+        any = any_ ? 1u : 0u;
+        sp = 0;
+        const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
+        for (int k = 0; k < g.n_big; ++k) {
+            const uint32_t id = __ldg(g.bvh_big + k);
+            const float4* pp = hot + 4 * (size_t)id;
+            const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
+            const float t = hit_prim(a0, b0, c0, g0, o, d, best);
+            if (t >= 0.0f) {
+                best = t;
+                best_prim = id;
+                if (any_) return true;
+            }
+        }
+        float3 dd = d;
+        if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
+        if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
+        if (fabsf(dd.z) < 1.0e-20f) dd.z = copysignf(1.0e-20f, dd.z);
+        idir = f3(__fdividef(1.0f, dd.x), __fdividef(1.0f, dd.y), __fdividef(1.0f, dd.z));
+        ood = f3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        cur = g.bvh_root;
+        return cur == kBvhDone;
+    }
+
+    template <bool ALL, bool COOP> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
+        const PathSceneD& g = *S.g;
+        const int kWalkSteps = S.walk_steps;
+        const float4* __restrict__ nodes = g.bvh_nodes;
+#pragma unroll 1
+        for (int it = 0; it < kWalkSteps; ++it) {
+            __syncwarp();
+            if (active && cur < kBvhLeaf) { // an internal node: both children's slabs
+                const float4* __restrict__ np = nodes + 4 * (size_t)cur;
+                const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                // slightly widened: a hit ON a box face must not be lost to rounding (the primitive test decides)
+                const float hi = best * 1.000002f + 1.0e-6f;
+                const float c0lox = fmaf(n0.x, idir.x, -ood.x), c0hix = fmaf(n0.y, idir.x, -ood.x);
+                const float c0loy = fmaf(n0.z, idir.y, -ood.y), c0hiy = fmaf(n0.w, idir.y, -ood.y);
+                const float c0loz = fmaf(n2.x, idir.z, -ood.z), c0hiz = fmaf(n2.y, idir.z, -ood.z);
+                const float c1lox = fmaf(n1.x, idir.x, -ood.x), c1hix = fmaf(n1.y, idir.x, -ood.x);
+                const float c1loy = fmaf(n1.z, idir.y, -ood.y), c1hiy = fmaf(n1.w, idir.y, -ood.y);
+                const float c1loz = fmaf(n2.z, idir.z, -ood.z), c1hiz = fmaf(n2.w, idir.z, -ood.z);
+                const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+                const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), hi));
+                const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+                const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), hi));
+                // (1 + 3 ulp on the far side: the products above round independently)
+                const bool h0 = t0n <= t0f * 1.0000004f, h1 = t1n <= t1f * 1.0000004f;
+                const uint32_t r0 = __float_as_uint(n3.x), r1 = __float_as_uint(n3.y);
+                if (h0 && h1) {
+                    const bool swap = t1n < t0n;
+                    cur = swap ? r1 : r0;
+                    if (sp < kBvhStack) stk[sp++] = swap ? r0 : r1;
+                } else if (h0 || h1) {
+                    cur = h0 ? r0 : r1;
+                } else {
+                    pop();
+                }
+            }
+        }
+        __syncwarp();
+        if (active && cur >= kBvhLeaf && cur != kBvhDone) { // a leaf: its primitives, nearest so far kept
+            const uint32_t first = cur & 0x0fffffffu, cnt = ((cur >> 28) & 7u) + 1u;
+            const float4* __restrict__ pp = g.bvh_prims + 4 * (size_t)first;
+#pragma unroll 1
+            for (uint32_t k = 0; k < cnt; ++k, pp += 4) {
+                const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
+                const float t = hit_prim(a0, b0, c0, g0, o, d, best);
+                if (t >= 0.0f) { best = t; best_prim = __float_as_uint(g0.w); }
+            }
+            if (any && best_prim != kInvalid) cur = kBvhDone;
+            else pop();
+        }
+        __syncwarp();
+        return active && cur == kBvhDone;
+    }
+};
+
 template <int WALK> struct WalkOf { using type = TreeWalk; };
 template <> struct WalkOf<1> { using type = TreeWalk2<false>; };
 template <> struct WalkOf<2> { using type = TreeWalk2<true>; };
+template <> struct WalkOf<3> { using type = BvhWalk; };
 template <typename W> __device__ __forceinline__ void walk_counts(const W&, unsigned&, unsigned&) {}
 template <> __device__ __forceinline__ void walk_counts(const TreeWalk2<true>& w, unsigned& nodes, unsigned& prims) {
     nodes += w.n_node;
@@ -2119,7 +2227,8 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
         const int occ = a.raygen_occ; // tuning knob
         // 3 CTAs per SM at 80 registers (68 bytes of spills) beat 2 at 95: 23.8 vs 26.4 ms per 66 M camera rays
         void (*kernel)(PassArgs);
-        if (a.walk == 2) kernel = a.coop_leaf ? raygen_extend_kernel<3, true, 2> : raygen_extend_kernel<3, false, 2>;
+        if (a.walk == 3) kernel = raygen_extend_kernel<3, false, 3>;
+        else if (a.walk == 2) kernel = a.coop_leaf ? raygen_extend_kernel<3, true, 2> : raygen_extend_kernel<3, false, 2>;
         else if (a.walk == 1) kernel = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true, 1> : raygen_extend_kernel<3, true, 1>)
                                                    : (occ == 2 ? raygen_extend_kernel<2, false, 1> : raygen_extend_kernel<3, false, 1>);
         else kernel = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true, 0> : raygen_extend_kernel<3, true, 0>)
@@ -2133,7 +2242,8 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a);
     void (*kernel)(PassArgs, int);
-    if (a.walk == 2) kernel = a.coop_leaf ? trace_kernel<true, 2> : trace_kernel<false, 2>;
+    if (a.walk == 3) kernel = a.trace_occ == 4 ? trace_kernel<false, 3, 4> : trace_kernel<false, 3, 3>;
+    else if (a.walk == 2) kernel = a.coop_leaf ? trace_kernel<true, 2> : trace_kernel<false, 2>;
     else if (a.walk == 1) kernel = a.coop_leaf ? (a.trace_occ == 4 ? trace_kernel<true, 1, 4> : trace_kernel<true, 1, 3>) : trace_kernel<false, 1>;
     else kernel = a.coop_leaf ? trace_kernel<true, 0> : trace_kernel<false, 0>;
     const int grid = persistent_grid(kernel, smem, sm_count);

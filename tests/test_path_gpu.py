@@ -295,3 +295,39 @@ def test_flat_then_tree_scene_on_one_context(g19, abi):
         rt.camera, rt.light = cam, tuple(light)
         rt.setScene(sc)
         assert rt.run(w, h, **kw)["radiance"].tobytes() == want[k].tobytes(), k
+
+
+@pytest.mark.parametrize("which,n,w,h,spp,depth", [("HEIGHTFIELD", 24, 64, 36, 4, 4), ("HEIGHTFIELD_ROOM", 40, 96, 54, 4, 5),
+                                                    ("HEIGHTFIELD_ROOM", 150, 160, 90, 2, 4), ("ZOO", 0, 120, 120, 8, 4)])
+def test_bvh_walk_matches_oracle_and_octree(g19, abi, oracle, which, n, w, h, spp, depth):
+    """tune walk=3: the bounding-volume hierarchy (csrc/bvh_build.cu, BvhWalk) instead of the linear octree. Same
+    nearest hits, so the same radiance as the brute-force oracle and as the octree walk (they may part ways only where
+    two primitives tie in t along a shared edge), same segment counts. n = 150 builds both trees on the device."""
+    if which == "ZOO":
+        from util import zoo
+        sc = zoo(g19)
+        sc.push_back(g19.ImpTriangle((-6, -9, 9), (-6, 9, 9), (6, 0, 9), (1, 1, 1), bsdf=abi.BSDF_EMITTER, emission=(6.0, 6.0, 6.0)))
+        sc.push_back(g19.ExpQuad((2, 0, -3), 6, 8, 0.2, (0.8, 0.8, 0.8)))
+        cam, light = g19.Camera((-10, 0, 0), (1, 0, 0), 0.1), (0, 0, 0)
+    else:
+        sc, cam, light = g19.Octree.builtin(getattr(abi, "SCENE_" + which), n=n, w=w, h=h)
+    outs = {}
+    for walk in (1, 3):
+        rt = g19.RayTracer(cam, light)
+        rt.tune("walk", walk)
+        rt.setScene(sc)
+        rt.start()
+        rad = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=spp, max_depth=depth, seed=17)["radiance"]
+        st = rt.stats()
+        outs[walk] = (rad, int(st.extend_segments), int(st.shadow_segments))
+        again = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=spp, max_depth=depth, seed=17)["radiance"]
+        assert rad.tobytes() == again.tobytes()
+    exp, segs = binding.path_render(mirror(oracle, sc), cam, w, h, spp, depth, seed=17)
+    assert exp.mean() > 0.005
+    for walk, (rad, ext, shd) in outs.items():
+        err = rel_rmse(rad, exp)
+        print("%s walk=%d: same-seed relRMSE %.3e, segments %d/%d vs oracle %d/%d" % (which, walk, err, ext, shd, segs[0], segs[1]))
+        assert err <= 1e-2
+        assert abs(ext - segs[0]) <= 1e-3 * segs[0] + 2
+        assert abs(shd - segs[1]) <= 1e-3 * segs[1] + 2
+    assert rel_rmse(outs[3][0], outs[1][0]) <= 2e-3
