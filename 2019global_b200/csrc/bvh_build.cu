@@ -19,7 +19,9 @@
 // Primitives much larger than their neighbours (walls around a mesh) would drag a huge box through every level above
 // them; the host keeps those out (path.cu: the "big" list, tested up front by BvhWalk::init).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <string>
 
 #include "path.h"
@@ -140,13 +142,24 @@ __global__ void bvh_refit_kernel(const float* __restrict__ boxes, const uint32_t
     }
 }
 
+// Internal nodes the walk can reach: the root and every node whose range is larger than a leaf. The others (the inside
+// of a collapsed leaf) get no record: the records are compacted, in Karras order (which follows the Morton curve), so the
+// hierarchy of 1 M primitives is 25 MB of live cache lines instead of 64 MB with dead records in between.
+__global__ void bvh_live_kernel(const int2* __restrict__ range, int n, int leaf_max, uint32_t* __restrict__ live) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int2 rg = range[i];
+    live[i] = (i == 0 || rg.y - rg.x + 1 > leaf_max) ? 1u : 0u;
+}
+
 // The records the walk reads, 64 B per internal node (Aila & Laine 2009 layout):
 //   (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y) (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y) (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z) (ref0, ref1, -, -)
 // ref = index of an internal node, or kLeafRef | (count - 1) << 28 | first position in leaf order.
 __global__ void bvh_emit_kernel(const float* __restrict__ boxes, const uint32_t* __restrict__ vals, int n, const uint32_t* __restrict__ child,
-                                const int2* __restrict__ range, const Box6* __restrict__ node_box, int leaf_max, float4* __restrict__ out) {
+                                const int2* __restrict__ range, const Box6* __restrict__ node_box, int leaf_max,
+                                const uint32_t* __restrict__ live, const uint32_t* __restrict__ new_index, float4* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
+    if (i >= n - 1 || !live[i]) return;
     Box6 cb[2];
     uint32_t ref[2];
     for (int c = 0; c < 2; ++c) {
@@ -159,14 +172,97 @@ __global__ void bvh_emit_kernel(const float* __restrict__ boxes, const uint32_t*
             cb[c] = node_box[r];
             const int2 rg = range[r];
             const int cnt = rg.y - rg.x + 1;
-            ref[c] = cnt <= leaf_max ? (kLeafRef | (uint32_t(cnt - 1) << 28) | uint32_t(rg.x)) : r;
+            ref[c] = cnt <= leaf_max ? (kLeafRef | (uint32_t(cnt - 1) << 28) | uint32_t(rg.x)) : new_index[r];
         }
     }
-    float4* o = out + 4 * size_t(i);
+    float4* o = out + 4 * size_t(new_index[i]);
     o[0] = make_float4(cb[0].lo[0], cb[0].hi[0], cb[0].lo[1], cb[0].hi[1]);
     o[1] = make_float4(cb[1].lo[0], cb[1].hi[0], cb[1].lo[1], cb[1].hi[1]);
     o[2] = make_float4(cb[0].lo[2], cb[0].hi[2], cb[1].lo[2], cb[1].hi[2]);
     o[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), 0.f, 0.f);
+}
+
+// ---- 4-wide form: every second level of the binary tree is folded into its parent ---------------------------
+// The walk is bound by the latency of one dependent load per visited node (profiles/r02m: 15.7 warps stalled on long
+// scoreboard per issue); a node with four children halves the number of those round trips per ray for the same number of
+// box tests. Kept nodes = live internal nodes at EVEN depth; a live child at odd depth is replaced by its two children.
+__global__ void bvh_kept4_kernel(const uint32_t* __restrict__ parent_of_node, const uint32_t* __restrict__ live, int n, uint32_t* __restrict__ kept) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    uint32_t k = 0;
+    if (live[i]) {
+        int depth = 0;
+        for (uint32_t p = parent_of_node[i]; p != 0xffffffffu; p = parent_of_node[p]) ++depth;
+        k = (depth & 1) ? 0u : 1u;
+    }
+    kept[i] = k;
+}
+
+// 64 B per node -- the capture of the binary walk (profiles/r02m) has the L1 data pipe at 81 % of its peak: every lane
+// pulls its own 64-byte record through it, four wavefronts per visit; the same four wavefronts now carry FOUR children.
+// Boxes are quantised to 16 bits per coordinate on the root box's grid (40 units / 65535 = 0.6 mm on the room scene, a
+// hundredth of a mesh triangle), rounded outwards plus one unit, so a quantised box always contains the exact one:
+//   row 0: x  (lo0 | lo1 << 16, lo2 | lo3 << 16, hi0 | hi1 << 16, hi2 | hi3 << 16)     row 1: y     row 2: z
+//   row 3: the four references
+// Slots are filled from the front (at least two); an empty slot carries the reference 0xffffffff, which the walk checks.
+__global__ void bvh_emit4_kernel(const float* __restrict__ boxes, const uint32_t* __restrict__ vals, int n, const uint32_t* __restrict__ child,
+                                 const int2* __restrict__ range, const Box6* __restrict__ node_box, int leaf_max,
+                                 const uint32_t* __restrict__ kept, const uint32_t* __restrict__ new_index, float3 root_lo, float3 to_grid,
+                                 uint4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1 || !kept[i]) return;
+    Box6 cb[4];
+    uint32_t ref[4];
+    int m = 0;
+    const float inf = __int_as_float(0x7f800000);
+    // a child reference of the binary tree -> one slot (leaf / kept node), or the two slots of an absorbed node's children
+    auto slot = [&](uint32_t r, bool absorb) {
+        if (r & kLeafRef) {
+            const uint32_t pos = r & ~kLeafRef;
+            cb[m] = prim_box(boxes, vals[pos]);
+            ref[m++] = kLeafRef | pos;
+            return true;
+        }
+        const int2 rg = range[r];
+        const int cnt = rg.y - rg.x + 1;
+        if (cnt <= leaf_max) {
+            cb[m] = node_box[r];
+            ref[m++] = kLeafRef | (uint32_t(cnt - 1) << 28) | uint32_t(rg.x);
+            return true;
+        }
+        if (absorb) return false; // a live node at odd depth: the caller takes its children instead
+        cb[m] = node_box[r];
+        ref[m++] = new_index[r];
+        return true;
+    };
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t r = child[2 * i + c];
+        if (!slot(r, true)) {
+            slot(child[2 * r], false);
+            slot(child[2 * r + 1], false);
+        }
+    }
+    for (; m < 4;) {
+        for (int a = 0; a < 3; ++a) { cb[m].lo[a] = inf; cb[m].hi[a] = -inf; }
+        ref[m++] = 0xffffffffu;
+    }
+    const float rl[3] = {root_lo.x, root_lo.y, root_lo.z}, tg[3] = {to_grid.x, to_grid.y, to_grid.z};
+    uint4 row[3];
+    for (int a = 0; a < 3; ++a) {
+        uint32_t lo[4], hi[4];
+        for (int c = 0; c < 4; ++c) {
+            if (ref[c] == 0xffffffffu) { lo[c] = 65535u; hi[c] = 0u; continue; }
+            const int ql = int(floorf((cb[c].lo[a] - rl[a]) * tg[a])) - 1, qh = int(ceilf((cb[c].hi[a] - rl[a]) * tg[a])) + 1;
+            lo[c] = uint32_t(min(max(ql, 0), 65535));
+            hi[c] = uint32_t(min(max(qh, 0), 65535));
+        }
+        row[a] = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16));
+    }
+    uint4* o = out + 4 * size_t(new_index[i]);
+    o[0] = row[0];
+    o[1] = row[1];
+    o[2] = row[2];
+    o[3] = make_uint4(ref[0], ref[1], ref[2], ref[3]);
 }
 
 __global__ void bvh_gather_kernel(const float4* __restrict__ hot, const uint32_t* __restrict__ vals, int n, float4* __restrict__ out) {
@@ -188,17 +284,18 @@ __global__ void bvh_gather_kernel(const float4* __restrict__ hot, const uint32_t
 // d_ids: the n primitives that go into the hierarchy (the host kept the big ones out). Returns the root reference
 // (a node index, or a leaf reference when n <= leaf_max) in *root; n == 0: *root = 0xffffffff.
 int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t n, const float root_lo[3], const float root_size[3],
-                          const PrimHot* d_hot, int leaf_max, cudaStream_t s, DeviceArray& nodes, DeviceArray& prims, uint32_t* root,
-                          std::string& err) {
+                          const PrimHot* d_hot, int leaf_max, cudaStream_t s, DeviceArray& nodes, DeviceArray& nodes4, DeviceArray& prims,
+                          uint32_t* root, std::string& err) {
     *root = 0xffffffffu;
     if (n == 0) return G19_OK;
     auto fail = [&](const char* what, cudaError_t e) {
         err = std::string("path_build_bvh_device (") + what + "): " + cudaGetErrorString(e);
         return G19_ERR_CUDA;
     };
-    DeviceArray keys, vals, keys2, vals2, tmp, child, par_n, par_l, range, arrived, nbox;
+    DeviceArray keys, vals, keys2, vals2, tmp, child, par_n, par_l, range, arrived, nbox, live, new_index, tmp2;
     auto release_all = [&] {
-        for (DeviceArray* d : {&keys, &vals, &keys2, &vals2, &tmp, &child, &par_n, &par_l, &range, &arrived, &nbox}) d->release();
+        for (DeviceArray* d : {&keys, &vals, &keys2, &vals2, &tmp, &child, &par_n, &par_l, &range, &arrived, &nbox, &live, &new_index, &tmp2})
+            d->release();
     };
     cudaError_t e;
 #define BVH_TRY(what, call)            \
@@ -228,6 +325,7 @@ int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t 
     if (n <= uint32_t(leaf_max)) { // one leaf
         *root = kLeafRef | ((n - 1) << 28);
         BVH_TRY("nodes", nodes.ensure(64));
+        BVH_TRY("nodes", nodes4.ensure(64));
         BVH_TRY("sync", cudaStreamSynchronize(s));
         release_all();
         return G19_OK;
@@ -238,14 +336,41 @@ int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t 
     BVH_TRY("alloc", range.ensure(size_t(n - 1) * 8));
     BVH_TRY("alloc", arrived.ensure(size_t(n - 1) * 4));
     BVH_TRY("alloc", nbox.ensure(size_t(n - 1) * sizeof(Box6)));
-    BVH_TRY("alloc", nodes.ensure(size_t(n - 1) * 64));
+    BVH_TRY("alloc", live.ensure(size_t(n) * 4));
+    BVH_TRY("alloc", new_index.ensure(size_t(n) * 4));
     BVH_TRY("memset", cudaMemsetAsync(arrived.p, 0, size_t(n - 1) * 4, s));
     bvh_topology_kernel<<<blocks, threads, 0, s>>>(skeys, int(n), static_cast<uint32_t*>(child.p), static_cast<uint32_t*>(par_n.p),
                                                    static_cast<uint32_t*>(par_l.p), static_cast<int2*>(range.p));
     bvh_refit_kernel<<<blocks, threads, 0, s>>>(d_boxes, svals, int(n), static_cast<const uint32_t*>(child.p), static_cast<const uint32_t*>(par_n.p),
                                                 static_cast<const uint32_t*>(par_l.p), static_cast<unsigned*>(arrived.p), static_cast<Box6*>(nbox.p));
+    // compaction: position of every live node among the live ones
+    BVH_TRY("memset", cudaMemsetAsync(live.p, 0, size_t(n) * 4, s));
+    bvh_live_kernel<<<blocks, threads, 0, s>>>(static_cast<const int2*>(range.p), int(n), leaf_max, static_cast<uint32_t*>(live.p));
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<const uint32_t*>(live.p), static_cast<uint32_t*>(new_index.p), int(n), s);
+    BVH_TRY("alloc", tmp2.ensure(scan_bytes));
+    BVH_TRY("scan", cub::DeviceScan::ExclusiveSum(tmp2.p, scan_bytes, static_cast<const uint32_t*>(live.p), static_cast<uint32_t*>(new_index.p), int(n), s));
+    uint32_t n_live = 0; // live[n - 1] is 0 (there are n - 1 internal nodes): the last scan entry is the total
+    BVH_TRY("copy", cudaMemcpyAsync(&n_live, static_cast<const uint32_t*>(new_index.p) + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+    BVH_TRY("sync", cudaStreamSynchronize(s));
+    BVH_TRY("alloc", nodes.ensure(size_t(std::max<uint32_t>(n_live, 1u)) * 64));
     bvh_emit_kernel<<<blocks, threads, 0, s>>>(d_boxes, svals, int(n), static_cast<const uint32_t*>(child.p), static_cast<const int2*>(range.p),
-                                               static_cast<const Box6*>(nbox.p), leaf_max, static_cast<float4*>(nodes.p));
+                                               static_cast<const Box6*>(nbox.p), leaf_max, static_cast<const uint32_t*>(live.p),
+                                               static_cast<const uint32_t*>(new_index.p), static_cast<float4*>(nodes.p));
+    // the 4-wide form over the same topology, boxes and leaf order (root = node 0 in both)
+    bvh_kept4_kernel<<<blocks, threads, 0, s>>>(static_cast<const uint32_t*>(par_n.p), static_cast<const uint32_t*>(live.p), int(n),
+                                                static_cast<uint32_t*>(arrived.p));
+    BVH_TRY("memset", cudaMemsetAsync(live.p, 0, size_t(n) * 4, s)); // reuse: live <- kept (entry n - 1 stays 0)
+    BVH_TRY("copy", cudaMemcpyAsync(live.p, arrived.p, size_t(n - 1) * 4, cudaMemcpyDeviceToDevice, s));
+    BVH_TRY("scan", cub::DeviceScan::ExclusiveSum(tmp2.p, scan_bytes, static_cast<const uint32_t*>(live.p), static_cast<uint32_t*>(new_index.p), int(n), s));
+    uint32_t n_kept = 0;
+    BVH_TRY("copy", cudaMemcpyAsync(&n_kept, static_cast<const uint32_t*>(new_index.p) + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+    BVH_TRY("sync", cudaStreamSynchronize(s));
+    BVH_TRY("alloc", nodes4.ensure(size_t(std::max<uint32_t>(n_kept, 1u)) * 64));
+    const float3 to_grid = make_float3(65535.0f / root_size[0], 65535.0f / root_size[1], 65535.0f / root_size[2]);
+    bvh_emit4_kernel<<<blocks, threads, 0, s>>>(d_boxes, svals, int(n), static_cast<const uint32_t*>(child.p), static_cast<const int2*>(range.p),
+                                                static_cast<const Box6*>(nbox.p), leaf_max, static_cast<const uint32_t*>(live.p),
+                                                static_cast<const uint32_t*>(new_index.p), lo, to_grid, static_cast<uint4*>(nodes4.p));
     BVH_TRY("launch", cudaGetLastError());
     BVH_TRY("sync", cudaStreamSynchronize(s));
 #undef BVH_TRY

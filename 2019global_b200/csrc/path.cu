@@ -149,7 +149,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -172,12 +172,14 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "raygen_occ") t.raygen_occ = num(def.raygen_occ, 2, 3);
     else if (k == "tree_build") t.tree_build = !value ? -1 : (std::strcmp(value, "device") == 0 ? 1 : (std::strcmp(value, "host") == 0 ? 0 : -1));
     else if (k == "debug_tree") t.debug_tree = value ? 1 : 0;
-    else if (k == "walk") { t.walk = num(def.walk, 0, 3); if (t.walk == 2) t.walk = 1; }
+    else if (k == "walk") { t.walk = num(def.walk, 0, 4); if (t.walk == 2) t.walk = 1; }
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
     else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
+    else if (k == "bvh_spec") t.bvh_spec = num(def.bvh_spec, 0, 1);
+    else if (k == "bvh_leaf") t.bvh_leaf = num(def.bvh_leaf, 1, 8);
     else if (k == "upload_threads") t.upload_threads = num(def.upload_threads, 0, 64);
-    else if (k == "sort_rays") t.sort_rays = num(def.sort_rays, 0, 1);
+    else if (k == "sort_rays") t.sort_rays = num(def.sort_rays, -1, 1);
     else if (k == "ref_heavy") t.ref_heavy = num(def.ref_heavy, 0, 1 << 30);
     else if (k == "l2_persist") t.l2_persist = num(def.l2_persist, 0, 1);
     else return false;
@@ -625,11 +627,12 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     }
     // bounding-volume hierarchy for tune walk=3 (tree scenes only)
     v.bvh_nodes = nullptr;
+    v.bvh4_nodes = nullptr;
     v.bvh_prims = nullptr;
     v.bvh_big = nullptr;
     v.n_big = 0;
     v.bvh_root = 0xffffffffu;
-    if (tune.walk == 3 && v.n_nodes > 1) {
+    if (tune.walk >= 3 && v.n_nodes > 1) {
         const auto t_bvh = std::chrono::steady_clock::now();
         // primitives much larger than the rest stay out of the hierarchy: at most 64, larger than 1/32 of the root box
         float root_max = std::max(root_size[0], std::max(root_size[1], root_size[2]));
@@ -671,12 +674,13 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
             rc = G19_ERR_CUDA;
         } else {
             rc = path_build_bvh_device(static_cast<const float*>(d_boxes.p), static_cast<const uint32_t*>(d_small.p), uint32_t(small_ids.size()),
-                                       root_lo, root_size, v.hot, 4, stream, b.bvh_nodes, b.bvh_prims, &v.bvh_root, err);
+                                       root_lo, root_size, v.hot, tune.bvh_leaf, stream, b.bvh_nodes, b.bvh4_nodes, b.bvh_prims, &v.bvh_root, err);
         }
         d_boxes.release();
         d_small.release();
         if (rc != G19_OK) return rc;
         v.bvh_nodes = static_cast<const float4*>(b.bvh_nodes.p);
+        v.bvh4_nodes = static_cast<const uint4*>(b.bvh4_nodes.p);
         v.bvh_prims = static_cast<const float4*>(b.bvh_prims.p);
         v.bvh_big = static_cast<const uint32_t*>(b.bvh_big.p);
         v.n_big = int32_t(big_ids.size());
@@ -697,7 +701,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &b.bvh_nodes, &b.bvh_prims, &b.bvh_big, &w.totals, &w.accum,
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &b.bvh_nodes, &b.bvh4_nodes, &b.bvh_prims, &b.bvh_big, &w.totals, &w.accum,
                            &w.rad_l, &w.rgb_l, &w.iota})
         d->release();
     w.iota_n = 0;
@@ -791,10 +795,13 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa0.raygen_occ = a.tune.raygen_occ;
     pa0.trace_occ = a.tune.trace_occ;
     pa0.bounce_occ = a.tune.bounce_occ;
+    pa0.bvh_spec = a.tune.bvh_spec;
     pa0.walk = a.tune.walk ? (p.profile ? 2 : 1) : 0; // the new walk counts its node / primitive tests under params.profile
-    if (a.tune.walk == 3 && b.view.bvh_root != 0xffffffffu && b.view.bvh_nodes) {
-        pa0.walk = 3; // bounding-volume hierarchy (no test counts under params.profile)
-        if (a.tune.walk_steps <= 0) pa0.walk_steps = 6;
+    if (a.tune.walk >= 3 && b.view.bvh_root != 0xffffffffu && b.view.bvh_nodes) {
+        pa0.walk = a.tune.walk == 4 ? 5 : 3; // bounding-volume hierarchy, binary / 4-wide (no test counts under params.profile)
+        // node visits per round, room scene: binary 4 / 6 / 8 / 12 = 437 / 423 / 418 / 418 ms; 4-wide 4 / 6 / 8 / 12 = 346 / 345 / 364 / 382 ms
+        if (a.tune.walk_steps <= 0) pa0.walk_steps = a.tune.walk == 4 ? 5 : 8;
+        pa0.stack_levels = std::max(pa0.stack_levels, kBvhSmemStack);
     }
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
     // primary-hit AOV: the un-jittered ray of every pixel (the reference's ray) through this engine's structures
@@ -937,7 +944,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             pa.perm = nullptr;
             pa.perm_n = 0;
             pa.ray_hint = nullptr;
-            if (a.tune.sort_rays && p.max_depth > 1) {
+            const bool sort_rays = a.tune.sort_rays < 0 ? pa0.walk < 3 : a.tune.sort_rays != 0;
+            if (sort_rays && p.max_depth > 1) {
                 PATH_CUDA(l.rkeys.ensure(2 * ray_cap * sizeof(uint16_t)));
                 PATH_CUDA(l.perm.ensure(ray_cap * sizeof(uint32_t)));
                 PATH_CUDA(l.sort_tmp.ensure(ray_sort_temp_bytes(ray_cap)));

@@ -28,6 +28,7 @@ namespace g19 {
 
 constexpr int kMaxPathDepth = 64;    // segments per path
 constexpr int kMaxTreeDepth = 14;    // linear-octree levels below the root
+constexpr int kBvhSmemStack = 24;    // walk=3: levels of the postponed-children stack kept in shared memory (PassArgs::stack_levels)
 constexpr int kNumQueues = 6;        // (diffuse, mirror, glass) x two bounce parities
 // Queue entries are reserved in warp-private chunks; a launch can leave at most one partly used
 // chunk per warp and queue behind (padded with an invalid marker): 2 Mi entries of slack cover
@@ -53,6 +54,7 @@ struct PathSceneD {
     int32_t top_level;
     // bounding-volume hierarchy (bvh_build.cu), the structure tune walk=3 traverses; nullptr = not built
     const float4* bvh_nodes; // 4 x float4 per internal node: both children's boxes and references
+    const uint4* bvh4_nodes; // the 4-wide form (walk=4): 64 B per node, boxes quantised to 16 bits on the root box's grid
     const float4* bvh_prims; // the hot records in leaf order, original primitive id in row 3 .w
     const uint32_t* bvh_big; // primitives kept out of the hierarchy (much larger than the rest): tested up front
     int32_t n_big;
@@ -72,7 +74,7 @@ struct DeviceArray {
 
 struct PathSceneBuffers {
     DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity, top;
-    DeviceArray bvh_nodes, bvh_prims, bvh_big;
+    DeviceArray bvh_nodes, bvh4_nodes, bvh_prims, bvh_big;
     PathSceneD view{};
     bool has_bsdf[4] = {false, false, false, false};
     unsigned long long upload_serial = 0; // counts path_upload calls: a new number = a different scene
@@ -135,13 +137,17 @@ struct PathTuning {
     int tree_build = -1;      // -1 auto (device from 4096 primitives), 0 host, 1 device
     int debug_tree = 0;       // print octree statistics at upload
     int walk = 1;             // tree walk: 1 = point-location restart walk over the octree (TreeWalk2), 0 = parametric stack walk (TreeWalk),
-                              // 3 = bounding-volume hierarchy (BvhWalk, bvh_build.cu)
+                              // 3 = bounding-volume hierarchy (BvhWalk, bvh_build.cu), 4 = its 4-wide form (Bvh4Walk)
     int trace_occ = 4;        // CTAs per SM of trace_kernel (4 = 64 registers, 114 bytes of spills: the walk is bound by memory
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
     int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
+    int bvh_spec = 1;         // walk=3: a lane that reaches a leaf postpones it and keeps descending
+    int bvh_leaf = 4;         // walk=3: primitives per BVH leaf at most (1..8; read at scene upload)
     int upload_threads = 0;   // host threads of the primitive extraction at scene upload (0 = auto: one below 32 Ki entities, else up to 16)
-    int sort_rays = 1;        // tree scenes: reorder each bounce's ray queue by origin cell / kind / octant before the walk (ray_sort.cu)
+    int sort_rays = -1;       // tree scenes: reorder each bounce's ray queue by origin cell / kind / octant before the walk (ray_sort.cu).
+                              // -1 = auto: on for the octree walks (room scene 611 -> 566 ms), off for the BVH walk (397 with, 378 without:
+                              // its walk is short enough for the sort to cost more than the coherence brings)
     int ref_heavy = 128;      // REF mode: node expansions after which a ray is spread over many warps (ref_heavy_kernel; 0 = never)
     int l2_persist = 0;       // tree scenes: pin the primitive records in L2 (access policy window on the lanes' streams). Measured
                               // on the room scene: 869 ms with the window, 775 ms without -- the set-aside starves everything else; off
@@ -188,8 +194,8 @@ int path_build_tree_device(const float* d_boxes, uint32_t n_prims, const float r
                            uint32_t** d_index, uint32_t* n_index, int* tree_depth, std::string& err);
 // bvh_build.cu
 int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t n, const float root_lo[3], const float root_size[3],
-                          const PrimHot* d_hot, int leaf_max, cudaStream_t s, DeviceArray& nodes, DeviceArray& prims, uint32_t* root,
-                          std::string& err);
+                          const PrimHot* d_hot, int leaf_max, cudaStream_t s, DeviceArray& nodes, DeviceArray& nodes4, DeviceArray& prims,
+                          uint32_t* root, std::string& err);
 int path_build_top_table(const PathNodeD* d_nodes, int top_level, uint2* d_table, cudaStream_t s);
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err);
 int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_stats& stats, std::string& err);
@@ -244,6 +250,7 @@ struct PassArgs {
     int32_t raygen_occ;    // tree scenes: CTAs per SM of the camera-ray kernel (2 or 3)
     int32_t trace_occ;     // CTAs per SM of trace_kernel (3 or 4)
     int32_t bounce_occ;    // CTAs per SM of bounce_flat_kernel<diffuse> (3 or 4)
+    int32_t bvh_spec;      // BvhWalk: speculative traversal (PathTuning::bvh_spec)
     int32_t walk;          // tree walk variant (PathTuning::walk); +2 when the walk counts its node / primitive tests
 };
 

@@ -134,6 +134,7 @@ template <bool ALL> struct SceneAccess {
     int n_nodes_s;
     int walk_steps;      // tree walk: cell moves per round
     uint32_t leaf_batch; // tree walk: primitives tested per round
+    int bvh_spec;        // BvhWalk: a lane that reaches a leaf postpones it and keeps descending (speculative traversal)
     unsigned long long* coop; // tree walk, cooperative leaf tests: this warp's 32 result slots, or nullptr
     __device__ __forceinline__ uint2 node(uint32_t i) const {
         if (ALL || i < (uint32_t)n_nodes_s) return nodes_s[i];
@@ -178,6 +179,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     acc.n_nodes_s = a.stage_nodes;
     acc.walk_steps = a.walk_steps;
     acc.leaf_batch = uint32_t(a.leaf_batch);
+    acc.bvh_spec = a.bvh_spec;
     acc.coop = nullptr;
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
@@ -930,17 +932,30 @@ template <bool COUNT> struct TreeWalk2 {
 // The few primitives the host kept out of the hierarchy (walls around a mesh: their boxes would cover every level above
 // them) are tested first -- which also gives the walk a finite nearest-hit bound from its first node on.
 constexpr uint32_t kBvhLeaf = 0x80000000u, kBvhDone = 0xffffffffu;
-constexpr int kBvhStack = 64;
+constexpr int kBvhLocalStack = 40; // entries beyond the kBvhSmemStack levels in shared memory (path.h): rarely touched
 struct BvhWalk {
     float3 o, d, idir, ood;
     float best;
     uint32_t best_prim;
     uint32_t cur;  // node index, kBvhLeaf | (count - 1) << 28 | first, or kBvhDone
+    uint32_t pend; // a leaf reached but not tested yet (speculative traversal), 0 = none
     uint32_t any;
     int sp;
-    uint32_t stk[kBvhStack];
+    uint32_t stk[kBvhLocalStack];
 
-    __device__ __forceinline__ void pop() { cur = sp > 0 ? stk[--sp] : kBvhDone; }
+    // The postponed children: the first kBvhSmemStack levels in the thread's column of shared memory (the capture of the
+    // all-local form had 22 % of trace_kernel's stall samples on the push / pop lines), deeper ones in local memory.
+    __device__ __forceinline__ void push(uint32_t* __restrict__ smem, uint32_t v) {
+        if (sp < kBvhSmemStack) smem[sp * kThreads] = v;
+        else if (sp < kBvhSmemStack + kBvhLocalStack) stk[sp - kBvhSmemStack] = v;
+        else return;
+        ++sp;
+    }
+    __device__ __forceinline__ void pop(const uint32_t* __restrict__ smem) {
+        if (sp == 0) { cur = kBvhDone; return; }
+        --sp;
+        cur = sp < kBvhSmemStack ? smem[sp * kThreads] : stk[sp - kBvhSmemStack];
+    }
 
     template <bool ALL>
     __device__ __forceinline__ bool init(const SceneAccess<ALL>& S, float3 o_, float3 d_, float tmax, bool any_) {
@@ -951,6 +966,7 @@ struct BvhWalk {
         best_prim = kInvalid;
         any = any_ ? 1u : 0u;
         sp = 0;
+        pend = 0u;
         const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
         for (int k = 0; k < g.n_big; ++k) {
             const uint32_t id = __ldg(g.bvh_big + k);
@@ -978,8 +994,16 @@ struct BvhWalk {
         const int kWalkSteps = S.walk_steps;
         const float4* __restrict__ nodes = g.bvh_nodes;
 #pragma unroll 1
+        const bool spec = S.bvh_spec != 0;
         for (int it = 0; it < kWalkSteps; ++it) {
             __syncwarp();
+            // Speculative traversal (Aila & Laine 2009): a lane that arrives at a leaf while the others still descend
+            // puts the leaf aside and goes on with its next postponed node instead of idling until the leaf step. The
+            // nearest-hit bound is then one leaf behind, which can only cost visits, never a hit.
+            if (spec && active && pend == 0u && cur >= kBvhLeaf && cur != kBvhDone) {
+                pend = cur;
+                pop(S.stack);
+            }
             if (active && cur < kBvhLeaf) { // an internal node: both children's slabs
                 const float4* __restrict__ np = nodes + 4 * (size_t)cur;
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
@@ -998,20 +1022,20 @@ struct BvhWalk {
                 // (1 + 3 ulp on the far side: the products above round independently)
                 const bool h0 = t0n <= t0f * 1.0000004f, h1 = t1n <= t1f * 1.0000004f;
                 const uint32_t r0 = __float_as_uint(n3.x), r1 = __float_as_uint(n3.y);
-                if (h0 && h1) {
-                    const bool swap = t1n < t0n;
-                    cur = swap ? r1 : r0;
-                    if (sp < kBvhStack) stk[sp++] = swap ? r0 : r1;
-                } else if (h0 || h1) {
-                    cur = h0 ? r0 : r1;
-                } else {
-                    pop();
-                }
+                const bool both = h0 && h1, swap = both && t1n < t0n; // swap: child 1 is entered first
+                if (both) push(S.stack, swap ? r0 : r1);
+                if (h0 || h1) cur = (h0 && !swap) ? r0 : r1;
+                else pop(S.stack);
             }
         }
         __syncwarp();
-        if (active && cur >= kBvhLeaf && cur != kBvhDone) { // a leaf: its primitives, nearest so far kept
-            const uint32_t first = cur & 0x0fffffffu, cnt = ((cur >> 28) & 7u) + 1u;
+        if (active && pend == 0u && cur >= kBvhLeaf && cur != kBvhDone) { // the leaf the lane stands at
+            pend = cur;
+            pop(S.stack);
+        }
+        if (active && pend != 0u) { // a leaf: its primitives, nearest so far kept
+            const uint32_t first = pend & 0x0fffffffu, cnt = ((pend >> 28) & 7u) + 1u;
+            pend = 0u;
             const float4* __restrict__ pp = g.bvh_prims + 4 * (size_t)first;
 #pragma unroll 1
             for (uint32_t k = 0; k < cnt; ++k, pp += 4) {
@@ -1020,7 +1044,143 @@ struct BvhWalk {
                 if (t >= 0.0f) { best = t; best_prim = __float_as_uint(g0.w); }
             }
             if (any && best_prim != kInvalid) cur = kBvhDone;
-            else pop();
+        }
+        __syncwarp();
+        return active && cur == kBvhDone;
+    }
+};
+
+// ---- Bvh4Walk: the 4-wide, quantised form of the same hierarchy ---------------------------------------------
+// What the capture of the binary walk showed (profiles/r02m_*): issue 37 %, but the L1 data pipe at 81 % of its peak --
+// every lane pulls its own 64-byte node record through L1, four wavefronts per visit. Here the same four wavefronts
+// carry FOUR children (boxes as 16-bit coordinates on the root box's grid, bvh_build.cu), and a ray makes half as many
+// dependent visits. A coordinate q becomes a float with one byte permute and one subtraction (0x4B000000 | q is the
+// float 2^23 + q), the grid scale and the ray's origin are folded into the per-ray slab constants (sc, of), the hit
+// children are ordered by entry distance with a five-exchange network on (distance bits | slot) keys, nearest entered,
+// the others pushed farthest first.
+struct Bvh4Walk {
+    float3 o, d, sc, of; // slab parameter of grid coordinate q along x: q * sc.x + of.x
+    float best;
+    uint32_t best_prim;
+    uint32_t cur, pend, any;
+    int sp;
+    uint32_t stk[kBvhLocalStack];
+
+    __device__ __forceinline__ void push(uint32_t* __restrict__ smem, uint32_t v) {
+        if (sp < kBvhSmemStack) smem[sp * kThreads] = v;
+        else if (sp < kBvhSmemStack + kBvhLocalStack) stk[sp - kBvhSmemStack] = v;
+        else return;
+        ++sp;
+    }
+    __device__ __forceinline__ void pop(const uint32_t* __restrict__ smem) {
+        if (sp == 0) { cur = kBvhDone; return; }
+        --sp;
+        cur = sp < kBvhSmemStack ? smem[sp * kThreads] : stk[sp - kBvhSmemStack];
+    }
+
+    template <bool ALL>
+    __device__ __forceinline__ bool init(const SceneAccess<ALL>& S, float3 o_, float3 d_, float tmax, bool any_) {
+        const PathSceneD& g = *S.g;
+        o = o_;
+        d = d_;
+        best = tmax;
+        best_prim = kInvalid;
+        any = any_ ? 1u : 0u;
+        sp = 0;
+        pend = 0u;
+        const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
+        for (int k = 0; k < g.n_big; ++k) {
+            const uint32_t id = __ldg(g.bvh_big + k);
+            const float4* pp = hot + 4 * (size_t)id;
+            const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
+            const float t = hit_prim(a0, b0, c0, g0, o, d, best);
+            if (t >= 0.0f) {
+                best = t;
+                best_prim = id;
+                if (any_) return true;
+            }
+        }
+        float3 dd = d;
+        if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
+        if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
+        if (fabsf(dd.z) < 1.0e-20f) dd.z = copysignf(1.0e-20f, dd.z);
+        const float3 idir = f3(__fdividef(1.0f, dd.x), __fdividef(1.0f, dd.y), __fdividef(1.0f, dd.z));
+        sc = f3(g.root_size[0] * (1.0f / 65535.0f) * idir.x, g.root_size[1] * (1.0f / 65535.0f) * idir.y, g.root_size[2] * (1.0f / 65535.0f) * idir.z);
+        of = f3((g.root_lo[0] - o.x) * idir.x, (g.root_lo[1] - o.y) * idir.y, (g.root_lo[2] - o.z) * idir.z);
+        cur = g.bvh_root;
+        return cur == kBvhDone;
+    }
+
+    // 16-bit grid coordinate (low / high half of w) as a float: exact
+    __device__ __forceinline__ static float q_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f; }
+    __device__ __forceinline__ static float q_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
+
+    // entry distance of one child as an orderable key: distance bits with the slot number in the two lowest bits, or
+    // 0xffffffff when the slab test fails
+    __device__ __forceinline__ uint32_t child_key(float lox, float hix, float loy, float hiy, float loz, float hiz, float hi, uint32_t slot) const {
+        const float ax = fmaf(lox, sc.x, of.x), bx = fmaf(hix, sc.x, of.x);
+        const float ay = fmaf(loy, sc.y, of.y), by = fmaf(hiy, sc.y, of.y);
+        const float az = fmaf(loz, sc.z, of.z), bz = fmaf(hiz, sc.z, of.z);
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hi));
+        return tn <= tf * 1.0000004f ? ((__float_as_uint(tn) & ~3u) | slot) : 0xffffffffu;
+    }
+
+    template <bool ALL, bool COOP> __device__ __forceinline__ bool step(const SceneAccess<ALL>& S, bool active) {
+        const PathSceneD& g = *S.g;
+        const int kWalkSteps = S.walk_steps;
+        const uint4* __restrict__ nodes = g.bvh4_nodes;
+        const bool spec = S.bvh_spec != 0;
+#pragma unroll 1
+        for (int it = 0; it < kWalkSteps; ++it) {
+            __syncwarp();
+            if (spec && active && pend == 0u && cur >= kBvhLeaf && cur != kBvhDone) { // speculative traversal, see BvhWalk
+                pend = cur;
+                pop(S.stack);
+            }
+            if (active && cur < kBvhLeaf) {
+                const uint4* __restrict__ np = nodes + 4 * (size_t)cur;
+                const uint4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2), rf = __ldg(np + 3);
+                const float hi = best * 1.000002f + 1.0e-6f;
+                // (slots 0 and 1 are always filled; an empty slot 2 / 3 carries the reference kBvhDone)
+                uint32_t k0 = child_key(q_lo(bx.x), q_lo(bx.z), q_lo(by.x), q_lo(by.z), q_lo(bz.x), q_lo(bz.z), hi, 0u);
+                uint32_t k1 = child_key(q_hi(bx.x), q_hi(bx.z), q_hi(by.x), q_hi(by.z), q_hi(bz.x), q_hi(bz.z), hi, 1u);
+                uint32_t k2 = rf.z != kBvhDone ? child_key(q_lo(bx.y), q_lo(bx.w), q_lo(by.y), q_lo(by.w), q_lo(bz.y), q_lo(bz.w), hi, 2u) : 0xffffffffu;
+                uint32_t k3 = rf.w != kBvhDone ? child_key(q_hi(bx.y), q_hi(bx.w), q_hi(by.y), q_hi(by.w), q_hi(bz.y), q_hi(bz.w), hi, 3u) : 0xffffffffu;
+                // ascending order (misses last): five compare-exchanges
+                uint32_t t;
+                t = min(k0, k1); k1 = max(k0, k1); k0 = t;
+                t = min(k2, k3); k3 = max(k2, k3); k2 = t;
+                t = min(k0, k2); k2 = max(k0, k2); k0 = t;
+                t = min(k1, k3); k3 = max(k1, k3); k1 = t;
+                t = min(k1, k2); k2 = max(k1, k2); k1 = t;
+                auto ref_of = [&](uint32_t key) {
+                    const uint32_t sl = key & 3u;
+                    return sl == 0u ? rf.x : (sl == 1u ? rf.y : (sl == 2u ? rf.z : rf.w));
+                };
+                if (k3 != 0xffffffffu) push(S.stack, ref_of(k3));
+                if (k2 != 0xffffffffu) push(S.stack, ref_of(k2));
+                if (k1 != 0xffffffffu) push(S.stack, ref_of(k1));
+                if (k0 != 0xffffffffu) cur = ref_of(k0);
+                else pop(S.stack);
+            }
+        }
+        __syncwarp();
+        if (active && pend == 0u && cur >= kBvhLeaf && cur != kBvhDone) {
+            pend = cur;
+            pop(S.stack);
+        }
+        if (active && pend != 0u) {
+            const uint32_t first = pend & 0x0fffffffu, cnt = ((pend >> 28) & 7u) + 1u;
+            pend = 0u;
+            const float4* __restrict__ pp = g.bvh_prims + 4 * (size_t)first;
+#pragma unroll 1
+            for (uint32_t k = 0; k < cnt; ++k, pp += 4) {
+                const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
+                const float t = hit_prim(a0, b0, c0, g0, o, d, best);
+                if (t >= 0.0f) { best = t; best_prim = __float_as_uint(g0.w); }
+            }
+            if (any && best_prim != kInvalid) cur = kBvhDone;
         }
         __syncwarp();
         return active && cur == kBvhDone;
@@ -1031,6 +1191,7 @@ template <int WALK> struct WalkOf { using type = TreeWalk; };
 template <> struct WalkOf<1> { using type = TreeWalk2<false>; };
 template <> struct WalkOf<2> { using type = TreeWalk2<true>; };
 template <> struct WalkOf<3> { using type = BvhWalk; };
+template <> struct WalkOf<5> { using type = Bvh4Walk; };
 template <typename W> __device__ __forceinline__ void walk_counts(const W&, unsigned&, unsigned&) {}
 template <> __device__ __forceinline__ void walk_counts(const TreeWalk2<true>& w, unsigned& nodes, unsigned& prims) {
     nodes += w.n_node;
@@ -2227,7 +2388,8 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
         const int occ = a.raygen_occ; // tuning knob
         // 3 CTAs per SM at 80 registers (68 bytes of spills) beat 2 at 95: 23.8 vs 26.4 ms per 66 M camera rays
         void (*kernel)(PassArgs);
-        if (a.walk == 3) kernel = raygen_extend_kernel<3, false, 3>;
+        if (a.walk == 5) kernel = raygen_extend_kernel<3, false, 5>;
+        else if (a.walk == 3) kernel = raygen_extend_kernel<3, false, 3>;
         else if (a.walk == 2) kernel = a.coop_leaf ? raygen_extend_kernel<3, true, 2> : raygen_extend_kernel<3, false, 2>;
         else if (a.walk == 1) kernel = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true, 1> : raygen_extend_kernel<3, true, 1>)
                                                    : (occ == 2 ? raygen_extend_kernel<2, false, 1> : raygen_extend_kernel<3, false, 1>);
@@ -2242,7 +2404,8 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a);
     void (*kernel)(PassArgs, int);
-    if (a.walk == 3) kernel = a.trace_occ == 4 ? trace_kernel<false, 3, 4> : trace_kernel<false, 3, 3>;
+    if (a.walk == 5) kernel = a.trace_occ == 4 ? trace_kernel<false, 5, 4> : trace_kernel<false, 5, 3>;
+    else if (a.walk == 3) kernel = a.trace_occ == 4 ? trace_kernel<false, 3, 4> : trace_kernel<false, 3, 3>;
     else if (a.walk == 2) kernel = a.coop_leaf ? trace_kernel<true, 2> : trace_kernel<false, 2>;
     else if (a.walk == 1) kernel = a.coop_leaf ? (a.trace_occ == 4 ? trace_kernel<true, 1, 4> : trace_kernel<true, 1, 3>) : trace_kernel<false, 1>;
     else kernel = a.coop_leaf ? trace_kernel<true, 0> : trace_kernel<false, 0>;

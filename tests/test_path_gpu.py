@@ -300,7 +300,7 @@ def test_flat_then_tree_scene_on_one_context(g19, abi):
 @pytest.mark.parametrize("which,n,w,h,spp,depth", [("HEIGHTFIELD", 24, 64, 36, 4, 4), ("HEIGHTFIELD_ROOM", 40, 96, 54, 4, 5),
                                                     ("HEIGHTFIELD_ROOM", 150, 160, 90, 2, 4), ("ZOO", 0, 120, 120, 8, 4)])
 def test_bvh_walk_matches_oracle_and_octree(g19, abi, oracle, which, n, w, h, spp, depth):
-    """tune walk=3: the bounding-volume hierarchy (csrc/bvh_build.cu, BvhWalk) instead of the linear octree. Same
+    """tune walk=3 / 4: the bounding-volume hierarchy (csrc/bvh_build.cu; BvhWalk binary, Bvh4Walk 4-wide) instead of the linear octree. Same
     nearest hits, so the same radiance as the brute-force oracle and as the octree walk (they may part ways only where
     two primitives tie in t along a shared edge), same segment counts. n = 150 builds both trees on the device."""
     if which == "ZOO":
@@ -312,7 +312,7 @@ def test_bvh_walk_matches_oracle_and_octree(g19, abi, oracle, which, n, w, h, sp
     else:
         sc, cam, light = g19.Octree.builtin(getattr(abi, "SCENE_" + which), n=n, w=w, h=h)
     outs = {}
-    for walk in (1, 3):
+    for walk in (1, 3, 4):
         rt = g19.RayTracer(cam, light)
         rt.tune("walk", walk)
         rt.setScene(sc)
@@ -331,3 +331,4 @@ def test_bvh_walk_matches_oracle_and_octree(g19, abi, oracle, which, n, w, h, sp
         assert abs(ext - segs[0]) <= 1e-3 * segs[0] + 2
         assert abs(shd - segs[1]) <= 1e-3 * segs[1] + 2
     assert rel_rmse(outs[3][0], outs[1][0]) <= 2e-3
+    assert rel_rmse(outs[4][0], outs[1][0]) <= 2e-3
