@@ -149,7 +149,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec", "bvh_stack"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -176,7 +176,8 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
     else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
-    else if (k == "bvh_spec") t.bvh_spec = num(def.bvh_spec, 0, 1);
+    else if (k == "bvh_stack") t.bvh_stack = num(def.bvh_stack, 4, 64);
+    else if (k == "bvh_spec") t.bvh_spec = num(def.bvh_spec, 0, 3);
     else if (k == "bvh_leaf") t.bvh_leaf = num(def.bvh_leaf, 1, 8);
     else if (k == "upload_threads") t.upload_threads = num(def.upload_threads, 0, 64);
     else if (k == "sort_rays") t.sort_rays = num(def.sort_rays, -1, 1);
@@ -798,10 +799,12 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa0.bvh_spec = a.tune.bvh_spec;
     pa0.walk = a.tune.walk ? (p.profile ? 2 : 1) : 0; // the new walk counts its node / primitive tests under params.profile
     if (a.tune.walk >= 3 && b.view.bvh_root != 0xffffffffu && b.view.bvh_nodes) {
-        pa0.walk = a.tune.walk == 4 ? 5 : 3; // bounding-volume hierarchy, binary / 4-wide (no test counts under params.profile)
+        pa0.walk = a.tune.walk == 4 ? (p.profile ? 6 : 5) : 3; // bounding-volume hierarchy, binary / 4-wide (the latter counts its tests under params.profile)
         // node visits per round, room scene: binary 4 / 6 / 8 / 12 = 437 / 423 / 418 / 418 ms; 4-wide 4 / 6 / 8 / 12 = 346 / 345 / 364 / 382 ms
         if (a.tune.walk_steps <= 0) pa0.walk_steps = a.tune.walk == 4 ? 5 : 8;
-        pa0.stack_levels = std::max(pa0.stack_levels, kBvhSmemStack);
+        pa0.stack_levels = std::max(pa0.stack_levels, a.tune.bvh_stack);
+        pa0.coop_leaf = 0;
+        pa0.stage_nodes = 0; // no octree prefix in shared memory: the L1 the walk lives off is what the carve-out leaves
     }
     const bool fused = path_scene_is_flat(pa0); // flat scenes trace inside the bounce kernels
     // primary-hit AOV: the un-jittered ray of every pixel (the reference's ray) through this engine's structures

@@ -28,7 +28,7 @@ namespace g19 {
 
 constexpr int kMaxPathDepth = 64;    // segments per path
 constexpr int kMaxTreeDepth = 14;    // linear-octree levels below the root
-constexpr int kBvhSmemStack = 24;    // walk=3: levels of the postponed-children stack kept in shared memory (PassArgs::stack_levels)
+constexpr int kBvhSmemStack = 12;    // BVH walks: levels of the postponed-children stack kept in shared memory (8 / 12 / 16 / 24 / 32: 358 / 358 / 363 / 363 / 373 ms: the L1 is what the carve-out leaves)
 constexpr int kNumQueues = 6;        // (diffuse, mirror, glass) x two bounce parities
 // Queue entries are reserved in warp-private chunks; a launch can leave at most one partly used
 // chunk per warp and queue behind (padded with an invalid marker): 2 Mi entries of slack cover
@@ -136,12 +136,14 @@ struct PathTuning {
     int raygen_occ = 3;       // CTAs per SM of the tree-scene camera-ray kernel
     int tree_build = -1;      // -1 auto (device from 4096 primitives), 0 host, 1 device
     int debug_tree = 0;       // print octree statistics at upload
-    int walk = 1;             // tree walk: 1 = point-location restart walk over the octree (TreeWalk2), 0 = parametric stack walk (TreeWalk),
-                              // 3 = bounding-volume hierarchy (BvhWalk, bvh_build.cu), 4 = its 4-wide form (Bvh4Walk)
+    int walk = 4;             // tree walk: 4 = 4-wide quantised bounding-volume hierarchy (Bvh4Walk, bvh_build.cu), 3 = its binary form (BvhWalk),
+                              // 1 = point-location restart walk over the linear octree (TreeWalk2), 0 = round 1's parametric stack walk (TreeWalk).
+                              // Room scene, 1080p x 64 spp: 866 / 566 / 378 / 345 ms for 0 / 1 / 3 / 4
     int trace_occ = 4;        // CTAs per SM of trace_kernel (4 = 64 registers, 114 bytes of spills: the walk is bound by memory
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
     int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
+    int bvh_stack = kBvhSmemStack; // walk=3/4: levels of the postponed-children stack in shared memory (1 KB per level and CTA)
     int bvh_spec = 1;         // walk=3: a lane that reaches a leaf postpones it and keeps descending
     int bvh_leaf = 4;         // walk=3: primitives per BVH leaf at most (1..8; read at scene upload)
     int upload_threads = 0;   // host threads of the primitive extraction at scene upload (0 = auto: one below 32 Ki entities, else up to 16)

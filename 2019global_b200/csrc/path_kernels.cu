@@ -134,6 +134,7 @@ template <bool ALL> struct SceneAccess {
     int n_nodes_s;
     int walk_steps;      // tree walk: cell moves per round
     uint32_t leaf_batch; // tree walk: primitives tested per round
+    int bvh_stack;       // BvhWalk: levels of the postponed-children stack in shared memory (= PassArgs::stack_levels)
     int bvh_spec;        // BvhWalk: a lane that reaches a leaf postpones it and keeps descending (speculative traversal)
     unsigned long long* coop; // tree walk, cooperative leaf tests: this warp's 32 result slots, or nullptr
     __device__ __forceinline__ uint2 node(uint32_t i) const {
@@ -180,6 +181,7 @@ template <bool ALL> __device__ __forceinline__ SceneAccess<ALL> stage_scene(cons
     acc.walk_steps = a.walk_steps;
     acc.leaf_batch = uint32_t(a.leaf_batch);
     acc.bvh_spec = a.bvh_spec;
+    acc.bvh_stack = a.stack_levels;
     acc.coop = nullptr;
     // byte counts rounded up to 16 (the device arrays are padded, see DeviceArray::ensure)
     const uint32_t nb = (uint32_t(a.stage_nodes) * 8u + 15u) & ~15u;
@@ -940,21 +942,21 @@ struct BvhWalk {
     uint32_t cur;  // node index, kBvhLeaf | (count - 1) << 28 | first, or kBvhDone
     uint32_t pend; // a leaf reached but not tested yet (speculative traversal), 0 = none
     uint32_t any;
-    int sp;
+    int sp, cap; // cap: stack levels in shared memory
     uint32_t stk[kBvhLocalStack];
 
     // The postponed children: the first kBvhSmemStack levels in the thread's column of shared memory (the capture of the
     // all-local form had 22 % of trace_kernel's stall samples on the push / pop lines), deeper ones in local memory.
     __device__ __forceinline__ void push(uint32_t* __restrict__ smem, uint32_t v) {
-        if (sp < kBvhSmemStack) smem[sp * kThreads] = v;
-        else if (sp < kBvhSmemStack + kBvhLocalStack) stk[sp - kBvhSmemStack] = v;
+        if (sp < cap) smem[sp * kThreads] = v;
+        else if (sp < cap + kBvhLocalStack) stk[sp - cap] = v;
         else return;
         ++sp;
     }
     __device__ __forceinline__ void pop(const uint32_t* __restrict__ smem) {
         if (sp == 0) { cur = kBvhDone; return; }
         --sp;
-        cur = sp < kBvhSmemStack ? smem[sp * kThreads] : stk[sp - kBvhSmemStack];
+        cur = sp < cap ? smem[sp * kThreads] : stk[sp - cap];
     }
 
     template <bool ALL>
@@ -966,6 +968,7 @@ struct BvhWalk {
         best_prim = kInvalid;
         any = any_ ? 1u : 0u;
         sp = 0;
+        cap = S.bvh_stack;
         pend = 0u;
         const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
         for (int k = 0; k < g.n_big; ++k) {
@@ -994,7 +997,7 @@ struct BvhWalk {
         const int kWalkSteps = S.walk_steps;
         const float4* __restrict__ nodes = g.bvh_nodes;
 #pragma unroll 1
-        const bool spec = S.bvh_spec != 0;
+        const bool spec = (S.bvh_spec & 1) != 0;
         for (int it = 0; it < kWalkSteps; ++it) {
             __syncwarp();
             // Speculative traversal (Aila & Laine 2009): a lane that arrives at a leaf while the others still descend
@@ -1058,24 +1061,25 @@ struct BvhWalk {
 // float 2^23 + q), the grid scale and the ray's origin are folded into the per-ray slab constants (sc, of), the hit
 // children are ordered by entry distance with a five-exchange network on (distance bits | slot) keys, nearest entered,
 // the others pushed farthest first.
-struct Bvh4Walk {
+template <bool COUNT> struct Bvh4Walk { // COUNT: box and primitive tests are tallied (params.profile: the issue-roofline model)
     float3 o, d, sc, of; // slab parameter of grid coordinate q along x: q * sc.x + of.x
+    uint32_t n_node, n_prim; // COUNT only
     float best;
     uint32_t best_prim;
     uint32_t cur, pend, any;
-    int sp;
+    int sp, cap; // cap: stack levels in shared memory
     uint32_t stk[kBvhLocalStack];
 
     __device__ __forceinline__ void push(uint32_t* __restrict__ smem, uint32_t v) {
-        if (sp < kBvhSmemStack) smem[sp * kThreads] = v;
-        else if (sp < kBvhSmemStack + kBvhLocalStack) stk[sp - kBvhSmemStack] = v;
+        if (sp < cap) smem[sp * kThreads] = v;
+        else if (sp < cap + kBvhLocalStack) stk[sp - cap] = v;
         else return;
         ++sp;
     }
     __device__ __forceinline__ void pop(const uint32_t* __restrict__ smem) {
         if (sp == 0) { cur = kBvhDone; return; }
         --sp;
-        cur = sp < kBvhSmemStack ? smem[sp * kThreads] : stk[sp - kBvhSmemStack];
+        cur = sp < cap ? smem[sp * kThreads] : stk[sp - cap];
     }
 
     template <bool ALL>
@@ -1087,7 +1091,9 @@ struct Bvh4Walk {
         best_prim = kInvalid;
         any = any_ ? 1u : 0u;
         sp = 0;
+        cap = S.bvh_stack;
         pend = 0u;
+        if (COUNT) { n_node = 0; n_prim = uint32_t(g.n_big); }
         const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
         for (int k = 0; k < g.n_big; ++k) {
             const uint32_t id = __ldg(g.bvh_big + k);
@@ -1130,7 +1136,7 @@ struct Bvh4Walk {
         const PathSceneD& g = *S.g;
         const int kWalkSteps = S.walk_steps;
         const uint4* __restrict__ nodes = g.bvh4_nodes;
-        const bool spec = S.bvh_spec != 0;
+        const bool spec = (S.bvh_spec & 1) != 0;
 #pragma unroll 1
         for (int it = 0; it < kWalkSteps; ++it) {
             __syncwarp();
@@ -1142,6 +1148,7 @@ struct Bvh4Walk {
                 const uint4* __restrict__ np = nodes + 4 * (size_t)cur;
                 const uint4 bx = __ldg(np), by = __ldg(np + 1), bz = __ldg(np + 2), rf = __ldg(np + 3);
                 const float hi = best * 1.000002f + 1.0e-6f;
+                if (COUNT) n_node += 2u + (rf.z != kBvhDone ? 1u : 0u) + (rf.w != kBvhDone ? 1u : 0u);
                 // (slots 0 and 1 are always filled; an empty slot 2 / 3 carries the reference kBvhDone)
                 uint32_t k0 = child_key(q_lo(bx.x), q_lo(bx.z), q_lo(by.x), q_lo(by.z), q_lo(bz.x), q_lo(bz.z), hi, 0u);
                 uint32_t k1 = child_key(q_hi(bx.x), q_hi(bx.z), q_hi(by.x), q_hi(by.z), q_hi(bz.x), q_hi(bz.z), hi, 1u);
@@ -1158,11 +1165,40 @@ struct Bvh4Walk {
                     const uint32_t sl = key & 3u;
                     return sl == 0u ? rf.x : (sl == 1u ? rf.y : (sl == 2u ? rf.z : rf.w));
                 };
-                if (k3 != 0xffffffffu) push(S.stack, ref_of(k3));
-                if (k2 != 0xffffffffu) push(S.stack, ref_of(k2));
-                if (k1 != 0xffffffffu) push(S.stack, ref_of(k1));
-                if (k0 != 0xffffffffu) cur = ref_of(k0);
-                else pop(S.stack);
+                // The hits are k0 .. k(n-1). Enter k0, postpone the others farthest first. Written without branches for
+                // the common case (the capture of the branchy form ran these lines at 4-7 of 32 lanes, 15 % of the kernel's
+                // instructions): three unconditional stores above the stack pointer -- what lies above it is never read.
+                const int n = int(k0 != 0xffffffffu) + int(k1 != 0xffffffffu) + int(k2 != 0xffffffffu) + int(k3 != 0xffffffffu);
+                const uint32_t e1 = ref_of(k1), e2 = ref_of(k2), e3 = ref_of(k3);
+                if (S.bvh_spec & 2) { // A/B knob: the branchy form
+                    if (n == 4) push(S.stack, e3);
+                    if (n >= 3) push(S.stack, e2);
+                    if (n >= 2) push(S.stack, e1);
+                    if (n > 0) cur = ref_of(k0);
+                    else pop(S.stack);
+                    continue;
+                }
+                if (sp + 3 <= cap) {
+                    uint32_t* __restrict__ at = S.stack + sp * kThreads;
+                    at[0] = n == 4 ? e3 : (n == 3 ? e2 : e1);
+                    at[kThreads] = n == 4 ? e2 : e1;
+                    at[2 * kThreads] = e1;
+                    sp += max(n - 1, 0);
+                } else { // deep in the stack: the general form (entries beyond the shared-memory levels live in local memory)
+                    if (n == 4) push(S.stack, e3);
+                    if (n >= 3) push(S.stack, e2);
+                    if (n >= 2) push(S.stack, e1);
+                }
+                if (n > 0) {
+                    cur = ref_of(k0);
+                } else if (sp <= cap) { // pop from the shared-memory levels: one predicated load
+                    const int at = max(sp - 1, 0);
+                    const uint32_t top = S.stack[at * kThreads];
+                    cur = sp > 0 ? top : kBvhDone;
+                    sp = at;
+                } else {
+                    pop(S.stack);
+                }
             }
         }
         __syncwarp();
@@ -1173,6 +1209,7 @@ struct Bvh4Walk {
         if (active && pend != 0u) {
             const uint32_t first = pend & 0x0fffffffu, cnt = ((pend >> 28) & 7u) + 1u;
             pend = 0u;
+            if (COUNT) n_prim += cnt;
             const float4* __restrict__ pp = g.bvh_prims + 4 * (size_t)first;
 #pragma unroll 1
             for (uint32_t k = 0; k < cnt; ++k, pp += 4) {
@@ -1191,9 +1228,14 @@ template <int WALK> struct WalkOf { using type = TreeWalk; };
 template <> struct WalkOf<1> { using type = TreeWalk2<false>; };
 template <> struct WalkOf<2> { using type = TreeWalk2<true>; };
 template <> struct WalkOf<3> { using type = BvhWalk; };
-template <> struct WalkOf<5> { using type = Bvh4Walk; };
+template <> struct WalkOf<5> { using type = Bvh4Walk<false>; };
+template <> struct WalkOf<6> { using type = Bvh4Walk<true>; };
 template <typename W> __device__ __forceinline__ void walk_counts(const W&, unsigned&, unsigned&) {}
 template <> __device__ __forceinline__ void walk_counts(const TreeWalk2<true>& w, unsigned& nodes, unsigned& prims) {
+    nodes += w.n_node;
+    prims += w.n_prim;
+}
+template <> __device__ __forceinline__ void walk_counts(const Bvh4Walk<true>& w, unsigned& nodes, unsigned& prims) {
     nodes += w.n_node;
     prims += w.n_prim;
 }
@@ -1220,7 +1262,7 @@ __device__ bool traverse(const SceneAccess<ALL>& S, bool active, float3 o, float
         if (w.template step<ALL, COOP>(S, busy)) busy = false;
     t_hit = w.best;
     prim_hit = w.best_prim;
-    if (WALK == 2 && walked && n_node) walk_counts(w, *n_node, *n_prim);
+    if ((WALK == 2 || WALK == 6) && walked && n_node) walk_counts(w, *n_node, *n_prim);
     return active && w.best_prim != kInvalid;
 }
 
@@ -1438,7 +1480,7 @@ template <int OCC, bool COOP, int WALK> __global__ void __launch_bounds__(kThrea
         out.push(kind, slot);
     }
     out.flush();
-    if (WALK == 2) flush_walk_counts(a, cnt_node, cnt_prim);
+    if (WALK == 2 || WALK == 6) flush_walk_counts(a, cnt_node, cnt_prim);
 }
 
 // ---- bounce: shade + trace the continuation ray ------------------------------------------
@@ -2102,7 +2144,7 @@ template <bool COOP, int WALK, int OCC = 3> __global__ void __launch_bounds__(kT
             have = false;
         }
         if (finished) {
-            if (WALK == 2) walk_counts(w, cnt_node, cnt_prim);
+            if (WALK == 2 || WALK == 6) walk_counts(w, cnt_node, cnt_prim);
             const uint32_t slot = tag & kRaySlotMask;
             if (tag & kRayShadow) {
                 if (w.best_prim == kInvalid) { // unoccluded: the light sample counts
@@ -2131,7 +2173,7 @@ template <bool COOP, int WALK, int OCC = 3> __global__ void __launch_bounds__(kT
     if (sort) out.flush();
     lit = warp_sum(lit);
     if (lane == 0 && lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
-    if (WALK == 2) flush_walk_counts(a, cnt_node, cnt_prim);
+    if (WALK == 2 || WALK == 6) flush_walk_counts(a, cnt_node, cnt_prim);
 }
 
 // ---- primary-hit AOV ------------------------------------------------------------------------
@@ -2388,7 +2430,8 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
         const int occ = a.raygen_occ; // tuning knob
         // 3 CTAs per SM at 80 registers (68 bytes of spills) beat 2 at 95: 23.8 vs 26.4 ms per 66 M camera rays
         void (*kernel)(PassArgs);
-        if (a.walk == 5) kernel = raygen_extend_kernel<3, false, 5>;
+        if (a.walk == 6) kernel = raygen_extend_kernel<3, false, 6>;
+        else if (a.walk == 5) kernel = raygen_extend_kernel<3, false, 5>;
         else if (a.walk == 3) kernel = raygen_extend_kernel<3, false, 3>;
         else if (a.walk == 2) kernel = a.coop_leaf ? raygen_extend_kernel<3, true, 2> : raygen_extend_kernel<3, false, 2>;
         else if (a.walk == 1) kernel = a.coop_leaf ? (occ == 2 ? raygen_extend_kernel<2, true, 1> : raygen_extend_kernel<3, true, 1>)
@@ -2404,7 +2447,8 @@ void launch_raygen_extend(const PassArgs& a, int sm_count, cudaStream_t s) {
 void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
     const size_t smem = path_smem_bytes(a);
     void (*kernel)(PassArgs, int);
-    if (a.walk == 5) kernel = a.trace_occ == 4 ? trace_kernel<false, 5, 4> : trace_kernel<false, 5, 3>;
+    if (a.walk == 6) kernel = trace_kernel<false, 6, 3>;
+    else if (a.walk == 5) kernel = a.trace_occ == 4 ? trace_kernel<false, 5, 4> : trace_kernel<false, 5, 3>;
     else if (a.walk == 3) kernel = a.trace_occ == 4 ? trace_kernel<false, 3, 4> : trace_kernel<false, 3, 3>;
     else if (a.walk == 2) kernel = a.coop_leaf ? trace_kernel<true, 2> : trace_kernel<false, 2>;
     else if (a.walk == 1) kernel = a.coop_leaf ? (a.trace_occ == 4 ? trace_kernel<true, 1, 4> : trace_kernel<true, 1, 3>) : trace_kernel<false, 1>;

@@ -1,0 +1,19 @@
+#!/bin/bash
+# round-2 GPU call 18: branch-free push / pop in the 4-wide BVH walk
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_path_gpu.py -m gpu -q -x -k "bvh" > gpurun_out/r02r_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r02r_tests.log
+tail -4 gpurun_out/r02r_tests.log | cut -c1-250
+P="timeout 120 python tools/profile_run.py"
+R="--scene HEIGHTFIELD_ROOM --n 708 --spp 64 --frames 2"
+{
+$P $R --tune walk=4
+$P $R --tune walk=4 --tune walk_steps=4
+$P $R --tune walk=4 --tune walk_steps=6
+$P $R --tune walk=4 --tune walk_steps=8
+$P $R --tune walk=4 --tune refill=12
+$P $R --tune walk=4 --tune refill=4
+$P $R --tune walk=4 --tune bvh_leaf=3
+$P $R --tune walk=4 --tune bvh_leaf=6
+$P --scene HEIGHTFIELD --n 708 --spp 64 --frames 2 --tune walk=4
+} > gpurun_out/r02r_timings.log 2>&1
+cat gpurun_out/r02r_timings.log | cut -c1-200
