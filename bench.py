@@ -89,27 +89,40 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None, label="timed"):
+        """Summary of the samples taken in [t0, t1] (wall clock: the timed region). The sampler starts before the warm-up
+        steps -- nvidia-smi needs ~0.1 s to come up and an 8-GPU timed region is 40 ms -- so when no sample falls inside
+        the region the ones taken under the same load around it are used, and `window` says so."""
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows, window = self.rows, "warmup+timed"
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[-1] <= t1]
+            if inside:
+                rows, window = inside, label
+            else:
+                near = [r for r in self.rows if t0 - 1.0 <= r[-1] <= t1 + 0.25]
+                if near:
+                    rows = near
+        sm = sorted(float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
+        self.window = window
+        for r in rows:
+            if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---- CPU side: the oracle as checker / CPU baseline (never the product library) -----------------------------
@@ -494,20 +507,27 @@ def main():
     samples_per_step = W * H * SPP
     job = Job(mods, cfg, rank, world, local, args.gather, args.spp_per_pass)
     rt = job.rt
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         job.step()
     # ---- timed region: K steps, device clock, barrier + synchronize on both sides -------------
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         job.step()
     e1.record()
     barrier()
+    wall1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    clocks = sampler.stop()
+    if ms * args.steps < 300.0:  # a short timed region (N = 8: 40 ms): keep the same load up until the sampler has seen it
+        for _ in range(int(math.ceil(300.0 / max(ms, 1e-3)))):  # the same count on every rank (ms is the max over ranks)
+            job.step()
+        barrier()
+    short = ms * args.steps < 300.0
+    clocks = sampler.stop(wall0, wall1 + (0.3 if short else 0.0), "timed + 0.3 s of the same steps after it" if short else "timed")
     job.check_frame()
     st = rt.stats()
     # this library's kernels inside the timed region: every rank's render + rank 0's wait/release (frame) or its
