@@ -187,6 +187,29 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     return true;
 }
 
+// Primitive PAIRS for the packed-FP32 loops of path_kernels.cu (plane_pairs / sphere_roots2): `hot[first ...]` holds
+// n_par parallelograms, then n_tri triangles, then n_sph spheres. Planar pair = rows a, b, c with every coefficient a
+// float2 (primitive 2j, 2j+1), 96 B; sphere pair = (-centre, radius^2) as float2s, 32 B. Each kind group is padded to an
+// even count with NaNs: every comparison on a NaN fails, so a padding record is never hit.
+static void build_pairs(const std::vector<PrimHot>& hot, size_t first, size_t n_par, size_t n_tri, size_t n_sph, std::vector<float>& pairs) {
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    auto planar = [&](size_t f, size_t count) {
+        for (size_t k = 0; k < count; k += 2)
+            for (int c = 0; c < 12; ++c)
+                for (size_t e = 0; e < 2; ++e) pairs.push_back(k + e < count ? hot[f + k + e].q[c] : nan);
+    };
+    planar(first, n_par);
+    planar(first + n_par, n_tri);
+    const size_t s0 = first + n_par + n_tri;
+    for (size_t k = 0; k < n_sph; k += 2)
+        for (int c = 0; c < 4; ++c)
+            for (size_t e = 0; e < 2; ++e) {
+                float v = nan;
+                if (k + e < n_sph) v = c < 3 ? -hot[s0 + k + e].q[c] : hot[s0 + k + e].q[3] * hot[s0 + k + e].q[3];
+                pairs.push_back(v);
+            }
+}
+
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err) {
     const auto t_start = std::chrono::steady_clock::now();
     ++b.upload_serial;
@@ -553,24 +576,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     // 96 B; sphere pair = (-centre, radius^2) as float2s, 32 B. Each kind group is padded to an even
     // count with NaNs: every comparison on a NaN fails, so a padding record is never hit.
     std::vector<float> pairs;
-    if (!on_device && nodes.size() == 1) {
-        const float nan = std::numeric_limits<float>::quiet_NaN();
-        auto planar = [&](size_t first, size_t count) {
-            for (size_t k = 0; k < count; k += 2)
-                for (int c = 0; c < 12; ++c)
-                    for (size_t e = 0; e < 2; ++e) pairs.push_back(k + e < count ? hot[first + k + e].q[c] : nan);
-        };
-        planar(0, size_t(n_par));
-        planar(size_t(n_par), size_t(n_tri));
-        const size_t s0 = size_t(n_par) + size_t(n_tri), ns = hot.size() - s0;
-        for (size_t k = 0; k < ns; k += 2)
-            for (int c = 0; c < 4; ++c)
-                for (size_t e = 0; e < 2; ++e) {
-                    float v = nan;
-                    if (k + e < ns) v = c < 3 ? -hot[s0 + k + e].q[c] : hot[s0 + k + e].q[3] * hot[s0 + k + e].q[3];
-                    pairs.push_back(v);
-                }
-    }
+    if (!on_device && nodes.size() == 1) build_pairs(hot, 0, size_t(n_par), size_t(n_tri), hot.size() - size_t(n_par) - size_t(n_tri), pairs);
     auto up = [&](DeviceArray& d, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = d.ensure(bytes ? bytes : 16);
         if (e != cudaSuccess || !bytes) return e;
@@ -631,7 +637,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     v.bvh4_nodes = nullptr;
     v.bvh_prims = nullptr;
     v.bvh_big = nullptr;
-    v.n_big = 0;
+    v.bvh_big_pairs = nullptr;
+    v.n_big = v.big_par = v.big_tri = 0;
     v.bvh_root = 0xffffffffu;
     if (tune.walk >= 3 && v.n_nodes > 1) {
         const auto t_bvh = std::chrono::steady_clock::now();
@@ -650,7 +657,21 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
         std::vector<uint32_t> big_ids;
         std::vector<char> is_big(prims.size(), 0);
         for (auto& l : large) { big_ids.push_back(l.second); is_big[l.second] = 1; }
-        std::sort(big_ids.begin(), big_ids.end());
+        // kind-sorted (parallelograms | triangles | spheres, by id inside a kind) for the pair loops that test them
+        auto kind_rank = [&](uint32_t id) { return prims[id].hot.q[14] == 2.0f ? 0 : (prims[id].hot.q[14] == 1.0f ? 1 : 2); };
+        std::sort(big_ids.begin(), big_ids.end(), [&](uint32_t x, uint32_t y) {
+            const int rx = kind_rank(x), ry = kind_rank(y);
+            return rx < ry || (rx == ry && x < y);
+        });
+        std::vector<PrimHot> big_hot;
+        size_t big_par = 0, big_tri = 0;
+        for (uint32_t id : big_ids) {
+            big_hot.push_back(hot[id]);
+            if (kind_rank(id) == 0) ++big_par;
+            else if (kind_rank(id) == 1) ++big_tri;
+        }
+        std::vector<float> big_pairs;
+        build_pairs(big_hot, 0, big_par, big_tri, big_hot.size() - big_par - big_tri, big_pairs);
         std::vector<uint32_t> small_ids;
         small_ids.reserve(prims.size());
         for (size_t i = 0; i < prims.size(); ++i)
@@ -668,6 +689,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
         if (be == cudaSuccess && !small_ids.empty())
             be = cudaMemcpyAsync(d_small.p, small_ids.data(), small_ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
         if (be == cudaSuccess) be = up(b.bvh_big, big_ids.data(), big_ids.size() * sizeof(uint32_t));
+        if (be == cudaSuccess) be = up(b.bvh_big_pairs, big_pairs.data(), big_pairs.size() * sizeof(float));
         if (be == cudaSuccess) be = cudaStreamSynchronize(stream);
         int rc = G19_OK;
         if (be != cudaSuccess) {
@@ -685,6 +707,9 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
         v.bvh_prims = static_cast<const float4*>(b.bvh_prims.p);
         v.bvh_big = static_cast<const uint32_t*>(b.bvh_big.p);
         v.n_big = int32_t(big_ids.size());
+        v.bvh_big_pairs = static_cast<const float*>(b.bvh_big_pairs.p);
+        v.big_par = int32_t(big_par);
+        v.big_tri = int32_t(big_tri);
         if (tune.debug_tree)
             std::fprintf(stderr, "[g19] path bvh: %zu primitives in the hierarchy, %zu kept out (big), built in %.1f ms\n", small_ids.size(),
                          big_ids.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_bvh).count());
@@ -702,7 +727,7 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
 }
 
 void path_release(PathSceneBuffers& b, PathWork& w) {
-    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &b.bvh_nodes, &b.bvh4_nodes, &b.bvh_prims, &b.bvh_big, &w.totals, &w.accum,
+    for (DeviceArray* d : {&b.nodes, &b.prim_index, &b.hot, &b.cold, &b.materials, &b.lights, &b.pairs, &b.prim_entity, &b.top, &b.bvh_nodes, &b.bvh4_nodes, &b.bvh_prims, &b.bvh_big, &b.bvh_big_pairs, &w.totals, &w.accum,
                            &w.rad_l, &w.rgb_l, &w.iota})
         d->release();
     w.iota_n = 0;

@@ -56,8 +56,10 @@ struct PathSceneD {
     const float4* bvh_nodes; // 4 x float4 per internal node: both children's boxes and references
     const uint4* bvh4_nodes; // the 4-wide form (walk=4): 64 B per node, boxes quantised to 16 bits on the root box's grid
     const float4* bvh_prims; // the hot records in leaf order, original primitive id in row 3 .w
-    const uint32_t* bvh_big; // primitives kept out of the hierarchy (much larger than the rest): tested up front
-    int32_t n_big;
+    const uint32_t* bvh_big; // primitives kept out of the hierarchy (much larger than the rest): tested up front,
+    int32_t n_big;           // kind-sorted (big_par parallelograms, big_tri triangles, spheres) ...
+    const float* bvh_big_pairs; // ... as primitive PAIRS through the packed-FP32 loops of the flat scenes
+    int32_t big_par, big_tri;
     uint32_t bvh_root;       // node index, leaf reference, or 0xffffffff (nothing in the hierarchy)
 };
 
@@ -74,7 +76,7 @@ struct DeviceArray {
 
 struct PathSceneBuffers {
     DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity, top;
-    DeviceArray bvh_nodes, bvh4_nodes, bvh_prims, bvh_big;
+    DeviceArray bvh_nodes, bvh4_nodes, bvh_prims, bvh_big, bvh_big_pairs;
     PathSceneD view{};
     bool has_bsdf[4] = {false, false, false, false};
     unsigned long long upload_serial = 0; // counts path_upload calls: a new number = a different scene

@@ -933,8 +933,41 @@ template <bool COUNT> struct TreeWalk2 {
 // postponed children lives in local memory (L1): an LBVH over 30-bit Morton codes is at most ~40 levels deep.
 // The few primitives the host kept out of the hierarchy (walls around a mesh: their boxes would cover every level above
 // them) are tested first -- which also gives the walk a finite nearest-hit bound from its first node on.
+// The primitives the host kept out of the hierarchy, nearest hit within `best`: the flat scenes' pair loops (two
+// primitives per packed-FP32 instruction, kind-sorted, no branch per primitive) over records every lane reads from the
+// same addresses. Round 2 capture: the room's seven big primitives were 2/3 of all primitive tests of the BVH walk.
+__device__ __forceinline__ void bvh_big_hits(const PathSceneD& g, float3 o, float3 d, float& best, uint32_t& best_prim) {
+    if (g.n_big == 0) return;
+    uint32_t lim1 = range_limit(best), lim0 = 0u, hit_k = kInvalid;
+    const uint32_t n_par = uint32_t(g.big_par), n_tri = uint32_t(g.big_tri), n = uint32_t(g.n_big);
+    const uint32_t p_par = (n_par + 1u) >> 1, p_tri = (n_tri + 1u) >> 1, p_sph = (n - n_par - n_tri + 1u) >> 1;
+    const RayDir r1 = ray_dir(d);
+    const ulonglong2* rec = reinterpret_cast<const ulonglong2*>(g.bvh_big_pairs);
+    plane_pairs<2, false>(rec, p_par, 0u, o, r1, r1, lim1, lim0, hit_k);
+    rec += 6u * p_par;
+    plane_pairs<1, false>(rec, p_tri, n_par, o, r1, r1, lim1, lim0, hit_k);
+    rec += 6u * p_tri;
+#pragma unroll 1
+    for (uint32_t j = 0; j < p_sph; ++j, rec += 2) {
+        const ulonglong2 c0 = rec[0], c1 = rec[1];
+        const f2 ocx = add2(c0.x, bc(o.x)), ocy = add2(c0.y, bc(o.y)), ocz = add2(c1.x, bc(o.z));
+        uint32_t ta, tb;
+        sphere_roots2(ocx, ocy, ocz, c1.y, r1, ta, tb);
+        const uint32_t id = n_par + n_tri + 2u * j;
+        if (ta < lim1) { lim1 = ta; hit_k = id; }
+        if (tb < lim1) { lim1 = tb; hit_k = id + 1u; }
+    }
+    if (hit_k != kInvalid) {
+        best = __uint_as_float(lim1);
+        best_prim = __ldg(g.bvh_big + hit_k);
+    }
+}
+
 constexpr uint32_t kBvhLeaf = 0x80000000u, kBvhDone = 0xffffffffu;
-constexpr int kBvhLocalStack = 40; // entries beyond the kBvhSmemStack levels in shared memory (path.h): rarely touched
+// Entries beyond the shared-memory levels live in local memory (rarely touched). Together they can hold the deepest walk
+// there is: Karras' tree over (30-bit code, 32-bit position) keys is at most 62 levels deep, the binary walk postpones at
+// most one child per level, the 4-wide walk (31 levels) at most three.
+constexpr int kBvhLocalStack = 96;
 struct BvhWalk {
     float3 o, d, idir, ood;
     float best;
@@ -970,18 +1003,8 @@ struct BvhWalk {
         sp = 0;
         cap = S.bvh_stack;
         pend = 0u;
-        const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
-        for (int k = 0; k < g.n_big; ++k) {
-            const uint32_t id = __ldg(g.bvh_big + k);
-            const float4* pp = hot + 4 * (size_t)id;
-            const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
-            const float t = hit_prim(a0, b0, c0, g0, o, d, best);
-            if (t >= 0.0f) {
-                best = t;
-                best_prim = id;
-                if (any_) return true;
-            }
-        }
+        bvh_big_hits(g, o, d, best, best_prim);
+        if (any_ && best_prim != kInvalid) return true;
         float3 dd = d;
         if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
         if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);
@@ -1094,18 +1117,8 @@ template <bool COUNT> struct Bvh4Walk { // COUNT: box and primitive tests are ta
         cap = S.bvh_stack;
         pend = 0u;
         if (COUNT) { n_node = 0; n_prim = uint32_t(g.n_big); }
-        const float4* __restrict__ hot = reinterpret_cast<const float4*>(g.hot);
-        for (int k = 0; k < g.n_big; ++k) {
-            const uint32_t id = __ldg(g.bvh_big + k);
-            const float4* pp = hot + 4 * (size_t)id;
-            const float4 a0 = __ldg(pp), b0 = __ldg(pp + 1), c0 = __ldg(pp + 2), g0 = __ldg(pp + 3);
-            const float t = hit_prim(a0, b0, c0, g0, o, d, best);
-            if (t >= 0.0f) {
-                best = t;
-                best_prim = id;
-                if (any_) return true;
-            }
-        }
+        bvh_big_hits(g, o, d, best, best_prim);
+        if (any_ && best_prim != kInvalid) return true;
         float3 dd = d;
         if (fabsf(dd.x) < 1.0e-20f) dd.x = copysignf(1.0e-20f, dd.x);
         if (fabsf(dd.y) < 1.0e-20f) dd.y = copysignf(1.0e-20f, dd.y);

@@ -332,3 +332,42 @@ def test_bvh_walk_matches_oracle_and_octree(g19, abi, oracle, which, n, w, h, sp
         assert abs(shd - segs[1]) <= 1e-3 * segs[1] + 2
     assert rel_rmse(outs[3][0], outs[1][0]) <= 2e-3
     assert rel_rmse(outs[4][0], outs[1][0]) <= 2e-3
+
+
+def test_bvh_deep_stack_on_a_pile_of_overlapping_triangles(g19, abi, oracle):
+    """Worst case for the postponed-children stack of the BVH walks: 1500 small triangles piled on one spot (every box
+    overlaps every other, equal Morton codes split by position only, so the hierarchy is deep and a ray through the pile
+    is inside every box) next to a regular floor. Twelve stack levels live in shared memory, the rest in local memory:
+    no child may be dropped -- the nearest hits, hence radiance and segment counts, must equal the oracle's and the
+    octree walk's."""
+    rng = np.random.default_rng(5)
+    sc = g19.Octree((-20,) * 3, (20,) * 3)
+    for k in range(1500):
+        c = np.array([2.0, 0.0, 0.0]) + rng.uniform(-0.02, 0.02, 3)
+        a, b, d = (c + rng.uniform(-0.3, 0.3, 3) for _ in range(3))
+        sc.push_back(g19.ImpTriangle(tuple(a), tuple(b), tuple(d), tuple(rng.uniform(0.3, 0.9, 3))))
+    for i in range(-8, 8):
+        for j in range(-8, 8):
+            p = [(i, j, -2.0), (i + 1, j, -2.0), (i + 1, j + 1, -2.0), (i, j + 1, -2.0)]
+            sc.push_back(g19.ImpTriangle(p[0], p[1], p[2], (0.7, 0.7, 0.7)))
+            sc.push_back(g19.ImpTriangle(p[0], p[2], p[3], (0.7, 0.7, 0.7)))
+    sc.push_back(g19.ImpTriangle((-6, -9, 9), (-6, 9, 9), (6, 0, 9), (1, 1, 1), bsdf=abi.BSDF_EMITTER, emission=(8.0, 8.0, 8.0)))
+    cam = g19.Camera((-10, 0, 0), (1, 0, 0), 0.1)
+    w, h, spp, depth = 96, 96, 2, 3
+    outs = {}
+    for walk, stack in ((1, 12), (3, 4), (4, 4), (4, 12)):
+        rt = g19.RayTracer(cam, (0, 0, 0))
+        rt.tune("walk", walk)
+        rt.tune("bvh_stack", stack)
+        rt.setScene(sc)
+        rt.start()
+        rad = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=spp, max_depth=depth, seed=2)["radiance"]
+        st = rt.stats()
+        outs[(walk, stack)] = (rad, int(st.extend_segments), int(st.shadow_segments))
+    exp, segs = binding.path_render(mirror(oracle, sc), cam, w, h, spp, depth, seed=2)
+    assert exp.mean() > 0.005
+    for key, (rad, ext, shd) in outs.items():
+        err = rel_rmse(rad, exp)
+        print("pile walk/stack %s: relRMSE %.3e segments %d/%d vs %d/%d" % (key, err, ext, shd, segs[0], segs[1]))
+        assert err <= 1e-2
+        assert abs(ext - segs[0]) <= 1e-3 * segs[0] + 2 and abs(shd - segs[1]) <= 1e-3 * segs[1] + 2
