@@ -1780,7 +1780,7 @@ __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, boo
 // One launch per material queue and bounce: next-event estimation, BSDF sample, the trace of BOTH
 // rays in one loop over the staged primitives, and the new vertex record written straight into
 // the next bounce's material queue.
-template <int KIND, bool FIRST, bool LAST, bool SPEC>
+template <int KIND, bool FIRST, bool LAST, bool SPEC, bool SPLIT = false>
 __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bounce, const SceneAccess<true>& S, const uint32_t n,
                                                  const uint32_t cta, const uint32_t n_cta, RecStage<!FIRST>& stage) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
@@ -1828,7 +1828,21 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
             bool blocked = false;
             float t_hit = FLT_MAX;
             uint32_t prim_hit = kInvalid;
-            if (kDiffuse && !LAST) {
+            if (kDiffuse && !LAST && SPLIT) {
+                // (bounce_occ = 4 experiment: one ray at a time through the primitive loops -- fewer live registers, the
+                // origin half of the affine maps computed twice)
+                if (sh.want_shadow) {
+                    bool unused;
+                    float ts;
+                    uint32_t ps;
+                    trace_flat<false>(S, sh.no, sh.w, sh.tmax_s, sh.w, -1.0f, ts, ps, unused);
+                    blocked = ps != kInvalid;
+                }
+                if (cont) {
+                    bool unused;
+                    trace_flat<false>(S, sh.no, sh.nd, FLT_MAX, sh.nd, -1.0f, t_hit, prim_hit, unused);
+                }
+            } else if (kDiffuse && !LAST) {
                 if (sh.want_shadow || cont)
                     trace_flat<true>(S, sh.no, sh.nd, cont ? FLT_MAX : -1.0f, sh.w, sh.tmax_s, t_hit, prim_hit, blocked);
             } else if (kDiffuse) { // LAST: the shadow ray alone
@@ -1908,7 +1922,7 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : OCC) bounce_
     const uint32_t n = a.counts[bounce * 4 + KIND];
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     __shared__ RecStage<!FIRST> stage;
-    bounce_flat_body<KIND, FIRST, LAST, SPEC>(a, bounce, S, n, blockIdx.x, gridDim.x, stage);
+    bounce_flat_body<KIND, FIRST, LAST, SPEC, OCC == 4>(a, bounce, S, n, blockIdx.x, gridDim.x, stage);
 }
 
 // All three material queues of one bounce in ONE launch (scenes with mirror / glass). The mirror and

@@ -12,7 +12,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ap = argparse.ArgumentParser()
-ap.add_argument("--c4-spp", type=int, default=16)
+ap.add_argument("--c4-spp", type=int, default=64)
 ap.add_argument("--c4-n", type=int, default=708)
 ap.add_argument("--c5-spp", type=int, default=64)
 a = ap.parse_args()
@@ -49,6 +49,7 @@ run("C1 default scene", abi.SCENE_DEFAULT, 0, 1920, 1080, abi.MODE_REF, 1, 1)
 run("C2 Cornell (REF loop)", abi.SCENE_CORNELL, 0, 1920, 1080, abi.MODE_REF, 1, 1)
 run("C2 Cornell", abi.SCENE_CORNELL, 0, 1920, 1080, abi.MODE_PATH, 64, 5)
 run("C3 Cornell glass+mirror", abi.SCENE_CORNELL_GLASS, 0, 1920, 1080, abi.MODE_PATH, 64, 12)
-run("C4 heightfield n=%d (REF loop)" % a.c4_n, abi.SCENE_HEIGHTFIELD, a.c4_n, 1920, 1080, abi.MODE_REF, 1, 1, reps=1)
-run("C4 heightfield n=%d" % a.c4_n, abi.SCENE_HEIGHTFIELD, a.c4_n, 1920, 1080, abi.MODE_PATH, a.c4_spp, 5)
+run("C4 heightfield room n=%d (REF loop)" % a.c4_n, abi.SCENE_HEIGHTFIELD_ROOM, a.c4_n, 1920, 1080, abi.MODE_REF, 1, 1, reps=2)
+run("C4 heightfield room n=%d" % a.c4_n, abi.SCENE_HEIGHTFIELD_ROOM, a.c4_n, 1920, 1080, abi.MODE_PATH, a.c4_spp, 5)
+run("   open heightfield n=%d (round 1's C4 scene)" % a.c4_n, abi.SCENE_HEIGHTFIELD, a.c4_n, 1920, 1080, abi.MODE_PATH, a.c4_spp, 5)
 run("C5 Cornell 4K", abi.SCENE_CORNELL, 0, 3840, 2160, abi.MODE_PATH, a.c5_spp, 8)
