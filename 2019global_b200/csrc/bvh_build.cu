@@ -292,9 +292,9 @@ int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t 
         err = std::string("path_build_bvh_device (") + what + "): " + cudaGetErrorString(e);
         return G19_ERR_CUDA;
     };
-    DeviceArray keys, vals, keys2, vals2, tmp, child, par_n, par_l, range, arrived, nbox, live, new_index, tmp2;
+    PoolArray keys, vals, keys2, vals2, tmp, child, par_n, par_l, range, arrived, nbox, live, new_index, tmp2; // temporaries: pooled
     auto release_all = [&] {
-        for (DeviceArray* d : {&keys, &vals, &keys2, &vals2, &tmp, &child, &par_n, &par_l, &range, &arrived, &nbox, &live, &new_index, &tmp2})
+        for (PoolArray* d : {&keys, &vals, &keys2, &vals2, &tmp, &child, &par_n, &par_l, &range, &arrived, &nbox, &live, &new_index, &tmp2})
             d->release();
     };
     cudaError_t e;
@@ -303,10 +303,10 @@ int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t 
         release_all();                 \
         return fail(what, e);          \
     }
-    BVH_TRY("alloc", keys.ensure(size_t(n) * 4));
-    BVH_TRY("alloc", vals.ensure(size_t(n) * 4));
-    BVH_TRY("alloc", keys2.ensure(size_t(n) * 4));
-    BVH_TRY("alloc", vals2.ensure(size_t(n) * 4));
+    BVH_TRY("alloc", keys.ensure(size_t(n) * 4, s));
+    BVH_TRY("alloc", vals.ensure(size_t(n) * 4, s));
+    BVH_TRY("alloc", keys2.ensure(size_t(n) * 4, s));
+    BVH_TRY("alloc", vals2.ensure(size_t(n) * 4, s));
     const int threads = 256, blocks = int((n + threads - 1) / threads);
     const float3 lo = make_float3(root_lo[0], root_lo[1], root_lo[2]);
     const float3 inv = make_float3(1024.0f / root_size[0], 1024.0f / root_size[1], 1024.0f / root_size[2]);
@@ -314,7 +314,7 @@ int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t 
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<const uint32_t*>(keys.p), static_cast<uint32_t*>(keys2.p),
                                     static_cast<const uint32_t*>(vals.p), static_cast<uint32_t*>(vals2.p), n, 0, 30, s);
-    BVH_TRY("alloc", tmp.ensure(tmp_bytes));
+    BVH_TRY("alloc", tmp.ensure(tmp_bytes, s));
     BVH_TRY("sort", cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, static_cast<const uint32_t*>(keys.p), static_cast<uint32_t*>(keys2.p),
                                                     static_cast<const uint32_t*>(vals.p), static_cast<uint32_t*>(vals2.p), n, 0, 30, s));
     const uint32_t* skeys = static_cast<const uint32_t*>(keys2.p);
@@ -330,14 +330,14 @@ int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t 
         release_all();
         return G19_OK;
     }
-    BVH_TRY("alloc", child.ensure(size_t(n - 1) * 8));
-    BVH_TRY("alloc", par_n.ensure(size_t(n - 1) * 4));
-    BVH_TRY("alloc", par_l.ensure(size_t(n) * 4));
-    BVH_TRY("alloc", range.ensure(size_t(n - 1) * 8));
-    BVH_TRY("alloc", arrived.ensure(size_t(n - 1) * 4));
-    BVH_TRY("alloc", nbox.ensure(size_t(n - 1) * sizeof(Box6)));
-    BVH_TRY("alloc", live.ensure(size_t(n) * 4));
-    BVH_TRY("alloc", new_index.ensure(size_t(n) * 4));
+    BVH_TRY("alloc", child.ensure(size_t(n - 1) * 8, s));
+    BVH_TRY("alloc", par_n.ensure(size_t(n - 1) * 4, s));
+    BVH_TRY("alloc", par_l.ensure(size_t(n) * 4, s));
+    BVH_TRY("alloc", range.ensure(size_t(n - 1) * 8, s));
+    BVH_TRY("alloc", arrived.ensure(size_t(n - 1) * 4, s));
+    BVH_TRY("alloc", nbox.ensure(size_t(n - 1) * sizeof(Box6), s));
+    BVH_TRY("alloc", live.ensure(size_t(n) * 4, s));
+    BVH_TRY("alloc", new_index.ensure(size_t(n) * 4, s));
     BVH_TRY("memset", cudaMemsetAsync(arrived.p, 0, size_t(n - 1) * 4, s));
     bvh_topology_kernel<<<blocks, threads, 0, s>>>(skeys, int(n), static_cast<uint32_t*>(child.p), static_cast<uint32_t*>(par_n.p),
                                                    static_cast<uint32_t*>(par_l.p), static_cast<int2*>(range.p));
@@ -348,7 +348,7 @@ int path_build_bvh_device(const float* d_boxes, const uint32_t* d_ids, uint32_t 
     bvh_live_kernel<<<blocks, threads, 0, s>>>(static_cast<const int2*>(range.p), int(n), leaf_max, static_cast<uint32_t*>(live.p));
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<const uint32_t*>(live.p), static_cast<uint32_t*>(new_index.p), int(n), s);
-    BVH_TRY("alloc", tmp2.ensure(scan_bytes));
+    BVH_TRY("alloc", tmp2.ensure(scan_bytes, s));
     BVH_TRY("scan", cub::DeviceScan::ExclusiveSum(tmp2.p, scan_bytes, static_cast<const uint32_t*>(live.p), static_cast<uint32_t*>(new_index.p), int(n), s));
     uint32_t n_live = 0; // live[n - 1] is 0 (there are n - 1 internal nodes): the last scan entry is the total
     BVH_TRY("copy", cudaMemcpyAsync(&n_live, static_cast<const uint32_t*>(new_index.p) + (n - 1), 4, cudaMemcpyDeviceToHost, s));

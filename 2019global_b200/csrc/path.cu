@@ -43,6 +43,31 @@ void DeviceArray::release() {
     p = nullptr;
     bytes = 0;
 }
+cudaError_t PoolArray::ensure(size_t need, cudaStream_t s) {
+    if (need <= bytes && p) return cudaSuccess;
+    release();
+    stream = s;
+    cudaError_t e = cudaMallocAsync(&p, need + 256, s);
+    if (e == cudaSuccess) bytes = need;
+    else p = nullptr;
+    return e;
+}
+void PoolArray::release() {
+    if (p) cudaFreeAsync(p, stream);
+    p = nullptr;
+    bytes = 0;
+}
+void path_pool_keep() {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    unsigned long long keep = 2ull << 30; // what the builders of a 1 M-triangle scene hold at their peak is ~0.5 GB
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaGetLastError();
+}
 
 namespace {
 
@@ -213,6 +238,7 @@ static void build_pairs(const std::vector<PrimHot>& hot, size_t first, size_t n_
 int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& tune, cudaStream_t stream, std::string& err) {
     const auto t_start = std::chrono::steady_clock::now();
     ++b.upload_serial;
+    path_pool_keep();
     // Extraction runs on the host's cores, a contiguous range of entities per thread with its own primitive, material
     // and light lists (a 1 M-triangle mesh: 0.26 s single-threaded); the ranges are then joined in entity order, with the
     // "same material as the previous entity" rule applied across the seams too, so the result does not depend on the
@@ -445,8 +471,8 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
                 boxes[6 * i + k] = prims[i].box.lo[k];
                 boxes[6 * i + 3 + k] = prims[i].box.hi[k];
             }
-        DeviceArray d_boxes;
-        cudaError_t be = d_boxes.ensure(boxes.size() * sizeof(float) + 16);
+        PoolArray d_boxes;
+        cudaError_t be = d_boxes.ensure(boxes.size() * sizeof(float) + 16, stream);
         if (be == cudaSuccess) be = cudaMemcpyAsync(d_boxes.p, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
         if (be == cudaSuccess) be = cudaStreamSynchronize(stream);
         if (be != cudaSuccess) {
@@ -682,9 +708,9 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
                 boxes[6 * i + k] = prims[i].box.lo[k];
                 boxes[6 * i + 3 + k] = prims[i].box.hi[k];
             }
-        DeviceArray d_boxes, d_small;
-        cudaError_t be = d_boxes.ensure(boxes.size() * sizeof(float) + 16);
-        if (be == cudaSuccess) be = d_small.ensure(small_ids.size() * sizeof(uint32_t) + 16);
+        PoolArray d_boxes, d_small;
+        cudaError_t be = d_boxes.ensure(boxes.size() * sizeof(float) + 16, stream);
+        if (be == cudaSuccess) be = d_small.ensure(small_ids.size() * sizeof(uint32_t) + 16, stream);
         if (be == cudaSuccess) be = cudaMemcpyAsync(d_boxes.p, boxes.data(), boxes.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
         if (be == cudaSuccess && !small_ids.empty())
             be = cudaMemcpyAsync(d_small.p, small_ids.data(), small_ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);

@@ -74,6 +74,17 @@ struct DeviceArray {
     void release();
 };
 
+// A temporary of the scene builders, from the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on the
+// builder's stream): no device synchronisation per allocation, and the pool keeps the memory for the next upload.
+struct PoolArray {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaError_t ensure(size_t need, cudaStream_t s);
+    void release();
+};
+void path_pool_keep(); // raise the release threshold of the current device's default pool (idempotent)
+
 struct PathSceneBuffers {
     DeviceArray nodes, prim_index, hot, cold, materials, lights, pairs, prim_entity, top;
     DeviceArray bvh_nodes, bvh4_nodes, bvh_prims, bvh_big, bvh_big_pairs;
