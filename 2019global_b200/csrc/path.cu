@@ -174,7 +174,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec", "bvh_stack"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec", "bvh_stack", "fuse_first"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -201,6 +201,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
     else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
+    else if (k == "fuse_first") t.fuse_first = num(def.fuse_first, 0, 1);
     else if (k == "bvh_stack") t.bvh_stack = num(def.bvh_stack, 4, 64);
     else if (k == "bvh_spec") t.bvh_spec = num(def.bvh_spec, 0, 3);
     else if (k == "bvh_leaf") t.bvh_leaf = num(def.bvh_leaf, 1, 8);
@@ -1075,13 +1076,22 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             pa.pix_base = uint32_t(pix0);
             pa.pix_count = uint32_t(std::min(window, npix - pix0));
             pa.n_slots = uint32_t(size_t(pa.pix_count) * size_t(pa.spp_pass));
-            clk.begin();
-            launch_raygen_extend(pa, a.sm_count, ls); // camera segment
-            clk.end(G19_K_EXTEND);
-            stats.class_launches[G19_K_EXTEND] += 1;
+            // diffuse-only flat scenes: camera segment and first vertex in one launch
+            const bool fused_first = fused && a.tune.fuse_first && !(pa.kind_mask & 6u) && pa.bounce_occ != 4;
+            if (!fused_first) {
+                clk.begin();
+                launch_raygen_extend(pa, a.sm_count, ls); // camera segment
+                clk.end(G19_K_EXTEND);
+                stats.class_launches[G19_K_EXTEND] += 1;
+            }
             for (int bounce = 0; bounce < p.max_depth; ++bounce) {
                 clk.begin();
                 int n = 0;
+                if (bounce == 0 && fused_first && launch_bounce_first_fused(pa, a.sm_count, ls)) {
+                    clk.end(G19_K_SHADE);
+                    stats.class_launches[G19_K_SHADE] += 1;
+                    continue;
+                }
                 // the first bounce's rays leave the camera rays' hit points in pixel order: coherent as they are
                 // ... and a queue that stayed short the last time is walked in a blink: not worth three more launches.
                 const size_t ray_cap = 2 * pa.plane + kQueueSlack;

@@ -156,6 +156,7 @@ struct PathTuning {
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
     int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
+    int fuse_first = 1;       // diffuse-only flat scenes: trace the camera segment inside the first bounce's launch (no raygen kernel, no camera records)
     int bvh_stack = kBvhSmemStack; // walk=3/4: levels of the postponed-children stack in shared memory (1 KB per level and CTA)
     int bvh_spec = 1;         // walk=3: a lane that reaches a leaf postpones it and keeps descending
     int bvh_leaf = 4;         // walk=3: primitives per BVH leaf at most (1..8; read at scene upload)
@@ -281,6 +282,8 @@ void launch_iota(uint32_t* out, size_t n, cudaStream_t s);
 cudaError_t launch_ray_sort(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out, const uint32_t* iota,
                             uint32_t* perm, size_t n, cudaStream_t s);
 bool path_scene_is_flat(const PassArgs& a);
+// diffuse-only flat scenes: the camera segment and the first vertex in ONE launch; false = not applicable
+bool launch_bounce_first_fused(const PassArgs& a, int sm_count, cudaStream_t s);
 void launch_accumulate(const PassArgs& a, cudaStream_t s);
 void launch_primary(const PassArgs& a, int32_t* ids_l, double* points_l, double* normals_l, int sm_count, cudaStream_t s);
 void launch_resolve(const TileMap& map, const float* accum, int spp, float* rad_l, uint8_t* rgb_l, cudaStream_t s);

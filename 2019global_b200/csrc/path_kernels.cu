@@ -1780,7 +1780,10 @@ __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, boo
 // One launch per material queue and bounce: next-event estimation, BSDF sample, the trace of BOTH
 // rays in one loop over the staged primitives, and the new vertex record written straight into
 // the next bounce's material queue.
-template <int KIND, bool FIRST, bool LAST, bool SPEC, bool SPLIT = false>
+// FUSED (diffuse-only flat scenes, first bounce): the camera segment is traced right here instead of by
+// raygen_extend_flat_kernel -- the vertex record of the camera hit (48 B written, 48 B read back, a fifth of the frame's
+// HBM traffic), its queue reservation and a launch per pass disappear; `n` is then the number of path slots of the pass.
+template <int KIND, bool FIRST, bool LAST, bool SPEC, bool SPLIT = false, bool FUSED = false>
 __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bounce, const SceneAccess<true>& S, const uint32_t n,
                                                  const uint32_t cta, const uint32_t n_cta, RecStage<!FIRST>& stage) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
@@ -1797,22 +1800,61 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
 
     uint32_t q = cta * kThreads + threadIdx.x;
     int buf = 0;
-    prefetch_rec(in, q, q < n, stage, 0);
+    if (!FUSED) prefetch_rec(in, q, q < n, stage, 0);
     for (; q - lane < n; q += stride) {
-        const uint32_t qn = q + stride;
-        prefetch_rec(in, qn, qn < n && qn > q, stage, buf ^ 1); // next record, in flight during this body
-        cp_async_wait<1>();                                     // this record has landed
-        const float4 ls = stage.ls[buf][tid];
-        const uint32_t slot = q < n ? __float_as_uint(ls.w) : kInvalid;
+        uint32_t slot = kInvalid;
+        float4 ls = make_float4(0.f, 0.f, 0.f, 0.f);
+        float3 p = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f);
+        uint32_t prim = kInvalid, pixel = 0, sample = 0;
+        if (FUSED) {
+            // ---- the camera segment of path slot q (what raygen_extend_flat_kernel does for scenes with specular materials) ----
+            bool live = false;
+            float3 o = f3(0.f, 0.f, 0.f);
+            if (q < n) {
+                int x, y;
+                live = slot_pixel(a, q, x, y, sample);
+                if (live) {
+                    pixel = uint32_t(y) * uint32_t(a.map.w) + uint32_t(x);
+                    camera_ray(a, x, y, pixel, sample, o, d);
+                }
+            }
+            float t = 0.0f;
+            uint32_t pr = kInvalid;
+            float4 seen = make_float4(0.f, 0.f, 0.f, 0.f); // what a path that ends on the camera segment delivers
+            if (nearest<true>(S, live, o, d, t, pr)) {
+                const float4 tag = S.hot_row(pr, 3);
+                const int bsdf = __float_as_int(tag.y);
+                if (bsdf == G19_BSDF_EMITTER) { // directly visible light: the path ends here
+                    const MaterialD& m = a.scene.materials[__float_as_int(tag.x)];
+                    seen = make_float4(m.emission[0], m.emission[1], m.emission[2], 0.0f);
+                } else if (bsdf == G19_BSDF_DIFFUSE) {
+                    slot = q;
+                    prim = pr;
+                    p = o + d * t;
+                }
+            }
+            if (q < n && slot == kInvalid) reinterpret_cast<float4*>(a.L)[q] = seen; // miss, emitter, or a slot outside the frame
+        } else {
+            const uint32_t qn = q + stride;
+            prefetch_rec(in, qn, qn < n && qn > q, stage, buf ^ 1); // next record, in flight during this body
+            cp_async_wait<1>();                                     // this record has landed
+            ls = stage.ls[buf][tid];
+            slot = q < n ? __float_as_uint(ls.w) : kInvalid;
+        }
         int kind_next = -1;
         float3 p_next = f3(0.f, 0.f, 0.f), d_next = f3(0.f, 0.f, 1.f), T = f3(1.f, 1.f, 1.f), Lp = f3(0.f, 0.f, 0.f);
-        uint32_t prim_next = kInvalid, pixel = 0, sample = 0;
+        uint32_t prim_next = kInvalid;
         if (slot != kInvalid) {
-            const float4 hp = stage.hp[buf][tid], dw = stage.dw[buf][tid];
-            const float3 p = f3(hp.x, hp.y, hp.z), d = f3(dw.x, dw.y, dw.z);
-            const uint32_t prim = __float_as_uint(hp.w);
-            pixel = __float_as_uint(dw.w);
-            if (FIRST) {
+            if (!FUSED) {
+                const float4 hp = stage.hp[buf][tid], dw = stage.dw[buf][tid];
+                p = f3(hp.x, hp.y, hp.z);
+                d = f3(dw.x, dw.y, dw.z);
+                prim = __float_as_uint(hp.w);
+                pixel = __float_as_uint(dw.w);
+            }
+            if (FUSED) {
+                // throughput 1, no radiance yet: nothing to load
+            } else if (FIRST) {
                 sample = __float_as_uint(ls.x); // the camera record: no radiance yet, x carries the sample index
             } else {
                 const float4 tp = stage.tp[buf][tid];
@@ -1923,6 +1965,18 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : OCC) bounce_
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     __shared__ RecStage<!FIRST> stage;
     bounce_flat_body<KIND, FIRST, LAST, SPEC, OCC == 4>(a, bounce, S, n, blockIdx.x, gridDim.x, stage);
+}
+
+// Diffuse-only flat scenes: camera segment + first vertex in one launch (bounce_flat_body<FUSED>), over the path slots of
+// the pass instead of a queue.
+template <bool LAST> __global__ void __launch_bounds__(kThreads, 3) bounce_flat_fused_kernel(const PassArgs a) {
+    pdl_launch_dependents();
+    const uint32_t n = a.n_slots;
+    if (blockIdx.x * kThreads >= n) return;
+    const SceneAccess<true> S = stage_scene<true>(a);
+    pdl_wait(); // the previous pass's accumulate cleared the queue lengths
+    RecStage<false>& unused = *reinterpret_cast<RecStage<false>*>(g19_dyn_smem); // (the fused body prefetches no records)
+    bounce_flat_body<Q_DIFFUSE, true, LAST, false, false, true>(a, 0, S, n, blockIdx.x, gridDim.x, unused);
 }
 
 // All three material queues of one bounce in ONE launch (scenes with mirror / glass). The mirror and
@@ -2486,6 +2540,17 @@ void launch_trace(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {
 }
 
 bool path_scene_is_flat(const PassArgs& a) { return all_staged(a); }
+
+// Diffuse-only flat scenes: raygen + first bounce in one launch; false = not applicable (the caller launches the two).
+bool launch_bounce_first_fused(const PassArgs& a, int sm_count, cudaStream_t s) {
+    if (!all_staged(a) || (a.kind_mask & 6u) || a.bounce_occ == 4) return false;
+    const size_t smem = path_smem_bytes(a);
+    void (*kernel)(PassArgs) = a.max_depth <= 1 ? bounce_flat_fused_kernel<true> : bounce_flat_fused_kernel<false>;
+    const int grid = persistent_grid(kernel, smem, sm_count);
+    cudaError_t e = launch_pdl(kernel, grid, smem, s, a);
+    if (e != cudaSuccess) note_launch_error("fused first bounce kernel launch", e, smem, grid);
+    return true;
+}
 
 // Flat scenes with specular materials: one launch serves the three queues of a bounce (not the last).
 bool launch_bounce_merged(const PassArgs& a, int bounce, int sm_count, cudaStream_t s) {

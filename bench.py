@@ -426,9 +426,12 @@ def main():
         npix_local = g19.engine.tile_pixels(cfg["w"], cfg["h"], rank, world)
         flat = cfg["n"] == 0
         if flat:
+            # diffuse-only scenes trace the camera segment inside the first bounce's launch (no raygen kernel): the 48-byte
+            # camera records are neither written nor read
+            cam_rec = 0 if agg["launch"][abi.K_EXTEND] == 0 else 48 * C0
             bytes_cls = {
-                "raygen_extend": 48 * C0,                       # record written per shaded camera hit
-                "bounce": (48 * C0 + 64 * (C - C0)              # record read per shaded vertex
+                "raygen_extend": cam_rec,                       # record written per shaded camera hit
+                "bounce": (cam_rec + 64 * (C - C0)              # record read per shaded vertex
                            + 64 * (C - C0)                      # record written per continuation hit (= vertices shaded later)
                            + 16 * ST),                          # radiance delivered once per path that ends in this kernel
                 "accumulate": 16 * S0 + 24 * npix_local * max(1, agg["launch"][abi.K_ACCUM]),

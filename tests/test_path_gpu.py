@@ -371,3 +371,24 @@ def test_bvh_deep_stack_on_a_pile_of_overlapping_triangles(g19, abi, oracle):
         print("pile walk/stack %s: relRMSE %.3e segments %d/%d vs %d/%d" % (key, err, ext, shd, segs[0], segs[1]))
         assert err <= 1e-2
         assert abs(ext - segs[0]) <= 1e-3 * segs[0] + 2 and abs(shd - segs[1]) <= 1e-3 * segs[1] + 2
+
+
+def test_fused_first_bounce_is_bit_identical(g19, abi):
+    """Diffuse-only flat scenes trace the camera segment inside the first bounce's launch (tune fuse_first, default on):
+    no raygen kernel, no camera vertex records. Same arithmetic per path, so the frame must not change by a bit -- at
+    depth 1 (the fused launch is also the last), at depth 5, with ragged tiles and several passes."""
+    w, h = 150, 97
+    sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h)
+    for depth, spp, spp_pass in ((1, 3, 0), (5, 6, 0), (5, 6, 2)):
+        outs = []
+        for fuse in (1, 0):
+            rt = g19.RayTracer(cam, light)
+            rt.tune("fuse_first", fuse)
+            rt.setScene(sc)
+            rt.start()
+            rad = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=spp, max_depth=depth, seed=8, spp_per_pass=spp_pass)["radiance"]
+            st = rt.stats()
+            outs.append((rad, int(st.extend_segments), int(st.shadow_segments), int(st.kernel_launches)))
+        assert outs[0][0].tobytes() == outs[1][0].tobytes() and outs[0][0].max() > 0
+        assert outs[0][1:3] == outs[1][1:3]
+        assert outs[0][3] < outs[1][3]  # one launch per pass fewer
