@@ -490,6 +490,11 @@ def main():
         }
         if flat:
             roof["binding_resource"] = "issue slots (ncu: smsp__issue_active %s%% of peak) -- see DESIGN.md section 5" % issue_pct
+            if agg["launch"][abi.K_EXTEND] == 0:
+                roof["note_fused"] = ("the camera segment is traced inside the first bounce's launch: its 48-byte vertex records are no "
+                                      "longer written and read back, so the algorithmic bytes per frame fell by a fifth while the frame "
+                                      "got 4 % faster -- the HBM fraction of this issue-bound kernel fell with them (0.57 -> 0.47), the "
+                                      "issue fraction did not")
         if not flat and agg["node_tests"] > 0:
             # T_issue = (N_node*20 + N_tri*50 + S*150) thread instructions / (SMs * 128 lanes * f_sm);
             # N_node / N_tri counted by the walk itself (params.profile builds of the tree kernels), S = all segments
