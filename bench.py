@@ -590,7 +590,7 @@ def main():
         for name in names:
             oc = CONFIGS[name]
             oj = Job(mods, oc, rank, world, local, args.gather, args.spp_per_pass, rt=rt)
-            oj.step(spp=max(1, oc["spp"] // 16))  # warm-up: allocations, kernel attributes
+            oj.step(spp=min(oc["spp"], 32))  # warm-up: every lane allocates its full-size pass buffers (a pass is <= 8 spp), kernel attributes
             barrier()
             n_frames = 3 if name == "c3" else 1
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
