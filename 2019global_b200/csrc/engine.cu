@@ -260,6 +260,7 @@ int flatten_ref(g19_ctx* ctx, const g19_scene& s) {
             }
         }
     });
+    const auto t_host = std::chrono::steady_clock::now();
     ctx->ref_depth = max_depth(s);
     if (ctx->ref_depth >= 39) {
         ctx->err = "reference octree deeper than the device traversal stack (39 levels)";
@@ -270,6 +271,10 @@ int flatten_ref(g19_ctx* ctx, const g19_scene& s) {
     G19_CUDA(ctx, upload(ctx->ref_entities, ents, ctx->stream));
     G19_CUDA(ctx, upload(ctx->ref_tris, tris, ctx->stream));
     G19_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host vectors die at scope exit
+    if (ctx->tune.debug_tree)
+        std::fprintf(stderr, "[g19] REF view: %zu nodes, %zu entities, %zu triangles; copies %.1f ms (%.0f MB)\n", nodes.size(), ents.size(),
+                     tris.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host).count(),
+                     double(nodes.size() * sizeof(RefNodeD) + lists.size() * 4 + ents.size() * sizeof(RefEntityD) + tris.size() * sizeof(RefTriD)) / 1e6);
     ctx->ref.nodes = ctx->ref_nodes.as<RefNodeD>();
     ctx->ref.ents = ctx->ref_ents.as<int32_t>();
     ctx->ref.entities = ctx->ref_entities.as<RefEntityD>();

@@ -630,6 +630,9 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
         err = std::string("path_upload: ") + cudaGetErrorString(e);
         return G19_ERR_CUDA;
     }
+    if (tune.debug_tree)
+        std::fprintf(stderr, "[g19] path_upload: record arrays uploaded %.1f ms after the tree\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_tree).count());
     PathSceneD& v = b.view;
     v.nodes = static_cast<const PathNodeD*>(b.nodes.p);
     v.index = static_cast<const uint32_t*>(b.prim_index.p);
