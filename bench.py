@@ -516,7 +516,8 @@ def main():
     job = Job(mods, cfg, rank, world, local, args.gather, args.spp_per_pass)
     rt = job.rt
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # rank 0's GPU is the one reported (eight nvidia-smi processes starting at once take seconds to come up)
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         job.step()
     # ---- timed region: K steps, device clock, barrier + synchronize on both sides -------------
@@ -530,12 +531,13 @@ def main():
     barrier()
     wall1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    if ms * args.steps < 300.0:  # a short timed region (N = 8: 40 ms): keep the same load up until the sampler has seen it
-        for _ in range(int(math.ceil(300.0 / max(ms, 1e-3)))):  # the same count on every rank (ms is the max over ranks)
+    short = ms * args.steps < 1000.0
+    if short:  # a short timed region (N = 8: 40 ms): keep the same load up until the sampler has seen it
+        for _ in range(int(math.ceil(1000.0 / max(ms, 1e-3)))):  # the same count on every rank (ms is the max over ranks)
             job.step()
         barrier()
-    short = ms * args.steps < 300.0
-    clocks = sampler.stop(wall0, wall1 + (0.3 if short else 0.0), "timed + 0.3 s of the same steps after it" if short else "timed")
+    clocks = (sampler.stop(wall0, wall1 + (1.0 if short else 0.0), "timed + 1 s of the same steps after it" if short else "timed")
+              if rank == 0 else {})
     job.check_frame()
     st = rt.stats()
     # this library's kernels inside the timed region: every rank's render + rank 0's wait/release (frame) or its
