@@ -326,13 +326,25 @@ int path_upload(PathSceneBuffers& b, const g19_scene& scene, const PathTuning& t
     std::vector<Extracted> parts(n_threads);
     {
         const size_t chunk = (n_ents + n_threads - 1) / n_threads;
+        std::atomic<bool> failed{false}; // an exception (out of host memory) must not escape a worker thread
+        auto guarded = [&](size_t eb, size_t ee, Extracted& out) {
+            try {
+                extract(eb, ee, out);
+            } catch (...) {
+                failed.store(true);
+            }
+        };
         std::vector<std::thread> pool;
         for (size_t t = 1; t < n_threads; ++t) {
             const size_t eb = std::min(n_ents, t * chunk), ee = std::min(n_ents, eb + chunk);
-            pool.emplace_back([&, eb, ee, t] { extract(eb, ee, parts[t]); });
+            pool.emplace_back([&, eb, ee, t] { guarded(eb, ee, parts[t]); });
         }
-        extract(0, std::min(n_ents, chunk), parts[0]);
+        guarded(0, std::min(n_ents, chunk), parts[0]);
         for (std::thread& th : pool) th.join();
+        if (failed.load()) {
+            err = "path_upload: out of host memory while extracting primitives";
+            return G19_ERR_LIMIT;
+        }
     }
     std::vector<BuildPrim> prims;
     std::vector<MaterialD> materials;
