@@ -174,7 +174,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec", "bvh_stack", "fuse_first"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec", "bvh_stack", "fuse_first", "fold_last"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -201,6 +201,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
     else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
+    else if (k == "fold_last") t.fold_last = num(def.fold_last, 0, 1);
     else if (k == "fuse_first") t.fuse_first = num(def.fuse_first, 0, 1);
     else if (k == "bvh_stack") t.bvh_stack = num(def.bvh_stack, 4, 64);
     else if (k == "bvh_spec") t.bvh_spec = num(def.bvh_spec, 0, 3);
@@ -864,6 +865,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     pa0.trace_occ = a.tune.trace_occ;
     pa0.bounce_occ = a.tune.bounce_occ;
     pa0.bvh_spec = a.tune.bvh_spec;
+    pa0.fold_last = 0;
     pa0.walk = a.tune.walk ? (p.profile ? 2 : 1) : 0; // the new walk counts its node / primitive tests under params.profile
     if (a.tune.walk >= 3 && b.view.bvh_root != 0xffffffffu && b.view.bvh_nodes) {
         pa0.walk = a.tune.walk == 4 ? (p.profile ? 6 : 5) : 3; // bounding-volume hierarchy, binary / 4-wide (the latter counts its tests under params.profile)
@@ -1099,7 +1101,11 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
                 clk.end(G19_K_EXTEND);
                 stats.class_launches[G19_K_EXTEND] += 1;
             }
+            // ... and the launch before the last shades the last vertex in place: the last launch disappears
+            const bool fold_last = fused && a.tune.fold_last && pa.bounce_occ != 4 && p.max_depth >= 2;
             for (int bounce = 0; bounce < p.max_depth; ++bounce) {
+                if (fold_last && bounce == p.max_depth - 1) break; // folded into the previous launch
+                pa.fold_last = (fold_last && bounce == p.max_depth - 2) ? 1 : 0;
                 clk.begin();
                 int n = 0;
                 if (bounce == 0 && fused_first && launch_bounce_first_fused(pa, a.sm_count, ls)) {

@@ -156,6 +156,7 @@ struct PathTuning {
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
     int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
+    int fold_last = 1;        // flat scenes: a path's last vertex (next-event estimation only) is shaded by the launch that finds it
     int fuse_first = 1;       // diffuse-only flat scenes: trace the camera segment inside the first bounce's launch (no raygen kernel, no camera records)
     int bvh_stack = kBvhSmemStack; // walk=3/4: levels of the postponed-children stack in shared memory (1 KB per level and CTA)
     int bvh_spec = 1;         // walk=3: a lane that reaches a leaf postpones it and keeps descending
@@ -267,6 +268,7 @@ struct PassArgs {
     int32_t trace_occ;     // CTAs per SM of trace_kernel (3 or 4)
     int32_t bounce_occ;    // CTAs per SM of bounce_flat_kernel<diffuse> (3 or 4)
     int32_t bvh_spec;      // BvhWalk: speculative traversal (PathTuning::bvh_spec)
+    int32_t fold_last;     // this launch shades the path's last vertex in place (flat scenes, bounce max_depth - 2)
     int32_t walk;          // tree walk variant (PathTuning::walk); +2 when the walk counts its node / primitive tests
 };
 

@@ -1783,13 +1783,16 @@ __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, boo
 // FUSED (diffuse-only flat scenes, first bounce): the camera segment is traced right here instead of by
 // raygen_extend_flat_kernel -- the vertex record of the camera hit (48 B written, 48 B read back, a fifth of the frame's
 // HBM traffic), its queue reservation and a launch per pass disappear; `n` is then the number of path slots of the pass.
-template <int KIND, bool FIRST, bool LAST, bool SPEC, bool SPLIT = false, bool FUSED = false>
+// FOLD (flat scenes, the bounce before the last): the vertex the continuation ray finds would be the path's
+// last one -- next-event estimation only. It is shaded right here (light sample + shadow ray) instead of being written as a
+// 64-byte record for a launch of its own to read back: same arithmetic in the same order, one launch per pass fewer.
+template <int KIND, bool FIRST, bool LAST, bool SPEC, bool SPLIT = false, bool FUSED = false, bool FOLD = false>
 __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bounce, const SceneAccess<true>& S, const uint32_t n,
                                                  const uint32_t cta, const uint32_t n_cta, RecStage<!FIRST>& stage) {
     constexpr bool kDiffuse = KIND == Q_DIFFUSE;
     const RecView in = rec_queue(a, (bounce & 1) * 3 + (KIND - 1));
     RecSorter<SPEC> out;
-    if (!LAST) out.init(a, bounce + 1);
+    if (!LAST && !FOLD) out.init(a, bounce + 1);
     // statistics (g19_stats), two 16-bit counters per register (a thread runs < 2^16 iterations: the grid
     // has > 10^5 threads and a queue < 2^32 entries): calls | traced << 16, shadow rays | lit << 16
     uint32_t cnt_a = 0, cnt_b = 0, stored = 0;
@@ -1917,6 +1920,20 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
                     prim_next = prim_hit;
                 }
             }
+            if (FOLD && kind_next == G19_BSDF_DIFFUSE) { // the path's last vertex, shaded in place (next_last holds for this launch)
+                const Shaded s2 = shade_vertex<Q_DIFFUSE, true, true>(a, S, bounce + 1, p_next, d_next, T, prim_next, pixel, sample);
+                cnt_a += 1u;
+                if (s2.want_shadow) {
+                    bool unused;
+                    float t2;
+                    uint32_t k2;
+                    trace_flat<false>(S, s2.no, s2.w, s2.tmax_s, s2.w, -1.0f, t2, k2, unused);
+                    const bool lit2 = k2 == kInvalid;
+                    cnt_b += 1u + (lit2 ? 0x10000u : 0u);
+                    if (lit2) Lp = Lp + s2.lit_rgb;
+                }
+                kind_next = -1;
+            }
             if (kind_next < 0) {
                 // the path ends here: its radiance goes to the slot's accumulator input, once (zero or not:
                 // accumulate does not clear what it read)
@@ -1926,7 +1943,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
                 reinterpret_cast<float4*>(a.L)[slot] = make_float4(Lp.x, Lp.y, Lp.z, 0.0f);
             }
         }
-        if (!LAST) {
+        if (!LAST && !FOLD) {
             const uint32_t pos = out.reserve(kind_next);
             if (pos != kInvalid) {
                 const RecView r = rec_queue(a, out.set + kind_next);
@@ -1940,7 +1957,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
         buf ^= 1;
     }
     cp_async_wait<0>();
-    if (!LAST) out.flush(a);
+    if (!LAST && !FOLD) out.flush(a);
     const unsigned calls = warp_sum(cnt_a & 0xffffu), traced = warp_sum(cnt_a >> 16);
     const unsigned shadow_rays = warp_sum(cnt_b & 0xffffu), lit = warp_sum(cnt_b >> 16);
     stored = warp_sum(stored);
@@ -1955,7 +1972,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
 }
 
 // One material queue per launch (diffuse-only scenes, and the last bounce of any scene).
-template <int KIND, bool FIRST, bool LAST, bool SPEC, int OCC = 3>
+template <int KIND, bool FIRST, bool LAST, bool SPEC, int OCC = 3, bool FOLD = false>
 __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : OCC) bounce_flat_kernel(const PassArgs a, const int bounce) {
     pdl_launch_dependents();
     if (LAST && KIND != Q_DIFFUSE) return; // a specular vertex on the last segment contributes nothing
@@ -1964,19 +1981,19 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : OCC) bounce_
     const uint32_t n = a.counts[bounce * 4 + KIND];
     if (blockIdx.x * kThreads >= n) return; // short queue: surplus CTAs leave
     __shared__ RecStage<!FIRST> stage;
-    bounce_flat_body<KIND, FIRST, LAST, SPEC, OCC == 4>(a, bounce, S, n, blockIdx.x, gridDim.x, stage);
+    bounce_flat_body<KIND, FIRST, LAST, SPEC, OCC == 4, false, FOLD>(a, bounce, S, n, blockIdx.x, gridDim.x, stage);
 }
 
 // Diffuse-only flat scenes: camera segment + first vertex in one launch (bounce_flat_body<FUSED>), over the path slots of
 // the pass instead of a queue.
-template <bool LAST> __global__ void __launch_bounds__(kThreads, 3) bounce_flat_fused_kernel(const PassArgs a) {
+template <bool LAST, bool FOLD = false> __global__ void __launch_bounds__(kThreads, 3) bounce_flat_fused_kernel(const PassArgs a) {
     pdl_launch_dependents();
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
     const SceneAccess<true> S = stage_scene<true>(a);
     pdl_wait(); // the previous pass's accumulate cleared the queue lengths
     RecStage<false>& unused = *reinterpret_cast<RecStage<false>*>(g19_dyn_smem); // (the fused body prefetches no records)
-    bounce_flat_body<Q_DIFFUSE, true, LAST, false, false, true>(a, 0, S, n, blockIdx.x, gridDim.x, unused);
+    bounce_flat_body<Q_DIFFUSE, true, LAST, false, false, true, FOLD>(a, 0, S, n, blockIdx.x, gridDim.x, unused);
 }
 
 // All three material queues of one bounce in ONE launch (scenes with mirror / glass). The mirror and
@@ -1986,7 +2003,7 @@ template <bool LAST> __global__ void __launch_bounds__(kThreads, 3) bounce_flat_
 // Here the grid's CTAs are split between the queues in proportion to their estimated work, so the
 // specular vertices fill issue slots beside the diffuse ones and a pass is 13 launches, not 34.
 // The per-material queues and kernels' code are unchanged: a CTA runs exactly one KIND.
-template <bool FIRST>
+template <bool FIRST, bool FOLD = false>
 __global__ void __launch_bounds__(kThreads, 3) bounce_flat_all_kernel(const PassArgs a, const int bounce) {
     pdl_launch_dependents();
     const SceneAccess<true> S = stage_scene<true>(a);
@@ -2004,9 +2021,9 @@ __global__ void __launch_bounds__(kThreads, 3) bounce_flat_all_kernel(const Pass
     const uint32_t g1 = n1 ? min(G - g2 - g3, (n1 + kThreads - 1) / kThreads) : 0u;
     __shared__ RecStage<!FIRST> stage;
     const uint32_t b = blockIdx.x;
-    if (b < g1) bounce_flat_body<Q_DIFFUSE, FIRST, false, true>(a, bounce, S, n1, b, g1, stage);
-    else if (b < g1 + g2) bounce_flat_body<Q_MIRROR, FIRST, false, true>(a, bounce, S, n2, b - g1, g2, stage);
-    else if (b < g1 + g2 + g3) bounce_flat_body<Q_GLASS, FIRST, false, true>(a, bounce, S, n3, b - g1 - g2, g3, stage);
+    if (b < g1) bounce_flat_body<Q_DIFFUSE, FIRST, false, true, false, false, FOLD>(a, bounce, S, n1, b, g1, stage);
+    else if (b < g1 + g2) bounce_flat_body<Q_MIRROR, FIRST, false, true, false, false, FOLD>(a, bounce, S, n2, b - g1, g2, stage);
+    else if (b < g1 + g2 + g3) bounce_flat_body<Q_GLASS, FIRST, false, true, false, false, FOLD>(a, bounce, S, n3, b - g1 - g2, g3, stage);
 }
 
 // ---- bounce, tree scenes: shade and queue the rays -----------------------------------------
@@ -2478,8 +2495,10 @@ static void launch_bounce_k(const PassArgs& a, int bounce, size_t smem, int sm_c
     if constexpr (ALL) {
         if constexpr (KIND == Q_DIFFUSE) {
             if (a.bounce_occ == 4) kernel = (a.kind_mask & 6u) ? bounce_flat_kernel<KIND, FIRST, LAST, true, 4> : bounce_flat_kernel<KIND, FIRST, LAST, false, 4>;
+            else if (!LAST && a.fold_last) kernel = (a.kind_mask & 6u) ? bounce_flat_kernel<KIND, FIRST, LAST, true, 3, true> : bounce_flat_kernel<KIND, FIRST, LAST, false, 3, true>;
             else kernel = (a.kind_mask & 6u) ? bounce_flat_kernel<KIND, FIRST, LAST, true> : bounce_flat_kernel<KIND, FIRST, LAST, false>;
         }
+        else if (!LAST && a.fold_last) kernel = bounce_flat_kernel<KIND, FIRST, LAST, true, 3, true>;
         else kernel = bounce_flat_kernel<KIND, FIRST, LAST, true>;
     } else {
         kernel = bounce_kernel<KIND, FIRST, LAST>;
@@ -2545,7 +2564,8 @@ bool path_scene_is_flat(const PassArgs& a) { return all_staged(a); }
 bool launch_bounce_first_fused(const PassArgs& a, int sm_count, cudaStream_t s) {
     if (!all_staged(a) || (a.kind_mask & 6u) || a.bounce_occ == 4) return false;
     const size_t smem = path_smem_bytes(a);
-    void (*kernel)(PassArgs) = a.max_depth <= 1 ? bounce_flat_fused_kernel<true> : bounce_flat_fused_kernel<false>;
+    void (*kernel)(PassArgs) = a.max_depth <= 1 ? bounce_flat_fused_kernel<true>
+                               : (a.fold_last ? bounce_flat_fused_kernel<false, true> : bounce_flat_fused_kernel<false>);
     const int grid = persistent_grid(kernel, smem, sm_count);
     cudaError_t e = launch_pdl(kernel, grid, smem, s, a);
     if (e != cudaSuccess) note_launch_error("fused first bounce kernel launch", e, smem, grid);
@@ -2557,7 +2577,8 @@ bool launch_bounce_merged(const PassArgs& a, int bounce, int sm_count, cudaStrea
     const bool first = bounce == 0, last = bounce + 1 >= a.max_depth;
     if (!all_staged(a) || last || !(a.kind_mask & 6u)) return false;
     const size_t smem = path_smem_bytes(a);
-    void (*kernel)(PassArgs, int) = first ? bounce_flat_all_kernel<true> : bounce_flat_all_kernel<false>;
+    void (*kernel)(PassArgs, int) = a.fold_last ? (first ? bounce_flat_all_kernel<true, true> : bounce_flat_all_kernel<false, true>)
+                                                : (first ? bounce_flat_all_kernel<true> : bounce_flat_all_kernel<false>);
     const int grid = persistent_grid(kernel, smem, sm_count);
     cudaError_t e = launch_pdl(kernel, grid, smem, s, a, bounce);
     if (e != cudaSuccess) note_launch_error("merged bounce kernel launch", e, smem, grid);

@@ -374,15 +374,18 @@ def test_bvh_deep_stack_on_a_pile_of_overlapping_triangles(g19, abi, oracle):
 
 
 def test_fused_first_bounce_is_bit_identical(g19, abi):
-    """Diffuse-only flat scenes trace the camera segment inside the first bounce's launch (tune fuse_first, default on):
-    no raygen kernel, no camera vertex records. Same arithmetic per path, so the frame must not change by a bit -- at
-    depth 1 (the fused launch is also the last), at depth 5, with ragged tiles and several passes."""
+    """Diffuse-only flat scenes trace the camera segment inside the first bounce's launch (tune fuse_first, default on:
+    no raygen kernel, no camera vertex records) and shade a path's last vertex in the launch that finds it (tune
+    fold_last, default on: no launch for the last bounce). Same arithmetic per path in the same order, so the frame must
+    not change by a bit -- at depth 1 (the fused launch is also the last), depth 2 (fused AND folding), depth 5, with
+    ragged tiles and several passes."""
     w, h = 150, 97
     sc, cam, light = g19.Octree.builtin(abi.SCENE_CORNELL, w=w, h=h)
-    for depth, spp, spp_pass in ((1, 3, 0), (5, 6, 0), (5, 6, 2)):
+    for depth, spp, spp_pass in ((1, 3, 0), (2, 4, 0), (3, 4, 0), (5, 6, 0), (5, 6, 2)):
         outs = []
         for fuse in (1, 0):
             rt = g19.RayTracer(cam, light)
+            rt.tune("fold_last", fuse)
             rt.tune("fuse_first", fuse)
             rt.setScene(sc)
             rt.start()
@@ -391,4 +394,24 @@ def test_fused_first_bounce_is_bit_identical(g19, abi):
             outs.append((rad, int(st.extend_segments), int(st.shadow_segments), int(st.kernel_launches)))
         assert outs[0][0].tobytes() == outs[1][0].tobytes() and outs[0][0].max() > 0
         assert outs[0][1:3] == outs[1][1:3]
-        assert outs[0][3] < outs[1][3]  # one launch per pass fewer
+        assert outs[0][3] < outs[1][3]  # fewer launches per pass
+    # scenes with mirror / glass fold the last vertex too (merged per-bounce launch and one launch per material queue)
+    sg, camg, lightg = g19.Octree.builtin(abi.SCENE_CORNELL_GLASS, w=w, h=h)
+    for depth, no_merge in ((2, None), (8, None), (8, 1)):
+        frames = []
+        for fold in (1, 0):
+            rt = g19.RayTracer(camg, lightg)
+            rt.tune("fold_last", fold)
+            rt.tune("no_merge", no_merge)
+            rt.setScene(sg)
+            rt.start()
+            frames.append(rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=5, max_depth=depth, seed=3)["radiance"])
+        assert frames[0].tobytes() == frames[1].tobytes() and frames[0].max() > 0, (depth, no_merge)
+    # each of the two on its own
+    for key in ("fuse_first", "fold_last"):
+        rt = g19.RayTracer(cam, light)
+        rt.tune(key, 0)
+        rt.setScene(sc)
+        rt.start()
+        rad = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=6, max_depth=5, seed=8, spp_per_pass=2)["radiance"]
+        assert rad.tobytes() == outs[0][0].tobytes(), key

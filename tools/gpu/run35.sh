@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_path_gpu.py tests/test_full_size_gpu.py tests/test_analytic.py -m gpu -q > gpurun_out/r02zk_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r02zk_tests.log
+tail -6 gpurun_out/r02zk_tests.log | cut -c1-220
+P="timeout 120 python tools/profile_run.py"
+{
+for rep in 1 2; do
+$P --scene CORNELL_GLASS --spp 64 --depth 12 --frames 4
+$P --scene CORNELL_GLASS --spp 64 --depth 12 --frames 4 --tune fold_last=0
+done
+$P --scene CORNELL --spp 64 --frames 5
+} > gpurun_out/r02zk_timings.log 2>&1
+cat gpurun_out/r02zk_timings.log | cut -c1-150
