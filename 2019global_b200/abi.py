@@ -73,7 +73,7 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("class_ms", C.c_double * 8),
                 ("class_launches", C.c_uint64 * 8), ("node_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("shade_calls", C.c_uint64), ("shade_calls_first", C.c_uint64), ("lit_samples", C.c_uint64),
-                ("radiance_reads", C.c_uint64), ("radiance_stores", C.c_uint64)]
+                ("radiance_reads", C.c_uint64), ("radiance_stores", C.c_uint64), ("shade_calls_folded", C.c_uint64)]
 
 
 def d3(v):

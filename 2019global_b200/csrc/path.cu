@@ -1247,6 +1247,7 @@ int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
     stats.radiance_stores = h[6];
     stats.node_tests = h[7]; // tree scenes under params.profile: octree node records visited / primitive tests (TreeWalk2<COUNT>)
     stats.prim_tests = h[8];
+    stats.shade_calls_folded = h[9];
     for (int i = 0; i + 1 < w.used_events; i += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, w.events[i], w.events[i + 1]) == cudaSuccess) stats.class_ms[w.event_class[i / 2]] += ms;

@@ -1795,7 +1795,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
     if (!LAST && !FOLD) out.init(a, bounce + 1);
     // statistics (g19_stats), two 16-bit counters per register (a thread runs < 2^16 iterations: the grid
     // has > 10^5 threads and a queue < 2^32 entries): calls | traced << 16, shadow rays | lit << 16
-    uint32_t cnt_a = 0, cnt_b = 0, stored = 0;
+    uint32_t cnt_a = 0, cnt_b = 0, stored = 0, folded = 0;
     const uint32_t stride = n_cta * kThreads;
     const uint32_t lane = threadIdx.x & 31u;
     const int tid = threadIdx.x;
@@ -1923,6 +1923,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
             if (FOLD && kind_next == G19_BSDF_DIFFUSE) { // the path's last vertex, shaded in place (next_last holds for this launch)
                 const Shaded s2 = shade_vertex<Q_DIFFUSE, true, true>(a, S, bounce + 1, p_next, d_next, T, prim_next, pixel, sample);
                 cnt_a += 1u;
+                ++folded;
                 if (s2.want_shadow) {
                     bool unused;
                     float t2;
@@ -1968,6 +1969,10 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
         if (shadow_rays) atomicAdd(a.totals + 1, (unsigned long long)shadow_rays);
         if (lit) atomicAdd(a.totals + 4, (unsigned long long)lit);
         if (stored) atomicAdd(a.totals + 6, (unsigned long long)stored);
+    }
+    if (FOLD) {
+        folded = warp_sum(folded);
+        if (lane == 0 && folded) atomicAdd(a.totals + 9, (unsigned long long)folded);
     }
 }
 

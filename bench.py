@@ -398,7 +398,7 @@ def main():
     def class_profile(job, steps):
         """Per-kernel-class CUDA-event times and counters (event brackets on, one pass in flight)."""
         cls_ms = [0.0] * 8
-        agg = {"extend": 0, "shadow": 0, "shade": 0, "shade_first": 0, "lit": 0, "rad_stores": 0, "samples": 0,
+        agg = {"extend": 0, "shadow": 0, "shade": 0, "shade_first": 0, "shade_folded": 0, "lit": 0, "rad_stores": 0, "samples": 0,
                "node_tests": 0, "prim_tests": 0, "launch": [0] * 8}
         for _ in range(steps):
             job.step(profile=1)
@@ -411,6 +411,7 @@ def main():
             agg["shadow"] += s.shadow_segments
             agg["shade"] += s.shade_calls
             agg["shade_first"] += s.shade_calls_first
+            agg["shade_folded"] += s.shade_calls_folded
             agg["lit"] += s.lit_samples
             agg["rad_stores"] += s.radiance_stores
             agg["samples"] += s.samples
@@ -429,10 +430,11 @@ def main():
             # diffuse-only scenes trace the camera segment inside the first bounce's launch (no raygen kernel): the 48-byte
             # camera records are neither written nor read
             cam_rec = 0 if agg["launch"][abi.K_EXTEND] == 0 else 48 * C0
+            CR = C - C0 - agg["shade_folded"]  # vertices that travel as records (a path's last vertex is shaded where it is found)
             bytes_cls = {
                 "raygen_extend": cam_rec,                       # record written per shaded camera hit
-                "bounce": (cam_rec + 64 * (C - C0)              # record read per shaded vertex
-                           + 64 * (C - C0)                      # record written per continuation hit (= vertices shaded later)
+                "bounce": (cam_rec + 64 * CR                    # record read per shaded vertex
+                           + 64 * CR                            # record written per continuation hit (= vertices shaded later)
                            + 16 * ST),                          # radiance delivered once per path that ends in this kernel
                 "accumulate": 16 * S0 + 24 * npix_local * max(1, agg["launch"][abi.K_ACCUM]),
             }
@@ -491,10 +493,10 @@ def main():
         if flat:
             roof["binding_resource"] = "issue slots (ncu: smsp__issue_active %s%% of peak) -- see DESIGN.md section 5" % issue_pct
             if agg["launch"][abi.K_EXTEND] == 0:
-                roof["note_fused"] = ("the camera segment is traced inside the first bounce's launch: its 48-byte vertex records are no "
-                                      "longer written and read back, so the algorithmic bytes per frame fell by a fifth while the frame "
-                                      "got 4 % faster -- the HBM fraction of this issue-bound kernel fell with them (0.57 -> 0.47), the "
-                                      "issue fraction did not")
+                roof["note_fused"] = ("the camera segment is traced inside the first bounce's launch and a path's last vertex is shaded "
+                                      "by the launch that finds it: their vertex records are no longer written and read back, so the "
+                                      "algorithmic bytes per frame fell by 40 % while the frame got 11 % faster -- the HBM fraction of "
+                                      "this issue-bound kernel fell with them (0.57 -> ~0.4), the issue fraction did not")
         if not flat and agg["node_tests"] > 0:
             # T_issue = (N_node*20 + N_tri*50 + S*150) thread instructions / (SMs * 128 lanes * f_sm);
             # N_node / N_tri counted by the walk itself (params.profile builds of the tree kernels), S = all segments

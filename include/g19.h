@@ -201,6 +201,8 @@ typedef struct g19_stats {
                                  (their light sample reads the slot's radiance so far)        */
     uint64_t radiance_stores; /* PATH, flat scenes: paths that ended in a bounce kernel (one
                                  16-byte radiance store each; bench.py's byte model)          */
+    uint64_t shade_calls_folded; /* PATH, flat scenes: last vertices shaded by the launch that found
+                                 them (counted in shade_calls; no vertex record written or read) */
 } g19_stats;
 
 enum { G19_K_EXTEND = 0, G19_K_SHADE = 1, G19_K_SHADOW = 2, G19_K_ACCUM = 3,
