@@ -629,15 +629,31 @@ int g19_upload_scene(g19_ctx* ctx, const g19_scene* scene) {
     if (!ctx || !scene) return G19_ERR_INVALID;
     G19_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->has_scene = false;
+    // The two views are independent (REF: the reference's octree and FP64 records; PATH: primitives, octree, BVH): a large
+    // scene flattens the REF view on a second host thread while this one builds the PATH view (1 M triangles: 0.22 s and
+    // 0.32 s, 0.54 s one after the other).
     const auto t0 = std::chrono::steady_clock::now();
-    int rc = flatten_ref(ctx, *scene);
-    if (rc != G19_OK) return rc;
+    const bool two_threads = scene->ents.size() >= (size_t(1) << 15);
+    int rc_ref = G19_OK;
+    double ms_ref = 0;
+    std::thread ref_thread;
+    auto do_ref = [&] {
+        cudaSetDevice(ctx->device);
+        rc_ref = flatten_ref(ctx, *scene);
+        ms_ref = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    if (two_threads) ref_thread = std::thread(do_ref);
+    else do_ref();
+    if (!two_threads && rc_ref != G19_OK) return rc_ref;
     const auto t1 = std::chrono::steady_clock::now();
     std::string perr;
-    rc = path_upload(ctx->path, *scene, ctx->tune, ctx->stream, perr);
+    int rc = path_upload(ctx->path, *scene, ctx->tune, ctx->stream, perr);
+    const double ms_path = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    if (two_threads) ref_thread.join();
     if (ctx->tune.debug_tree)
-        std::fprintf(stderr, "[g19] upload: REF view %.1f ms, PATH view %.1f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+        std::fprintf(stderr, "[g19] upload: REF view %.1f ms, PATH view %.1f ms%s, together %.1f ms\n", ms_ref, ms_path,
+                     two_threads ? " (side by side)" : "", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    if (rc_ref != G19_OK) return rc_ref;
     if (rc != G19_OK) {
         ctx->err = perr;
         return rc;
