@@ -174,7 +174,7 @@ static inline float cell_edge(float root_lo, float root_size, int level, uint32_
 
 void path_tuning_from_env(PathTuning& t) {
     static const char* const keys[] = {"lanes", "pass_slots", "no_merge", "leaf_max", "refill", "coop_leaf", "walk_steps",
-                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec", "bvh_stack", "fuse_first", "fold_last"};
+                                       "leaf_batch", "raygen_occ", "tree_build", "debug_tree", "walk", "trace_occ", "l2_persist", "bounce_occ", "top_level", "ref_heavy", "sort_rays", "upload_threads", "bvh_leaf", "bvh_spec", "bvh_stack", "fuse_first", "fold_last", "overlap_frames"};
     for (const char* k : keys) {
         std::string env = "G19_";
         for (const char* c = k; *c; ++c) env += char(std::toupper(*c));
@@ -201,6 +201,7 @@ bool path_tuning_set(PathTuning& t, const char* key, const char* value) {
     else if (k == "trace_occ") t.trace_occ = num(def.trace_occ, 3, 4);
     else if (k == "bounce_occ") t.bounce_occ = num(def.bounce_occ, 3, 4);
     else if (k == "top_level") t.top_level = num(def.top_level, 0, 8);
+    else if (k == "overlap_frames") t.overlap_frames = num(def.overlap_frames, 0, 1);
     else if (k == "fold_last") t.fold_last = num(def.fold_last, 0, 1);
     else if (k == "fuse_first") t.fuse_first = num(def.fuse_first, 0, 1);
     else if (k == "bvh_stack") t.bvh_stack = num(def.bvh_stack, 4, 64);
@@ -792,6 +793,11 @@ void path_release(PathSceneBuffers& b, PathWork& w) {
     }
     if (w.ev_fork) cudaEventDestroy(w.ev_fork);
     w.ev_fork = nullptr;
+    for (cudaEvent_t& e : w.ev_start) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
+    w.overlap_key = 0;
     if (w.events) {
         for (int i = 0; i < w.n_events; ++i) cudaEventDestroy(w.events[i]);
         delete[] w.events;
@@ -935,17 +941,32 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     const int n_lanes = (p.profile || a.on_pass) ? 1 : int(std::min<size_t>(size_t(a.tune.lanes), n_passes)); // profiling and progressive refresh: one at a time
     if (n_lanes > 1 && !w.ev_fork) PATH_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < n_lanes; ++i) {
-        if (i > 0 && !w.side[i]) PATH_CUDA(cudaStreamCreateWithFlags(&w.side[i], cudaStreamNonBlocking));
+        if ((i > 0 || n_lanes > 1) && !w.side[i]) PATH_CUDA(cudaStreamCreateWithFlags(&w.side[i], cudaStreamNonBlocking));
         if (n_lanes > 1 && !w.ev_acc[i]) {
             PATH_CUDA(cudaEventCreateWithFlags(&w.ev_acc[i], cudaEventDisableTiming));
             PATH_CUDA(cudaEventCreateWithFlags(&w.ev_join[i], cudaEventDisableTiming));
         }
     }
-    PATH_CUDA(w.totals.ensure(10 * sizeof(unsigned long long)));
+    // Frames in a row with the same buffers may overlap on the side lanes (PathWork::ev_start): anything allocated,
+    // resized or reset in this call, profiling, progressive refresh or a single lane switch it off for this frame.
+    const size_t bytes_before = w.totals.bytes + w.accum.bytes + w.rad_l.bytes + w.rgb_l.bytes + w.iota.bytes + w.ray_hint_d.bytes;
+    size_t lane_bytes_before = 0;
+    for (const PathLane& l : w.lane) lane_bytes_before += l.capacity + l.L.bytes + l.recs.bytes + l.rays.bytes + l.queues.bytes + l.counts.bytes + l.rkeys.bytes;
+    const unsigned long long this_key = ((b.upload_serial + 1) << 44) ^ (static_cast<unsigned long long>(P) << 12) ^
+                                        (static_cast<unsigned long long>(n_lanes) << 8) ^ static_cast<unsigned long long>(p.max_depth) ^
+                                        (static_cast<unsigned long long>(npix) << 20) ^ reinterpret_cast<unsigned long long>(s);
+    PATH_CUDA(w.totals.ensure(2 * 10 * sizeof(unsigned long long)));
     PATH_CUDA(w.accum.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rad_l.ensure(npix * 3 * sizeof(float)));
     PATH_CUDA(w.rgb_l.ensure(npix * 3));
-    PATH_CUDA(cudaMemsetAsync(w.totals.p, 0, 10 * sizeof(unsigned long long), s));
+    for (cudaEvent_t& e : w.ev_start)
+        if (!e) PATH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const bool may_overlap = a.tune.overlap_frames && n_lanes > 1 && w.overlap_key == this_key && !p.profile && !a.on_pass;
+    w.overlap_key = 0; // set again once this frame is enqueued whole
+    const int parity = int(w.frame_serial & 1ull);
+    unsigned long long* const totals2 = static_cast<unsigned long long*>(w.totals.p);
+    if (!may_overlap) PATH_CUDA(cudaMemsetAsync(totals2, 0, 2 * 10 * sizeof(unsigned long long), s));
+    else PATH_CUDA(cudaMemsetAsync(totals2 + 10 * (parity ^ 1), 0, 10 * sizeof(unsigned long long), s)); // the NEXT frame's block
     PATH_CUDA(cudaMemsetAsync(w.accum.p, 0, npix * 3 * sizeof(float), s));
     if (p.profile && !w.events) {
         w.n_events = 65536;
@@ -953,7 +974,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         for (int i = 0; i < w.n_events; ++i) PATH_CUDA(cudaEventCreate(&w.events[i]));
     }
     w.used_events = 0;
-    pa0.totals = static_cast<unsigned long long*>(w.totals.p);
+    pa0.totals = totals2 + 10 * parity;
+    w.totals_parity = parity;
     pa0.accum = static_cast<float*>(w.accum.p);
 
     // per-lane buffers
@@ -963,22 +985,26 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
         lanes[i] = pa0;
         lane_stream[i] = s;
     }
-    for (int i = 1; i < n_lanes; ++i) lane_stream[i] = w.side[i];
+    // Several lanes: with overlap_frames ALL of them run on streams of their own (the caller's stream only zeroes, joins and
+    // resolves), so that the next frame's passes can follow this frame's on every lane; otherwise lane 0 is the caller's stream.
+    const int first_side = (n_lanes > 1 && a.tune.overlap_frames) ? 0 : 1;
+    for (int i = first_side; i < n_lanes; ++i) lane_stream[i] = w.side[i];
     for (int li = 0; li < n_lanes; ++li) {
         PathLane& l = w.lane[li];
         PassArgs& pa = lanes[li];
         if (P > l.capacity) {
             PATH_CUDA(l.L.ensure(P * 4 * sizeof(float))); // flat scenes: float4 per slot; tree scenes: three planes
             l.capacity = P;
-            PATH_CUDA(cudaMemsetAsync(l.L.p, 0, P * 4 * sizeof(float), s));
+            PATH_CUDA(cudaMemsetAsync(l.L.p, 0, P * 4 * sizeof(float), lane_stream[li]));
             l.L_written_whole = false;
         }
         // tree scenes ADD to zeroed planes (accumulate clears what it read); flat scenes store every slot
-        if (!fused && l.L_written_whole) PATH_CUDA(cudaMemsetAsync(l.L.p, 0, l.capacity * 4 * sizeof(float), s));
+        // (a lane's own buffers are cleared on the lane's own stream: in order with its passes, whatever the caller's stream is at)
+        if (!fused && l.L_written_whole) PATH_CUDA(cudaMemsetAsync(l.L.p, 0, l.capacity * 4 * sizeof(float), lane_stream[li]));
         l.L_written_whole = fused;
         const size_t plane = l.capacity;
         PATH_CUDA(l.counts.ensure((kMaxPathDepth + 1) * 5 * sizeof(uint32_t)));
-        PATH_CUDA(cudaMemsetAsync(l.counts.p, 0, (kMaxPathDepth + 1) * 5 * sizeof(uint32_t), s));
+        PATH_CUDA(cudaMemsetAsync(l.counts.p, 0, (kMaxPathDepth + 1) * 5 * sizeof(uint32_t), lane_stream[li]));
         pa.L = static_cast<float*>(l.L.p);
         pa.plane = plane;
         pa.queue_cap = plane + kQueueSlack;
@@ -1066,9 +1092,22 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             cudaGetLastError(); // best effort: a refused hint is not an error of the render
         }
     }
-    if (n_lanes > 1) { // the other lanes start after everything enqueued so far on the caller's stream
-        PATH_CUDA(cudaEventRecord(w.ev_fork, s));
-        for (int i = 1; i < n_lanes; ++i) PATH_CUDA(cudaStreamWaitEvent(w.side[i], w.ev_fork, 0));
+    {
+        size_t lane_bytes_after = 0;
+        for (const PathLane& l : w.lane) lane_bytes_after += l.capacity + l.L.bytes + l.recs.bytes + l.rays.bytes + l.queues.bytes + l.counts.bytes + l.rkeys.bytes;
+        const size_t bytes_after = w.totals.bytes + w.accum.bytes + w.rad_l.bytes + w.rgb_l.bytes + w.iota.bytes + w.ray_hint_d.bytes;
+        const bool overlap = may_overlap && lane_bytes_after == lane_bytes_before && bytes_after == bytes_before;
+        PATH_CUDA(cudaEventRecord(w.ev_start[parity], s)); // the memsets above (this frame's accum, the next frame's statistics)
+        if (n_lanes > 1) {
+            if (overlap) {
+                // a frame behind a frame of the same shape: the side lanes go on behind their own passes; all they need from the
+                // caller's stream is last frame's start (their statistics block was zeroed there)
+                for (int i = first_side; i < n_lanes; ++i) PATH_CUDA(cudaStreamWaitEvent(w.side[i], w.ev_start[parity ^ 1], 0));
+            } else { // the other lanes start after everything enqueued so far on the caller's stream
+                PATH_CUDA(cudaEventRecord(w.ev_fork, s));
+                for (int i = first_side; i < n_lanes; ++i) PATH_CUDA(cudaStreamWaitEvent(w.side[i], w.ev_fork, 0));
+            }
+        }
     }
     const bool merge_kinds = !a.tune.no_merge; // tuning knob: one launch per material queue
     ClassClock clk{w, s, p.profile != 0};
@@ -1149,6 +1188,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             }
             // the per-pixel sums are taken in pass order whichever lane a pass ran on
             if (n_lanes > 1 && prev_lane >= 0) PATH_CUDA(cudaStreamWaitEvent(ls, w.ev_acc[prev_lane], 0));
+            else if (n_lanes > 1 && ls != s) PATH_CUDA(cudaStreamWaitEvent(ls, w.ev_start[parity], 0)); // the frame's first: behind the memset of accum
             clk.begin();
             launch_accumulate(pa, ls);
             clk.end(G19_K_ACCUM);
@@ -1177,7 +1217,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             }
         }
     }
-    for (int i = 1; i < n_lanes; ++i) { // join: the caller's stream continues after the other lanes
+    for (int i = first_side; i < n_lanes; ++i) { // join: the caller's stream continues after the other lanes
         PATH_CUDA(cudaEventRecord(w.ev_join[i], w.side[i]));
         PATH_CUDA(cudaStreamWaitEvent(s, w.ev_join[i], 0));
     }
@@ -1226,6 +1266,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
     stats.samples = owned * uint64_t(done_spp);
     w.totals_pending = true;
     w.totals_stream = s;
+    ++w.frame_serial;
+    if (rc == G19_OK) w.overlap_key = this_key; // the next frame of the same shape may start behind this one's passes
     return rc;
 #undef PATH_CUDA
 }
@@ -1233,7 +1275,7 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
 int path_finish_stats(PathWork& w, g19_stats& stats, std::string& err) {
     if (!w.totals_pending) return G19_OK;
     unsigned long long h[10];
-    cudaError_t e = cudaMemcpy(h, w.totals.p, sizeof h, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(h, static_cast<const unsigned long long*>(w.totals.p) + 10 * w.totals_parity, sizeof h, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) {
         err = std::string("path_finish_stats: ") + cudaGetErrorString(e);
         return G19_ERR_CUDA;

@@ -116,6 +116,14 @@ struct PathWork {
     PathLane lane[kMaxLanes];
     cudaStream_t side[kMaxLanes] = {}; // streams of lanes 1.. (lane 0 runs on the caller's; side[0] unused)
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {}, ev_acc[kMaxLanes] = {};
+    // Frames in a row (tune overlap_frames): the side lanes of frame k + 1 need not wait for frame k's join, resolve and
+    // gather -- their passes touch lane-private buffers only; what they share with the caller's stream is the statistics
+    // block (two of them, by frame parity, the next frame's zeroed at this frame's start: ev_start) and `accum` (only the
+    // accumulate launches touch it, and those are chained behind the frame's memset through pass 0 on the caller's stream).
+    cudaEvent_t ev_start[2] = {nullptr, nullptr};
+    unsigned long long frame_serial = 0;
+    unsigned long long overlap_key = 0; // (scene, pass size, lanes, depth ...) of the last frame that completed its enqueue, 0 = none
+    int totals_parity = 0;
     DeviceArray totals;        // uint64[8]: extend segments, shadow segments, ...
     DeviceArray accum;         // float[3][n_local_pix]
     DeviceArray rad_l, rgb_l;  // resolved local-pixel outputs
@@ -156,6 +164,7 @@ struct PathTuning {
                               // latency, a third more warps in flight buys more than the spills cost -- room scene 775 -> 687 ms)
     int bounce_occ = 3;       // CTAs per SM of the diffuse flat-scene bounce kernel (4 = 64 registers, some spills)
     int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
+    int overlap_frames = 1;   // frames rendered back to back: the side lanes start the next frame's passes behind their own, not behind the join
     int fold_last = 1;        // flat scenes: a path's last vertex (next-event estimation only) is shaded by the launch that finds it
     int fuse_first = 1;       // diffuse-only flat scenes: trace the camera segment inside the first bounce's launch (no raygen kernel, no camera records)
     int bvh_stack = kBvhSmemStack; // walk=3/4: levels of the postponed-children stack in shared memory (1 KB per level and CTA)

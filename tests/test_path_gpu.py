@@ -415,3 +415,32 @@ def test_fused_first_bounce_is_bit_identical(g19, abi):
         rt.start()
         rad = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=6, max_depth=5, seed=8, spp_per_pass=2)["radiance"]
         assert rad.tobytes() == outs[0][0].tobytes(), key
+
+
+@pytest.mark.parametrize("which,n,depth", [("CORNELL", 0, 5), ("CORNELL_GLASS", 0, 8), ("HEIGHTFIELD_ROOM", 40, 4)])
+def test_frames_in_a_row_overlap_and_stay_bit_identical(g19, abi, which, n, depth):
+    """Frames enqueued back to back on one stream (tune overlap_frames, default on): the side lanes start frame k + 1's
+    passes behind their own passes of frame k instead of behind frame k's join and resolve. Every frame must still be
+    what a lone, synchronous render of the same seed produces, bit for bit -- statistics included."""
+    import torch
+    w, h, spp = 320, 200, 12
+    sc, cam, light = g19.Octree.builtin(getattr(abi, "SCENE_" + which), n=n, w=w, h=h)
+    seeds = [3, 4, 3, 5, 4, 3, 6, 6]
+    stream = torch.cuda.current_stream().cuda_stream
+    for overlap in (1, 0):
+        rt = g19.RayTracer(cam, light)
+        rt.tune("overlap_frames", overlap)
+        rt.setScene(sc)
+        rt.start()
+        alone = {}
+        for sd in sorted(set(seeds)):
+            alone[sd] = rt.run(w, h, mode=abi.MODE_PATH, want=("radiance",), spp=spp, max_depth=depth, seed=sd, spp_per_pass=2)["radiance"]
+            alone[sd] = (alone[sd], int(rt.stats().extend_segments))
+        bufs = [torch.zeros(h * w * 3, dtype=torch.float32, device="cuda") for _ in seeds]
+        for sd, buf in zip(seeds, bufs):  # nothing synchronises between these
+            rt.run_device(rt.params(w, h, mode=abi.MODE_PATH, spp=spp, max_depth=depth, seed=sd, spp_per_pass=2), d_rad=buf.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        assert int(rt.stats().extend_segments) == alone[seeds[-1]][1]  # the statistics are the last frame's
+        for sd, buf in zip(seeds, bufs):
+            got = buf.cpu().numpy().reshape(h, w, 3)
+            assert got.tobytes() == alone[sd][0].tobytes(), (overlap, sd)
