@@ -112,3 +112,26 @@ def test_no_gpu_fails_loudly(g19):
     with pytest.raises(g19.G19Error) as e:
         g19.RayTracer(g19.Camera((-10, 0, 0)), (0, 0, 0))
     assert e.value.code == g19.abi.ERR_NO_DEVICE and "no CPU path" in str(e.value)
+
+
+def test_stats_and_params_layout_matches_the_header(tmp_path):
+    """The ctypes mirrors of g19_stats / g19_params / g19_camera (2019global_b200/abi.py) against the C header itself:
+    sizes and the offsets of the last fields, as gcc lays them out."""
+    import ctypes
+    import os
+    import subprocess
+    import importlib
+    abi = importlib.import_module("2019global_b200").abi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "g19.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(g19_stats), offsetof(g19_stats, shade_calls_folded), '
+                   'offsetof(g19_stats, class_launches), sizeof(g19_params), sizeof(g19_camera)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(abi.Stats)
+    assert int(out[1]) == abi.Stats.shade_calls_folded.offset
+    assert int(out[2]) == abi.Stats.class_launches.offset
+    assert int(out[3]) == ctypes.sizeof(abi.Params)
+    assert int(out[4]) == ctypes.sizeof(abi.Camera)
