@@ -24,6 +24,9 @@ gather is inside every timed step.
   cpu_baseline   this repo's FP64 path oracle (same work per sample) on all host cores, on a bounded crop of the
            same frame; `literal_reference` = the unmodified reference (oracle/_ref) on the depth-0, 1-spp slice
            it is able to execute
+  config   the WORKLOAD only (same keys and values in both arms + the L2 statement); `engine` = how this arm runs it
+  clocks   nvidia-smi on rank 0's GPU, sampled from the warm-up on; a timed region shorter than 1 s (8 GPUs: 40 ms)
+           is followed by 1 s of the same steps so that the sampler sees the load, and `window` says which samples count
 
 --impl reference times the CPU implementation (see reference_arm()); it never loads the product library.
 """
