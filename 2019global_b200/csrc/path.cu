@@ -1133,7 +1133,8 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
             pa.pix_count = uint32_t(std::min(window, npix - pix0));
             pa.n_slots = uint32_t(size_t(pa.pix_count) * size_t(pa.spp_pass));
             // diffuse-only flat scenes: camera segment and first vertex in one launch
-            const bool fused_first = fused && a.tune.fuse_first && !(pa.kind_mask & 6u) && pa.bounce_occ != 4;
+            const bool fused_first = fused && a.tune.fuse_first && pa.bounce_occ != 4;
+            const bool spec_scene = (pa.kind_mask & 6u) != 0u;
             if (!fused_first) {
                 clk.begin();
                 launch_raygen_extend(pa, a.sm_count, ls); // camera segment
@@ -1148,9 +1149,12 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
                 clk.begin();
                 int n = 0;
                 if (bounce == 0 && fused_first && launch_bounce_first_fused(pa, a.sm_count, ls)) {
-                    clk.end(G19_K_SHADE);
-                    stats.class_launches[G19_K_SHADE] += 1;
-                    continue;
+                    ++n;
+                    if (!spec_scene || p.max_depth <= 1) { // (with mirror / glass the camera hits on those still have their launch below)
+                        clk.end(G19_K_SHADE);
+                        stats.class_launches[G19_K_SHADE] += n;
+                        continue;
+                    }
                 }
                 // the first bounce's rays leave the camera rays' hit points in pixel order: coherent as they are
                 // ... and a queue that stayed short the last time is walked in a blink: not worth three more launches.
@@ -1167,10 +1171,11 @@ int path_render(PathSceneBuffers& b, PathWork& w, const PathRenderArgs& a, g19_s
                 if (!sort_this) pb.rkey = nullptr, pb.perm = nullptr;
                 if (sort_this) PATH_CUDA(cudaMemsetAsync(pa.rkey, 0xff, n_sort * sizeof(uint16_t), ls));
                 if (merge_kinds && launch_bounce_merged(pa, bounce, a.sm_count, ls)) {
-                    n = 1;
+                    n += 1;
                 } else {
                     for (int kind = Q_DIFFUSE; kind <= Q_GLASS; ++kind) {
                         if (!b.has_bsdf[kind - 1]) continue; // no such material in the scene: queue is always empty
+                        if (bounce == 0 && fused_first && kind == Q_DIFFUSE) continue; // shaded by the fused launch above
                         if (launch_bounce(pb, bounce, kind, a.sm_count, ls)) ++n;
                     }
                 }

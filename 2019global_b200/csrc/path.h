@@ -166,7 +166,7 @@ struct PathTuning {
     int top_level = 7;        // levels covered by the walk's direct-index table (0 = none; capped at tree depth - 2): 16 MB at 7; ROOM 668 / 630 / 611 ms at 0 / 6 / 7
     int overlap_frames = 1;   // frames rendered back to back: the side lanes start the next frame's passes behind their own, not behind the join
     int fold_last = 1;        // flat scenes: a path's last vertex (next-event estimation only) is shaded by the launch that finds it
-    int fuse_first = 1;       // diffuse-only flat scenes: trace the camera segment inside the first bounce's launch (no raygen kernel, no camera records)
+    int fuse_first = 1;       // flat scenes: trace the camera segment inside the first bounce's launch (no raygen kernel; camera records only for hits on mirror / glass)
     int bvh_stack = kBvhSmemStack; // walk=3/4: levels of the postponed-children stack in shared memory (1 KB per level and CTA)
     int bvh_spec = 1;         // walk=3: a lane that reaches a leaf postpones it and keeps descending
     int bvh_leaf = 4;         // walk=3: primitives per BVH leaf at most (1..8; read at scene upload)

@@ -1780,7 +1780,7 @@ __device__ __forceinline__ void prefetch_rec(const RecView& r, uint32_t pos, boo
 // One launch per material queue and bounce: next-event estimation, BSDF sample, the trace of BOTH
 // rays in one loop over the staged primitives, and the new vertex record written straight into
 // the next bounce's material queue.
-// FUSED (diffuse-only flat scenes, first bounce): the camera segment is traced right here instead of by
+// FUSED (flat scenes, first bounce): the camera segment is traced right here instead of by
 // raygen_extend_flat_kernel -- the vertex record of the camera hit (48 B written, 48 B read back, a fifth of the frame's
 // HBM traffic), its queue reservation and a launch per pass disappear; `n` is then the number of path slots of the pass.
 // FOLD (flat scenes, the bounce before the last): the vertex the continuation ray finds would be the path's
@@ -1823,6 +1823,7 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
             }
             float t = 0.0f;
             uint32_t pr = kInvalid;
+            int spec_kind = -1; // SPEC: the camera ray met a mirror / glass surface: that vertex goes to its material's queue
             float4 seen = make_float4(0.f, 0.f, 0.f, 0.f); // what a path that ends on the camera segment delivers
             if (nearest<true>(S, live, o, d, t, pr)) {
                 const float4 tag = S.hot_row(pr, 3);
@@ -1834,9 +1835,32 @@ __device__ __forceinline__ void bounce_flat_body(const PassArgs& a, const int bo
                     slot = q;
                     prim = pr;
                     p = o + d * t;
+                } else if (SPEC && a.max_depth > 1) {
+                    spec_kind = bsdf;
                 }
             }
-            if (q < n && slot == kInvalid) reinterpret_cast<float4*>(a.L)[q] = seen; // miss, emitter, or a slot outside the frame
+            if (q < n && slot == kInvalid && spec_kind < 0) reinterpret_cast<float4*>(a.L)[q] = seen; // miss, emitter, or a slot outside the frame
+            if (SPEC) {
+                // The few camera hits on mirror / glass (the two spheres of the glass Cornell box: a tenth of the pixels) keep
+                // the material queues: their 48-byte camera records go to bounce 0's queue of their kind, reserved with one
+                // atomic per warp and kind -- no cursor state carried through the loop -- for the launch that follows this one.
+#pragma unroll
+                for (int k = G19_BSDF_MIRROR; k <= G19_BSDF_GLASS; ++k) {
+                    const uint32_t m = __ballot_sync(kFull, spec_kind == k);
+                    if (m == 0u) continue;
+                    uint32_t base = 0;
+                    if (lane == uint32_t(__ffs(int(m)) - 1)) base = atomicAdd(a.counts + Q_DIFFUSE + k, uint32_t(__popc(m)));
+                    base = __shfl_sync(kFull, base, __ffs(int(m)) - 1);
+                    if (spec_kind == k) {
+                        const RecView r = rec_queue(a, k); // bounce 0, parity 0
+                        const ptrdiff_t at = r.at(base + uint32_t(__popc(m & ((1u << lane) - 1u))));
+                        const float3 ph = o + d * t;
+                        r.ls[at] = make_float4(__uint_as_float(sample), 0.f, 0.f, __uint_as_float(q));
+                        r.hp[at] = make_float4(ph.x, ph.y, ph.z, __uint_as_float(pr));
+                        r.dw[at] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+                    }
+                }
+            }
         } else {
             const uint32_t qn = q + stride;
             prefetch_rec(in, qn, qn < n && qn > q, stage, buf ^ 1); // next record, in flight during this body
@@ -1991,14 +2015,14 @@ __global__ void __launch_bounds__(kThreads, KIND != Q_DIFFUSE ? 4 : OCC) bounce_
 
 // Diffuse-only flat scenes: camera segment + first vertex in one launch (bounce_flat_body<FUSED>), over the path slots of
 // the pass instead of a queue.
-template <bool LAST, bool FOLD = false> __global__ void __launch_bounds__(kThreads, 3) bounce_flat_fused_kernel(const PassArgs a) {
+template <bool LAST, bool FOLD = false, bool SPEC = false> __global__ void __launch_bounds__(kThreads, 3) bounce_flat_fused_kernel(const PassArgs a) {
     pdl_launch_dependents();
     const uint32_t n = a.n_slots;
     if (blockIdx.x * kThreads >= n) return;
     const SceneAccess<true> S = stage_scene<true>(a);
     pdl_wait(); // the previous pass's accumulate cleared the queue lengths
     RecStage<false>& unused = *reinterpret_cast<RecStage<false>*>(g19_dyn_smem); // (the fused body prefetches no records)
-    bounce_flat_body<Q_DIFFUSE, true, LAST, false, false, true, FOLD>(a, 0, S, n, blockIdx.x, gridDim.x, unused);
+    bounce_flat_body<Q_DIFFUSE, true, LAST, SPEC, false, true, FOLD>(a, 0, S, n, blockIdx.x, gridDim.x, unused);
 }
 
 // All three material queues of one bounce in ONE launch (scenes with mirror / glass). The mirror and
@@ -2567,10 +2591,14 @@ bool path_scene_is_flat(const PassArgs& a) { return all_staged(a); }
 
 // Diffuse-only flat scenes: raygen + first bounce in one launch; false = not applicable (the caller launches the two).
 bool launch_bounce_first_fused(const PassArgs& a, int sm_count, cudaStream_t s) {
-    if (!all_staged(a) || (a.kind_mask & 6u) || a.bounce_occ == 4) return false;
+    if (!all_staged(a) || a.bounce_occ == 4) return false;
     const size_t smem = path_smem_bytes(a);
-    void (*kernel)(PassArgs) = a.max_depth <= 1 ? bounce_flat_fused_kernel<true>
-                               : (a.fold_last ? bounce_flat_fused_kernel<false, true> : bounce_flat_fused_kernel<false>);
+    void (*kernel)(PassArgs);
+    if (a.kind_mask & 6u) // mirror / glass in the scene: diffuse camera hits shaded in place, specular ones queued
+        kernel = a.max_depth <= 1 ? bounce_flat_fused_kernel<true, false, true>
+                                  : (a.fold_last ? bounce_flat_fused_kernel<false, true, true> : bounce_flat_fused_kernel<false, false, true>);
+    else
+        kernel = a.max_depth <= 1 ? bounce_flat_fused_kernel<true> : (a.fold_last ? bounce_flat_fused_kernel<false, true> : bounce_flat_fused_kernel<false>);
     const int grid = persistent_grid(kernel, smem, sm_count);
     cudaError_t e = launch_pdl(kernel, grid, smem, s, a);
     if (e != cudaSuccess) note_launch_error("fused first bounce kernel launch", e, smem, grid);

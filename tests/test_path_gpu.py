@@ -397,11 +397,12 @@ def test_fused_first_bounce_is_bit_identical(g19, abi):
         assert outs[0][3] < outs[1][3]  # fewer launches per pass
     # scenes with mirror / glass fold the last vertex too (merged per-bounce launch and one launch per material queue)
     sg, camg, lightg = g19.Octree.builtin(abi.SCENE_CORNELL_GLASS, w=w, h=h)
-    for depth, no_merge in ((2, None), (8, None), (8, 1)):
+    for depth, no_merge in ((1, None), (2, None), (8, None), (8, 1)):
         frames = []
         for fold in (1, 0):
             rt = g19.RayTracer(camg, lightg)
             rt.tune("fold_last", fold)
+            rt.tune("fuse_first", fold)  # (with mirror / glass: diffuse camera hits shaded in place, specular ones queued)
             rt.tune("no_merge", no_merge)
             rt.setScene(sg)
             rt.start()
